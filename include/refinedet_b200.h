@@ -1,0 +1,178 @@
+/*
+ * refinedet_b200.h — C ABI of librefinedet_b200.so
+ *
+ * B200 (sm_100a) implementation of the RefineDet detection post-processing and
+ * anchor-matching hot path.  This library replaces the reference's native
+ * extension (utils/nms/gpu_nms.hpp:1-2, utils/nms/nms_kernel.cu, utils/build.py)
+ * and backs the Python drop-ins for layers/box_utils.py,
+ * layers/functions/detection_refinedet.py and
+ * layers/modules/refinedet_multibox_loss.py (paths relative to the reference
+ * checkout).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends
+ *     in `_host`; all float tensors are contiguous fp32.
+ *   - `stream` is a `cudaStream_t` passed as `void*`; calls are asynchronous on
+ *     it.  The library never allocates device memory, never synchronises and
+ *     never changes the current device (the one exception is `rd_nms_host`,
+ *     which mirrors the reference's synchronous host-pointer ABI).
+ *   - every function returns 0 on success, a positive `cudaError_t` value on a
+ *     CUDA failure, or a negative `RD_ERR_*` code on an argument error.
+ *     `rd_error_string` turns either into text.
+ *   - workspaces are caller-owned and reusable; `rd_*_workspace_bytes` gives the
+ *     size.  A detect workspace must be zero-filled ONCE before first use
+ *     (`rd_detect_workspace_reset`); every call leaves it ready for the next.
+ */
+#ifndef REFINEDET_B200_H_
+#define REFINEDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RD_ABI_VERSION 1
+
+/* only the C ABI below is exported from the shared library */
+#if defined(__GNUC__)
+#define RD_API __attribute__((visibility("default")))
+#else
+#define RD_API
+#endif
+
+/* argument errors (negative so they never collide with cudaError_t) */
+#define RD_ERR_BAD_ARG      (-1)   /* null pointer / non-positive size */
+#define RD_ERR_ALIGNMENT    (-2)   /* a float4-accessed tensor is not 16-byte aligned */
+#define RD_ERR_UNSUPPORTED  (-3)   /* size beyond what the kernels support (see RD_MAX_*) */
+#define RD_ERR_WORKSPACE    (-4)   /* workspace too small */
+
+/* largest number of boxes one NMS problem may keep in flight (top_k, or n for the
+ * standalone calls after top_k truncation) */
+#define RD_MAX_NMS_BOXES 4096
+/* largest number of ground-truth boxes per image in rd_refine_match */
+#define RD_MAX_GT 1024
+
+/* NMS flavour flags */
+#define RD_NMS_NORMALISED   0  /* layers/box_utils.py:241-285: area=(x2-x1)*(y2-y1),
+                                  IoU = inter/((area_j-inter)+area_i), keep IoU <= thr */
+#define RD_NMS_PIXEL_PLUS1  1  /* utils/nms/py_cpu_nms.py:18-36 == nms_kernel.cu:24-32:
+                                  +1 widths, IoU = inter/(S_i+S_j-inter), keep IoU <= thr */
+#define RD_NMS_SUPPRESS_EQ  2  /* OR-able: suppress on IoU >= thr (utils/nms/cpu_nms.pyx:65) */
+/* output row layout of the fused detect stage */
+#define RD_ROW_BOX_SCORE    0  /* x1,y1,x2,y2,score  (eval_refinedet_coco.py:226) */
+#define RD_ROW_SCORE_BOX    1  /* score,x1,y1,x2,y2  (detection_refinedet.py:106-108) */
+
+RD_API int         rd_abi_version(void);
+RD_API const char* rd_error_string(int code);
+/* number of kernels this library has launched in this process (bench accounting) */
+RD_API unsigned long long rd_launch_count(void);
+
+/* ---- layers/box_utils.py element-wise functions --------------------------- */
+/* point_form (box_utils.py:5-14): [n,4] (cx,cy,w,h) -> (x1,y1,x2,y2) */
+RD_API int rd_point_form(const float* boxes, float* out, int n, void* stream);
+/* center_size (box_utils.py:17-26): [n,4] (x1,y1,x2,y2) -> (cx,cy,w,h) */
+RD_API int rd_center_size(const float* boxes, float* out, int n, void* stream);
+/* decode (box_utils.py:187-205): loc[n,4], priors[n,4] (cx,cy,w,h) -> [n,4] point form */
+RD_API int rd_decode(const float* loc, const float* priors, float v0, float v1,
+              float* out, int n, void* stream);
+/* encode (box_utils.py:162-183): matched[n,4] point form, priors[n,4] -> [n,4] */
+RD_API int rd_encode(const float* matched, const float* priors, float v0, float v1,
+              float* out, int n, void* stream);
+/* intersect / jaccard (box_utils.py:29-68): box_a[A,4] x box_b[Bn,4] -> out[A,Bn] */
+RD_API int rd_intersect(const float* box_a, const float* box_b, float* out, int A, int Bn, void* stream);
+RD_API int rd_jaccard(const float* box_a, const float* box_b, float* out, int A, int Bn, void* stream);
+
+/* ---- Detect_RefineDet.forward (detection_refinedet.py:27-65) --------------- */
+/* ARM filter + two-stage decode, dense outputs.  `odm_conf` is modified IN PLACE
+ * exactly like the reference (:40-42): rows with arm_conf[...,1] <= objectness_thre
+ * become all-zero.  boxes_out[B,P,4] point form, unclipped; scores_out[B,P,C]. */
+RD_API int rd_detect_forward(const float* arm_loc, const float* arm_conf, const float* odm_loc,
+                      float* odm_conf, const float* priors, int B, int P, int C,
+                      float objectness_thre, float v0, float v1,
+                      float* boxes_out, float* scores_out, void* stream);
+
+/* ---- fused detect stage ---------------------------------------------------- */
+/* (Detect_RefineDet.forward + the per-class loop of eval_refinedet_coco.py:205-232,
+ *  or Detect_RefineDet.forward_python_nms, detection_refinedet.py:67-113, depending
+ *  on the flags.)  Inputs are read once and are NOT modified. */
+RD_API size_t rd_detect_workspace_bytes(int B, int P, int C);
+RD_API int    rd_detect_workspace_reset(void* workspace, size_t workspace_bytes, void* stream);
+/* per (image b, class c>=1):
+ *   candidates = anchors with arm_conf[b,p,1] > objectness_thre and
+ *                odm_conf[b,p,c] > conf_thresh; the top_k highest scores are kept
+ *                (ties: lower anchor index first), boxes are the two-stage decode
+ *                multiplied by img_scale[b] (may be NULL = no scaling), greedy NMS in
+ *                score order with `nms_flags`, at most `max_out` rows are emitted.
+ * outputs:
+ *   out_counts [B,C]            int32   (class 0 is always 0)
+ *   out_dets   [B,C,max_out,5]  float   rows per `row_layout`; only the first
+ *                                       out_counts[b,c] rows of a slot are written
+ *   out_anchor [B,C,max_out]    int32   anchor index of each row (may be NULL)      */
+RD_API int rd_detect_fused(const float* arm_loc, const float* arm_conf, const float* odm_loc,
+                    const float* odm_conf, const float* priors, int B, int P, int C,
+                    float objectness_thre, float conf_thresh, float nms_thresh,
+                    int top_k, int max_out, const float* img_scale, int nms_flags,
+                    int row_layout, float v0, float v1,
+                    void* workspace, size_t workspace_bytes,
+                    int* out_counts, float* out_dets, int* out_anchor, void* stream);
+
+/* compact [B,C,max_out,5] slots into packed rows (score-descending inside a class,
+ * classes ascending, images ascending).  out_offsets[B*C+1] = exclusive prefix sum
+ * of counts; packed[total,5]; packed_capacity = rows available in `packed`. */
+RD_API int rd_pack_detections(const int* counts, const float* dets, int B, int C, int max_out,
+                       int* out_offsets, float* packed, int packed_capacity, void* stream);
+
+/* ---- stand-alone NMS ------------------------------------------------------- */
+RD_API size_t rd_nms_workspace_bytes(int n);
+/* box_utils.nms (box_utils.py:222-286) / utils.nms_wrapper.nms on device tensors:
+ * boxes[n,4], scores[n]; keeps the top_k highest scores, greedy NMS, writes the
+ * ORIGINAL indices of the kept boxes (score-descending) to keep_out[n] (int64,
+ * entries past the count are left untouched) and the count to count_out[1] (int32). */
+RD_API int rd_nms(const float* boxes, const float* scores, int n, float thresh, int top_k,
+           int nms_flags, void* workspace, size_t workspace_bytes,
+           long long* keep_out, int* count_out, void* stream);
+/* Drop-in for `_nms` (utils/nms/gpu_nms.hpp:1-2, nms_kernel.cu:91-144): HOST pointers,
+ * boxes_host[boxes_num, boxes_dim>=5] rows x1,y1,x2,y2,score ALREADY sorted by score
+ * descending (gpu_nms.pyx:26-29); pixel +1 IoU, suppress IoU > thresh; synchronous;
+ * allocates and frees its own device scratch like the reference. */
+RD_API int rd_nms_host(int* keep_out_host, int* num_out_host, const float* boxes_host,
+                int boxes_num, int boxes_dim, float nms_overlap_thresh, int device_id);
+/* same with explicit flavour flags (RD_NMS_PIXEL_PLUS1 | RD_NMS_SUPPRESS_EQ reproduces the
+ * Cython cpu_nms the reference dispatches to under force_cpu, utils/nms_wrapper.py:28-30) */
+RD_API int rd_nms_host_ex(int* keep_out_host, int* num_out_host, const float* boxes_host,
+                   int boxes_num, int boxes_dim, float nms_overlap_thresh, int device_id,
+                   int nms_flags);
+
+/* ---- training side: refine_match + hard-negative mining -------------------- */
+/* refine_match / match over a batch (box_utils.py:70-160, called per image at
+ * refinedet_multibox_loss.py:75-86).
+ *   truths [B,Gmax,4] point form, labels [B,Gmax] float, gt_count [B] int32 (<= Gmax)
+ *   priors [P,4] (cx,cy,w,h);  arm_loc [B,P,4] or NULL (ARM criterion / SSD match)
+ *   label_mode: 0 = conf = (int64)labels[g]          (ODM, 1-based labels)
+ *               1 = conf = labels[g] >= 0 ? 1 : 0    (ARM 2-class, :78-79)
+ *               2 = conf = (int64)labels[g] + 1      (SSD match(), box_utils.py:107)
+ *   outputs loc_t [B,P,4] float, conf_t [B,P] int64, best_truth_idx [B,P] int32 and
+ *   best_truth_overlap [B,P] float (after the forced matches of :146-150; both are
+ *   REQUIRED — they double as the scratch between the two kernels).
+ * An image with gt_count == 0 yields conf_t = 0 and loc_t = 0 (the reference raises). */
+RD_API size_t rd_match_workspace_bytes(int B, int Gmax);
+RD_API int rd_refine_match(const float* truths, const float* labels, const int* gt_count,
+                    const float* priors, const float* arm_loc, int B, int P, int Gmax,
+                    float threshold, float v0, float v1, int label_mode,
+                    void* workspace, size_t workspace_bytes,
+                    float* loc_t, long long* conf_t, int* best_truth_idx,
+                    float* best_truth_overlap, void* stream);
+
+/* hard-negative mining (refinedet_multibox_loss.py:117-123):
+ *   loss_c [B,P] float (values at positives are ignored = treated as 0, :117),
+ *   pos [B,P] uint8;  neg_out [B,P] uint8 = 1 for the num_neg = min(ratio*num_pos, P-1)
+ *   largest entries of each row (ties: lower index first); num_pos_out [B] int32. */
+RD_API int rd_hnm_select(const float* loss_c, const unsigned char* pos, int B, int P,
+                  int negpos_ratio, unsigned char* neg_out, int* num_pos_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* REFINEDET_B200_H_ */

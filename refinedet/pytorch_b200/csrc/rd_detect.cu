@@ -1,0 +1,589 @@
+// rd_detect.cu — detect stage of RefineDet on B200 (sm_100a).
+//
+// Replaces (reference paths): layers/functions/detection_refinedet.py:27-113,
+// eval_refinedet_coco.py:205-232, utils/nms_wrapper.py:23-31, utils/nms/nms_kernel.cu.
+//
+// Kernels
+//   detect_forward_kernel   a3: ARM filter + two-stage decode, dense boxes/scores, in-place zeroing
+//   collect_kernel          K1: ARM filter, decode of passing anchors, per-(image,class)
+//                           candidate lists.  Data-dependent traffic: odm_conf / loc rows of
+//                           ARM-filtered anchors are never fetched.
+//   nms_small_kernel        K2+K3 for (image,class) problems with <= kSmallCap candidates,
+//                           one CTA each, ~15 KB smem so many CTAs are resident per SM
+//   nms_large_kernel        persistent CTAs draining the queue of larger problems
+//   nms_single_kernel       stand-alone problem (rd_nms / rd_nms_host)
+//   pack_kernel             slot layout -> packed rows
+#include "rd_nms_core.cuh"
+
+#include <atomic>
+
+namespace rd {
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+constexpr int kSmallCap = 256;       // problems up to this many boxes run in nms_small_kernel
+constexpr int kCollectThreads = 256;
+
+// ---------------------------------------------------------------------------------------
+// workspace of the fused stage
+//   [0, 256)                 : header: u32 queue_count
+//   cnt    int  [B*C]        : candidate counts (zero between calls)
+//   queue  int  [B*C]        : (image,class) problems routed to nms_large_kernel
+//   boxes  f4   [B*P]        : decoded boxes of ARM-passing anchors
+//   cand   u64  [B*C*P]      : candidate keys, capacity P per (image,class)
+// ---------------------------------------------------------------------------------------
+struct DetectWs {
+    uint32_t* header;
+    int* cnt;
+    int* queue;
+    float4* boxes;
+    unsigned long long* cand;
+    size_t total;
+};
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static DetectWs carve_ws(void* base, int B, int P, int C) {
+    DetectWs w;
+    size_t o = 0;
+    unsigned char* p = static_cast<unsigned char*>(base);
+    w.header = reinterpret_cast<uint32_t*>(p + o);             o += 256;
+    w.cnt = reinterpret_cast<int*>(p + o);                     o += align_up((size_t)B * C * 4, 256);
+    w.queue = reinterpret_cast<int*>(p + o);                   o += align_up((size_t)B * C * 4, 256);
+    w.boxes = reinterpret_cast<float4*>(p + o);                o += align_up((size_t)B * P * 16, 256);
+    w.cand = reinterpret_cast<unsigned long long*>(p + o);     o += align_up((size_t)B * C * P * 8, 256);
+    w.total = o;
+    return w;
+}
+
+// ---------------------------------------------------------------------------------------
+// a3: Detect_RefineDet.forward (detection_refinedet.py:27-65)
+// One warp per 32 consecutive (image*P + anchor) rows of the flattened batch.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCollectThreads)
+detect_forward_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ arm_conf,
+                      const float4* __restrict__ odm_loc, float* odm_conf,
+                      const float4* __restrict__ priors, long long total, int P, int C,
+                      float obj_thre, float v0, float v1, float4* __restrict__ boxes_out,
+                      float* __restrict__ scores_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * kCollectThreads + threadIdx.x) >> 5;
+    const long long g0 = warp_global * 32;
+    if (g0 >= total) return;
+    const long long g = g0 + lane;
+    const bool valid = g < total;
+    bool pass = false;
+    if (valid) {
+        float2 ac = ldg_stream2(arm_conf + g);
+        pass = !(ac.y <= obj_thre);            // reference zeroes where arm_conf[...,1] <= thre (:41)
+        const int a = (int)(g % P);
+        float4 box = refine_decode(ldg_stream4(arm_loc + g), ldg_stream4(odm_loc + g), __ldg(priors + a), v0, v1);
+        boxes_out[g] = box;
+    }
+    const unsigned mask = __ballot_sync(kFullMask, pass);
+    const int nvalid = (int)min((long long)32, total - g0);
+    const long long e_base = g0 * C;
+    const int nelem = nvalid * C;
+    float* conf = odm_conf + e_base;
+    float* sc = scores_out + e_base;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(conf) | reinterpret_cast<uintptr_t>(sc)) & 15) == 0;
+    const int nvec = vec_ok ? (nelem >> 2) : 0;
+    // per-lane running (anchor, class) of element 4*q, advanced by 128 elements per iteration
+    int e0 = lane * 4;
+    int al = e0 / C, c = e0 - al * C;
+    const int dal = 128 / C, dc = 128 - dal * C;
+    for (int q = lane; q < nvec; q += 32) {
+        // anchors of the 4 elements
+        int a0 = al, c0 = c;
+        unsigned pm = 0;       // pass bit per element
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            pm |= ((mask >> a0) & 1u) << k;
+            if (++c0 == C) { c0 = 0; ++a0; }
+        }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pm) {
+            v = *reinterpret_cast<const float4*>(conf + 4 * q);
+            if (!(pm & 1u)) v.x = 0.f;
+            if (!(pm & 2u)) v.y = 0.f;
+            if (!(pm & 4u)) v.z = 0.f;
+            if (!(pm & 8u)) v.w = 0.f;
+        }
+        *reinterpret_cast<float4*>(sc + 4 * q) = v;
+        if (pm != 15u) *reinterpret_cast<float4*>(conf + 4 * q) = v;   // in-place zeroing (:42)
+        al += dal; c += dc;
+        if (c >= C) { c -= C; ++al; }
+    }
+    // scalar tail (and the whole region when the pointers are not 16-byte aligned)
+    for (int e = nvec * 4 + lane; e < nelem; e += 32) {
+        int a1 = e / C;
+        float v = 0.f;
+        if ((mask >> a1) & 1u) v = conf[e]; else conf[e] = 0.f;
+        sc[e] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K1: ARM filter + decode + candidate collection
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_candidate(float v, int al, int c, long long g0, int P, int C, int cap,
+                                               int* cnt, unsigned long long* cand) {
+    long long g = g0 + al;
+    int b = (int)(g / P);
+    int a = (int)(g - (long long)b * P);
+    int bc = b * C + c;
+    int slot = atomicAdd(&cnt[bc], 1);
+    cand[(size_t)bc * cap + slot] = make_key(v, (uint32_t)a);
+}
+
+__global__ void __launch_bounds__(kCollectThreads)
+collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ arm_conf,
+               const float4* __restrict__ odm_loc, const float* __restrict__ odm_conf,
+               const float4* __restrict__ priors, long long total, int P, int C, float obj_thre,
+               float conf_thresh, float v0, float v1, float4* __restrict__ boxes_ws, int* cnt,
+               unsigned long long* cand, uint32_t* header) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) header[0] = 0;   // queue of the large-NMS kernel
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * kCollectThreads + threadIdx.x) >> 5;
+    const long long g0 = warp_global * 32;
+    if (g0 >= total) return;
+    const long long g = g0 + lane;
+    const bool valid = g < total;
+    bool pass = false;
+    if (valid) {
+        float2 ac = ldg_stream2(arm_conf + g);
+        pass = !(ac.y <= obj_thre);
+    }
+    const unsigned mask = __ballot_sync(kFullMask, pass);
+    if (mask == 0) return;                  // no anchor of this warp survives the ARM filter
+    if (pass) {
+        const int a = (int)(g % P);
+        boxes_ws[g] = refine_decode(ldg_stream4(arm_loc + g), ldg_stream4(odm_loc + g), __ldg(priors + a), v0, v1);
+    }
+    const int nvalid = (int)min((long long)32, total - g0);
+    const int nelem = nvalid * C;
+    const float* conf = odm_conf + g0 * C;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(conf) & 15) == 0;
+    const int nvec = vec_ok ? (nelem >> 2) : 0;
+    int e0 = lane * 4;
+    int al = e0 / C, c = e0 - al * C;
+    const int dal = 128 / C, dc = 128 - dal * C;
+    for (int q = lane; q < nvec; q += 32) {
+        int a0 = al, c0 = c;
+        unsigned pm = 0;
+        int an[4], cn[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            an[k] = a0; cn[k] = c0;
+            pm |= (((mask >> a0) & 1u) & (c0 != 0 ? 1u : 0u)) << k;   // class 0 = background, never a candidate
+            if (++c0 == C) { c0 = 0; ++a0; }
+        }
+        if (pm) {
+            float4 v = ldg_stream4(reinterpret_cast<const float4*>(conf) + q);
+            if ((pm & 1u) && v.x > conf_thresh) emit_candidate(v.x, an[0], cn[0], g0, P, C, P, cnt, cand);
+            if ((pm & 2u) && v.y > conf_thresh) emit_candidate(v.y, an[1], cn[1], g0, P, C, P, cnt, cand);
+            if ((pm & 4u) && v.z > conf_thresh) emit_candidate(v.z, an[2], cn[2], g0, P, C, P, cnt, cand);
+            if ((pm & 8u) && v.w > conf_thresh) emit_candidate(v.w, an[3], cn[3], g0, P, C, P, cnt, cand);
+        }
+        al += dal; c += dc;
+        if (c >= C) { c -= C; ++al; }
+    }
+    for (int e = nvec * 4 + lane; e < nelem; e += 32) {
+        int a1 = e / C, c1 = e - a1 * C;
+        if (c1 != 0 && ((mask >> a1) & 1u)) {
+            float v = ldg_stream1(conf + e);
+            if (v > conf_thresh) emit_candidate(v, a1, c1, g0, P, C, P, cnt, cand);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2+K3
+// ---------------------------------------------------------------------------------------
+struct FusedNmsArgs {
+    int* cnt;                        // [B*C]
+    const unsigned long long* cand;  // [B*C*cap]
+    const float4* boxes;             // [B*P]
+    const float* img_scale;          // [B,4] or null
+    int* queue;
+    uint32_t* header;
+    int C, P, cap;
+    float thr;
+    int top_k, max_out, flags, row_layout;
+    int* out_counts;
+    float* out_dets;
+    int* out_anchor;
+};
+
+__device__ __forceinline__ void emit_rows(unsigned char* smem, const NmsSmemLayout& L, int kept, int bc,
+                                          const FusedNmsArgs& A) {
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(smem + L.off_keys);
+    const float* sx1 = reinterpret_cast<const float*>(smem + L.off_x1);
+    const float* sy1 = reinterpret_cast<const float*>(smem + L.off_y1);
+    const float* sx2 = reinterpret_cast<const float*>(smem + L.off_x2);
+    const float* sy2 = reinterpret_cast<const float*>(smem + L.off_y2);
+    const int* keptidx = reinterpret_cast<const int*>(smem + L.off_keptidx);
+    float* rows = A.out_dets + (size_t)bc * A.max_out * 5;
+    for (int t = threadIdx.x; t < kept; t += kNmsThreads) {
+        int j = keptidx[t];
+        unsigned long long k = keys[j];
+        float s = key_score(k);
+        float* r = rows + (size_t)t * 5;
+        if (A.row_layout == RD_ROW_SCORE_BOX) {
+            r[0] = s; r[1] = sx1[j]; r[2] = sy1[j]; r[3] = sx2[j]; r[4] = sy2[j];
+        } else {
+            r[0] = sx1[j]; r[1] = sy1[j]; r[2] = sx2[j]; r[3] = sy2[j]; r[4] = s;
+        }
+        if (A.out_anchor) A.out_anchor[(size_t)bc * A.max_out + t] = (int)key_index(k);
+    }
+}
+
+__device__ __forceinline__ void run_fused_problem(unsigned char* smem, const NmsSmemLayout& L, int bc, int n,
+                                                  const FusedNmsArgs& A) {
+    const int b = bc / A.C;
+    NmsProblem pb;
+    pb.cand = A.cand + (size_t)bc * A.cap;
+    pb.n = n;
+    pb.boxes = A.boxes + (size_t)b * A.P;
+    pb.has_scale = A.img_scale != nullptr;
+    pb.scale = pb.has_scale ? __ldg(reinterpret_cast<const float4*>(A.img_scale) + b) : make_float4(1.f, 1.f, 1.f, 1.f);
+    pb.thr = A.thr;
+    pb.top_k = A.top_k;
+    pb.max_out = A.max_out;
+    pb.flags = A.flags;
+    int kept = nms_process(smem, L, pb);
+    emit_rows(smem, L, kept, bc, A);
+    if (threadIdx.x == 0) {
+        A.out_counts[bc] = kept;
+        A.cnt[bc] = 0;                // leave the workspace ready for the next call
+    }
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+nms_small_kernel(FusedNmsArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int bc = blockIdx.x;
+    const int c = bc % A.C;
+    if (c == 0) {                      // background is never evaluated (eval_refinedet_coco.py:213)
+        if (threadIdx.x == 0) A.out_counts[bc] = 0;
+        return;
+    }
+    const int n = A.cnt[bc];
+    if (n == 0) {
+        if (threadIdx.x == 0) A.out_counts[bc] = 0;
+        return;
+    }
+    const int m = n < A.top_k ? n : A.top_k;
+    if (m > kSmallCap) {
+        if (threadIdx.x == 0) {
+            uint32_t pos = atomicAdd(&A.header[0], 1u);
+            A.queue[pos] = bc;
+        }
+        return;
+    }
+    const NmsSmemLayout L = nms_layout(kSmallCap);
+    run_fused_problem(smem, L, bc, n, A);
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+nms_large_kernel(FusedNmsArgs A, int mcap) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const NmsSmemLayout L = nms_layout(mcap);
+    const uint32_t nq = A.header[0];
+    for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
+        const int bc = A.queue[q];
+        const int n = A.cnt[bc];
+        run_fused_problem(smem, L, bc, n, A);
+        __syncthreads();
+    }
+}
+
+// stand-alone problem
+__global__ void make_keys_kernel(const float* __restrict__ scores, int n, unsigned long long* keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = make_key(scores[i], (uint32_t)i);
+}
+// rows already sorted by score descending (rd_nms_host): the key order must follow the row order
+__global__ void make_keys_sorted_kernel(int n, unsigned long long* keys) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ((unsigned long long)(0xffffffffu - (uint32_t)i) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+}
+__global__ void strip_boxes_kernel(const float* __restrict__ dets, int n, int dim, float4* boxes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) boxes[i] = make_float4(dets[(size_t)i * dim], dets[(size_t)i * dim + 1], dets[(size_t)i * dim + 2],
+                                      dets[(size_t)i * dim + 3]);
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+nms_single_kernel(const unsigned long long* cand, int n, const float4* boxes, float thr, int top_k, int max_out,
+                  int flags, int mcap, long long* keep_out, int* keep_out32, int* count_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const NmsSmemLayout L = nms_layout(mcap);
+    NmsProblem pb;
+    pb.cand = cand; pb.n = n; pb.boxes = boxes; pb.has_scale = 0;
+    pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
+    pb.thr = thr; pb.top_k = top_k; pb.max_out = max_out; pb.flags = flags;
+    int kept = nms_process(smem, L, pb);
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(smem + L.off_keys);
+    const int* keptidx = reinterpret_cast<const int*>(smem + L.off_keptidx);
+    for (int t = threadIdx.x; t < kept; t += kNmsThreads) {
+        uint32_t idx = key_index(keys[keptidx[t]]);
+        if (keep_out) keep_out[t] = (long long)idx;
+        if (keep_out32) keep_out32[t] = (int)idx;
+    }
+    if (threadIdx.x == 0) *count_out = kept;
+}
+
+// ---------------------------------------------------------------------------------------
+// packing: [B,C,max_out,5] slots -> packed rows + offsets
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+pack_offsets_kernel(const int* __restrict__ counts, int nbc, int* __restrict__ offsets) {
+    // single CTA exclusive scan (nbc is a few thousand)
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nbc; base += 1024) {
+        int i = base + tid;
+        int v = i < nbc ? counts[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(kFullMask, x, d); if (lane >= d) x += o; }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int s = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(kFullMask, s, d); if (lane >= d) s += o; }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        int prefix = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + x - v;
+        if (i < nbc) offsets[i] = prefix;
+        __syncthreads();
+        if (tid == 1023) carry = prefix + v;
+        __syncthreads();
+    }
+    if (tid == 0) offsets[nbc] = carry;
+}
+
+__global__ void pack_rows_kernel(const int* __restrict__ counts, const int* __restrict__ offsets,
+                                 const float* __restrict__ dets, int max_out, float* __restrict__ packed,
+                                 int capacity) {
+    const int bc = blockIdx.x;
+    const int n = counts[bc];
+    const int off = offsets[bc];
+    const float* src = dets + (size_t)bc * max_out * 5;
+    for (int t = threadIdx.x; t < n * 5; t += blockDim.x) {
+        int row = off + t / 5;
+        if (row < capacity) packed[(size_t)off * 5 + t] = src[t];
+    }
+}
+
+}  // namespace rd
+
+using namespace rd;
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+unsigned long long rd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int rd_detect_forward(const float* arm_loc, const float* arm_conf, const float* odm_loc, float* odm_conf,
+                      const float* priors, int B, int P, int C, float objectness_thre, float v0, float v1,
+                      float* boxes_out, float* scores_out, void* stream) {
+    if (!arm_loc || !arm_conf || !odm_loc || !odm_conf || !priors || !boxes_out || !scores_out) return RD_ERR_BAD_ARG;
+    if (B <= 0 || P <= 0 || C <= 0) return RD_ERR_BAD_ARG;
+    if (C > 128) return RD_ERR_UNSUPPORTED;
+    if ((((uintptr_t)arm_loc | (uintptr_t)odm_loc | (uintptr_t)priors | (uintptr_t)boxes_out) & 15) ||
+        ((uintptr_t)arm_conf & 7))
+        return RD_ERR_ALIGNMENT;
+    const long long total = (long long)B * P;
+    const long long warps = (total + 31) / 32;
+    const int blocks = (int)((warps * 32 + kCollectThreads - 1) / kCollectThreads);
+    detect_forward_kernel<<<blocks, kCollectThreads, 0, (cudaStream_t)stream>>>(
+        (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
+        total, P, C, objectness_thre, v0, v1, (float4*)boxes_out, scores_out);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+size_t rd_detect_workspace_bytes(int B, int P, int C) {
+    if (B <= 0 || P <= 0 || C <= 0) return 0;
+    return carve_ws(nullptr, B, P, C).total;
+}
+
+int rd_detect_workspace_reset(void* workspace, size_t workspace_bytes, void* stream) {
+    if (!workspace) return RD_ERR_BAD_ARG;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream);
+    return (int)e;
+}
+
+int rd_detect_fused(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
+                    const float* priors, int B, int P, int C, float objectness_thre, float conf_thresh,
+                    float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
+                    int row_layout, float v0, float v1, void* workspace, size_t workspace_bytes,
+                    int* out_counts, float* out_dets, int* out_anchor, void* stream) {
+    if (!arm_loc || !arm_conf || !odm_loc || !odm_conf || !priors || !workspace || !out_counts || !out_dets)
+        return RD_ERR_BAD_ARG;
+    if (B <= 0 || P <= 0 || C <= 0 || top_k <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
+    if (C > 128 || (long long)B * C > (1 << 30)) return RD_ERR_UNSUPPORTED;
+    if (top_k > RD_MAX_NMS_BOXES) return RD_ERR_UNSUPPORTED;
+    if ((((uintptr_t)arm_loc | (uintptr_t)odm_loc | (uintptr_t)priors | (uintptr_t)workspace) & 15) ||
+        ((uintptr_t)arm_conf & 7) || (img_scale && ((uintptr_t)img_scale & 15)))
+        return RD_ERR_ALIGNMENT;
+    DetectWs ws = carve_ws(workspace, B, P, C);
+    if (workspace_bytes < ws.total) return RD_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    const long long total = (long long)B * P;
+    const long long warps = (total + 31) / 32;
+    const int blocks = (int)((warps * 32 + kCollectThreads - 1) / kCollectThreads);
+    collect_kernel<<<blocks, kCollectThreads, 0, st>>>(
+        (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
+        total, P, C, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.header);
+    note_launch();
+    RD_CHECK_LAUNCH();
+
+    FusedNmsArgs A;
+    A.cnt = ws.cnt; A.cand = ws.cand; A.boxes = ws.boxes; A.img_scale = img_scale;
+    A.queue = ws.queue; A.header = ws.header; A.C = C; A.P = P; A.cap = P;
+    A.thr = nms_thresh; A.top_k = top_k; A.max_out = max_out; A.flags = nms_flags; A.row_layout = row_layout;
+    A.out_counts = out_counts; A.out_dets = out_dets; A.out_anchor = out_anchor;
+
+    static int s_dev_sms = 0;
+    if (s_dev_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&s_dev_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (s_dev_sms <= 0) s_dev_sms = 148;
+    }
+    const NmsSmemLayout Ls = nms_layout(kSmallCap);
+    nms_small_kernel<<<B * C, kNmsThreads, Ls.total, st>>>(A);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    if (top_k > kSmallCap) {
+        const int mcap = top_k < P ? top_k : P;
+        const NmsSmemLayout Ll = nms_layout(mcap);
+        static size_t s_attr = 0;
+        if (Ll.total > s_attr) {
+            cudaError_t e = cudaFuncSetAttribute(nms_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)Ll.total);
+            if (e != cudaSuccess) return (int)e;
+            s_attr = Ll.total;
+        }
+        int per_sm = (int)((220 * 1024) / (Ll.total + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        int grid = s_dev_sms * per_sm;
+        if (grid > B * C) grid = B * C;
+        nms_large_kernel<<<grid, kNmsThreads, Ll.total, st>>>(A, mcap);
+        note_launch();
+        RD_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+int rd_pack_detections(const int* counts, const float* dets, int B, int C, int max_out, int* out_offsets,
+                       float* packed, int packed_capacity, void* stream) {
+    if (!counts || !dets || !out_offsets || !packed || B <= 0 || C <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    pack_offsets_kernel<<<1, 1024, 0, st>>>(counts, B * C, out_offsets);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    pack_rows_kernel<<<B * C, 128, 0, st>>>(counts, out_offsets, dets, max_out, packed, packed_capacity);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---- stand-alone NMS --------------------------------------------------------------------
+size_t rd_nms_workspace_bytes(int n) {
+    if (n <= 0) return 256;
+    return align_up((size_t)n * 8, 256) + align_up((size_t)n * 16, 256);
+}
+
+static int launch_single(const unsigned long long* keys, int n, const float4* boxes, float thresh, int top_k,
+                         int nms_flags, long long* keep64, int* keep32, int* count_out, cudaStream_t st) {
+    int m = top_k < n ? top_k : n;
+    if (m > RD_MAX_NMS_BOXES) return RD_ERR_UNSUPPORTED;
+    const NmsSmemLayout L = nms_layout(m);
+    static size_t s_attr = 48 * 1024;
+    if (L.total > s_attr) {
+        cudaError_t e = cudaFuncSetAttribute(nms_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)L.total);
+        if (e != cudaSuccess) return (int)e;
+        s_attr = L.total;
+    }
+    nms_single_kernel<<<1, kNmsThreads, L.total, st>>>(keys, n, boxes, thresh, top_k, m, nms_flags, m, keep64,
+                                                        keep32, count_out);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+int rd_nms(const float* boxes, const float* scores, int n, float thresh, int top_k, int nms_flags,
+           void* workspace, size_t workspace_bytes, long long* keep_out, int* count_out, void* stream) {
+    if (!count_out || n < 0 || top_k <= 0) return RD_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return (int)cudaMemsetAsync(count_out, 0, sizeof(int), st);
+    if (!boxes || !scores || !workspace || !keep_out) return RD_ERR_BAD_ARG;
+    if (((uintptr_t)boxes | (uintptr_t)workspace) & 15) return RD_ERR_ALIGNMENT;
+    if (workspace_bytes < align_up((size_t)n * 8, 256)) return RD_ERR_WORKSPACE;
+    unsigned long long* keys = (unsigned long long*)workspace;
+    make_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(scores, n, keys);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return launch_single(keys, n, (const float4*)boxes, thresh, top_k, nms_flags, keep_out, nullptr, count_out, st);
+}
+
+int rd_nms_host_ex(int* keep_out_host, int* num_out_host, const float* boxes_host, int boxes_num, int boxes_dim,
+                   float nms_overlap_thresh, int device_id, int nms_flags) {
+    if (!keep_out_host || !num_out_host || boxes_num < 0 || boxes_dim < 5) return RD_ERR_BAD_ARG;
+    if (boxes_num == 0) { *num_out_host = 0; return 0; }
+    if (!boxes_host) return RD_ERR_BAD_ARG;
+    if (boxes_num > RD_MAX_NMS_BOXES) return RD_ERR_UNSUPPORTED;
+    cudaError_t e = cudaSetDevice(device_id);
+    if (e != cudaSuccess) return (int)e;
+    const int n = boxes_num;
+    const size_t b_dets = align_up((size_t)n * boxes_dim * 4, 256);
+    const size_t b_box = align_up((size_t)n * 16, 256);
+    const size_t b_keys = align_up((size_t)n * 8, 256);
+    const size_t b_keep = align_up((size_t)n * 4, 256);
+    unsigned char* d = nullptr;
+    e = cudaMalloc(&d, b_dets + b_box + b_keys + b_keep + 256);
+    if (e != cudaSuccess) return (int)e;
+    float* d_dets = (float*)d;
+    float4* d_box = (float4*)(d + b_dets);
+    unsigned long long* d_keys = (unsigned long long*)(d + b_dets + b_box);
+    int* d_keep = (int*)(d + b_dets + b_box + b_keys);
+    int* d_cnt = (int*)(d + b_dets + b_box + b_keys + b_keep);
+    int rc = 0;
+    cudaStream_t st = 0;
+    e = cudaMemcpyAsync(d_dets, boxes_host, (size_t)n * boxes_dim * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cudaFree(d); return (int)e; }
+    strip_boxes_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_dets, n, boxes_dim, d_box);
+    make_keys_sorted_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d_keys);
+    note_launch(2);
+    rc = launch_single(d_keys, n, d_box, nms_overlap_thresh, n, nms_flags, nullptr, d_keep, d_cnt, st);
+    if (rc == 0) {
+        e = cudaMemcpyAsync(num_out_host, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(keep_out_host, d_keep, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        rc = (int)e;
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int rd_nms_host(int* keep_out_host, int* num_out_host, const float* boxes_host, int boxes_num, int boxes_dim,
+                float nms_overlap_thresh, int device_id) {
+    return rd_nms_host_ex(keep_out_host, num_out_host, boxes_host, boxes_num, boxes_dim, nms_overlap_thresh,
+                          device_id, RD_NMS_PIXEL_PLUS1);
+}
+
+}  // extern "C"

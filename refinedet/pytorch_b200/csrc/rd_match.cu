@@ -1,0 +1,373 @@
+// rd_match.cu — training-side anchor matching and hard-negative mining on B200 (sm_100a).
+//
+// Replaces (reference paths): layers/box_utils.py:29-160 (intersect, jaccard, match,
+// refine_match, encode) as driven by layers/modules/refinedet_multibox_loss.py:73-86, and
+// the double-sort hard-negative ranking of refinedet_multibox_loss.py:117-123.
+//
+// Kernels
+//   match_pass1_kernel   per (image, anchor): anchor box (point_form(prior) or decode(arm_loc,
+//                        prior)), running best truth (first index on ties) over the ground
+//                        truths staged in shared memory; per-truth best prior through a
+//                        CTA-level 64-bit max in shared memory and one global atomicMax per
+//                        (CTA, truth).  The [G,P] overlap matrix never exists in memory.
+//   match_pass2_kernel   forced matches (last truth wins, box_utils.py:146-150), labels,
+//                        threshold, encode -> loc_t, conf_t
+//   hnm_select_kernel    one CTA per image row: count positives, MSB-first radix select of the
+//                        num_neg-th largest (loss, ~index) key, write the neg mask
+//   elementwise kernels  point_form / center_size / decode / encode / intersect / jaccard
+#include "rd_common.cuh"
+
+namespace rd {
+
+constexpr int kMatchThreads = 256;
+
+// key of (overlap, prior): larger overlap wins, then the LOWER prior index (torch.max returns
+// the first maximal index)
+__device__ __forceinline__ unsigned long long prior_key(float iou, uint32_t p) {
+    return ((unsigned long long)float_to_ordered(iou) << 32) | (unsigned long long)(0xffffffffu - p);
+}
+
+__device__ __forceinline__ float4 anchor_point_box(const float4* priors, const float4* arm_loc, int b, int p, int P,
+                                                   float v0, float v1) {
+    float4 pr = __ldg(priors + p);
+    if (arm_loc) return decode_box(ldg_stream4(arm_loc + (size_t)b * P + p), pr, v0, v1);   // box_utils.py:135
+    return point_form_box(pr);                                                                // box_utils.py:133
+}
+
+__global__ void __launch_bounds__(kMatchThreads)
+match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt_count,
+                   const float4* __restrict__ priors, const float4* __restrict__ arm_loc, int P, int Gmax,
+                   float v0, float v1, unsigned long long* __restrict__ best_prior,   // [B,Gmax]
+                   float* __restrict__ bt_overlap, int* __restrict__ bt_idx) {       // [B,P] temporaries
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_truth = reinterpret_cast<float4*>(smem_raw);
+    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)Gmax * 16);
+    const int b = blockIdx.y;
+    const int G = gt_count[b];
+    const int p = blockIdx.x * kMatchThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (G <= 0) return;
+    for (int g = threadIdx.x; g < G; g += kMatchThreads) {
+        s_truth[g] = __ldg(truths + (size_t)b * Gmax + g);
+        s_best[g] = 0ull;
+    }
+    __syncthreads();
+    const bool valid = p < P;
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) box = anchor_point_box(priors, arm_loc, b, p, P, v0, v1);
+    const float area_b = (box.z - box.x) * (box.w - box.y);
+    float best = 0.f;
+    int best_g = 0;
+    const bool first_warp_of_row = (blockIdx.x == 0) && (threadIdx.x < 32);
+    for (int g = 0; g < G; ++g) {
+        const float4 t = s_truth[g];
+        // box_utils.py:42-47,62-68 (truth = box_a, anchor = box_b)
+        float w = fmaxf(fminf(t.z, box.z) - fmaxf(t.x, box.x), 0.0f);
+        float h = fmaxf(fminf(t.w, box.w) - fmaxf(t.y, box.y), 0.0f);
+        float inter = w * h;
+        float area_t = (t.z - t.x) * (t.w - t.y);
+        float iou = inter / (area_t + area_b - inter);
+        if (!valid) iou = -1.0f;
+        if (g == 0 || iou > best) { best = iou; best_g = g; }
+        // per-truth best prior: only overlapping anchors (or the row's first warp, which
+        // supplies prior 0 for a truth that overlaps nothing) can win
+        const bool contend = valid && (iou > 0.0f || iou != iou);
+        if (__any_sync(kFullMask, contend) || first_warp_of_row) {
+            uint32_t ord = valid ? float_to_ordered(iou) : 0u;
+            uint32_t mx = __reduce_max_sync(kFullMask, ord);
+            unsigned who = __ballot_sync(kFullMask, valid && ord == mx);
+            if (lane == __ffs(who) - 1) atomicMax(&s_best[g], prior_key(iou, (uint32_t)p));
+        }
+    }
+    if (valid) {
+        bt_overlap[(size_t)b * P + p] = best;
+        bt_idx[(size_t)b * P + p] = best_g;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += kMatchThreads) {
+        unsigned long long k = s_best[g];
+        if (k) atomicMax(best_prior + (size_t)b * Gmax + g, k);
+    }
+}
+
+__global__ void __launch_bounds__(kMatchThreads)
+match_pass2_kernel(const float4* __restrict__ truths, const float* __restrict__ labels,
+                   const int* __restrict__ gt_count, const float4* __restrict__ priors,
+                   const float4* __restrict__ arm_loc, int P, int Gmax, float threshold, float v0, float v1,
+                   int label_mode, const unsigned long long* __restrict__ best_prior,
+                   const float* bt_overlap_tmp, const int* bt_idx_tmp,
+                   float4* __restrict__ loc_t, long long* __restrict__ conf_t,
+                   int* out_bt_idx, float* out_bt_overlap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* s_bp = reinterpret_cast<int*>(smem_raw);   // best prior index of each truth
+    const int b = blockIdx.y;
+    const int G = gt_count[b];
+    const int p = blockIdx.x * kMatchThreads + threadIdx.x;
+    for (int g = threadIdx.x; g < G; g += kMatchThreads)
+        s_bp[g] = (int)key_index(best_prior[(size_t)b * Gmax + g]);
+    __syncthreads();
+    if (p >= P) return;
+    const size_t o = (size_t)b * P + p;
+    if (G <= 0) {
+        loc_t[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+        conf_t[o] = 0;
+        if (out_bt_idx) out_bt_idx[o] = 0;
+        if (out_bt_overlap) out_bt_overlap[o] = 0.f;
+        return;
+    }
+    float ov = bt_overlap_tmp[o];
+    int idx = bt_idx_tmp[o];
+    // box_utils.py:146-150: best_truth_overlap[best_prior_idx] = 2; ascending j, last j wins
+    for (int g = 0; g < G; ++g)
+        if (s_bp[g] == p) { idx = g; ov = 2.0f; }
+    const float4 m = __ldg(truths + (size_t)b * Gmax + idx);
+    const float lab = __ldg(labels + (size_t)b * Gmax + idx);
+    long long conf;
+    if (label_mode == 1) conf = (lab >= 0.0f) ? 1 : 0;          // refinedet_multibox_loss.py:78-79
+    else if (label_mode == 2) conf = (long long)(lab + 1.0f);   // box_utils.py:107
+    else conf = (long long)lab;                                 // box_utils.py:152-156
+    if (ov < threshold) conf = 0;                               // box_utils.py:158
+    float4 pr = __ldg(priors + p);
+    float4 ref = pr;
+    if (arm_loc) ref = center_size_box(decode_box(ldg_stream4(arm_loc + o), pr, v0, v1));   // :157
+    loc_t[o] = encode_box(m, ref, v0, v1);
+    conf_t[o] = conf;
+    if (out_bt_idx) out_bt_idx[o] = idx;
+    if (out_bt_overlap) out_bt_overlap[o] = ov;
+}
+
+// ---------------------------------------------------------------------------------------
+// hard-negative mining: neg = the num_neg largest loss_c of the row (positives count as 0)
+// ---------------------------------------------------------------------------------------
+constexpr int kHnmThreads = 1024;
+
+__global__ void __launch_bounds__(kHnmThreads)
+hnm_select_kernel(const float* __restrict__ loss_c, const unsigned char* __restrict__ pos, int P, int ratio,
+                  unsigned char* __restrict__ neg_out, int* __restrict__ num_pos_out) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_misc[4];   // 0 digit, 1 need, 2 done, 3 num_pos
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* row = loss_c + (size_t)b * P;
+    const unsigned char* prow = pos + (size_t)b * P;
+    unsigned char* nrow = neg_out + (size_t)b * P;
+    if (tid == 0) s_misc[3] = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < P; i += kHnmThreads) local += prow[i] ? 1 : 0;
+    local = __reduce_add_sync(kFullMask, local);
+    if (lane == 0 && local) atomicAdd(&s_misc[3], (uint32_t)local);
+    __syncthreads();
+    const int num_pos = (int)s_misc[3];
+    if (tid == 0 && num_pos_out) num_pos_out[b] = num_pos;
+    long long want = (long long)ratio * num_pos;
+    if (want > P - 1) want = P - 1;                        // torch.clamp(max=P-1), :122
+    int need = (int)(want < 0 ? 0 : want);
+    if (need == 0) {
+        for (int i = tid; i < P; i += kHnmThreads) nrow[i] = 0;
+        return;
+    }
+    unsigned long long prefix = 0, thresh_key = 0;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += kHnmThreads) hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < P; i += kHnmThreads) {
+            float v = prow[i] ? 0.0f : row[i];             // loss_c[pos] = 0, :117
+            unsigned long long k = make_key(v, (uint32_t)i);
+            if (shift == 56 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t loc[8], s = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { loc[q] = hist[lane * 8 + q]; s += loc[q]; }
+            uint32_t v = s;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_down_sync(kFullMask, v, d);
+                if (lane + d < 32) v += o;
+            }
+            uint32_t cum = v - s;
+            int found = -1;
+            uint32_t new_need = 0;
+#pragma unroll
+            for (int q = 7; q >= 0; --q) {
+                if (found < 0 && cum < (uint32_t)need && cum + loc[q] >= (uint32_t)need) {
+                    found = lane * 8 + q;
+                    new_need = (uint32_t)need - cum;
+                }
+                cum += loc[q];
+            }
+            if (found >= 0) {
+                s_misc[0] = (uint32_t)found;
+                s_misc[1] = new_need;
+                s_misc[2] = (hist[found] == new_need) ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+        prefix = (prefix << 8) | s_misc[0];
+        need = (int)s_misc[1];
+        const bool done = s_misc[2] != 0;
+        __syncthreads();
+        if (done || shift == 0) { thresh_key = prefix << shift; break; }
+    }
+    for (int i = tid; i < P; i += kHnmThreads) {
+        float v = prow[i] ? 0.0f : row[i];
+        nrow[i] = make_key(v, (uint32_t)i) >= thresh_key ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// element-wise box_utils functions
+// ---------------------------------------------------------------------------------------
+enum { OP_POINT_FORM = 0, OP_CENTER_SIZE = 1 };
+template <int OP>
+__global__ void unary_box_kernel(const float4* __restrict__ in, float4* __restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 b = in[i];
+    out[i] = OP == OP_POINT_FORM ? point_form_box(b) : center_size_box(b);
+}
+template <bool ENCODE>
+__global__ void coder_kernel(const float4* __restrict__ a, const float4* __restrict__ priors, float v0, float v1,
+                             float4* __restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = ENCODE ? encode_box(a[i], priors[i], v0, v1) : decode_box(a[i], priors[i], v0, v1);
+}
+template <bool IOU>
+__global__ void pairwise_kernel(const float4* __restrict__ box_a, const float4* __restrict__ box_b,
+                                float* __restrict__ out, int A, int Bn) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= Bn || i >= A) return;
+    float4 a = __ldg(box_a + i), b = box_b[j];
+    out[(size_t)i * Bn + j] = IOU ? jaccard_pair(a, b) : intersect_pair(a, b);
+}
+
+}  // namespace rd
+
+using namespace rd;
+
+extern "C" {
+
+#define RD_ALIGNED16(p) ((((uintptr_t)(p)) & 15) == 0)
+
+int rd_point_form(const float* boxes, float* out, int n, void* stream) {
+    if (n == 0) return 0;
+    if (!boxes || !out || n < 0) return RD_ERR_BAD_ARG;
+    if (!RD_ALIGNED16(boxes) || !RD_ALIGNED16(out)) return RD_ERR_ALIGNMENT;
+    unary_box_kernel<OP_POINT_FORM><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes, (float4*)out, n);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+int rd_center_size(const float* boxes, float* out, int n, void* stream) {
+    if (n == 0) return 0;
+    if (!boxes || !out || n < 0) return RD_ERR_BAD_ARG;
+    if (!RD_ALIGNED16(boxes) || !RD_ALIGNED16(out)) return RD_ERR_ALIGNMENT;
+    unary_box_kernel<OP_CENTER_SIZE><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes, (float4*)out, n);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+int rd_decode(const float* loc, const float* priors, float v0, float v1, float* out, int n, void* stream) {
+    if (n == 0) return 0;
+    if (!loc || !priors || !out || n < 0) return RD_ERR_BAD_ARG;
+    if (!RD_ALIGNED16(loc) || !RD_ALIGNED16(priors) || !RD_ALIGNED16(out)) return RD_ERR_ALIGNMENT;
+    coder_kernel<false><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)loc, (const float4*)priors, v0, v1, (float4*)out, n);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+int rd_encode(const float* matched, const float* priors, float v0, float v1, float* out, int n, void* stream) {
+    if (n == 0) return 0;
+    if (!matched || !priors || !out || n < 0) return RD_ERR_BAD_ARG;
+    if (!RD_ALIGNED16(matched) || !RD_ALIGNED16(priors) || !RD_ALIGNED16(out)) return RD_ERR_ALIGNMENT;
+    coder_kernel<true><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)matched, (const float4*)priors, v0, v1, (float4*)out, n);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+static int pairwise(bool iou, const float* box_a, const float* box_b, float* out, int A, int Bn, void* stream) {
+    if (A == 0 || Bn == 0) return 0;
+    if (!box_a || !box_b || !out || A < 0 || Bn < 0) return RD_ERR_BAD_ARG;
+    if (A > 65535) return RD_ERR_UNSUPPORTED;
+    if (!RD_ALIGNED16(box_a) || !RD_ALIGNED16(box_b)) return RD_ERR_ALIGNMENT;
+    dim3 grid((Bn + 255) / 256, A);
+    if (iou) pairwise_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)box_a, (const float4*)box_b, out, A, Bn);
+    else pairwise_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)box_a, (const float4*)box_b, out, A, Bn);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+int rd_intersect(const float* box_a, const float* box_b, float* out, int A, int Bn, void* stream) {
+    return pairwise(false, box_a, box_b, out, A, Bn, stream);
+}
+int rd_jaccard(const float* box_a, const float* box_b, float* out, int A, int Bn, void* stream) {
+    return pairwise(true, box_a, box_b, out, A, Bn, stream);
+}
+
+size_t rd_match_workspace_bytes(int B, int Gmax) {
+    if (B <= 0 || Gmax <= 0) return 256;
+    return ((size_t)B * Gmax * 8 + 255) / 256 * 256;
+}
+
+int rd_refine_match(const float* truths, const float* labels, const int* gt_count, const float* priors,
+                    const float* arm_loc, int B, int P, int Gmax, float threshold, float v0, float v1,
+                    int label_mode, void* workspace, size_t workspace_bytes, float* loc_t, long long* conf_t,
+                    int* best_truth_idx, float* best_truth_overlap, void* stream) {
+    if (!truths || !labels || !gt_count || !priors || !workspace || !loc_t || !conf_t) return RD_ERR_BAD_ARG;
+    if (B <= 0 || P <= 0 || Gmax <= 0 || label_mode < 0 || label_mode > 2) return RD_ERR_BAD_ARG;
+    if (Gmax > RD_MAX_GT || B > 65535) return RD_ERR_UNSUPPORTED;
+    if (!RD_ALIGNED16(truths) || !RD_ALIGNED16(priors) || !RD_ALIGNED16(loc_t) || (arm_loc && !RD_ALIGNED16(arm_loc)) ||
+        !RD_ALIGNED16(workspace) || (((uintptr_t)conf_t) & 7))
+        return RD_ERR_ALIGNMENT;
+    if (workspace_bytes < rd_match_workspace_bytes(B, Gmax)) return RD_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* best_prior = (unsigned long long*)workspace;
+    cudaError_t e = cudaMemsetAsync(best_prior, 0, (size_t)B * Gmax * 8, st);
+    if (e != cudaSuccess) return (int)e;
+    // best_truth_idx / best_truth_overlap are outputs AND the scratch between the two passes
+    if (!best_truth_idx || !best_truth_overlap) return RD_ERR_BAD_ARG;
+    dim3 grid((P + kMatchThreads - 1) / kMatchThreads, B);
+    float* tmp_ov = best_truth_overlap;
+    int* tmp_idx = best_truth_idx;
+    match_pass1_kernel<<<grid, kMatchThreads, (size_t)Gmax * 24, st>>>(
+        (const float4*)truths, gt_count, (const float4*)priors, (const float4*)arm_loc, P, Gmax, v0, v1, best_prior,
+        tmp_ov, tmp_idx);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    match_pass2_kernel<<<grid, kMatchThreads, (size_t)Gmax * 4, st>>>(
+        (const float4*)truths, labels, gt_count, (const float4*)priors, (const float4*)arm_loc, P, Gmax, threshold,
+        v0, v1, label_mode, best_prior, tmp_ov, tmp_idx, (float4*)loc_t, conf_t, best_truth_idx, best_truth_overlap);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+int rd_hnm_select(const float* loss_c, const unsigned char* pos, int B, int P, int negpos_ratio,
+                  unsigned char* neg_out, int* num_pos_out, void* stream) {
+    if (!loss_c || !pos || !neg_out || B <= 0 || P <= 0 || negpos_ratio < 0) return RD_ERR_BAD_ARG;
+    hnm_select_kernel<<<B, kHnmThreads, 0, (cudaStream_t)stream>>>(loss_c, pos, P, negpos_ratio, neg_out, num_pos_out);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+int rd_abi_version(void) { return RD_ABI_VERSION; }
+
+const char* rd_error_string(int code) {
+    switch (code) {
+        case 0: return "success";
+        case RD_ERR_BAD_ARG: return "refinedet_b200: bad argument (null pointer or non-positive size)";
+        case RD_ERR_ALIGNMENT: return "refinedet_b200: tensor is not 16-byte aligned";
+        case RD_ERR_UNSUPPORTED: return "refinedet_b200: size beyond the supported limit";
+        case RD_ERR_WORKSPACE: return "refinedet_b200: workspace too small";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "refinedet_b200: unknown error";
+}
+
+}  // extern "C"

@@ -1,0 +1,171 @@
+"""Drop-in for ``layers/functions/detection_refinedet.py`` (reference :7-113).
+
+``Detect_RefineDet`` keeps the reference's constructor and the two methods
+``models/refinedet.py:141`` and the eval scripts call (``forward``,
+``forward_python_nms``) and adds the fused detect stage the metric is quoted on
+(``detect``: Detect_RefineDet.forward + the per-class loop of
+``eval_refinedet_coco.py:205-232`` in three kernel launches, inputs read once).
+"""
+import torch
+
+from .. import box_utils  # noqa: F401  (kept importable like the reference module)
+from ... import _ffi
+from ..._ffi import check, lib, ptr, require_cuda_f32, stream_ptr
+
+# data/config.py:103,115 — the only field of the config this layer reads (:25)
+_VARIANCE = {'320': [0.1, 0.2], '512': [0.1, 0.2]}
+
+
+class Detections(object):
+    """Result of the fused detect stage.
+
+    ``counts[B,C]`` int32, ``dets[B,C,max_out,5]`` f32 (only the first ``counts[b,c]``
+    rows of a slot are meaningful), ``anchors[B,C,max_out]`` int32 anchor index per row."""
+
+    def __init__(self, counts, dets, anchors, row_layout):
+        self.counts, self.dets, self.anchors, self.row_layout = counts, dets, anchors, row_layout
+
+    def packed(self):
+        """``(offsets[B*C+1] int32, rows[total,5])`` — one device pass, one host sync."""
+        B, C, max_out, _ = self.dets.shape
+        dev = self.dets.device
+        offsets = torch.empty(B * C + 1, dtype=torch.int32, device=dev)
+        rows = torch.empty(B * C * max_out, 5, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().rd_pack_detections(ptr(self.counts), ptr(self.dets), B, C, max_out, ptr(offsets),
+                                           ptr(rows), rows.shape[0], stream_ptr()), 'rd_pack_detections')
+        total = int(offsets[-1].item())
+        return offsets, rows[:total]
+
+    def to_all_boxes(self):
+        """``all_boxes[c][b]`` numpy arrays ``[n,5]`` as built by eval_refinedet_coco.py:214-232."""
+        counts = self.counts.cpu().numpy()
+        dets = self.dets.cpu().numpy()
+        B, C = counts.shape
+        return [[dets[b, c, :counts[b, c]].copy() for b in range(B)] for c in range(C)]
+
+
+class Detect_RefineDet(object):
+    """At test time, the final layer of RefineDet: ARM-objectness filter, two-stage decode
+    and (in ``detect`` / ``forward_python_nms``) per-class threshold, top-k and NMS.
+
+    Constructor arguments are the reference's (detection_refinedet.py:13-25)."""
+
+    def __init__(self, num_classes, size, bkg_label, top_k, conf_thresh, nms_thresh,
+                 objectness_thre, keep_top_k):
+        self.num_classes = num_classes
+        self.background_label = bkg_label
+        self.top_k = top_k
+        self.keep_top_k = keep_top_k
+        self.nms_thresh = nms_thresh
+        if nms_thresh <= 0:
+            raise ValueError('nms_threshold must be non negative.')
+        self.conf_thresh = conf_thresh
+        self.objectness_thre = objectness_thre
+        self.variance = _VARIANCE[str(size)]
+        self._ws = None
+        self._ws_key = None
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _inputs(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data):
+        arm_loc = require_cuda_f32(arm_loc_data, 'arm_loc_data')
+        arm_conf = require_cuda_f32(arm_conf_data, 'arm_conf_data', align=8)
+        odm_loc = require_cuda_f32(odm_loc_data, 'odm_loc_data')
+        odm_conf = require_cuda_f32(odm_conf_data, 'odm_conf_data')
+        priors = require_cuda_f32(prior_data, 'prior_data')
+        B = odm_loc.shape[0]
+        P = priors.shape[0]
+        C = self.num_classes
+        if tuple(arm_loc.shape) != (B, P, 4) or tuple(odm_loc.shape) != (B, P, 4):
+            raise ValueError('loc tensors must be [B,P,4] with P = prior_data.size(0)')
+        if arm_conf.numel() != B * P * 2 or odm_conf.numel() != B * P * C:
+            raise ValueError('conf tensors must hold [B,P,2] and [B,P,num_classes] values')
+        return arm_loc, arm_conf, odm_loc, odm_conf, priors, B, P, C
+
+    def _workspace(self, B, P, C, device):
+        key = (B, P, C, device)
+        if self._ws_key != key:
+            L = lib()
+            nbytes = int(L.rd_detect_workspace_bytes(B, P, C))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                check(L.rd_detect_workspace_reset(ptr(ws), nbytes, stream_ptr()), 'rd_detect_workspace_reset')
+            self._ws, self._ws_key = ws, key
+        return self._ws
+
+    # -- reference API ---------------------------------------------------------------------
+    def forward(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data):
+        """detection_refinedet.py:27-65.  Returns ``(boxes[B,P,4], scores[B,P,C])`` and, like
+        the reference (:40-42), zeroes the ARM-filtered rows of the caller's ``odm_conf_data``
+        in place."""
+        arm_loc, arm_conf, odm_loc, odm_conf, priors, B, P, C = self._inputs(
+            arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data)
+        dev = odm_loc.device
+        boxes = torch.empty(B, P, 4, dtype=torch.float32, device=dev)
+        scores = torch.empty(B, P, C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().rd_detect_forward(ptr(arm_loc), ptr(arm_conf), ptr(odm_loc), ptr(odm_conf), ptr(priors),
+                                          B, P, C, float(self.objectness_thre), float(self.variance[0]),
+                                          float(self.variance[1]), ptr(boxes), ptr(scores), stream_ptr()),
+                  'rd_detect_forward')
+        if odm_conf.data_ptr() != odm_conf_data.data_ptr():      # a copy was made: mirror the in-place write
+            odm_conf_data.detach().copy_(odm_conf.view(odm_conf_data.shape))
+        self.boxes, self.scores = boxes, scores                  # the reference keeps them on the instance
+        return self.boxes, self.scores
+
+    def detect(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale=None,
+               force_cpu_semantics=False):
+        """Fused detect stage as evaluated (eval_refinedet_coco.py:205-232), whole batch:
+        ARM filter, two-stage decode, ``boxes *= scale``, per class ``score > conf_thresh``,
+        top ``top_k``, pixel(+1) NMS at ``nms_thresh``, first ``keep_top_k`` rows per class.
+
+        ``scale``: None, a 4-vector, or ``[B,4]`` (x,y,x,y image size).  The inputs are NOT
+        modified.  Returns a :class:`Detections` with rows ``x1,y1,x2,y2,score``."""
+        flags = _ffi.RD_NMS_PIXEL_PLUS1 | (_ffi.RD_NMS_SUPPRESS_EQ if force_cpu_semantics else 0)
+        return self._fused(arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale, flags,
+                           _ffi.RD_ROW_BOX_SCORE, self.keep_top_k)
+
+    def _fused(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale, flags,
+               row_layout, max_out, dets=None):
+        arm_loc, arm_conf, odm_loc, odm_conf, priors, B, P, C = self._inputs(
+            arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data)
+        dev = odm_loc.device
+        if self.top_k > _ffi.RD_MAX_NMS_BOXES:
+            raise RuntimeError('top_k = %d exceeds the supported %d' % (self.top_k, _ffi.RD_MAX_NMS_BOXES))
+        max_out = max(1, min(int(max_out), int(self.top_k)))
+        if scale is not None:
+            scale = torch.as_tensor(scale, dtype=torch.float32).to(dev)
+            scale = scale.reshape(1, 4).expand(B, 4).contiguous() if scale.numel() == 4 else scale.reshape(B, 4).contiguous()
+        ws = self._workspace(B, P, C, dev)
+        counts = torch.empty(B, C, dtype=torch.int32, device=dev)
+        if dets is None:
+            dets = torch.empty(B, C, max_out, 5, dtype=torch.float32, device=dev)
+        anchors = torch.empty(B, C, max_out, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().rd_detect_fused(ptr(arm_loc), ptr(arm_conf), ptr(odm_loc), ptr(odm_conf), ptr(priors),
+                                        B, P, C, float(self.objectness_thre), float(self.conf_thresh),
+                                        float(self.nms_thresh), int(self.top_k), max_out, ptr(scale), int(flags),
+                                        int(row_layout), float(self.variance[0]), float(self.variance[1]),
+                                        ptr(ws), ws.numel(), ptr(counts), ptr(dets), ptr(anchors), stream_ptr()),
+                  'rd_detect_fused')
+        return Detections(counts, dets, anchors, row_layout)
+
+    def forward_python_nms(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data):
+        """detection_refinedet.py:67-113.  Returns ``output[B,C,top_k,5]`` rows
+        ``(score,x1,y1,x2,y2)``, zero padded, class 0 empty; NMS on normalised boxes without
+        the +1 convention (box_utils.nms).  Like the reference it zeroes the ARM-filtered rows
+        of ``odm_conf_data`` in place; the reference's cross-class ``keep_top_k`` step
+        (:109-112) fills a temporary and has no effect, so it is not performed."""
+        B = odm_loc_data.shape[0]
+        output = torch.zeros(B, self.num_classes, self.top_k, 5, dtype=torch.float32,
+                             device=odm_loc_data.device)
+        res = self._fused(arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, None,
+                          _ffi.RD_NMS_NORMALISED, _ffi.RD_ROW_SCORE_BOX, self.top_k, dets=output)
+        self.last_detections = res
+        # in-place ARM zeroing of the caller's tensor (:79-81)
+        arm_obj = arm_conf_data.detach().reshape(B, -1, 2)[:, :, 1:]
+        conf_view = odm_conf_data.detach().view(B, -1, self.num_classes)
+        conf_view.masked_fill_(arm_obj <= self.objectness_thre, 0)
+        return output
+
+    __call__ = forward
