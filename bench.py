@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — RefineDet512 detect-stage throughput (decode + NMS) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload sparse|dense] [--impl reference]
+
+A *step* is one pass of the detect stage (ARM filter, two-stage decode, per-class threshold,
+top-k 1000, pixel NMS 0.45, keep 500/class) over a batch of 32 synthetic images of
+BASELINE.json config 3 (P = 16,320 anchors, C = 81 classes); every rank owns its own batch
+(weak scaling, no data-path collective).  One JSON line on stdout (rank 0):
+
+  value        images/s, device time (CUDA events), inputs resident in HBM, L2 flushed and
+               input buffers rotated between steps, max over ranks
+  e2e          images/s through the public API with HOST (pinned) inputs: H2D copies, the three
+               kernels, packing, D2H of counts + packed rows, all inside the timed region
+  roofline     algorithmic bytes of the stage (5,940,480 B/image) / device time
+               of the stage's kernels, against MEASURED_PEAKS.json hbm_gbs; per-kernel shares
+  cpu_baseline the numpy oracle (port of the reference's CPU path) on a bounded sample
+  clocks       SM clock / throttle reasons sampled through NVML during the timed regions
+
+``--impl reference`` times the CPU port of the reference path (oracle/) on the box's host
+cores and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = 'RefineDet512 detect-stage images/s (decode+NMS)'
+UNIT = 'images/s'
+SIZE, P, C, BATCH = '512', 16320, 81, 32
+TOP_K, KEEP_TOP_K, CONF_THR, NMS_THR, OBJ_THR = 1000, 500, 0.01, 0.45, 0.01
+BYTES_PER_IMAGE = 4 * P * (4 + 2 + 4 + C)           # SURVEY.md §8d, + 20 B per kept row (added at run time)
+NBUF = 4                                             # rotated input sets (4 x 190 MB > L2)
+
+
+def seed_for(rank, buf=0):
+    return 1234 + 1000 * 3 + rank + 100 * buf        # 1234 + 1000*config + rank
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """Polls NVML (SM clock, throttle reasons) from a thread while a timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._active = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self._err = repr(e)
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
+        if self._h is None:
+            return
+        nv = self._nv
+        names = {
+            getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8): 'hw_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+            getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4): 'sw_power_cap',
+            getattr(nv, 'nvmlClocksThrottleReasonHwPowerBrakeSlowdown', 0x80): 'hw_power_brake_slowdown',
+        }
+        while not self._stop.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        self._active.set()
+        return self
+
+    def __exit__(self, *a):
+        self._active.clear()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': (s[len(s) // 2] if s else None), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU port of the reference path (oracle) — the cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
+def _cpu_one_image(args):
+    """One image through the reference's CPU path: Detect_RefineDet.forward +
+    eval_refinedet_coco.py:205-232 (numpy port in oracle/box_oracle.py)."""
+    seed, kind = args
+    from oracle import box_oracle as bo
+    from refinedet.pytorch_b200 import synthetic
+    key = (seed, kind)
+    if key not in _CPU_CACHE:
+        torch.set_num_threads(1)
+        a = [t.numpy() for t in synthetic.detect_inputs(seed, 1, P, C, kind)]
+        _CPU_CACHE.clear()
+        _CPU_CACHE[key] = a + [bo.prior_box(bo.REFINEDET_CFG[SIZE])]
+        return 0.0                                            # warm-up call: inputs only
+    arm_loc, arm_conf, odm_loc, odm_conf, priors = _CPU_CACHE[key]
+    t0 = time.perf_counter()
+    boxes, scores = bo.detect_forward(arm_loc, arm_conf, odm_loc, odm_conf.copy(), priors, OBJ_THR)
+    bo.detect_stage_eval(boxes[0], scores[0], np.array([512.0] * 4, np.float32), CONF_THR, TOP_K, NMS_THR,
+                         KEEP_TOP_K)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_run(kind, steps, warmup, cores, budget_s=None):
+    """Each step = `cores` images, one per worker process.  Returns (images/s, steps done, sample)."""
+    import multiprocessing as mp
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        jobs = [(seed_for(0) + 7 * w, kind) for w in range(cores)]
+        pool.map(_cpu_one_image, jobs, chunksize=1)           # generate inputs in the workers
+        for _ in range(warmup):
+            pool.map(_cpu_one_image, jobs, chunksize=1)
+        t_begin = time.perf_counter()
+        done = 0
+        for _ in range(steps):
+            pool.map(_cpu_one_image, jobs, chunksize=1)
+            done += 1
+            if budget_s is not None and time.perf_counter() - t_begin > budget_s:
+                break
+        elapsed = time.perf_counter() - t_begin
+    return cores * done / elapsed, done, elapsed
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--workload', default='sparse', choices=['sparse', 'dense'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    cores = max(1, len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1))
+    workload = 'RefineDet512 COCO detect stage: B=%d/GPU, P=%d, C=%d, top_k=%d, keep_top_k=%d, %s generator' % (
+        BATCH, P, C, TOP_K, KEEP_TOP_K, args.workload)
+    config = {'workload': workload, 'batch_per_gpu': BATCH, 'anchors': P, 'classes': C, 'generator': args.workload,
+              'sharding': 'images sharded by rank, no data-path collective'}
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        steps = max(1, args.steps)
+        value, done, elapsed = cpu_reference_run(args.workload, steps, max(0, args.warmup), cores, budget_s=150.0)
+        sample = '%d steps x %d images (1 per worker process), numpy port of Detect_RefineDet.forward + ' \
+                 'eval_refinedet_coco.py:205-232 with py_cpu_nms semantics' % (done, cores)
+        line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+                'steps': done, 'warmup': args.warmup, 'ms_per_step': 1e3 * elapsed / done,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': config,
+                'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+                'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+                'gpu_launches': 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---- native arm -------------------------------------------------------------------------
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py (native arm) needs a CUDA device: there is no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    import refinedet.pytorch_b200 as rd
+    from refinedet.pytorch_b200 import _ffi, synthetic
+    _ffi.lib()
+
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS[SIZE]).forward().to(dev)
+    host_sets = [[t.pin_memory() for t in synthetic.detect_inputs(seed_for(rank, i), BATCH, P, C, args.workload)]
+                 for i in range(NBUF)]
+    dev_sets = [[t.to(dev) for t in hs] for hs in host_sets]
+    arm_pass = float((host_sets[0][1][..., 1] > OBJ_THR).float().mean())
+    scale = torch.tensor([512.0] * 4, device=dev).reshape(1, 4).expand(BATCH, 4).contiguous()
+    det = rd.Detect_RefineDet(C, 512, 0, TOP_K, CONF_THR, NMS_THR, OBJ_THR, KEEP_TOP_K)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    clocks = ClockSampler(local_rank)
+
+    def step(i):
+        a = dev_sets[i % NBUF]
+        return det.detect(a[0], a[1], a[2], a[3], priors, scale=scale)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        res = step(i)
+    torch.cuda.synchronize()
+    kept_rows = int(res.counts.sum())
+
+    # timed region: K steps, each bracketed by events; L2 flushed (untimed) before every step
+    K = max(1, args.steps)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    barrier()
+    launches0 = _ffi.launch_count()
+    with clocks:
+        for i in range(K):
+            flush.zero_()
+            starts[i].record()
+            step(i)
+            stops[i].record()
+        barrier()
+    launches = _ffi.launch_count() - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = float(sum(step_ms))
+    if dist is not None:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = world * BATCH * K / (total_ms * 1e-3)
+
+    # per-kernel breakdown (separate pass: stage events recorded between the kernels)
+    kern = det.profile_stage(dev_sets, priors, scale, flush, steps=min(K, 20))
+    stage_ms = sum(kern.values())
+    bytes_per_launch = BATCH * BYTES_PER_IMAGE + 20 * kept_rows
+    peak, peak_src = measured_peak()
+    achieved = bytes_per_launch / (stage_ms * 1e-3) / 1e9
+    dominant = max(kern, key=kern.get)
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': None, 'peak_source': peak_src, 'kernel': dominant,
+                'algorithmic_bytes_per_launch': bytes_per_launch,
+                'stage_ms': stage_ms,
+                'kernels_ms': kern, 'kernel_share': {k: v / stage_ms for k, v in kern.items()},
+                'note': 'achieved = stage bytes (SURVEY 8d: 4*P*(10+C) B/image + 20 B/kept row) / summed device '
+                        'time of the stage\'s kernels; ARM-filtered anchors (%.1f%% here) are skipped, so DRAM '
+                        'traffic is far below the algorithmic bytes' % (100 * (1 - arm_pass))}
+
+    # e2e: host (pinned) inputs -> H2D -> kernels -> pack -> D2H (counts + packed rows)
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = min(K, 20)
+        stage = [torch.empty_like(t, device=dev) for t in host_sets[0]]
+        h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
+        d2h = 0
+        for i in range(2):
+            det.detect_host(host_sets[i % NBUF], priors, scale, stage)
+        barrier()
+        with clocks:
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                counts_h, rows_h = det.detect_host(host_sets[i % NBUF], priors, scale, stage)
+                d2h = counts_h.numel() * 4 + rows_h.numel() * 4
+            barrier()
+            e2e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e2e_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {'value': world * BATCH * e2e_steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+               'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'ms_per_step': 1e3 * e2e_s / e2e_steps}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, done, elapsed = cpu_reference_run(args.workload, 6, 1, cores, budget_s=25.0)
+        cpu_baseline = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                        'sample': '%d steps x %d images (1 per worker process) of the same workload, %.1f s'
+                                  % (done, cores, elapsed)}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K,
+                'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': dict(config, l2='flushed (512 MiB memset) before every timed step; %d rotated input '
+                                          'sets' % NBUF, arm_pass_fraction=arm_pass, kept_rows_per_step=kept_rows),
+                'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gpu_launches': int(launches),
+                'clocks': clocks.summary()}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

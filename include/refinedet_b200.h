@@ -118,6 +118,18 @@ RD_API int rd_detect_fused(const float* arm_loc, const float* arm_conf, const fl
                     void* workspace, size_t workspace_bytes,
                     int* out_counts, float* out_dets, int* out_anchor, void* stream);
 
+/* Diagnostics twin of rd_detect_fused: records CUDA events between the stage's kernels on
+ * `stream`, WAITS for the stage, and writes the device time in ms of
+ * {collect_kernel, nms_small_kernel, nms_large_kernel} to stage_ms_host[3] (host pointer). */
+RD_API int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, const float* odm_loc,
+                    const float* odm_conf, const float* priors, int B, int P, int C,
+                    float objectness_thre, float conf_thresh, float nms_thresh,
+                    int top_k, int max_out, const float* img_scale, int nms_flags,
+                    int row_layout, float v0, float v1,
+                    void* workspace, size_t workspace_bytes,
+                    int* out_counts, float* out_dets, int* out_anchor, void* stream,
+                    float* stage_ms_host);
+
 /* compact [B,C,max_out,5] slots into packed rows (score-descending inside a class,
  * classes ascending, images ascending).  out_offsets[B*C+1] = exclusive prefix sum
  * of counts; packed[total,5]; packed_capacity = rows available in `packed`. */

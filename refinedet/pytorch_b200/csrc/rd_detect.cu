@@ -423,11 +423,13 @@ int rd_detect_workspace_reset(void* workspace, size_t workspace_bytes, void* str
     return (int)e;
 }
 
-int rd_detect_fused(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
+}  // extern "C"
+
+static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
                     const float* priors, int B, int P, int C, float objectness_thre, float conf_thresh,
                     float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
                     int row_layout, float v0, float v1, void* workspace, size_t workspace_bytes,
-                    int* out_counts, float* out_dets, int* out_anchor, void* stream) {
+                    int* out_counts, float* out_dets, int* out_anchor, void* stream, cudaEvent_t* ev) {
     if (!arm_loc || !arm_conf || !odm_loc || !odm_conf || !priors || !workspace || !out_counts || !out_dets)
         return RD_ERR_BAD_ARG;
     if (B <= 0 || P <= 0 || C <= 0 || top_k <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
@@ -443,6 +445,7 @@ int rd_detect_fused(const float* arm_loc, const float* arm_conf, const float* od
     const long long total = (long long)B * P;
     const long long warps = (total + 31) / 32;
     const int blocks = (int)((warps * 32 + kCollectThreads - 1) / kCollectThreads);
+    if (ev) cudaEventRecord(ev[0], st);
     collect_kernel<<<blocks, kCollectThreads, 0, st>>>(
         (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
         total, P, C, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.header);
@@ -463,9 +466,11 @@ int rd_detect_fused(const float* arm_loc, const float* arm_conf, const float* od
         if (s_dev_sms <= 0) s_dev_sms = 148;
     }
     const NmsSmemLayout Ls = nms_layout(kSmallCap);
+    if (ev) cudaEventRecord(ev[1], st);
     nms_small_kernel<<<B * C, kNmsThreads, Ls.total, st>>>(A);
     note_launch();
     RD_CHECK_LAUNCH();
+    if (ev) cudaEventRecord(ev[2], st);
     if (top_k > kSmallCap) {
         const int mcap = top_k < P ? top_k : P;
         const NmsSmemLayout Ll = nms_layout(mcap);
@@ -485,7 +490,46 @@ int rd_detect_fused(const float* arm_loc, const float* arm_conf, const float* od
         note_launch();
         RD_CHECK_LAUNCH();
     }
+    if (ev) cudaEventRecord(ev[3], st);
     return 0;
+}
+
+extern "C" {
+
+int rd_detect_fused(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
+                    const float* priors, int B, int P, int C, float objectness_thre, float conf_thresh,
+                    float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
+                    int row_layout, float v0, float v1, void* workspace, size_t workspace_bytes,
+                    int* out_counts, float* out_dets, int* out_anchor, void* stream) {
+    return detect_fused_impl(arm_loc, arm_conf, odm_loc, odm_conf, priors, B, P, C, objectness_thre, conf_thresh,
+                             nms_thresh, top_k, max_out, img_scale, nms_flags, row_layout, v0, v1, workspace,
+                             workspace_bytes, out_counts, out_dets, out_anchor, stream, nullptr);
+}
+
+int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
+                          const float* priors, int B, int P, int C, float objectness_thre, float conf_thresh,
+                          float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
+                          int row_layout, float v0, float v1, void* workspace, size_t workspace_bytes,
+                          int* out_counts, float* out_dets, int* out_anchor, void* stream, float* stage_ms_host) {
+    if (!stage_ms_host) return RD_ERR_BAD_ARG;
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; ++i) {
+        cudaError_t e = cudaEventCreate(&ev[i]);
+        if (e != cudaSuccess) return (int)e;
+    }
+    int rc = detect_fused_impl(arm_loc, arm_conf, odm_loc, odm_conf, priors, B, P, C, objectness_thre, conf_thresh,
+                               nms_thresh, top_k, max_out, img_scale, nms_flags, row_layout, v0, v1, workspace,
+                               workspace_bytes, out_counts, out_dets, out_anchor, stream, ev);
+    if (rc == 0) {
+        cudaError_t e = cudaEventSynchronize(ev[3]);
+        if (e != cudaSuccess) rc = (int)e;
+        for (int i = 0; i < 3 && rc == 0; ++i) {
+            e = cudaEventElapsedTime(&stage_ms_host[i], ev[i], ev[i + 1]);
+            if (e != cudaSuccess) rc = (int)e;
+        }
+    }
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    return rc;
 }
 
 int rd_pack_detections(const int* counts, const float* dets, int B, int C, int max_out, int* out_offsets,

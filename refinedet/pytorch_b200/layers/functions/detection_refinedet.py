@@ -125,8 +125,39 @@ class Detect_RefineDet(object):
         return self._fused(arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale, flags,
                            _ffi.RD_ROW_BOX_SCORE, self.keep_top_k)
 
+    def detect_host(self, host_inputs, prior_data, scale=None, staging=None):
+        """End-to-end form of :meth:`detect` for HOST inputs (pinned tensors
+        ``arm_loc, arm_conf, odm_loc, odm_conf``): asynchronous H2D copies into ``staging``
+        (device buffers, allocated when None), the fused stage, device-side packing, and D2H of
+        ``counts[B,C]`` and the packed rows ``[total,5]``.  Returns CPU tensors."""
+        dev = prior_data.device
+        if staging is None:
+            staging = [torch.empty_like(t, device=dev) for t in host_inputs]
+        for d, h in zip(staging, host_inputs):
+            d.copy_(h, non_blocking=True)
+        res = self.detect(staging[0], staging[1], staging[2], staging[3], prior_data, scale=scale)
+        offsets, rows = res.packed()
+        return res.counts.cpu(), rows.cpu()
+
+    def profile_stage(self, input_sets, prior_data, scale, flush=None, steps=10):
+        """Device time (ms, mean over ``steps``) of each kernel of the fused stage, measured with
+        CUDA events recorded between the launches (``rd_detect_fused_timed``)."""
+        import ctypes
+        names = ('collect_kernel', 'nms_small_kernel', 'nms_large_kernel')
+        acc = [0.0, 0.0, 0.0]
+        ms = (ctypes.c_float * 3)()
+        for i in range(steps):
+            if flush is not None:
+                flush.zero_()
+            a = input_sets[i % len(input_sets)]
+            self._fused(a[0], a[1], a[2], a[3], prior_data, scale, _ffi.RD_NMS_PIXEL_PLUS1, _ffi.RD_ROW_BOX_SCORE,
+                        self.keep_top_k, timed=ms)
+            for k in range(3):
+                acc[k] += float(ms[k])
+        return {n: v / steps for n, v in zip(names, acc)}
+
     def _fused(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale, flags,
-               row_layout, max_out, dets=None):
+               row_layout, max_out, dets=None, timed=None):
         arm_loc, arm_conf, odm_loc, odm_conf, priors, B, P, C = self._inputs(
             arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data)
         dev = odm_loc.device
@@ -141,13 +172,18 @@ class Detect_RefineDet(object):
         if dets is None:
             dets = torch.empty(B, C, max_out, 5, dtype=torch.float32, device=dev)
         anchors = torch.empty(B, C, max_out, dtype=torch.int32, device=dev)
+        args = (ptr(arm_loc), ptr(arm_conf), ptr(odm_loc), ptr(odm_conf), ptr(priors),
+                B, P, C, float(self.objectness_thre), float(self.conf_thresh),
+                float(self.nms_thresh), int(self.top_k), max_out, ptr(scale), int(flags),
+                int(row_layout), float(self.variance[0]), float(self.variance[1]),
+                ptr(ws), ws.numel(), ptr(counts), ptr(dets), ptr(anchors))
         with torch.cuda.device(dev):
-            check(lib().rd_detect_fused(ptr(arm_loc), ptr(arm_conf), ptr(odm_loc), ptr(odm_conf), ptr(priors),
-                                        B, P, C, float(self.objectness_thre), float(self.conf_thresh),
-                                        float(self.nms_thresh), int(self.top_k), max_out, ptr(scale), int(flags),
-                                        int(row_layout), float(self.variance[0]), float(self.variance[1]),
-                                        ptr(ws), ws.numel(), ptr(counts), ptr(dets), ptr(anchors), stream_ptr()),
-                  'rd_detect_fused')
+            if timed is None:
+                check(lib().rd_detect_fused(*args, stream_ptr()), 'rd_detect_fused')
+            else:
+                import ctypes
+                check(lib().rd_detect_fused_timed(*args, stream_ptr(), ctypes.cast(timed, ctypes.c_void_p)),
+                      'rd_detect_fused_timed')
         return Detections(counts, dets, anchors, row_layout)
 
     def forward_python_nms(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data):

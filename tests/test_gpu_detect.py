@@ -1,0 +1,335 @@
+"""GPU tier (run on the B200 box: ``pytest -m gpu``): the CUDA detect path, called through the
+C ABI, against (i) the reference-generated golden fixtures, (ii) the numpy oracle on seeded
+inputs, (iii) size-independent properties at BASELINE.json's full size.
+
+Bars: kept-index sets / counts / masks bit-exact; decoded boxes within 1e-5 relative (fp32,
+only ``exp`` differs between CUDA and the CPU libm — SURVEY.md A.1); pure copies exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import box_oracle as bo
+from tests import gen
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6          # north_star: decoded boxes within 1e-5 relative in fp32
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope='module')
+def rd():
+    import refinedet.pytorch_b200 as rd
+    rd._ffi.lib()
+    return rd
+
+
+def load_detect(golden, tag):
+    g = golden('detect_%s.npz' % tag)
+    C, top_k, keep_top_k, conf_thr, nms_thr, obj_thr = g['params']
+    return g, int(C), int(top_k), int(keep_top_k), float(conf_thr), float(nms_thr), float(obj_thr)
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures (outputs of the unmodified reference)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('tag', ['sparse', 'dense'])
+def test_forward_golden(rd, golden, tag):
+    g, C, top_k, keep_top_k, conf_thr, nms_thr, obj_thr = load_detect(golden, tag)
+    det = rd.Detect_RefineDet(C, 320, 0, top_k, conf_thr, nms_thr, obj_thr, keep_top_k)
+    conf = cu(g['odm_conf'])
+    boxes, scores = det.forward(cu(g['arm_loc']), cu(g['arm_conf']), cu(g['odm_loc']), conf, cu(g['priors']))
+    np.testing.assert_allclose(boxes.cpu().numpy(), g['boxes'], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(scores.cpu().numpy(), g['scores'])
+    assert np.array_equal(conf.cpu().numpy(), g['conf_after'])          # in-place ARM zeroing
+    assert scores.data_ptr() != conf.data_ptr()
+
+
+@pytest.mark.parametrize('tag', ['sparse', 'dense'])
+def test_fused_detect_golden_a4(rd, golden, tag):
+    g, C, top_k, keep_top_k, conf_thr, nms_thr, obj_thr = load_detect(golden, tag)
+    det = rd.Detect_RefineDet(C, 320, 0, top_k, conf_thr, nms_thr, obj_thr, keep_top_k)
+    conf = cu(g['odm_conf'])
+    res = det.detect(cu(g['arm_loc']), cu(g['arm_conf']), cu(g['odm_loc']), conf, cu(g['priors']),
+                     scale=g['scale'])
+    assert np.array_equal(conf.cpu().numpy(), g['odm_conf'])            # fused stage never mutates inputs
+    counts = res.counts.cpu().numpy()
+    assert np.array_equal(counts, g['a4_counts'])
+    dets = res.dets.cpu().numpy()
+    B = counts.shape[0]
+    for b in range(B):
+        for c in range(C):
+            n = counts[b, c]
+            ref = g['a4_dets'][b, c, :n]
+            assert np.array_equal(dets[b, c, :n, 4], ref[:, 4])          # scores are copies: exact
+            np.testing.assert_allclose(dets[b, c, :n, :4], ref[:, :4], rtol=RTOL, atol=ATOL * 320)
+
+
+@pytest.mark.parametrize('tag', ['sparse', 'dense'])
+def test_forward_python_nms_golden_a5(rd, golden, tag):
+    g, C, top_k, keep_top_k, conf_thr, nms_thr, obj_thr = load_detect(golden, tag)
+    det = rd.Detect_RefineDet(C, 320, 0, top_k, conf_thr, nms_thr, obj_thr, keep_top_k)
+    conf = cu(g['odm_conf'])
+    out = det.forward_python_nms(cu(g['arm_loc']), cu(g['arm_conf']), cu(g['odm_loc']), conf, cu(g['priors']))
+    out = out.cpu().numpy()
+    ref = g['a5_output']
+    assert out.shape == ref.shape
+    assert np.array_equal(out[..., 0], ref[..., 0])                      # scores + zero padding exact
+    np.testing.assert_allclose(out[..., 1:], ref[..., 1:], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(conf.cpu().numpy(), g['conf_after'])
+
+
+def test_box_utils_golden(rd, golden):
+    g = golden('box_utils.npz')
+    bu = rd.box_utils
+    pri, loc, truths, matched = cu(g['priors']), cu(g['loc']), cu(g['truths']), cu(g['matched'])
+    assert np.array_equal(bu.point_form(pri).cpu().numpy(), g['point_form'])
+    dec = bu.decode(loc, pri, [0.1, 0.2])
+    np.testing.assert_allclose(dec.cpu().numpy(), g['decode'], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(bu.center_size(cu(g['decode'])).cpu().numpy(), g['center_size'])
+    np.testing.assert_allclose(bu.encode(matched, pri, [0.1, 0.2]).cpu().numpy(), g['encode'], rtol=RTOL, atol=ATOL)
+    pf = cu(g['point_form'])
+    assert np.array_equal(bu.intersect(truths, pf).cpu().numpy(), g['intersect'])
+    assert np.array_equal(bu.jaccard(truths, pf).cpu().numpy(), g['jaccard'])
+    assert np.array_equal(bu.jaccard(truths, cu(g['decode'])).cpu().numpy(), g['jaccard_dec'])
+    np.testing.assert_allclose(bu.log_sum_exp(cu(g['x'])).cpu().numpy(), g['log_sum_exp'], rtol=1e-6)
+    # SURVEY.md Appendix B KAT: two-stage decode
+    d1 = bu.decode(cu(g['kat_arm']), cu(g['kat_pri']), [0.1, 0.2])
+    d2 = bu.decode(cu(g['kat_odm']), bu.center_size(d1), [0.1, 0.2])
+    np.testing.assert_allclose(d2.cpu().numpy(), [[0.38644654, 0.45778579, 0.59460866, 0.55483037],
+                                                  [-0.06584629, -0.00404091, 0.07186650, 0.07004091]], rtol=2e-6)
+
+
+def test_nms_box_utils_golden(rd, golden):
+    g = golden('nms_box_utils.npz')
+    bu = rd.box_utils
+    k, c = bu.nms(cu(g['kat_boxes']), cu(g['kat_scores']), 0.45, 200)
+    assert c == 3 and k.tolist() == [3, 4, 5, 0, 0, 0]
+    k, c = bu.nms(cu(g['kat_boxes']), cu(g['kat_scores']), 0.45, 3)
+    assert c == 1 and k.tolist() == [3, 0, 0, 0, 0, 0]
+    e = bu.nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), 0.45, 200)
+    assert isinstance(e, torch.Tensor) and e.numel() == 0 and e.dtype == torch.int64
+    for tag in 'abc':
+        thr, tk = g['args_' + tag]
+        k, c = bu.nms(cu(g['boxes']), cu(g['scores']), float(thr), int(tk))
+        assert c == int(g['count_' + tag])
+        assert np.array_equal(k.cpu().numpy(), g['keep_' + tag])
+
+
+def test_nms_wrapper_golden(rd, golden):
+    g = golden('nms_pixel.npz')
+    nms = rd.nms_wrapper.nms
+    for tag, thr in (('045', 0.45), ('049', 0.49), ('070', 0.7)):
+        assert nms(g['dets'], thr) == list(g['keep_' + tag])              # host ndarray -> rd_nms_host
+        assert nms(cu(g['dets']), thr) == list(g['keep_' + tag])          # device tensor -> rd_nms
+        assert nms(g['dets'], thr, force_cpu=True) == bo.nms_pixel(g['dets'], thr, suppress_on_equal=True)
+    assert nms(np.zeros((0, 5), np.float32), 0.5) == []
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle parity on seeded inputs
+# ---------------------------------------------------------------------------------------------
+def _oracle_a4(boxes, scores, scale, conf_thr, top_k, nms_thr, keep_top_k):
+    B, P, C = scores.shape
+    counts = np.zeros((B, C), np.int32)
+    anchors = {}
+    rows = {}
+    for b in range(B):
+        out, anc = bo.detect_stage_eval(boxes[b], scores[b], scale, conf_thr, top_k, nms_thr, keep_top_k)
+        for c in range(C):
+            counts[b, c] = out[c].shape[0]
+            anchors[b, c] = anc[c]
+            rows[b, c] = out[c]
+    return counts, anchors, rows
+
+
+@pytest.mark.parametrize('kind,B,size,C,top_k,keep', [
+    ('sparse', 3, '320', 21, 1000, 500),
+    ('dense', 2, '320', 21, 400, 200),       # top_k saturates: exercises the radix select + large kernel
+    ('dense', 2, '320', 3, 400, 100),        # keep_top_k cap bites
+    ('sparse', 2, '512', 81, 1000, 500),
+])
+def test_fused_detect_vs_oracle(rd, kind, B, size, C, top_k, keep):
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward()
+    P = priors.shape[0]
+    arm_shift = -3.0 if kind == 'sparse' else 0.0
+    arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs(4242 + B + C, B, P, C, kind, arm_shift=arm_shift)
+    conf_thr, nms_thr, obj_thr = 0.01, 0.45, 0.01
+    det = rd.Detect_RefineDet(C, int(size), 0, top_k, conf_thr, nms_thr, obj_thr, keep)
+    scale = np.array([float(size)] * 4, np.float32)
+    d_in = [t.cuda() for t in (arm_loc, arm_conf, odm_loc, odm_conf)]
+    res = det.detect(*d_in, priors.cuda(), scale=scale)
+    # a3 on the GPU gives the boxes the fused kernel used (same device function -> same bits)
+    conf_a3 = odm_conf.clone().cuda()
+    g_boxes, g_scores = det.forward(d_in[0], d_in[1], d_in[2], conf_a3, priors.cuda())
+    # a3 vs oracle
+    o_conf = odm_conf.numpy().copy()
+    o_boxes, o_scores = bo.detect_forward(arm_loc.numpy(), arm_conf.numpy(), odm_loc.numpy(), o_conf,
+                                          priors.numpy(), obj_thr)
+    np.testing.assert_allclose(g_boxes.cpu().numpy(), o_boxes, rtol=RTOL, atol=ATOL)
+    assert np.array_equal(g_scores.cpu().numpy(), o_scores)
+    assert np.array_equal(conf_a3.cpu().numpy(), o_conf)
+    assert gen.assert_tie_free(o_scores, conf_thr)
+    # a4: oracle NMS fed the GPU's boxes -> kept anchor sets must be bit-exact
+    counts, anchors, rows = _oracle_a4(g_boxes.cpu().numpy(), o_scores, scale, conf_thr, top_k, nms_thr, keep)
+    g_counts = res.counts.cpu().numpy()
+    assert np.array_equal(g_counts, counts)
+    g_anchor = res.anchors.cpu().numpy()
+    g_dets = res.dets.cpu().numpy()
+    for b in range(B):
+        for c in range(C):
+            n = counts[b, c]
+            assert np.array_equal(g_anchor[b, c, :n], anchors[b, c]), (b, c)
+            assert np.array_equal(g_dets[b, c, :n], rows[b, c]), (b, c)
+    assert (g_counts[:, 0] == 0).all()
+    # and against the oracle's own boxes (exp differs by <= 2 ulp): same sets on these inputs
+    counts2, anchors2, _ = _oracle_a4(o_boxes, o_scores, scale, conf_thr, top_k, nms_thr, keep)
+    assert np.array_equal(g_counts, counts2)
+    # second call on the same workspace gives identical results (workspace is left clean)
+    res2 = det.detect(*d_in, priors.cuda(), scale=scale)
+    assert torch.equal(res2.counts, res.counts)
+    for b in range(B):
+        for c in range(C):
+            n = counts[b, c]
+            assert torch.equal(res2.anchors[b, c, :n], res.anchors[b, c, :n])
+
+
+def test_forward_python_nms_vs_oracle(rd):
+    size, C, B, top_k = '320', 5, 2, 200
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward()
+    P = priors.shape[0]
+    arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs(77, B, P, C, 'dense')
+    det = rd.Detect_RefineDet(C, 320, 0, top_k, 0.01, 0.45, 0.01, 50)
+    conf = odm_conf.clone().cuda()
+    out = det.forward_python_nms(arm_loc.cuda(), arm_conf.cuda(), odm_loc.cuda(), conf, priors.cuda())
+    conf2 = odm_conf.clone().cuda()
+    g_boxes, g_scores = det.forward(arm_loc.cuda(), arm_conf.cuda(), odm_loc.cuda(), conf2, priors.cuda())
+    gb, gs = g_boxes.cpu().numpy(), g_scores.cpu().numpy()
+    exp = np.zeros((B, C, top_k, 5), np.float32)
+    for i in range(B):
+        for cl in range(1, C):
+            m = gs[i, :, cl] > np.float32(0.01)
+            if m.sum() == 0:
+                continue
+            ids, count = bo.nms(gb[i][m], gs[i, m, cl], 0.45, top_k)
+            ids = ids[:count]
+            exp[i, cl, :count, 0] = gs[i, m, cl][ids]
+            exp[i, cl, :count, 1:] = gb[i][m][ids]
+    assert np.array_equal(out.cpu().numpy(), exp)
+    assert torch.equal(conf, conf2)
+
+
+@pytest.mark.parametrize('n,top_k,flavour', [(1, 5, 0), (33, 200, 0), (700, 200, 1), (3000, 1000, 1),
+                                             (4096, 4096, 0), (5000, 300, 1)])
+def test_standalone_nms_vs_oracle(rd, n, top_k, flavour):
+    g = torch.Generator().manual_seed(n)
+    if flavour:
+        cxy = 512 * torch.rand(n, 2, generator=g)
+        wh = 10 + 90 * torch.rand(n, 2, generator=g)
+    else:
+        cxy = torch.rand(n, 2, generator=g)
+        wh = 0.03 + 0.2 * torch.rand(n, 2, generator=g)
+    boxes = torch.cat([cxy - wh / 2, cxy + wh / 2], 1)
+    scores = torch.rand(n, generator=g)
+    assert scores.unique().numel() == n
+    if flavour:
+        dets = torch.cat([boxes, scores[:, None]], 1).numpy()
+        order = np.argsort(-dets[:, 4], kind='stable')[:top_k]
+        exp = [int(order[i]) for i in bo.nms_pixel(dets[order], 0.45)]
+        from refinedet.pytorch_b200 import _ffi
+        keep, count = rd.box_utils.nms_device(boxes.cuda(), scores.cuda(), 0.45, top_k, _ffi.RD_NMS_PIXEL_PLUS1)
+        assert keep[:int(count)].tolist() == exp
+    else:
+        ek, ec = bo.nms(boxes.numpy(), scores.numpy(), 0.45, top_k)
+        keep, count = rd.box_utils.nms(boxes.cuda(), scores.cuda(), 0.45, top_k)
+        assert count == ec
+        assert np.array_equal(keep.cpu().numpy(), ek)
+
+
+def test_nms_degenerate_boxes_and_thresholds(rd):
+    """zero-area / inverted / duplicate boxes and thr = 0 take the exact path (no spatial cull)."""
+    boxes = np.array([[0.1, 0.1, 0.5, 0.5], [0.1, 0.1, 0.5, 0.5], [0.7, 0.7, 0.7, 0.9], [0.2, 0.2, 0.2, 0.2],
+                      [0.9, 0.9, 0.8, 0.8], [0.6, 0.1, 0.9, 0.4], [0.61, 0.11, 0.9, 0.4], [0.3, 0.3, 0.6, 0.6]],
+                     np.float32)
+    scores = np.array([0.9, 0.8, 0.7, 0.6, 0.5, 0.4, 0.3, 0.2], np.float32)
+    for thr in (0.0, 0.3, 0.45, 0.99):
+        ek, ec = bo.nms(boxes, scores, thr, 200)
+        keep, count = rd.box_utils.nms(cu(boxes), cu(scores), thr, 200)
+        assert count == ec and np.array_equal(keep.cpu().numpy(), ek), thr
+    dets = np.concatenate([boxes * 300, scores[:, None]], 1).astype(np.float32)
+    for thr in (0.0, 0.3, 0.7):
+        assert rd.nms_wrapper.nms(dets, thr) == bo.nms_pixel(dets, thr)
+        assert rd.nms_wrapper.nms(dets, thr, force_cpu=True) == bo.nms_pixel(dets, thr, suppress_on_equal=True)
+
+
+def test_nms_heavy_overlap_clusters(rd):
+    """many near-duplicates: long suppression chains, kept << n (the cull gives no help)."""
+    g = torch.Generator().manual_seed(5)
+    centres = torch.rand(12, 2, generator=g) * 400 + 50
+    idx = torch.randint(0, 12, (2000,), generator=g)
+    cxy = centres[idx] + 6 * torch.randn(2000, 2, generator=g)
+    wh = 60 + 10 * torch.rand(2000, 2, generator=g)
+    dets = torch.cat([cxy - wh / 2, cxy + wh / 2, torch.rand(2000, 1, generator=g)], 1).numpy()
+    for thr in (0.3, 0.49, 0.8):
+        assert rd.nms_wrapper.nms(dets, thr) == bo.nms_pixel(dets, thr)
+
+
+# ---------------------------------------------------------------------------------------------
+# full size (BASELINE.json config 3): properties that do not need the oracle
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(rd):
+    B, C, top_k, keep = 32, 81, 1000, 500
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS['512']).forward().cuda()
+    P = priors.shape[0]
+    arm_loc, arm_conf, odm_loc, odm_conf = [t.cuda() for t in gen.detect_inputs(1234 + 3000, B, P, C, 'sparse')]
+    det = rd.Detect_RefineDet(C, 512, 0, top_k, 0.01, 0.45, 0.01, keep)
+    scale = torch.tensor([512.0] * 4)
+    res = det.detect(arm_loc, arm_conf, odm_loc, odm_conf, priors, scale=scale)
+    counts = res.counts
+    assert int(counts[:, 0].sum()) == 0 and int(counts.max()) <= keep and int(counts.sum()) > 0
+    conf_copy = odm_conf.clone()
+    boxes, scores = det.forward(arm_loc, arm_conf, odm_loc, conf_copy, priors)
+    # every emitted row is (scaled box of its anchor, score of its anchor/class), scores descending
+    ar = torch.arange(keep, device='cuda')
+    valid = ar[None, None, :] < counts[:, :, None]
+    a = res.anchors.long().clamp(min=0, max=P - 1)
+    bidx = torch.arange(B, device='cuda')[:, None, None].expand_as(a)
+    cidx = torch.arange(C, device='cuda')[None, :, None].expand_as(a)
+    exp_score = scores[bidx, a, cidx]
+    exp_box = boxes[bidx, a] * scale.cuda()
+    assert torch.equal(res.dets[..., 4][valid], exp_score[valid])
+    assert torch.equal(res.dets[..., :4][valid], exp_box[valid])
+    assert bool((res.dets[..., 4][valid] > 0.01).all())
+    s = res.dets[..., 4]
+    desc = (s[..., 1:] <= s[..., :-1]) | ~valid[..., 1:]
+    assert bool(desc.all())
+    # NMS invariant: no two kept rows of one (image, class) overlap above the threshold (+1 IoU)
+    for b in (0, 17, 31):
+        for c in (1, 40, 80):
+            n = int(counts[b, c])
+            d = res.dets[b, c, :n, :4]
+            x1, y1, x2, y2 = d[:, 0], d[:, 1], d[:, 2], d[:, 3]
+            area = (x2 - x1 + 1) * (y2 - y1 + 1)
+            w = (torch.min(x2[:, None], x2[None]) - torch.max(x1[:, None], x1[None]) + 1).clamp(min=0)
+            h = (torch.min(y2[:, None], y2[None]) - torch.max(y1[:, None], y1[None]) + 1).clamp(min=0)
+            iou = w * h / (area[:, None] + area[None] - w * h)
+            iou.fill_diagonal_(0)
+            assert float(iou.max()) <= 0.45 if n else True
+    # idempotence / determinism and pack round trip
+    res2 = det.detect(arm_loc, arm_conf, odm_loc, odm_conf, priors, scale=scale)
+    assert torch.equal(res2.counts, counts)
+    assert torch.equal(res2.dets[valid], res.dets[valid])
+    offsets, rows = res.packed()
+    assert int(offsets[-1]) == int(counts.sum()) == rows.shape[0]
+    assert torch.equal(rows, res.dets[valid])
+    assert torch.equal(offsets[:-1].long(), (counts.flatten().long().cumsum(0) - counts.flatten().long()))
+    # one oracle spot check at full size: image 5, three classes
+    gb, gs = boxes[5].cpu().numpy(), scores[5].cpu().numpy()
+    out, anc = bo.detect_stage_eval(gb, gs, scale.numpy(), 0.01, top_k, 0.45, keep)
+    for c in (1, 33, 80):
+        n = int(counts[5, c])
+        assert np.array_equal(res.anchors[5, c, :n].cpu().numpy(), anc[c])

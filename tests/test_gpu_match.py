@@ -1,0 +1,150 @@
+"""GPU tier: training-side matching (refine_match / match / encode), hard-negative mining and
+the RefineDetMultiBoxLoss drop-in against the reference-generated golden fixtures and the
+numpy oracle.  ``conf_t`` / ``pos`` / ``neg`` are bit-exact; ``loc_t`` (log) within 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import box_oracle as bo
+from tests import gen
+
+pytestmark = pytest.mark.gpu
+VAR = [0.1, 0.2]
+RTOL, ATOL = 1e-5, 2e-6
+
+
+def cu(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope='module')
+def rd():
+    import refinedet.pytorch_b200 as rd
+    rd._ffi.lib()
+    return rd
+
+
+def test_refine_match_golden(rd, golden):
+    g = golden('match_loss.npz')
+    bu = rd.box_utils
+    priors, targets = cu(g['priors']), cu(g['targets'])
+    B, P = targets.shape[0], priors.shape[0]
+    arm_loc = cu(g['arm_loc'])
+    for mode in ('arm', 'odm', 'ssd'):
+        loc_t = torch.zeros(B, P, 4).cuda()
+        conf_t = torch.zeros(B, P, dtype=torch.long).cuda()
+        for idx in range(B):
+            truths, labels = targets[idx][:, :-1], targets[idx][:, -1]
+            if mode == 'arm':
+                bu.refine_match(0.5, truths, priors, VAR, labels >= 0, loc_t, conf_t, idx)
+            elif mode == 'odm':
+                bu.refine_match(0.5, truths, priors, VAR, labels, loc_t, conf_t, idx, arm_loc[idx])
+            else:
+                bu.match(0.5, truths, priors, VAR, labels - 1, loc_t, conf_t, idx)
+        assert np.array_equal(conf_t.cpu().numpy(), g['conf_t_' + mode]), mode
+        np.testing.assert_allclose(loc_t.cpu().numpy(), g['loc_t_' + mode], rtol=RTOL, atol=ATOL, err_msg=mode)
+    with pytest.raises(IndexError):                                  # G = 0: the reference raises too
+        bu.refine_match(0.5, targets[0][:0, :-1], priors, VAR, targets[0][:0, -1],
+                        torch.zeros(B, P, 4).cuda(), torch.zeros(B, P, dtype=torch.long).cuda(), 0)
+
+
+def test_loss_golden(rd, golden):
+    g = golden('match_loss.npz')
+    C = g['odm_conf'].shape[-1]
+    preds = tuple(cu(g[k]) for k in ('arm_loc', 'arm_conf', 'odm_loc', 'odm_conf', 'priors'))
+    targets = [cu(t) for t in g['targets']]
+    arm_crit = rd.RefineDetMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)
+    odm_crit = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True)
+    al, ac = arm_crit(preds, targets)
+    ol, oc = odm_crit(preds, targets)
+    np.testing.assert_allclose([al.item(), ac.item()], g['arm_loss'], rtol=2e-5)
+    np.testing.assert_allclose([ol.item(), oc.item()], g['odm_loss'], rtol=2e-5)
+    # masks: pos / neg bit-exact against the reference's sort-based ranking
+    bu = rd.box_utils
+    for mode, conf_key, nc in (('arm', 'arm_conf', 2), ('odm', 'odm_conf', C)):
+        pos = cu(g['pos_' + mode])
+        neg, num_pos = bu.hnm_select(cu(g['loss_c_rows_' + mode]), pos, 3)
+        assert np.array_equal(neg.cpu().numpy(), g['neg_' + mode]), mode
+        assert np.array_equal(num_pos.cpu().numpy(), g['pos_' + mode].sum(1))
+    # every positive ARM-filtered -> (zeros(1), zeros(1)) like the reference (:135-136)
+    arm_conf_off = preds[1].clone()
+    arm_conf_off[..., 0] += 50.0
+    zl, zc = odm_crit((preds[0], arm_conf_off, preds[2], preds[3], preds[4]), targets)
+    assert zl.shape == (1,) and float(zl) == 0.0 and float(zc) == 0.0
+    # gradients flow to the predictions through the stock-PyTorch loss tail
+    p2 = tuple(t.clone().requires_grad_(True) if i < 4 else t for i, t in enumerate(preds))
+    l, c = odm_crit(p2, targets)
+    (l + c).backward()
+    assert p2[2].grad is not None and float(p2[2].grad.abs().sum()) > 0
+    assert p2[3].grad is not None and float(p2[3].grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize('B,size,C,G,use_arm', [(4, '320', 21, 9, True), (4, '320', 21, 9, False),
+                                                (3, '512', 81, 50, True), (2, '512', 2, 200, True)])
+def test_match_batch_vs_oracle(rd, B, size, C, G, use_arm):
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward()
+    P = priors.shape[0]
+    small = C == 2
+    tg = gen.targets(9000 + G, B, G, C, 0.01 if small else 0.02, 0.06 if small else 0.17)
+    # ragged ground truth: drop a different number of boxes per image
+    tg = [t[:max(1, G - 3 * i)] for i, t in enumerate(tg)]
+    arm_loc, arm_conf, odm_loc, odm_conf = gen.train_predictions(31 + G, B, P, C)
+    bu = rd.box_utils
+    truths, labels, cnt = bu.pad_targets([t.cuda() for t in tg], 'cuda')
+    mode = bu.LABEL_ODM if use_arm else bu.LABEL_ARM_BINARY
+    loc_t, conf_t, bt_idx, bt_ov = bu.match_batch(0.5, truths, labels, cnt, priors.cuda(), VAR,
+                                                  arm_loc.cuda() if use_arm else None, mode, return_best=True)
+    for i in range(B):
+        t = tg[i].numpy()
+        lab = t[:, 4] if use_arm else (t[:, 4] >= 0)
+        l, c, bti, bto = bo.refine_match(0.5, t[:, :4], priors.numpy(), VAR, lab,
+                                         arm_loc[i].numpy() if use_arm else None)
+        assert np.array_equal(conf_t[i].cpu().numpy(), c), i
+        assert np.array_equal(bt_idx[i].cpu().numpy(), bti), i
+        pos = c > 0
+        np.testing.assert_allclose(loc_t[i].cpu().numpy()[pos], l[pos], rtol=RTOL, atol=ATOL)
+        if not use_arm:      # ARM branch has no exp/log ahead of jaccard: overlaps are bit-exact
+            assert np.array_equal(bt_ov[i].cpu().numpy(), bto)
+            np.testing.assert_allclose(loc_t[i].cpu().numpy(), l, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize('B,P', [(3, 1275), (32, 16320)])
+def test_hnm_vs_oracle_and_properties(rd, B, P):
+    g = torch.Generator().manual_seed(P)
+    loss = torch.rand(B, P, generator=g) * 8
+    pos = torch.rand(B, P, generator=g) < 0.015
+    pos[0] = False                                   # num_pos = 0 -> no negatives
+    if B > 2:
+        pos[1] = torch.rand(P, generator=g) < 0.4    # 3*num_pos > P-1 -> clamp
+    neg, num_pos = rd.box_utils.hnm_select(loss.cuda(), pos.cuda(), 3)
+    e_neg, _ = bo.hnm_select(loss.numpy(), pos.numpy(), 3)
+    assert np.array_equal(neg.cpu().numpy(), e_neg)
+    assert np.array_equal(num_pos.cpu().numpy(), pos.sum(1).numpy())
+    n_neg = neg.sum(1).cpu()
+    assert torch.equal(n_neg, torch.clamp(3 * pos.sum(1), max=P - 1))
+    # every selected loss >= every unselected loss of the row (positives count as zero)
+    lz = loss.clone()
+    lz[pos] = 0
+    lz = lz.cuda()
+    for b in range(B):
+        if 0 < int(n_neg[b]) < P:
+            assert float(lz[b][neg[b]].min()) >= float(lz[b][~neg[b]].max())
+
+
+def test_full_size_loss_step(rd):
+    """BASELINE.json config 4 shape: both criteria run, finite, N = sum(num_pos)."""
+    B, P, C, G = 32, 16320, 81, 50
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS['512']).forward().cuda()
+    preds = tuple(t.cuda() for t in gen.train_predictions(1234 + 4000, B, P, C)) + (priors,)
+    tg = [t.cuda() for t in gen.targets(55, B, G, C)]
+    arm_crit = rd.RefineDetMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)
+    odm_crit = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True)
+    for crit in (arm_crit, odm_crit):
+        l, c = crit(preds, tg)
+        assert torch.isfinite(l) and torch.isfinite(c) and float(l) > 0 and float(c) > 0
+    loc_t, conf_t = odm_crit.match_targets(preds, tg)
+    # every ground truth owns at least one positive anchor (forced match), labels in range
+    assert int(conf_t.min()) == 0 and int(conf_t.max()) <= C - 1
+    assert int((conf_t > 0).sum(1).min()) >= 1
+    l2, c2 = odm_crit.match_targets(preds, tg)
+    assert torch.equal(c2, conf_t) and torch.equal(l2, loc_t)
