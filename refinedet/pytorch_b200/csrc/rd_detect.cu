@@ -8,9 +8,9 @@
 //   collect_kernel          K1: ARM filter, decode of passing anchors, per-(image,class)
 //                           candidate lists.  Data-dependent traffic: odm_conf / loc rows of
 //                           ARM-filtered anchors are never fetched.
-//   nms_small_kernel        K2+K3 for (image,class) problems with <= kSmallCap candidates,
-//                           one CTA each, ~15 KB smem so many CTAs are resident per SM
-//   nms_large_kernel        persistent CTAs draining the queue of larger problems
+//   nms_fused_kernel        K2+K3: one WARP per (image,class) problem with <= 256 candidates
+//                           (register bitonic sort, no CTA barrier); problems that need the
+//                           top-k select or hold more boxes are then run CTA-wide by the same CTA
 //   nms_single_kernel       stand-alone problem (rd_nms / rd_nms_host)
 //   pack_kernel             slot layout -> packed rows
 #include "rd_nms_core.cuh"
@@ -22,23 +22,19 @@ namespace rd {
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
-constexpr int kSmallCap = 256;       // problems up to this many boxes run in nms_small_kernel
 constexpr int kCollectThreads = 256;
 
 // ---------------------------------------------------------------------------------------
 // workspace of the fused stage
-//   [0, 256)                 : header: u32 queue_count
 //   cnt    int  [B*C]        : candidate counts (zero between calls)
-//   queue  int  [B*C]        : (image,class) problems routed to nms_large_kernel
 //   boxes  f4   [B*P]        : decoded boxes of ARM-passing anchors
-//   cand   u64  [B*C*P]      : candidate keys, capacity P per (image,class)
+//   cand   u64  [B*C*cap]    : candidate keys, capacity cap = P rounded up to even per (image,class)
 // ---------------------------------------------------------------------------------------
 struct DetectWs {
-    uint32_t* header;
     int* cnt;
-    int* queue;
     float4* boxes;
     unsigned long long* cand;
+    int cap;
     size_t total;
 };
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -46,11 +42,10 @@ static DetectWs carve_ws(void* base, int B, int P, int C) {
     DetectWs w;
     size_t o = 0;
     unsigned char* p = static_cast<unsigned char*>(base);
-    w.header = reinterpret_cast<uint32_t*>(p + o);             o += 256;
+    w.cap = (P + 1) & ~1;
     w.cnt = reinterpret_cast<int*>(p + o);                     o += align_up((size_t)B * C * 4, 256);
-    w.queue = reinterpret_cast<int*>(p + o);                   o += align_up((size_t)B * C * 4, 256);
     w.boxes = reinterpret_cast<float4*>(p + o);                o += align_up((size_t)B * P * 16, 256);
-    w.cand = reinterpret_cast<unsigned long long*>(p + o);     o += align_up((size_t)B * C * P * 8, 256);
+    w.cand = reinterpret_cast<unsigned long long*>(p + o);     o += align_up((size_t)B * C * w.cap * 8, 256);
     w.total = o;
     return w;
 }
@@ -123,75 +118,74 @@ detect_forward_kernel(const float4* __restrict__ arm_loc, const float2* __restri
 }
 
 // ---------------------------------------------------------------------------------------
-// K1: ARM filter + decode + candidate collection
+// K1: ARM filter + decode + candidate collection.
+// Each warp owns kChunks x 32 consecutive rows of the flattened [B*P] anchor axis: the
+// arm_conf loads of all chunks are issued first (memory-level parallelism), then the warp
+// visits ONLY the anchors that pass the ARM filter; their odm_conf rows are read with
+// coalesced 128 B requests (lane = class).  Rows / loc vectors of filtered anchors are never
+// touched, so DRAM traffic scales with the pass fraction, not with B*P*C.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void emit_candidate(float v, int al, int c, long long g0, int P, int C, int cap,
-                                               int* cnt, unsigned long long* cand) {
-    long long g = g0 + al;
-    int b = (int)(g / P);
-    int a = (int)(g - (long long)b * P);
-    int bc = b * C + c;
-    int slot = atomicAdd(&cnt[bc], 1);
-    cand[(size_t)bc * cap + slot] = make_key(v, (uint32_t)a);
-}
+constexpr int kChunks = 4;
 
 __global__ void __launch_bounds__(kCollectThreads)
 collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ arm_conf,
                const float4* __restrict__ odm_loc, const float* __restrict__ odm_conf,
                const float4* __restrict__ priors, long long total, int P, int C, float obj_thre,
                float conf_thresh, float v0, float v1, float4* __restrict__ boxes_ws, int* cnt,
-               unsigned long long* cand, uint32_t* header) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) header[0] = 0;   // queue of the large-NMS kernel
+               unsigned long long* cand, int cap) {
     const int lane = threadIdx.x & 31;
     const long long warp_global = ((long long)blockIdx.x * kCollectThreads + threadIdx.x) >> 5;
-    const long long g0 = warp_global * 32;
+    const long long g0 = warp_global * (32 * kChunks);
     if (g0 >= total) return;
-    const long long g = g0 + lane;
-    const bool valid = g < total;
-    bool pass = false;
-    if (valid) {
-        float2 ac = ldg_stream2(arm_conf + g);
-        pass = !(ac.y <= obj_thre);
-    }
-    const unsigned mask = __ballot_sync(kFullMask, pass);
-    if (mask == 0) return;                  // no anchor of this warp survives the ARM filter
-    if (pass) {
-        const int a = (int)(g % P);
-        boxes_ws[g] = refine_decode(ldg_stream4(arm_loc + g), ldg_stream4(odm_loc + g), __ldg(priors + a), v0, v1);
-    }
-    const int nvalid = (int)min((long long)32, total - g0);
-    const int nelem = nvalid * C;
-    const float* conf = odm_conf + g0 * C;
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(conf) & 15) == 0;
-    const int nvec = vec_ok ? (nelem >> 2) : 0;
-    int e0 = lane * 4;
-    int al = e0 / C, c = e0 - al * C;
-    const int dal = 128 / C, dc = 128 - dal * C;
-    for (int q = lane; q < nvec; q += 32) {
-        int a0 = al, c0 = c;
-        unsigned pm = 0;
-        int an[4], cn[4];
+    unsigned mask[kChunks];
+    bool pass[kChunks];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            an[k] = a0; cn[k] = c0;
-            pm |= (((mask >> a0) & 1u) & (c0 != 0 ? 1u : 0u)) << k;   // class 0 = background, never a candidate
-            if (++c0 == C) { c0 = 0; ++a0; }
+    for (int ch = 0; ch < kChunks; ++ch) {
+        const long long g = g0 + ch * 32 + lane;
+        pass[ch] = false;
+        if (g < total) {
+            float2 ac = ldg_stream2(arm_conf + g);
+            pass[ch] = !(ac.y <= obj_thre);        // kept unless arm_conf[...,1] <= thre (:41)
         }
-        if (pm) {
-            float4 v = ldg_stream4(reinterpret_cast<const float4*>(conf) + q);
-            if ((pm & 1u) && v.x > conf_thresh) emit_candidate(v.x, an[0], cn[0], g0, P, C, P, cnt, cand);
-            if ((pm & 2u) && v.y > conf_thresh) emit_candidate(v.y, an[1], cn[1], g0, P, C, P, cnt, cand);
-            if ((pm & 4u) && v.z > conf_thresh) emit_candidate(v.z, an[2], cn[2], g0, P, C, P, cnt, cand);
-            if ((pm & 8u) && v.w > conf_thresh) emit_candidate(v.w, an[3], cn[3], g0, P, C, P, cnt, cand);
-        }
-        al += dal; c += dc;
-        if (c >= C) { c -= C; ++al; }
     }
-    for (int e = nvec * 4 + lane; e < nelem; e += 32) {
-        int a1 = e / C, c1 = e - a1 * C;
-        if (c1 != 0 && ((mask >> a1) & 1u)) {
-            float v = ldg_stream1(conf + e);
-            if (v > conf_thresh) emit_candidate(v, a1, c1, g0, P, C, P, cnt, cand);
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) mask[ch] = __ballot_sync(kFullMask, pass[ch]);
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) {
+        if (pass[ch]) {
+            const long long g = g0 + ch * 32 + lane;
+            const int a = (int)(g % P);
+            boxes_ws[g] = refine_decode(ldg_stream4(arm_loc + g), ldg_stream4(odm_loc + g), __ldg(priors + a), v0, v1);
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) {
+        unsigned m = mask[ch];
+        while (m) {
+            const int al = __ffs(m) - 1;
+            m &= m - 1;
+            const long long g = g0 + ch * 32 + al;
+            const int b = (int)(g / P);
+            const int a = (int)(g - (long long)b * P);
+            const float* row = odm_conf + g * C;
+            for (int c0 = 0; c0 < C; c0 += 128) {
+                float v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = c0 + k * 32 + lane;
+                    v[k] = (c < C) ? ldg_stream1(row + c) : 0.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = c0 + k * 32 + lane;
+                    // class 0 = background, never evaluated (eval_refinedet_coco.py:213)
+                    if (c < C && c != 0 && v[k] > conf_thresh) {
+                        const int bc = b * C + c;
+                        const int slot = atomicAdd(&cnt[bc], 1);
+                        cand[(size_t)bc * cap + slot] = make_key(v[k], (uint32_t)a);
+                    }
+                }
+            }
         }
     }
 }
@@ -204,15 +198,28 @@ struct FusedNmsArgs {
     const unsigned long long* cand;  // [B*C*cap]
     const float4* boxes;             // [B*P]
     const float* img_scale;          // [B,4] or null
-    int* queue;
-    uint32_t* header;
-    int C, P, cap;
+    int nbc, C, P, cap;
     float thr;
     int top_k, max_out, flags, row_layout;
     int* out_counts;
     float* out_dets;
     int* out_anchor;
 };
+
+__device__ __forceinline__ NmsProblem make_problem(int bc, int n, const FusedNmsArgs& A) {
+    const int b = bc / A.C;
+    NmsProblem pb;
+    pb.cand = A.cand + (size_t)bc * A.cap;
+    pb.n = n;
+    pb.boxes = A.boxes + (size_t)b * A.P;
+    pb.has_scale = A.img_scale != nullptr;
+    pb.scale = pb.has_scale ? __ldg(reinterpret_cast<const float4*>(A.img_scale) + b) : make_float4(1.f, 1.f, 1.f, 1.f);
+    pb.thr = A.thr;
+    pb.top_k = A.top_k;
+    pb.max_out = A.max_out;
+    pb.flags = A.flags;
+    return pb;
+}
 
 __device__ __forceinline__ void emit_rows(unsigned char* smem, const NmsSmemLayout& L, int kept, int bc,
                                           const FusedNmsArgs& A) {
@@ -237,62 +244,54 @@ __device__ __forceinline__ void emit_rows(unsigned char* smem, const NmsSmemLayo
     }
 }
 
-__device__ __forceinline__ void run_fused_problem(unsigned char* smem, const NmsSmemLayout& L, int bc, int n,
-                                                  const FusedNmsArgs& A) {
-    const int b = bc / A.C;
-    NmsProblem pb;
-    pb.cand = A.cand + (size_t)bc * A.cap;
-    pb.n = n;
-    pb.boxes = A.boxes + (size_t)b * A.P;
-    pb.has_scale = A.img_scale != nullptr;
-    pb.scale = pb.has_scale ? __ldg(reinterpret_cast<const float4*>(A.img_scale) + b) : make_float4(1.f, 1.f, 1.f, 1.f);
-    pb.thr = A.thr;
-    pb.top_k = A.top_k;
-    pb.max_out = A.max_out;
-    pb.flags = A.flags;
-    int kept = nms_process(smem, L, pb);
-    emit_rows(smem, L, kept, bc, A);
-    if (threadIdx.x == 0) {
-        A.out_counts[bc] = kept;
-        A.cnt[bc] = 0;                // leave the workspace ready for the next call
-    }
-}
+constexpr int kWarpsPerCta = kNmsThreads / 32;
 
 __global__ void __launch_bounds__(kNmsThreads)
-nms_small_kernel(FusedNmsArgs A) {
+nms_fused_kernel(FusedNmsArgs A, int mcap_large) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int bc = blockIdx.x;
-    const int c = bc % A.C;
-    if (c == 0) {                      // background is never evaluated (eval_refinedet_coco.py:213)
-        if (threadIdx.x == 0) A.out_counts[bc] = 0;
-        return;
-    }
-    const int n = A.cnt[bc];
-    if (n == 0) {
-        if (threadIdx.x == 0) A.out_counts[bc] = 0;
-        return;
-    }
-    const int m = n < A.top_k ? n : A.top_k;
-    if (m > kSmallCap) {
-        if (threadIdx.x == 0) {
-            uint32_t pos = atomicAdd(&A.header[0], 1u);
-            A.queue[pos] = bc;
+    __shared__ int s_large[kWarpsPerCta];
+    __shared__ int s_nlarge;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_nlarge = 0;
+    __syncthreads();
+    const int bc = blockIdx.x * kWarpsPerCta + warp;
+    if (bc < A.nbc) {
+        const int c = bc % A.C;
+        int n = 0;
+        if (c != 0) n = A.cnt[bc];           // class 0 = background, never evaluated
+        if (n == 0) {
+            if (lane == 0) A.out_counts[bc] = 0;
+        } else if (n <= A.top_k && n <= kWarpCap) {
+            WarpSmem& S = *reinterpret_cast<WarpSmem*>(smem + (size_t)warp * sizeof(WarpSmem));
+            NmsProblem pb = make_problem(bc, n, A);
+            RowSink sink;
+            sink.rows = A.out_dets + (size_t)bc * A.max_out * 5;
+            sink.anchors = A.out_anchor ? A.out_anchor + (size_t)bc * A.max_out : nullptr;
+            sink.row_layout = A.row_layout;
+            const int kept = warp_nms_small(S, pb, sink);
+            if (lane == 0) {
+                A.out_counts[bc] = kept;
+                A.cnt[bc] = 0;                // leave the workspace ready for the next call
+            }
+        } else if (lane == 0) {
+            s_large[atomicAdd(&s_nlarge, 1)] = bc;
         }
-        return;
     }
-    const NmsSmemLayout L = nms_layout(kSmallCap);
-    run_fused_problem(smem, L, bc, n, A);
-}
-
-__global__ void __launch_bounds__(kNmsThreads)
-nms_large_kernel(FusedNmsArgs A, int mcap) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const NmsSmemLayout L = nms_layout(mcap);
-    const uint32_t nq = A.header[0];
-    for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
-        const int bc = A.queue[q];
-        const int n = A.cnt[bc];
-        run_fused_problem(smem, L, bc, n, A);
+    __syncthreads();
+    const int nlarge = s_nlarge;
+    if (nlarge == 0) return;
+    const NmsSmemLayout L = nms_layout(mcap_large);
+    for (int q = 0; q < nlarge; ++q) {
+        const int lbc = s_large[q];
+        const int n = A.cnt[lbc];
+        NmsProblem pb = make_problem(lbc, n, A);
+        const int kept = nms_process(smem, L, pb);
+        emit_rows(smem, L, kept, lbc, A);
+        if (threadIdx.x == 0) {
+            A.out_counts[lbc] = kept;
+            A.cnt[lbc] = 0;
+        }
         __syncthreads();
     }
 }
@@ -443,53 +442,37 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     cudaStream_t st = (cudaStream_t)stream;
 
     const long long total = (long long)B * P;
-    const long long warps = (total + 31) / 32;
+    const long long warps = (total + 32 * kChunks - 1) / (32 * kChunks);
     const int blocks = (int)((warps * 32 + kCollectThreads - 1) / kCollectThreads);
     if (ev) cudaEventRecord(ev[0], st);
     collect_kernel<<<blocks, kCollectThreads, 0, st>>>(
         (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
-        total, P, C, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.header);
+        total, P, C, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.cap);
     note_launch();
     RD_CHECK_LAUNCH();
 
     FusedNmsArgs A;
     A.cnt = ws.cnt; A.cand = ws.cand; A.boxes = ws.boxes; A.img_scale = img_scale;
-    A.queue = ws.queue; A.header = ws.header; A.C = C; A.P = P; A.cap = P;
+    A.nbc = B * C; A.C = C; A.P = P; A.cap = ws.cap;
     A.thr = nms_thresh; A.top_k = top_k; A.max_out = max_out; A.flags = nms_flags; A.row_layout = row_layout;
     A.out_counts = out_counts; A.out_dets = out_dets; A.out_anchor = out_anchor;
 
-    static int s_dev_sms = 0;
-    if (s_dev_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&s_dev_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (s_dev_sms <= 0) s_dev_sms = 148;
+    const int mcap = top_k < P ? top_k : P;
+    const size_t smem_large = nms_layout(mcap).total;
+    const size_t smem_warp = (size_t)kWarpsPerCta * sizeof(WarpSmem);
+    const size_t smem_bytes = smem_large > smem_warp ? smem_large : smem_warp;
+    static size_t s_attr = 48 * 1024;
+    if (smem_bytes > s_attr) {
+        cudaError_t e = cudaFuncSetAttribute(nms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        s_attr = smem_bytes;
     }
-    const NmsSmemLayout Ls = nms_layout(kSmallCap);
     if (ev) cudaEventRecord(ev[1], st);
-    nms_small_kernel<<<B * C, kNmsThreads, Ls.total, st>>>(A);
+    nms_fused_kernel<<<(B * C + kWarpsPerCta - 1) / kWarpsPerCta, kNmsThreads, smem_bytes, st>>>(A, mcap);
     note_launch();
     RD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[2], st);
-    if (top_k > kSmallCap) {
-        const int mcap = top_k < P ? top_k : P;
-        const NmsSmemLayout Ll = nms_layout(mcap);
-        static size_t s_attr = 0;
-        if (Ll.total > s_attr) {
-            cudaError_t e = cudaFuncSetAttribute(nms_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)Ll.total);
-            if (e != cudaSuccess) return (int)e;
-            s_attr = Ll.total;
-        }
-        int per_sm = (int)((220 * 1024) / (Ll.total + 1024));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 8) per_sm = 8;
-        int grid = s_dev_sms * per_sm;
-        if (grid > B * C) grid = B * C;
-        nms_large_kernel<<<grid, kNmsThreads, Ll.total, st>>>(A, mcap);
-        note_launch();
-        RD_CHECK_LAUNCH();
-    }
     if (ev) cudaEventRecord(ev[3], st);
     return 0;
 }
@@ -523,7 +506,8 @@ int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, const flo
     if (rc == 0) {
         cudaError_t e = cudaEventSynchronize(ev[3]);
         if (e != cudaSuccess) rc = (int)e;
-        for (int i = 0; i < 3 && rc == 0; ++i) {
+        stage_ms_host[2] = 0.f;
+        for (int i = 0; i < 2 && rc == 0; ++i) {
             e = cudaEventElapsedTime(&stage_ms_host[i], ev[i], ev[i + 1]);
             if (e != cudaSuccess) rc = (int)e;
         }

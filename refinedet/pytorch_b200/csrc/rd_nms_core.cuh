@@ -228,13 +228,11 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
             if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
             float area = pixel ? (b.z - b.x + 1.0f) * (b.w - b.y + 1.0f) : (b.z - b.x) * (b.w - b.y);
             sx1[i] = b.x; sy1[i] = b.y; sx2[i] = b.z; sy2[i] = b.w; sarea[i] = area;
-            float hx = pixel ? b.z + 1.0f : b.z, hy = pixel ? b.w + 1.0f : b.w;
-            if (isfinite(b.x) && isfinite(hx)) {
-                mnx = min(mnx, float_to_ordered(b.x)); mxx = max(mxx, float_to_ordered(hx));
-            }
-            if (isfinite(b.y) && isfinite(hy)) {
-                mny = min(mny, float_to_ordered(b.y)); mxy = max(mxy, float_to_ordered(hy));
-            }
+            // binning extent = range of the box CENTRES (a few huge boxes must not coarsen the bins);
+            // boxes reaching beyond it clamp to the edge bins, which stays conservative
+            float cx = 0.5f * b.x + 0.5f * b.z, cy = 0.5f * b.y + 0.5f * b.w;
+            if (isfinite(cx)) { mnx = min(mnx, float_to_ordered(cx)); mxx = max(mxx, float_to_ordered(cx)); }
+            if (isfinite(cy)) { mny = min(mny, float_to_ordered(cy)); mxy = max(mxy, float_to_ordered(cy)); }
         }
         mnx = __reduce_min_sync(kFullMask, mnx); mxx = __reduce_max_sync(kFullMask, mxx);
         mny = __reduce_min_sync(kFullMask, mny); mxy = __reduce_max_sync(kFullMask, mxy);
@@ -369,6 +367,227 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
     }
     __syncthreads();
     return (int)misc[8];
+}
+
+
+// =========================================================================================
+// warp-per-problem path: n <= 256 candidates, no select needed.  One warp sorts the keys in
+// registers (bitonic network, R = 1/2/4/8 keys per lane, cross-lane steps by shuffle), stages
+// boxes and the bin tables in its private slice of shared memory and walks the score order;
+// rows are emitted straight from the walk.  No CTA-wide barrier anywhere.
+// =========================================================================================
+constexpr int kWarpCap = 256;
+constexpr int kWarpW = kWarpCap / 32;      // 8 mask words
+constexpr int kWarpWS = kWarpW + 1;        // padded row stride
+struct WarpSmem {
+    unsigned long long keys[kWarpCap];
+    float x1[kWarpCap], y1[kWarpCap], x2[kWarpCap], y2[kWarpCap], area[kWarpCap];
+    uint32_t cr[kWarpCap];
+    uint32_t tab[4 * kCols * kWarpWS];
+    uint32_t keptbits[kWarpW];
+    uint32_t pad[8];
+};
+
+template <int R>
+__device__ __forceinline__ void warp_bitonic_desc(unsigned long long (&k)[R], int lane) {
+    // element index e = lane * R + r ; N = 32 * R elements ; result descending in e
+    constexpr int N = 32 * R;
+#pragma unroll
+    for (int k2 = 2; k2 <= N; k2 <<= 1) {
+#pragma unroll
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            if (j < R) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & j) == 0) {
+                        const int e = lane * R + r;
+                        const bool desc = (e & k2) == 0;
+                        unsigned long long a = k[r], b = k[r | j];
+                        const bool sw = (a < b) == desc;
+                        k[r] = sw ? b : a;
+                        k[r | j] = sw ? a : b;
+                    }
+                }
+            } else {
+                const int lj = j / R;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const int e = lane * R + r;
+                    const bool desc = (e & k2) == 0;
+                    const bool lower = (lane & lj) == 0;
+                    unsigned long long a = k[r];
+                    unsigned long long b = __shfl_xor_sync(kFullMask, a, lj);
+                    const bool take_max = (lower == desc);
+                    k[r] = take_max ? (a > b ? a : b) : (a < b ? a : b);
+                }
+            }
+        }
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void warp_load_sort_store(const unsigned long long* cand, int n, unsigned long long* skeys,
+                                                     int lane) {
+    unsigned long long k[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int e = lane * R + r;
+        k[r] = e < n ? cand[e] : 0ull;
+    }
+    warp_bitonic_desc<R>(k, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) skeys[lane * R + r] = k[r];
+}
+
+struct RowSink {           // where the fused stage writes its rows
+    float* rows;           // [max_out,5] slot of this (image, class)
+    int* anchors;          // [max_out] or null
+    int row_layout;
+};
+
+// returns kept count (uniform over the warp)
+__device__ inline int warp_nms_small(WarpSmem& S, const NmsProblem& pb, const RowSink& sink) {
+    const int lane = threadIdx.x & 31;
+    const int m = pb.n;                                   // caller guarantees n <= min(top_k, kWarpCap)
+    if (m <= 32) warp_load_sort_store<1>(pb.cand, m, S.keys, lane);
+    else if (m <= 64) warp_load_sort_store<2>(pb.cand, m, S.keys, lane);
+    else if (m <= 128) warp_load_sort_store<4>(pb.cand, m, S.keys, lane);
+    else warp_load_sort_store<8>(pb.cand, m, S.keys, lane);
+    const int Wm = (m + 31) >> 5;
+    for (int i = lane; i < 4 * kCols * kWarpWS; i += 32) S.tab[i] = 0;
+    __syncwarp();
+
+    const bool pixel = (pb.flags & RD_NMS_PIXEL_PLUS1) != 0;
+    uint32_t mnx = 0xffffffffu, mxx = 0, mny = 0xffffffffu, mxy = 0;
+    for (int j = lane; j < m; j += 32) {
+        float4 b = pb.boxes[key_index(S.keys[j])];
+        if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
+        float area = pixel ? (b.z - b.x + 1.0f) * (b.w - b.y + 1.0f) : (b.z - b.x) * (b.w - b.y);
+        S.x1[j] = b.x; S.y1[j] = b.y; S.x2[j] = b.z; S.y2[j] = b.w; S.area[j] = area;
+        float cx = 0.5f * b.x + 0.5f * b.z, cy = 0.5f * b.y + 0.5f * b.w;
+        if (isfinite(cx)) { mnx = min(mnx, float_to_ordered(cx)); mxx = max(mxx, float_to_ordered(cx)); }
+        if (isfinite(cy)) { mny = min(mny, float_to_ordered(cy)); mxy = max(mxy, float_to_ordered(cy)); }
+    }
+    mnx = __reduce_min_sync(kFullMask, mnx); mxx = __reduce_max_sync(kFullMask, mxx);
+    mny = __reduce_min_sync(kFullMask, mny); mxy = __reduce_max_sync(kFullMask, mxy);
+    float lox = 0.f, invx = 0.f, loy = 0.f, invy = 0.f;
+    if (mnx <= mxx) {
+        lox = ordered_to_float(mnx);
+        float hi = ordered_to_float(mxx);
+        invx = hi > lox ? (float)kCols / (hi - lox) : 0.f;
+    }
+    if (mny <= mxy) {
+        loy = ordered_to_float(mny);
+        float hi = ordered_to_float(mxy);
+        invy = hi > loy ? (float)kCols / (hi - loy) : 0.f;
+    }
+    if (!isfinite(invx)) invx = 0.f;
+    if (!isfinite(invy)) invy = 0.f;
+    const bool eq = (pb.flags & RD_NMS_SUPPRESS_EQ) != 0;
+    const bool force_full = eq ? !(pb.thr > 0.0f) : !(pb.thr >= 0.0f);
+    const float eps = 9.5367431640625e-07f;
+    for (int i = lane; i < m; i += 32) {
+        float x1 = S.x1[i], y1 = S.y1[i], x2 = S.x2[i], y2 = S.y2[i], ar = S.area[i];
+        float hx = pixel ? x2 + 1.0f : x2, hy = pixel ? y2 + 1.0f : y2;
+        int ax, bx, ay, by;
+        bool ok = isfinite(x1) && isfinite(y1) && isfinite(hx) && isfinite(hy) && (ar > 0.0f) && isfinite(ar) &&
+                  !force_full;
+        if (ok) {
+            ax = col_of(x1 - fabsf(x1) * eps, lox, invx);
+            bx = col_of(hx + fabsf(hx) * eps, lox, invx);
+            ay = col_of(y1 - fabsf(y1) * eps, loy, invy);
+            by = col_of(hy + fabsf(hy) * eps, loy, invy);
+        } else {
+            ax = 0; bx = kCols - 1; ay = 0; by = kCols - 1;
+        }
+        S.cr[i] = (uint32_t)ax | ((uint32_t)bx << 8) | ((uint32_t)ay << 16) | ((uint32_t)by << 24);
+        const uint32_t bit = 1u << (i & 31);
+        const int w = i >> 5;
+        atomicOr(&S.tab[(0 * kCols + ax) * kWarpWS + w], bit);
+        if (bx + 1 < kCols) atomicOr(&S.tab[(1 * kCols + bx + 1) * kWarpWS + w], bit);
+        atomicOr(&S.tab[(2 * kCols + ay) * kWarpWS + w], bit);
+        if (by + 1 < kCols) atomicOr(&S.tab[(3 * kCols + by + 1) * kWarpWS + w], bit);
+    }
+    __syncwarp();
+    for (int task = lane; task < 4 * Wm; task += 32) {
+        int t = task / Wm, w = task - t * Wm;
+        uint32_t acc = 0;
+        uint32_t* p = S.tab + t * kCols * kWarpWS + w;
+#pragma unroll 8
+        for (int c = 0; c < kCols; ++c) { acc |= p[c * kWarpWS]; p[c * kWarpWS] = acc; }
+    }
+    __syncwarp();
+
+    const float thr = pb.thr;
+    const int flags = pb.flags;
+    const int max_out = pb.max_out;
+    int kept_total = 0;
+    const uint32_t* Sx = S.tab;
+    const uint32_t* Ex = S.tab + 1 * kCols * kWarpWS;
+    const uint32_t* Sy = S.tab + 2 * kCols * kWarpWS;
+    const uint32_t* Ey = S.tab + 3 * kCols * kWarpWS;
+    for (int ib = 0; ib < Wm; ++ib) {
+        const int j = ib * 32 + lane;
+        const bool valid = j < m;
+        bool alive = valid;
+        float x1 = 0, y1 = 0, x2 = 0, y2 = 0, ar = 0;
+        uint32_t cr = 0;
+        if (valid) { x1 = S.x1[j]; y1 = S.y1[j]; x2 = S.x2[j]; y2 = S.y2[j]; ar = S.area[j]; cr = S.cr[j]; }
+        const uint32_t* rSx = Sx + ((cr >> 8) & 255u) * kWarpWS;
+        const uint32_t* rEx = Ex + (cr & 255u) * kWarpWS;
+        const uint32_t* rSy = Sy + ((cr >> 24) & 255u) * kWarpWS;
+        const uint32_t* rEy = Ey + ((cr >> 16) & 255u) * kWarpWS;
+        for (int w = 0; w < ib; ++w) {
+            uint32_t h = rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & S.keptbits[w];
+            while (alive && h) {
+                int i = (w << 5) + __ffs(h) - 1;
+                h &= h - 1;
+                if (suppresses(S.x1[i], S.y1[i], S.x2[i], S.y2[i], S.area[i], x1, y1, x2, y2, ar, thr, flags))
+                    alive = false;
+            }
+        }
+        uint32_t tin = 0;
+        if (alive) {
+            uint32_t h = rSx[ib] & ~rEx[ib] & rSy[ib] & ~rEy[ib] & ((1u << lane) - 1u);
+            while (h) {
+                int k = __ffs(h) - 1;
+                h &= h - 1;
+                int i = (ib << 5) + k;
+                if (suppresses(S.x1[i], S.y1[i], S.x2[i], S.y2[i], S.area[i], x1, y1, x2, y2, ar, thr, flags))
+                    tin |= 1u << k;
+            }
+        }
+        uint32_t u = __reduce_or_sync(kFullMask, tin);
+        while (u) {
+            int k = __ffs(u) - 1;
+            u &= u - 1;
+            uint32_t al = __ballot_sync(kFullMask, alive);
+            if (((al >> k) & 1u) && ((tin >> k) & 1u)) alive = false;
+        }
+        uint32_t keptw = __ballot_sync(kFullMask, alive);
+        int room = max_out - kept_total;
+        int cnt = __popc(keptw);
+        if (cnt > room) {
+            uint32_t t = keptw, keep = 0;
+            for (int r = 0; r < room; ++r) { uint32_t low = t & (0u - t); keep |= low; t ^= low; }
+            keptw = keep;
+            cnt = room;
+        }
+        if ((keptw >> lane) & 1u) {
+            const int t = kept_total + __popc(keptw & ((1u << lane) - 1u));
+            const unsigned long long key = S.keys[j];
+            const float sc = key_score(key);
+            float* r = sink.rows + (size_t)t * 5;
+            if (sink.row_layout == RD_ROW_SCORE_BOX) { r[0] = sc; r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2; }
+            else { r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = sc; }
+            if (sink.anchors) sink.anchors[t] = (int)key_index(key);
+        }
+        if (lane == 0) S.keptbits[ib] = keptw;
+        __syncwarp();
+        kept_total += cnt;
+        if (kept_total >= max_out) break;
+    }
+    return kept_total;
 }
 
 }  // namespace rd

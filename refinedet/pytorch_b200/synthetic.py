@@ -66,3 +66,15 @@ def assert_tie_free(scores, conf_thresh):
             if np.unique(v).size != v.size:
                 return False
     return True
+
+
+def tie_free_detect_inputs(seed, B, P, C, kind, conf_thresh, obj_thresh, arm_shift=-8.0, max_tries=20):
+    """``detect_inputs`` with the SURVEY.md §8d guarantee: per (image, class) the candidate scores
+    (ARM-passing anchors with score > conf_thresh) are pairwise distinct; ``seed + 1`` otherwise."""
+    for k in range(max_tries):
+        a = detect_inputs(seed + k, B, P, C, kind, arm_shift=arm_shift)
+        scores = a[3].clone()
+        scores[a[1][..., 1] <= obj_thresh] = 0
+        if assert_tie_free(scores, conf_thresh):
+            return a
+    raise RuntimeError('no tie-free input found in %d seeds' % max_tries)

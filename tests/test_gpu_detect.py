@@ -157,8 +157,12 @@ def test_fused_detect_vs_oracle(rd, kind, B, size, C, top_k, keep):
     priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward()
     P = priors.shape[0]
     arm_shift = -3.0 if kind == 'sparse' else 0.0
-    arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs(4242 + B + C, B, P, C, kind, arm_shift=arm_shift)
     conf_thr, nms_thr, obj_thr = 0.01, 0.45, 0.01
+    # fp32 softmax scores collide often at these candidate counts, so tie-free inputs are not
+    # attainable by reseeding; the kernel and the oracle share one documented tie rule (score
+    # descending, lower anchor first) and must agree bit-exactly WITH ties present.  The golden
+    # fixtures (reference outputs) were generated tie-free, where the rule is unobservable.
+    arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs(4242 + B + C, B, P, C, kind, arm_shift=arm_shift)
     det = rd.Detect_RefineDet(C, int(size), 0, top_k, conf_thr, nms_thr, obj_thr, keep)
     scale = np.array([float(size)] * 4, np.float32)
     d_in = [t.cuda() for t in (arm_loc, arm_conf, odm_loc, odm_conf)]
@@ -173,7 +177,6 @@ def test_fused_detect_vs_oracle(rd, kind, B, size, C, top_k, keep):
     np.testing.assert_allclose(g_boxes.cpu().numpy(), o_boxes, rtol=RTOL, atol=ATOL)
     assert np.array_equal(g_scores.cpu().numpy(), o_scores)
     assert np.array_equal(conf_a3.cpu().numpy(), o_conf)
-    assert gen.assert_tie_free(o_scores, conf_thr)
     # a4: oracle NMS fed the GPU's boxes -> kept anchor sets must be bit-exact
     counts, anchors, rows = _oracle_a4(g_boxes.cpu().numpy(), o_scores, scale, conf_thr, top_k, nms_thr, keep)
     g_counts = res.counts.cpu().numpy()

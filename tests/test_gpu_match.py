@@ -11,6 +11,11 @@ from tests import gen
 pytestmark = pytest.mark.gpu
 VAR = [0.1, 0.2]
 RTOL, ATOL = 1e-5, 2e-6
+# ODM targets are encoded against center_size(decode(arm_loc, prior)): a 1-ulp difference of exp
+# between CUDA and the CPU libm moves the refined anchor's centre/size by ~6e-8, and encode divides the
+# centre offset by v0*w (w down to 0.03) and takes log((gt_w)/w): the error is amplified to ~2e-5
+# absolute.  conf_t and best_truth_idx stay bit-exact.
+ATOL_ODM = 1e-4
 
 
 def cu(a):
@@ -42,7 +47,8 @@ def test_refine_match_golden(rd, golden):
             else:
                 bu.match(0.5, truths, priors, VAR, labels - 1, loc_t, conf_t, idx)
         assert np.array_equal(conf_t.cpu().numpy(), g['conf_t_' + mode]), mode
-        np.testing.assert_allclose(loc_t.cpu().numpy(), g['loc_t_' + mode], rtol=RTOL, atol=ATOL, err_msg=mode)
+        np.testing.assert_allclose(loc_t.cpu().numpy(), g['loc_t_' + mode], rtol=RTOL,
+                                   atol=ATOL_ODM if mode == 'odm' else ATOL, err_msg=mode)
     with pytest.raises(IndexError):                                  # G = 0: the reference raises too
         bu.refine_match(0.5, targets[0][:0, :-1], priors, VAR, targets[0][:0, -1],
                         torch.zeros(B, P, 4).cuda(), torch.zeros(B, P, dtype=torch.long).cuda(), 0)
@@ -102,7 +108,7 @@ def test_match_batch_vs_oracle(rd, B, size, C, G, use_arm):
         assert np.array_equal(conf_t[i].cpu().numpy(), c), i
         assert np.array_equal(bt_idx[i].cpu().numpy(), bti), i
         pos = c > 0
-        np.testing.assert_allclose(loc_t[i].cpu().numpy()[pos], l[pos], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(loc_t[i].cpu().numpy()[pos], l[pos], rtol=RTOL, atol=ATOL_ODM if use_arm else ATOL)
         if not use_arm:      # ARM branch has no exp/log ahead of jaccard: overlaps are bit-exact
             assert np.array_equal(bt_ov[i].cpu().numpy(), bto)
             np.testing.assert_allclose(loc_t[i].cpu().numpy(), l, rtol=RTOL, atol=ATOL)
