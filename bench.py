@@ -168,6 +168,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--workload', default='sparse', choices=['sparse', 'dense'])
+    ap.add_argument('--flush', default='write', choices=['write', 'write+read', 'read', 'none'],
+                    help='how L2 is flushed before every timed step (exploration; the default is the contract)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -217,7 +219,16 @@ def main():
     arm_pass = float((host_sets[0][1][..., 1] > OBJ_THR).float().mean())
     scale = torch.tensor([512.0] * 4, device=dev).reshape(1, 4).expand(BATCH, 4).contiguous()
     det = rd.Detect_RefineDet(C, 512, 0, TOP_K, CONF_THR, NMS_THR, OBJ_THR, KEEP_TOP_K)
-    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    flush_rd = torch.empty(64 << 20, dtype=torch.float32, device=dev) if 'read' in args.flush else None
+
+    class _Flush(object):
+        def zero_(self):
+            if 'write' in args.flush:
+                flush_buf.zero_()
+            if flush_rd is not None:
+                flush_rd.sum()
+    flush = _Flush()
     clocks = ClockSampler(local_rank)
 
     def step(i):

@@ -126,64 +126,76 @@ detect_forward_kernel(const float4* __restrict__ arm_loc, const float2* __restri
 // touched, so DRAM traffic scales with the pass fraction, not with B*P*C.
 // ---------------------------------------------------------------------------------------
 constexpr int kChunks = 4;
+constexpr int kRowBatch = 4;     // odm_conf rows in flight per warp
 
 __global__ void __launch_bounds__(kCollectThreads)
 collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ arm_conf,
                const float4* __restrict__ odm_loc, const float* __restrict__ odm_conf,
-               const float4* __restrict__ priors, long long total, int P, int C, float obj_thre,
+               const float4* __restrict__ priors, int total, int P, int C, float obj_thre,
                float conf_thresh, float v0, float v1, float4* __restrict__ boxes_ws, int* cnt,
                unsigned long long* cand, int cap) {
+    __shared__ unsigned char s_list[kCollectThreads / 32][32 * kChunks];   // passing anchors of each warp
     const int lane = threadIdx.x & 31;
-    const long long warp_global = ((long long)blockIdx.x * kCollectThreads + threadIdx.x) >> 5;
-    const long long g0 = warp_global * (32 * kChunks);
-    if (g0 >= total) return;
-    unsigned mask[kChunks];
-    bool pass[kChunks];
+    const int wib = threadIdx.x >> 5;
+    const int warp_global = (int)(((long long)blockIdx.x * kCollectThreads + threadIdx.x) >> 5);
+    const long long g0l = (long long)warp_global * (32 * kChunks);
+    if (g0l >= total) return;
+    const int g0 = (int)g0l;
+    // 1. ARM filter for 32*kChunks anchors; all loads issued before the first use
+    float obj[kChunks];
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
-        const long long g = g0 + ch * 32 + lane;
-        pass[ch] = false;
-        if (g < total) {
-            float2 ac = ldg_stream2(arm_conf + g);
-            pass[ch] = !(ac.y <= obj_thre);        // kept unless arm_conf[...,1] <= thre (:41)
-        }
+        const int g = g0 + ch * 32 + lane;
+        obj[ch] = (g < total) ? ldg_stream2(arm_conf + g).y : -INFINITY;
     }
-#pragma unroll
-    for (int ch = 0; ch < kChunks; ++ch) mask[ch] = __ballot_sync(kFullMask, pass[ch]);
+    int npass = 0;
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
-        if (pass[ch]) {
-            const long long g = g0 + ch * 32 + lane;
-            const int a = (int)(g % P);
+        const int g = g0 + ch * 32 + lane;
+        const bool pass = (g < total) && !(obj[ch] <= obj_thre);    // kept unless arm_conf[...,1] <= thre (:41)
+        const unsigned mask = __ballot_sync(kFullMask, pass);
+        if (pass) s_list[wib][npass + __popc(mask & ((1u << lane) - 1u))] = (unsigned char)(ch * 32 + lane);
+        npass += __popc(mask);
+    }
+    if (npass == 0) return;                  // nothing of this warp survives: no loc / odm_conf traffic
+    __syncwarp();
+    // 2. decode the passing anchors, one per lane
+    for (int r0 = 0; r0 < npass; r0 += 32) {
+        const int r = r0 + lane;
+        if (r < npass) {
+            const int g = g0 + s_list[wib][r];
+            const int a = g % P;
             boxes_ws[g] = refine_decode(ldg_stream4(arm_loc + g), ldg_stream4(odm_loc + g), __ldg(priors + a), v0, v1);
         }
     }
+    // 3. their odm_conf rows: lane = class, kRowBatch rows in flight
+    const int nseg = (C + 31) >> 5;          // <= 4 (C <= 128)
+    for (int r0 = 0; r0 < npass; r0 += kRowBatch) {
+        float v[kRowBatch][4];
+        int gi[kRowBatch];
 #pragma unroll
-    for (int ch = 0; ch < kChunks; ++ch) {
-        unsigned m = mask[ch];
-        while (m) {
-            const int al = __ffs(m) - 1;
-            m &= m - 1;
-            const long long g = g0 + ch * 32 + al;
-            const int b = (int)(g / P);
-            const int a = (int)(g - (long long)b * P);
-            const float* row = odm_conf + g * C;
-            for (int c0 = 0; c0 < C; c0 += 128) {
-                float v[4];
+        for (int k = 0; k < kRowBatch; ++k) {
+            gi[k] = (r0 + k < npass) ? g0 + s_list[wib][r0 + k] : -1;
+            const float* row = odm_conf + (size_t)(gi[k] < 0 ? 0 : gi[k]) * C;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int c = c0 + k * 32 + lane;
-                    v[k] = (c < C) ? ldg_stream1(row + c) : 0.0f;
-                }
+            for (int sgm = 0; sgm < 4; ++sgm) {
+                const int c = sgm * 32 + lane;
+                v[k][sgm] = (gi[k] >= 0 && sgm < nseg && c < C) ? ldg_stream1(row + c) : -INFINITY;
+            }
+        }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int c = c0 + k * 32 + lane;
-                    // class 0 = background, never evaluated (eval_refinedet_coco.py:213)
-                    if (c < C && c != 0 && v[k] > conf_thresh) {
-                        const int bc = b * C + c;
-                        const int slot = atomicAdd(&cnt[bc], 1);
-                        cand[(size_t)bc * cap + slot] = make_key(v[k], (uint32_t)a);
-                    }
+        for (int k = 0; k < kRowBatch; ++k) {
+            if (gi[k] < 0) continue;
+            const int b = gi[k] / P;
+            const int a = gi[k] - b * P;
+#pragma unroll
+            for (int sgm = 0; sgm < 4; ++sgm) {
+                const int c = sgm * 32 + lane;
+                // class 0 = background, never evaluated (eval_refinedet_coco.py:213)
+                if (sgm < nseg && c < C && c != 0 && v[k][sgm] > conf_thresh) {
+                    const int bc = b * C + c;
+                    const int slot = atomicAdd(&cnt[bc], 1);
+                    cand[(size_t)bc * cap + slot] = make_key(v[k][sgm], (uint32_t)a);
                 }
             }
         }
@@ -442,12 +454,13 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     cudaStream_t st = (cudaStream_t)stream;
 
     const long long total = (long long)B * P;
+    if (total > 0x7fffffffLL - 32 * kChunks) return RD_ERR_UNSUPPORTED;
     const long long warps = (total + 32 * kChunks - 1) / (32 * kChunks);
     const int blocks = (int)((warps * 32 + kCollectThreads - 1) / kCollectThreads);
     if (ev) cudaEventRecord(ev[0], st);
     collect_kernel<<<blocks, kCollectThreads, 0, st>>>(
         (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
-        total, P, C, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.cap);
+        (int)total, P, C, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.cap);
     note_launch();
     RD_CHECK_LAUNCH();
 

@@ -371,72 +371,46 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
 
 
 // =========================================================================================
-// warp-per-problem path: n <= 256 candidates, no select needed.  One warp sorts the keys in
-// registers (bitonic network, R = 1/2/4/8 keys per lane, cross-lane steps by shuffle), stages
-// boxes and the bin tables in its private slice of shared memory and walks the score order;
-// rows are emitted straight from the walk.  No CTA-wide barrier anywhere.
+// warp-per-problem path: n <= 256 candidates, no select needed.  One warp
+//   1. sorts the keys 32 at a time in registers (bitonic network over shuffles) and merges
+//      the sorted runs by rank (binary search of every key in the other runs),
+//   2. stages boxes and the bin tables in its private slice of shared memory,
+//   3. walks the score order 32 candidates at a time; the (candidate, kept-earlier-box) pairs
+//      that survive the bin cull are flattened into a list and tested 32 pairs per step, so a
+//      few large boxes that overlap many others do not serialise the warp,
+//   4. emits rows straight from the walk.
+// No CTA-wide barrier anywhere.
 // =========================================================================================
 constexpr int kWarpCap = 256;
 constexpr int kWarpW = kWarpCap / 32;      // 8 mask words
 constexpr int kWarpWS = kWarpW + 1;        // padded row stride
+constexpr int kPairCap = 384;              // flattened (candidate, earlier box) pairs per 32-candidate block
 struct WarpSmem {
     unsigned long long keys[kWarpCap];
-    float x1[kWarpCap], y1[kWarpCap], x2[kWarpCap], y2[kWarpCap], area[kWarpCap];
-    uint32_t cr[kWarpCap];
+    float x1[kWarpCap], y1[kWarpCap], x2[kWarpCap], y2[kWarpCap], area[kWarpCap];   // x1,y1 double as the
+                                                                                    // sorted-runs buffer
     uint32_t tab[4 * kCols * kWarpWS];
+    uint32_t pairs[kPairCap];
     uint32_t keptbits[kWarpW];
-    uint32_t pad[8];
+    uint32_t tin[32];
+    uint32_t sup;
+    uint32_t pad[7];
 };
 
-template <int R>
-__device__ __forceinline__ void warp_bitonic_desc(unsigned long long (&k)[R], int lane) {
-    // element index e = lane * R + r ; N = 32 * R elements ; result descending in e
-    constexpr int N = 32 * R;
+// 32 keys, one per lane, sorted descending across lanes
+__device__ __forceinline__ unsigned long long warp_sort32_desc(unsigned long long a, int lane) {
 #pragma unroll
-    for (int k2 = 2; k2 <= N; k2 <<= 1) {
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
 #pragma unroll
         for (int j = k2 >> 1; j > 0; j >>= 1) {
-            if (j < R) {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if ((r & j) == 0) {
-                        const int e = lane * R + r;
-                        const bool desc = (e & k2) == 0;
-                        unsigned long long a = k[r], b = k[r | j];
-                        const bool sw = (a < b) == desc;
-                        k[r] = sw ? b : a;
-                        k[r | j] = sw ? a : b;
-                    }
-                }
-            } else {
-                const int lj = j / R;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const int e = lane * R + r;
-                    const bool desc = (e & k2) == 0;
-                    const bool lower = (lane & lj) == 0;
-                    unsigned long long a = k[r];
-                    unsigned long long b = __shfl_xor_sync(kFullMask, a, lj);
-                    const bool take_max = (lower == desc);
-                    k[r] = take_max ? (a > b ? a : b) : (a < b ? a : b);
-                }
-            }
+            const bool desc = (lane & k2) == 0;
+            const bool lower = (lane & j) == 0;
+            const unsigned long long b = __shfl_xor_sync(kFullMask, a, j);
+            const bool take_max = (lower == desc);
+            a = take_max ? (a > b ? a : b) : (a < b ? a : b);
         }
     }
-}
-
-template <int R>
-__device__ __forceinline__ void warp_load_sort_store(const unsigned long long* cand, int n, unsigned long long* skeys,
-                                                     int lane) {
-    unsigned long long k[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int e = lane * R + r;
-        k[r] = e < n ? cand[e] : 0ull;
-    }
-    warp_bitonic_desc<R>(k, lane);
-#pragma unroll
-    for (int r = 0; r < R; ++r) skeys[lane * R + r] = k[r];
+    return a;
 }
 
 struct RowSink {           // where the fused stage writes its rows
@@ -449,24 +423,63 @@ struct RowSink {           // where the fused stage writes its rows
 __device__ inline int warp_nms_small(WarpSmem& S, const NmsProblem& pb, const RowSink& sink) {
     const int lane = threadIdx.x & 31;
     const int m = pb.n;                                   // caller guarantees n <= min(top_k, kWarpCap)
-    if (m <= 32) warp_load_sort_store<1>(pb.cand, m, S.keys, lane);
-    else if (m <= 64) warp_load_sort_store<2>(pb.cand, m, S.keys, lane);
-    else if (m <= 128) warp_load_sort_store<4>(pb.cand, m, S.keys, lane);
-    else warp_load_sort_store<8>(pb.cand, m, S.keys, lane);
     const int Wm = (m + 31) >> 5;
-    for (int i = lane; i < 4 * kCols * kWarpWS; i += 32) S.tab[i] = 0;
-    __syncwarp();
+    const uint32_t lt_mask = (1u << lane) - 1u;
 
+    // ---- 1. sort: runs of 32 in registers, then merge by rank -------------------------------
+    unsigned long long* runs = reinterpret_cast<unsigned long long*>(S.x1);   // 256 x 8 B = x1 + y1
+    for (int blk = 0; blk < Wm; ++blk) {
+        const int e = blk * 32 + lane;
+        unsigned long long k = e < m ? pb.cand[e] : 0ull;
+        k = warp_sort32_desc(k, lane);
+        if (Wm == 1) S.keys[lane] = k; else runs[e] = k;
+    }
+    for (int i = lane; i < 4 * kCols * kWarpWS; i += 32) S.tab[i] = 0;
+    if (lane == 0) S.sup = 0;
+    S.tin[lane] = 0;
+    __syncwarp();
+    if (Wm > 1) {
+        for (int blk = 0; blk < Wm; ++blk) {
+            const unsigned long long k = runs[blk * 32 + lane];
+            int pos = lane;
+            for (int ob = 0; ob < Wm; ++ob) {
+                if (ob == blk) continue;
+                const unsigned long long* r = runs + ob * 32;
+                int lo = 0;                         // number of keys of run `ob` greater than k
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
+                    if (r[lo + step - 1] > k) lo += step;
+                if (lo == 31 && r[31] > k) lo = 32;
+                pos += lo;
+            }
+            if (k != 0ull) S.keys[pos] = k;         // zero = padding, sorts last
+        }
+        __syncwarp();
+    }
+
+    // ---- 2. boxes, bin tables ----------------------------------------------------------------
     const bool pixel = (pb.flags & RD_NMS_PIXEL_PLUS1) != 0;
     uint32_t mnx = 0xffffffffu, mxx = 0, mny = 0xffffffffu, mxy = 0;
-    for (int j = lane; j < m; j += 32) {
-        float4 b = pb.boxes[key_index(S.keys[j])];
-        if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
-        float area = pixel ? (b.z - b.x + 1.0f) * (b.w - b.y + 1.0f) : (b.z - b.x) * (b.w - b.y);
-        S.x1[j] = b.x; S.y1[j] = b.y; S.x2[j] = b.z; S.y2[j] = b.w; S.area[j] = area;
-        float cx = 0.5f * b.x + 0.5f * b.z, cy = 0.5f * b.y + 0.5f * b.w;
-        if (isfinite(cx)) { mnx = min(mnx, float_to_ordered(cx)); mxx = max(mxx, float_to_ordered(cx)); }
-        if (isfinite(cy)) { mny = min(mny, float_to_ordered(cy)); mxy = max(mxy, float_to_ordered(cy)); }
+    float bx1[kWarpW], by1[kWarpW], bx2[kWarpW], by2[kWarpW], bar[kWarpW];
+#pragma unroll
+    for (int ib = 0; ib < kWarpW; ++ib) {
+        const int j = ib * 32 + lane;
+        bx1[ib] = by1[ib] = bx2[ib] = by2[ib] = bar[ib] = 0.f;
+        if (ib < Wm && j < m) {
+            float4 b = pb.boxes[key_index(S.keys[j])];
+            if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
+            bx1[ib] = b.x; by1[ib] = b.y; bx2[ib] = b.z; by2[ib] = b.w;
+            bar[ib] = pixel ? (b.z - b.x + 1.0f) * (b.w - b.y + 1.0f) : (b.z - b.x) * (b.w - b.y);
+            float cx = 0.5f * b.x + 0.5f * b.z, cy = 0.5f * b.y + 0.5f * b.w;
+            if (isfinite(cx)) { mnx = min(mnx, float_to_ordered(cx)); mxx = max(mxx, float_to_ordered(cx)); }
+            if (isfinite(cy)) { mny = min(mny, float_to_ordered(cy)); mxy = max(mxy, float_to_ordered(cy)); }
+        }
+    }
+    __syncwarp();                                   // all lanes are done reading `runs`
+#pragma unroll
+    for (int ib = 0; ib < kWarpW; ++ib) {
+        const int j = ib * 32 + lane;
+        if (ib < Wm && j < m) { S.x1[j] = bx1[ib]; S.y1[j] = by1[ib]; S.x2[j] = bx2[ib]; S.y2[j] = by2[ib]; S.area[j] = bar[ib]; }
     }
     mnx = __reduce_min_sync(kFullMask, mnx); mxx = __reduce_max_sync(kFullMask, mxx);
     mny = __reduce_min_sync(kFullMask, mny); mxy = __reduce_max_sync(kFullMask, mxy);
@@ -486,27 +499,32 @@ __device__ inline int warp_nms_small(WarpSmem& S, const NmsProblem& pb, const Ro
     const bool eq = (pb.flags & RD_NMS_SUPPRESS_EQ) != 0;
     const bool force_full = eq ? !(pb.thr > 0.0f) : !(pb.thr >= 0.0f);
     const float eps = 9.5367431640625e-07f;
-    for (int i = lane; i < m; i += 32) {
-        float x1 = S.x1[i], y1 = S.y1[i], x2 = S.x2[i], y2 = S.y2[i], ar = S.area[i];
-        float hx = pixel ? x2 + 1.0f : x2, hy = pixel ? y2 + 1.0f : y2;
-        int ax, bx, ay, by;
-        bool ok = isfinite(x1) && isfinite(y1) && isfinite(hx) && isfinite(hy) && (ar > 0.0f) && isfinite(ar) &&
-                  !force_full;
-        if (ok) {
-            ax = col_of(x1 - fabsf(x1) * eps, lox, invx);
-            bx = col_of(hx + fabsf(hx) * eps, lox, invx);
-            ay = col_of(y1 - fabsf(y1) * eps, loy, invy);
-            by = col_of(hy + fabsf(hy) * eps, loy, invy);
-        } else {
-            ax = 0; bx = kCols - 1; ay = 0; by = kCols - 1;
+    uint32_t crr[kWarpW];
+#pragma unroll
+    for (int ib = 0; ib < kWarpW; ++ib) {
+        const int i = ib * 32 + lane;
+        crr[ib] = 0;
+        if (ib < Wm && i < m) {
+            const float x1 = bx1[ib], y1 = by1[ib], x2 = bx2[ib], y2 = by2[ib], ar = bar[ib];
+            const float hx = pixel ? x2 + 1.0f : x2, hy = pixel ? y2 + 1.0f : y2;
+            int ax, bx, ay, by;
+            const bool ok = isfinite(x1) && isfinite(y1) && isfinite(hx) && isfinite(hy) && (ar > 0.0f) &&
+                            isfinite(ar) && !force_full;
+            if (ok) {
+                ax = col_of(x1 - fabsf(x1) * eps, lox, invx);
+                bx = col_of(hx + fabsf(hx) * eps, lox, invx);
+                ay = col_of(y1 - fabsf(y1) * eps, loy, invy);
+                by = col_of(hy + fabsf(hy) * eps, loy, invy);
+            } else {
+                ax = 0; bx = kCols - 1; ay = 0; by = kCols - 1;
+            }
+            crr[ib] = (uint32_t)ax | ((uint32_t)bx << 8) | ((uint32_t)ay << 16) | ((uint32_t)by << 24);
+            const uint32_t bit = 1u << lane;
+            atomicOr(&S.tab[(0 * kCols + ax) * kWarpWS + ib], bit);
+            if (bx + 1 < kCols) atomicOr(&S.tab[(1 * kCols + bx + 1) * kWarpWS + ib], bit);
+            atomicOr(&S.tab[(2 * kCols + ay) * kWarpWS + ib], bit);
+            if (by + 1 < kCols) atomicOr(&S.tab[(3 * kCols + by + 1) * kWarpWS + ib], bit);
         }
-        S.cr[i] = (uint32_t)ax | ((uint32_t)bx << 8) | ((uint32_t)ay << 16) | ((uint32_t)by << 24);
-        const uint32_t bit = 1u << (i & 31);
-        const int w = i >> 5;
-        atomicOr(&S.tab[(0 * kCols + ax) * kWarpWS + w], bit);
-        if (bx + 1 < kCols) atomicOr(&S.tab[(1 * kCols + bx + 1) * kWarpWS + w], bit);
-        atomicOr(&S.tab[(2 * kCols + ay) * kWarpWS + w], bit);
-        if (by + 1 < kCols) atomicOr(&S.tab[(3 * kCols + by + 1) * kWarpWS + w], bit);
     }
     __syncwarp();
     for (int task = lane; task < 4 * Wm; task += 32) {
@@ -518,6 +536,7 @@ __device__ inline int warp_nms_small(WarpSmem& S, const NmsProblem& pb, const Ro
     }
     __syncwarp();
 
+    // ---- 3. walk -----------------------------------------------------------------------------
     const float thr = pb.thr;
     const int flags = pb.flags;
     const int max_out = pb.max_out;
@@ -526,46 +545,85 @@ __device__ inline int warp_nms_small(WarpSmem& S, const NmsProblem& pb, const Ro
     const uint32_t* Ex = S.tab + 1 * kCols * kWarpWS;
     const uint32_t* Sy = S.tab + 2 * kCols * kWarpWS;
     const uint32_t* Ey = S.tab + 3 * kCols * kWarpWS;
-    for (int ib = 0; ib < Wm; ++ib) {
+#pragma unroll
+    for (int ib = 0; ib < kWarpW; ++ib) {
+        if (ib >= Wm || kept_total >= max_out) break;
         const int j = ib * 32 + lane;
         const bool valid = j < m;
         bool alive = valid;
-        float x1 = 0, y1 = 0, x2 = 0, y2 = 0, ar = 0;
-        uint32_t cr = 0;
-        if (valid) { x1 = S.x1[j]; y1 = S.y1[j]; x2 = S.x2[j]; y2 = S.y2[j]; ar = S.area[j]; cr = S.cr[j]; }
+        const float x1 = bx1[ib], y1 = by1[ib], x2 = bx2[ib], y2 = by2[ib], ar = bar[ib];
+        const uint32_t cr = crr[ib];
         const uint32_t* rSx = Sx + ((cr >> 8) & 255u) * kWarpWS;
         const uint32_t* rEx = Ex + (cr & 255u) * kWarpWS;
         const uint32_t* rSy = Sy + ((cr >> 24) & 255u) * kWarpWS;
         const uint32_t* rEy = Ey + ((cr >> 16) & 255u) * kWarpWS;
-        for (int w = 0; w < ib; ++w) {
-            uint32_t h = rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & S.keptbits[w];
-            while (alive && h) {
-                int i = (w << 5) + __ffs(h) - 1;
-                h &= h - 1;
-                if (suppresses(S.x1[i], S.y1[i], S.x2[i], S.y2[i], S.area[i], x1, y1, x2, y2, ar, thr, flags))
-                    alive = false;
+        // candidate pairs after the bin cull: kept boxes of earlier blocks, earlier lanes of this block
+        uint32_t h[kWarpW];
+        int nh = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpW; ++w) {
+            h[w] = 0;
+            if (w <= ib && valid) {
+                h[w] = rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & (w < ib ? S.keptbits[w] : lt_mask);
+                nh += __popc(h[w]);
             }
         }
+        int off = nh;                                // inclusive scan over lanes
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(kFullMask, off, d); if (lane >= d) off += o; }
+        const int total = __shfl_sync(kFullMask, off, 31);
+        off -= nh;
         uint32_t tin = 0;
-        if (alive) {
-            uint32_t h = rSx[ib] & ~rEx[ib] & rSy[ib] & ~rEy[ib] & ((1u << lane) - 1u);
-            while (h) {
-                int k = __ffs(h) - 1;
-                h &= h - 1;
-                int i = (ib << 5) + k;
-                if (suppresses(S.x1[i], S.y1[i], S.x2[i], S.y2[i], S.area[i], x1, y1, x2, y2, ar, thr, flags))
-                    tin |= 1u << k;
+        if (total > 0 && total <= kPairCap) {
+#pragma unroll
+            for (int w = 0; w < kWarpW; ++w) {
+                uint32_t hw = h[w];
+                while (hw) {
+                    const int i = (w << 5) + __ffs(hw) - 1;
+                    hw &= hw - 1;
+                    S.pairs[off++] = ((uint32_t)lane << 16) | (uint32_t)i;
+                }
+            }
+            __syncwarp();
+            for (int p = lane; p < total; p += 32) {
+                const uint32_t e = S.pairs[p];
+                const int jl = (int)(e >> 16), i = (int)(e & 0xffffu);
+                const int jj = ib * 32 + jl;
+                if (suppresses(S.x1[i], S.y1[i], S.x2[i], S.y2[i], S.area[i], S.x1[jj], S.y1[jj], S.x2[jj], S.y2[jj],
+                               S.area[jj], thr, flags)) {
+                    if (i < ib * 32) atomicOr(&S.sup, 1u << jl);
+                    else atomicOr(&S.tin[jl], 1u << (i - ib * 32));
+                }
+            }
+            __syncwarp();
+            if ((S.sup >> lane) & 1u) alive = false;
+            tin = S.tin[lane];
+            __syncwarp();
+            S.tin[lane] = 0;
+            if (lane == 0) S.sup = 0;
+        } else if (total > 0) {                      // pair list would overflow: test in place
+#pragma unroll
+            for (int w = 0; w < kWarpW; ++w) {
+                uint32_t hw = h[w];
+                while (hw && (alive || w == ib)) {
+                    const int i = (w << 5) + __ffs(hw) - 1;
+                    hw &= hw - 1;
+                    if (suppresses(S.x1[i], S.y1[i], S.x2[i], S.y2[i], S.area[i], x1, y1, x2, y2, ar, thr, flags)) {
+                        if (w < ib) alive = false; else tin |= 1u << (i - ib * 32);
+                    }
+                }
             }
         }
-        uint32_t u = __reduce_or_sync(kFullMask, tin);
+        // in-block resolution in score order
+        uint32_t u = __reduce_or_sync(kFullMask, alive ? tin : 0u);
         while (u) {
-            int k = __ffs(u) - 1;
+            const int k = __ffs(u) - 1;
             u &= u - 1;
-            uint32_t al = __ballot_sync(kFullMask, alive);
+            const uint32_t al = __ballot_sync(kFullMask, alive);
             if (((al >> k) & 1u) && ((tin >> k) & 1u)) alive = false;
         }
         uint32_t keptw = __ballot_sync(kFullMask, alive);
-        int room = max_out - kept_total;
+        const int room = max_out - kept_total;
         int cnt = __popc(keptw);
         if (cnt > room) {
             uint32_t t = keptw, keep = 0;
@@ -574,7 +632,7 @@ __device__ inline int warp_nms_small(WarpSmem& S, const NmsProblem& pb, const Ro
             cnt = room;
         }
         if ((keptw >> lane) & 1u) {
-            const int t = kept_total + __popc(keptw & ((1u << lane) - 1u));
+            const int t = kept_total + __popc(keptw & lt_mask);
             const unsigned long long key = S.keys[j];
             const float sc = key_score(key);
             float* r = sink.rows + (size_t)t * 5;
@@ -585,7 +643,6 @@ __device__ inline int warp_nms_small(WarpSmem& S, const NmsProblem& pb, const Ro
         if (lane == 0) S.keptbits[ib] = keptw;
         __syncwarp();
         kept_total += cnt;
-        if (kept_total >= max_out) break;
     }
     return kept_total;
 }
