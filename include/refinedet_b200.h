@@ -20,8 +20,8 @@
  *     CUDA failure, or a negative `RD_ERR_*` code on an argument error.
  *     `rd_error_string` turns either into text.
  *   - workspaces are caller-owned and reusable; `rd_*_workspace_bytes` gives the
- *     size.  A detect workspace must be zero-filled ONCE before first use
- *     (`rd_detect_workspace_reset`); every call leaves it ready for the next.
+ *     size.  A detect workspace should be passed through `rd_detect_workspace_reset` once
+ *     before first use; every call leaves it ready for the next.
  */
 #ifndef REFINEDET_B200_H_
 #define REFINEDET_B200_H_
@@ -120,7 +120,7 @@ RD_API int rd_detect_fused(const float* arm_loc, const float* arm_conf, const fl
 
 /* Diagnostics twin of rd_detect_fused: records CUDA events between the stage's kernels on
  * `stream`, WAITS for the stage, and writes the device time in ms of
- * {collect_kernel, nms_fused_kernel, reserved = 0} to stage_ms_host[3] (host pointer). */
+ * {collect_kernel, nms_small_kernel, nms_large_kernel} to stage_ms_host[3] (host pointer). */
 RD_API int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, const float* odm_loc,
                     const float* odm_conf, const float* priors, int B, int P, int C,
                     float objectness_thre, float conf_thresh, float nms_thresh,

@@ -5,14 +5,16 @@
 //
 // Kernels
 //   detect_forward_kernel   a3: ARM filter + two-stage decode, dense boxes/scores, in-place zeroing
-//   collect_kernel          K1: ARM filter, decode of passing anchors, per-(image,class)
-//                           candidate lists.  Data-dependent traffic: odm_conf / loc rows of
-//                           ARM-filtered anchors are never fetched.
-//   nms_fused_kernel        K2+K3: one WARP per (image,class) problem with <= 256 candidates
-//                           (register bitonic sort, no CTA barrier); problems that need the
-//                           top-k select or hold more boxes are then run CTA-wide by the same CTA
+//   collect_kernel          K1: one CTA per (image, slice of 1024 anchors).  ARM filter, decode of the
+//                           passing anchors, per-class candidate sub-lists.  Slots are reserved with
+//                           SHARED-memory atomics (the CTA owns its sub-list), so there is no global
+//                           atomic and nothing to reset between calls.  odm_conf / loc rows of
+//                           ARM-filtered anchors are never fetched: traffic scales with the pass rate.
+//   nms_small_kernel        K2+K3: one 64-thread CTA per (image, class) with <= 256 candidates,
+//                           12.7 KB shared memory -> 16 CTAs resident per SM; other problems are queued
+//   nms_large_kernel        persistent CTAs draining the queue (radix select when n > top_k)
 //   nms_single_kernel       stand-alone problem (rd_nms / rd_nms_host)
-//   pack_kernel             slot layout -> packed rows
+//   pack kernels            slot layout -> packed rows
 #include "rd_nms_core.cuh"
 
 #include <atomic>
@@ -23,18 +25,25 @@ static std::atomic<unsigned long long> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 constexpr int kCollectThreads = 256;
+constexpr int kSliceAnchors = 1024;   // anchors per collect CTA = capacity of one candidate sub-list
+constexpr int kLargeThreads = 128;
 
 // ---------------------------------------------------------------------------------------
-// workspace of the fused stage
-//   cnt    int  [B*C]        : candidate counts (zero between calls)
-//   boxes  f4   [B*P]        : decoded boxes of ARM-passing anchors
-//   cand   u64  [B*C*cap]    : candidate keys, capacity cap = P rounded up to even per (image,class)
+// workspace of the fused stage (nothing in it needs initialisation except the queue header,
+// which collect_kernel clears on every call)
+//   header u32 [64]           : [0] = number of queued large problems
+//   queue  int [B*C]          : (image,class) problems routed to nms_large_kernel
+//   cnt    int [B*C*S]        : candidate count of every sub-list, S = ceil(P / 1024)
+//   boxes  f4  [B*P]          : decoded boxes of ARM-passing anchors
+//   cand   u64 [B*C*S*1024]   : candidate keys, sub-list (b,c,s) written by collect CTA (s,b)
 // ---------------------------------------------------------------------------------------
 struct DetectWs {
+    uint32_t* header;
+    int* queue;
     int* cnt;
     float4* boxes;
     unsigned long long* cand;
-    int cap;
+    int S;
     size_t total;
 };
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -42,10 +51,12 @@ static DetectWs carve_ws(void* base, int B, int P, int C) {
     DetectWs w;
     size_t o = 0;
     unsigned char* p = static_cast<unsigned char*>(base);
-    w.cap = (P + 1) & ~1;
-    w.cnt = reinterpret_cast<int*>(p + o);                     o += align_up((size_t)B * C * 4, 256);
+    w.S = (P + kSliceAnchors - 1) / kSliceAnchors;
+    w.header = reinterpret_cast<uint32_t*>(p + o);             o += 256;
+    w.queue = reinterpret_cast<int*>(p + o);                   o += align_up((size_t)B * C * 4, 256);
+    w.cnt = reinterpret_cast<int*>(p + o);                     o += align_up((size_t)B * C * w.S * 4, 256);
     w.boxes = reinterpret_cast<float4*>(p + o);                o += align_up((size_t)B * P * 16, 256);
-    w.cand = reinterpret_cast<unsigned long long*>(p + o);     o += align_up((size_t)B * C * w.cap * 8, 256);
+    w.cand = reinterpret_cast<unsigned long long*>(p + o);     o += align_up((size_t)B * C * w.S * kSliceAnchors * 8, 256);
     w.total = o;
     return w;
 }
@@ -118,99 +129,100 @@ detect_forward_kernel(const float4* __restrict__ arm_loc, const float2* __restri
 }
 
 // ---------------------------------------------------------------------------------------
-// K1: ARM filter + decode + candidate collection.
-// Each warp owns kChunks x 32 consecutive rows of the flattened [B*P] anchor axis: the
-// arm_conf loads of all chunks are issued first (memory-level parallelism), then the warp
-// visits ONLY the anchors that pass the ARM filter; their odm_conf rows are read with
-// coalesced 128 B requests (lane = class).  Rows / loc vectors of filtered anchors are never
-// touched, so DRAM traffic scales with the pass fraction, not with B*P*C.
+// K1: ARM filter + decode + candidate collection
+// grid = (S, B); CTA (s, b) owns anchors [s*1024, s*1024 + 1024) of image b: 8 warps x 128 anchors.
 // ---------------------------------------------------------------------------------------
-constexpr int kChunks = 4;
-constexpr int kRowBatch = 4;     // odm_conf rows in flight per warp
+constexpr int kChunks = kSliceAnchors / (kCollectThreads / 32) / 32;   // 32-anchor chunks per warp = 4
+constexpr int kRowBatch = 4;                                           // odm_conf rows in flight per warp
+constexpr int kMaxClasses = 128;
 
 __global__ void __launch_bounds__(kCollectThreads)
 collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ arm_conf,
                const float4* __restrict__ odm_loc, const float* __restrict__ odm_conf,
-               const float4* __restrict__ priors, int total, int P, int C, float obj_thre,
-               float conf_thresh, float v0, float v1, float4* __restrict__ boxes_ws, int* cnt,
-               unsigned long long* cand, int cap) {
+               const float4* __restrict__ priors, int P, int C, int S, float obj_thre,
+               float conf_thresh, float v0, float v1, float4* __restrict__ boxes_ws, int* __restrict__ cnt,
+               unsigned long long* __restrict__ cand, uint32_t* header) {
     __shared__ unsigned char s_list[kCollectThreads / 32][32 * kChunks];   // passing anchors of each warp
+    __shared__ int s_cnt[kMaxClasses];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int warp_global = (int)(((long long)blockIdx.x * kCollectThreads + threadIdx.x) >> 5);
-    const long long g0l = (long long)warp_global * (32 * kChunks);
-    if (g0l >= total) return;
-    const int g0 = (int)g0l;
+    const int s = blockIdx.x, b = blockIdx.y;
+    if (s == 0 && b == 0 && threadIdx.x == 0) header[0] = 0;          // queue of the large-NMS kernel
+    for (int c = threadIdx.x; c < C; c += kCollectThreads) s_cnt[c] = 0;
+    __syncthreads();
+    const int a0 = s * kSliceAnchors + wib * (32 * kChunks);          // first anchor of this warp
+    const size_t img = (size_t)b * P;
     // 1. ARM filter for 32*kChunks anchors; all loads issued before the first use
     float obj[kChunks];
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
-        const int g = g0 + ch * 32 + lane;
-        obj[ch] = (g < total) ? ldg_stream2(arm_conf + g).y : -INFINITY;
+        const int a = a0 + ch * 32 + lane;
+        obj[ch] = (a < P) ? ldg_stream2(arm_conf + img + a).y : -INFINITY;
     }
     int npass = 0;
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
-        const int g = g0 + ch * 32 + lane;
-        const bool pass = (g < total) && !(obj[ch] <= obj_thre);    // kept unless arm_conf[...,1] <= thre (:41)
+        const int a = a0 + ch * 32 + lane;
+        const bool pass = (a < P) && !(obj[ch] <= obj_thre);           // kept unless arm_conf[...,1] <= thre (:41)
         const unsigned mask = __ballot_sync(kFullMask, pass);
         if (pass) s_list[wib][npass + __popc(mask & ((1u << lane) - 1u))] = (unsigned char)(ch * 32 + lane);
         npass += __popc(mask);
     }
-    if (npass == 0) return;                  // nothing of this warp survives: no loc / odm_conf traffic
     __syncwarp();
     // 2. decode the passing anchors, one per lane
     for (int r0 = 0; r0 < npass; r0 += 32) {
         const int r = r0 + lane;
         if (r < npass) {
-            const int g = g0 + s_list[wib][r];
-            const int a = g % P;
-            boxes_ws[g] = refine_decode(ldg_stream4(arm_loc + g), ldg_stream4(odm_loc + g), __ldg(priors + a), v0, v1);
+            const int a = a0 + s_list[wib][r];
+            boxes_ws[img + a] = refine_decode(ldg_stream4(arm_loc + img + a), ldg_stream4(odm_loc + img + a),
+                                              __ldg(priors + a), v0, v1);
         }
     }
     // 3. their odm_conf rows: lane = class, kRowBatch rows in flight
     const int nseg = (C + 31) >> 5;          // <= 4 (C <= 128)
+    unsigned long long* cand_b = cand + ((size_t)b * C * S + s) * kSliceAnchors;    // + c * S * 1024 per class
     for (int r0 = 0; r0 < npass; r0 += kRowBatch) {
         float v[kRowBatch][4];
-        int gi[kRowBatch];
+        int ai[kRowBatch];
 #pragma unroll
         for (int k = 0; k < kRowBatch; ++k) {
-            gi[k] = (r0 + k < npass) ? g0 + s_list[wib][r0 + k] : -1;
-            const float* row = odm_conf + (size_t)(gi[k] < 0 ? 0 : gi[k]) * C;
+            ai[k] = (r0 + k < npass) ? a0 + s_list[wib][r0 + k] : -1;
+            const float* row = odm_conf + (img + (ai[k] < 0 ? 0 : ai[k])) * C;
 #pragma unroll
             for (int sgm = 0; sgm < 4; ++sgm) {
                 const int c = sgm * 32 + lane;
-                v[k][sgm] = (gi[k] >= 0 && sgm < nseg && c < C) ? ldg_stream1(row + c) : -INFINITY;
+                v[k][sgm] = (ai[k] >= 0 && sgm < nseg && c < C) ? ldg_stream1(row + c) : -INFINITY;
             }
         }
 #pragma unroll
         for (int k = 0; k < kRowBatch; ++k) {
-            if (gi[k] < 0) continue;
-            const int b = gi[k] / P;
-            const int a = gi[k] - b * P;
+            if (ai[k] < 0) continue;
 #pragma unroll
             for (int sgm = 0; sgm < 4; ++sgm) {
                 const int c = sgm * 32 + lane;
                 // class 0 = background, never evaluated (eval_refinedet_coco.py:213)
                 if (sgm < nseg && c < C && c != 0 && v[k][sgm] > conf_thresh) {
-                    const int bc = b * C + c;
-                    const int slot = atomicAdd(&cnt[bc], 1);
-                    cand[(size_t)bc * cap + slot] = make_key(v[k][sgm], (uint32_t)a);
+                    const int slot = atomicAdd(&s_cnt[c], 1);          // shared-memory atomic, < 1024 by construction
+                    cand_b[(size_t)c * S * kSliceAnchors + slot] = make_key(v[k][sgm], (uint32_t)ai[k]);
                 }
             }
         }
     }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kCollectThreads) cnt[((size_t)b * C + c) * S + s] = s_cnt[c];
 }
 
 // ---------------------------------------------------------------------------------------
 // K2+K3
 // ---------------------------------------------------------------------------------------
 struct FusedNmsArgs {
-    int* cnt;                        // [B*C]
-    const unsigned long long* cand;  // [B*C*cap]
+    const int* cnt;                  // [B*C*S]
+    const unsigned long long* cand;  // [B*C*S*1024]
     const float4* boxes;             // [B*P]
     const float* img_scale;          // [B,4] or null
-    int nbc, C, P, cap;
+    int* queue;
+    uint32_t* header;
+    int nbc, C, P, S;
     float thr;
     int top_k, max_out, flags, row_layout;
     int* out_counts;
@@ -218,11 +230,35 @@ struct FusedNmsArgs {
     int* out_anchor;
 };
 
-__device__ __forceinline__ NmsProblem make_problem(int bc, int n, const FusedNmsArgs& A) {
+// slice counts -> shared memory + exclusive prefix sums; returns n (uniform).  One warp's worth of work.
+__device__ __forceinline__ int load_slice_counts(const int* __restrict__ gcnt, int S, int* s_cnt, int* s_offs) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int run = 0;
+        for (int base = 0; base < S; base += 32) {
+            const int sidx = base + lane;
+            const int c = sidx < S ? gcnt[sidx] : 0;
+            int x = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, x, d); if (lane >= d) x += o; }
+            if (sidx < S) { s_cnt[sidx] = c; s_offs[sidx] = run + x - c; }
+            run += __shfl_sync(kFullMask, x, 31);
+        }
+        if (lane == 0) s_offs[S] = run;
+    }
+    __syncthreads();
+    return s_offs[S];
+}
+
+__device__ __forceinline__ void fill_problem(NmsProblem& pb, RowSink& sink, int bc, int n, const int* s_cnt,
+                                             const int* s_offs, const FusedNmsArgs& A) {
     const int b = bc / A.C;
-    NmsProblem pb;
-    pb.cand = A.cand + (size_t)bc * A.cap;
-    pb.n = n;
+    pb.cl.base = A.cand + (size_t)bc * A.S * kSliceAnchors;
+    pb.cl.S = A.S;
+    pb.cl.stride = kSliceAnchors;
+    pb.cl.cnt = s_cnt;
+    pb.cl.offs = s_offs;
+    pb.cl.n = n;
     pb.boxes = A.boxes + (size_t)b * A.P;
     pb.has_scale = A.img_scale != nullptr;
     pb.scale = pb.has_scale ? __ldg(reinterpret_cast<const float4*>(A.img_scale) + b) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -230,80 +266,53 @@ __device__ __forceinline__ NmsProblem make_problem(int bc, int n, const FusedNms
     pb.top_k = A.top_k;
     pb.max_out = A.max_out;
     pb.flags = A.flags;
-    return pb;
+    sink.rows = A.out_dets + (size_t)bc * A.max_out * 5;
+    sink.anchors = A.out_anchor ? A.out_anchor + (size_t)bc * A.max_out : nullptr;
+    sink.keep64 = nullptr;
+    sink.keep32 = nullptr;
+    sink.row_layout = A.row_layout;
 }
 
-__device__ __forceinline__ void emit_rows(unsigned char* smem, const NmsSmemLayout& L, int kept, int bc,
-                                          const FusedNmsArgs& A) {
-    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(smem + L.off_keys);
-    const float* sx1 = reinterpret_cast<const float*>(smem + L.off_x1);
-    const float* sy1 = reinterpret_cast<const float*>(smem + L.off_y1);
-    const float* sx2 = reinterpret_cast<const float*>(smem + L.off_x2);
-    const float* sy2 = reinterpret_cast<const float*>(smem + L.off_y2);
-    const int* keptidx = reinterpret_cast<const int*>(smem + L.off_keptidx);
-    float* rows = A.out_dets + (size_t)bc * A.max_out * 5;
-    for (int t = threadIdx.x; t < kept; t += kNmsThreads) {
-        int j = keptidx[t];
-        unsigned long long k = keys[j];
-        float s = key_score(k);
-        float* r = rows + (size_t)t * 5;
-        if (A.row_layout == RD_ROW_SCORE_BOX) {
-            r[0] = s; r[1] = sx1[j]; r[2] = sy1[j]; r[3] = sx2[j]; r[4] = sy2[j];
-        } else {
-            r[0] = sx1[j]; r[1] = sy1[j]; r[2] = sx2[j]; r[3] = sy2[j]; r[4] = s;
-        }
-        if (A.out_anchor) A.out_anchor[(size_t)bc * A.max_out + t] = (int)key_index(k);
+__global__ void __launch_bounds__(kSmallThreads, 16)
+nms_small_kernel(FusedNmsArgs A) {
+    __shared__ SmallSmem S;
+    const int bc = blockIdx.x;
+    const int c = bc % A.C;
+    if (c == 0) {                      // background is never evaluated (eval_refinedet_coco.py:213)
+        if (threadIdx.x == 0) A.out_counts[bc] = 0;
+        return;
     }
+    const int n = load_slice_counts(A.cnt + (size_t)bc * A.S, A.S, S.cnt, S.offs);
+    if (n == 0) {
+        if (threadIdx.x == 0) A.out_counts[bc] = 0;
+        return;
+    }
+    if (n > A.top_k || n > kSmallCap) {
+        if (threadIdx.x == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
+        return;
+    }
+    NmsProblem pb;
+    RowSink sink;
+    fill_problem(pb, sink, bc, n, S.cnt, S.offs, A);
+    const int kept = cta_nms_small(S, pb, sink);
+    if (threadIdx.x == 0) A.out_counts[bc] = kept;
 }
 
-constexpr int kWarpsPerCta = kNmsThreads / 32;
-
-__global__ void __launch_bounds__(kNmsThreads)
-nms_fused_kernel(FusedNmsArgs A, int mcap_large) {
+__global__ void __launch_bounds__(kLargeThreads)
+nms_large_kernel(FusedNmsArgs A, int mcap) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_large[kWarpsPerCta];
-    __shared__ int s_nlarge;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_nlarge = 0;
-    __syncthreads();
-    const int bc = blockIdx.x * kWarpsPerCta + warp;
-    if (bc < A.nbc) {
-        const int c = bc % A.C;
-        int n = 0;
-        if (c != 0) n = A.cnt[bc];           // class 0 = background, never evaluated
-        if (n == 0) {
-            if (lane == 0) A.out_counts[bc] = 0;
-        } else if (n <= A.top_k && n <= kWarpCap) {
-            WarpSmem& S = *reinterpret_cast<WarpSmem*>(smem + (size_t)warp * sizeof(WarpSmem));
-            NmsProblem pb = make_problem(bc, n, A);
-            RowSink sink;
-            sink.rows = A.out_dets + (size_t)bc * A.max_out * 5;
-            sink.anchors = A.out_anchor ? A.out_anchor + (size_t)bc * A.max_out : nullptr;
-            sink.row_layout = A.row_layout;
-            const int kept = warp_nms_small(S, pb, sink);
-            if (lane == 0) {
-                A.out_counts[bc] = kept;
-                A.cnt[bc] = 0;                // leave the workspace ready for the next call
-            }
-        } else if (lane == 0) {
-            s_large[atomicAdd(&s_nlarge, 1)] = bc;
-        }
-    }
-    __syncthreads();
-    const int nlarge = s_nlarge;
-    if (nlarge == 0) return;
-    const NmsSmemLayout L = nms_layout(mcap_large);
-    for (int q = 0; q < nlarge; ++q) {
-        const int lbc = s_large[q];
-        const int n = A.cnt[lbc];
-        NmsProblem pb = make_problem(lbc, n, A);
-        const int kept = nms_process(smem, L, pb);
-        emit_rows(smem, L, kept, lbc, A);
-        if (threadIdx.x == 0) {
-            A.out_counts[lbc] = kept;
-            A.cnt[lbc] = 0;
-        }
+    const NmsSmemLayout L = nms_layout(mcap);
+    int* s_cnt = reinterpret_cast<int*>(smem + L.off_cnt);
+    int* s_offs = reinterpret_cast<int*>(smem + L.off_offs);
+    const uint32_t nq = A.header[0];
+    for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
+        const int bc = A.queue[q];
+        const int n = load_slice_counts(A.cnt + (size_t)bc * A.S, A.S, s_cnt, s_offs);
+        NmsProblem pb;
+        RowSink sink;
+        fill_problem(pb, sink, bc, n, s_cnt, s_offs, A);
+        const int kept = nms_process(smem, L, pb, sink);
+        if (threadIdx.x == 0) A.out_counts[bc] = kept;
         __syncthreads();
     }
 }
@@ -324,23 +333,23 @@ __global__ void strip_boxes_kernel(const float* __restrict__ dets, int n, int di
                                       dets[(size_t)i * dim + 3]);
 }
 
-__global__ void __launch_bounds__(kNmsThreads)
+__global__ void __launch_bounds__(kLargeThreads)
 nms_single_kernel(const unsigned long long* cand, int n, const float4* boxes, float thr, int top_k, int max_out,
                   int flags, int mcap, long long* keep_out, int* keep_out32, int* count_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const NmsSmemLayout L = nms_layout(mcap);
+    int* s_cnt = reinterpret_cast<int*>(smem + L.off_cnt);
+    int* s_offs = reinterpret_cast<int*>(smem + L.off_offs);
+    if (threadIdx.x == 0) { s_cnt[0] = n; s_offs[0] = 0; s_offs[1] = n; }
+    __syncthreads();
     NmsProblem pb;
-    pb.cand = cand; pb.n = n; pb.boxes = boxes; pb.has_scale = 0;
+    pb.cl.base = cand; pb.cl.S = 1; pb.cl.stride = n; pb.cl.cnt = s_cnt; pb.cl.offs = s_offs; pb.cl.n = n;
+    pb.boxes = boxes; pb.has_scale = 0;
     pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
     pb.thr = thr; pb.top_k = top_k; pb.max_out = max_out; pb.flags = flags;
-    int kept = nms_process(smem, L, pb);
-    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(smem + L.off_keys);
-    const int* keptidx = reinterpret_cast<const int*>(smem + L.off_keptidx);
-    for (int t = threadIdx.x; t < kept; t += kNmsThreads) {
-        uint32_t idx = key_index(keys[keptidx[t]]);
-        if (keep_out) keep_out[t] = (long long)idx;
-        if (keep_out32) keep_out32[t] = (int)idx;
-    }
+    RowSink sink;
+    sink.rows = nullptr; sink.anchors = nullptr; sink.keep64 = keep_out; sink.keep32 = keep_out32; sink.row_layout = 0;
+    const int kept = nms_process(smem, L, pb, sink);
     if (threadIdx.x == 0) *count_out = kept;
 }
 
@@ -408,7 +417,7 @@ int rd_detect_forward(const float* arm_loc, const float* arm_conf, const float* 
                       float* boxes_out, float* scores_out, void* stream) {
     if (!arm_loc || !arm_conf || !odm_loc || !odm_conf || !priors || !boxes_out || !scores_out) return RD_ERR_BAD_ARG;
     if (B <= 0 || P <= 0 || C <= 0) return RD_ERR_BAD_ARG;
-    if (C > 128) return RD_ERR_UNSUPPORTED;
+    if (C > kMaxClasses) return RD_ERR_UNSUPPORTED;
     if ((((uintptr_t)arm_loc | (uintptr_t)odm_loc | (uintptr_t)priors | (uintptr_t)boxes_out) & 15) ||
         ((uintptr_t)arm_conf & 7))
         return RD_ERR_ALIGNMENT;
@@ -430,21 +439,23 @@ size_t rd_detect_workspace_bytes(int B, int P, int C) {
 
 int rd_detect_workspace_reset(void* workspace, size_t workspace_bytes, void* stream) {
     if (!workspace) return RD_ERR_BAD_ARG;
-    cudaError_t e = cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream);
+    // only the header needs a defined value; the candidate area is write-before-read
+    cudaError_t e = cudaMemsetAsync(workspace, 0, workspace_bytes < 256 ? workspace_bytes : 256, (cudaStream_t)stream);
     return (int)e;
 }
 
 }  // extern "C"
 
 static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
-                    const float* priors, int B, int P, int C, float objectness_thre, float conf_thresh,
-                    float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
-                    int row_layout, float v0, float v1, void* workspace, size_t workspace_bytes,
-                    int* out_counts, float* out_dets, int* out_anchor, void* stream, cudaEvent_t* ev) {
+                             const float* priors, int B, int P, int C, float objectness_thre, float conf_thresh,
+                             float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
+                             int row_layout, float v0, float v1, void* workspace, size_t workspace_bytes,
+                             int* out_counts, float* out_dets, int* out_anchor, void* stream, cudaEvent_t* ev) {
     if (!arm_loc || !arm_conf || !odm_loc || !odm_conf || !priors || !workspace || !out_counts || !out_dets)
         return RD_ERR_BAD_ARG;
     if (B <= 0 || P <= 0 || C <= 0 || top_k <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
-    if (C > 128 || (long long)B * C > (1 << 30)) return RD_ERR_UNSUPPORTED;
+    if (C > kMaxClasses || B > 65535 || (long long)B * C > (1 << 30)) return RD_ERR_UNSUPPORTED;
+    if (P > kMaxSlices * kSliceAnchors) return RD_ERR_UNSUPPORTED;
     if (top_k > RD_MAX_NMS_BOXES) return RD_ERR_UNSUPPORTED;
     if ((((uintptr_t)arm_loc | (uintptr_t)odm_loc | (uintptr_t)priors | (uintptr_t)workspace) & 15) ||
         ((uintptr_t)arm_conf & 7) || (img_scale && ((uintptr_t)img_scale & 15)))
@@ -453,39 +464,51 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     if (workspace_bytes < ws.total) return RD_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
 
-    const long long total = (long long)B * P;
-    if (total > 0x7fffffffLL - 32 * kChunks) return RD_ERR_UNSUPPORTED;
-    const long long warps = (total + 32 * kChunks - 1) / (32 * kChunks);
-    const int blocks = (int)((warps * 32 + kCollectThreads - 1) / kCollectThreads);
     if (ev) cudaEventRecord(ev[0], st);
-    collect_kernel<<<blocks, kCollectThreads, 0, st>>>(
+    collect_kernel<<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
         (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
-        (int)total, P, C, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.cap);
+        P, C, ws.S, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.header);
     note_launch();
     RD_CHECK_LAUNCH();
 
     FusedNmsArgs A;
     A.cnt = ws.cnt; A.cand = ws.cand; A.boxes = ws.boxes; A.img_scale = img_scale;
-    A.nbc = B * C; A.C = C; A.P = P; A.cap = ws.cap;
+    A.queue = ws.queue; A.header = ws.header;
+    A.nbc = B * C; A.C = C; A.P = P; A.S = ws.S;
     A.thr = nms_thresh; A.top_k = top_k; A.max_out = max_out; A.flags = nms_flags; A.row_layout = row_layout;
     A.out_counts = out_counts; A.out_dets = out_dets; A.out_anchor = out_anchor;
 
-    const int mcap = top_k < P ? top_k : P;
-    const size_t smem_large = nms_layout(mcap).total;
-    const size_t smem_warp = (size_t)kWarpsPerCta * sizeof(WarpSmem);
-    const size_t smem_bytes = smem_large > smem_warp ? smem_large : smem_warp;
-    static size_t s_attr = 48 * 1024;
-    if (smem_bytes > s_attr) {
-        cudaError_t e = cudaFuncSetAttribute(nms_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem_bytes);
-        if (e != cudaSuccess) return (int)e;
-        s_attr = smem_bytes;
-    }
     if (ev) cudaEventRecord(ev[1], st);
-    nms_fused_kernel<<<(B * C + kWarpsPerCta - 1) / kWarpsPerCta, kNmsThreads, smem_bytes, st>>>(A, mcap);
+    nms_small_kernel<<<B * C, kSmallThreads, 0, st>>>(A);
     note_launch();
     RD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[2], st);
+    {
+        const int mcap = top_k < P ? top_k : P;
+        const NmsSmemLayout Ll = nms_layout(mcap);
+        static size_t s_attr = 48 * 1024;
+        if (Ll.total > s_attr) {
+            cudaError_t e = cudaFuncSetAttribute(nms_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)Ll.total);
+            if (e != cudaSuccess) return (int)e;
+            s_attr = Ll.total;
+        }
+        static int s_dev_sms = 0;
+        if (s_dev_sms == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&s_dev_sms, cudaDevAttrMultiProcessorCount, dev);
+            if (s_dev_sms <= 0) s_dev_sms = 148;
+        }
+        int per_sm = (int)((220 * 1024) / (Ll.total + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        int grid = s_dev_sms * per_sm;
+        if (grid > B * C) grid = B * C;
+        nms_large_kernel<<<grid, kLargeThreads, Ll.total, st>>>(A, mcap);
+        note_launch();
+        RD_CHECK_LAUNCH();
+    }
     if (ev) cudaEventRecord(ev[3], st);
     return 0;
 }
@@ -519,8 +542,7 @@ int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, const flo
     if (rc == 0) {
         cudaError_t e = cudaEventSynchronize(ev[3]);
         if (e != cudaSuccess) rc = (int)e;
-        stage_ms_host[2] = 0.f;
-        for (int i = 0; i < 2 && rc == 0; ++i) {
+        for (int i = 0; i < 3 && rc == 0; ++i) {
             e = cudaEventElapsedTime(&stage_ms_host[i], ev[i], ev[i + 1]);
             if (e != cudaSuccess) rc = (int)e;
         }
@@ -560,8 +582,8 @@ static int launch_single(const unsigned long long* keys, int n, const float4* bo
         if (e != cudaSuccess) return (int)e;
         s_attr = L.total;
     }
-    nms_single_kernel<<<1, kNmsThreads, L.total, st>>>(keys, n, boxes, thresh, top_k, m, nms_flags, m, keep64,
-                                                        keep32, count_out);
+    nms_single_kernel<<<1, kLargeThreads, L.total, st>>>(keys, n, boxes, thresh, top_k, m, nms_flags, m, keep64,
+                                                          keep32, count_out);
     note_launch();
     RD_CHECK_LAUNCH();
     return 0;
