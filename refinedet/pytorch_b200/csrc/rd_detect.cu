@@ -10,7 +10,10 @@
 //                           SHARED-memory atomics (the CTA owns its sub-list), so there is no global
 //                           atomic and nothing to reset between calls.  odm_conf / loc rows of
 //                           ARM-filtered anchors are never fetched: traffic scales with the pass rate.
-//   nms_small_kernel        K2+K3: one 64-thread CTA per (image, class) with <= 256 candidates,
+//   graph_kernel            KG: one CTA per (image, slice): exact suppression graph between the ARM-passing
+//                           anchors of an image (class independent), adjacency lists per anchor
+//   nms_small_kernel        K2+K3: one 64-thread CTA per (image, class) with <= 256 candidates: sort +
+//                           graph look-ups (or its own bins when the image's graph is unavailable),
 //                           12.7 KB shared memory -> 16 CTAs resident per SM; other problems are queued
 //   nms_large_kernel        persistent CTAs draining the queue (radix select when n > top_k)
 //   nms_single_kernel       stand-alone problem (rd_nms / rd_nms_host)
@@ -34,6 +37,11 @@ constexpr int kLargeThreads = 128;
 //   header u32 [64]           : [0] = number of queued large problems
 //   queue  int [B*C]          : (image,class) problems routed to nms_large_kernel
 //   cnt    int [B*C*S]        : candidate count of every sub-list, S = ceil(P / 1024)
+//   pcnt   int [B*S]          : ARM-passing anchors of every slice
+//   flag   int [B]            : 1 = the image has no suppression graph (too many nodes / degree overflow)
+//   plist  int [B*S*1024]     : their anchor indices
+//   adjn   u8  [B*P]          : graph degree of every passing anchor
+//   adj    u32 [B*P*8]        : adjacency lists (anchor indices)
 //   boxes  f4  [B*P]          : decoded boxes of ARM-passing anchors
 //   cand   u64 [B*C*S*1024]   : candidate keys, sub-list (b,c,s) written by collect CTA (s,b)
 // ---------------------------------------------------------------------------------------
@@ -41,6 +49,11 @@ struct DetectWs {
     uint32_t* header;
     int* queue;
     int* cnt;
+    int* pcnt;
+    int* flag;
+    int* plist;
+    unsigned char* adjn;
+    uint32_t* adj;
     float4* boxes;
     unsigned long long* cand;
     int S;
@@ -55,6 +68,11 @@ static DetectWs carve_ws(void* base, int B, int P, int C) {
     w.header = reinterpret_cast<uint32_t*>(p + o);             o += 256;
     w.queue = reinterpret_cast<int*>(p + o);                   o += align_up((size_t)B * C * 4, 256);
     w.cnt = reinterpret_cast<int*>(p + o);                     o += align_up((size_t)B * C * w.S * 4, 256);
+    w.pcnt = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * w.S * 4, 256);
+    w.flag = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * 4, 256);
+    w.plist = reinterpret_cast<int*>(p + o);                   o += align_up((size_t)B * w.S * kSliceAnchors * 4, 256);
+    w.adjn = reinterpret_cast<unsigned char*>(p + o);          o += align_up((size_t)B * P, 256);
+    w.adj = reinterpret_cast<uint32_t*>(p + o);                o += align_up((size_t)B * P * kAdjDeg * 4, 256);
     w.boxes = reinterpret_cast<float4*>(p + o);                o += align_up((size_t)B * P * 16, 256);
     w.cand = reinterpret_cast<unsigned long long*>(p + o);     o += align_up((size_t)B * C * w.S * kSliceAnchors * 8, 256);
     w.total = o;
@@ -141,13 +159,16 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
                const float4* __restrict__ odm_loc, const float* __restrict__ odm_conf,
                const float4* __restrict__ priors, int P, int C, int S, float obj_thre,
                float conf_thresh, float v0, float v1, float4* __restrict__ boxes_ws, int* __restrict__ cnt,
-               unsigned long long* __restrict__ cand, uint32_t* header) {
+               unsigned long long* __restrict__ cand, uint32_t* header, int* __restrict__ pcnt,
+               int* __restrict__ plist, int* __restrict__ img_flag) {
     __shared__ unsigned char s_list[kCollectThreads / 32][32 * kChunks];   // passing anchors of each warp
     __shared__ int s_cnt[kMaxClasses];
+    __shared__ int s_wpass[kCollectThreads / 32];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int s = blockIdx.x, b = blockIdx.y;
     if (s == 0 && b == 0 && threadIdx.x == 0) header[0] = 0;          // queue of the large-NMS kernel
+    if (s == 0 && threadIdx.x == 0) img_flag[b] = 0;
     for (int c = threadIdx.x; c < C; c += kCollectThreads) s_cnt[c] = 0;
     __syncthreads();
     const int a0 = s * kSliceAnchors + wib * (32 * kChunks);          // first anchor of this warp
@@ -168,7 +189,16 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
         if (pass) s_list[wib][npass + __popc(mask & ((1u << lane) - 1u))] = (unsigned char)(ch * 32 + lane);
         npass += __popc(mask);
     }
-    __syncwarp();
+    if (lane == 0) s_wpass[wib] = npass;
+    __syncthreads();
+    {   // node list of the suppression graph: passing anchors of this slice, warp after warp
+        int off = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kCollectThreads / 32; ++w) { if (w < wib) off += s_wpass[w]; tot += s_wpass[w]; }
+        int* pl = plist + ((size_t)b * S + s) * kSliceAnchors + off;
+        for (int r = lane; r < npass; r += 32) pl[r] = a0 + s_list[wib][r];
+        if (threadIdx.x == 0) pcnt[b * S + s] = tot;
+    }
     // 2. decode the passing anchors, one per lane
     for (int r0 = 0; r0 < npass; r0 += 32) {
         const int r = r0 + lane;
@@ -213,6 +243,186 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
 }
 
 // ---------------------------------------------------------------------------------------
+// KG: suppression graph of one image.  grid = (S, B), CTA (s, b) owns the passing anchors of slice s
+// ("own nodes") and tests them against ALL passing anchors of image b.  Every CTA of an image builds
+// the image's bin tables redundantly (cheap) so no inter-CTA communication is needed.
+//   adj[anchor j] = { anchor u : suppresses(kept = u, candidate = j) }    (exact fp32 test, boxes scaled)
+// Images with more than kGraphNodes passing anchors, or a node of degree > kAdjDeg, are flagged and
+// handled by the per-problem bin path instead.
+// ---------------------------------------------------------------------------------------
+constexpr int kGraphThreads = 256;
+constexpr int kGraphNodes = 1024;
+constexpr int kGraphW = kGraphNodes / 32;
+constexpr int kGraphWS = kGraphW + 1;
+constexpr int kGraphPairCap = 4096;
+
+struct GraphSmem {
+    float x1[kGraphNodes], y1[kGraphNodes], x2[kGraphNodes], y2[kGraphNodes];
+    uint32_t cr[kGraphNodes];
+    int anchor[kGraphNodes];
+    uint32_t tab[4 * kCols * kGraphWS];
+    uint32_t pairs[kGraphPairCap];
+    int deg[kSliceAnchors];
+    int cnt[kMaxSlices];
+    int offs[kMaxSlices + 1];
+    uint32_t ext[4];
+    int wsum[kGraphThreads / 32];
+    int overflow;
+    int npairs;
+};
+
+__device__ __forceinline__ int load_slice_counts(const int* __restrict__ gcnt, int S, int* s_cnt, int* s_offs);
+
+__global__ void __launch_bounds__(kGraphThreads)
+graph_kernel(const int* __restrict__ pcnt, const int* __restrict__ plist, const float4* __restrict__ boxes_ws,
+             const float* __restrict__ img_scale, int P, int S, float thr, int flags,
+             uint32_t* __restrict__ adj, unsigned char* __restrict__ adjn, int* __restrict__ img_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GraphSmem& G = *reinterpret_cast<GraphSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = blockIdx.x, b = blockIdx.y;
+    const int N = load_slice_counts(pcnt + (size_t)b * S, S, G.cnt, G.offs);
+    if (N > kGraphNodes) {
+        if (s == 0 && tid == 0) img_flag[b] = 1;
+        return;
+    }
+    // own nodes: i = s, s + S, s + 2S, ... (interleaved, so the few large boxes that overlap
+    // hundreds of others are spread over the CTAs of the image)
+    const int nown = N > s ? (N - s + S - 1) / S : 0;
+    if (nown == 0) return;
+    const bool pixel = (flags & RD_NMS_PIXEL_PLUS1) != 0;
+    const bool has_scale = img_scale != nullptr;
+    const float4 scale = has_scale ? __ldg(reinterpret_cast<const float4*>(img_scale) + b) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const size_t img = (size_t)b * P;
+    const int Wn = (N + 31) >> 5;
+    // 1. nodes of the whole image -> shared memory
+    for (int i = tid; i < 4 * kCols * kGraphWS; i += kGraphThreads) G.tab[i] = 0;
+    for (int i = tid; i < nown; i += kGraphThreads) G.deg[i] = 0;
+    if (tid < 4) G.ext[tid] = (tid & 1) ? 0u : 0xffffffffu;
+    if (tid == 0) { G.overflow = 0; G.npairs = 0; }
+    __syncthreads();
+    {
+        uint32_t mnx = 0xffffffffu, mxx = 0, mny = 0xffffffffu, mxy = 0;
+        for (int i = tid; i < N; i += kGraphThreads) {      // all loads of the image in flight together
+            int lo = 0, hi = S;                            // slice of node i: largest t with offs[t] <= i
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (G.offs[mid] <= i) lo = mid; else hi = mid;
+            }
+            const int a = plist[((size_t)b * S + lo) * kSliceAnchors + (i - G.offs[lo])];
+            float4 bx = boxes_ws[img + a];
+            if (has_scale) { bx.x *= scale.x; bx.y *= scale.y; bx.z *= scale.z; bx.w *= scale.w; }
+            G.anchor[i] = a;
+            G.x1[i] = bx.x; G.y1[i] = bx.y; G.x2[i] = bx.z; G.y2[i] = bx.w;
+            const float cx = 0.5f * bx.x + 0.5f * bx.z, cy = 0.5f * bx.y + 0.5f * bx.w;
+            if (isfinite(cx)) { mnx = min(mnx, float_to_ordered(cx)); mxx = max(mxx, float_to_ordered(cx)); }
+            if (isfinite(cy)) { mny = min(mny, float_to_ordered(cy)); mxy = max(mxy, float_to_ordered(cy)); }
+        }
+        mnx = __reduce_min_sync(kFullMask, mnx); mxx = __reduce_max_sync(kFullMask, mxx);
+        mny = __reduce_min_sync(kFullMask, mny); mxy = __reduce_max_sync(kFullMask, mxy);
+        if (lane == 0) {
+            atomicMin(&G.ext[0], mnx); atomicMax(&G.ext[1], mxx);
+            atomicMin(&G.ext[2], mny); atomicMax(&G.ext[3], mxy);
+        }
+    }
+    __syncthreads();
+    // 2. bin ranges, marks, prefix-OR
+    {
+        float lox, invx, loy, invy;
+        extent_to_scale(G.ext[0], G.ext[1], lox, invx);
+        extent_to_scale(G.ext[2], G.ext[3], loy, invy);
+        const bool force_full = cull_disabled(thr, flags);
+        for (int i = tid; i < N; i += kGraphThreads) {
+            const uint32_t cr = bin_range(G.x1[i], G.y1[i], G.x2[i], G.y2[i], pixel, force_full, lox, invx, loy, invy);
+            G.cr[i] = cr;
+            const int ax = cr & 255u, bx = (cr >> 8) & 255u, ay = (cr >> 16) & 255u, by = cr >> 24;
+            const uint32_t bit = 1u << (i & 31);
+            const int w = i >> 5;
+            atomicOr(&G.tab[(0 * kCols + ax) * kGraphWS + w], bit);
+            if (bx + 1 < kCols) atomicOr(&G.tab[(1 * kCols + bx + 1) * kGraphWS + w], bit);
+            atomicOr(&G.tab[(2 * kCols + ay) * kGraphWS + w], bit);
+            if (by + 1 < kCols) atomicOr(&G.tab[(3 * kCols + by + 1) * kGraphWS + w], bit);
+        }
+    }
+    __syncthreads();
+    for (int task = tid; task < 4 * Wn; task += kGraphThreads) {
+        const int t = task / Wn, w = task - t * Wn;
+        uint32_t acc = 0;
+        uint32_t* p = G.tab + (size_t)t * kCols * kGraphWS + w;
+#pragma unroll 8
+        for (int c = 0; c < kCols; ++c) { acc |= p[c * kGraphWS]; p[c * kGraphWS] = acc; }
+    }
+    __syncthreads();
+    // 3. own nodes: candidate pairs after the bin cull, flattened and tested by all threads
+    const uint32_t* Sx = G.tab;
+    const uint32_t* Ex = G.tab + 1 * kCols * kGraphWS;
+    const uint32_t* Sy = G.tab + 2 * kCols * kGraphWS;
+    const uint32_t* Ey = G.tab + 3 * kCols * kGraphWS;
+    // one WARP per own node, lane = mask word (Wn <= 32): every lane lists at most 32 pairs, so a large
+    // box that overlaps hundreds of others does not serialise anything
+    for (int jl = warp; jl < nown; jl += kGraphThreads / 32) {
+        const int j = s + jl * S;
+        const uint32_t cr = G.cr[j];
+        uint32_t h = 0;
+        if (lane < Wn) {
+            h = Sx[((cr >> 8) & 255u) * kGraphWS + lane] & ~Ex[(cr & 255u) * kGraphWS + lane] &
+                Sy[((cr >> 24) & 255u) * kGraphWS + lane] & ~Ey[((cr >> 16) & 255u) * kGraphWS + lane];
+            if (lane == (j >> 5)) h &= ~(1u << (j & 31));
+        }
+        const int c = __popc(h);
+        int x = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, x, d); if (lane >= d) x += o; }
+        const int tot = __shfl_sync(kFullMask, x, 31);
+        if (tot == 0) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&G.npairs, tot);
+        base = __shfl_sync(kFullMask, base, 0);
+        int off = base + x - c;
+        if (base + tot <= kGraphPairCap) {
+            while (h) {
+                const int i = (lane << 5) + __ffs(h) - 1;
+                h &= h - 1;
+                G.pairs[off++] = ((uint32_t)jl << 16) | (uint32_t)i;
+            }
+        } else {                                   // list full: void the reserved slots, test in place
+            for (int q = base + lane; q < min(base + tot, kGraphPairCap); q += 32) G.pairs[q] = 0xffffffffu;
+            const float jx1 = G.x1[j], jy1 = G.y1[j], jx2 = G.x2[j], jy2 = G.y2[j];
+            while (h) {
+                const int i = (lane << 5) + __ffs(h) - 1;
+                h &= h - 1;
+                if (suppresses(G.x1[i], G.y1[i], G.x2[i], G.y2[i], jx1, jy1, jx2, jy2, thr, flags)) {
+                    const int slot = atomicAdd(&G.deg[jl], 1);
+                    if (slot < kAdjDeg) adj[(img + G.anchor[j]) * kAdjDeg + slot] = (uint32_t)G.anchor[i];
+                    else G.overflow = 1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int cnt = min(G.npairs, kGraphPairCap);
+        for (int p = tid; p < cnt; p += kGraphThreads) {
+            const uint32_t e = G.pairs[p];
+            if (e == 0xffffffffu) continue;
+            const int jl = (int)(e >> 16), i = (int)(e & 0xffffu);
+            const int jj = s + jl * S;
+            if (suppresses(G.x1[i], G.y1[i], G.x2[i], G.y2[i], G.x1[jj], G.y1[jj], G.x2[jj], G.y2[jj], thr, flags)) {
+                const int slot = atomicAdd(&G.deg[jl], 1);
+                if (slot < kAdjDeg) adj[(img + G.anchor[jj]) * kAdjDeg + slot] = (uint32_t)G.anchor[i];
+                else G.overflow = 1;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nown; i += kGraphThreads) {
+        const int d = G.deg[i];
+        adjn[img + G.anchor[s + i * S]] = (unsigned char)(d < kAdjDeg ? d : kAdjDeg);
+    }
+    if (tid == 0 && G.overflow) img_flag[b] = 1;
+}
+
+// ---------------------------------------------------------------------------------------
 // K2+K3
 // ---------------------------------------------------------------------------------------
 struct FusedNmsArgs {
@@ -222,6 +432,11 @@ struct FusedNmsArgs {
     const float* img_scale;          // [B,4] or null
     int* queue;
     uint32_t* header;
+    const int* img_flag;             // [B] 1 = no graph for this image
+    const uint32_t* adj;             // [B*P*kAdjDeg]
+    const unsigned char* adjn;       // [B*P]
+    const float* odm_conf;           // [B,P,C]
+    float conf_thresh;
     int nbc, C, P, S;
     float thr;
     int top_k, max_out, flags, row_layout;
@@ -294,7 +509,18 @@ nms_small_kernel(FusedNmsArgs A) {
     NmsProblem pb;
     RowSink sink;
     fill_problem(pb, sink, bc, n, S.cnt, S.offs, A);
-    const int kept = cta_nms_small(S, pb, sink);
+    const int b = bc / A.C;
+    int kept;
+    if (A.img_flag[b] == 0) {
+        GraphView G;
+        G.adj = A.adj + (size_t)b * A.P * kAdjDeg;
+        G.adjn = A.adjn + (size_t)b * A.P;
+        G.conf = A.odm_conf + (size_t)b * A.P * A.C;
+        G.C = A.C; G.c = c; G.conf_thresh = A.conf_thresh;
+        kept = cta_nms_graph(S, pb, sink, G);
+    } else {
+        kept = cta_nms_small(S, pb, sink);
+    }
     if (threadIdx.x == 0) A.out_counts[bc] = kept;
 }
 
@@ -467,22 +693,38 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     if (ev) cudaEventRecord(ev[0], st);
     collect_kernel<<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
         (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
-        P, C, ws.S, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.header);
+        P, C, ws.S, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.header, ws.pcnt, ws.plist,
+        ws.flag);
     note_launch();
     RD_CHECK_LAUNCH();
+    if (ev) cudaEventRecord(ev[1], st);
+    {
+        static bool s_graph_attr = false;
+        if (!s_graph_attr) {
+            cudaError_t e = cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)sizeof(GraphSmem));
+            if (e != cudaSuccess) return (int)e;
+            s_graph_attr = true;
+        }
+        graph_kernel<<<dim3(ws.S, B), kGraphThreads, sizeof(GraphSmem), st>>>(
+            ws.pcnt, ws.plist, ws.boxes, img_scale, P, ws.S, nms_thresh, nms_flags, ws.adj, ws.adjn, ws.flag);
+        note_launch();
+        RD_CHECK_LAUNCH();
+    }
 
     FusedNmsArgs A;
     A.cnt = ws.cnt; A.cand = ws.cand; A.boxes = ws.boxes; A.img_scale = img_scale;
     A.queue = ws.queue; A.header = ws.header;
+    A.img_flag = ws.flag; A.adj = ws.adj; A.adjn = ws.adjn; A.odm_conf = odm_conf; A.conf_thresh = conf_thresh;
     A.nbc = B * C; A.C = C; A.P = P; A.S = ws.S;
     A.thr = nms_thresh; A.top_k = top_k; A.max_out = max_out; A.flags = nms_flags; A.row_layout = row_layout;
     A.out_counts = out_counts; A.out_dets = out_dets; A.out_anchor = out_anchor;
 
-    if (ev) cudaEventRecord(ev[1], st);
+    if (ev) cudaEventRecord(ev[2], st);
     nms_small_kernel<<<B * C, kSmallThreads, 0, st>>>(A);
     note_launch();
     RD_CHECK_LAUNCH();
-    if (ev) cudaEventRecord(ev[2], st);
+    if (ev) cudaEventRecord(ev[3], st);
     {
         const int mcap = top_k < P ? top_k : P;
         const NmsSmemLayout Ll = nms_layout(mcap);
@@ -509,7 +751,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
         note_launch();
         RD_CHECK_LAUNCH();
     }
-    if (ev) cudaEventRecord(ev[3], st);
+    if (ev) cudaEventRecord(ev[4], st);
     return 0;
 }
 
@@ -531,8 +773,8 @@ int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, const flo
                           int row_layout, float v0, float v1, void* workspace, size_t workspace_bytes,
                           int* out_counts, float* out_dets, int* out_anchor, void* stream, float* stage_ms_host) {
     if (!stage_ms_host) return RD_ERR_BAD_ARG;
-    cudaEvent_t ev[4];
-    for (int i = 0; i < 4; ++i) {
+    cudaEvent_t ev[5];
+    for (int i = 0; i < 5; ++i) {
         cudaError_t e = cudaEventCreate(&ev[i]);
         if (e != cudaSuccess) return (int)e;
     }
@@ -540,14 +782,14 @@ int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, const flo
                                nms_thresh, top_k, max_out, img_scale, nms_flags, row_layout, v0, v1, workspace,
                                workspace_bytes, out_counts, out_dets, out_anchor, stream, ev);
     if (rc == 0) {
-        cudaError_t e = cudaEventSynchronize(ev[3]);
+        cudaError_t e = cudaEventSynchronize(ev[4]);
         if (e != cudaSuccess) rc = (int)e;
-        for (int i = 0; i < 3 && rc == 0; ++i) {
+        for (int i = 0; i < 4 && rc == 0; ++i) {
             e = cudaEventElapsedTime(&stage_ms_host[i], ev[i], ev[i + 1]);
             if (e != cudaSuccess) rc = (int)e;
         }
     }
-    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
     return rc;
 }
 

@@ -198,31 +198,22 @@ __device__ __forceinline__ unsigned long long cand_at(const CandList& cl, int e)
     return cl.base[(size_t)s * cl.stride + (e - cl.offs[s])];
 }
 
-// Runs one small problem on the calling CTA (kSmallThreads threads).  S.cnt / S.offs must hold the
-// candidate list's slice counts / prefix sums.  Returns the kept count (uniform over the CTA).
-__device__ inline int cta_nms_small(SmallSmem& S, const NmsProblem& pb, const RowSink& sink) {
+// Phases A+B of a small problem: sorted runs of 32 in registers (one run per warp at a time), merged
+// by rank.  On return (after a CTA barrier) S.keys[0..m) holds the keys in descending order.
+__device__ __forceinline__ void cta_sort_small(SmallSmem& S, const CandList& cl) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int m = pb.cl.n;                                   // caller guarantees n <= min(top_k, kSmallCap)
+    const int m = cl.n;
     const int Wm = (m + 31) >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const bool pixel = (pb.flags & RD_NMS_PIXEL_PLUS1) != 0;
     unsigned long long* runs = reinterpret_cast<unsigned long long*>(S.x1);   // 256 x 8 B = x1 + y1
-
-    // ---- A. sorted runs of 32 (one run per warp at a time), table init ------------------------
-    for (int i = tid; i < 4 * kSmallW * kCols; i += kSmallThreads) S.tab[i] = 0;
-    if (tid < 4) S.ext[tid] = (tid & 1) ? 0u : 0xffffffffu;   // min cx, max cx, min cy, max cy (ordered)
-    if (tid < 32) S.tin[tid] = 0;
-    if (tid == 0) { S.sup = 0; S.kept_total = 0; S.stop = 0; }
     for (int run = warp; run < Wm; run += kSmallWarps) {
         const int e = run * 32 + lane;
-        unsigned long long k = e < m ? cand_at(pb.cl, e) : 0ull;
+        unsigned long long k = e < m ? cand_at(cl, e) : 0ull;
         k = warp_sort32_desc(k, lane);
         if (Wm == 1) S.keys[lane] = k; else runs[e] = k;
     }
     __syncthreads();
-    // ---- B. merge by rank ---------------------------------------------------------------------
     if (Wm > 1) {
         for (int run = warp; run < Wm; run += kSmallWarps) {
             const unsigned long long k = runs[run * 32 + lane];
@@ -241,6 +232,25 @@ __device__ inline int cta_nms_small(SmallSmem& S, const NmsProblem& pb, const Ro
         }
         __syncthreads();
     }
+}
+
+// Runs one small problem on the calling CTA (kSmallThreads threads) with its own bin tables.
+// S.cnt / S.offs must hold the candidate list's slice counts / prefix sums.  Returns the kept count
+// (uniform over the CTA).
+__device__ inline int cta_nms_small(SmallSmem& S, const NmsProblem& pb, const RowSink& sink) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int m = pb.cl.n;                                   // caller guarantees n <= min(top_k, kSmallCap)
+    const int Wm = (m + 31) >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool pixel = (pb.flags & RD_NMS_PIXEL_PLUS1) != 0;
+
+    for (int i = tid; i < 4 * kSmallW * kCols; i += kSmallThreads) S.tab[i] = 0;
+    if (tid < 4) S.ext[tid] = (tid & 1) ? 0u : 0xffffffffu;   // min cx, max cx, min cy, max cy (ordered)
+    if (tid < 32) S.tin[tid] = 0;
+    if (tid == 0) { S.sup = 0; S.kept_total = 0; S.stop = 0; }
+    cta_sort_small(S, pb.cl);
     // ---- C. boxes + extent of the box centres --------------------------------------------------
     float bx1[kSmallCap / kSmallThreads], by1[kSmallCap / kSmallThreads], bx2[kSmallCap / kSmallThreads],
         by2[kSmallCap / kSmallThreads];
@@ -414,6 +424,112 @@ __device__ inline int cta_nms_small(SmallSmem& S, const NmsProblem& pb, const Ro
         if (S.stop) break;
     }
     return S.kept_total;
+}
+
+// =========================================================================================
+// small problems, graph mode: the suppression relation between the ARM-passing anchors of an
+// image does not depend on the class, so it is computed once per image (graph_kernel in
+// rd_detect.cu) as adjacency lists  adj[anchor] = {u : box u suppresses box anchor when u is kept}.
+// A problem then only sorts its keys, looks up the few neighbours that are candidates of ITS class
+// with a higher key, and resolves the dependencies; no boxes, bins or IoUs per class.
+// =========================================================================================
+constexpr int kAdjDeg = 8;            // adjacency slots per anchor; an image whose graph overflows is flagged dense
+
+struct GraphView {
+    const uint32_t* adj;              // [P][kAdjDeg] anchors of the image
+    const unsigned char* adjn;        // [P] degree (<= kAdjDeg)
+    const float* conf;                // odm_conf rows of the image, [P][C]
+    int C, c;
+    float conf_thresh;
+};
+
+__device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const RowSink& sink, const GraphView& G) {
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int m = pb.cl.n;                                   // n <= min(top_k, kSmallCap): nothing is truncated
+    unsigned char* depn = reinterpret_cast<unsigned char*>(S.cr);       // [256] number of dependencies
+    unsigned char* deps = reinterpret_cast<unsigned char*>(S.tab);      // [256][kAdjDeg] rank of each dependency
+    unsigned char* state = reinterpret_cast<unsigned char*>(S.pairs);   // [256] 0 undecided, 1 kept, 2 suppressed
+    int* wsum = reinterpret_cast<int*>(S.tin);                          // cross-warp scan scratch
+    cta_sort_small(S, pb.cl);
+
+    // ---- dependencies: neighbours that are candidates of this class and rank earlier -------------
+    for (int r = tid; r < m; r += kSmallThreads) {
+        const unsigned long long key = S.keys[r];
+        const uint32_t a = key_index(key);
+        const int dn = G.adjn[a];
+        int nd = 0;
+        for (int k = 0; k < dn; ++k) {
+            const uint32_t u = G.adj[(size_t)a * kAdjDeg + k];
+            const float su = G.conf[(size_t)u * G.C + G.c];
+            if (!(su > G.conf_thresh)) continue;
+            const unsigned long long ku = make_key(su, u);
+            if (ku > key) {
+                int lo = 0, hi = r;                          // keys are descending: first index with keys[idx] <= ku
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (S.keys[mid] > ku) lo = mid + 1; else hi = mid;
+                }
+                if (lo < r && S.keys[lo] == ku) deps[r * kAdjDeg + nd++] = (unsigned char)lo;
+            }
+        }
+        depn[r] = (unsigned char)nd;
+        state[r] = nd == 0 ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- resolve in rounds (dependencies always point to earlier ranks: terminates) ---------------
+    for (int round = 0; round < kSmallCap; ++round) {
+        int undecided = 0;
+        for (int r = tid; r < m; r += kSmallThreads) {
+            if (state[r] != 0) continue;
+            const int nd = depn[r];
+            bool any_kept = false, all_sup = true;
+            for (int k = 0; k < nd; ++k) {
+                const unsigned char st = state[deps[r * kAdjDeg + k]];
+                any_kept |= (st == 1);
+                all_sup &= (st == 2);
+            }
+            if (any_kept) state[r] = 2;
+            else if (all_sup) state[r] = 1;
+            else undecided = 1;
+        }
+        if (!__syncthreads_or(undecided)) break;
+    }
+    // ---- emit kept rows in rank order, first max_out ----------------------------------------------
+    constexpr int kPer = kSmallCap / kSmallThreads;          // consecutive ranks per thread
+    int local = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int r = tid * kPer + q;
+        if (r < m && state[r] == 1) ++local;
+    }
+    int x = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, x, d); if (lane >= d) x += o; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    int base = x - local;
+    int total = 0;
+#pragma unroll
+    for (int w = 0; w < kSmallWarps; ++w) {
+        if (w < warp) base += wsum[w];
+        total += wsum[w];
+    }
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int r = tid * kPer + q;
+        if (r < m && state[r] == 1) {
+            if (base < pb.max_out) {
+                const unsigned long long key = S.keys[r];
+                float4 b = pb.boxes[key_index(key)];
+                if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
+                sink_emit(sink, base, key, b.x, b.y, b.z, b.w);
+            }
+            ++base;
+        }
+    }
+    return total < pb.max_out ? total : pb.max_out;
 }
 
 // =========================================================================================
