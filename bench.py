@@ -10,7 +10,7 @@ BASELINE.json config 3 (P = 16,320 anchors, C = 81 classes); every rank owns its
 
   value        images/s, device time (CUDA events), inputs resident in HBM, L2 flushed and
                input buffers rotated between steps, max over ranks
-  e2e          images/s through the public API with HOST (pinned) inputs: H2D copies, the three
+  e2e          images/s through the public API with HOST (pinned) inputs: H2D copies, the stage's
                kernels, packing, D2H of counts + packed rows, all inside the timed region
   roofline     algorithmic bytes of the stage (5,940,480 B/image) / device time
                of the stage's kernels, against MEASURED_PEAKS.json hbm_gbs; per-kernel shares
@@ -310,7 +310,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, done, elapsed = cpu_reference_run(args.workload, 6, 1, cores, budget_s=25.0)
+        v, done, elapsed = cpu_reference_run(args.workload, 1000, 1, cores, budget_s=12.0)
         cpu_baseline = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                         'sample': '%d steps x %d images (1 per worker process) of the same workload, %.1f s'
                                   % (done, cores, elapsed)}
