@@ -32,31 +32,42 @@ constexpr int kSliceAnchors = 1024;   // anchors per collect CTA = capacity of o
 constexpr int kLargeThreads = 128;
 
 // ---------------------------------------------------------------------------------------
-// workspace of the fused stage (nothing in it needs initialisation except the queue header,
-// which collect_kernel clears on every call)
-//   header u32 [64]           : [0] = number of queued large problems
-//   queue  int [B*C]          : (image,class) problems routed to nms_large_kernel
-//   cnt    int [B*C*S]        : candidate count of every sub-list, S = ceil(P / 1024)
-//   pcnt   int [B*S]          : ARM-passing anchors of every slice
-//   flag   int [B]            : 1 = the image has no suppression graph (too many nodes / degree overflow)
-//   plist  int [B*S*1024]     : their anchor indices
-//   adjn   u8  [B*P]          : graph degree of every passing anchor
-//   adj    u32 [B*P*8]        : adjacency lists (anchor indices)
-//   boxes  f4  [B*P]          : decoded boxes of ARM-passing anchors
-//   cand   u64 [B*C*S*1024]   : candidate keys, sub-list (b,c,s) written by collect CTA (s,b)
+// workspace of the fused stage.  The control block (header, nnodes, gtab) must be zero when a call
+// starts: rd_detect_workspace_reset zeroes it once, every call leaves it zero again (collect clears
+// the queue header, nms_small's class-0 CTAs clear nnodes / gtab of their image).
+//   header u32 [64]               : [0] = number of queued large problems
+//   nnodes int [B]                : graph nodes (= ARM-passing anchors) of every image
+//   gtab   u32 [B][4][32][33]     : start/end bin marks of the nodes (OR-ed in by collect)
+//   flag   int [B]                : 1 = the image has no suppression graph (too many nodes / degree overflow)
+//   queue  int [B*C]              : (image,class) problems routed to nms_large_kernel
+//   cnt    int [B*C*S]            : candidate count of every sub-list, S = ceil(P / 1024)
+//   nbox   f4  [B][1024], nanc int [B][1024], ncr u32 [B][1024] : node box / anchor / bin range
+//   adjn   int [B*P]              : graph degree of every passing anchor (collect zeroes, graph counts)
+//   adj    u32 [B*P*8]            : adjacency lists (anchor indices)
+//   boxes  f4  [B*P]              : decoded boxes of ARM-passing anchors
+//   cand   u64 [B*C*S*1024]       : candidate keys, sub-list (b,c,s) written by collect CTA (s,b)
 // ---------------------------------------------------------------------------------------
+constexpr int kGraphNodes = 1024;       // images with more ARM-passing anchors fall back to per-problem bins
+constexpr int kGraphW = kGraphNodes / 32;
+constexpr int kGraphWS = kGraphW + 1;
+constexpr int kGtabWords = 4 * kCols * kGraphWS;
+
 struct DetectWs {
     uint32_t* header;
+    int* nnodes;
+    uint32_t* gtab;
+    int* flag;
     int* queue;
     int* cnt;
-    int* pcnt;
-    int* flag;
-    int* plist;
-    unsigned char* adjn;
+    float4* nbox;
+    int* nanc;
+    uint32_t* ncr;
+    int* adjn;
     uint32_t* adj;
     float4* boxes;
     unsigned long long* cand;
     int S;
+    size_t ctrl_bytes;
     size_t total;
 };
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -66,12 +77,16 @@ static DetectWs carve_ws(void* base, int B, int P, int C) {
     unsigned char* p = static_cast<unsigned char*>(base);
     w.S = (P + kSliceAnchors - 1) / kSliceAnchors;
     w.header = reinterpret_cast<uint32_t*>(p + o);             o += 256;
+    w.nnodes = reinterpret_cast<int*>(p + o);                  o += align_up((size_t)B * 4, 256);
+    w.gtab = reinterpret_cast<uint32_t*>(p + o);               o += align_up((size_t)B * kGtabWords * 4, 256);
+    w.ctrl_bytes = o;
+    w.flag = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * 4, 256);
     w.queue = reinterpret_cast<int*>(p + o);                   o += align_up((size_t)B * C * 4, 256);
     w.cnt = reinterpret_cast<int*>(p + o);                     o += align_up((size_t)B * C * w.S * 4, 256);
-    w.pcnt = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * w.S * 4, 256);
-    w.flag = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * 4, 256);
-    w.plist = reinterpret_cast<int*>(p + o);                   o += align_up((size_t)B * w.S * kSliceAnchors * 4, 256);
-    w.adjn = reinterpret_cast<unsigned char*>(p + o);          o += align_up((size_t)B * P, 256);
+    w.nbox = reinterpret_cast<float4*>(p + o);                 o += align_up((size_t)B * kGraphNodes * 16, 256);
+    w.nanc = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * kGraphNodes * 4, 256);
+    w.ncr = reinterpret_cast<uint32_t*>(p + o);                o += align_up((size_t)B * kGraphNodes * 4, 256);
+    w.adjn = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * P * 4, 256);
     w.adj = reinterpret_cast<uint32_t*>(p + o);                o += align_up((size_t)B * P * kAdjDeg * 4, 256);
     w.boxes = reinterpret_cast<float4*>(p + o);                o += align_up((size_t)B * P * 16, 256);
     w.cand = reinterpret_cast<unsigned long long*>(p + o);     o += align_up((size_t)B * C * w.S * kSliceAnchors * 8, 256);
@@ -154,23 +169,35 @@ constexpr int kChunks = kSliceAnchors / (kCollectThreads / 32) / 32;   // 32-anc
 constexpr int kRowBatch = 4;                                           // odm_conf rows in flight per warp
 constexpr int kMaxClasses = 128;
 
+struct GraphOut {            // what collect contributes to the per-image suppression graph
+    int* nnodes;             // [B]
+    uint32_t* gtab;          // [B][kGtabWords]
+    float4* nbox;            // [B][kGraphNodes] scaled boxes
+    int* nanc;               // [B][kGraphNodes]
+    uint32_t* ncr;           // [B][kGraphNodes]
+    int* adjn;               // [B*P]
+    int* img_flag;           // [B]
+    const float* img_scale;  // [B,4] or null
+    float thr;
+    int flags;
+};
+
 __global__ void __launch_bounds__(kCollectThreads)
 collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ arm_conf,
                const float4* __restrict__ odm_loc, const float* __restrict__ odm_conf,
                const float4* __restrict__ priors, int P, int C, int S, float obj_thre,
                float conf_thresh, float v0, float v1, float4* __restrict__ boxes_ws, int* __restrict__ cnt,
-               unsigned long long* __restrict__ cand, uint32_t* header, int* __restrict__ pcnt,
-               int* __restrict__ plist, int* __restrict__ img_flag) {
+               unsigned long long* __restrict__ cand, uint32_t* header, GraphOut GO) {
     __shared__ unsigned char s_list[kCollectThreads / 32][32 * kChunks];   // passing anchors of each warp
     __shared__ int s_cnt[kMaxClasses];
     __shared__ int s_wpass[kCollectThreads / 32];
+    __shared__ int s_base;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int s = blockIdx.x, b = blockIdx.y;
     if (s == 0 && b == 0 && threadIdx.x == 0) header[0] = 0;          // queue of the large-NMS kernel
-    if (s == 0 && threadIdx.x == 0) img_flag[b] = 0;
+    if (s == 0 && threadIdx.x == 0) GO.img_flag[b] = 0;
     for (int c = threadIdx.x; c < C; c += kCollectThreads) s_cnt[c] = 0;
-    __syncthreads();
     const int a0 = s * kSliceAnchors + wib * (32 * kChunks);          // first anchor of this warp
     const size_t img = (size_t)b * P;
     // 1. ARM filter for 32*kChunks anchors; all loads issued before the first use
@@ -191,24 +218,12 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
     }
     if (lane == 0) s_wpass[wib] = npass;
     __syncthreads();
-    {   // node list of the suppression graph: passing anchors of this slice, warp after warp
-        int off = 0, tot = 0;
+    // graph nodes: reserve a contiguous range of the image's node array for this CTA
+    int woff = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < kCollectThreads / 32; ++w) { if (w < wib) off += s_wpass[w]; tot += s_wpass[w]; }
-        int* pl = plist + ((size_t)b * S + s) * kSliceAnchors + off;
-        for (int r = lane; r < npass; r += 32) pl[r] = a0 + s_list[wib][r];
-        if (threadIdx.x == 0) pcnt[b * S + s] = tot;
-    }
-    // 2. decode the passing anchors, one per lane
-    for (int r0 = 0; r0 < npass; r0 += 32) {
-        const int r = r0 + lane;
-        if (r < npass) {
-            const int a = a0 + s_list[wib][r];
-            boxes_ws[img + a] = refine_decode(ldg_stream4(arm_loc + img + a), ldg_stream4(odm_loc + img + a),
-                                              __ldg(priors + a), v0, v1);
-        }
-    }
-    // 3. their odm_conf rows: lane = class, kRowBatch rows in flight
+    for (int w = 0; w < kCollectThreads / 32; ++w) { if (w < wib) woff += s_wpass[w]; tot += s_wpass[w]; }
+    if (threadIdx.x == 0) s_base = tot ? atomicAdd(&GO.nnodes[b], tot) : 0;
+    // 2. odm_conf rows of the passing anchors: lane = class, kRowBatch rows in flight
     const int nseg = (C + 31) >> 5;          // <= 4 (C <= 128)
     unsigned long long* cand_b = cand + ((size_t)b * C * S + s) * kSliceAnchors;    // + c * S * 1024 per class
     for (int r0 = 0; r0 < npass; r0 += kRowBatch) {
@@ -240,185 +255,200 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += kCollectThreads) cnt[((size_t)b * C + c) * S + s] = s_cnt[c];
+    // 3. decode the passing anchors, one per lane; register them as graph nodes: scaled box, bin range
+    //    (fixed bins over the image extent: any monotone binning keeps the cull conservative) and the
+    //    start / end marks OR-ed into the image's table
+    const int base = s_base;
+    const bool graph_ok = base + tot <= kGraphNodes;
+    if (!graph_ok && threadIdx.x == 0 && tot) GO.img_flag[b] = 1;
+    const bool pixel = (GO.flags & RD_NMS_PIXEL_PLUS1) != 0;
+    const bool has_scale = GO.img_scale != nullptr;
+    const float4 scale = has_scale ? __ldg(reinterpret_cast<const float4*>(GO.img_scale) + b) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const bool force_full = cull_disabled(GO.thr, GO.flags);
+    const float invx = scale.x > 0.f ? (float)kCols / scale.x : 0.f;
+    const float invy = scale.y > 0.f ? (float)kCols / scale.y : 0.f;
+    for (int r0 = 0; r0 < npass; r0 += 32) {
+        const int r = r0 + lane;
+        if (r < npass) {
+            const int a = a0 + s_list[wib][r];
+            float4 bx = refine_decode(ldg_stream4(arm_loc + img + a), ldg_stream4(odm_loc + img + a), __ldg(priors + a), v0, v1);
+            boxes_ws[img + a] = bx;
+            GO.adjn[img + a] = 0;                    // degree counter of the suppression graph
+            if (graph_ok) {
+                if (has_scale) { bx.x *= scale.x; bx.y *= scale.y; bx.z *= scale.z; bx.w *= scale.w; }
+                const int i = base + woff + r;
+                const uint32_t cr = bin_range(bx.x, bx.y, bx.z, bx.w, pixel, force_full, 0.f, invx, 0.f, invy);
+                GO.nbox[(size_t)b * kGraphNodes + i] = bx;
+                GO.nanc[(size_t)b * kGraphNodes + i] = a;
+                GO.ncr[(size_t)b * kGraphNodes + i] = cr;
+                const int ax = cr & 255u, bxx = (cr >> 8) & 255u, ay = (cr >> 16) & 255u, by = cr >> 24;
+                const uint32_t bit = 1u << (i & 31);
+                const int w = i >> 5;
+                uint32_t* tab = GO.gtab + (size_t)b * kGtabWords;
+                atomicOr(&tab[(0 * kCols + ax) * kGraphWS + w], bit);
+                if (bxx + 1 < kCols) atomicOr(&tab[(1 * kCols + bxx + 1) * kGraphWS + w], bit);
+                atomicOr(&tab[(2 * kCols + ay) * kGraphWS + w], bit);
+                if (by + 1 < kCols) atomicOr(&tab[(3 * kCols + by + 1) * kGraphWS + w], bit);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
-// KG: suppression graph of one image.  grid = (S, B), CTA (s, b) owns the passing anchors of slice s
-// ("own nodes") and tests them against ALL passing anchors of image b.  Every CTA of an image builds
-// the image's bin tables redundantly (cheap) so no inter-CTA communication is needed.
+// KG: suppression graph of one image.  grid = (kGraphSplit, B).  Every CTA loads the image's node
+// array and mark table (one round of coalesced L2 loads), finishes the prefix-OR, owns every
+// kGraphSplit-th node, lists the pairs (i < j) that survive the bin cull and tests them exactly.
 //   adj[anchor j] = { anchor u : suppresses(kept = u, candidate = j) }    (exact fp32 test, boxes scaled)
 // Images with more than kGraphNodes passing anchors, or a node of degree > kAdjDeg, are flagged and
 // handled by the per-problem bin path instead.
 // ---------------------------------------------------------------------------------------
+#ifdef RD_PROFILE_PHASES
+__device__ long long g_dbg[64];
+#define RD_MARK(slot) do { if (blockIdx.x == 3 && blockIdx.y == 5 && threadIdx.x == 0) g_dbg[slot] = clock64(); } while (0)
+#else
+#define RD_MARK(slot) do {} while (0)
+#endif
 constexpr int kGraphThreads = 256;
-constexpr int kGraphNodes = 1024;
-constexpr int kGraphW = kGraphNodes / 32;
-constexpr int kGraphWS = kGraphW + 1;
-constexpr int kGraphPairCap = 4096;
+constexpr int kGraphSplit = 16;         // CTAs per image
+constexpr int kGraphPairCap = 2048;
 
 struct GraphSmem {
     float x1[kGraphNodes], y1[kGraphNodes], x2[kGraphNodes], y2[kGraphNodes];
     uint32_t cr[kGraphNodes];
     int anchor[kGraphNodes];
-    uint32_t tab[4 * kCols * kGraphWS];
+    uint32_t tab[kGtabWords];
     uint32_t pairs[kGraphPairCap];
-    int deg[kSliceAnchors];
-    int cnt[kMaxSlices];
-    int offs[kMaxSlices + 1];
-    uint32_t ext[4];
     int wsum[kGraphThreads / 32];
     int overflow;
     int npairs;
 };
 
-__device__ __forceinline__ int load_slice_counts(const int* __restrict__ gcnt, int S, int* s_cnt, int* s_offs);
+__device__ __forceinline__ void graph_add_edge(int* __restrict__ adjn, uint32_t* __restrict__ adj, size_t img,
+                                               int a_to, int a_from, int* overflow) {
+    const int slot = atomicAdd(&adjn[img + a_to], 1);
+    if (slot < kAdjDeg) adj[(img + a_to) * kAdjDeg + slot] = (uint32_t)a_from;
+    else *overflow = 1;
+}
+
+// exact tests of one unordered pair (i < j), both directions
+__device__ __forceinline__ void graph_test_pair(const GraphSmem& G, int i, int j, float thr, int flags,
+                                                int* __restrict__ adjn, uint32_t* __restrict__ adj, size_t img,
+                                                int* overflow) {
+    const bool i_sup_j = suppresses(G.x1[i], G.y1[i], G.x2[i], G.y2[i], G.x1[j], G.y1[j], G.x2[j], G.y2[j], thr, flags);
+    // the pixel(+1) IoU is symmetric in fp32 (ai + aj commutes); the normalised one is not ((aj - inter) + ai)
+    const bool j_sup_i = (flags & RD_NMS_PIXEL_PLUS1)
+                             ? i_sup_j
+                             : suppresses(G.x1[j], G.y1[j], G.x2[j], G.y2[j], G.x1[i], G.y1[i], G.x2[i], G.y2[i], thr, flags);
+    if (i_sup_j) graph_add_edge(adjn, adj, img, G.anchor[j], G.anchor[i], overflow);
+    if (j_sup_i) graph_add_edge(adjn, adj, img, G.anchor[i], G.anchor[j], overflow);
+}
 
 __global__ void __launch_bounds__(kGraphThreads)
-graph_kernel(const int* __restrict__ pcnt, const int* __restrict__ plist, const float4* __restrict__ boxes_ws,
-             const float* __restrict__ img_scale, int P, int S, float thr, int flags,
-             uint32_t* __restrict__ adj, unsigned char* __restrict__ adjn, int* __restrict__ img_flag) {
+graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, const float4* __restrict__ nbox,
+             const int* __restrict__ nanc, const uint32_t* __restrict__ ncr, int P, float thr, int flags,
+             uint32_t* __restrict__ adj, int* __restrict__ adjn, int* __restrict__ img_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphSmem& G = *reinterpret_cast<GraphSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int s = blockIdx.x, b = blockIdx.y;
-    const int N = load_slice_counts(pcnt + (size_t)b * S, S, G.cnt, G.offs);
-    if (N > kGraphNodes) {
-        if (s == 0 && tid == 0) img_flag[b] = 1;
+    const int g = blockIdx.x, b = blockIdx.y;
+    RD_MARK(0);
+    const int N = nnodes[b];
+    if (N > kGraphNodes || img_flag[b] != 0) {
+        if (g == 0 && tid == 0) img_flag[b] = 1;
         return;
     }
-    // own nodes: i = s, s + S, s + 2S, ... (interleaved, so the few large boxes that overlap
-    // hundreds of others are spread over the CTAs of the image)
-    const int nown = N > s ? (N - s + S - 1) / S : 0;
+    // own nodes: j = g, g + kGraphSplit, ... (interleaved, so the few large boxes that overlap hundreds
+    // of others, and the later nodes that have more predecessors, are spread over the CTAs of the image)
+    const int nown = N > g ? (N - g + kGraphSplit - 1) / kGraphSplit : 0;
     if (nown == 0) return;
-    const bool pixel = (flags & RD_NMS_PIXEL_PLUS1) != 0;
-    const bool has_scale = img_scale != nullptr;
-    const float4 scale = has_scale ? __ldg(reinterpret_cast<const float4*>(img_scale) + b) : make_float4(1.f, 1.f, 1.f, 1.f);
     const size_t img = (size_t)b * P;
     const int Wn = (N + 31) >> 5;
-    // 1. nodes of the whole image -> shared memory
-    for (int i = tid; i < 4 * kCols * kGraphWS; i += kGraphThreads) G.tab[i] = 0;
-    for (int i = tid; i < nown; i += kGraphThreads) G.deg[i] = 0;
-    if (tid < 4) G.ext[tid] = (tid & 1) ? 0u : 0xffffffffu;
+    // 1. node array + mark table -> shared memory (independent loads, one round trip)
     if (tid == 0) { G.overflow = 0; G.npairs = 0; }
-    __syncthreads();
+    for (int i = tid; i < N; i += kGraphThreads) {
+        const float4 bx = nbox[(size_t)b * kGraphNodes + i];
+        G.x1[i] = bx.x; G.y1[i] = bx.y; G.x2[i] = bx.z; G.y2[i] = bx.w;
+        G.anchor[i] = nanc[(size_t)b * kGraphNodes + i];
+        G.cr[i] = ncr[(size_t)b * kGraphNodes + i];
+    }
+    RD_MARK(1);
+    // 2. inclusive prefix-OR over the bins, straight from the global marks: S[c] = starts at <= c,
+    //    E[c] = ends before c.  One (table, word) column per thread, 32 independent loads each.
     {
-        uint32_t mnx = 0xffffffffu, mxx = 0, mny = 0xffffffffu, mxy = 0;
-        for (int i = tid; i < N; i += kGraphThreads) {      // all loads of the image in flight together
-            int lo = 0, hi = S;                            // slice of node i: largest t with offs[t] <= i
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (G.offs[mid] <= i) lo = mid; else hi = mid;
-            }
-            const int a = plist[((size_t)b * S + lo) * kSliceAnchors + (i - G.offs[lo])];
-            float4 bx = boxes_ws[img + a];
-            if (has_scale) { bx.x *= scale.x; bx.y *= scale.y; bx.z *= scale.z; bx.w *= scale.w; }
-            G.anchor[i] = a;
-            G.x1[i] = bx.x; G.y1[i] = bx.y; G.x2[i] = bx.z; G.y2[i] = bx.w;
-            const float cx = 0.5f * bx.x + 0.5f * bx.z, cy = 0.5f * bx.y + 0.5f * bx.w;
-            if (isfinite(cx)) { mnx = min(mnx, float_to_ordered(cx)); mxx = max(mxx, float_to_ordered(cx)); }
-            if (isfinite(cy)) { mny = min(mny, float_to_ordered(cy)); mxy = max(mxy, float_to_ordered(cy)); }
-        }
-        mnx = __reduce_min_sync(kFullMask, mnx); mxx = __reduce_max_sync(kFullMask, mxx);
-        mny = __reduce_min_sync(kFullMask, mny); mxy = __reduce_max_sync(kFullMask, mxy);
-        if (lane == 0) {
-            atomicMin(&G.ext[0], mnx); atomicMax(&G.ext[1], mxx);
-            atomicMin(&G.ext[2], mny); atomicMax(&G.ext[3], mxy);
+        const uint32_t* gt = gtab + (size_t)b * kGtabWords;
+        for (int task = tid; task < 4 * Wn; task += kGraphThreads) {
+            const int t = task / Wn, w = task - t * Wn;
+            uint32_t v[kCols];
+#pragma unroll
+            for (int c = 0; c < kCols; ++c) v[c] = __ldg(gt + (t * kCols + c) * kGraphWS + w);
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < kCols; ++c) { acc |= v[c]; G.tab[(t * kCols + c) * kGraphWS + w] = acc; }
         }
     }
     __syncthreads();
-    // 2. bin ranges, marks, prefix-OR
-    {
-        float lox, invx, loy, invy;
-        extent_to_scale(G.ext[0], G.ext[1], lox, invx);
-        extent_to_scale(G.ext[2], G.ext[3], loy, invy);
-        const bool force_full = cull_disabled(thr, flags);
-        for (int i = tid; i < N; i += kGraphThreads) {
-            const uint32_t cr = bin_range(G.x1[i], G.y1[i], G.x2[i], G.y2[i], pixel, force_full, lox, invx, loy, invy);
-            G.cr[i] = cr;
-            const int ax = cr & 255u, bx = (cr >> 8) & 255u, ay = (cr >> 16) & 255u, by = cr >> 24;
-            const uint32_t bit = 1u << (i & 31);
-            const int w = i >> 5;
-            atomicOr(&G.tab[(0 * kCols + ax) * kGraphWS + w], bit);
-            if (bx + 1 < kCols) atomicOr(&G.tab[(1 * kCols + bx + 1) * kGraphWS + w], bit);
-            atomicOr(&G.tab[(2 * kCols + ay) * kGraphWS + w], bit);
-            if (by + 1 < kCols) atomicOr(&G.tab[(3 * kCols + by + 1) * kGraphWS + w], bit);
-        }
-    }
-    __syncthreads();
-    for (int task = tid; task < 4 * Wn; task += kGraphThreads) {
-        const int t = task / Wn, w = task - t * Wn;
-        uint32_t acc = 0;
-        uint32_t* p = G.tab + (size_t)t * kCols * kGraphWS + w;
-#pragma unroll 8
-        for (int c = 0; c < kCols; ++c) { acc |= p[c * kGraphWS]; p[c * kGraphWS] = acc; }
-    }
-    __syncthreads();
-    // 3. own nodes: candidate pairs after the bin cull, flattened and tested by all threads
+    RD_MARK(2);
+    RD_MARK(3);
+    // 3. pairs (i < j) of own nodes that survive the bin cull.  Work item = (own node, mask word):
+    //    every thread handles a few items, so nothing serialises on a box that overlaps hundreds of others.
     const uint32_t* Sx = G.tab;
     const uint32_t* Ex = G.tab + 1 * kCols * kGraphWS;
     const uint32_t* Sy = G.tab + 2 * kCols * kGraphWS;
     const uint32_t* Ey = G.tab + 3 * kCols * kGraphWS;
-    // one WARP per own node, lane = mask word (Wn <= 32): every lane lists at most 32 pairs, so a large
-    // box that overlaps hundreds of others does not serialise anything
-    for (int jl = warp; jl < nown; jl += kGraphThreads / 32) {
-        const int j = s + jl * S;
-        const uint32_t cr = G.cr[j];
+    const int nitems = nown * Wn;
+    for (int q0 = 0; q0 < nitems; q0 += kGraphThreads) {
+        const int q = q0 + tid;
         uint32_t h = 0;
-        if (lane < Wn) {
-            h = Sx[((cr >> 8) & 255u) * kGraphWS + lane] & ~Ex[(cr & 255u) * kGraphWS + lane] &
-                Sy[((cr >> 24) & 255u) * kGraphWS + lane] & ~Ey[((cr >> 16) & 255u) * kGraphWS + lane];
-            if (lane == (j >> 5)) h &= ~(1u << (j & 31));
+        int jl = 0, w = 0;
+        if (q < nitems) {
+            jl = q / Wn; w = q - jl * Wn;
+            const int j = g + jl * kGraphSplit;
+            const int jw = j >> 5;
+            if (w <= jw) {
+                const uint32_t cr = G.cr[j];
+                h = Sx[((cr >> 8) & 255u) * kGraphWS + w] & ~Ex[(cr & 255u) * kGraphWS + w] &
+                    Sy[((cr >> 24) & 255u) * kGraphWS + w] & ~Ey[((cr >> 16) & 255u) * kGraphWS + w];
+                if (w == jw) h &= (1u << (j & 31)) - 1u;      // predecessors only
+            }
         }
         const int c = __popc(h);
         int x = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, x, d); if (lane >= d) x += o; }
-        const int tot = __shfl_sync(kFullMask, x, 31);
-        if (tot == 0) continue;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&G.npairs, tot);
-        base = __shfl_sync(kFullMask, base, 0);
-        int off = base + x - c;
-        if (base + tot <= kGraphPairCap) {
-            while (h) {
-                const int i = (lane << 5) + __ffs(h) - 1;
-                h &= h - 1;
-                G.pairs[off++] = ((uint32_t)jl << 16) | (uint32_t)i;
-            }
-        } else {                                   // list full: void the reserved slots, test in place
-            for (int q = base + lane; q < min(base + tot, kGraphPairCap); q += 32) G.pairs[q] = 0xffffffffu;
-            const float jx1 = G.x1[j], jy1 = G.y1[j], jx2 = G.x2[j], jy2 = G.y2[j];
-            while (h) {
-                const int i = (lane << 5) + __ffs(h) - 1;
-                h &= h - 1;
-                if (suppresses(G.x1[i], G.y1[i], G.x2[i], G.y2[i], jx1, jy1, jx2, jy2, thr, flags)) {
-                    const int slot = atomicAdd(&G.deg[jl], 1);
-                    if (slot < kAdjDeg) adj[(img + G.anchor[j]) * kAdjDeg + slot] = (uint32_t)G.anchor[i];
-                    else G.overflow = 1;
-                }
-            }
+        if (lane == 31) G.wsum[warp] = x;
+        __syncthreads();
+        int off = x - c, tot = 0;
+#pragma unroll
+        for (int ww = 0; ww < kGraphThreads / 32; ++ww) { if (ww < warp) off += G.wsum[ww]; tot += G.wsum[ww]; }
+        const int base = G.npairs;                      // uniform: updated below after a barrier
+        off += base;
+        const int j = g + jl * kGraphSplit;
+        while (h) {
+            const int i = (w << 5) + __ffs(h) - 1;
+            h &= h - 1;
+            if (off < kGraphPairCap) G.pairs[off] = ((uint32_t)jl << 16) | (uint32_t)i;
+            else graph_test_pair(G, i, j, thr, flags, adjn, adj, img, &G.overflow);   // list full: test in place
+            ++off;
         }
+        __syncthreads();
+        if (tid == 0) G.npairs = base + tot;
+        __syncthreads();
     }
-    __syncthreads();
+    RD_MARK(4);
+    RD_MARK(5);
     {
         const int cnt = min(G.npairs, kGraphPairCap);
         for (int p = tid; p < cnt; p += kGraphThreads) {
             const uint32_t e = G.pairs[p];
-            if (e == 0xffffffffu) continue;
-            const int jl = (int)(e >> 16), i = (int)(e & 0xffffu);
-            const int jj = s + jl * S;
-            if (suppresses(G.x1[i], G.y1[i], G.x2[i], G.y2[i], G.x1[jj], G.y1[jj], G.x2[jj], G.y2[jj], thr, flags)) {
-                const int slot = atomicAdd(&G.deg[jl], 1);
-                if (slot < kAdjDeg) adj[(img + G.anchor[jj]) * kAdjDeg + slot] = (uint32_t)G.anchor[i];
-                else G.overflow = 1;
-            }
+            graph_test_pair(G, (int)(e & 0xffffu), g + (int)(e >> 16) * kGraphSplit, thr, flags, adjn, adj, img,
+                            &G.overflow);
         }
     }
     __syncthreads();
-    for (int i = tid; i < nown; i += kGraphThreads) {
-        const int d = G.deg[i];
-        adjn[img + G.anchor[s + i * S]] = (unsigned char)(d < kAdjDeg ? d : kAdjDeg);
-    }
+    RD_MARK(6);
+#ifdef RD_PROFILE_PHASES
+    if (blockIdx.x == 3 && blockIdx.y == 5 && tid == 0) { g_dbg[10] = N; g_dbg[11] = G.npairs; g_dbg[12] = nown; }
+#endif
     if (tid == 0 && G.overflow) img_flag[b] = 1;
 }
 
@@ -432,11 +462,11 @@ struct FusedNmsArgs {
     const float* img_scale;          // [B,4] or null
     int* queue;
     uint32_t* header;
+    int* nnodes;                     // [B]   } control block, cleared by the class-0 CTA of every image
+    uint32_t* gtab;                  // [B][kGtabWords]
     const int* img_flag;             // [B] 1 = no graph for this image
     const uint32_t* adj;             // [B*P*kAdjDeg]
-    const unsigned char* adjn;       // [B*P]
-    const float* odm_conf;           // [B,P,C]
-    float conf_thresh;
+    const int* adjn;                 // [B*P]
     int nbc, C, P, S;
     float thr;
     int top_k, max_out, flags, row_layout;
@@ -488,13 +518,18 @@ __device__ __forceinline__ void fill_problem(NmsProblem& pb, RowSink& sink, int 
     sink.row_layout = A.row_layout;
 }
 
-__global__ void __launch_bounds__(kSmallThreads, 16)
+__global__ void __launch_bounds__(kSmallThreads, 24)
 nms_small_kernel(FusedNmsArgs A) {
     __shared__ SmallSmem S;
     const int bc = blockIdx.x;
     const int c = bc % A.C;
     if (c == 0) {                      // background is never evaluated (eval_refinedet_coco.py:213)
-        if (threadIdx.x == 0) A.out_counts[bc] = 0;
+        // this CTA has no problem: it leaves the graph control block of its image zero for the next call
+        // (graph_kernel, the only reader, completed before this kernel started)
+        const int b0 = bc / A.C;
+        uint32_t* gt = A.gtab + (size_t)b0 * kGtabWords;
+        for (int i = threadIdx.x; i < kGtabWords; i += kSmallThreads) gt[i] = 0;
+        if (threadIdx.x == 0) { A.nnodes[b0] = 0; A.out_counts[bc] = 0; }
         return;
     }
     const int n = load_slice_counts(A.cnt + (size_t)bc * A.S, A.S, S.cnt, S.offs);
@@ -502,25 +537,18 @@ nms_small_kernel(FusedNmsArgs A) {
         if (threadIdx.x == 0) A.out_counts[bc] = 0;
         return;
     }
-    if (n > A.top_k || n > kSmallCap) {
+    const int b = bc / A.C;
+    if (n > A.top_k || n > kSmallCap || A.img_flag[b] != 0) {     // needs the select / own bins: large kernel
         if (threadIdx.x == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
         return;
     }
     NmsProblem pb;
     RowSink sink;
     fill_problem(pb, sink, bc, n, S.cnt, S.offs, A);
-    const int b = bc / A.C;
-    int kept;
-    if (A.img_flag[b] == 0) {
-        GraphView G;
-        G.adj = A.adj + (size_t)b * A.P * kAdjDeg;
-        G.adjn = A.adjn + (size_t)b * A.P;
-        G.conf = A.odm_conf + (size_t)b * A.P * A.C;
-        G.C = A.C; G.c = c; G.conf_thresh = A.conf_thresh;
-        kept = cta_nms_graph(S, pb, sink, G);
-    } else {
-        kept = cta_nms_small(S, pb, sink);
-    }
+    GraphView G;
+    G.adj = reinterpret_cast<const uint4*>(A.adj + (size_t)b * A.P * kAdjDeg);
+    G.adjn = A.adjn + (size_t)b * A.P;
+    const int kept = cta_nms_graph(S, pb, sink, G);
     if (threadIdx.x == 0) A.out_counts[bc] = kept;
 }
 
@@ -638,6 +666,12 @@ extern "C" {
 
 unsigned long long rd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+#ifdef RD_PROFILE_PHASES
+__attribute__((visibility("default"))) int rd_debug_read(long long* out64) {
+    return (int)cudaMemcpyFromSymbol(out64, g_dbg, sizeof(long long) * 64);
+}
+#endif
+
 int rd_detect_forward(const float* arm_loc, const float* arm_conf, const float* odm_loc, float* odm_conf,
                       const float* priors, int B, int P, int C, float objectness_thre, float v0, float v1,
                       float* boxes_out, float* scores_out, void* stream) {
@@ -665,8 +699,8 @@ size_t rd_detect_workspace_bytes(int B, int P, int C) {
 
 int rd_detect_workspace_reset(void* workspace, size_t workspace_bytes, void* stream) {
     if (!workspace) return RD_ERR_BAD_ARG;
-    // only the header needs a defined value; the candidate area is write-before-read
-    cudaError_t e = cudaMemsetAsync(workspace, 0, workspace_bytes < 256 ? workspace_bytes : 256, (cudaStream_t)stream);
+    // the control block (header, nnodes, gtab) must start zero; its size depends on B, so clear everything
+    cudaError_t e = cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream);
     return (int)e;
 }
 
@@ -690,11 +724,13 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     if (workspace_bytes < ws.total) return RD_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
 
+    GraphOut GO;
+    GO.nnodes = ws.nnodes; GO.gtab = ws.gtab; GO.nbox = ws.nbox; GO.nanc = ws.nanc; GO.ncr = ws.ncr;
+    GO.adjn = ws.adjn; GO.img_flag = ws.flag; GO.img_scale = img_scale; GO.thr = nms_thresh; GO.flags = nms_flags;
     if (ev) cudaEventRecord(ev[0], st);
     collect_kernel<<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
         (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
-        P, C, ws.S, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.header, ws.pcnt, ws.plist,
-        ws.flag);
+        P, C, ws.S, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.header, GO);
     note_launch();
     RD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[1], st);
@@ -706,8 +742,8 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
             if (e != cudaSuccess) return (int)e;
             s_graph_attr = true;
         }
-        graph_kernel<<<dim3(ws.S, B), kGraphThreads, sizeof(GraphSmem), st>>>(
-            ws.pcnt, ws.plist, ws.boxes, img_scale, P, ws.S, nms_thresh, nms_flags, ws.adj, ws.adjn, ws.flag);
+        graph_kernel<<<dim3(kGraphSplit, B), kGraphThreads, sizeof(GraphSmem), st>>>(
+            ws.nnodes, ws.gtab, ws.nbox, ws.nanc, ws.ncr, P, nms_thresh, nms_flags, ws.adj, ws.adjn, ws.flag);
         note_launch();
         RD_CHECK_LAUNCH();
     }
@@ -715,7 +751,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     FusedNmsArgs A;
     A.cnt = ws.cnt; A.cand = ws.cand; A.boxes = ws.boxes; A.img_scale = img_scale;
     A.queue = ws.queue; A.header = ws.header;
-    A.img_flag = ws.flag; A.adj = ws.adj; A.adjn = ws.adjn; A.odm_conf = odm_conf; A.conf_thresh = conf_thresh;
+    A.img_flag = ws.flag; A.adj = ws.adj; A.adjn = ws.adjn; A.nnodes = ws.nnodes; A.gtab = ws.gtab;
     A.nbc = B * C; A.C = C; A.P = P; A.S = ws.S;
     A.thr = nms_thresh; A.top_k = top_k; A.max_out = max_out; A.flags = nms_flags; A.row_layout = row_layout;
     A.out_counts = out_counts; A.out_dets = out_dets; A.out_anchor = out_anchor;

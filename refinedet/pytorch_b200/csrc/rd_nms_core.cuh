@@ -18,10 +18,10 @@
 //   step; the surviving (candidate, kept earlier box) pairs are flattened into a list and tested
 //   by all threads, in-block dependencies are resolved with ballots.
 //
-//   small problems (n <= 256, no select): cta_nms_small — sorted runs of 32 in registers
-//     (bitonic over shuffles) merged by rank, 12.7 KB of shared memory so 16 CTAs fit per SM
-//   large problems: nms_process — radix select over the L2-resident key list when n > top_k,
-//     shared-memory bitonic sort, same cull / walk with the tests done in place
+//   small problems (n <= 256, no select) of images whose suppression graph exists: cta_nms_graph —
+//     sorted runs of 32 in registers (bitonic over shuffles) merged by rank, then graph look-ups
+//   everything else: nms_process — radix select over the L2-resident key list when n > top_k,
+//     shared-memory bitonic sort, per-problem bin tables, walk with the tests done in place
 #pragma once
 #include "rd_common.cuh"
 
@@ -165,23 +165,24 @@ constexpr int kSmallThreads = 64;
 constexpr int kSmallWarps = kSmallThreads / 32;
 constexpr int kSmallCap = 256;
 constexpr int kSmallW = kSmallCap / 32;      // 8 mask words
-constexpr int kPairCap = 256;                // flattened (candidate, earlier box) pairs per 32-candidate step
+
+constexpr int kAdjDeg = 8;            // adjacency slots per anchor; an image whose graph overflows is flagged dense
+constexpr int kHashSlots = 512;       // anchor -> rank hash table of one problem (load factor <= 0.5)
 
 struct SmallSmem {
-    unsigned long long keys[kSmallCap];                                    // sorted keys
-    float x1[kSmallCap], y1[kSmallCap], x2[kSmallCap], y2[kSmallCap];      // x1,y1 double as the runs buffer
-    uint32_t cr[kSmallCap];                                                // bin ranges
-    uint32_t tab[4 * kSmallW * kCols];                                     // [table][word][bin]
-    uint32_t pairs[kPairCap];
+    unsigned long long keys[kSmallCap];           // sorted keys
+    union {
+        unsigned long long runs[kSmallCap];       // sorted runs of 32 (during the sort)
+        struct {
+            uint32_t hash[kHashSlots];            // (anchor << 8) | rank, 0xffffffff = empty
+            unsigned char deps[kSmallCap * kAdjDeg];   // ranks of the dependencies of every candidate
+        } g;
+    } u;
+    unsigned char depn[kSmallCap];
+    unsigned char state[kSmallCap];               // 0 undecided, 1 kept, 2 suppressed
     int cnt[kMaxSlices];
     int offs[kMaxSlices + 1];
-    uint32_t keptbits[kSmallW];
-    uint32_t tin[32];
-    uint32_t ext[4];
-    uint32_t sup;
-    int total;
-    int kept_total;
-    int stop;
+    int wsum[kSmallWarps];
 };
 
 // key of flattened element e of a sliced candidate list
@@ -206,7 +207,7 @@ __device__ __forceinline__ void cta_sort_small(SmallSmem& S, const CandList& cl)
     const int warp = tid >> 5;
     const int m = cl.n;
     const int Wm = (m + 31) >> 5;
-    unsigned long long* runs = reinterpret_cast<unsigned long long*>(S.x1);   // 256 x 8 B = x1 + y1
+    unsigned long long* runs = S.u.runs;
     for (int run = warp; run < Wm; run += kSmallWarps) {
         const int e = run * 32 + lane;
         unsigned long long k = e < m ? cand_at(cl, e) : 0ull;
@@ -234,292 +235,119 @@ __device__ __forceinline__ void cta_sort_small(SmallSmem& S, const CandList& cl)
     }
 }
 
-// Runs one small problem on the calling CTA (kSmallThreads threads) with its own bin tables.
-// S.cnt / S.offs must hold the candidate list's slice counts / prefix sums.  Returns the kept count
-// (uniform over the CTA).
-__device__ inline int cta_nms_small(SmallSmem& S, const NmsProblem& pb, const RowSink& sink) {
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int m = pb.cl.n;                                   // caller guarantees n <= min(top_k, kSmallCap)
-    const int Wm = (m + 31) >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    const bool pixel = (pb.flags & RD_NMS_PIXEL_PLUS1) != 0;
-
-    for (int i = tid; i < 4 * kSmallW * kCols; i += kSmallThreads) S.tab[i] = 0;
-    if (tid < 4) S.ext[tid] = (tid & 1) ? 0u : 0xffffffffu;   // min cx, max cx, min cy, max cy (ordered)
-    if (tid < 32) S.tin[tid] = 0;
-    if (tid == 0) { S.sup = 0; S.kept_total = 0; S.stop = 0; }
-    cta_sort_small(S, pb.cl);
-    // ---- C. boxes + extent of the box centres --------------------------------------------------
-    float bx1[kSmallCap / kSmallThreads], by1[kSmallCap / kSmallThreads], bx2[kSmallCap / kSmallThreads],
-        by2[kSmallCap / kSmallThreads];
-    {
-        uint32_t mnx = 0xffffffffu, mxx = 0, mny = 0xffffffffu, mxy = 0;
-#pragma unroll
-        for (int q = 0; q < kSmallCap / kSmallThreads; ++q) {
-            const int j = q * kSmallThreads + tid;
-            bx1[q] = by1[q] = bx2[q] = by2[q] = 0.f;
-            if (j < m) {
-                float4 b = pb.boxes[key_index(S.keys[j])];
-                if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
-                bx1[q] = b.x; by1[q] = b.y; bx2[q] = b.z; by2[q] = b.w;
-                // bin extent = range of the box CENTRES: a few huge boxes must not coarsen the bins;
-                // boxes reaching beyond it clamp to the edge bins, which stays conservative
-                const float cx = 0.5f * b.x + 0.5f * b.z, cy = 0.5f * b.y + 0.5f * b.w;
-                if (isfinite(cx)) { mnx = min(mnx, float_to_ordered(cx)); mxx = max(mxx, float_to_ordered(cx)); }
-                if (isfinite(cy)) { mny = min(mny, float_to_ordered(cy)); mxy = max(mxy, float_to_ordered(cy)); }
-            }
-        }
-        mnx = __reduce_min_sync(kFullMask, mnx); mxx = __reduce_max_sync(kFullMask, mxx);
-        mny = __reduce_min_sync(kFullMask, mny); mxy = __reduce_max_sync(kFullMask, mxy);
-        if (lane == 0) {
-            atomicMin(&S.ext[0], mnx); atomicMax(&S.ext[1], mxx);
-            atomicMin(&S.ext[2], mny); atomicMax(&S.ext[3], mxy);
-        }
-    }
-    __syncthreads();                                 // `runs` is dead, extents are final
-    // ---- D. SoA stores, bin ranges, start / end marks -------------------------------------------
-    {
-        float lox, invx, loy, invy;
-        extent_to_scale(S.ext[0], S.ext[1], lox, invx);
-        extent_to_scale(S.ext[2], S.ext[3], loy, invy);
-        const bool force_full = cull_disabled(pb.thr, pb.flags);
-#pragma unroll
-        for (int q = 0; q < kSmallCap / kSmallThreads; ++q) {
-            const int j = q * kSmallThreads + tid;
-            if (j < m) {
-                S.x1[j] = bx1[q]; S.y1[j] = by1[q]; S.x2[j] = bx2[q]; S.y2[j] = by2[q];
-                const uint32_t cr = bin_range(bx1[q], by1[q], bx2[q], by2[q], pixel, force_full, lox, invx, loy, invy);
-                S.cr[j] = cr;
-                const int ax = cr & 255u, bx = (cr >> 8) & 255u, ay = (cr >> 16) & 255u, by = cr >> 24;
-                const uint32_t bit = 1u << (j & 31);
-                const int w = j >> 5;
-                atomicOr(&S.tab[(0 * kSmallW + w) * kCols + ax], bit);
-                if (bx + 1 < kCols) atomicOr(&S.tab[(1 * kSmallW + w) * kCols + bx + 1], bit);
-                atomicOr(&S.tab[(2 * kSmallW + w) * kCols + ay], bit);
-                if (by + 1 < kCols) atomicOr(&S.tab[(3 * kSmallW + w) * kCols + by + 1], bit);
-            }
-        }
-    }
-    __syncthreads();
-    // ---- E. inclusive prefix-OR over the bins (lane = bin) --------------------------------------
-    for (int task = warp; task < 4 * Wm; task += kSmallWarps) {
-        const int t = task / Wm, w = task - t * Wm;
-        uint32_t* p = S.tab + (t * kSmallW + w) * kCols + lane;
-        uint32_t v = *p;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(kFullMask, v, d); if (lane >= d) v |= o; }
-        *p = v;
-    }
-    __syncthreads();
-
-    // ---- F. walk: warp 0 drives, every thread helps with the exact tests -------------------------
-    const float thr = pb.thr;
-    const int flags = pb.flags;
-    const int max_out = pb.max_out;
-    int kept_total = 0;                               // meaningful in warp 0
-    for (int ib = 0; ib < Wm; ++ib) {
-        const int j = ib * 32 + lane;
-        const bool valid = j < m;
-        bool alive = valid;
-        uint32_t h[kSmallW];
-        float x1 = 0.f, y1 = 0.f, x2 = 0.f, y2 = 0.f;
-        int total = 0;
-        if (warp == 0) {
-            uint32_t cr = 0;
-            if (valid) { x1 = S.x1[j]; y1 = S.y1[j]; x2 = S.x2[j]; y2 = S.y2[j]; cr = S.cr[j]; }
-            const int ax = cr & 255u, bx = (cr >> 8) & 255u, ay = (cr >> 16) & 255u, by = cr >> 24;
-            int nh = 0;
-#pragma unroll
-            for (int w = 0; w < kSmallW; ++w) {
-                h[w] = 0;
-                if (w <= ib && valid) {
-                    h[w] = S.tab[(0 * kSmallW + w) * kCols + bx] & ~S.tab[(1 * kSmallW + w) * kCols + ax] &
-                           S.tab[(2 * kSmallW + w) * kCols + by] & ~S.tab[(3 * kSmallW + w) * kCols + ay] &
-                           (w < ib ? S.keptbits[w] : lt_mask);
-                    nh += __popc(h[w]);
-                }
-            }
-            int off = nh;                            // inclusive scan over lanes
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, off, d); if (lane >= d) off += o; }
-            total = __shfl_sync(kFullMask, off, 31);
-            off -= nh;
-            if (total > 0 && total <= kPairCap) {
-#pragma unroll
-                for (int w = 0; w < kSmallW; ++w) {
-                    uint32_t hw = h[w];
-                    while (hw) {
-                        const int i = (w << 5) + __ffs(hw) - 1;
-                        hw &= hw - 1;
-                        S.pairs[off++] = ((uint32_t)lane << 16) | (uint32_t)i;
-                    }
-                }
-            }
-            if (lane == 0) S.total = total;
-        }
-        __syncthreads();
-        total = S.total;
-        if (total > 0 && total <= kPairCap) {
-            for (int p = tid; p < total; p += kSmallThreads) {
-                const uint32_t e = S.pairs[p];
-                const int jl = (int)(e >> 16), i = (int)(e & 0xffffu);
-                const int jj = ib * 32 + jl;
-                if (suppresses(S.x1[i], S.y1[i], S.x2[i], S.y2[i], S.x1[jj], S.y1[jj], S.x2[jj], S.y2[jj], thr, flags)) {
-                    if (i < ib * 32) atomicOr(&S.sup, 1u << jl);
-                    else atomicOr(&S.tin[jl], 1u << (i - ib * 32));
-                }
-            }
-        }
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t tin = 0;
-            if (total > 0 && total <= kPairCap) {
-                if ((S.sup >> lane) & 1u) alive = false;
-                tin = S.tin[lane];
-                __syncwarp();
-                S.tin[lane] = 0;
-                if (lane == 0) S.sup = 0;
-            } else if (total > 0) {                  // pair list would overflow: test in place
-#pragma unroll
-                for (int w = 0; w < kSmallW; ++w) {
-                    uint32_t hw = h[w];
-                    while (hw && (alive || w == ib)) {
-                        const int i = (w << 5) + __ffs(hw) - 1;
-                        hw &= hw - 1;
-                        if (suppresses(S.x1[i], S.y1[i], S.x2[i], S.y2[i], x1, y1, x2, y2, thr, flags)) {
-                            if (w < ib) alive = false; else tin |= 1u << (i - ib * 32);
-                        }
-                    }
-                }
-            }
-            // in-block resolution in score order
-            uint32_t u = __reduce_or_sync(kFullMask, alive ? tin : 0u);
-            while (u) {
-                const int k = __ffs(u) - 1;
-                u &= u - 1;
-                const uint32_t al = __ballot_sync(kFullMask, alive);
-                if (((al >> k) & 1u) && ((tin >> k) & 1u)) alive = false;
-            }
-            uint32_t keptw = __ballot_sync(kFullMask, alive);
-            const int room = max_out - kept_total;
-            int cnt = __popc(keptw);
-            if (cnt > room) {
-                uint32_t t = keptw, keep = 0;
-                for (int r = 0; r < room; ++r) { const uint32_t low = t & (0u - t); keep |= low; t ^= low; }
-                keptw = keep;
-                cnt = room;
-            }
-            if ((keptw >> lane) & 1u)
-                sink_emit(sink, kept_total + __popc(keptw & lt_mask), S.keys[j], x1, y1, x2, y2);
-            kept_total += cnt;
-            if (lane == 0) {
-                S.keptbits[ib] = keptw;
-                S.kept_total = kept_total;
-                if (kept_total >= max_out) S.stop = 1;
-            }
-        }
-        __syncthreads();
-        if (S.stop) break;
-    }
-    return S.kept_total;
-}
-
 // =========================================================================================
 // small problems, graph mode: the suppression relation between the ARM-passing anchors of an
 // image does not depend on the class, so it is computed once per image (graph_kernel in
 // rd_detect.cu) as adjacency lists  adj[anchor] = {u : box u suppresses box anchor when u is kept}.
-// A problem then only sorts its keys, looks up the few neighbours that are candidates of ITS class
-// with a higher key, and resolves the dependencies; no boxes, bins or IoUs per class.
+// A problem then only sorts its keys, finds which graph neighbours are candidates of ITS class with
+// a higher key (shared-memory hash anchor -> rank) and resolves the dependencies; no boxes, bins or
+// IoUs per class.  7.1 KB of shared memory, <= 40 registers: 24 CTAs resident per SM.
 // =========================================================================================
-constexpr int kAdjDeg = 8;            // adjacency slots per anchor; an image whose graph overflows is flagged dense
-
 struct GraphView {
-    const uint32_t* adj;              // [P][kAdjDeg] anchors of the image
-    const unsigned char* adjn;        // [P] degree (<= kAdjDeg)
-    const float* conf;                // odm_conf rows of the image, [P][C]
-    int C, c;
-    float conf_thresh;
+    const uint4* adj;                 // [P][kAdjDeg] anchors of the image, as two uint4 per anchor
+    const int* adjn;                  // [P] degree (<= kAdjDeg when the image is not flagged)
 };
+
+__device__ __forceinline__ uint32_t hash_anchor(uint32_t a) { return (a * 2654435761u) >> 23; }   // 9 bits
 
 __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const RowSink& sink, const GraphView& G) {
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int m = pb.cl.n;                                   // n <= min(top_k, kSmallCap): nothing is truncated
-    unsigned char* depn = reinterpret_cast<unsigned char*>(S.cr);       // [256] number of dependencies
-    unsigned char* deps = reinterpret_cast<unsigned char*>(S.tab);      // [256][kAdjDeg] rank of each dependency
-    unsigned char* state = reinterpret_cast<unsigned char*>(S.pairs);   // [256] 0 undecided, 1 kept, 2 suppressed
-    int* wsum = reinterpret_cast<int*>(S.tin);                          // cross-warp scan scratch
-    cta_sort_small(S, pb.cl);
-
-    // ---- dependencies: neighbours that are candidates of this class and rank earlier -------------
-    for (int r = tid; r < m; r += kSmallThreads) {
-        const unsigned long long key = S.keys[r];
-        const uint32_t a = key_index(key);
-        const int dn = G.adjn[a];
-        int nd = 0;
-        for (int k = 0; k < dn; ++k) {
-            const uint32_t u = G.adj[(size_t)a * kAdjDeg + k];
-            const float su = G.conf[(size_t)u * G.C + G.c];
-            if (!(su > G.conf_thresh)) continue;
-            const unsigned long long ku = make_key(su, u);
-            if (ku > key) {
-                int lo = 0, hi = r;                          // keys are descending: first index with keys[idx] <= ku
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (S.keys[mid] > ku) lo = mid + 1; else hi = mid;
-                }
-                if (lo < r && S.keys[lo] == ku) deps[r * kAdjDeg + nd++] = (unsigned char)lo;
-            }
+    cta_sort_small(S, pb.cl);                                // ends with a CTA barrier: `runs` is dead
+    for (int i = tid; i < kHashSlots; i += kSmallThreads) S.u.g.hash[i] = 0xffffffffu;
+    __syncthreads();
+    // adjacency rows of my candidates (independent of the rank): issue the loads first
+    constexpr int kPerT = kSmallCap / kSmallThreads;
+    uint4 row0[kPerT], row1[kPerT];
+    int dn[kPerT];
+#pragma unroll
+    for (int q = 0; q < kPerT; ++q) {
+        const int r = q * kSmallThreads + tid;
+        dn[q] = 0;
+        if (r < m) {
+            const uint32_t a = key_index(S.keys[r]);
+            dn[q] = G.adjn[a];
+            row0[q] = __ldg(G.adj + (size_t)a * 2);
+            row1[q] = __ldg(G.adj + (size_t)a * 2 + 1);
+            uint32_t h = hash_anchor(a);                     // insert (anchor -> rank)
+            const uint32_t val = (a << 8) | (uint32_t)r;
+            while (atomicCAS(&S.u.g.hash[h], 0xffffffffu, val) != 0xffffffffu) h = (h + 1) & (kHashSlots - 1);
         }
-        depn[r] = (unsigned char)nd;
-        state[r] = nd == 0 ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- dependencies: graph neighbours that are candidates of this class and rank earlier --------
+#pragma unroll
+    for (int q = 0; q < kPerT; ++q) {
+        const int r = q * kSmallThreads + tid;
+        if (r < m) {
+            const uint32_t nb[kAdjDeg] = {row0[q].x, row0[q].y, row0[q].z, row0[q].w,
+                                          row1[q].x, row1[q].y, row1[q].z, row1[q].w};
+            int nd = 0;
+#pragma unroll
+            for (int k = 0; k < kAdjDeg; ++k) {
+                if (k < dn[q]) {
+                    const uint32_t u = nb[k];
+                    uint32_t h = hash_anchor(u);
+                    for (;;) {
+                        const uint32_t v = S.u.g.hash[h];
+                        if (v == 0xffffffffu) break;                    // u is not a candidate of this class
+                        if ((v >> 8) == u) {
+                            const int ru = (int)(v & 255u);
+                            if (ru < r) S.u.g.deps[r * kAdjDeg + nd++] = (unsigned char)ru;
+                            break;
+                        }
+                        h = (h + 1) & (kHashSlots - 1);
+                    }
+                }
+            }
+            S.depn[r] = (unsigned char)nd;
+            S.state[r] = nd == 0 ? 1 : 0;
+        }
     }
     __syncthreads();
     // ---- resolve in rounds (dependencies always point to earlier ranks: terminates) ---------------
     for (int round = 0; round < kSmallCap; ++round) {
         int undecided = 0;
         for (int r = tid; r < m; r += kSmallThreads) {
-            if (state[r] != 0) continue;
-            const int nd = depn[r];
+            if (S.state[r] != 0) continue;
+            const int nd = S.depn[r];
             bool any_kept = false, all_sup = true;
             for (int k = 0; k < nd; ++k) {
-                const unsigned char st = state[deps[r * kAdjDeg + k]];
+                const unsigned char st = S.state[S.u.g.deps[r * kAdjDeg + k]];
                 any_kept |= (st == 1);
                 all_sup &= (st == 2);
             }
-            if (any_kept) state[r] = 2;
-            else if (all_sup) state[r] = 1;
+            if (any_kept) S.state[r] = 2;
+            else if (all_sup) S.state[r] = 1;
             else undecided = 1;
         }
         if (!__syncthreads_or(undecided)) break;
     }
     // ---- emit kept rows in rank order, first max_out ----------------------------------------------
-    constexpr int kPer = kSmallCap / kSmallThreads;          // consecutive ranks per thread
     int local = 0;
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-        const int r = tid * kPer + q;
-        if (r < m && state[r] == 1) ++local;
+    for (int q = 0; q < kPerT; ++q) {
+        const int r = tid * kPerT + q;
+        if (r < m && S.state[r] == 1) ++local;
     }
     int x = local;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, x, d); if (lane >= d) x += o; }
-    if (lane == 31) wsum[warp] = x;
+    if (lane == 31) S.wsum[warp] = x;
     __syncthreads();
     int base = x - local;
     int total = 0;
 #pragma unroll
     for (int w = 0; w < kSmallWarps; ++w) {
-        if (w < warp) base += wsum[w];
-        total += wsum[w];
+        if (w < warp) base += S.wsum[w];
+        total += S.wsum[w];
     }
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-        const int r = tid * kPer + q;
-        if (r < m && state[r] == 1) {
+    for (int q = 0; q < kPerT; ++q) {
+        const int r = tid * kPerT + q;
+        if (r < m && S.state[r] == 1) {
             if (base < pb.max_out) {
                 const unsigned long long key = S.keys[r];
                 float4 b = pb.boxes[key_index(key)];
