@@ -35,7 +35,7 @@ constexpr int kLargeThreads = 128;
 // workspace of the fused stage.  The control block (header, nnodes, gtab) must be zero when a call
 // starts: rd_detect_workspace_reset zeroes it once, every call leaves it zero again (collect clears
 // the queue header, nms_small's class-0 CTAs clear nnodes / gtab of their image).
-//   header u32 [64]               : [0] = number of queued large problems
+//   header u32 [64]               : [0] = number of queued large problems, [1] = CTA ticket of nms_small
 //   nnodes int [B]                : graph nodes (= ARM-passing anchors) of every image
 //   gtab   u32 [B][4][32][33]     : start/end bin marks of the nodes (OR-ed in by collect)
 //   flag   int [B]                : 1 = the image has no suppression graph (too many nodes / degree overflow)
@@ -468,6 +468,7 @@ struct FusedNmsArgs {
     const uint32_t* adj;             // [B*P*kAdjDeg]
     const int* adjn;                 // [B*P]
     int nbc, C, P, S;
+    int large_grid, large_mcap, large_smem;   // launch shape of nms_large_kernel (tail-launched on demand)
     float thr;
     int top_k, max_out, flags, row_layout;
     int* out_counts;
@@ -518,6 +519,32 @@ __device__ __forceinline__ void fill_problem(NmsProblem& pb, RowSink& sink, int 
     sink.row_layout = A.row_layout;
 }
 
+__global__ void nms_large_kernel(FusedNmsArgs A, int mcap);
+
+// Last CTA of nms_small_kernel: if any problem was queued, tail-launch nms_large_kernel from the device
+// (CUDA dynamic parallelism) so the common case -- nothing queued -- costs no launch at all.
+__device__ __forceinline__ void small_epilogue(const FusedNmsArgs& A) {
+#ifndef RD_USE_CDP
+    return;
+#endif
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t t = atomicAdd(&A.header[1], 1u);
+        if (t == gridDim.x - 1) {
+            A.header[1] = 0;
+            __threadfence();
+            const uint32_t nq = *((volatile uint32_t*)&A.header[0]);
+#ifdef RD_USE_CDP
+            if (nq > 0) {
+                const uint32_t grid = nq < (uint32_t)A.large_grid ? nq : (uint32_t)A.large_grid;
+                nms_large_kernel<<<grid, kLargeThreads, A.large_smem, cudaStreamTailLaunch>>>(A, A.large_mcap);
+            }
+#endif
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kSmallThreads, 24)
 nms_small_kernel(FusedNmsArgs A) {
     __shared__ SmallSmem S;
@@ -530,16 +557,19 @@ nms_small_kernel(FusedNmsArgs A) {
         uint32_t* gt = A.gtab + (size_t)b0 * kGtabWords;
         for (int i = threadIdx.x; i < kGtabWords; i += kSmallThreads) gt[i] = 0;
         if (threadIdx.x == 0) { A.nnodes[b0] = 0; A.out_counts[bc] = 0; }
+        small_epilogue(A);
         return;
     }
     const int n = load_slice_counts(A.cnt + (size_t)bc * A.S, A.S, S.cnt, S.offs);
     if (n == 0) {
         if (threadIdx.x == 0) A.out_counts[bc] = 0;
+        small_epilogue(A);
         return;
     }
     const int b = bc / A.C;
     if (n > A.top_k || n > kSmallCap || A.img_flag[b] != 0) {     // needs the select / own bins: large kernel
         if (threadIdx.x == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
+        small_epilogue(A);
         return;
     }
     NmsProblem pb;
@@ -550,6 +580,7 @@ nms_small_kernel(FusedNmsArgs A) {
     G.adjn = A.adjn + (size_t)b * A.P;
     const int kept = cta_nms_graph(S, pb, sink, G);
     if (threadIdx.x == 0) A.out_counts[bc] = kept;
+    small_epilogue(A);
 }
 
 __global__ void __launch_bounds__(kLargeThreads)
@@ -756,11 +787,6 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     A.thr = nms_thresh; A.top_k = top_k; A.max_out = max_out; A.flags = nms_flags; A.row_layout = row_layout;
     A.out_counts = out_counts; A.out_dets = out_dets; A.out_anchor = out_anchor;
 
-    if (ev) cudaEventRecord(ev[2], st);
-    nms_small_kernel<<<B * C, kSmallThreads, 0, st>>>(A);
-    note_launch();
-    RD_CHECK_LAUNCH();
-    if (ev) cudaEventRecord(ev[3], st);
     {
         const int mcap = top_k < P ? top_k : P;
         const NmsSmemLayout Ll = nms_layout(mcap);
@@ -781,12 +807,20 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
         int per_sm = (int)((220 * 1024) / (Ll.total + 1024));
         if (per_sm < 1) per_sm = 1;
         if (per_sm > 8) per_sm = 8;
-        int grid = s_dev_sms * per_sm;
-        if (grid > B * C) grid = B * C;
-        nms_large_kernel<<<grid, kLargeThreads, Ll.total, st>>>(A, mcap);
-        note_launch();
-        RD_CHECK_LAUNCH();
+        A.large_grid = s_dev_sms * per_sm;
+        A.large_mcap = mcap;
+        A.large_smem = (int)Ll.total;
     }
+    if (ev) cudaEventRecord(ev[2], st);
+    nms_small_kernel<<<B * C, kSmallThreads, 0, st>>>(A);      // tail-launches nms_large_kernel when needed
+    note_launch();
+    RD_CHECK_LAUNCH();
+#ifndef RD_USE_CDP
+    nms_large_kernel<<<A.large_grid < B * C ? A.large_grid : B * C, kLargeThreads, A.large_smem, st>>>(A, A.large_mcap);
+    note_launch();
+    RD_CHECK_LAUNCH();
+#endif
+    if (ev) cudaEventRecord(ev[3], st);
     if (ev) cudaEventRecord(ev[4], st);
     return 0;
 }

@@ -143,8 +143,8 @@ class Detect_RefineDet(object):
         """Device time (ms, mean over ``steps``) of each kernel of the fused stage, measured with
         CUDA events recorded between the launches (``rd_detect_fused_timed``)."""
         import ctypes
-        names = ('collect_kernel', 'graph_kernel', 'nms_small_kernel', 'nms_large_kernel')
-        acc = [0.0, 0.0, 0.0, 0.0]
+        names = ('collect_kernel', 'graph_kernel', 'nms_small_kernel')   # + tail-launched nms_large_kernel
+        acc = [0.0, 0.0, 0.0]
         ms = (ctypes.c_float * 4)()
         for i in range(steps):
             if flush is not None:
@@ -152,7 +152,7 @@ class Detect_RefineDet(object):
             a = input_sets[i % len(input_sets)]
             self._fused(a[0], a[1], a[2], a[3], prior_data, scale, _ffi.RD_NMS_PIXEL_PLUS1, _ffi.RD_ROW_BOX_SCORE,
                         self.keep_top_k, timed=ms)
-            for k in range(4):
+            for k in range(3):
                 acc[k] += float(ms[k])
         return {n: v / steps for n, v in zip(names, acc)}
 
