@@ -125,19 +125,53 @@ class Detect_RefineDet(object):
         return self._fused(arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale, flags,
                            _ffi.RD_ROW_BOX_SCORE, self.keep_top_k)
 
-    def detect_host(self, host_inputs, prior_data, scale=None, staging=None):
+    def detect_host(self, host_inputs, prior_data, scale=None, staging=None, zero_copy=True):
         """End-to-end form of :meth:`detect` for HOST inputs (pinned tensors
-        ``arm_loc, arm_conf, odm_loc, odm_conf``): asynchronous H2D copies into ``staging``
-        (device buffers, allocated when None), the fused stage, device-side packing, and D2H of
-        ``counts[B,C]`` and the packed rows ``[total,5]``.  Returns CPU tensors."""
+        ``arm_loc, arm_conf, odm_loc, odm_conf``).  Returns CPU tensors ``(counts[B,C], rows[total,5])``.
+
+        ``zero_copy=True`` (default): the kernels read the pinned host buffers directly over PCIe
+        (unified addressing) — ``arm_conf`` is streamed once and only the loc / odm_conf rows of
+        ARM-passing anchors ever cross the bus, instead of copying every tensor in full.
+        ``zero_copy=False``: asynchronous H2D copies into ``staging`` device buffers first.
+        Either way the stage, device-side packing and the D2H of counts + packed rows follow."""
         dev = prior_data.device
-        if staging is None:
-            staging = [torch.empty_like(t, device=dev) for t in host_inputs]
-        for d, h in zip(staging, host_inputs):
-            d.copy_(h, non_blocking=True)
-        res = self.detect(staging[0], staging[1], staging[2], staging[3], prior_data, scale=scale)
-        offsets, rows = res.packed()
-        return res.counts.cpu(), rows.cpu()
+        if zero_copy:
+            for t in host_inputs:
+                if t.is_cuda or not t.is_pinned() or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError('detect_host(zero_copy=True) needs contiguous pinned float32 host tensors')
+            res = self._fused(host_inputs[0], host_inputs[1], host_inputs[2], host_inputs[3], prior_data, scale,
+                              _ffi.RD_NMS_PIXEL_PLUS1, _ffi.RD_ROW_BOX_SCORE, self.keep_top_k, host_mapped=True)
+        else:
+            if staging is None:
+                staging = [torch.empty_like(t, device=dev) for t in host_inputs]
+            for d, h in zip(staging, host_inputs):
+                d.copy_(h, non_blocking=True)
+            res = self.detect(staging[0], staging[1], staging[2], staging[3], prior_data, scale=scale)
+        return self._to_host(res)
+
+    def _to_host(self, res):
+        """counts + packed rows of ``res`` as CPU tensors with ONE stream synchronisation: the pack kernels
+        write offsets and rows straight into persistent pinned host buffers (zero-copy stores over PCIe),
+        counts follow with an async copy.  The returned tensors are views of those buffers, valid until
+        the next call."""
+        B, C, max_out, _ = res.dets.shape
+        dev = res.dets.device
+        key = (B, C, max_out)
+        if getattr(self, '_host_key', None) != key:
+            self._host_offsets = torch.empty(B * C + 1, dtype=torch.int32).pin_memory()
+            self._host_rows = torch.empty(B * C * max_out, 5, dtype=torch.float32).pin_memory()
+            self._host_counts = torch.empty(B, C, dtype=torch.int32).pin_memory()
+            self._dev_offsets = torch.empty(B * C + 1, dtype=torch.int32, device=dev)
+            self._host_key = key
+        with torch.cuda.device(dev):
+            check(lib().rd_pack_detections(ptr(res.counts), ptr(res.dets), B, C, max_out, ptr(self._dev_offsets),
+                                           ptr(self._host_rows), self._host_rows.shape[0], stream_ptr()),
+                  'rd_pack_detections')
+            self._host_counts.copy_(res.counts, non_blocking=True)
+            self._host_offsets.copy_(self._dev_offsets, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        total = int(self._host_offsets[-1])
+        return self._host_counts, self._host_rows[:total]
 
     def profile_stage(self, input_sets, prior_data, scale, flush=None, steps=10):
         """Device time (ms, mean over ``steps``) of each kernel of the fused stage, measured with
@@ -157,10 +191,18 @@ class Detect_RefineDet(object):
         return {n: v / steps for n, v in zip(names, acc)}
 
     def _fused(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale, flags,
-               row_layout, max_out, dets=None, timed=None):
-        arm_loc, arm_conf, odm_loc, odm_conf, priors, B, P, C = self._inputs(
-            arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data)
-        dev = odm_loc.device
+               row_layout, max_out, dets=None, timed=None, host_mapped=False):
+        if host_mapped:      # pinned host tensors, dereferenced by the kernels through unified addressing
+            arm_loc, arm_conf, odm_loc, odm_conf = arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data
+            priors = require_cuda_f32(prior_data, 'prior_data')
+            B, P, C = odm_loc.shape[0], priors.shape[0], self.num_classes
+            if tuple(arm_loc.shape) != (B, P, 4) or arm_conf.numel() != B * P * 2 or odm_conf.numel() != B * P * C:
+                raise ValueError('host tensors must be [B,P,4], [B,P,2], [B,P,4], [B,P,C]')
+            dev = priors.device
+        else:
+            arm_loc, arm_conf, odm_loc, odm_conf, priors, B, P, C = self._inputs(
+                arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data)
+            dev = odm_loc.device
         if self.top_k > _ffi.RD_MAX_NMS_BOXES:
             raise RuntimeError('top_k = %d exceeds the supported %d' % (self.top_k, _ffi.RD_MAX_NMS_BOXES))
         max_out = max(1, min(int(max_out), int(self.top_k)))

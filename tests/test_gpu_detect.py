@@ -336,3 +336,19 @@ def test_full_size_properties(rd):
     for c in (1, 33, 80):
         n = int(counts[5, c])
         assert np.array_equal(res.anchors[5, c, :n].cpu().numpy(), anc[c])
+
+
+def test_detect_host_zero_copy_matches_staged(rd):
+    """e2e API: kernels reading the pinned host tensors directly give the same packed rows as the
+    staged H2D copy path."""
+    B, C = 3, 21
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS['320']).forward().cuda()
+    P = priors.shape[0]
+    host = [t.pin_memory() for t in gen.detect_inputs(31, B, P, C, 'sparse', arm_shift=-3.0)]
+    det = rd.Detect_RefineDet(C, 320, 0, 1000, 0.01, 0.45, 0.01, 500)
+    scale = torch.tensor([320.0] * 4)
+    c1, r1 = det.detect_host(host, priors, scale, zero_copy=False)
+    c2, r2 = det.detect_host(host, priors, scale, zero_copy=True)
+    assert torch.equal(c1, c2) and torch.equal(r1, r2) and int(c1.sum()) > 0
+    with pytest.raises(RuntimeError):
+        det.detect_host([t.clone() for t in host], priors, scale, zero_copy=True)     # not pinned
