@@ -27,6 +27,17 @@ namespace rd {
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
+#ifdef RD_PROFILE_PHASES
+__device__ long long g_dbg[64];
+#define RD_MARK(slot) do { if (blockIdx.x == 3 && blockIdx.y == 5 && threadIdx.x == 0) g_dbg[slot] = clock64(); } while (0)
+__device__ __forceinline__ unsigned long long rd_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define RD_TMAX(slot) do { if (threadIdx.x == 0) atomicMax((unsigned long long*)&g_dbg[slot], rd_gtime()); } while (0)
+#define RD_TMIN(slot) do { if (threadIdx.x == 0) atomicMin((unsigned long long*)&g_dbg[slot], rd_gtime()); } while (0)
+#else
+#define RD_MARK(slot) do {} while (0)
+#define RD_TMAX(slot) do {} while (0)
+#define RD_TMIN(slot) do {} while (0)
+#endif
 constexpr int kCollectThreads = 256;
 constexpr int kSliceAnchors = 1024;   // anchors per collect CTA = capacity of one candidate sub-list
 constexpr int kLargeThreads = 128;
@@ -195,6 +206,7 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int s = blockIdx.x, b = blockIdx.y;
+    RD_TMIN(25);
     if (s == 0 && b == 0 && threadIdx.x == 0) header[0] = 0;          // queue of the large-NMS kernel
     if (s == 0 && threadIdx.x == 0) GO.img_flag[b] = 0;
     for (int c = threadIdx.x; c < C; c += kCollectThreads) s_cnt[c] = 0;
@@ -302,12 +314,6 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
 // Images with more than kGraphNodes passing anchors, or a node of degree > kAdjDeg, are flagged and
 // handled by the per-problem bin path instead.
 // ---------------------------------------------------------------------------------------
-#ifdef RD_PROFILE_PHASES
-__device__ long long g_dbg[64];
-#define RD_MARK(slot) do { if (blockIdx.x == 3 && blockIdx.y == 5 && threadIdx.x == 0) g_dbg[slot] = clock64(); } while (0)
-#else
-#define RD_MARK(slot) do {} while (0)
-#endif
 constexpr int kGraphThreads = 256;
 constexpr int kGraphSplit = 16;         // CTAs per image
 constexpr int kGraphPairCap = 2048;
@@ -352,6 +358,8 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.x, b = blockIdx.y;
     RD_MARK(0);
+    RD_TMIN(24);
+    grid_launch_dependents();        // nms_small_kernel may start its (graph independent) sort phase now
     const int N = nnodes[b];
     if (N > kGraphNodes || img_flag[b] != 0) {
         if (g == 0 && tid == 0) img_flag[b] = 1;
@@ -411,28 +419,28 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
                 if (w == jw) h &= (1u << (j & 31)) - 1u;      // predecessors only
             }
         }
+        // reserve list slots: warp-aggregated shared-memory atomic (list order is irrelevant)
         const int c = __popc(h);
         int x = c;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, x, d); if (lane >= d) x += o; }
-        if (lane == 31) G.wsum[warp] = x;
-        __syncthreads();
-        int off = x - c, tot = 0;
-#pragma unroll
-        for (int ww = 0; ww < kGraphThreads / 32; ++ww) { if (ww < warp) off += G.wsum[ww]; tot += G.wsum[ww]; }
-        const int base = G.npairs;                      // uniform: updated below after a barrier
-        off += base;
-        const int j = g + jl * kGraphSplit;
+        const int wtot = __shfl_sync(kFullMask, x, 31);
+        int wbase = 0;
+        if (lane == 31 && wtot) wbase = atomicAdd(&G.npairs, wtot);
+        wbase = __shfl_sync(kFullMask, wbase, 31);
+        int off = wbase + x - c;
+        const uint32_t tag = (uint32_t)jl << 16;
         while (h) {
             const int i = (w << 5) + __ffs(h) - 1;
             h &= h - 1;
-            if (off < kGraphPairCap) G.pairs[off] = ((uint32_t)jl << 16) | (uint32_t)i;
-            else graph_test_pair(G, i, j, thr, flags, adjn, adj, img, &G.overflow);   // list full: test in place
+            if (off < kGraphPairCap) G.pairs[off] = tag | (uint32_t)i;
             ++off;
         }
-        __syncthreads();
-        if (tid == 0) G.npairs = base + tot;
-        __syncthreads();
+    }
+    __syncthreads();
+    if (G.npairs > kGraphPairCap) {          // rare: more pairs than the list holds -> leave the graph to the fallback
+        if (tid == 0) img_flag[b] = 1;
+        return;
     }
     RD_MARK(4);
     RD_MARK(5);
@@ -450,6 +458,7 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
     if (blockIdx.x == 3 && blockIdx.y == 5 && tid == 0) { g_dbg[10] = N; g_dbg[11] = G.npairs; g_dbg[12] = nown; }
 #endif
     if (tid == 0 && G.overflow) img_flag[b] = 1;
+    RD_TMAX(20);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -548,11 +557,13 @@ __device__ __forceinline__ void small_epilogue(const FusedNmsArgs& A) {
 __global__ void __launch_bounds__(kSmallThreads, 24)
 nms_small_kernel(FusedNmsArgs A) {
     __shared__ SmallSmem S;
+    RD_TMIN(21);
     const int bc = blockIdx.x;
     const int c = bc % A.C;
     if (c == 0) {                      // background is never evaluated (eval_refinedet_coco.py:213)
         // this CTA has no problem: it leaves the graph control block of its image zero for the next call
-        // (graph_kernel, the only reader, completed before this kernel started)
+        // (after graph_kernel, the only reader, has completed)
+        grid_dependency_wait();
         const int b0 = bc / A.C;
         uint32_t* gt = A.gtab + (size_t)b0 * kGtabWords;
         for (int i = threadIdx.x; i < kGtabWords; i += kSmallThreads) gt[i] = 0;
@@ -567,7 +578,7 @@ nms_small_kernel(FusedNmsArgs A) {
         return;
     }
     const int b = bc / A.C;
-    if (n > A.top_k || n > kSmallCap || A.img_flag[b] != 0) {     // needs the select / own bins: large kernel
+    if (n > A.top_k || n > kSmallCap) {                           // needs the top-k select: large kernel
         if (threadIdx.x == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
         small_epilogue(A);
         return;
@@ -578,8 +589,14 @@ nms_small_kernel(FusedNmsArgs A) {
     GraphView G;
     G.adj = reinterpret_cast<const uint4*>(A.adj + (size_t)b * A.P * kAdjDeg);
     G.adjn = A.adjn + (size_t)b * A.P;
+    G.img_flag = A.img_flag + b;
     const int kept = cta_nms_graph(S, pb, sink, G);
-    if (threadIdx.x == 0) A.out_counts[bc] = kept;
+    if (kept < 0) {                                               // the image has no graph: own bins, large kernel
+        if (threadIdx.x == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
+    } else if (threadIdx.x == 0) {
+        A.out_counts[bc] = kept;
+    }
+    RD_TMAX(23);
     small_epilogue(A);
 }
 
@@ -701,6 +718,9 @@ unsigned long long rd_launch_count(void) { return g_launches.load(std::memory_or
 __attribute__((visibility("default"))) int rd_debug_read(long long* out64) {
     return (int)cudaMemcpyFromSymbol(out64, g_dbg, sizeof(long long) * 64);
 }
+__attribute__((visibility("default"))) int rd_debug_write(const long long* in64) {
+    return (int)cudaMemcpyToSymbol(g_dbg, in64, sizeof(long long) * 64);
+}
 #endif
 
 int rd_detect_forward(const float* arm_loc, const float* arm_conf, const float* odm_loc, float* odm_conf,
@@ -812,7 +832,20 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
         A.large_smem = (int)Ll.total;
     }
     if (ev) cudaEventRecord(ev[2], st);
-    nms_small_kernel<<<B * C, kSmallThreads, 0, st>>>(A);      // tail-launches nms_large_kernel when needed
+    {   // programmatic dependent launch: the sort phase of nms_small overlaps graph_kernel
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(B * C);
+        cfg.blockDim = dim3(kSmallThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, nms_small_kernel, A);
+        if (e != cudaSuccess) return (int)e;
+    }
     note_launch();
     RD_CHECK_LAUNCH();
 #ifndef RD_USE_CDP

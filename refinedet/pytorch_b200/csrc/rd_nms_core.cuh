@@ -243,9 +243,15 @@ __device__ __forceinline__ void cta_sort_small(SmallSmem& S, const CandList& cl)
 // a higher key (shared-memory hash anchor -> rank) and resolves the dependencies; no boxes, bins or
 // IoUs per class.  7.1 KB of shared memory, <= 40 registers: 24 CTAs resident per SM.
 // =========================================================================================
+// programmatic dependent launch (sm_90+): wait until the preceding kernel of the stream has completed and
+// its memory is visible / allow the next kernel of the stream to start launching
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct GraphView {
     const uint4* adj;                 // [P][kAdjDeg] anchors of the image, as two uint4 per anchor
     const int* adjn;                  // [P] degree (<= kAdjDeg when the image is not flagged)
+    const int* img_flag;              // this image: 1 = no graph (checked after the dependency wait)
 };
 
 __device__ __forceinline__ uint32_t hash_anchor(uint32_t a) { return (a * 2654435761u) >> 23; }   // 9 bits
@@ -257,6 +263,10 @@ __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const Ro
     const int m = pb.cl.n;                                   // n <= min(top_k, kSmallCap): nothing is truncated
     cta_sort_small(S, pb.cl);                                // ends with a CTA barrier: `runs` is dead
     for (int i = tid; i < kHashSlots; i += kSmallThreads) S.u.g.hash[i] = 0xffffffffu;
+    // Everything above depends on collect_kernel only.  The kernel is launched with programmatic stream
+    // serialisation, so it overlaps graph_kernel up to here; the adjacency lists are read below.
+    grid_dependency_wait();
+    if (*G.img_flag != 0) return -1;                         // uniform: the caller queues the problem
     __syncthreads();
     // adjacency rows of my candidates (independent of the rank): issue the loads first
     constexpr int kPerT = kSmallCap / kSmallThreads;
