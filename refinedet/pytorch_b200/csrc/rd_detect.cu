@@ -554,7 +554,7 @@ __device__ __forceinline__ void small_epilogue(const FusedNmsArgs& A) {
     }
 }
 
-__global__ void __launch_bounds__(kSmallThreads, 24)
+__global__ void __launch_bounds__(kSmallThreads, 16)
 nms_small_kernel(FusedNmsArgs A) {
     __shared__ SmallSmem S;
     RD_TMIN(21);

@@ -161,7 +161,7 @@ __device__ __forceinline__ unsigned long long warp_sort32_desc(unsigned long lon
 // =========================================================================================
 // small problems: one CTA of kSmallThreads threads, n <= kSmallCap, no select
 // =========================================================================================
-constexpr int kSmallThreads = 64;
+constexpr int kSmallThreads = 96;
 constexpr int kSmallWarps = kSmallThreads / 32;
 constexpr int kSmallCap = 256;
 constexpr int kSmallW = kSmallCap / 32;      // 8 mask words
@@ -269,7 +269,7 @@ __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const Ro
     if (*G.img_flag != 0) return -1;                         // uniform: the caller queues the problem
     __syncthreads();
     // adjacency rows of my candidates (independent of the rank): issue the loads first
-    constexpr int kPerT = kSmallCap / kSmallThreads;
+    constexpr int kPerT = (kSmallCap + kSmallThreads - 1) / kSmallThreads;
     uint4 row0[kPerT], row1[kPerT];
     int dn[kPerT];
 #pragma unroll

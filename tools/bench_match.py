@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Secondary measurement (BASELINE.json config 4/5): training-side matching and
+hard-negative selection on one B200 — device time with CUDA events, L2 flushed between iterations,
+against the algorithmic bytes (refine_match 40*P + 20*G per image, HNM 6*P per image), next to the
+numpy oracle on the host.
+
+    python tools/bench_match.py [--G 50] [--classes 81] [--steps 30]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--G', type=int, default=50)
+    ap.add_argument('--classes', type=int, default=81)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--batch', type=int, default=32)
+    args = ap.parse_args()
+    import refinedet.pytorch_b200 as rd
+    from refinedet.pytorch_b200 import synthetic
+    from oracle import box_oracle as bo
+    B, C, G, P = args.batch, args.classes, args.G, 16320
+    dev = torch.device('cuda', 0)
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS['512']).forward().to(dev)
+    small = C == 2
+    tg = synthetic.targets(5234, B, G, C, 0.01 if small else 0.02, 0.06 if small else 0.17)
+    arm_loc, arm_conf, odm_loc, odm_conf = [t.to(dev) for t in synthetic.train_predictions(5235, B, P, C)]
+    bu = rd.box_utils
+    truths, labels, cnt = bu.pad_targets([t.to(dev) for t in tg], dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'] if os.path.exists(
+        os.path.join(ROOT, 'MEASURED_PEAKS.json')) else 6650.0
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ms = []
+        for _ in range(args.steps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record(); torch.cuda.synchronize()
+            ms.append(s.elapsed_time(e))
+        return float(np.median(ms))
+
+    out = {'config': {'B': B, 'P': P, 'C': C, 'G': G}}
+    ms = timed(lambda: bu.match_batch(0.5, truths, labels, cnt, priors, [0.1, 0.2], arm_loc, bu.LABEL_ODM))
+    byts = B * (40 * P + 20 * G)
+    out['refine_match_odm'] = {'ms': ms, 'images_per_s': B / ms * 1e3, 'algorithmic_GBs': byts / ms / 1e6,
+                               'frac_of_hbm_peak': byts / ms / 1e6 / peak}
+    loss = torch.rand(B, P, device=dev) * 8
+    pos = torch.rand(B, P, device=dev) < 0.015
+    ms = timed(lambda: bu.hnm_select(loss, pos, 3))
+    byts = B * 6 * P
+    out['hnm_select'] = {'ms': ms, 'images_per_s': B / ms * 1e3, 'algorithmic_GBs': byts / ms / 1e6,
+                         'frac_of_hbm_peak': byts / ms / 1e6 / peak}
+    crit = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True)
+    preds = (arm_loc, arm_conf, odm_loc, odm_conf, priors)
+    tgd = [t.to(dev) for t in tg]
+    ms = timed(lambda: crit(preds, tgd))
+    out['odm_criterion_forward'] = {'ms': ms, 'images_per_s': B / ms * 1e3}
+    # CPU oracle, one image, one core
+    t0 = time.perf_counter()
+    n_img = 2
+    for i in range(n_img):
+        bo.refine_match(0.5, tg[i][:, :4].numpy(), priors.cpu().numpy(), [0.1, 0.2], tg[i][:, 4].numpy(),
+                        arm_loc[i].cpu().numpy())
+    out['cpu_oracle_refine_match'] = {'images_per_s_per_core': n_img / (time.perf_counter() - t0)}
+    print(json.dumps(out))
+
+
+if __name__ == '__main__':
+    main()
