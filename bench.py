@@ -275,8 +275,17 @@ def main():
     peak, peak_src = measured_peak()
     achieved = bytes_per_launch / (stage_ms * 1e-3) / 1e9
     dominant = max(kern, key=kern.get)
+    traffic, traffic_src = None, None
+    try:                                   # DRAM bytes per launch from the committed ncu --set full capture
+        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+            tj = json.load(f)
+        traffic = tj['kernels'][dominant]['traffic_bytes']
+        traffic_src = {'file': 'profiles/r01_traffic.json', 'stage_traffic_bytes': tj['stage_traffic_bytes'],
+                       'per_kernel': {k: v['traffic_bytes'] for k, v in tj['kernels'].items()}}
+    except Exception:
+        pass
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                'traffic': None, 'peak_source': peak_src, 'kernel': dominant,
+                'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'kernel': dominant,
                 'algorithmic_bytes_per_launch': bytes_per_launch,
                 'stage_ms': stage_ms,
                 'kernels_ms': kern, 'kernel_share': {k: v / stage_ms for k, v in kern.items()},
