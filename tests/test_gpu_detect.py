@@ -352,3 +352,74 @@ def test_detect_host_zero_copy_matches_staged(rd):
     assert torch.equal(c1, c2) and torch.equal(r1, r2) and int(c1.sum()) > 0
     with pytest.raises(RuntimeError):
         det.detect_host([t.clone() for t in host], priors, scale, zero_copy=True)     # not pinned
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: ragged / tiny / empty inputs, extreme parameters
+# ---------------------------------------------------------------------------------------------
+def _run_vs_oracle(rd, B, P, C, top_k, keep, kind='dense', seed=5, conf_thr=0.01, nms_thr=0.45, obj_thr=0.01,
+                   arm_shift=-3.0, size=320):
+    g = torch.Generator().manual_seed(seed)
+    cxy = torch.rand(P, 2, generator=g)
+    wh = 0.03 + 0.3 * torch.rand(P, 2, generator=g)
+    priors = torch.cat([cxy, wh], 1).clamp(0, 1)
+    arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs(seed, B, P, C, kind, arm_shift=arm_shift)
+    det = rd.Detect_RefineDet(C, size, 0, top_k, conf_thr, nms_thr, obj_thr, keep)
+    scale = np.array([float(size)] * 4, np.float32)
+    d_in = [t.cuda() for t in (arm_loc, arm_conf, odm_loc, odm_conf)]
+    res = det.detect(*d_in, priors.cuda(), scale=scale)
+    g_boxes, g_scores = det.forward(d_in[0], d_in[1], d_in[2], odm_conf.clone().cuda(), priors.cuda())
+    gb, gs = g_boxes.cpu().numpy(), g_scores.cpu().numpy()
+    counts = res.counts.cpu().numpy()
+    anchors = res.anchors.cpu().numpy()
+    dets = res.dets.cpu().numpy()
+    for b in range(B):
+        out, anc = bo.detect_stage_eval(gb[b], gs[b], scale, conf_thr, top_k, nms_thr, keep)
+        for c in range(C):
+            assert counts[b, c] == out[c].shape[0], (b, c, counts[b, c], out[c].shape[0])
+            assert np.array_equal(anchors[b, c, :counts[b, c]], anc[c]), (b, c)
+            assert np.array_equal(dets[b, c, :counts[b, c]], out[c]), (b, c)
+    return counts
+
+
+@pytest.mark.parametrize('B,P,C,top_k,keep', [
+    (1, 1, 2, 10, 10),          # a single anchor
+    (1, 33, 3, 1000, 500),      # one warp + one lane
+    (2, 100, 5, 5, 5),          # top_k < candidates: radix-select path on a graph image
+    (3, 1025, 4, 200, 1),       # slice boundary (1024 + 1), keep_top_k = 1
+    (2, 2500, 2, 300, 300),     # 2-class (SAR config), >256 candidates per problem, 3 slices
+    (1, 700, 128, 50, 20),      # the class limit (C = 128)
+])
+def test_edge_shapes_vs_oracle(rd, B, P, C, top_k, keep):
+    counts = _run_vs_oracle(rd, B, P, C, top_k, keep)
+    assert counts[:, 0].sum() == 0
+
+
+def test_no_candidates_and_all_candidates(rd):
+    # every anchor ARM-filtered: all counts zero, nothing else touched
+    counts = _run_vs_oracle(rd, 2, 500, 4, 100, 50, obj_thr=2.0)
+    assert counts.sum() == 0
+    # conf threshold above every score
+    counts = _run_vs_oracle(rd, 2, 500, 4, 100, 50, conf_thr=1.5)
+    assert counts.sum() == 0
+    # negative thresholds: every (anchor, class>=1) is a candidate
+    counts = _run_vs_oracle(rd, 1, 300, 3, 1000, 500, conf_thr=-1.0, obj_thr=-1.0)
+    assert counts[:, 1:].sum() > 0
+
+
+def test_graph_fallback_paths_agree(rd):
+    """An image with more ARM-passing anchors than the graph holds (1024) falls back to per-problem
+    bins; both paths must give the oracle's result (here: same generator, pass rate high vs low)."""
+    _run_vs_oracle(rd, 2, 3000, 3, 150, 100, kind='dense')                      # ~2600 passing: flagged
+    _run_vs_oracle(rd, 2, 3000, 3, 150, 100, kind='sparse', arm_shift=-2.0)     # few hundred passing: graph
+
+
+def test_limits_raise(rd):
+    det = rd.Detect_RefineDet(200, 320, 0, 10, 0.01, 0.45, 0.01, 5)
+    P = 64
+    z = lambda *s: torch.zeros(*s).cuda()
+    with pytest.raises(RuntimeError):
+        det.detect(z(1, P, 4), z(1, P, 2), z(1, P, 4), z(1, P, 200), z(P, 4))    # C > 128
+    det = rd.Detect_RefineDet(3, 320, 0, 5000, 0.01, 0.45, 0.01, 5)
+    with pytest.raises(RuntimeError):
+        det.detect(z(1, P, 4), z(1, P, 2), z(1, P, 4), z(1, P, 3), z(P, 4))      # top_k > 4096
