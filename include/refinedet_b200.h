@@ -120,8 +120,9 @@ RD_API int rd_detect_fused(const float* arm_loc, const float* arm_conf, const fl
 
 /* Diagnostics twin of rd_detect_fused: records CUDA events between the stage's kernels on
  * `stream`, WAITS for the stage, and writes the device time in ms of
- * {collect_kernel, graph_kernel, nms_small_kernel incl. the nms_large_kernel it tail-launches,
- * 0} to stage_ms_host[4] (host pointer). */
+ * {collect_kernel, graph_kernel, sort_kernel + resolve_kernel + nms_large_kernel, 0} to
+ * stage_ms_host[4] (host pointer).  The events serialise graph_kernel and sort_kernel, which overlap
+ * in rd_detect_fused. */
 RD_API int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, const float* odm_loc,
                     const float* odm_conf, const float* priors, int B, int P, int C,
                     float objectness_thre, float conf_thresh, float nms_thresh,

@@ -16,7 +16,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'librefinedet_b200.so')
+LIB_PATH = os.environ.get('RD_LIB_PATH') or os.path.join(_HERE, 'lib', 'librefinedet_b200.so')
 HEADER_PATH = os.path.join(os.path.dirname(os.path.dirname(_HERE)), 'include', 'refinedet_b200.h')
 
 c_int, c_float, c_void_p, c_size_t = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t

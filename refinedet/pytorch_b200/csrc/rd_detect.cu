@@ -12,9 +12,9 @@
 //                           ARM-filtered anchors are never fetched: traffic scales with the pass rate.
 //   graph_kernel            KG: one CTA per (image, slice): exact suppression graph between the ARM-passing
 //                           anchors of an image (class independent), adjacency lists per anchor
-//   nms_small_kernel        K2+K3: one 64-thread CTA per (image, class) with <= 256 candidates: sort +
-//                           graph look-ups (or its own bins when the image's graph is unavailable),
-//                           12.7 KB shared memory -> 16 CTAs resident per SM; other problems are queued
+//   sort_kernel             K2a: one 96-thread CTA per (image, class) with <= 256 candidates: key sort;
+//                           runs beside graph_kernel (programmatic dependent launch)
+//   resolve_kernel          K2b+K3: graph look-ups through a smem hash, dependency resolution, rows
 //   nms_large_kernel        persistent CTAs draining the queue (radix select when n > top_k)
 //   nms_single_kernel       stand-alone problem (rd_nms / rd_nms_host)
 //   pack kernels            slot layout -> packed rows
@@ -52,6 +52,7 @@ constexpr int kLargeThreads = 128;
 //   flag   int [B]                : 1 = the image has no suppression graph (too many nodes / degree overflow)
 //   queue  int [B*C]              : (image,class) problems routed to nms_large_kernel
 //   cnt    int [B*C*S]            : candidate count of every sub-list, S = ceil(P / 1024)
+//   sn     int [B*C], skeys u64 [B*C][256] : size and sorted keys of every small problem (sort_kernel)
 //   nbox   f4  [B][1024], nanc int [B][1024], ncr u32 [B][1024] : node box / anchor / bin range
 //   adjn   int [B*P]              : graph degree of every passing anchor (collect zeroes, graph counts)
 //   adj    u32 [B*P*8]            : adjacency lists (anchor indices)
@@ -70,6 +71,8 @@ struct DetectWs {
     int* flag;
     int* queue;
     int* cnt;
+    int* sn;
+    unsigned long long* skeys;
     float4* nbox;
     int* nanc;
     uint32_t* ncr;
@@ -94,6 +97,8 @@ static DetectWs carve_ws(void* base, int B, int P, int C) {
     w.flag = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * 4, 256);
     w.queue = reinterpret_cast<int*>(p + o);                   o += align_up((size_t)B * C * 4, 256);
     w.cnt = reinterpret_cast<int*>(p + o);                     o += align_up((size_t)B * C * w.S * 4, 256);
+    w.sn = reinterpret_cast<int*>(p + o);                      o += align_up((size_t)B * C * 4, 256);
+    w.skeys = reinterpret_cast<unsigned long long*>(p + o);    o += align_up((size_t)B * C * kSmallCap * 8, 256);
     w.nbox = reinterpret_cast<float4*>(p + o);                 o += align_up((size_t)B * kGraphNodes * 16, 256);
     w.nanc = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * kGraphNodes * 4, 256);
     w.ncr = reinterpret_cast<uint32_t*>(p + o);                o += align_up((size_t)B * kGraphNodes * 4, 256);
@@ -357,9 +362,10 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
     GraphSmem& G = *reinterpret_cast<GraphSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.x, b = blockIdx.y;
+    grid_dependency_wait();          // collect_kernel has completed (this kernel is launched early)
     RD_MARK(0);
     RD_TMIN(24);
-    grid_launch_dependents();        // nms_small_kernel may start its (graph independent) sort phase now
+    grid_launch_dependents();        // sort_kernel (graph independent) may run beside this kernel
     const int N = nnodes[b];
     if (N > kGraphNodes || img_flag[b] != 0) {
         if (g == 0 && tid == 0) img_flag[b] = 1;
@@ -471,13 +477,15 @@ struct FusedNmsArgs {
     const float* img_scale;          // [B,4] or null
     int* queue;
     uint32_t* header;
+    unsigned long long* skeys;       // [B*C][256] sorted keys of the small problems
+    int* sn;                         // [B*C] n of a sorted problem, 0 = empty, -1 = queued
     int* nnodes;                     // [B]   } control block, cleared by the class-0 CTA of every image
     uint32_t* gtab;                  // [B][kGtabWords]
     const int* img_flag;             // [B] 1 = no graph for this image
     const uint32_t* adj;             // [B*P*kAdjDeg]
     const int* adjn;                 // [B*P]
     int nbc, C, P, S;
-    int large_grid, large_mcap, large_smem;   // launch shape of nms_large_kernel (tail-launched on demand)
+    int large_grid, large_mcap, large_smem;   // launch shape of nms_large_kernel
     float thr;
     int top_k, max_out, flags, row_layout;
     int* out_counts;
@@ -528,76 +536,70 @@ __device__ __forceinline__ void fill_problem(NmsProblem& pb, RowSink& sink, int 
     sink.row_layout = A.row_layout;
 }
 
-__global__ void nms_large_kernel(FusedNmsArgs A, int mcap);
-
-// Last CTA of nms_small_kernel: if any problem was queued, tail-launch nms_large_kernel from the device
-// (CUDA dynamic parallelism) so the common case -- nothing queued -- costs no launch at all.
-__device__ __forceinline__ void small_epilogue(const FusedNmsArgs& A) {
-#ifndef RD_USE_CDP
-    return;
-#endif
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const uint32_t t = atomicAdd(&A.header[1], 1u);
-        if (t == gridDim.x - 1) {
-            A.header[1] = 0;
-            __threadfence();
-            const uint32_t nq = *((volatile uint32_t*)&A.header[0]);
-#ifdef RD_USE_CDP
-            if (nq > 0) {
-                const uint32_t grid = nq < (uint32_t)A.large_grid ? nq : (uint32_t)A.large_grid;
-                nms_large_kernel<<<grid, kLargeThreads, A.large_smem, cudaStreamTailLaunch>>>(A, A.large_mcap);
-            }
-#endif
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kSmallThreads, 16)
-nms_small_kernel(FusedNmsArgs A) {
+// K2a: sort.  One CTA per (image, class): gather the candidate sub-lists, sort the keys (runs of 32 in
+// registers, merged by rank) and store them.  Depends on collect_kernel only; launched with
+// programmatic stream serialisation behind graph_kernel (which triggers at its start), so the two run
+// side by side.  Problems that need the top-k select are queued for nms_large_kernel.
+__global__ void __launch_bounds__(kSortThreads, 1536 / kSortThreads)
+sort_kernel(FusedNmsArgs A) {
     __shared__ SmallSmem S;
     RD_TMIN(21);
     const int bc = blockIdx.x;
     const int c = bc % A.C;
-    if (c == 0) {                      // background is never evaluated (eval_refinedet_coco.py:213)
-        // this CTA has no problem: it leaves the graph control block of its image zero for the next call
-        // (after graph_kernel, the only reader, has completed)
-        grid_dependency_wait();
-        const int b0 = bc / A.C;
-        uint32_t* gt = A.gtab + (size_t)b0 * kGtabWords;
-        for (int i = threadIdx.x; i < kGtabWords; i += kSmallThreads) gt[i] = 0;
-        if (threadIdx.x == 0) { A.nnodes[b0] = 0; A.out_counts[bc] = 0; }
-        small_epilogue(A);
-        return;
-    }
+    if (c == 0) return;                // background is never evaluated (eval_refinedet_coco.py:213)
     const int n = load_slice_counts(A.cnt + (size_t)bc * A.S, A.S, S.cnt, S.offs);
     if (n == 0) {
-        if (threadIdx.x == 0) A.out_counts[bc] = 0;
-        small_epilogue(A);
+        if (threadIdx.x == 0) A.sn[bc] = 0;
         return;
     }
-    const int b = bc / A.C;
     if (n > A.top_k || n > kSmallCap) {                           // needs the top-k select: large kernel
-        if (threadIdx.x == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
-        small_epilogue(A);
+        if (threadIdx.x == 0) { A.sn[bc] = -1; A.queue[atomicAdd(&A.header[0], 1u)] = bc; }
         return;
     }
+    CandList cl;
+    cl.base = A.cand + (size_t)bc * A.S * kSliceAnchors;
+    cl.S = A.S; cl.stride = kSliceAnchors; cl.cnt = S.cnt; cl.offs = S.offs; cl.n = n;
+    cta_sort_small<kSortThreads>(S, cl);
+    unsigned long long* out = A.skeys + (size_t)bc * kSmallCap;
+    for (int i = threadIdx.x; i < n; i += kSortThreads) out[i] = S.keys[i];
+    if (threadIdx.x == 0) A.sn[bc] = n;
+    RD_TMAX(22);
+}
+
+// K2b + K3: resolve.  Normal launch: starts when graph_kernel AND sort_kernel have completed.
+__global__ void __launch_bounds__(kResolveThreads, 1536 / kResolveThreads)
+resolve_kernel(FusedNmsArgs A) {
+    __shared__ SmallSmem S;
+    const int bc = blockIdx.x;
+    const int c = bc % A.C;
+    const int b = bc / A.C;
+    if (c == 0) {
+        // this CTA has no problem: it leaves the graph control block of its image zero for the next call
+        uint32_t* gt = A.gtab + (size_t)b * kGtabWords;
+        for (int i = threadIdx.x; i < kGtabWords; i += kResolveThreads) gt[i] = 0;
+        if (threadIdx.x == 0) { A.nnodes[b] = 0; A.out_counts[bc] = 0; }
+        return;
+    }
+    const int n = A.sn[bc];
+    if (n <= 0) {                                                 // empty, or already queued by sort_kernel
+        if (n == 0 && threadIdx.x == 0) A.out_counts[bc] = 0;
+        return;
+    }
+    if (A.img_flag[b] != 0) {                                     // the image has no graph: own bins, large kernel
+        if (threadIdx.x == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
+        return;
+    }
+    const unsigned long long* in = A.skeys + (size_t)bc * kSmallCap;
+    for (int i = threadIdx.x; i < n; i += kResolveThreads) S.keys[i] = in[i];
     NmsProblem pb;
     RowSink sink;
     fill_problem(pb, sink, bc, n, S.cnt, S.offs, A);
     GraphView G;
     G.adj = reinterpret_cast<const uint4*>(A.adj + (size_t)b * A.P * kAdjDeg);
     G.adjn = A.adjn + (size_t)b * A.P;
-    G.img_flag = A.img_flag + b;
-    const int kept = cta_nms_graph(S, pb, sink, G);
-    if (kept < 0) {                                               // the image has no graph: own bins, large kernel
-        if (threadIdx.x == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
-    } else if (threadIdx.x == 0) {
-        A.out_counts[bc] = kept;
-    }
+    const int kept = cta_nms_graph<kResolveThreads>(S, pb, sink, G);
+    if (threadIdx.x == 0) A.out_counts[bc] = kept;
     RD_TMAX(23);
-    small_epilogue(A);
 }
 
 __global__ void __launch_bounds__(kLargeThreads)
@@ -606,6 +608,7 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
     const NmsSmemLayout L = nms_layout(mcap);
     int* s_cnt = reinterpret_cast<int*>(smem + L.off_cnt);
     int* s_offs = reinterpret_cast<int*>(smem + L.off_offs);
+    grid_dependency_wait();          // resolve_kernel (and everything before it) has completed
     const uint32_t nq = A.header[0];
     for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
         const int bc = A.queue[q];
@@ -757,6 +760,23 @@ int rd_detect_workspace_reset(void* workspace, size_t workspace_bytes, void* str
 
 }  // extern "C"
 
+// launch with programmatic stream serialisation: the kernel may begin launching while its predecessor in
+// the stream drains; kernels launched this way call grid_dependency_wait() before touching its results
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
                              const float* priors, int B, int P, int C, float objectness_thre, float conf_thresh,
                              float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
@@ -793,15 +813,18 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
             if (e != cudaSuccess) return (int)e;
             s_graph_attr = true;
         }
-        graph_kernel<<<dim3(kGraphSplit, B), kGraphThreads, sizeof(GraphSmem), st>>>(
-            ws.nnodes, ws.gtab, ws.nbox, ws.nanc, ws.ncr, P, nms_thresh, nms_flags, ws.adj, ws.adjn, ws.flag);
+        cudaError_t e = launch_pdl(graph_kernel, dim3(kGraphSplit, B), dim3(kGraphThreads), sizeof(GraphSmem), st,
+                                   (const int*)ws.nnodes, (const uint32_t*)ws.gtab, (const float4*)ws.nbox,
+                                   (const int*)ws.nanc, (const uint32_t*)ws.ncr, P, nms_thresh, nms_flags, ws.adj,
+                                   ws.adjn, ws.flag);
+        if (e != cudaSuccess) return (int)e;
         note_launch();
         RD_CHECK_LAUNCH();
     }
 
     FusedNmsArgs A;
     A.cnt = ws.cnt; A.cand = ws.cand; A.boxes = ws.boxes; A.img_scale = img_scale;
-    A.queue = ws.queue; A.header = ws.header;
+    A.queue = ws.queue; A.header = ws.header; A.skeys = ws.skeys; A.sn = ws.sn;
     A.img_flag = ws.flag; A.adj = ws.adj; A.adjn = ws.adjn; A.nnodes = ws.nnodes; A.gtab = ws.gtab;
     A.nbc = B * C; A.C = C; A.P = P; A.S = ws.S;
     A.thr = nms_thresh; A.top_k = top_k; A.max_out = max_out; A.flags = nms_flags; A.row_layout = row_layout;
@@ -832,27 +855,22 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
         A.large_smem = (int)Ll.total;
     }
     if (ev) cudaEventRecord(ev[2], st);
-    {   // programmatic dependent launch: the sort phase of nms_small overlaps graph_kernel
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(B * C);
-        cfg.blockDim = dim3(kSmallThreads);
-        cfg.dynamicSmemBytes = 0;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, nms_small_kernel, A);
+    {   // programmatic dependent launch: sort_kernel runs beside graph_kernel
+        cudaError_t e = launch_pdl(sort_kernel, dim3(B * C), dim3(kSortThreads), 0, st, A);
         if (e != cudaSuccess) return (int)e;
     }
     note_launch();
     RD_CHECK_LAUNCH();
-#ifndef RD_USE_CDP
-    nms_large_kernel<<<A.large_grid < B * C ? A.large_grid : B * C, kLargeThreads, A.large_smem, st>>>(A, A.large_mcap);
+    resolve_kernel<<<B * C, kResolveThreads, 0, st>>>(A);
     note_launch();
     RD_CHECK_LAUNCH();
-#endif
+    {
+        cudaError_t e = launch_pdl(nms_large_kernel, dim3(A.large_grid < B * C ? A.large_grid : B * C),
+                                   dim3(kLargeThreads), (size_t)A.large_smem, st, A, A.large_mcap);
+        if (e != cudaSuccess) return (int)e;
+    }
+    note_launch();
+    RD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[3], st);
     if (ev) cudaEventRecord(ev[4], st);
     return 0;

@@ -161,8 +161,14 @@ __device__ __forceinline__ unsigned long long warp_sort32_desc(unsigned long lon
 // =========================================================================================
 // small problems: one CTA of kSmallThreads threads, n <= kSmallCap, no select
 // =========================================================================================
-constexpr int kSmallThreads = 96;
-constexpr int kSmallWarps = kSmallThreads / 32;
+#ifndef RD_SORT_THREADS
+#define RD_SORT_THREADS 96
+#endif
+#ifndef RD_RESOLVE_THREADS
+#define RD_RESOLVE_THREADS 128
+#endif
+constexpr int kSortThreads = RD_SORT_THREADS;         // sort_kernel: the warps share the <= 8 runs of a problem
+constexpr int kResolveThreads = RD_RESOLVE_THREADS;   // resolve_kernel
 constexpr int kSmallCap = 256;
 constexpr int kSmallW = kSmallCap / 32;      // 8 mask words
 
@@ -182,7 +188,7 @@ struct SmallSmem {
     unsigned char state[kSmallCap];               // 0 undecided, 1 kept, 2 suppressed
     int cnt[kMaxSlices];
     int offs[kMaxSlices + 1];
-    int wsum[kSmallWarps];
+    int wsum[4];
 };
 
 // key of flattened element e of a sliced candidate list
@@ -201,7 +207,9 @@ __device__ __forceinline__ unsigned long long cand_at(const CandList& cl, int e)
 
 // Phases A+B of a small problem: sorted runs of 32 in registers (one run per warp at a time), merged
 // by rank.  On return (after a CTA barrier) S.keys[0..m) holds the keys in descending order.
+template <int kThreads>
 __device__ __forceinline__ void cta_sort_small(SmallSmem& S, const CandList& cl) {
+    constexpr int kSmallWarps = kThreads / 32;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -251,22 +259,19 @@ __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddep
 struct GraphView {
     const uint4* adj;                 // [P][kAdjDeg] anchors of the image, as two uint4 per anchor
     const int* adjn;                  // [P] degree (<= kAdjDeg when the image is not flagged)
-    const int* img_flag;              // this image: 1 = no graph (checked after the dependency wait)
 };
 
 __device__ __forceinline__ uint32_t hash_anchor(uint32_t a) { return (a * 2654435761u) >> 23; }   // 9 bits
 
+template <int kSmallThreads>
 __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const RowSink& sink, const GraphView& G) {
+    constexpr int kSmallWarps = kSmallThreads / 32;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int m = pb.cl.n;                                   // n <= min(top_k, kSmallCap): nothing is truncated
-    cta_sort_small(S, pb.cl);                                // ends with a CTA barrier: `runs` is dead
+    // S.keys[0..m) already holds the keys in descending order (sort_kernel), loaded by the caller
     for (int i = tid; i < kHashSlots; i += kSmallThreads) S.u.g.hash[i] = 0xffffffffu;
-    // Everything above depends on collect_kernel only.  The kernel is launched with programmatic stream
-    // serialisation, so it overlaps graph_kernel up to here; the adjacency lists are read below.
-    grid_dependency_wait();
-    if (*G.img_flag != 0) return -1;                         // uniform: the caller queues the problem
     __syncthreads();
     // adjacency rows of my candidates (independent of the rank): issue the loads first
     constexpr int kPerT = (kSmallCap + kSmallThreads - 1) / kSmallThreads;

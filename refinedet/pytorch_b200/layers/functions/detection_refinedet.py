@@ -177,7 +177,7 @@ class Detect_RefineDet(object):
         """Device time (ms, mean over ``steps``) of each kernel of the fused stage, measured with
         CUDA events recorded between the launches (``rd_detect_fused_timed``)."""
         import ctypes
-        names = ('collect_kernel', 'graph_kernel', 'nms_small_kernel')   # + tail-launched nms_large_kernel
+        names = ('collect_kernel', 'graph_kernel', 'sort_resolve_large_kernels')
         acc = [0.0, 0.0, 0.0]
         ms = (ctypes.c_float * 4)()
         for i in range(steps):
