@@ -581,23 +581,22 @@ resolve_kernel(FusedNmsArgs A) {
         return;
     }
     const int n = A.sn[bc];
+    const int noflag = A.img_flag[b] == 0;
     if (n <= 0) {                                                 // empty, or already queued by sort_kernel
         if (n == 0 && threadIdx.x == 0) A.out_counts[bc] = 0;
         return;
     }
-    if (A.img_flag[b] != 0) {                                     // the image has no graph: own bins, large kernel
+    if (!noflag) {                                                // the image has no graph: own bins, large kernel
         if (threadIdx.x == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
         return;
     }
-    const unsigned long long* in = A.skeys + (size_t)bc * kSmallCap;
-    for (int i = threadIdx.x; i < n; i += kResolveThreads) S.keys[i] = in[i];
     NmsProblem pb;
     RowSink sink;
     fill_problem(pb, sink, bc, n, S.cnt, S.offs, A);
     GraphView G;
     G.adj = reinterpret_cast<const uint4*>(A.adj + (size_t)b * A.P * kAdjDeg);
     G.adjn = A.adjn + (size_t)b * A.P;
-    const int kept = cta_nms_graph<kResolveThreads>(S, pb, sink, G);
+    const int kept = cta_nms_graph<kResolveThreads>(S, pb, sink, G, A.skeys + (size_t)bc * kSmallCap);
     if (threadIdx.x == 0) A.out_counts[bc] = kept;
     RD_TMAX(23);
 }

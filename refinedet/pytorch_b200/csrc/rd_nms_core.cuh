@@ -188,7 +188,7 @@ struct SmallSmem {
     unsigned char state[kSmallCap];               // 0 undecided, 1 kept, 2 suppressed
     int cnt[kMaxSlices];
     int offs[kMaxSlices + 1];
-    int wsum[4];
+    int wsum[8];
 };
 
 // key of flattened element e of a sliced candidate list
@@ -263,29 +263,39 @@ struct GraphView {
 
 __device__ __forceinline__ uint32_t hash_anchor(uint32_t a) { return (a * 2654435761u) >> 23; }   // 9 bits
 
+// `skeys` = the problem's sorted keys in global memory (sort_kernel), n of them.  Two dependent rounds of
+// global loads in total: (keys) -> (adjacency rows + boxes of every candidate).
 template <int kSmallThreads>
-__device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const RowSink& sink, const GraphView& G) {
+__device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const RowSink& sink, const GraphView& G,
+                                    const unsigned long long* __restrict__ skeys) {
     constexpr int kSmallWarps = kSmallThreads / 32;
+    constexpr int kPerT = (kSmallCap + kSmallThreads - 1) / kSmallThreads;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int m = pb.cl.n;                                   // n <= min(top_k, kSmallCap): nothing is truncated
-    // S.keys[0..m) already holds the keys in descending order (sort_kernel), loaded by the caller
+    // candidate r = q * kSmallThreads + tid (striped); everything about it stays in registers
+    unsigned long long key[kPerT];
+#pragma unroll
+    for (int q = 0; q < kPerT; ++q) {
+        const int r = q * kSmallThreads + tid;
+        key[q] = r < m ? skeys[r] : 0ull;
+    }
     for (int i = tid; i < kHashSlots; i += kSmallThreads) S.u.g.hash[i] = 0xffffffffu;
     __syncthreads();
-    // adjacency rows of my candidates (independent of the rank): issue the loads first
-    constexpr int kPerT = (kSmallCap + kSmallThreads - 1) / kSmallThreads;
     uint4 row0[kPerT], row1[kPerT];
+    float4 box[kPerT];
     int dn[kPerT];
 #pragma unroll
     for (int q = 0; q < kPerT; ++q) {
         const int r = q * kSmallThreads + tid;
         dn[q] = 0;
         if (r < m) {
-            const uint32_t a = key_index(S.keys[r]);
+            const uint32_t a = key_index(key[q]);
             dn[q] = G.adjn[a];
             row0[q] = __ldg(G.adj + (size_t)a * 2);
             row1[q] = __ldg(G.adj + (size_t)a * 2 + 1);
+            box[q] = pb.boxes[a];                            // most candidates are kept: fetch the row data now
             uint32_t h = hash_anchor(a);                     // insert (anchor -> rank)
             const uint32_t val = (a << 8) | (uint32_t)r;
             while (atomicCAS(&S.u.g.hash[h], 0xffffffffu, val) != 0xffffffffu) h = (h + 1) & (kHashSlots - 1);
@@ -325,8 +335,10 @@ __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const Ro
     // ---- resolve in rounds (dependencies always point to earlier ranks: terminates) ---------------
     for (int round = 0; round < kSmallCap; ++round) {
         int undecided = 0;
-        for (int r = tid; r < m; r += kSmallThreads) {
-            if (S.state[r] != 0) continue;
+#pragma unroll
+        for (int q = 0; q < kPerT; ++q) {
+            const int r = q * kSmallThreads + tid;
+            if (r >= m || S.state[r] != 0) continue;
             const int nd = S.depn[r];
             bool any_kept = false, all_sup = true;
             for (int k = 0; k < nd; ++k) {
@@ -340,39 +352,31 @@ __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const Ro
         }
         if (!__syncthreads_or(undecided)) break;
     }
-    // ---- emit kept rows in rank order, first max_out ----------------------------------------------
-    int local = 0;
+    // ---- emit kept rows in rank order, first max_out: scan of the kept flags chunk by chunk -----------
+    int carry = 0;
 #pragma unroll
     for (int q = 0; q < kPerT; ++q) {
-        const int r = tid * kPerT + q;
-        if (r < m && S.state[r] == 1) ++local;
-    }
-    int x = local;
+        const int r = q * kSmallThreads + tid;
+        const bool kept = r < m && S.state[r] == 1;
+        const unsigned bal = __ballot_sync(kFullMask, kept);
+        if (lane == 0) S.wsum[warp] = __popc(bal);
+        __syncthreads();
+        int base = carry + __popc(bal & ((1u << lane) - 1u));
+        int chunk = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, x, d); if (lane >= d) x += o; }
-    if (lane == 31) S.wsum[warp] = x;
-    __syncthreads();
-    int base = x - local;
-    int total = 0;
-#pragma unroll
-    for (int w = 0; w < kSmallWarps; ++w) {
-        if (w < warp) base += S.wsum[w];
-        total += S.wsum[w];
-    }
-#pragma unroll
-    for (int q = 0; q < kPerT; ++q) {
-        const int r = tid * kPerT + q;
-        if (r < m && S.state[r] == 1) {
-            if (base < pb.max_out) {
-                const unsigned long long key = S.keys[r];
-                float4 b = pb.boxes[key_index(key)];
-                if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
-                sink_emit(sink, base, key, b.x, b.y, b.z, b.w);
-            }
-            ++base;
+        for (int w = 0; w < kSmallWarps; ++w) {
+            if (w < warp) base += S.wsum[w];
+            chunk += S.wsum[w];
         }
+        if (kept && base < pb.max_out) {
+            float4 b = box[q];
+            if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
+            sink_emit(sink, base, key[q], b.x, b.y, b.z, b.w);
+        }
+        carry += chunk;
+        __syncthreads();
     }
-    return total < pb.max_out ? total : pb.max_out;
+    return carry < pb.max_out ? carry : pb.max_out;
 }
 
 // =========================================================================================
