@@ -42,24 +42,71 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_truth = reinterpret_cast<float4*>(smem_raw);
     unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)Gmax * 16);
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(smem_raw + (size_t)Gmax * 24);   // truths to visit
+    __shared__ uint32_t s_bb[4];          // bounding box of this CTA's anchor boxes (ordered-uint min/max)
+    __shared__ int s_wcnt[kMatchThreads / 32];
+    __shared__ int s_nlist;
     const int b = blockIdx.y;
     const int G = gt_count[b];
     const int p = blockIdx.x * kMatchThreads + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (G <= 0) return;
     for (int g = threadIdx.x; g < G; g += kMatchThreads) {
         s_truth[g] = __ldg(truths + (size_t)b * Gmax + g);
         s_best[g] = 0ull;
     }
+    if (threadIdx.x < 4) s_bb[threadIdx.x] = (threadIdx.x < 2) ? 0xffffffffu : 0u;   // min x, min y, max x, max y
+    if (threadIdx.x == 0) s_nlist = 0;
     __syncthreads();
     const bool valid = p < P;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) box = anchor_point_box(priors, arm_loc, b, p, P, v0, v1);
+    {
+        uint32_t mnx = valid ? float_to_ordered(box.x) : 0xffffffffu, mny = valid ? float_to_ordered(box.y) : 0xffffffffu;
+        uint32_t mxx = valid ? float_to_ordered(box.z) : 0u, mxy = valid ? float_to_ordered(box.w) : 0u;
+        mnx = __reduce_min_sync(kFullMask, mnx); mny = __reduce_min_sync(kFullMask, mny);
+        mxx = __reduce_max_sync(kFullMask, mxx); mxy = __reduce_max_sync(kFullMask, mxy);
+        if (lane == 0) { atomicMin(&s_bb[0], mnx); atomicMin(&s_bb[1], mny); atomicMax(&s_bb[2], mxx); atomicMax(&s_bb[3], mxy); }
+    }
+    __syncthreads();
+    // Truths that cannot intersect ANY anchor box of this CTA have IoU exactly 0 with all of them
+    // (min(t.x2, a.x2) - max(t.x1, a.x1) <= min(t.x2, bb.x2) - max(t.x1, bb.x1) <= 0, clamped): they can
+    // neither become an anchor's best truth (strict >, ascending g, start at (0, g = 0)) nor win a best
+    // prior, so they are skipped.  The first CTA of an image visits every truth: it supplies prior 0
+    // for truths that overlap nothing (torch.max returns the first index).
+    {
+        const float bx1 = ordered_to_float(s_bb[0]), by1 = ordered_to_float(s_bb[1]);
+        const float bx2 = ordered_to_float(s_bb[2]), by2 = ordered_to_float(s_bb[3]);
+        const bool all = blockIdx.x == 0 || !(bx1 <= bx2) || !(by1 <= by2);
+        for (int g0 = 0; g0 < G; g0 += kMatchThreads) {        // ordered compaction (ascending g)
+            const int g = g0 + threadIdx.x;
+            bool take = false;
+            if (g < G) {
+                const float4 t = s_truth[g];
+                const float w = fminf(t.z, bx2) - fmaxf(t.x, bx1);
+                const float h = fminf(t.w, by2) - fmaxf(t.y, by1);
+                take = all || (w > 0.0f && h > 0.0f) || !(w == w) || !(h == h);
+            }
+            const unsigned bal = __ballot_sync(kFullMask, take);
+            if (lane == 0) s_wcnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = s_nlist + __popc(bal & ((1u << lane) - 1u));
+            int tot = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < kMatchThreads / 32; ++w2) { if (w2 < warp) off += s_wcnt[w2]; tot += s_wcnt[w2]; }
+            if (take) s_list[off] = (unsigned short)g;
+            __syncthreads();
+            if (threadIdx.x == 0) s_nlist += tot;
+            __syncthreads();
+        }
+    }
+    const int nlist = s_nlist;
     const float area_b = (box.z - box.x) * (box.w - box.y);
-    float best = 0.f;
+    float best = 0.f;           // IoU with every skipped truth is 0; ties keep the lowest index
     int best_g = 0;
     const bool first_warp_of_row = (blockIdx.x == 0) && (threadIdx.x < 32);
-    for (int g = 0; g < G; ++g) {
+    for (int li = 0; li < nlist; ++li) {
+        const int g = s_list[li];
         const float4 t = s_truth[g];
         // box_utils.py:42-47,62-68 (truth = box_a, anchor = box_b)
         float w = fmaxf(fminf(t.z, box.z) - fmaxf(t.x, box.x), 0.0f);
@@ -68,7 +115,7 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
         float area_t = (t.z - t.x) * (t.w - t.y);
         float iou = inter / (area_t + area_b - inter);
         if (!valid) iou = -1.0f;
-        if (g == 0 || iou > best) { best = iou; best_g = g; }
+        if (iou > best) { best = iou; best_g = g; }        // first maximal index; (0, g = 0) when nothing overlaps
         // per-truth best prior: only overlapping anchors (or the row's first warp, which
         // supplies prior 0 for a truth that overlaps nothing) can win
         const bool contend = valid && (iou > 0.0f || iou != iou);
@@ -333,7 +380,7 @@ int rd_refine_match(const float* truths, const float* labels, const int* gt_coun
     dim3 grid((P + kMatchThreads - 1) / kMatchThreads, B);
     float* tmp_ov = best_truth_overlap;
     int* tmp_idx = best_truth_idx;
-    match_pass1_kernel<<<grid, kMatchThreads, (size_t)Gmax * 24, st>>>(
+    match_pass1_kernel<<<grid, kMatchThreads, (size_t)Gmax * 26, st>>>(
         (const float4*)truths, gt_count, (const float4*)priors, (const float4*)arm_loc, P, Gmax, v0, v1, best_prior,
         tmp_ov, tmp_idx);
     note_launch();
