@@ -182,7 +182,10 @@ detect_forward_kernel(const float4* __restrict__ arm_loc, const float2* __restri
 // grid = (S, B); CTA (s, b) owns anchors [s*1024, s*1024 + 1024) of image b: 8 warps x 128 anchors.
 // ---------------------------------------------------------------------------------------
 constexpr int kChunks = kSliceAnchors / (kCollectThreads / 32) / 32;   // 32-anchor chunks per warp = 4
-constexpr int kRowBatch = 4;                                           // odm_conf rows in flight per warp
+#ifndef RD_ROW_BATCH
+#define RD_ROW_BATCH 4
+#endif
+constexpr int kRowBatch = RD_ROW_BATCH;                                // odm_conf rows in flight per warp
 constexpr int kMaxClasses = 128;
 
 struct GraphOut {            // what collect contributes to the per-image suppression graph
@@ -240,6 +243,14 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
 #pragma unroll
     for (int w = 0; w < kCollectThreads / 32; ++w) { if (w < wib) woff += s_wpass[w]; tot += s_wpass[w]; }
     if (threadIdx.x == 0) s_base = tot ? atomicAdd(&GO.nnodes[b], tot) : 0;
+    // decode inputs of the first 32 passing anchors: issue the loads now, use them after the row phase
+    float4 pre_al = make_float4(0.f, 0.f, 0.f, 0.f), pre_ol = pre_al, pre_pr = pre_al;
+    if (lane < npass) {
+        const int a = a0 + s_list[wib][lane];
+        pre_al = ldg_stream4(arm_loc + img + a);
+        pre_ol = ldg_stream4(odm_loc + img + a);
+        pre_pr = __ldg(priors + a);
+    }
     // 2. odm_conf rows of the passing anchors: lane = class, kRowBatch rows in flight
     const int nseg = (C + 31) >> 5;          // <= 4 (C <= 128)
     unsigned long long* cand_b = cand + ((size_t)b * C * S + s) * kSliceAnchors;    // + c * S * 1024 per class
@@ -288,7 +299,9 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
         const int r = r0 + lane;
         if (r < npass) {
             const int a = a0 + s_list[wib][r];
-            float4 bx = refine_decode(ldg_stream4(arm_loc + img + a), ldg_stream4(odm_loc + img + a), __ldg(priors + a), v0, v1);
+            float4 bx = r0 == 0 ? refine_decode(pre_al, pre_ol, pre_pr, v0, v1)
+                                : refine_decode(ldg_stream4(arm_loc + img + a), ldg_stream4(odm_loc + img + a),
+                                                __ldg(priors + a), v0, v1);
             boxes_ws[img + a] = bx;
             GO.adjn[img + a] = 0;                    // degree counter of the suppression graph
             if (graph_ok) {

@@ -423,3 +423,63 @@ def test_limits_raise(rd):
     det = rd.Detect_RefineDet(3, 320, 0, 5000, 0.01, 0.45, 0.01, 5)
     with pytest.raises(RuntimeError):
         det.detect(z(1, P, 4), z(1, P, 2), z(1, P, 4), z(1, P, 3), z(P, 4))      # top_k > 4096
+
+
+def test_model_cfg1_fixture_gpu(rd, golden):
+    """BASELINE.json config 1 (real RefineDet320/VOC head outputs, random init): a3 against the reference,
+    a4 against the reference for tie-free classes and against the oracle for all (4,600 candidates per
+    class: radix-select + large-problem path on real model data)."""
+    g = golden('model_cfg1.npz')
+    C, top_k, keep, conf_thr, nms_thr, obj_thr = [float(v) for v in g['params']]
+    C, top_k, keep = int(C), int(top_k), int(keep)
+    det = rd.Detect_RefineDet(C, 320, 0, top_k, conf_thr, nms_thr, obj_thr, keep)
+    ins = [cu(g[k][None]) for k in ('arm_loc', 'arm_conf', 'odm_loc', 'odm_conf')]
+    pri = cu(g['priors'])
+    conf = ins[3].clone()
+    boxes, scores = det.forward(ins[0], ins[1], ins[2], conf, pri)
+    np.testing.assert_allclose(boxes[0].cpu().numpy(), g['boxes'], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(scores[0].cpu().numpy(), g['scores'])
+    scale = np.array([320.0] * 4, np.float32)
+    res = det.detect(*ins, pri, scale=scale)
+    counts = res.counts.cpu().numpy()[0]
+    dets = res.dets.cpu().numpy()[0]
+    out, anc = bo.detect_stage_eval(boxes[0].cpu().numpy(), g['scores'], scale, conf_thr, top_k, nms_thr, keep)
+    for j in range(1, C):
+        assert counts[j] == out[j].shape[0], j
+        assert np.array_equal(res.anchors[0, j, :counts[j]].cpu().numpy(), anc[j]), j
+        if g['a4_tie_free'][j]:
+            n = int(g['a4_counts'][j])
+            assert counts[j] == n
+            assert np.array_equal(dets[j, :n, 4], g['a4_dets'][j, :n, 4])
+            np.testing.assert_allclose(dets[j, :n, :4], g['a4_dets'][j, :n, :4], rtol=RTOL, atol=ATOL * 320)
+
+
+def test_api_variants(rd):
+    """per-image scale, non-contiguous / misaligned inputs (copied by the wrapper, in-place contract kept),
+    to_all_boxes layout."""
+    B, C = 2, 4
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS['320']).forward()[::3].contiguous().cuda()
+    P = priors.shape[0]
+    arm_loc, arm_conf, odm_loc, odm_conf = [t.cuda() for t in gen.detect_inputs(3, B, P, C, 'sparse', arm_shift=-2.0)]
+    det = rd.Detect_RefineDet(C, 320, 0, 200, 0.01, 0.45, 0.01, 100)
+    scale = torch.tensor([[320., 320., 320., 320.], [500., 375., 500., 375.]])
+    res = det.detect(arm_loc, arm_conf, odm_loc, odm_conf, priors, scale=scale)
+    boxes, scores = det.forward(arm_loc, arm_conf, odm_loc, odm_conf.clone(), priors)
+    for b in range(B):
+        out, _ = bo.detect_stage_eval(boxes[b].cpu().numpy(), scores[b].cpu().numpy(), scale[b].numpy(), 0.01, 200,
+                                      0.45, 100)
+        ab = res.to_all_boxes()
+        for c in range(C):
+            assert np.array_equal(ab[c][b], out[c].reshape(-1, 5)), (b, c)
+    # non-contiguous odm_conf view + misaligned arm_loc: results equal, caller's tensor still zeroed in place
+    big = torch.zeros(B, P, C + 3, device='cuda')
+    big[..., :C] = odm_conf
+    view = big[..., :C]
+    assert not view.is_contiguous()
+    raw = torch.zeros(arm_loc.numel() + 1, device='cuda')
+    mis = raw[1:].view_as(arm_loc)
+    mis.copy_(arm_loc)
+    assert mis.data_ptr() % 16 != 0
+    b2, s2 = det.forward(mis, arm_conf, odm_loc, view, priors)
+    assert torch.equal(b2, boxes) and torch.equal(s2, scores)
+    assert torch.equal(view, scores)                              # in-place zeroing reached the caller's storage

@@ -154,3 +154,25 @@ def test_multibox_loss(golden):
         assert np.array_equal(r['neg'], g['neg_' + mode])
         np.testing.assert_allclose([r['loss_l'], r['loss_c']], g[mode + '_loss'], rtol=2e-5)
         np.testing.assert_allclose(r['loss_c_rows'], g['loss_c_rows_' + mode], rtol=1e-5, atol=1e-6)
+
+
+def test_model_cfg1_fixture(golden):
+    """BASELINE.json config 1: head outputs of the reference RefineDet320/VOC model (random init) and the
+    reference's detect outputs for one image (tests/golden/make_golden_model.py)."""
+    g = golden('model_cfg1.npz')
+    C, top_k, keep, conf_thr, nms_thr, obj_thr = g['params']
+    conf = g['odm_conf'][None].copy()
+    boxes, scores = bo.detect_forward(g['arm_loc'][None], g['arm_conf'][None], g['odm_loc'][None], conf,
+                                      g['priors'], float(obj_thr))
+    np.testing.assert_allclose(boxes[0], g['boxes'], **RT)
+    assert np.array_equal(scores[0], g['scores'])
+    out, _ = bo.detect_stage_eval(g['boxes'], g['scores'], np.array([320.0] * 4, np.float32), float(conf_thr),
+                                  int(top_k), float(nms_thr), int(keep))
+    checked = 0
+    for j in range(1, int(C)):
+        if g['a4_tie_free'][j]:                       # with tied scores the reference's order is unstable
+            n = int(g['a4_counts'][j])
+            assert out[j].shape[0] == n
+            assert np.array_equal(out[j], g['a4_dets'][j, :n])
+            checked += 1
+    assert checked >= 1
