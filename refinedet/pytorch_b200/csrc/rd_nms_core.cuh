@@ -382,13 +382,15 @@ __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const Ro
 // =========================================================================================
 // large problems: one CTA (any multiple of 32 threads), n arbitrary, m = min(n, top_k) <= mcap
 // =========================================================================================
+constexpr int kLargePairCap = 2048;        // flattened (candidate, kept box) pairs per 32-candidate step
+
 struct NmsSmemLayout {
     int mcap;   // max boxes held (multiple of 32)
     int W;      // mcap / 32
     int WS;     // padded row stride of the bin tables (odd -> conflict-free)
     int Kp;     // power of two >= mcap (bitonic sort buffer)
     size_t off_keys, off_x1, off_y1, off_x2, off_y2, off_cr, off_tab, off_keptbits, off_hist, off_cnt,
-        off_offs, off_misc, total;
+        off_offs, off_misc, off_pairs, off_tin, total;
 };
 
 __host__ __device__ inline int next_pow2(int v) {
@@ -417,6 +419,8 @@ __host__ __device__ inline NmsSmemLayout nms_layout(int mcap_req) {
     L.off_cnt = o;       o += kMaxSlices * 4;
     L.off_offs = o;      o += (kMaxSlices + 1) * 4 + 12;
     L.off_misc = o;      o += 16 * 4;
+    L.off_tin = o;       o += 32 * 4;
+    L.off_pairs = o;     o += (size_t)kLargePairCap * 4;
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
@@ -440,7 +444,7 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
     uint32_t* keptbits = reinterpret_cast<uint32_t*>(smem + L.off_keptbits);
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem + L.off_hist);
     uint32_t* misc = reinterpret_cast<uint32_t*>(smem + L.off_misc);
-    // misc: 0 select counter, 1 digit, 2 need, 3 done, 4..7 ordered min/max, 8 kept count
+    // misc: 0 select counter, 1 digit, 2 need, 3 done, 4..7 ordered min/max, 8 kept count, 9 sup, 10 pairs, 11 stop
 
     const CandList& cl = pb.cl;
     const int n = cl.n;
@@ -595,47 +599,96 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
     }
     __syncthreads();
 
-    // ---- 5. greedy walk, one warp (tests in place) ------------------------------------------------------
-    if (warp == 0) {
-        const float thr = pb.thr;
-        const int flags = pb.flags;
-        const int max_out = pb.max_out;
-        int kept_total = 0;
-        const uint32_t* Sx = tab;
-        const uint32_t* Ex = tab + 1 * kCols * L.WS;
-        const uint32_t* Sy = tab + 2 * kCols * L.WS;
-        const uint32_t* Ey = tab + 3 * kCols * L.WS;
-        const uint32_t lt_mask = (1u << lane) - 1u;
-        for (int ib = 0; ib < Wm; ++ib) {
-            const int j = ib * 32 + lane;
-            const bool valid = j < m;
-            bool alive = valid;
-            float x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+    // ---- 5. greedy walk: warp 0 drives 32 candidates per step; the (candidate, kept earlier box) pairs
+    //         that survive the bin cull are flattened into a list and tested by ALL threads, so a box that
+    //         overlaps many others does not serialise the walk -------------------------------------------
+    uint32_t* pairs = reinterpret_cast<uint32_t*>(smem + L.off_pairs);
+    uint32_t* s_tin = reinterpret_cast<uint32_t*>(smem + L.off_tin);
+    // misc: 9 sup word, 10 pair total, 11 stop
+    if (tid < 32) s_tin[tid] = 0;
+    if (tid == 0) { misc[9] = 0; misc[11] = 0; }
+    __syncthreads();
+    const float thr = pb.thr;
+    const int flags = pb.flags;
+    const int max_out = pb.max_out;
+    const uint32_t* Sx = tab;
+    const uint32_t* Ex = tab + 1 * kCols * L.WS;
+    const uint32_t* Sy = tab + 2 * kCols * L.WS;
+    const uint32_t* Ey = tab + 3 * kCols * L.WS;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    int kept_total = 0;                                   // meaningful in warp 0
+    for (int ib = 0; ib < Wm; ++ib) {
+        const int j = ib * 32 + lane;
+        const bool valid = j < m;
+        bool alive = valid;
+        float x1 = 0, y1 = 0, x2 = 0, y2 = 0;
+        const uint32_t *rSx = Sx, *rEx = Ex, *rSy = Sy, *rEy = Ey;
+        int total = 0;
+        if (warp == 0) {
             uint32_t cr = 0;
             if (valid) { x1 = sx1[j]; y1 = sy1[j]; x2 = sx2[j]; y2 = sy2[j]; cr = scr[j]; }
-            const uint32_t* rSx = Sx + ((cr >> 8) & 255u) * L.WS;    // S_x[b_j]
-            const uint32_t* rEx = Ex + (cr & 255u) * L.WS;           // E_x[a_j]
-            const uint32_t* rSy = Sy + ((cr >> 24) & 255u) * L.WS;   // S_y[b_j]
-            const uint32_t* rEy = Ey + ((cr >> 16) & 255u) * L.WS;   // E_y[a_j]
-            for (int w = 0; w < ib; ++w) {                           // earlier blocks: KEPT boxes only
-                uint32_t h = rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & keptbits[w];
-                while (alive && h) {
-                    const int i = (w << 5) + __ffs(h) - 1;
-                    h &= h - 1;
-                    if (suppresses(sx1[i], sy1[i], sx2[i], sy2[i], x1, y1, x2, y2, thr, flags)) alive = false;
+            rSx = Sx + ((cr >> 8) & 255u) * L.WS;    // S_x[b_j]
+            rEx = Ex + (cr & 255u) * L.WS;           // E_x[a_j]
+            rSy = Sy + ((cr >> 24) & 255u) * L.WS;   // S_y[b_j]
+            rEy = Ey + ((cr >> 16) & 255u) * L.WS;   // E_y[a_j]
+            int nh = 0;
+            if (valid) {
+                for (int w = 0; w <= ib; ++w)
+                    nh += __popc(rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & (w < ib ? keptbits[w] : lt_mask));
+            }
+            int off = nh;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, off, d); if (lane >= d) off += o; }
+            total = __shfl_sync(kFullMask, off, 31);
+            off -= nh;
+            if (total > 0 && total <= kLargePairCap && valid) {
+                for (int w = 0; w <= ib; ++w) {
+                    uint32_t h = rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & (w < ib ? keptbits[w] : lt_mask);
+                    while (h) {
+                        const int i = (w << 5) + __ffs(h) - 1;
+                        h &= h - 1;
+                        pairs[off++] = ((uint32_t)lane << 16) | (uint32_t)i;
+                    }
                 }
             }
-            uint32_t tin = 0;                                        // same block: earlier lanes
-            if (alive) {
-                uint32_t h = rSx[ib] & ~rEx[ib] & rSy[ib] & ~rEy[ib] & lt_mask;
-                while (h) {
-                    const int k = __ffs(h) - 1;
-                    h &= h - 1;
-                    const int i = (ib << 5) + k;
-                    if (suppresses(sx1[i], sy1[i], sx2[i], sy2[i], x1, y1, x2, y2, thr, flags)) tin |= 1u << k;
+            if (lane == 0) misc[10] = (uint32_t)total;
+        }
+        __syncthreads();
+        total = (int)misc[10];
+        const bool listed = total > 0 && total <= kLargePairCap;
+        if (listed) {
+            for (int p = tid; p < total; p += nthr) {
+                const uint32_t e = pairs[p];
+                const int jl = (int)(e >> 16), i = (int)(e & 0xffffu);
+                const int jj = ib * 32 + jl;
+                if (suppresses(sx1[i], sy1[i], sx2[i], sy2[i], sx1[jj], sy1[jj], sx2[jj], sy2[jj], thr, flags)) {
+                    if (i < ib * 32) atomicOr(&misc[9], 1u << jl);
+                    else atomicOr(&s_tin[jl], 1u << (i - ib * 32));
                 }
             }
-            uint32_t u = __reduce_or_sync(kFullMask, tin);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t tin = 0;
+            if (listed) {
+                if ((misc[9] >> lane) & 1u) alive = false;
+                tin = s_tin[lane];
+                __syncwarp();
+                s_tin[lane] = 0;
+                if (lane == 0) misc[9] = 0;
+            } else if (total > 0 && valid) {         // pair list would overflow: test in place
+                for (int w = 0; w <= ib; ++w) {
+                    uint32_t h = rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & (w < ib ? keptbits[w] : lt_mask);
+                    while (h && (alive || w == ib)) {
+                        const int i = (w << 5) + __ffs(h) - 1;
+                        h &= h - 1;
+                        if (suppresses(sx1[i], sy1[i], sx2[i], sy2[i], x1, y1, x2, y2, thr, flags)) {
+                            if (w < ib) alive = false; else tin |= 1u << (i - ib * 32);
+                        }
+                    }
+                }
+            }
+            uint32_t u = __reduce_or_sync(kFullMask, alive ? tin : 0u);   // in-block resolution in score order
             while (u) {
                 const int k = __ffs(u) - 1;
                 u &= u - 1;
@@ -652,14 +705,16 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
                 cnt = room;
             }
             if ((keptw >> lane) & 1u) sink_emit(sink, kept_total + __popc(keptw & lt_mask), keys[j], x1, y1, x2, y2);
-            if (lane == 0) keptbits[ib] = keptw;
-            __syncwarp();
             kept_total += cnt;
-            if (kept_total >= max_out) break;
+            if (lane == 0) {
+                keptbits[ib] = keptw;
+                misc[8] = (uint32_t)kept_total;
+                if (kept_total >= max_out) misc[11] = 1;
+            }
         }
-        if (lane == 0) misc[8] = (uint32_t)kept_total;
+        __syncthreads();
+        if (misc[11]) break;
     }
-    __syncthreads();
     return (int)misc[8];
 }
 
