@@ -40,7 +40,10 @@ __device__ __forceinline__ unsigned long long rd_gtime() { unsigned long long t;
 #endif
 constexpr int kCollectThreads = 256;
 constexpr int kSliceAnchors = 1024;   // anchors per collect CTA = capacity of one candidate sub-list
-constexpr int kLargeThreads = 128;
+#ifndef RD_LARGE_THREADS
+#define RD_LARGE_THREADS 512
+#endif
+constexpr int kLargeThreads = RD_LARGE_THREADS;
 
 // ---------------------------------------------------------------------------------------
 // workspace of the fused stage.  The control block (header, nnodes, gtab) must be zero when a call
