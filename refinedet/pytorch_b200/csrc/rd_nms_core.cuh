@@ -283,9 +283,23 @@ __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const Ro
     }
     for (int i = tid; i < kHashSlots; i += kSmallThreads) S.u.g.hash[i] = 0xffffffffu;
     __syncthreads();
-    uint4 row0[kPerT], row1[kPerT];
     float4 box[kPerT];
+#pragma unroll
+    for (int q = 0; q < kPerT; ++q) {
+        const int r = q * kSmallThreads + tid;
+        if (r < m) {
+            const uint32_t a = key_index(key[q]);
+            box[q] = pb.boxes[a];                            // most candidates are kept: fetch the row data now
+            uint32_t h = hash_anchor(a);                     // insert (anchor -> rank)
+            const uint32_t val = (a << 8) | (uint32_t)r;
+            while (atomicCAS(&S.u.g.hash[h], 0xffffffffu, val) != 0xffffffffu) h = (h + 1) & (kHashSlots - 1);
+        }
+    }
+    __syncthreads();
+    // ---- dependencies: graph neighbours that are candidates of this class and rank earlier --------
+    // (adjacency rows are consumed as they arrive, nothing is held across the barrier)
     int dn[kPerT];
+    uint4 row0[kPerT], row1[kPerT];
 #pragma unroll
     for (int q = 0; q < kPerT; ++q) {
         const int r = q * kSmallThreads + tid;
@@ -295,14 +309,8 @@ __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const Ro
             dn[q] = G.adjn[a];
             row0[q] = __ldg(G.adj + (size_t)a * 2);
             row1[q] = __ldg(G.adj + (size_t)a * 2 + 1);
-            box[q] = pb.boxes[a];                            // most candidates are kept: fetch the row data now
-            uint32_t h = hash_anchor(a);                     // insert (anchor -> rank)
-            const uint32_t val = (a << 8) | (uint32_t)r;
-            while (atomicCAS(&S.u.g.hash[h], 0xffffffffu, val) != 0xffffffffu) h = (h + 1) & (kHashSlots - 1);
         }
     }
-    __syncthreads();
-    // ---- dependencies: graph neighbours that are candidates of this class and rank earlier --------
 #pragma unroll
     for (int q = 0; q < kPerT; ++q) {
         const int r = q * kSmallThreads + tid;
