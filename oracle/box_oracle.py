@@ -251,6 +251,26 @@ def forward_python_nms(arm_loc, arm_conf, odm_loc, odm_conf, priors, num_classes
     return output, anchors
 
 
+def coco_results(all_boxes, image_ids, class_to_cat_id):
+    """data/sarship_coco.py:293-336 (``_coco_results_one_category`` + ``_write_coco_results_file``):
+    ``all_boxes[c][i]`` = ``[n,5]`` rows (x1,y1,x2,y2,score) -> list of result dicts, classes ascending
+    (class 0 = background skipped), images ascending; bbox = [x, y, x2-x+1, y2-y+1] in float64."""
+    results = []
+    for c in range(1, len(all_boxes)):
+        for i, index in enumerate(image_ids):
+            dets = np.asarray(all_boxes[c][i]).astype(np.float64)      # :296 astype(np.float)
+            if dets.shape[0] == 0:                                     # :297-298
+                continue
+            scores = dets[:, -1]
+            xs, ys = dets[:, 0], dets[:, 1]
+            ws = dets[:, 2] - xs + 1                                   # :302
+            hs = dets[:, 3] - ys + 1
+            results.extend({'image_id': index, 'category_id': class_to_cat_id[c],
+                            'bbox': [xs[k], ys[k], ws[k], hs[k]], 'score': scores[k]}
+                           for k in range(dets.shape[0]))
+    return results
+
+
 # ----------------------------------------------------------------------------
 # layers/box_utils.py: match / refine_match
 # ----------------------------------------------------------------------------

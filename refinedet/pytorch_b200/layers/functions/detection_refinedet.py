@@ -37,6 +37,32 @@ class Detections(object):
         total = int(offsets[-1].item())
         return offsets, rows[:total]
 
+    def to_coco_results(self, image_ids, class_to_cat_id):
+        """The result wire format of the reference's eval (``data/sarship_coco.py:293-336``): a list of
+        ``{'image_id', 'category_id', 'bbox': [x, y, w, h], 'score'}`` with ``w = x2 - x1 + 1``,
+        ``h = y2 - y1 + 1`` computed in float64 (the reference's ``astype(np.float)``), classes ascending
+        (background skipped), images ascending inside a class, rows score-descending.
+        ``image_ids[b]`` is the dataset index of image b, ``class_to_cat_id[c]`` the COCO category of
+        class c (``None`` skips the class)."""
+        import numpy as np
+        counts = self.counts.cpu().numpy()
+        dets = self.dets.cpu().numpy()
+        B, C = counts.shape
+        results = []
+        for c in range(1, C):
+            cat = class_to_cat_id[c]
+            if cat is None:
+                continue
+            for b in range(B):
+                d = dets[b, c, :counts[b, c]].astype(np.float64)
+                if d.shape[0] == 0:
+                    continue
+                xs, ys = d[:, 0], d[:, 1]
+                ws, hs = d[:, 2] - xs + 1, d[:, 3] - ys + 1
+                results.extend({'image_id': image_ids[b], 'category_id': cat,
+                                'bbox': [xs[k], ys[k], ws[k], hs[k]], 'score': d[k, 4]} for k in range(d.shape[0]))
+        return results
+
     def to_all_boxes(self):
         """``all_boxes[c][b]`` numpy arrays ``[n,5]`` as built by eval_refinedet_coco.py:214-232."""
         counts = self.counts.cpu().numpy()

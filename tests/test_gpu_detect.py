@@ -483,3 +483,23 @@ def test_api_variants(rd):
     b2, s2 = det.forward(mis, arm_conf, odm_loc, view, priors)
     assert torch.equal(b2, boxes) and torch.equal(s2, scores)
     assert torch.equal(view, scores)                              # in-place zeroing reached the caller's storage
+
+
+def test_coco_wire_format(rd):
+    """SURVEY f-2: result rows in the reference's COCO json layout (data/sarship_coco.py:293-336)."""
+    B, C = 3, 5
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS['320']).forward()[::7].contiguous().cuda()
+    P = priors.shape[0]
+    ins = [t.cuda() for t in gen.detect_inputs(12, B, P, C, 'sparse', arm_shift=-2.0)]
+    det = rd.Detect_RefineDet(C, 320, 0, 100, 0.01, 0.49, 0.01, 50)
+    res = det.detect(*ins, priors, scale=[320., 320., 320., 320.])
+    ids = [101, 7, 55]
+    cats = [None, 3, 1, 18, 44]
+    got = res.to_coco_results(ids, cats)
+    exp = bo.coco_results(res.to_all_boxes(), ids, cats)
+    assert len(got) == len(exp) == int(res.counts.sum()) > 0
+    for a, b in zip(got, exp):
+        assert a['image_id'] == b['image_id'] and a['category_id'] == b['category_id']
+        assert a['bbox'] == b['bbox'] and a['score'] == b['score']
+    import json
+    json.dumps(got)                                              # serialisable like the reference's file
