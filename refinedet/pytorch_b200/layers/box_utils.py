@@ -104,6 +104,22 @@ def pad_targets(targets, device):
     return truths, labels, gt_count
 
 
+def check_targets(targets, device=None):
+    """The ground-truth sanity check of the reference's training loop (``train_refinedet.py:240-245``:
+    a triple Python loop, one host sync per coordinate) as one device reduction and one sync:
+    raises ``StopIteration`` when any box coordinate lies outside ``[0, 1]``.  Returns the padded
+    ``(truths, labels, gt_count)`` so the loss does not pad again."""
+    if device is None:
+        device = targets[0].device
+    truths, labels, gt_count = pad_targets(targets, device)
+    G = truths.shape[1]
+    valid = torch.arange(G, device=truths.device)[None, :] < gt_count[:, None]
+    bad = ((truths < 0) | (truths > 1)).any(-1) & valid
+    if bool(bad.any()):
+        raise StopIteration
+    return truths, labels, gt_count
+
+
 def match_batch(threshold, truths, labels, gt_count, priors, variances, arm_loc=None,
                 label_mode=LABEL_ODM, return_best=False):
     """Batched ``refine_match`` / ``match`` (box_utils.py:70-160) — one call for the whole

@@ -154,3 +154,19 @@ def test_full_size_loss_step(rd):
     assert int((conf_t > 0).sum(1).min()) >= 1
     l2, c2 = odm_crit.match_targets(preds, tg)
     assert torch.equal(c2, conf_t) and torch.equal(l2, loc_t)
+
+
+def test_check_targets(rd):
+    """SURVEY f-3: the per-coordinate validation loop of train_refinedet.py:240-245 as one reduction."""
+    tg = [t.cuda() for t in gen.targets(3, 4, 6, 21)]
+    truths, labels, cnt = rd.box_utils.check_targets(tg)
+    assert truths.shape == (4, 6, 4) and cnt.tolist() == [6, 6, 6, 6]
+    bad = [t.clone() for t in tg]
+    bad[2][3, 1] = 1.0001
+    with pytest.raises(StopIteration):
+        rd.box_utils.check_targets(bad)
+    bad[2][3, 1] = -1e-6
+    with pytest.raises(StopIteration):
+        rd.box_utils.check_targets(bad)
+    ragged = [tg[0][:2], tg[1], tg[2][:1], tg[3]]           # padding rows (zeros) must not trip the check
+    rd.box_utils.check_targets(ragged)
