@@ -24,12 +24,9 @@ LIB_PATH = os.path.join(LIB_DIR, 'librefinedet_b200.so')
 SOURCES = ['rd_detect.cu', 'rd_match.cu']
 HEADERS = ['rd_common.cuh', 'rd_nms_core.cuh']
 
-# -rdc=true: nms_small_kernel tail-launches nms_large_kernel from the device (CUDA dynamic parallelism)
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
               '-fmad=false', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
               '-I', INCLUDE]
-if os.environ.get('RD_USE_CDP', '0') == '1':
-    NVCC_FLAGS += ['-rdc=true', '-DRD_USE_CDP']
 
 
 def find_nvcc():
@@ -76,8 +73,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     tmp = LIB_PATH + '.tmp.%d' % os.getpid()
-    rdc = ['-rdc=true', '-lcudadevrt'] if '-rdc=true' in NVCC_FLAGS else []
-    cmd = [nvcc, '-shared', '-Xcompiler', '-fPIC', '-o', tmp] + objs + rdc + \
+    cmd = [nvcc, '-shared', '-Xcompiler', '-fPIC', '-o', tmp] + objs + \
           ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -10,8 +10,8 @@
 //                           SHARED-memory atomics (the CTA owns its sub-list), so there is no global
 //                           atomic and nothing to reset between calls.  odm_conf / loc rows of
 //                           ARM-filtered anchors are never fetched: traffic scales with the pass rate.
-//   graph_kernel            KG: one CTA per (image, slice): exact suppression graph between the ARM-passing
-//                           anchors of an image (class independent), adjacency lists per anchor
+//   graph_kernel            KG: 16 CTAs per image: exact suppression graph between the ARM-passing anchors
+//                           of an image (class independent), adjacency lists per anchor
 //   sort_kernel             K2a: one 96-thread CTA per (image, class) with <= 256 candidates: key sort;
 //                           runs beside graph_kernel (programmatic dependent launch)
 //   resolve_kernel          K2b+K3: graph look-ups through a smem hash, dependency resolution, rows
@@ -48,8 +48,8 @@ constexpr int kLargeThreads = RD_LARGE_THREADS;
 // ---------------------------------------------------------------------------------------
 // workspace of the fused stage.  The control block (header, nnodes, gtab) must be zero when a call
 // starts: rd_detect_workspace_reset zeroes it once, every call leaves it zero again (collect clears
-// the queue header, nms_small's class-0 CTAs clear nnodes / gtab of their image).
-//   header u32 [64]               : [0] = number of queued large problems, [1] = CTA ticket of nms_small
+// the queue header, resolve_kernel's class-0 CTAs clear nnodes / gtab of their image).
+//   header u32 [64]               : [0] = number of queued large problems
 //   nnodes int [B]                : graph nodes (= ARM-passing anchors) of every image
 //   gtab   u32 [B][4][32][33]     : start/end bin marks of the nodes (OR-ed in by collect)
 //   flag   int [B]                : 1 = the image has no suppression graph (too many nodes / degree overflow)

@@ -159,7 +159,7 @@ __device__ __forceinline__ unsigned long long warp_sort32_desc(unsigned long lon
 }
 
 // =========================================================================================
-// small problems: one CTA of kSmallThreads threads, n <= kSmallCap, no select
+// small problems: n <= kSmallCap candidates, no select (sort_kernel + resolve_kernel)
 // =========================================================================================
 #ifndef RD_SORT_THREADS
 #define RD_SORT_THREADS 96
