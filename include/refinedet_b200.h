@@ -132,6 +132,28 @@ RD_API int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, co
                     int* out_counts, float* out_dets, int* out_anchor, void* stream,
                     float* stage_ms_host);
 
+/* Plans: the launch chain of rd_detect_fused for FIXED buffers, captured once into a CUDA graph
+ * (programmatic-launch edges included) and replayed with one driver call.  A serving loop whose
+ * model writes its head outputs into static buffers replays the plan every batch; several plans
+ * over different workspaces / output buffers replayed on different streams keep more than one
+ * batch in flight (bench.py's pipelined mode).  Replaces nothing in the reference — its eval loop
+ * (eval_refinedet_coco.py:205-232) issues ~160 host-synchronous calls per image.
+ *   rd_detect_plan_create : same arguments as rd_detect_fused (no stream); the pointers are baked
+ *                           into the plan and must stay valid while it lives.  Creates and destroys
+ *                           a private capture stream; allocates host/driver objects only.
+ *   rd_detect_plan_launch : asynchronous replay on `stream`.
+ *   rd_detect_plan_destroy: releases the graph.                                              */
+typedef struct rd_detect_plan rd_detect_plan;
+RD_API int rd_detect_plan_create(const float* arm_loc, const float* arm_conf, const float* odm_loc,
+                    const float* odm_conf, const float* priors, int B, int P, int C,
+                    float objectness_thre, float conf_thresh, float nms_thresh,
+                    int top_k, int max_out, const float* img_scale, int nms_flags,
+                    int row_layout, float v0, float v1,
+                    void* workspace, size_t workspace_bytes,
+                    int* out_counts, float* out_dets, int* out_anchor, rd_detect_plan** plan_out);
+RD_API int rd_detect_plan_launch(rd_detect_plan* plan, void* stream);
+RD_API int rd_detect_plan_destroy(rd_detect_plan* plan);
+
 /* compact [B,C,max_out,5] slots into packed rows (score-descending inside a class,
  * classes ascending, images ascending).  out_offsets[B*C+1] = exclusive prefix sum
  * of counts; packed[total,5]; packed_capacity = rows available in `packed`. */

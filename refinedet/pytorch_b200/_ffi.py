@@ -50,6 +50,11 @@ _SIGNATURES = {
     'rd_detect_fused_timed': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float,
                                       c_int, c_int, _P, c_int, c_int, c_float, c_float, _P, c_size_t,
                                       _P, _P, _P, _P, _P]),
+    'rd_detect_plan_create': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float,
+                                      c_int, c_int, _P, c_int, c_int, c_float, c_float, _P, c_size_t,
+                                      _P, _P, _P, _P]),
+    'rd_detect_plan_launch': (c_int, [_P, _P]),
+    'rd_detect_plan_destroy': (c_int, [_P]),
     'rd_pack_detections': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P]),
     'rd_nms_workspace_bytes': (c_size_t, [c_int]),
     'rd_nms': (c_int, [_P, _P, c_int, c_float, c_int, c_int, _P, c_size_t, _P, _P, _P]),

@@ -929,6 +929,66 @@ int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, const flo
     return rc;
 }
 
+}  // extern "C"
+
+struct rd_detect_plan {
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    int launches;          // kernels per replay
+};
+
+extern "C" {
+
+int rd_detect_plan_create(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
+                          const float* priors, int B, int P, int C, float objectness_thre, float conf_thresh,
+                          float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
+                          int row_layout, float v0, float v1, void* workspace, size_t workspace_bytes,
+                          int* out_counts, float* out_dets, int* out_anchor, rd_detect_plan** plan_out) {
+    if (!plan_out) return RD_ERR_BAD_ARG;
+    *plan_out = nullptr;
+    cudaStream_t cs = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaStreamDestroy(cs); return (int)e; }
+    const unsigned long long l0 = g_launches.load(std::memory_order_relaxed);
+    int rc = detect_fused_impl(arm_loc, arm_conf, odm_loc, odm_conf, priors, B, P, C, objectness_thre, conf_thresh,
+                               nms_thresh, top_k, max_out, img_scale, nms_flags, row_layout, v0, v1, workspace,
+                               workspace_bytes, out_counts, out_dets, out_anchor, cs, nullptr);
+    const unsigned long long l1 = g_launches.load(std::memory_order_relaxed);
+    g_launches.fetch_sub(l1 - l0, std::memory_order_relaxed);      // captured, not executed
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(cs, &graph);                          // always end the capture, even on error
+    cudaStreamDestroy(cs);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return (int)e; }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return (int)e; }
+    rd_detect_plan* p = new rd_detect_plan;
+    p->graph = graph;
+    p->exec = exec;
+    p->launches = (int)(l1 - l0);
+    *plan_out = p;
+    return 0;
+}
+
+int rd_detect_plan_launch(rd_detect_plan* plan, void* stream) {
+    if (!plan || !plan->exec) return RD_ERR_BAD_ARG;
+    cudaError_t e = cudaGraphLaunch(plan->exec, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    note_launch(plan->launches);
+    return 0;
+}
+
+int rd_detect_plan_destroy(rd_detect_plan* plan) {
+    if (!plan) return 0;
+    if (plan->exec) cudaGraphExecDestroy(plan->exec);
+    if (plan->graph) cudaGraphDestroy(plan->graph);
+    delete plan;
+    return 0;
+}
+
 int rd_pack_detections(const int* counts, const float* dets, int B, int C, int max_out, int* out_offsets,
                        float* packed, int packed_capacity, void* stream) {
     if (!counts || !dets || !out_offsets || !packed || B <= 0 || C <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;

@@ -71,6 +71,37 @@ class Detections(object):
         return [[dets[b, c, :counts[b, c]].copy() for b in range(B)] for c in range(C)]
 
 
+class DetectPlan(object):
+    """The fused detect stage for fixed buffers as one CUDA-graph replay (``rd_detect_plan_*``).
+
+    ``launch(stream=None)`` replays asynchronously on ``stream`` (default: the current stream) and
+    returns the plan's :class:`Detections` (persistent buffers, overwritten by every replay)."""
+
+    def __init__(self, args, result, device, keep_alive):
+        import ctypes
+        self.result, self.device, self._keep = result, device, keep_alive
+        handle = ctypes.c_void_p(0)
+        with torch.cuda.device(device):
+            check(lib().rd_detect_plan_create(*args, ctypes.byref(handle)), 'rd_detect_plan_create')
+        self._handle = handle
+
+    def launch(self, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        check(lib().rd_detect_plan_launch(self._handle, s.cuda_stream), 'rd_detect_plan_launch')
+        return self.result
+
+    def close(self):
+        if getattr(self, '_handle', None) is not None and self._handle.value:
+            lib().rd_detect_plan_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Detect_RefineDet(object):
     """At test time, the final layer of RefineDet: ARM-objectness filter, two-stage decode
     and (in ``detect`` / ``forward_python_nms``) per-class threshold, top-k and NMS.
@@ -216,8 +247,9 @@ class Detect_RefineDet(object):
                 acc[k] += float(ms[k])
         return {n: v / steps for n, v in zip(names, acc)}
 
-    def _fused(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale, flags,
-               row_layout, max_out, dets=None, timed=None, host_mapped=False):
+    def _prepare(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale, flags,
+                 row_layout, max_out, dets=None, host_mapped=False, workspace=None, out=None):
+        """Validated argument tuple of ``rd_detect_fused`` (everything but the stream) + the result object."""
         if host_mapped:      # pinned host tensors, dereferenced by the kernels through unified addressing
             arm_loc, arm_conf, odm_loc, odm_conf = arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data
             priors = require_cuda_f32(prior_data, 'prior_data')
@@ -235,16 +267,28 @@ class Detect_RefineDet(object):
         if scale is not None:
             scale = torch.as_tensor(scale, dtype=torch.float32).to(dev)
             scale = scale.reshape(1, 4).expand(B, 4).contiguous() if scale.numel() == 4 else scale.reshape(B, 4).contiguous()
-        ws = self._workspace(B, P, C, dev)
-        counts = torch.empty(B, C, dtype=torch.int32, device=dev)
-        if dets is None:
-            dets = torch.empty(B, C, max_out, 5, dtype=torch.float32, device=dev)
-        anchors = torch.empty(B, C, max_out, dtype=torch.int32, device=dev)
+        ws = workspace if workspace is not None else self._workspace(B, P, C, dev)
+        if out is not None:
+            counts, dets, anchors = out.counts, out.dets, out.anchors
+            if tuple(counts.shape) != (B, C) or tuple(dets.shape) != (B, C, max_out, 5):
+                raise ValueError('out= buffers must be counts[B,C], dets[B,C,max_out,5], anchors[B,C,max_out]')
+        else:
+            counts = torch.empty(B, C, dtype=torch.int32, device=dev)
+            if dets is None:
+                dets = torch.empty(B, C, max_out, 5, dtype=torch.float32, device=dev)
+            anchors = torch.empty(B, C, max_out, dtype=torch.int32, device=dev)
         args = (ptr(arm_loc), ptr(arm_conf), ptr(odm_loc), ptr(odm_conf), ptr(priors),
                 B, P, C, float(self.objectness_thre), float(self.conf_thresh),
                 float(self.nms_thresh), int(self.top_k), max_out, ptr(scale), int(flags),
                 int(row_layout), float(self.variance[0]), float(self.variance[1]),
                 ptr(ws), ws.numel(), ptr(counts), ptr(dets), ptr(anchors))
+        keep_alive = (arm_loc, arm_conf, odm_loc, odm_conf, priors, scale, ws)
+        return args, Detections(counts, dets, anchors, row_layout), dev, keep_alive
+
+    def _fused(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale, flags,
+               row_layout, max_out, dets=None, timed=None, host_mapped=False):
+        args, res, dev, _ = self._prepare(arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data,
+                                          scale, flags, row_layout, max_out, dets=dets, host_mapped=host_mapped)
         with torch.cuda.device(dev):
             if timed is None:
                 check(lib().rd_detect_fused(*args, stream_ptr()), 'rd_detect_fused')
@@ -252,7 +296,43 @@ class Detect_RefineDet(object):
                 import ctypes
                 check(lib().rd_detect_fused_timed(*args, stream_ptr(), ctypes.cast(timed, ctypes.c_void_p)),
                       'rd_detect_fused_timed')
-        return Detections(counts, dets, anchors, row_layout)
+        return res
+
+    # -- plans: the stage for fixed buffers as one CUDA-graph replay ---------------------------
+    def new_workspace(self, B, P, device):
+        """A private workspace (one per batch in flight; :meth:`plan` ``workspace=``)."""
+        L = lib()
+        nbytes = int(L.rd_detect_workspace_bytes(B, P, self.num_classes))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            check(L.rd_detect_workspace_reset(ptr(ws), nbytes, stream_ptr()), 'rd_detect_workspace_reset')
+        return ws
+
+    def new_outputs(self, B, device, max_out=None, row_layout=_ffi.RD_ROW_BOX_SCORE):
+        """Persistent output buffers for :meth:`plan` ``out=``."""
+        max_out = max(1, min(int(self.keep_top_k if max_out is None else max_out), int(self.top_k)))
+        C = self.num_classes
+        return Detections(torch.empty(B, C, dtype=torch.int32, device=device),
+                          torch.empty(B, C, max_out, 5, dtype=torch.float32, device=device),
+                          torch.empty(B, C, max_out, dtype=torch.int32, device=device), row_layout)
+
+    def plan(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale=None,
+             workspace=None, out=None, force_cpu_semantics=False):
+        """:meth:`detect` for FIXED input buffers, captured once (``rd_detect_plan_create``): the returned
+        :class:`DetectPlan` replays the whole launch chain with one driver call per batch.  The tensors are
+        referenced, not copied — refill them in place between replays.  Plans that share ``workspace`` /
+        ``out`` must be replayed on the same stream; give every batch in flight its own pair
+        (:meth:`new_workspace`, :meth:`new_outputs`)."""
+        flags = _ffi.RD_NMS_PIXEL_PLUS1 | (_ffi.RD_NMS_SUPPRESS_EQ if force_cpu_semantics else 0)
+        for name, t in (('arm_loc_data', arm_loc_data), ('arm_conf_data', arm_conf_data),
+                        ('odm_loc_data', odm_loc_data), ('odm_conf_data', odm_conf_data)):
+            if not t.is_contiguous() or t.data_ptr() % 16:
+                raise ValueError('plan(): %s must be contiguous and 16-byte aligned (it is referenced, not copied)' % name)
+        args, res, dev, keep = self._prepare(arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data,
+                                             scale, flags, _ffi.RD_ROW_BOX_SCORE, self.keep_top_k,
+                                             workspace=workspace, out=out)
+        torch.cuda.synchronize(dev)      # the workspace reset / pending writers are done before the capture
+        return DetectPlan(args, res, dev, keep)
 
     def forward_python_nms(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data):
         """detection_refinedet.py:67-113.  Returns ``output[B,C,top_k,5]`` rows
