@@ -39,7 +39,9 @@ UNIT = 'images/s'
 SIZE, P, C, BATCH = '512', 16320, 81, 32
 TOP_K, KEEP_TOP_K, CONF_THR, NMS_THR, OBJ_THR = 1000, 500, 0.01, 0.45, 0.01
 BYTES_PER_IMAGE = 4 * P * (4 + 2 + 4 + C)           # SURVEY.md §8d, + 20 B per kept row (added at run time)
-NBUF = 4                                             # rotated input sets (4 x 190 MB > L2)
+NBUF = 8                                             # rotated device input sets (8 x 190 MB >> 126 MB L2)
+NBUF_HOST = 4                                        # rotated pinned host input sets (e2e)
+TRAFFIC_FILE = 'r01_traffic.json'
 
 
 def seed_for(rank, buf=0):
@@ -168,8 +170,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--workload', default='sparse', choices=['sparse', 'dense'])
-    ap.add_argument('--flush', default='write', choices=['write', 'write+read', 'read', 'none'],
-                    help='how L2 is flushed before every timed step (exploration; the default is the contract)')
+    ap.add_argument('--streams', type=int, default=2, help='batches in flight (lanes: stream + workspace + outputs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-secondary', action='store_true')
@@ -214,54 +215,63 @@ def main():
     _ffi.lib()
 
     priors = rd.PriorBox(rd.REFINEDET_ANCHORS[SIZE]).forward().to(dev)
+    S = max(1, args.streams)
     host_sets = [[t.pin_memory() for t in synthetic.detect_inputs(seed_for(rank, i), BATCH, P, C, args.workload)]
-                 for i in range(NBUF)]
+                 for i in range(NBUF_HOST)]
     dev_sets = [[t.to(dev) for t in hs] for hs in host_sets]
+    dev_sets += [[t.to(dev) for t in synthetic.detect_inputs(seed_for(rank, i), BATCH, P, C, args.workload)]
+                 for i in range(NBUF_HOST, NBUF)]
     arm_pass = float((host_sets[0][1][..., 1] > OBJ_THR).float().mean())
     scale = torch.tensor([512.0] * 4, device=dev).reshape(1, 4).expand(BATCH, 4).contiguous()
     det = rd.Detect_RefineDet(C, 512, 0, TOP_K, CONF_THR, NMS_THR, OBJ_THR, KEEP_TOP_K)
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-    flush_rd = torch.empty(64 << 20, dtype=torch.float32, device=dev) if 'read' in args.flush else None
-
-    class _Flush(object):
-        def zero_(self):
-            if 'write' in args.flush:
-                flush_buf.zero_()
-            if flush_rd is not None:
-                flush_rd.sum()
-    flush = _Flush()
     clocks = ClockSampler(local_rank)
 
+    # S lanes = batches in flight: each lane owns a stream, a workspace and output slots; one plan
+    # (CUDA graph of the launch chain, rd_detect_plan_*) per (lane, input set)
+    streams = [torch.cuda.Stream(dev) for _ in range(S)]
+    lanes = [(det.new_workspace(BATCH, P, dev), det.new_outputs(BATCH, dev)) for _ in range(S)]
+    plans = [[det.plan(a[0], a[1], a[2], a[3], priors, scale=scale, workspace=lanes[l][0], out=lanes[l][1])
+              for a in dev_sets] for l in range(S)]
+
     def step(i):
-        a = dev_sets[i % NBUF]
-        return det.detect(a[0], a[1], a[2], a[3], priors, scale=scale)
+        return plans[i % S][i % NBUF].launch(streams[i % S])
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(3, args.warmup)):
+    W = max(3, args.warmup)
+    for i in range(max(W, S * NBUF)):
         res = step(i)
     torch.cuda.synchronize()
-    kept_rows = int(res.counts.sum())
+    kept_rows = int(plans[0][0].launch(streams[0]).counts.sum())
+    # the replayed plan and the direct launch chain must agree (same kernels, same buffers)
+    chk = det.detect(dev_sets[0][0], dev_sets[0][1], dev_sets[0][2], dev_sets[0][3], priors, scale=scale)
+    torch.cuda.synchronize()
+    if not torch.equal(chk.counts, plans[0][0].result.counts):
+        raise RuntimeError('plan replay and direct launch disagree')
 
-    # timed region: K steps, each bracketed by events; L2 flushed (untimed) before every step
+    # ---- timed region: exactly K steps, S batches in flight, one event pair around all of them --------
     K = max(1, args.steps)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    main = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     launches0 = _ffi.launch_count()
     with clocks:
+        e0.record(main)
+        for st in streams:
+            st.wait_event(e0)
         for i in range(K):
-            flush.zero_()
-            starts[i].record()
             step(i)
-            stops[i].record()
+        for st in streams:
+            main.wait_stream(st)
+        e1.record(main)
         barrier()
     launches = _ffi.launch_count() - launches0
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
-    total_ms = float(sum(step_ms))
+    local_total_ms = float(e0.elapsed_time(e1))
+    total_ms = local_total_ms
     if dist is not None:
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -269,26 +279,44 @@ def main():
     ms_per_step = total_ms / K
     value = world * BATCH * K / (total_ms * 1e-3)
 
+    # ---- latency of ONE batch: single stream, L2 flushed (untimed) before every step -------------------
+    KL = min(K, 50)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(KL)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(KL)]
+    with clocks:
+        for i in range(KL):
+            flush_buf.zero_()
+            starts[i].record(main)
+            plans[0][i % NBUF].launch(main)
+            stops[i].record(main)
+        torch.cuda.synchronize()
+    lat = sorted(s_.elapsed_time(e_) for s_, e_ in zip(starts, stops))
+    latency_ms = float(sum(lat)) / KL
+
+    class _Flush(object):
+        def zero_(self):
+            flush_buf.zero_()
     # per-kernel breakdown (separate pass: stage events recorded between the kernels)
-    kern = det.profile_stage(dev_sets, priors, scale, flush, steps=min(K, 20))
+    kern = det.profile_stage(dev_sets, priors, scale, _Flush(), steps=min(K, 20))
     stage_ms_serialised = sum(kern.values())
     bytes_per_launch = BATCH * BYTES_PER_IMAGE + 20 * kept_rows
     peak, peak_src = measured_peak()
-    # The stage is one launch chain (collect -> graph || sort -> resolve -> large) whose kernels overlap
-    # (programmatic dependent launch), so its duration is the event-timed step itself; the per-kernel
-    # figures come from a separate pass with events BETWEEN the launches, which serialises them.
-    local_ms_per_step = float(sum(step_ms)) / K
-    achieved = bytes_per_launch / (local_ms_per_step * 1e-3) / 1e9
+    # The stage is one launch chain (collect -> graph || sort -> resolve -> large), replayed as one CUDA
+    # graph; its kernels overlap (programmatic dependent launch) and so do the chains of the S batches in
+    # flight, so the duration that counts is the event-timed region / K.
+    achieved = bytes_per_launch / (local_total_ms / K * 1e-3) / 1e9
+    achieved_single = bytes_per_launch / (latency_ms * 1e-3) / 1e9
     dominant = max(kern, key=kern.get)
     groups = {'collect_kernel': ['collect_kernel'], 'graph_kernel': ['graph_kernel'],
               'sort_resolve_large_kernels': ['sort_kernel', 'resolve_kernel', 'nms_large_kernel']}
     traffic, traffic_src = None, None
     try:                                   # DRAM bytes per launch from the committed ncu --set full capture
-        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', TRAFFIC_FILE)) as f:
             tj = json.load(f)
-        per_group = {g: sum(tj['kernels'][k]['traffic_bytes'] for k in ks) for g, ks in groups.items()}
+        per_group = {g: sum(tj['kernels'][k]['traffic_bytes'] for k in ks if k in tj['kernels'])
+                     for g, ks in groups.items()}
         traffic = tj['stage_traffic_bytes']
-        traffic_src = {'file': 'profiles/r01_traffic.json', 'what': 'dram__bytes_read.sum + dram__bytes_write.sum of '
+        traffic_src = {'file': 'profiles/' + TRAFFIC_FILE, 'what': 'dram__bytes_read.sum + dram__bytes_write.sum of '
                        'the whole launch chain, one ncu --set full capture', 'per_kernel_group': per_group}
     except Exception:
         pass
@@ -296,30 +324,39 @@ def main():
                 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                 'kernel': 'detect stage launch chain (dominant group: %s)' % dominant,
                 'algorithmic_bytes_per_launch': bytes_per_launch,
-                'stage_ms': local_ms_per_step, 'stage_ms_serialised': stage_ms_serialised,
+                'stage_ms': local_total_ms / K, 'batches_in_flight': S,
+                'single_batch': {'ms': latency_ms, 'median_ms': lat[KL // 2], 'achieved': achieved_single,
+                                 'frac': achieved_single / peak,
+                                 'how': 'one stream, 512 MiB memset (L2 flush, untimed) before every step, %d steps' % KL},
+                'stage_ms_serialised': stage_ms_serialised,
                 'kernels_ms': kern, 'kernel_share': {k: v / stage_ms_serialised for k, v in kern.items()},
-                'note': 'achieved = stage bytes (SURVEY 8d: 4*P*(10+C) B/image + 20 B/kept row) / event-timed device '
-                        'time of the stage (all its kernels, launch gaps included); ARM-filtered anchors (%.1f%% here) '
-                        'are skipped, so DRAM traffic is far below the algorithmic bytes: the stage is latency-bound'
-                        % (100 * (1 - arm_pass))}
+                'note': 'achieved = stage bytes (SURVEY 8d: 4*P*(10+C) B/image + 20 B/kept row) / (event-timed region '
+                        '/ K steps), %d batches in flight; ARM-filtered anchors (%.1f%% here) are skipped, so DRAM '
+                        'traffic is far below the algorithmic bytes: the stage is issue/latency-bound, not '
+                        'bandwidth-bound' % (S, 100 * (1 - arm_pass))}
 
-    # e2e: host (pinned) inputs -> H2D -> kernels -> pack -> D2H (counts + packed rows)
+    # e2e: host (pinned) inputs -> kernels read them over PCIe -> pack -> rows land in pinned host memory
     e2e = None
     if not args.no_e2e:
-        e2e_steps = min(K, 20)
-        stage = [torch.empty_like(t, device=dev) for t in host_sets[0]]
+        e2e_steps = min(K, 40)
         full_bytes = sum(t.numel() * t.element_size() for t in host_sets[0])
+        pipe = rd.DetectHostPipeline(det, priors, scale, BATCH, lanes=S)
 
-        def run_e2e(zero_copy):
+        def run_pipe():
             d2h = 0
-            for i in range(2):
-                det.detect_host(host_sets[i % NBUF], priors, scale, stage, zero_copy=zero_copy)
+            for i in range(S * NBUF_HOST):                        # plans of every (lane, host set)
+                pipe.result(pipe.submit(host_sets[i % NBUF_HOST]))
             barrier()
             with clocks:
                 t0 = time.perf_counter()
+                pending = []
                 for i in range(e2e_steps):
-                    counts_h, rows_h = det.detect_host(host_sets[i % NBUF], priors, scale, stage, zero_copy=zero_copy)
-                    d2h = counts_h.numel() * 4 + rows_h.numel() * 4
+                    pending.append(pipe.submit(host_sets[i % NBUF_HOST]))
+                    if len(pending) == S:
+                        counts_h, rows_h = pipe.result(pending.pop(0))
+                        d2h = counts_h.numel() * 4 + rows_h.numel() * 4 + 4
+                while pending:
+                    counts_h, rows_h = pipe.result(pending.pop(0))
                 barrier()
                 sec = time.perf_counter() - t0
             if dist is not None:
@@ -328,19 +365,36 @@ def main():
                 sec = float(t.item())
             return sec, d2h
 
-        copy_s, d2h = run_e2e(False)
-        zc_s, d2h = run_e2e(True)
+        def run_serial(zero_copy):
+            stage = [torch.empty_like(t, device=dev) for t in host_sets[0]]
+            for i in range(2):
+                det.detect_host(host_sets[i % NBUF_HOST], priors, scale, stage, zero_copy=zero_copy)
+            barrier()
+            n = min(e2e_steps, 10)
+            t0 = time.perf_counter()
+            for i in range(n):
+                det.detect_host(host_sets[i % NBUF_HOST], priors, scale, stage, zero_copy=zero_copy)
+            barrier()
+            return (time.perf_counter() - t0) / n
+
+        pipe_s, d2h = run_pipe()
+        serial_zc = run_serial(True)
+        serial_copy = run_serial(False)
         # bytes the zero-copy path pulls over PCIe: arm_conf in full + per ARM-passing anchor its two loc
         # vectors and its odm_conf row, rounded up to the 32-byte sectors they touch
         n_pass = int((host_sets[0][1][..., 1] > OBJ_THR).sum())
         row_sectors = (C * 4 + 31) // 32 + 1
         zc_bytes = host_sets[0][1].numel() * 4 + n_pass * (2 * 32 + row_sectors * 32)
-        e2e = {'value': world * BATCH * e2e_steps / zc_s, 'unit': UNIT, 'h2d_bytes_per_step': zc_bytes,
-               'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'ms_per_step': 1e3 * zc_s / e2e_steps,
-               'mode': 'zero-copy: kernels read the pinned host tensors over PCIe, only rows of ARM-passing '
-                       'anchors cross the bus (h2d_bytes_per_step is that traffic; the tensors hold %d B)' % full_bytes,
-               'staged_copy': {'value': world * BATCH * e2e_steps / copy_s, 'ms_per_step': 1e3 * copy_s / e2e_steps,
-                               'h2d_bytes_per_step': full_bytes}}
+        e2e = {'value': world * BATCH * e2e_steps / pipe_s, 'unit': UNIT, 'h2d_bytes_per_step': zc_bytes,
+               'd2h_bytes_per_step': d2h, 'steps': e2e_steps, 'ms_per_step': 1e3 * pipe_s / e2e_steps,
+               'batches_in_flight': S,
+               'mode': 'DetectHostPipeline: pinned host inputs read by the kernels over PCIe (only rows of ARM-passing '
+                       'anchors cross the bus: h2d_bytes_per_step; the tensors hold %d B), packed rows stored '
+                       'straight into pinned host memory, every result read on the host' % full_bytes,
+               'serial_zero_copy': {'value': world * BATCH / serial_zc, 'ms_per_step': 1e3 * serial_zc},
+               'serial_staged_copy': {'value': world * BATCH / serial_copy, 'ms_per_step': 1e3 * serial_copy,
+                                      'h2d_bytes_per_step': full_bytes}}
+        del pipe
 
     # secondary (reported, not the headline): the other generator of SURVEY.md §8d on the same config
     secondary = None
@@ -354,7 +408,7 @@ def main():
         s_ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_sec)]
         e_ev = [torch.cuda.Event(enable_timing=True) for _ in range(n_sec)]
         for i in range(n_sec):
-            flush.zero_()
+            flush_buf.zero_()
             s_ev[i].record()
             r2 = det.detect(o_dev[0], o_dev[1], o_dev[2], o_dev[3], priors, scale=scale)
             e_ev[i].record()
@@ -376,10 +430,13 @@ def main():
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K,
-                'warmup': max(3, args.warmup), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+                'warmup': W, 'ms_per_step': ms_per_step, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': dict(config, l2='flushed (512 MiB memset) before every timed step; %d rotated input '
-                                          'sets' % NBUF, arm_pass_fraction=arm_pass, kept_rows_per_step=kept_rows),
+                'config': dict(config, l2='inputs larger than L2: every step reads its own 190 MB input set, %d sets '
+                                          '(1.5 GB) rotated; no flush inside the timed region' % NBUF,
+                               batches_in_flight=S, launch='one CUDA-graph replay per step (rd_detect_plan_launch)',
+                               arm_pass_fraction=arm_pass, kept_rows_per_step=kept_rows),
+                'latency_ms_per_batch': latency_ms,
                 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'secondary': secondary,
                 'gpu_launches': int(launches),
                 'clocks': clocks.summary()}

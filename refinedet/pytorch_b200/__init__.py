@@ -9,10 +9,11 @@ loudly if it is missing (``python -m refinedet.pytorch_b200.build`` builds it).
 """
 from . import _ffi  # noqa: F401
 from .layers import box_utils  # noqa: F401
-from .layers.functions.detection_refinedet import Detect_RefineDet, Detections  # noqa: F401
+from .layers.functions.detection_refinedet import (Detect_RefineDet, Detections, DetectPlan,  # noqa: F401
+                                                         DetectHostPipeline)  # noqa: F401
 from .layers.functions.prior_box import PriorBox, REFINEDET_ANCHORS  # noqa: F401
 from .layers.modules.refinedet_multibox_loss import RefineDetMultiBoxLoss  # noqa: F401
 from .utils import nms_wrapper  # noqa: F401
 
-__all__ = ['Detect_RefineDet', 'Detections', 'RefineDetMultiBoxLoss', 'PriorBox', 'REFINEDET_ANCHORS',
+__all__ = ['Detect_RefineDet', 'Detections', 'DetectPlan', 'DetectHostPipeline', 'RefineDetMultiBoxLoss', 'PriorBox', 'REFINEDET_ANCHORS',
            'box_utils', 'nms_wrapper']

@@ -102,6 +102,76 @@ class DetectPlan(object):
             pass
 
 
+class DetectHostPipeline(object):
+    """End-to-end detect stage for HOST inputs with several batches in flight.
+
+    Each lane owns a stream, a workspace, device output slots and pinned host result buffers.
+    ``submit(host_inputs)`` (pinned ``arm_loc, arm_conf, odm_loc, odm_conf``) replays the lane's plan —
+    the kernels read the pinned tensors over PCIe (only rows of ARM-passing anchors cross the bus), the
+    pack kernels store the rows straight into pinned host memory — and returns a ticket at once;
+    ``result(ticket)`` waits for that batch only and returns CPU tensors ``(counts[B,C], rows[total,5])``
+    (views of the lane's buffers, valid until the lane is reused ``lanes`` submits later).  With two
+    lanes the PCIe reads of batch i+1 overlap the kernels and the result write-back of batch i."""
+
+    def __init__(self, det, prior_data, scale, B, lanes=2):
+        self.det, self.priors, self.B = det, require_cuda_f32(prior_data, 'prior_data'), B
+        dev = self.priors.device
+        self.device = dev
+        C = det.num_classes
+        max_out = max(1, min(int(det.keep_top_k), int(det.top_k)))
+        self.scale = None
+        if scale is not None:
+            sc = torch.as_tensor(scale, dtype=torch.float32).to(dev)
+            self.scale = sc.reshape(1, 4).expand(B, 4).contiguous() if sc.numel() == 4 else sc.reshape(B, 4).contiguous()
+        self.lanes = []
+        for _ in range(lanes):
+            self.lanes.append({
+                'stream': torch.cuda.Stream(dev),
+                'ws': det.new_workspace(B, self.priors.shape[0], dev),
+                'out': det.new_outputs(B, dev),
+                'dev_offsets': torch.empty(B * C + 1, dtype=torch.int32, device=dev),
+                'host_offsets': torch.empty(B * C + 1, dtype=torch.int32).pin_memory(),
+                'host_counts': torch.empty(B, C, dtype=torch.int32).pin_memory(),
+                'host_rows': torch.empty(B * C * max_out, 5, dtype=torch.float32).pin_memory(),
+                'done': torch.cuda.Event(),
+                'plans': {},
+            })
+        torch.cuda.synchronize(dev)
+        self._next = 0
+
+    def submit(self, host_inputs):
+        lane = self.lanes[self._next % len(self.lanes)]
+        self._next += 1
+        key = tuple(t.data_ptr() for t in host_inputs)
+        plan = lane['plans'].get(key)
+        if plan is None:
+            for t in host_inputs:
+                if t.is_cuda or not t.is_pinned() or t.dtype != torch.float32 or not t.is_contiguous():
+                    raise RuntimeError('DetectHostPipeline needs contiguous pinned float32 host tensors')
+            args, res, dev, keep = self.det._prepare(
+                host_inputs[0], host_inputs[1], host_inputs[2], host_inputs[3], self.priors, self.scale,
+                _ffi.RD_NMS_PIXEL_PLUS1, _ffi.RD_ROW_BOX_SCORE, self.det.keep_top_k, host_mapped=True,
+                workspace=lane['ws'], out=lane['out'])
+            torch.cuda.synchronize(self.device)
+            plan = lane['plans'][key] = DetectPlan(args, res, dev, keep)
+        st = lane['stream']
+        res = plan.launch(st)
+        B, C, max_out, _ = res.dets.shape
+        with torch.cuda.device(self.device), torch.cuda.stream(st):
+            check(lib().rd_pack_detections(ptr(res.counts), ptr(res.dets), B, C, max_out, ptr(lane['dev_offsets']),
+                                           ptr(lane['host_rows']), lane['host_rows'].shape[0], st.cuda_stream),
+                  'rd_pack_detections')
+            lane['host_counts'].copy_(res.counts, non_blocking=True)
+            lane['host_offsets'].copy_(lane['dev_offsets'], non_blocking=True)
+            lane['done'].record(st)
+        return lane
+
+    def result(self, ticket):
+        ticket['done'].synchronize()
+        total = int(ticket['host_offsets'][-1])
+        return ticket['host_counts'], ticket['host_rows'][:total]
+
+
 class Detect_RefineDet(object):
     """At test time, the final layer of RefineDet: ARM-objectness filter, two-stage decode
     and (in ``detect`` / ``forward_python_nms``) per-class threshold, top-k and NMS.
