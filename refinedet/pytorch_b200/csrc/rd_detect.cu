@@ -5,17 +5,19 @@
 //
 // Kernels
 //   detect_forward_kernel   a3: ARM filter + two-stage decode, dense boxes/scores, in-place zeroing
-//   collect_kernel          K1: one CTA per (image, slice of 1024 anchors).  ARM filter, decode of the
-//                           passing anchors, per-class candidate sub-lists.  Slots are reserved with
-//                           SHARED-memory atomics (the CTA owns its sub-list), so there is no global
-//                           atomic and nothing to reset between calls.  odm_conf / loc rows of
-//                           ARM-filtered anchors are never fetched: traffic scales with the pass rate.
-//   graph_kernel            KG: 16 CTAs per image: exact suppression graph between the ARM-passing anchors
-//                           of an image (class independent), adjacency lists per anchor
-//   sort_kernel             K2a: one 96-thread CTA per (image, class) with <= 256 candidates: key sort;
-//                           runs beside graph_kernel (programmatic dependent launch)
-//   resolve_kernel          K2b+K3: graph look-ups through a smem hash, dependency resolution, rows
-//   nms_large_kernel        persistent CTAs draining the queue (radix select when n > top_k)
+//   collect_kernel          K1: one CTA per (image, slice of 1024 anchors).  ARM filter; the ARM-passing
+//                           anchors of an image become its NODES, numbered in anchor order.  Per node:
+//                           decoded + scaled box, anchor, bin range and bin marks (graph input), and its
+//                           odm_conf row transposed through shared memory into the class-major score
+//                           matrix nsc[image][class][node].  odm_conf / loc rows of ARM-filtered anchors
+//                           are never fetched: traffic scales with the pass rate.  No atomics.
+//   graph_kernel            KG: 16 CTAs per image: exact suppression graph between the nodes of an image
+//                           (class independent), adjacency lists per node
+//   nms_small_kernel        K2: one CTA per (image, class): scan the class's score row, sort the candidates
+//                           (beside graph_kernel: programmatic dependent launch), then resolve the
+//                           suppression through the graph and emit rows
+//   nms_large_kernel        persistent CTAs draining the queue of problems without a graph or with more
+//                           than 256 candidates (radix select when n > top_k, own bin tables)
 //   nms_single_kernel       stand-alone problem (rd_nms / rd_nms_host)
 //   pack kernels            slot layout -> packed rows
 #include "rd_nms_core.cuh"
@@ -39,51 +41,46 @@ __device__ __forceinline__ unsigned long long rd_gtime() { unsigned long long t;
 #define RD_TMIN(slot) do {} while (0)
 #endif
 constexpr int kCollectThreads = 256;
-constexpr int kSliceAnchors = 1024;   // anchors per collect CTA = capacity of one candidate sub-list
+constexpr int kSliceAnchors = 1024;   // anchors per collect CTA
 #ifndef RD_LARGE_THREADS
 #define RD_LARGE_THREADS 512
 #endif
 constexpr int kLargeThreads = RD_LARGE_THREADS;
 
 // ---------------------------------------------------------------------------------------
-// workspace of the fused stage.  The control block (header, nnodes, gtab) must be zero when a call
+// workspace of the fused stage.  The control block (header, gtab) must be zero when a call
 // starts: rd_detect_workspace_reset zeroes it once, every call leaves it zero again (collect clears
-// the queue header, resolve_kernel's class-0 CTAs clear nnodes / gtab of their image).
+// the queue header, nms_small_kernel's class-0 CTAs clear gtab of their image).
 //   header u32 [64]               : [0] = number of queued large problems
-//   nnodes int [B]                : graph nodes (= ARM-passing anchors) of every image
-//   gtab   u32 [B][4][32][33]     : start/end bin marks of the nodes (OR-ed in by collect)
+//   gtab   u32 [B][4][32][33]     : start/end bin marks of the first 1024 nodes (OR-ed in by collect)
+//   nnodes int [B]                : nodes (= ARM-passing anchors) of every image (written by collect)
 //   flag   int [B]                : 1 = the image has no suppression graph (too many nodes / degree overflow)
 //   queue  int [B*C]              : (image,class) problems routed to nms_large_kernel
-//   cnt    int [B*C*S]            : candidate count of every sub-list, S = ceil(P / 1024)
-//   sn     int [B*C], skeys u64 [B*C][256] : size and sorted keys of every small problem (sort_kernel)
-//   nbox   f4  [B][1024], nanc int [B][1024], ncr u32 [B][1024] : node box / anchor / bin range
-//   adjn   int [B*P]              : graph degree of every passing anchor (collect zeroes, graph counts)
-//   adj    u32 [B*P*8]            : adjacency lists (anchor indices)
-//   boxes  f4  [B*P]              : decoded boxes of ARM-passing anchors
-//   cand   u64 [B*C*S*1024]       : candidate keys, sub-list (b,c,s) written by collect CTA (s,b)
+//   nsc    f32 [B][C][Pn]         : class-major scores of the nodes, Pn = P rounded up to 32
+//   nbox   f4  [B][P], nanc int [B][P] : node box (scaled) / anchor
+//   ncr    u32 [B][1024]          : bin range of the first 1024 nodes
+//   adjn   int [B][1024]          : graph degree of every node (collect zeroes, graph counts)
+//   adj    u16 [B][1024][8]       : adjacency lists (node indices)
+//   cand   u64 [B*C][P]           : candidate keys of the problems nms_large_kernel handles
 // ---------------------------------------------------------------------------------------
-constexpr int kGraphNodes = 1024;       // images with more ARM-passing anchors fall back to per-problem bins
 constexpr int kGraphW = kGraphNodes / 32;
 constexpr int kGraphWS = kGraphW + 1;
 constexpr int kGtabWords = 4 * kCols * kGraphWS;
 
 struct DetectWs {
     uint32_t* header;
-    int* nnodes;
     uint32_t* gtab;
+    int* nnodes;
     int* flag;
     int* queue;
-    int* cnt;
-    int* sn;
-    unsigned long long* skeys;
+    float* nsc;
     float4* nbox;
     int* nanc;
     uint32_t* ncr;
     int* adjn;
-    uint32_t* adj;
-    float4* boxes;
+    uint4* adj;
     unsigned long long* cand;
-    int S;
+    int S, Pn;
     size_t ctrl_bytes;
     size_t total;
 };
@@ -93,22 +90,20 @@ static DetectWs carve_ws(void* base, int B, int P, int C) {
     size_t o = 0;
     unsigned char* p = static_cast<unsigned char*>(base);
     w.S = (P + kSliceAnchors - 1) / kSliceAnchors;
+    w.Pn = (P + 31) & ~31;
     w.header = reinterpret_cast<uint32_t*>(p + o);             o += 256;
-    w.nnodes = reinterpret_cast<int*>(p + o);                  o += align_up((size_t)B * 4, 256);
     w.gtab = reinterpret_cast<uint32_t*>(p + o);               o += align_up((size_t)B * kGtabWords * 4, 256);
     w.ctrl_bytes = o;
+    w.nnodes = reinterpret_cast<int*>(p + o);                  o += align_up((size_t)B * 4, 256);
     w.flag = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * 4, 256);
     w.queue = reinterpret_cast<int*>(p + o);                   o += align_up((size_t)B * C * 4, 256);
-    w.cnt = reinterpret_cast<int*>(p + o);                     o += align_up((size_t)B * C * w.S * 4, 256);
-    w.sn = reinterpret_cast<int*>(p + o);                      o += align_up((size_t)B * C * 4, 256);
-    w.skeys = reinterpret_cast<unsigned long long*>(p + o);    o += align_up((size_t)B * C * kSmallCap * 8, 256);
-    w.nbox = reinterpret_cast<float4*>(p + o);                 o += align_up((size_t)B * kGraphNodes * 16, 256);
-    w.nanc = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * kGraphNodes * 4, 256);
+    w.nsc = reinterpret_cast<float*>(p + o);                   o += align_up((size_t)B * C * w.Pn * 4, 256);
+    w.nbox = reinterpret_cast<float4*>(p + o);                 o += align_up((size_t)B * P * 16, 256);
+    w.nanc = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * P * 4, 256);
     w.ncr = reinterpret_cast<uint32_t*>(p + o);                o += align_up((size_t)B * kGraphNodes * 4, 256);
-    w.adjn = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * P * 4, 256);
-    w.adj = reinterpret_cast<uint32_t*>(p + o);                o += align_up((size_t)B * P * kAdjDeg * 4, 256);
-    w.boxes = reinterpret_cast<float4*>(p + o);                o += align_up((size_t)B * P * 16, 256);
-    w.cand = reinterpret_cast<unsigned long long*>(p + o);     o += align_up((size_t)B * C * w.S * kSliceAnchors * 8, 256);
+    w.adjn = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * kGraphNodes * 4, 256);
+    w.adj = reinterpret_cast<uint4*>(p + o);                   o += align_up((size_t)B * kGraphNodes * 16, 256);
+    w.cand = reinterpret_cast<unsigned long long*>(p + o);     o += align_up((size_t)B * C * P * 8, 256);
     w.total = o;
     return w;
 }
@@ -181,8 +176,12 @@ detect_forward_kernel(const float4* __restrict__ arm_loc, const float2* __restri
 }
 
 // ---------------------------------------------------------------------------------------
-// K1: ARM filter + decode + candidate collection
+// K1: ARM filter + decode + node registration + class-major score matrix
 // grid = (S, B); CTA (s, b) owns anchors [s*1024, s*1024 + 1024) of image b: 8 warps x 128 anchors.
+// The node index of a passing anchor is its rank among the passing anchors of the image in anchor
+// order (so "lower node first" == "lower anchor first", the documented tie rule): the CTA counts the
+// passing anchors of the preceding slices itself (arm_conf is 8 B / anchor and L2 resident), which
+// keeps the kernel free of atomics, inter-CTA ordering and state to reset.
 // ---------------------------------------------------------------------------------------
 constexpr int kChunks = kSliceAnchors / (kCollectThreads / 32) / 32;   // 32-anchor chunks per warp = 4
 #ifndef RD_ROW_BATCH
@@ -190,14 +189,16 @@ constexpr int kChunks = kSliceAnchors / (kCollectThreads / 32) / 32;   // 32-anc
 #endif
 constexpr int kRowBatch = RD_ROW_BATCH;                                // odm_conf rows in flight per warp
 constexpr int kMaxClasses = 128;
+constexpr int kTileRows = 64;                                          // nodes per transposition tile
+constexpr int kRowsPerWarp = kTileRows / (kCollectThreads / 32);       // 8
 
 struct GraphOut {            // what collect contributes to the per-image suppression graph
     int* nnodes;             // [B]
     uint32_t* gtab;          // [B][kGtabWords]
-    float4* nbox;            // [B][kGraphNodes] scaled boxes
-    int* nanc;               // [B][kGraphNodes]
+    float4* nbox;            // [B][P] scaled boxes
+    int* nanc;               // [B][P]
     uint32_t* ncr;           // [B][kGraphNodes]
-    int* adjn;               // [B*P]
+    int* adjn;               // [B][kGraphNodes]
     int* img_flag;           // [B]
     const float* img_scale;  // [B,4] or null
     float thr;
@@ -207,20 +208,18 @@ struct GraphOut {            // what collect contributes to the per-image suppre
 __global__ void __launch_bounds__(kCollectThreads)
 collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ arm_conf,
                const float4* __restrict__ odm_loc, const float* __restrict__ odm_conf,
-               const float4* __restrict__ priors, int P, int C, int S, float obj_thre,
-               float conf_thresh, float v0, float v1, float4* __restrict__ boxes_ws, int* __restrict__ cnt,
-               unsigned long long* __restrict__ cand, uint32_t* header, GraphOut GO) {
-    __shared__ unsigned char s_list[kCollectThreads / 32][32 * kChunks];   // passing anchors of each warp
-    __shared__ int s_cnt[kMaxClasses];
+               const float4* __restrict__ priors, int P, int C, int S, int Pn, float obj_thre,
+               float v0, float v1, float* __restrict__ nsc, uint32_t* header, GraphOut GO) {
+    __shared__ float s_tile[kMaxClasses][kTileRows + 1];               // [class][node of the tile], padded
+    __shared__ unsigned short s_flat[kSliceAnchors];                   // passing anchors of the slice, anchor order
     __shared__ int s_wpass[kCollectThreads / 32];
-    __shared__ int s_base;
+    __shared__ int s_before[kCollectThreads / 32];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int s = blockIdx.x, b = blockIdx.y;
     RD_TMIN(25);
     if (s == 0 && b == 0 && threadIdx.x == 0) header[0] = 0;          // queue of the large-NMS kernel
     if (s == 0 && threadIdx.x == 0) GO.img_flag[b] = 0;
-    for (int c = threadIdx.x; c < C; c += kCollectThreads) s_cnt[c] = 0;
     const int a0 = s * kSliceAnchors + wib * (32 * kChunks);          // first anchor of this warp
     const size_t img = (size_t)b * P;
     // 1. ARM filter for 32*kChunks anchors; all loads issued before the first use
@@ -230,99 +229,125 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
         const int a = a0 + ch * 32 + lane;
         obj[ch] = (a < P) ? ldg_stream2(arm_conf + img + a).y : -INFINITY;
     }
+    //    ... and the number of passing anchors in the preceding slices of the image
+    int before = 0;
+    {
+        const int nprev = s * kSliceAnchors;                           // multiple of kCollectThreads * 4
+        for (int a = threadIdx.x; a < nprev; a += kCollectThreads * 4) {
+            float o4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o4[k] = __ldg(arm_conf + img + a + k * kCollectThreads).y;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) before += !(o4[k] <= obj_thre) ? 1 : 0;
+        }
+        before = __reduce_add_sync(kFullMask, before);
+    }
+    unsigned pmask[kChunks];
     int npass = 0;
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
         const int a = a0 + ch * 32 + lane;
         const bool pass = (a < P) && !(obj[ch] <= obj_thre);           // kept unless arm_conf[...,1] <= thre (:41)
-        const unsigned mask = __ballot_sync(kFullMask, pass);
-        if (pass) s_list[wib][npass + __popc(mask & ((1u << lane) - 1u))] = (unsigned char)(ch * 32 + lane);
-        npass += __popc(mask);
+        pmask[ch] = __ballot_sync(kFullMask, pass);
+        npass += __popc(pmask[ch]);
     }
-    if (lane == 0) s_wpass[wib] = npass;
+    if (lane == 0) { s_wpass[wib] = npass; s_before[wib] = before; }
     __syncthreads();
-    // graph nodes: reserve a contiguous range of the image's node array for this CTA
-    int woff = 0, tot = 0;
+    int woff = 0, tot = 0, base = 0;
 #pragma unroll
-    for (int w = 0; w < kCollectThreads / 32; ++w) { if (w < wib) woff += s_wpass[w]; tot += s_wpass[w]; }
-    if (threadIdx.x == 0) s_base = tot ? atomicAdd(&GO.nnodes[b], tot) : 0;
-    // decode inputs of the first 32 passing anchors: issue the loads now, use them after the row phase
+    for (int w = 0; w < kCollectThreads / 32; ++w) {
+        if (w < wib) woff += s_wpass[w];
+        tot += s_wpass[w];
+        base += s_before[w];
+    }
+    {
+        int pos = woff;
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) {
+            if ((pmask[ch] >> lane) & 1u)
+                s_flat[pos + __popc(pmask[ch] & ((1u << lane) - 1u))] = (unsigned short)(wib * (32 * kChunks) + ch * 32 + lane);
+            pos += __popc(pmask[ch]);
+        }
+    }
+    if (s == S - 1 && threadIdx.x == 0) GO.nnodes[b] = base + tot;
+    __syncthreads();
+    // decode inputs of the first kCollectThreads nodes: issue the loads now, use them after the row phase
     float4 pre_al = make_float4(0.f, 0.f, 0.f, 0.f), pre_ol = pre_al, pre_pr = pre_al;
-    if (lane < npass) {
-        const int a = a0 + s_list[wib][lane];
+    if ((int)threadIdx.x < tot) {
+        const int a = s * kSliceAnchors + s_flat[threadIdx.x];
         pre_al = ldg_stream4(arm_loc + img + a);
         pre_ol = ldg_stream4(odm_loc + img + a);
         pre_pr = __ldg(priors + a);
     }
-    // 2. odm_conf rows of the passing anchors: lane = class, kRowBatch rows in flight
+    // 2. odm_conf rows of the nodes: lane = class, kRowBatch rows in flight per warp, transposed through
+    //    shared memory so that nsc[b][c][base + t ...] is written in runs of consecutive nodes
     const int nseg = (C + 31) >> 5;          // <= 4 (C <= 128)
-    unsigned long long* cand_b = cand + ((size_t)b * C * S + s) * kSliceAnchors;    // + c * S * 1024 per class
-    for (int r0 = 0; r0 < npass; r0 += kRowBatch) {
-        float v[kRowBatch][4];
-        int ai[kRowBatch];
+    float* nsc_b = nsc + (size_t)b * C * Pn + base;
+    for (int t0 = 0; t0 < tot; t0 += kTileRows) {
+        const int rows_here = min(kTileRows, tot - t0);
 #pragma unroll
-        for (int k = 0; k < kRowBatch; ++k) {
-            ai[k] = (r0 + k < npass) ? a0 + s_list[wib][r0 + k] : -1;
-            const float* row = odm_conf + (img + (ai[k] < 0 ? 0 : ai[k])) * C;
+        for (int k0 = 0; k0 < kRowsPerWarp; k0 += kRowBatch) {
+            const int rl0 = wib * kRowsPerWarp + k0;               // row of the tile
+            if (rl0 >= rows_here) break;
+            float v[kRowBatch][4];
 #pragma unroll
-            for (int sgm = 0; sgm < 4; ++sgm) {
-                const int c = sgm * 32 + lane;
-                v[k][sgm] = (ai[k] >= 0 && sgm < nseg && c < C) ? ldg_stream1(row + c) : -INFINITY;
+            for (int k = 0; k < kRowBatch; ++k) {
+                const bool rv = rl0 + k < rows_here;
+                const int a = s * kSliceAnchors + (rv ? s_flat[t0 + rl0 + k] : 0);
+                const float* row = odm_conf + (img + a) * C;
+#pragma unroll
+                for (int sgm = 0; sgm < 4; ++sgm) {
+                    const int c = sgm * 32 + lane;
+                    v[k][sgm] = (rv && sgm < nseg && c < C) ? ldg_stream1(row + c) : 0.f;
+                }
             }
-        }
 #pragma unroll
-        for (int k = 0; k < kRowBatch; ++k) {
-            if (ai[k] < 0) continue;
+            for (int k = 0; k < kRowBatch; ++k) {
 #pragma unroll
-            for (int sgm = 0; sgm < 4; ++sgm) {
-                const int c = sgm * 32 + lane;
-                // class 0 = background, never evaluated (eval_refinedet_coco.py:213)
-                if (sgm < nseg && c < C && c != 0 && v[k][sgm] > conf_thresh) {
-                    const int slot = atomicAdd(&s_cnt[c], 1);          // shared-memory atomic, < 1024 by construction
-                    cand_b[(size_t)c * S * kSliceAnchors + slot] = make_key(v[k][sgm], (uint32_t)ai[k]);
+                for (int sgm = 0; sgm < 4; ++sgm) {
+                    const int c = sgm * 32 + lane;
+                    if (sgm < nseg && c < C) s_tile[c][rl0 + k] = v[k][sgm];
                 }
             }
         }
+        __syncthreads();
+        // class 0 = background, never evaluated (eval_refinedet_coco.py:213)
+        for (int task = 2 + wib; task < 2 * C; task += kCollectThreads / 32) {
+            const int c = task >> 1, r = (task & 1) * 32 + lane;
+            if (r < rows_here) nsc_b[(size_t)c * Pn + t0 + r] = s_tile[c][r];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += kCollectThreads) cnt[((size_t)b * C + c) * S + s] = s_cnt[c];
-    // 3. decode the passing anchors, one per lane; register them as graph nodes: scaled box, bin range
-    //    (fixed bins over the image extent: any monotone binning keeps the cull conservative) and the
-    //    start / end marks OR-ed into the image's table
-    const int base = s_base;
-    const bool graph_ok = base + tot <= kGraphNodes;
-    if (!graph_ok && threadIdx.x == 0 && tot) GO.img_flag[b] = 1;
+    // 3. decode the nodes, one per thread: scaled box, anchor, bin range (fixed bins over the image
+    //    extent: any monotone binning keeps the cull conservative) and the start / end marks OR-ed
+    //    into the image's table
     const bool pixel = (GO.flags & RD_NMS_PIXEL_PLUS1) != 0;
     const bool has_scale = GO.img_scale != nullptr;
     const float4 scale = has_scale ? __ldg(reinterpret_cast<const float4*>(GO.img_scale) + b) : make_float4(1.f, 1.f, 1.f, 1.f);
     const bool force_full = cull_disabled(GO.thr, GO.flags);
     const float invx = scale.x > 0.f ? (float)kCols / scale.x : 0.f;
     const float invy = scale.y > 0.f ? (float)kCols / scale.y : 0.f;
-    for (int r0 = 0; r0 < npass; r0 += 32) {
-        const int r = r0 + lane;
-        if (r < npass) {
-            const int a = a0 + s_list[wib][r];
-            float4 bx = r0 == 0 ? refine_decode(pre_al, pre_ol, pre_pr, v0, v1)
-                                : refine_decode(ldg_stream4(arm_loc + img + a), ldg_stream4(odm_loc + img + a),
-                                                __ldg(priors + a), v0, v1);
-            boxes_ws[img + a] = bx;
-            GO.adjn[img + a] = 0;                    // degree counter of the suppression graph
-            if (graph_ok) {
-                if (has_scale) { bx.x *= scale.x; bx.y *= scale.y; bx.z *= scale.z; bx.w *= scale.w; }
-                const int i = base + woff + r;
-                const uint32_t cr = bin_range(bx.x, bx.y, bx.z, bx.w, pixel, force_full, 0.f, invx, 0.f, invy);
-                GO.nbox[(size_t)b * kGraphNodes + i] = bx;
-                GO.nanc[(size_t)b * kGraphNodes + i] = a;
-                GO.ncr[(size_t)b * kGraphNodes + i] = cr;
-                const int ax = cr & 255u, bxx = (cr >> 8) & 255u, ay = (cr >> 16) & 255u, by = cr >> 24;
-                const uint32_t bit = 1u << (i & 31);
-                const int w = i >> 5;
-                uint32_t* tab = GO.gtab + (size_t)b * kGtabWords;
-                atomicOr(&tab[(0 * kCols + ax) * kGraphWS + w], bit);
-                if (bxx + 1 < kCols) atomicOr(&tab[(1 * kCols + bxx + 1) * kGraphWS + w], bit);
-                atomicOr(&tab[(2 * kCols + ay) * kGraphWS + w], bit);
-                if (by + 1 < kCols) atomicOr(&tab[(3 * kCols + by + 1) * kGraphWS + w], bit);
-            }
+    for (int t = threadIdx.x; t < tot; t += kCollectThreads) {
+        const int a = s * kSliceAnchors + s_flat[t];
+        float4 bx = t < kCollectThreads ? refine_decode(pre_al, pre_ol, pre_pr, v0, v1)
+                                        : refine_decode(ldg_stream4(arm_loc + img + a), ldg_stream4(odm_loc + img + a),
+                                                        __ldg(priors + a), v0, v1);
+        if (has_scale) { bx.x *= scale.x; bx.y *= scale.y; bx.z *= scale.z; bx.w *= scale.w; }
+        const int i = base + t;
+        GO.nbox[img + i] = bx;
+        GO.nanc[img + i] = a;
+        if (i < kGraphNodes) {
+            const uint32_t cr = bin_range(bx.x, bx.y, bx.z, bx.w, pixel, force_full, 0.f, invx, 0.f, invy);
+            GO.ncr[(size_t)b * kGraphNodes + i] = cr;
+            GO.adjn[(size_t)b * kGraphNodes + i] = 0;            // degree counter of the suppression graph
+            const int ax = cr & 255u, bxx = (cr >> 8) & 255u, ay = (cr >> 16) & 255u, by = cr >> 24;
+            const uint32_t bit = 1u << (i & 31);
+            const int w = i >> 5;
+            uint32_t* tab = GO.gtab + (size_t)b * kGtabWords;
+            atomicOr(&tab[(0 * kCols + ax) * kGraphWS + w], bit);
+            if (bxx + 1 < kCols) atomicOr(&tab[(1 * kCols + bxx + 1) * kGraphWS + w], bit);
+            atomicOr(&tab[(2 * kCols + ay) * kGraphWS + w], bit);
+            if (by + 1 < kCols) atomicOr(&tab[(3 * kCols + by + 1) * kGraphWS + w], bit);
         }
     }
 }
@@ -331,8 +356,8 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
 // KG: suppression graph of one image.  grid = (kGraphSplit, B).  Every CTA loads the image's node
 // array and mark table (one round of coalesced L2 loads), finishes the prefix-OR, owns every
 // kGraphSplit-th node, lists the pairs (i < j) that survive the bin cull and tests them exactly.
-//   adj[anchor j] = { anchor u : suppresses(kept = u, candidate = j) }    (exact fp32 test, boxes scaled)
-// Images with more than kGraphNodes passing anchors, or a node of degree > kAdjDeg, are flagged and
+//   adj[node j] = { node u : suppresses(kept = u, candidate = j) }    (exact fp32 test, boxes scaled)
+// Images with more than kGraphNodes nodes, or a node of degree > kAdjDeg, are flagged and
 // handled by the per-problem bin path instead.
 // ---------------------------------------------------------------------------------------
 constexpr int kGraphThreads = 256;
@@ -342,48 +367,46 @@ constexpr int kGraphPairCap = 2048;
 struct GraphSmem {
     float x1[kGraphNodes], y1[kGraphNodes], x2[kGraphNodes], y2[kGraphNodes];
     uint32_t cr[kGraphNodes];
-    int anchor[kGraphNodes];
     uint32_t tab[kGtabWords];
     uint32_t pairs[kGraphPairCap];
-    int wsum[kGraphThreads / 32];
     int overflow;
     int npairs;
 };
 
-__device__ __forceinline__ void graph_add_edge(int* __restrict__ adjn, uint32_t* __restrict__ adj, size_t img,
-                                               int a_to, int a_from, int* overflow) {
-    const int slot = atomicAdd(&adjn[img + a_to], 1);
-    if (slot < kAdjDeg) adj[(img + a_to) * kAdjDeg + slot] = (uint32_t)a_from;
+__device__ __forceinline__ void graph_add_edge(int* __restrict__ adjn, unsigned short* __restrict__ adj,
+                                               int to, int from, int* overflow) {
+    const int slot = atomicAdd(&adjn[to], 1);
+    if (slot < kAdjDeg) adj[to * kAdjDeg + slot] = (unsigned short)from;
     else *overflow = 1;
 }
 
 // exact tests of one unordered pair (i < j), both directions
 __device__ __forceinline__ void graph_test_pair(const GraphSmem& G, int i, int j, float thr, int flags,
-                                                int* __restrict__ adjn, uint32_t* __restrict__ adj, size_t img,
+                                                int* __restrict__ adjn, unsigned short* __restrict__ adj,
                                                 int* overflow) {
     const bool i_sup_j = suppresses(G.x1[i], G.y1[i], G.x2[i], G.y2[i], G.x1[j], G.y1[j], G.x2[j], G.y2[j], thr, flags);
     // the pixel(+1) IoU is symmetric in fp32 (ai + aj commutes); the normalised one is not ((aj - inter) + ai)
     const bool j_sup_i = (flags & RD_NMS_PIXEL_PLUS1)
                              ? i_sup_j
                              : suppresses(G.x1[j], G.y1[j], G.x2[j], G.y2[j], G.x1[i], G.y1[i], G.x2[i], G.y2[i], thr, flags);
-    if (i_sup_j) graph_add_edge(adjn, adj, img, G.anchor[j], G.anchor[i], overflow);
-    if (j_sup_i) graph_add_edge(adjn, adj, img, G.anchor[i], G.anchor[j], overflow);
+    if (i_sup_j) graph_add_edge(adjn, adj, j, i, overflow);
+    if (j_sup_i) graph_add_edge(adjn, adj, i, j, overflow);
 }
 
 __global__ void __launch_bounds__(kGraphThreads)
 graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, const float4* __restrict__ nbox,
-             const int* __restrict__ nanc, const uint32_t* __restrict__ ncr, int P, float thr, int flags,
-             uint32_t* __restrict__ adj, int* __restrict__ adjn, int* __restrict__ img_flag) {
+             const uint32_t* __restrict__ ncr, int P, float thr, int flags,
+             uint4* __restrict__ adj_all, int* __restrict__ adjn_all, int* __restrict__ img_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphSmem& G = *reinterpret_cast<GraphSmem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int g = blockIdx.x, b = blockIdx.y;
     grid_dependency_wait();          // collect_kernel has completed (this kernel is launched early)
     RD_MARK(0);
     RD_TMIN(24);
-    grid_launch_dependents();        // sort_kernel (graph independent) may run beside this kernel
+    grid_launch_dependents();        // nms_small_kernel's scan + sort (graph independent) may run beside this kernel
     const int N = nnodes[b];
-    if (N > kGraphNodes || img_flag[b] != 0) {
+    if (N > kGraphNodes) {
         if (g == 0 && tid == 0) img_flag[b] = 1;
         return;
     }
@@ -391,14 +414,14 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
     // of others, and the later nodes that have more predecessors, are spread over the CTAs of the image)
     const int nown = N > g ? (N - g + kGraphSplit - 1) / kGraphSplit : 0;
     if (nown == 0) return;
-    const size_t img = (size_t)b * P;
+    int* adjn = adjn_all + (size_t)b * kGraphNodes;
+    unsigned short* adj = reinterpret_cast<unsigned short*>(adj_all + (size_t)b * kGraphNodes);
     const int Wn = (N + 31) >> 5;
     // 1. node array + mark table -> shared memory (independent loads, one round trip)
     if (tid == 0) { G.overflow = 0; G.npairs = 0; }
     for (int i = tid; i < N; i += kGraphThreads) {
-        const float4 bx = nbox[(size_t)b * kGraphNodes + i];
+        const float4 bx = nbox[(size_t)b * P + i];
         G.x1[i] = bx.x; G.y1[i] = bx.y; G.x2[i] = bx.z; G.y2[i] = bx.w;
-        G.anchor[i] = nanc[(size_t)b * kGraphNodes + i];
         G.cr[i] = ncr[(size_t)b * kGraphNodes + i];
     }
     RD_MARK(1);
@@ -470,38 +493,34 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
         const int cnt = min(G.npairs, kGraphPairCap);
         for (int p = tid; p < cnt; p += kGraphThreads) {
             const uint32_t e = G.pairs[p];
-            graph_test_pair(G, (int)(e & 0xffffu), g + (int)(e >> 16) * kGraphSplit, thr, flags, adjn, adj, img,
+            graph_test_pair(G, (int)(e & 0xffffu), g + (int)(e >> 16) * kGraphSplit, thr, flags, adjn, adj,
                             &G.overflow);
         }
     }
     __syncthreads();
     RD_MARK(6);
-#ifdef RD_PROFILE_PHASES
-    if (blockIdx.x == 3 && blockIdx.y == 5 && tid == 0) { g_dbg[10] = N; g_dbg[11] = G.npairs; g_dbg[12] = nown; }
-#endif
     if (tid == 0 && G.overflow) img_flag[b] = 1;
     RD_TMAX(20);
 }
 
 // ---------------------------------------------------------------------------------------
-// K2+K3
+// K2
 // ---------------------------------------------------------------------------------------
 struct FusedNmsArgs {
-    const int* cnt;                  // [B*C*S]
-    const unsigned long long* cand;  // [B*C*S*1024]
-    const float4* boxes;             // [B*P]
-    const float* img_scale;          // [B,4] or null
+    const float* nsc;                // [B][C][Pn] node scores
+    const float4* nbox;              // [B][P] node boxes (scaled)
+    const int* nanc;                 // [B][P] node anchors
+    const int* nnodes;               // [B]
+    uint32_t* gtab;                  // [B][kGtabWords]   control block, cleared by the class-0 CTA of every image
+    const int* img_flag;             // [B] 1 = no graph for this image
+    const uint4* adj;                // [B][kGraphNodes]
+    const int* adjn;                 // [B][kGraphNodes]
     int* queue;
     uint32_t* header;
-    unsigned long long* skeys;       // [B*C][256] sorted keys of the small problems
-    int* sn;                         // [B*C] n of a sorted problem, 0 = empty, -1 = queued
-    int* nnodes;                     // [B]   } control block, cleared by the class-0 CTA of every image
-    uint32_t* gtab;                  // [B][kGtabWords]
-    const int* img_flag;             // [B] 1 = no graph for this image
-    const uint32_t* adj;             // [B*P*kAdjDeg]
-    const int* adjn;                 // [B*P]
-    int nbc, C, P, S;
+    unsigned long long* cand;        // [B*C][P] key scratch of the large problems
+    int nbc, C, P, Pn;
     int large_grid, large_mcap, large_smem;   // launch shape of nms_large_kernel
+    float conf_thresh;
     float thr;
     int top_k, max_out, flags, row_layout;
     int* out_counts;
@@ -509,111 +528,86 @@ struct FusedNmsArgs {
     int* out_anchor;
 };
 
-// slice counts -> shared memory + exclusive prefix sums; returns n (uniform).  One warp's worth of work.
-__device__ __forceinline__ int load_slice_counts(const int* __restrict__ gcnt, int S, int* s_cnt, int* s_offs) {
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        int run = 0;
-        for (int base = 0; base < S; base += 32) {
-            const int sidx = base + lane;
-            const int c = sidx < S ? gcnt[sidx] : 0;
-            int x = c;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, x, d); if (lane >= d) x += o; }
-            if (sidx < S) { s_cnt[sidx] = c; s_offs[sidx] = run + x - c; }
-            run += __shfl_sync(kFullMask, x, 31);
-        }
-        if (lane == 0) s_offs[S] = run;
-    }
-    __syncthreads();
-    return s_offs[S];
-}
-
-__device__ __forceinline__ void fill_problem(NmsProblem& pb, RowSink& sink, int bc, int n, const int* s_cnt,
-                                             const int* s_offs, const FusedNmsArgs& A) {
-    const int b = bc / A.C;
-    pb.cl.base = A.cand + (size_t)bc * A.S * kSliceAnchors;
-    pb.cl.S = A.S;
-    pb.cl.stride = kSliceAnchors;
-    pb.cl.cnt = s_cnt;
-    pb.cl.offs = s_offs;
-    pb.cl.n = n;
-    pb.boxes = A.boxes + (size_t)b * A.P;
-    pb.has_scale = A.img_scale != nullptr;
-    pb.scale = pb.has_scale ? __ldg(reinterpret_cast<const float4*>(A.img_scale) + b) : make_float4(1.f, 1.f, 1.f, 1.f);
-    pb.thr = A.thr;
-    pb.top_k = A.top_k;
-    pb.max_out = A.max_out;
-    pb.flags = A.flags;
-    sink.rows = A.out_dets + (size_t)bc * A.max_out * 5;
-    sink.anchors = A.out_anchor ? A.out_anchor + (size_t)bc * A.max_out : nullptr;
-    sink.keep64 = nullptr;
-    sink.keep32 = nullptr;
-    sink.row_layout = A.row_layout;
-}
-
-// K2a: sort.  One CTA per (image, class): gather the candidate sub-lists, sort the keys (runs of 32 in
-// registers, merged by rank) and store them.  Depends on collect_kernel only; launched with
-// programmatic stream serialisation behind graph_kernel (which triggers at its start), so the two run
-// side by side.  Problems that need the top-k select are queued for nms_large_kernel.
-__global__ void __launch_bounds__(kSortThreads, 1536 / kSortThreads)
-sort_kernel(FusedNmsArgs A) {
+// K2: one CTA per (image, class).  Launched with programmatic stream serialisation behind graph_kernel
+// (which triggers at its start): the scan of the class's score row and the sort need collect_kernel's
+// results only and run beside graph_kernel; the CTA then waits for the graph and resolves.
+__global__ void __launch_bounds__(kSmallThreads, 1536 / kSmallThreads)
+nms_small_kernel(FusedNmsArgs A) {
     __shared__ SmallSmem S;
-    RD_TMIN(21);
+    constexpr int kPerT = kGraphNodes / kSmallThreads;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int bc = blockIdx.x;
     const int c = bc % A.C;
-    if (c == 0) return;                // background is never evaluated (eval_refinedet_coco.py:213)
-    const int n = load_slice_counts(A.cnt + (size_t)bc * A.S, A.S, S.cnt, S.offs);
+    const int b = bc / A.C;
+    RD_TMIN(21);
+    if (c == 0) {
+        // this CTA has no problem (background is never evaluated, eval_refinedet_coco.py:213): it leaves the
+        // graph control block of its image zero for the next call, once graph_kernel is done with it
+        grid_dependency_wait();
+        uint32_t* gt = A.gtab + (size_t)b * kGtabWords;
+        for (int i = tid; i < kGtabWords; i += kSmallThreads) gt[i] = 0;
+        if (tid == 0) A.out_counts[bc] = 0;
+        return;
+    }
+    const int N = A.nnodes[b];
+    if (N > kGraphNodes) {                                        // the image has no graph: own bins, large kernel
+        if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
+        return;
+    }
+    if (tid == 0) S.n = 0;
+    __syncthreads();
+    // candidates: nodes whose score exceeds the threshold; keys in any order
+    {
+        const float* row = A.nsc + (size_t)bc * A.Pn;
+        float v[kPerT];
+#pragma unroll
+        for (int q = 0; q < kPerT; ++q) {
+            const int i = q * kSmallThreads + tid;
+            v[q] = i < N ? __ldg(row + i) : -INFINITY;
+        }
+#pragma unroll
+        for (int q = 0; q < kPerT; ++q) {
+            const int i = q * kSmallThreads + tid;
+            const bool pass = v[q] > A.conf_thresh;
+            const unsigned bal = __ballot_sync(kFullMask, pass);
+            if (bal) {
+                int wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&S.n, __popc(bal));
+                wbase = __shfl_sync(kFullMask, wbase, 0);
+                const int slot = wbase + __popc(bal & ((1u << lane) - 1u));
+                if (pass && slot < kSmallCap) S.u.runs[slot] = make_key(v[q], (uint32_t)i);
+            }
+        }
+    }
+    __syncthreads();
+    const int n = S.n;
     if (n == 0) {
-        if (threadIdx.x == 0) A.sn[bc] = 0;
+        if (tid == 0) A.out_counts[bc] = 0;
         return;
     }
     if (n > A.top_k || n > kSmallCap) {                           // needs the top-k select: large kernel
-        if (threadIdx.x == 0) { A.sn[bc] = -1; A.queue[atomicAdd(&A.header[0], 1u)] = bc; }
+        if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
         return;
     }
-    CandList cl;
-    cl.base = A.cand + (size_t)bc * A.S * kSliceAnchors;
-    cl.S = A.S; cl.stride = kSliceAnchors; cl.cnt = S.cnt; cl.offs = S.offs; cl.n = n;
-    cta_sort_small<kSortThreads>(S, cl);
-    unsigned long long* out = A.skeys + (size_t)bc * kSmallCap;
-    for (int i = threadIdx.x; i < n; i += kSortThreads) out[i] = S.keys[i];
-    if (threadIdx.x == 0) A.sn[bc] = n;
+    cta_sort_small<kSmallThreads>(S, n);
     RD_TMAX(22);
-}
-
-// K2b + K3: resolve.  Normal launch: starts when graph_kernel AND sort_kernel have completed.
-__global__ void __launch_bounds__(kResolveThreads, 1536 / kResolveThreads)
-resolve_kernel(FusedNmsArgs A) {
-    __shared__ SmallSmem S;
-    const int bc = blockIdx.x;
-    const int c = bc % A.C;
-    const int b = bc / A.C;
-    if (c == 0) {
-        // this CTA has no problem: it leaves the graph control block of its image zero for the next call
-        uint32_t* gt = A.gtab + (size_t)b * kGtabWords;
-        for (int i = threadIdx.x; i < kGtabWords; i += kResolveThreads) gt[i] = 0;
-        if (threadIdx.x == 0) { A.nnodes[b] = 0; A.out_counts[bc] = 0; }
+    grid_dependency_wait();                                       // graph_kernel has completed
+    if (A.img_flag[b] != 0) {                                     // degree / pair overflow: no graph after all
+        if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
         return;
     }
-    const int n = A.sn[bc];
-    const int noflag = A.img_flag[b] == 0;
-    if (n <= 0) {                                                 // empty, or already queued by sort_kernel
-        if (n == 0 && threadIdx.x == 0) A.out_counts[bc] = 0;
-        return;
-    }
-    if (!noflag) {                                                // the image has no graph: own bins, large kernel
-        if (threadIdx.x == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
-        return;
-    }
-    NmsProblem pb;
     RowSink sink;
-    fill_problem(pb, sink, bc, n, S.cnt, S.offs, A);
+    sink.rows = A.out_dets + (size_t)bc * A.max_out * 5;
+    sink.anchors = A.out_anchor ? A.out_anchor + (size_t)bc * A.max_out : nullptr;
+    sink.keep64 = nullptr; sink.keep32 = nullptr; sink.idx_map = nullptr;
+    sink.row_layout = A.row_layout;
     GraphView G;
-    G.adj = reinterpret_cast<const uint4*>(A.adj + (size_t)b * A.P * kAdjDeg);
-    G.adjn = A.adjn + (size_t)b * A.P;
-    const int kept = cta_nms_graph<kResolveThreads>(S, pb, sink, G, A.skeys + (size_t)bc * kSmallCap);
-    if (threadIdx.x == 0) A.out_counts[bc] = kept;
+    G.adj = A.adj + (size_t)b * kGraphNodes;
+    G.adjn = A.adjn + (size_t)b * kGraphNodes;
+    G.nbox = A.nbox + (size_t)b * A.P;
+    G.nanc = A.nanc + (size_t)b * A.P;
+    const int kept = cta_nms_graph<kSmallThreads>(S, n, A.max_out, sink, G);
+    if (tid == 0) A.out_counts[bc] = kept;
     RD_TMAX(23);
 }
 
@@ -623,16 +617,48 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
     const NmsSmemLayout L = nms_layout(mcap);
     int* s_cnt = reinterpret_cast<int*>(smem + L.off_cnt);
     int* s_offs = reinterpret_cast<int*>(smem + L.off_offs);
-    grid_dependency_wait();          // resolve_kernel (and everything before it) has completed
+    const int tid = threadIdx.x, lane = tid & 31;
+    grid_dependency_wait();          // nms_small_kernel (and everything before it) has completed
     const uint32_t nq = A.header[0];
     for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
         const int bc = A.queue[q];
-        const int n = load_slice_counts(A.cnt + (size_t)bc * A.S, A.S, s_cnt, s_offs);
+        const int b = bc / A.C;
+        const int N = A.nnodes[b];
+        // candidate keys of the problem -> its slot of the global scratch list
+        unsigned long long* keys = A.cand + (size_t)bc * A.P;
+        const float* row = A.nsc + (size_t)bc * A.Pn;
+        if (tid == 0) s_cnt[0] = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < N; i0 += kLargeThreads) {
+            const int i = i0 + tid;
+            const float v = i < N ? __ldg(row + i) : -INFINITY;
+            const bool pass = v > A.conf_thresh;
+            const unsigned bal = __ballot_sync(kFullMask, pass);
+            if (bal) {
+                int wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&s_cnt[0], __popc(bal));
+                wbase = __shfl_sync(kFullMask, wbase, 0);
+                if (pass) keys[wbase + __popc(bal & ((1u << lane) - 1u))] = make_key(v, (uint32_t)i);
+            }
+        }
+        __syncthreads();
+        const int n = s_cnt[0];
+        if (tid == 0) { s_offs[0] = 0; s_offs[1] = n; }
+        __syncthreads();
         NmsProblem pb;
+        pb.cl.base = keys; pb.cl.S = 1; pb.cl.stride = 0; pb.cl.cnt = s_cnt; pb.cl.offs = s_offs; pb.cl.n = n;
+        pb.boxes = A.nbox + (size_t)b * A.P;
+        pb.has_scale = 0;                                         // node boxes are already scaled
+        pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
+        pb.thr = A.thr; pb.top_k = A.top_k; pb.max_out = A.max_out; pb.flags = A.flags;
         RowSink sink;
-        fill_problem(pb, sink, bc, n, s_cnt, s_offs, A);
+        sink.rows = A.out_dets + (size_t)bc * A.max_out * 5;
+        sink.anchors = A.out_anchor ? A.out_anchor + (size_t)bc * A.max_out : nullptr;
+        sink.keep64 = nullptr; sink.keep32 = nullptr;
+        sink.idx_map = A.nanc + (size_t)b * A.P;
+        sink.row_layout = A.row_layout;
         const int kept = nms_process(smem, L, pb, sink);
-        if (threadIdx.x == 0) A.out_counts[bc] = kept;
+        if (tid == 0) A.out_counts[bc] = kept;
         __syncthreads();
     }
 }
@@ -669,6 +695,7 @@ nms_single_kernel(const unsigned long long* cand, int n, const float4* boxes, fl
     pb.thr = thr; pb.top_k = top_k; pb.max_out = max_out; pb.flags = flags;
     RowSink sink;
     sink.rows = nullptr; sink.anchors = nullptr; sink.keep64 = keep_out; sink.keep32 = keep_out32; sink.row_layout = 0;
+    sink.idx_map = nullptr;
     const int kept = nms_process(smem, L, pb, sink);
     if (threadIdx.x == 0) *count_out = kept;
 }
@@ -801,7 +828,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
         return RD_ERR_BAD_ARG;
     if (B <= 0 || P <= 0 || C <= 0 || top_k <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
     if (C > kMaxClasses || B > 65535 || (long long)B * C > (1 << 30)) return RD_ERR_UNSUPPORTED;
-    if (P > kMaxSlices * kSliceAnchors) return RD_ERR_UNSUPPORTED;
+    if (P > 65535 * kSliceAnchors / 64) return RD_ERR_UNSUPPORTED;
     if (top_k > RD_MAX_NMS_BOXES) return RD_ERR_UNSUPPORTED;
     if ((((uintptr_t)arm_loc | (uintptr_t)odm_loc | (uintptr_t)priors | (uintptr_t)workspace) & 15) ||
         ((uintptr_t)arm_conf & 7) || (img_scale && ((uintptr_t)img_scale & 15)))
@@ -816,7 +843,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     if (ev) cudaEventRecord(ev[0], st);
     collect_kernel<<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
         (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
-        P, C, ws.S, objectness_thre, conf_thresh, v0, v1, ws.boxes, ws.cnt, ws.cand, ws.header, GO);
+        P, C, ws.S, ws.Pn, objectness_thre, v0, v1, ws.nsc, ws.header, GO);
     note_launch();
     RD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[1], st);
@@ -830,18 +857,18 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
         }
         cudaError_t e = launch_pdl(graph_kernel, dim3(kGraphSplit, B), dim3(kGraphThreads), sizeof(GraphSmem), st,
                                    (const int*)ws.nnodes, (const uint32_t*)ws.gtab, (const float4*)ws.nbox,
-                                   (const int*)ws.nanc, (const uint32_t*)ws.ncr, P, nms_thresh, nms_flags, ws.adj,
-                                   ws.adjn, ws.flag);
+                                   (const uint32_t*)ws.ncr, P, nms_thresh, nms_flags, ws.adj, ws.adjn, ws.flag);
         if (e != cudaSuccess) return (int)e;
         note_launch();
         RD_CHECK_LAUNCH();
     }
 
     FusedNmsArgs A;
-    A.cnt = ws.cnt; A.cand = ws.cand; A.boxes = ws.boxes; A.img_scale = img_scale;
-    A.queue = ws.queue; A.header = ws.header; A.skeys = ws.skeys; A.sn = ws.sn;
-    A.img_flag = ws.flag; A.adj = ws.adj; A.adjn = ws.adjn; A.nnodes = ws.nnodes; A.gtab = ws.gtab;
-    A.nbc = B * C; A.C = C; A.P = P; A.S = ws.S;
+    A.nsc = ws.nsc; A.nbox = ws.nbox; A.nanc = ws.nanc; A.nnodes = ws.nnodes; A.gtab = ws.gtab;
+    A.img_flag = ws.flag; A.adj = ws.adj; A.adjn = ws.adjn; A.queue = ws.queue; A.header = ws.header;
+    A.cand = ws.cand;
+    A.nbc = B * C; A.C = C; A.P = P; A.Pn = ws.Pn;
+    A.conf_thresh = conf_thresh;
     A.thr = nms_thresh; A.top_k = top_k; A.max_out = max_out; A.flags = nms_flags; A.row_layout = row_layout;
     A.out_counts = out_counts; A.out_dets = out_dets; A.out_anchor = out_anchor;
 
@@ -870,13 +897,10 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
         A.large_smem = (int)Ll.total;
     }
     if (ev) cudaEventRecord(ev[2], st);
-    {   // programmatic dependent launch: sort_kernel runs beside graph_kernel
-        cudaError_t e = launch_pdl(sort_kernel, dim3(B * C), dim3(kSortThreads), 0, st, A);
+    {   // programmatic dependent launch: the scan + sort of nms_small_kernel run beside graph_kernel
+        cudaError_t e = launch_pdl(nms_small_kernel, dim3(B * C), dim3(kSmallThreads), 0, st, A);
         if (e != cudaSuccess) return (int)e;
     }
-    note_launch();
-    RD_CHECK_LAUNCH();
-    resolve_kernel<<<B * C, kResolveThreads, 0, st>>>(A);
     note_launch();
     RD_CHECK_LAUNCH();
     {

@@ -58,6 +58,7 @@ struct RowSink {           // where rows are written
     long long* keep64;     // stand-alone: kept key indices, or null
     int* keep32;
     int row_layout;
+    const int* idx_map;    // anchors[t] = idx_map[key index] when set (fused stage: key index = node)
 };
 
 __device__ __forceinline__ void sink_emit(const RowSink& sink, int t, unsigned long long key, float x1, float y1,
@@ -69,7 +70,7 @@ __device__ __forceinline__ void sink_emit(const RowSink& sink, int t, unsigned l
         if (sink.row_layout == RD_ROW_SCORE_BOX) { r[0] = sc; r[1] = x1; r[2] = y1; r[3] = x2; r[4] = y2; }
         else { r[0] = x1; r[1] = y1; r[2] = x2; r[3] = y2; r[4] = sc; }
     }
-    if (sink.anchors) sink.anchors[t] = (int)idx;
+    if (sink.anchors) sink.anchors[t] = sink.idx_map ? sink.idx_map[idx] : (int)idx;
     if (sink.keep64) sink.keep64[t] = (long long)idx;
     if (sink.keep32) sink.keep32[t] = (int)idx;
 }
@@ -159,66 +160,47 @@ __device__ __forceinline__ unsigned long long warp_sort32_desc(unsigned long lon
 }
 
 // =========================================================================================
-// small problems: n <= kSmallCap candidates, no select (sort_kernel + resolve_kernel)
+// small problems: n <= kSmallCap candidates, no select (nms_small_kernel)
 // =========================================================================================
-#ifndef RD_SORT_THREADS
-#define RD_SORT_THREADS 96
+#ifndef RD_SMALL_THREADS
+#define RD_SMALL_THREADS 128
 #endif
-#ifndef RD_RESOLVE_THREADS
-#define RD_RESOLVE_THREADS 128
-#endif
-constexpr int kSortThreads = RD_SORT_THREADS;         // sort_kernel: the warps share the <= 8 runs of a problem
-constexpr int kResolveThreads = RD_RESOLVE_THREADS;   // resolve_kernel
+constexpr int kSmallThreads = RD_SMALL_THREADS;
 constexpr int kSmallCap = 256;
 constexpr int kSmallW = kSmallCap / 32;      // 8 mask words
 
-constexpr int kAdjDeg = 8;            // adjacency slots per anchor; an image whose graph overflows is flagged dense
-constexpr int kHashSlots = 512;       // anchor -> rank hash table of one problem (load factor <= 0.5)
+constexpr int kGraphNodes = 1024;     // images with more ARM-passing anchors have no suppression graph
+constexpr int kAdjDeg = 8;            // adjacency slots per node; an image whose graph overflows is flagged dense
 
 struct SmallSmem {
     unsigned long long keys[kSmallCap];           // sorted keys
     union {
-        unsigned long long runs[kSmallCap];       // sorted runs of 32 (during the sort)
+        unsigned long long runs[kSmallCap];       // unsorted candidates, then sorted runs of 32 (during the sort)
         struct {
-            uint32_t hash[kHashSlots];            // (anchor << 8) | rank, 0xffffffff = empty
+            unsigned short rank[kGraphNodes];     // node -> rank in this problem, 0xffff = not a candidate
             unsigned char deps[kSmallCap * kAdjDeg];   // ranks of the dependencies of every candidate
         } g;
     } u;
     unsigned char depn[kSmallCap];
     unsigned char state[kSmallCap];               // 0 undecided, 1 kept, 2 suppressed
-    int cnt[kMaxSlices];
-    int offs[kMaxSlices + 1];
     int wsum[8];
+    int n;
 };
 
-// key of flattened element e of a sliced candidate list
-__device__ __forceinline__ unsigned long long cand_at(const CandList& cl, int e) {
-    int s = 0;
-    if (cl.S > 1) {
-        int lo = 0, hi = cl.S;                 // largest s with offs[s] <= e
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (cl.offs[mid] <= e) lo = mid; else hi = mid;
-        }
-        s = lo;
-    }
-    return cl.base[(size_t)s * cl.stride + (e - cl.offs[s])];
-}
-
-// Phases A+B of a small problem: sorted runs of 32 in registers (one run per warp at a time), merged
-// by rank.  On return (after a CTA barrier) S.keys[0..m) holds the keys in descending order.
+// Sort of a small problem: S.u.runs[0..m) holds the candidate keys in any order.  Sorted runs of 32 in
+// registers (one run per warp at a time, bitonic over shuffles), merged by rank.  On return (after a CTA
+// barrier) S.keys[0..m) holds the keys in descending order.
 template <int kThreads>
-__device__ __forceinline__ void cta_sort_small(SmallSmem& S, const CandList& cl) {
+__device__ __forceinline__ void cta_sort_small(SmallSmem& S, int m) {
     constexpr int kSmallWarps = kThreads / 32;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int m = cl.n;
     const int Wm = (m + 31) >> 5;
     unsigned long long* runs = S.u.runs;
     for (int run = warp; run < Wm; run += kSmallWarps) {
         const int e = run * 32 + lane;
-        unsigned long long k = e < m ? cand_at(cl, e) : 0ull;
+        unsigned long long k = e < m ? runs[e] : 0ull;
         k = warp_sort32_desc(k, lane);
         if (Wm == 1) S.keys[lane] = k; else runs[e] = k;
     }
@@ -244,12 +226,11 @@ __device__ __forceinline__ void cta_sort_small(SmallSmem& S, const CandList& cl)
 }
 
 // =========================================================================================
-// small problems, graph mode: the suppression relation between the ARM-passing anchors of an
+// small problems, graph mode: the suppression relation between the ARM-passing anchors (nodes) of an
 // image does not depend on the class, so it is computed once per image (graph_kernel in
-// rd_detect.cu) as adjacency lists  adj[anchor] = {u : box u suppresses box anchor when u is kept}.
-// A problem then only sorts its keys, finds which graph neighbours are candidates of ITS class with
-// a higher key (shared-memory hash anchor -> rank) and resolves the dependencies; no boxes, bins or
-// IoUs per class.  7.1 KB of shared memory, <= 40 registers: 24 CTAs resident per SM.
+// rd_detect.cu) as adjacency lists  adj[node] = {u : box u suppresses box node when u is kept}.
+// A problem then only sorts its keys, marks the rank of every candidate node in a direct table and
+// resolves the dependencies; no boxes, bins or IoUs per class.
 // =========================================================================================
 // programmatic dependent launch (sm_90+): wait until the preceding kernel of the stream has completed and
 // its memory is visible / allow the next kernel of the stream to start launching
@@ -257,82 +238,64 @@ __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepco
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 struct GraphView {
-    const uint4* adj;                 // [P][kAdjDeg] anchors of the image, as two uint4 per anchor
-    const int* adjn;                  // [P] degree (<= kAdjDeg when the image is not flagged)
+    const uint4* adj;                 // [kGraphNodes] node indices of the suppressors, 8 x u16 per node
+    const int* adjn;                  // [kGraphNodes] degree (<= kAdjDeg when the image is not flagged)
+    const float4* nbox;               // [N] node boxes, already multiplied by the image scale
+    const int* nanc;                  // [N] anchor index of every node
 };
 
-__device__ __forceinline__ uint32_t hash_anchor(uint32_t a) { return (a * 2654435761u) >> 23; }   // 9 bits
-
-// `skeys` = the problem's sorted keys in global memory (sort_kernel), n of them.  Two dependent rounds of
-// global loads in total: (keys) -> (adjacency rows + boxes of every candidate).
-template <int kSmallThreads>
-__device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const RowSink& sink, const GraphView& G,
-                                    const unsigned long long* __restrict__ skeys) {
-    constexpr int kSmallWarps = kSmallThreads / 32;
-    constexpr int kPerT = (kSmallCap + kSmallThreads - 1) / kSmallThreads;
+// S.keys[0..m) = the problem's sorted keys (key index = node).  One round of global loads: adjacency row,
+// box and anchor of every candidate.
+template <int kThreads>
+__device__ inline int cta_nms_graph(SmallSmem& S, int m, int max_out, const RowSink& sink, const GraphView& G) {
+    constexpr int kSmallWarps = kThreads / 32;
+    constexpr int kPerT = (kSmallCap + kThreads - 1) / kThreads;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int m = pb.cl.n;                                   // n <= min(top_k, kSmallCap): nothing is truncated
-    // candidate r = q * kSmallThreads + tid (striped); everything about it stays in registers
+    // candidate r = q * kThreads + tid (striped); everything about it stays in registers
     unsigned long long key[kPerT];
-#pragma unroll
-    for (int q = 0; q < kPerT; ++q) {
-        const int r = q * kSmallThreads + tid;
-        key[q] = r < m ? skeys[r] : 0ull;
-    }
-    for (int i = tid; i < kHashSlots; i += kSmallThreads) S.u.g.hash[i] = 0xffffffffu;
-    __syncthreads();
     float4 box[kPerT];
+    uint4 row[kPerT];
+    int dn[kPerT], anc[kPerT];
 #pragma unroll
     for (int q = 0; q < kPerT; ++q) {
-        const int r = q * kSmallThreads + tid;
+        const int r = q * kThreads + tid;
+        key[q] = r < m ? S.keys[r] : 0ull;
+        dn[q] = 0;
         if (r < m) {
-            const uint32_t a = key_index(key[q]);
-            box[q] = pb.boxes[a];                            // most candidates are kept: fetch the row data now
-            uint32_t h = hash_anchor(a);                     // insert (anchor -> rank)
-            const uint32_t val = (a << 8) | (uint32_t)r;
-            while (atomicCAS(&S.u.g.hash[h], 0xffffffffu, val) != 0xffffffffu) h = (h + 1) & (kHashSlots - 1);
+            const uint32_t u = key_index(key[q]);
+            dn[q] = G.adjn[u];
+            row[q] = __ldg(G.adj + u);
+            box[q] = G.nbox[u];                              // most candidates are kept: fetch the row data now
+            anc[q] = G.nanc[u];
         }
+    }
+    // rank table (aliases the sort buffer: every thread is past the merge, see the barrier in cta_sort_small)
+    {
+        uint4* t = reinterpret_cast<uint4*>(S.u.g.rank);
+        for (int i = tid; i < kGraphNodes * 2 / 16; i += kThreads) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kPerT; ++q) {
+        const int r = q * kThreads + tid;
+        if (r < m) S.u.g.rank[key_index(key[q])] = (unsigned short)r;
     }
     __syncthreads();
     // ---- dependencies: graph neighbours that are candidates of this class and rank earlier --------
-    // (adjacency rows are consumed as they arrive, nothing is held across the barrier)
-    int dn[kPerT];
-    uint4 row0[kPerT], row1[kPerT];
 #pragma unroll
     for (int q = 0; q < kPerT; ++q) {
-        const int r = q * kSmallThreads + tid;
-        dn[q] = 0;
+        const int r = q * kThreads + tid;
         if (r < m) {
-            const uint32_t a = key_index(key[q]);
-            dn[q] = G.adjn[a];
-            row0[q] = __ldg(G.adj + (size_t)a * 2);
-            row1[q] = __ldg(G.adj + (size_t)a * 2 + 1);
-        }
-    }
-#pragma unroll
-    for (int q = 0; q < kPerT; ++q) {
-        const int r = q * kSmallThreads + tid;
-        if (r < m) {
-            const uint32_t nb[kAdjDeg] = {row0[q].x, row0[q].y, row0[q].z, row0[q].w,
-                                          row1[q].x, row1[q].y, row1[q].z, row1[q].w};
+            const uint32_t nb[4] = {row[q].x, row[q].y, row[q].z, row[q].w};
             int nd = 0;
 #pragma unroll
             for (int k = 0; k < kAdjDeg; ++k) {
                 if (k < dn[q]) {
-                    const uint32_t u = nb[k];
-                    uint32_t h = hash_anchor(u);
-                    for (;;) {
-                        const uint32_t v = S.u.g.hash[h];
-                        if (v == 0xffffffffu) break;                    // u is not a candidate of this class
-                        if ((v >> 8) == u) {
-                            const int ru = (int)(v & 255u);
-                            if (ru < r) S.u.g.deps[r * kAdjDeg + nd++] = (unsigned char)ru;
-                            break;
-                        }
-                        h = (h + 1) & (kHashSlots - 1);
-                    }
+                    const uint32_t v = (nb[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                    const int rv = S.u.g.rank[v];
+                    if (rv < r) S.u.g.deps[r * kAdjDeg + nd++] = (unsigned char)rv;
                 }
             }
             S.depn[r] = (unsigned char)nd;
@@ -345,7 +308,7 @@ __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const Ro
         int undecided = 0;
 #pragma unroll
         for (int q = 0; q < kPerT; ++q) {
-            const int r = q * kSmallThreads + tid;
+            const int r = q * kThreads + tid;
             if (r >= m || S.state[r] != 0) continue;
             const int nd = S.depn[r];
             bool any_kept = false, all_sup = true;
@@ -364,7 +327,7 @@ __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const Ro
     int carry = 0;
 #pragma unroll
     for (int q = 0; q < kPerT; ++q) {
-        const int r = q * kSmallThreads + tid;
+        const int r = q * kThreads + tid;
         const bool kept = r < m && S.state[r] == 1;
         const unsigned bal = __ballot_sync(kFullMask, kept);
         if (lane == 0) S.wsum[warp] = __popc(bal);
@@ -376,15 +339,18 @@ __device__ inline int cta_nms_graph(SmallSmem& S, const NmsProblem& pb, const Ro
             if (w < warp) base += S.wsum[w];
             chunk += S.wsum[w];
         }
-        if (kept && base < pb.max_out) {
-            float4 b = box[q];
-            if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
-            sink_emit(sink, base, key[q], b.x, b.y, b.z, b.w);
+        if (kept && base < max_out) {
+            const float sc = key_score(key[q]);
+            float* o = sink.rows + (size_t)base * 5;
+            const float4 bx = box[q];
+            if (sink.row_layout == RD_ROW_SCORE_BOX) { o[0] = sc; o[1] = bx.x; o[2] = bx.y; o[3] = bx.z; o[4] = bx.w; }
+            else { o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w; o[4] = sc; }
+            if (sink.anchors) sink.anchors[base] = anc[q];
         }
         carry += chunk;
         __syncthreads();
     }
-    return carry < pb.max_out ? carry : pb.max_out;
+    return carry < max_out ? carry : max_out;
 }
 
 // =========================================================================================
