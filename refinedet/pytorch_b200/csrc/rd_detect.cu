@@ -314,7 +314,7 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
         // class 0 = background, never evaluated (eval_refinedet_coco.py:213)
         for (int task = 2 + wib; task < 2 * C; task += kCollectThreads / 32) {
             const int c = task >> 1, r = (task & 1) * 32 + lane;
-            if (r < rows_here) nsc_b[(size_t)c * Pn + t0 + r] = s_tile[c][r];
+            if (r < rows_here) nsc_b[c * Pn + t0 + r] = s_tile[c][r];
         }
         __syncthreads();
     }
@@ -535,10 +535,9 @@ __global__ void __launch_bounds__(kSmallThreads, 1536 / kSmallThreads)
 nms_small_kernel(FusedNmsArgs A) {
     __shared__ SmallSmem S;
     constexpr int kPerT = kGraphNodes / kSmallThreads;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int bc = blockIdx.x;
-    const int c = bc % A.C;
-    const int b = bc / A.C;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x, b = blockIdx.y;
+    const int bc = b * A.C + c;
     RD_TMIN(21);
     if (c == 0) {
         // this CTA has no problem (background is never evaluated, eval_refinedet_coco.py:213): it leaves the
@@ -554,28 +553,45 @@ nms_small_kernel(FusedNmsArgs A) {
         if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
         return;
     }
-    if (tid == 0) S.n = 0;
-    __syncthreads();
-    // candidates: nodes whose score exceeds the threshold; keys in any order
+    // candidates: nodes whose score exceeds the threshold.  Two passes over registers (count, then place)
+    // with one barrier in between: no atomics.
     {
         const float* row = A.nsc + (size_t)bc * A.Pn;
+        const int nq = (N + kSmallThreads - 1) / kSmallThreads;   // <= kPerT
         float v[kPerT];
+        unsigned bal[kPerT];
 #pragma unroll
         for (int q = 0; q < kPerT; ++q) {
             const int i = q * kSmallThreads + tid;
-            v[q] = i < N ? __ldg(row + i) : -INFINITY;
+            v[q] = (q < nq && i < N) ? __ldg(row + i) : -INFINITY;
         }
+        int cnt = 0;
 #pragma unroll
         for (int q = 0; q < kPerT; ++q) {
-            const int i = q * kSmallThreads + tid;
-            const bool pass = v[q] > A.conf_thresh;
-            const unsigned bal = __ballot_sync(kFullMask, pass);
-            if (bal) {
-                int wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&S.n, __popc(bal));
-                wbase = __shfl_sync(kFullMask, wbase, 0);
-                const int slot = wbase + __popc(bal & ((1u << lane) - 1u));
-                if (pass && slot < kSmallCap) S.u.runs[slot] = make_key(v[q], (uint32_t)i);
+            bal[q] = 0;
+            if (q < nq) {
+                bal[q] = __ballot_sync(kFullMask, v[q] > A.conf_thresh);
+                cnt += __popc(bal[q]);
+            }
+        }
+        if (lane == 0) S.wsum[warp] = cnt;
+        __syncthreads();
+        int slot = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kSmallThreads / 32; ++w) {
+            if (w < warp) slot += S.wsum[w];
+            tot += S.wsum[w];
+        }
+        if (tid == 0) S.n = tot;
+        if (tot <= kSmallCap) {
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int q = 0; q < kPerT; ++q) {
+                if (q < nq && bal[q]) {
+                    if ((bal[q] >> lane) & 1u)
+                        S.u.runs[slot + __popc(bal[q] & lt)] = make_key(v[q], (uint32_t)(q * kSmallThreads + tid));
+                    slot += __popc(bal[q]);
+                }
             }
         }
     }
@@ -898,7 +914,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     }
     if (ev) cudaEventRecord(ev[2], st);
     {   // programmatic dependent launch: the scan + sort of nms_small_kernel run beside graph_kernel
-        cudaError_t e = launch_pdl(nms_small_kernel, dim3(B * C), dim3(kSmallThreads), 0, st, A);
+        cudaError_t e = launch_pdl(nms_small_kernel, dim3(C, B), dim3(kSmallThreads), 0, st, A);
         if (e != cudaSuccess) return (int)e;
     }
     note_launch();
