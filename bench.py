@@ -170,7 +170,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
     ap.add_argument('--workload', default='sparse', choices=['sparse', 'dense'])
-    ap.add_argument('--streams', type=int, default=2, help='batches in flight (lanes: stream + workspace + outputs)')
+    ap.add_argument('--streams', type=int, default=4, help='batches in flight (lanes: stream + workspace + outputs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-secondary', action='store_true')

@@ -60,6 +60,11 @@ extern "C" {
 #define RD_NMS_PIXEL_PLUS1  1  /* utils/nms/py_cpu_nms.py:18-36 == nms_kernel.cu:24-32:
                                   +1 widths, IoU = inter/(S_i+S_j-inter), keep IoU <= thr */
 #define RD_NMS_SUPPRESS_EQ  2  /* OR-able: suppress on IoU >= thr (utils/nms/cpu_nms.pyx:65) */
+/* OR-able into the nms_flags of the fused detect stage only: arm_conf / odm_conf hold LOGITS and the
+ * softmax of models/refinedet.py:143-147 (over the last dimension, max-subtracted, fp32) is folded
+ * into the stage — the separate read+write pass over odm_conf disappears.  Scores agree with
+ * torch.softmax to fp32 rounding (the sum is reduced in a different order). */
+#define RD_INPUT_LOGITS     4
 /* output row layout of the fused detect stage */
 #define RD_ROW_BOX_SCORE    0  /* x1,y1,x2,y2,score  (eval_refinedet_coco.py:226) */
 #define RD_ROW_SCORE_BOX    1  /* score,x1,y1,x2,y2  (detection_refinedet.py:106-108) */
@@ -120,8 +125,8 @@ RD_API int rd_detect_fused(const float* arm_loc, const float* arm_conf, const fl
 
 /* Diagnostics twin of rd_detect_fused: records CUDA events between the stage's kernels on
  * `stream`, WAITS for the stage, and writes the device time in ms of
- * {collect_kernel, graph_kernel, sort_kernel + resolve_kernel + nms_large_kernel, 0} to
- * stage_ms_host[4] (host pointer).  The events serialise graph_kernel and sort_kernel, which overlap
+ * {collect_kernel, graph_kernel, nms_small_kernel + nms_large_kernel, 0} to
+ * stage_ms_host[4] (host pointer).  The events serialise graph_kernel and nms_small_kernel, which overlap
  * in rd_detect_fused. */
 RD_API int rd_detect_fused_timed(const float* arm_loc, const float* arm_conf, const float* odm_loc,
                     const float* odm_conf, const float* priors, int B, int P, int C,

@@ -27,6 +27,7 @@ RD_ERR_BAD_ARG, RD_ERR_ALIGNMENT, RD_ERR_UNSUPPORTED, RD_ERR_WORKSPACE = -1, -2,
 RD_MAX_NMS_BOXES = 4096
 RD_MAX_GT = 1024
 RD_NMS_NORMALISED, RD_NMS_PIXEL_PLUS1, RD_NMS_SUPPRESS_EQ = 0, 1, 2
+RD_INPUT_LOGITS = 4
 RD_ROW_BOX_SCORE, RD_ROW_SCORE_BOX = 0, 1
 
 _P = c_void_p

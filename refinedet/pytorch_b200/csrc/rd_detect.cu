@@ -23,6 +23,7 @@
 #include "rd_nms_core.cuh"
 
 #include <atomic>
+#include <cmath>
 
 namespace rd {
 
@@ -205,10 +206,30 @@ struct GraphOut {            // what collect contributes to the per-image suppre
     int flags;
 };
 
+// ARM objectness gate.  Probabilities in: pass unless arm_conf[...,1] <= thre (detection_refinedet.py:41).
+// Logits in (RD_INPUT_LOGITS; the softmax of models/refinedet.py:143-145 folded in): p1 =
+// e1 / (e0 + e1) with e_k = exp(l_k - max), evaluated only when the logit gap d = l1 - l0 is within
+// `margin` of logit(thre) — outside that band the outcome of the fp32 formula is certain.
+struct ArmGate {
+    float thre;
+    float gap_lo, gap_hi;     // d < gap_lo: fails for sure; d > gap_hi: passes for sure (logits only)
+};
+template <bool kLogits>
+__device__ __forceinline__ bool arm_pass(float2 ac, const ArmGate& g) {
+    if (!kLogits) return !(ac.y <= g.thre);
+    const float d = ac.y - ac.x;
+    if (d > g.gap_hi) return true;
+    if (d < g.gap_lo) return false;
+    const float m = fmaxf(ac.x, ac.y);
+    const float e0 = expf(ac.x - m), e1 = expf(ac.y - m);
+    return !(e1 / (e0 + e1) <= g.thre);
+}
+
+template <bool kLogits>
 __global__ void __launch_bounds__(kCollectThreads)
 collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ arm_conf,
                const float4* __restrict__ odm_loc, const float* __restrict__ odm_conf,
-               const float4* __restrict__ priors, int P, int C, int S, int Pn, float obj_thre,
+               const float4* __restrict__ priors, int P, int C, int S, int Pn, ArmGate gate,
                float v0, float v1, float* __restrict__ nsc, uint32_t* header, GraphOut GO) {
     __shared__ float s_tile[kMaxClasses][kTileRows + 1];               // [class][node of the tile], padded
     __shared__ unsigned short s_flat[kSliceAnchors];                   // passing anchors of the slice, anchor order
@@ -223,22 +244,22 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
     const int a0 = s * kSliceAnchors + wib * (32 * kChunks);          // first anchor of this warp
     const size_t img = (size_t)b * P;
     // 1. ARM filter for 32*kChunks anchors; all loads issued before the first use
-    float obj[kChunks];
+    float2 obj[kChunks];
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
         const int a = a0 + ch * 32 + lane;
-        obj[ch] = (a < P) ? ldg_stream2(arm_conf + img + a).y : -INFINITY;
+        obj[ch] = (a < P) ? ldg_stream2(arm_conf + img + a) : make_float2(0.f, 0.f);
     }
     //    ... and the number of passing anchors in the preceding slices of the image
     int before = 0;
     {
         const int nprev = s * kSliceAnchors;                           // multiple of kCollectThreads * 4
         for (int a = threadIdx.x; a < nprev; a += kCollectThreads * 4) {
-            float o4[4];
+            float2 o4[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o4[k] = __ldg(arm_conf + img + a + k * kCollectThreads).y;
+            for (int k = 0; k < 4; ++k) o4[k] = __ldg(arm_conf + img + a + k * kCollectThreads);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) before += !(o4[k] <= obj_thre) ? 1 : 0;
+            for (int k = 0; k < 4; ++k) before += arm_pass<kLogits>(o4[k], gate) ? 1 : 0;
         }
         before = __reduce_add_sync(kFullMask, before);
     }
@@ -247,7 +268,7 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
         const int a = a0 + ch * 32 + lane;
-        const bool pass = (a < P) && !(obj[ch] <= obj_thre);           // kept unless arm_conf[...,1] <= thre (:41)
+        const bool pass = (a < P) && arm_pass<kLogits>(obj[ch], gate);
         pmask[ch] = __ballot_sync(kFullMask, pass);
         npass += __popc(pmask[ch]);
     }
@@ -299,6 +320,30 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
                 for (int sgm = 0; sgm < 4; ++sgm) {
                     const int c = sgm * 32 + lane;
                     v[k][sgm] = (rv && sgm < nseg && c < C) ? ldg_stream1(row + c) : 0.f;
+                }
+            }
+            if (kLogits) {
+                // softmax over the class dimension (models/refinedet.py:146-147): max, exp(x - max), sum, divide;
+                // xor-butterfly reductions, so every lane holds the same max / sum and the order is fixed
+#pragma unroll
+                for (int k = 0; k < kRowBatch; ++k) {
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int sgm = 0; sgm < 4; ++sgm)
+                        if (sgm < nseg && sgm * 32 + lane < C) m = fmaxf(m, v[k][sgm]);
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, d));
+                    float sum = 0.f;
+#pragma unroll
+                    for (int sgm = 0; sgm < 4; ++sgm) {
+                        const bool on = sgm < nseg && sgm * 32 + lane < C;
+                        v[k][sgm] = on ? expf(v[k][sgm] - m) : 0.f;
+                        sum += v[k][sgm];
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
+#pragma unroll
+                    for (int sgm = 0; sgm < 4; ++sgm) v[k][sgm] = v[k][sgm] / sum;
                 }
             }
 #pragma unroll
@@ -645,16 +690,25 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
         const float* row = A.nsc + (size_t)bc * A.Pn;
         if (tid == 0) s_cnt[0] = 0;
         __syncthreads();
-        for (int i0 = 0; i0 < N; i0 += kLargeThreads) {
-            const int i = i0 + tid;
-            const float v = i < N ? __ldg(row + i) : -INFINITY;
-            const bool pass = v > A.conf_thresh;
-            const unsigned bal = __ballot_sync(kFullMask, pass);
-            if (bal) {
-                int wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&s_cnt[0], __popc(bal));
-                wbase = __shfl_sync(kFullMask, wbase, 0);
-                if (pass) keys[wbase + __popc(bal & ((1u << lane) - 1u))] = make_key(v, (uint32_t)i);
+        constexpr int kScanUnroll = 4;                            // independent loads in flight per thread
+        for (int i0 = 0; i0 < N; i0 += kLargeThreads * kScanUnroll) {
+            float v[kScanUnroll];
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                const int i = i0 + u * kLargeThreads + tid;
+                v[u] = i < N ? __ldg(row + i) : -INFINITY;
+            }
+#pragma unroll
+            for (int u = 0; u < kScanUnroll; ++u) {
+                const int i = i0 + u * kLargeThreads + tid;
+                const bool pass = v[u] > A.conf_thresh;
+                const unsigned bal = __ballot_sync(kFullMask, pass);
+                if (bal) {
+                    int wbase = 0;
+                    if (lane == 0) wbase = atomicAdd(&s_cnt[0], __popc(bal));
+                    wbase = __shfl_sync(kFullMask, wbase, 0);
+                    if (pass) keys[wbase + __popc(bal & ((1u << lane) - 1u))] = make_key(v[u], (uint32_t)i);
+                }
             }
         }
         __syncthreads();
@@ -857,9 +911,23 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     GO.nnodes = ws.nnodes; GO.gtab = ws.gtab; GO.nbox = ws.nbox; GO.nanc = ws.nanc; GO.ncr = ws.ncr;
     GO.adjn = ws.adjn; GO.img_flag = ws.flag; GO.img_scale = img_scale; GO.thr = nms_thresh; GO.flags = nms_flags;
     if (ev) cudaEventRecord(ev[0], st);
-    collect_kernel<<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
-        (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
-        P, C, ws.S, ws.Pn, objectness_thre, v0, v1, ws.nsc, ws.header, GO);
+    ArmGate gate;
+    gate.thre = objectness_thre;
+    gate.gap_lo = INFINITY; gate.gap_hi = -INFINITY;                  // always evaluate the formula ...
+    if (objectness_thre > 0.f && objectness_thre < 1.f) {             // ... unless logit(thre) exists
+        const double lg = std::log((double)objectness_thre / (1.0 - (double)objectness_thre));
+        const double margin = 1e-3 * (1.0 + std::fabs(lg));           // >> the fp32 error of the formula (~1e-6)
+        gate.gap_lo = (float)(lg - margin);
+        gate.gap_hi = (float)(lg + margin);
+    }
+    if (nms_flags & RD_INPUT_LOGITS)
+        collect_kernel<true><<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
+            (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
+            P, C, ws.S, ws.Pn, gate, v0, v1, ws.nsc, ws.header, GO);
+    else
+        collect_kernel<false><<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
+            (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
+            P, C, ws.S, ws.Pn, gate, v0, v1, ws.nsc, ws.header, GO);
     note_launch();
     RD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[1], st);

@@ -245,14 +245,17 @@ class Detect_RefineDet(object):
         return self.boxes, self.scores
 
     def detect(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale=None,
-               force_cpu_semantics=False):
+               force_cpu_semantics=False, logits=False):
         """Fused detect stage as evaluated (eval_refinedet_coco.py:205-232), whole batch:
         ARM filter, two-stage decode, ``boxes *= scale``, per class ``score > conf_thresh``,
         top ``top_k``, pixel(+1) NMS at ``nms_thresh``, first ``keep_top_k`` rows per class.
 
         ``scale``: None, a 4-vector, or ``[B,4]`` (x,y,x,y image size).  The inputs are NOT
-        modified.  Returns a :class:`Detections` with rows ``x1,y1,x2,y2,score``."""
-        flags = _ffi.RD_NMS_PIXEL_PLUS1 | (_ffi.RD_NMS_SUPPRESS_EQ if force_cpu_semantics else 0)
+        modified.  ``logits=True``: ``arm_conf_data`` / ``odm_conf_data`` are the head outputs BEFORE
+        ``models/refinedet.py:143-147``'s softmax, which is folded into the stage (the extra read+write
+        pass over ``odm_conf`` disappears).  Returns a :class:`Detections` with rows ``x1,y1,x2,y2,score``."""
+        flags = _ffi.RD_NMS_PIXEL_PLUS1 | (_ffi.RD_NMS_SUPPRESS_EQ if force_cpu_semantics else 0) | \
+            (_ffi.RD_INPUT_LOGITS if logits else 0)
         return self._fused(arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale, flags,
                            _ffi.RD_ROW_BOX_SCORE, self.keep_top_k)
 
@@ -395,13 +398,14 @@ class Detect_RefineDet(object):
                           torch.empty(B, C, max_out, dtype=torch.int32, device=device), row_layout)
 
     def plan(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale=None,
-             workspace=None, out=None, force_cpu_semantics=False):
+             workspace=None, out=None, force_cpu_semantics=False, logits=False):
         """:meth:`detect` for FIXED input buffers, captured once (``rd_detect_plan_create``): the returned
         :class:`DetectPlan` replays the whole launch chain with one driver call per batch.  The tensors are
         referenced, not copied — refill them in place between replays.  Plans that share ``workspace`` /
         ``out`` must be replayed on the same stream; give every batch in flight its own pair
         (:meth:`new_workspace`, :meth:`new_outputs`)."""
-        flags = _ffi.RD_NMS_PIXEL_PLUS1 | (_ffi.RD_NMS_SUPPRESS_EQ if force_cpu_semantics else 0)
+        flags = _ffi.RD_NMS_PIXEL_PLUS1 | (_ffi.RD_NMS_SUPPRESS_EQ if force_cpu_semantics else 0) | \
+            (_ffi.RD_INPUT_LOGITS if logits else 0)
         for name, t in (('arm_loc_data', arm_loc_data), ('arm_conf_data', arm_conf_data),
                         ('odm_loc_data', odm_loc_data), ('odm_conf_data', odm_conf_data)):
             if not t.is_contiguous() or t.data_ptr() % 16:

@@ -6,30 +6,38 @@ import numpy as np
 import torch
 
 
-def detect_inputs(seed, B, P, C, kind='sparse', arm_shift=-8.0):
-    """Returns arm_loc[B,P,4], arm_conf[B,P,2], odm_loc[B,P,4], odm_conf[B,P,C] (softmaxed).
+def detect_logits(seed, B, P, C, kind='sparse', arm_shift=-8.0):
+    """Returns arm_loc[B,P,4], arm_logits[B,P,2], odm_loc[B,P,4], odm_logits[B,P,C]: the head outputs
+    BEFORE the softmax of models/refinedet.py:143-147 (the ``RD_INPUT_LOGITS`` form of the stage).
 
-    ``dense``  : loc = 0.5 randn, arm/odm conf = softmax(3 randn)          (stress: ~86 % pass ARM)
+    ``dense``  : loc = 0.5 randn, arm/odm logits = 3 randn                 (stress: ~86 % pass ARM)
     ``sparse`` : loc = randn, ARM logit gap 2 randn + arm_shift, ODM logits 1.5 randn with +4 on
                  class 0                                                   (realistic: ~4 % pass ARM)
     """
     g = torch.Generator().manual_seed(int(seed))
     if kind == 'sparse':
         d = 2.0 * torch.randn(B, P, generator=g) + arm_shift
-        arm_conf = torch.softmax(torch.stack([torch.zeros(B, P), d], -1), -1)
-        logits = 1.5 * torch.randn(B, P, C, generator=g)
-        logits[..., 0] += 4.0
-        odm_conf = torch.softmax(logits, -1)
+        arm_logits = torch.stack([torch.zeros(B, P), d], -1)
+        odm_logits = 1.5 * torch.randn(B, P, C, generator=g)
+        odm_logits[..., 0] += 4.0
         loc_s = 1.0
     elif kind == 'dense':
-        arm_conf = torch.softmax(3 * torch.randn(B, P, 2, generator=g), -1)
-        odm_conf = torch.softmax(3 * torch.randn(B, P, C, generator=g), -1)
+        arm_logits = 3 * torch.randn(B, P, 2, generator=g)
+        odm_logits = 3 * torch.randn(B, P, C, generator=g)
         loc_s = 0.5
     else:
         raise ValueError(kind)
     arm_loc = loc_s * torch.randn(B, P, 4, generator=g)
     odm_loc = loc_s * torch.randn(B, P, 4, generator=g)
-    return arm_loc.contiguous(), arm_conf.contiguous(), odm_loc.contiguous(), odm_conf.contiguous()
+    return arm_loc.contiguous(), arm_logits.contiguous(), odm_loc.contiguous(), odm_logits.contiguous()
+
+
+def detect_inputs(seed, B, P, C, kind='sparse', arm_shift=-8.0):
+    """Returns arm_loc[B,P,4], arm_conf[B,P,2], odm_loc[B,P,4], odm_conf[B,P,C] (softmaxed):
+    :func:`detect_logits` followed by the model's softmax."""
+    arm_loc, arm_logits, odm_loc, odm_logits = detect_logits(seed, B, P, C, kind, arm_shift)
+    return (arm_loc, torch.softmax(arm_logits, -1).contiguous(), odm_loc,
+            torch.softmax(odm_logits, -1).contiguous())
 
 
 def targets(seed, B, G, num_classes, wh_lo=0.02, wh_hi=0.17):

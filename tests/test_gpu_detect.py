@@ -201,6 +201,56 @@ def test_fused_detect_vs_oracle(rd, kind, B, size, C, top_k, keep):
             assert torch.equal(res2.anchors[b, c, :n], res.anchors[b, c, :n])
 
 
+@pytest.mark.parametrize('arm_shift,B,size,C', [(-8.0, 3, '320', 21), (-8.0, 2, '512', 81), (-6.0, 2, '320', 5)])
+def test_fused_detect_logits_in(rd, arm_shift, B, size, C):
+    """f-1: ``logits=True`` folds the softmax of models/refinedet.py:143-147 into the stage.
+    Oracle = torch.softmax on the CPU followed by the a4 oracle.  The fused softmax reduces the row sum in
+    a different order, so a score may differ from torch's in the last bits (tolerance 2e-6 relative,
+    written here); a problem whose outcome could depend on those bits — a score within 1e-6 relative of
+    the threshold or of another candidate's score, an ARM probability within 1e-6 relative of the
+    objectness threshold — is excluded from the exact comparison, and at least 85 % must remain."""
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward()
+    P = priors.shape[0]
+    conf_thr, nms_thr, obj_thr, top_k, keep = 0.01, 0.45, 0.01, 1000, 500
+    arm_loc, arm_lg, odm_loc, odm_lg = gen.detect_logits(991 + C, B, P, C, 'sparse', arm_shift=arm_shift)
+    arm_conf, odm_conf = torch.softmax(arm_lg, -1), torch.softmax(odm_lg, -1)
+    det = rd.Detect_RefineDet(C, int(size), 0, top_k, conf_thr, nms_thr, obj_thr, keep)
+    scale = np.array([float(size)] * 4, np.float32)
+    res = det.detect(arm_loc.cuda(), arm_lg.cuda(), odm_loc.cuda(), odm_lg.cuda(), priors.cuda(), scale=scale,
+                     logits=True)
+    # reference: probabilities from torch.softmax, boxes from the GPU a3 kernel (same device function)
+    conf_a3 = odm_conf.clone().cuda()
+    g_boxes, g_scores = det.forward(arm_loc.cuda(), arm_conf.cuda(), odm_loc.cuda(), conf_a3, priors.cuda())
+    o_scores = g_scores.cpu().numpy()
+    counts, anchors, rows = _oracle_a4(g_boxes.cpu().numpy(), o_scores, scale, conf_thr, top_k, nms_thr, keep)
+    g_counts = res.counts.cpu().numpy()
+    g_anchor = res.anchors.cpu().numpy()
+    g_dets = res.dets.cpu().numpy()
+    eps = 1e-6
+    p1 = torch.softmax(arm_lg.double(), -1)[..., 1].numpy()
+    s64 = torch.softmax(odm_lg.double(), -1).numpy()
+    checked = total = 0
+    for b in range(B):
+        arm_fragile = bool((np.abs(p1[b] - obj_thr) <= eps * obj_thr).any())
+        passing = p1[b] > obj_thr
+        for c in range(1, C):
+            total += 1
+            v = np.sort(s64[b, passing, c])
+            v = v[v > conf_thr * (1 - 2 * eps)]
+            fragile = arm_fragile or bool((np.abs(v - conf_thr) <= eps * conf_thr).any()) or \
+                bool((np.diff(v) <= eps * v[1:]).any())
+            if fragile:
+                continue
+            checked += 1
+            n = counts[b, c]
+            assert g_counts[b, c] == n, (b, c)
+            assert np.array_equal(g_anchor[b, c, :n], anchors[b, c]), (b, c)
+            assert np.array_equal(g_dets[b, c, :n, :4], rows[b, c][:, :4]), (b, c)
+            np.testing.assert_allclose(g_dets[b, c, :n, 4], rows[b, c][:, 4], rtol=2e-6, atol=0)
+    assert checked >= 0.85 * total, (checked, total)
+    assert (g_counts[:, 0] == 0).all()
+
+
 def test_forward_python_nms_vs_oracle(rd):
     size, C, B, top_k = '320', 5, 2, 200
     priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward()
