@@ -213,6 +213,34 @@ RD_API int rd_refine_match(const float* truths, const float* labels, const int* 
 RD_API int rd_hnm_select(const float* loss_c, const unsigned char* pos, int B, int P,
                   int negpos_ratio, unsigned char* neg_out, int* num_pos_out, void* stream);
 
+/* ---- loss tail of RefineDetMultiBoxLoss (refinedet_multibox_loss.py:96-139) ---------- */
+/* Per row r of conf[rows,C] (rows = B*P, 2 <= C <= 128):
+ *   lse_out[r] = log(sum_c exp(conf[r,c]))         (log_sum_exp, box_utils.py:208-216; max-subtracted)
+ *   ce_out[r]  = lse_out[r] - conf[r, conf_t[r]]   (the mining loss of :114 = the cross-entropy term of :130)
+ *   pos_out[r] = conf_t[r] > 0, and — when arm_conf[rows,2] (LOGITS) is given — not
+ *                softmax(arm_conf[r])[1] <= theta  (:96-101)                                   */
+RD_API int rd_conf_loss(const float* conf, const long long* conf_t, const float* arm_conf, float theta,
+                 long long rows, int C, float* ce_out, float* lse_out, unsigned char* pos_out,
+                 void* stream);
+/* loss_l = sum_{pos} SmoothL1(loc - loc_t) / N (:105-110), loss_c = sum_{pos|neg} ce / N (:126-130),
+ * N = sum(num_pos) (:134); all three are written as device scalars; N < 1 gives zeros (:135-136).
+ * fp64 accumulation in a fixed order (deterministic). */
+RD_API size_t rd_multibox_loss_workspace_bytes(int B);
+RD_API int rd_multibox_loss_reduce(const float* loc, const float* loc_t, const float* ce,
+                 const unsigned char* pos, const unsigned char* neg, const int* num_pos, int B, int P,
+                 void* workspace, size_t workspace_bytes, float* loss_l, float* loss_c, float* n_out,
+                 void* stream);
+/* backward of the two losses (what autograd derives from :105-138): with g_l = *grad_loss_l,
+ * g_c = *grad_loss_c (device scalars, either may be NULL = 0) and N = *n_dev,
+ *   grad_conf[r,:] = (softmax(conf[r,:]) - onehot(conf_t[r])) * g_c / N   on pos|neg rows, 0 elsewhere
+ *   grad_loc[r,:]  = clamp(loc[r,:] - loc_t[r,:], -1, 1) * g_l / N        on pos rows, 0 elsewhere
+ * Either output may be NULL.  Every element of a given output is written. */
+RD_API int rd_multibox_loss_backward(const float* loc, const float* loc_t, const float* conf,
+                 const long long* conf_t, const float* lse, const unsigned char* pos,
+                 const unsigned char* neg, const float* grad_loss_l, const float* grad_loss_c,
+                 const float* n_dev, long long rows, int C, float* grad_loc, float* grad_conf,
+                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -391,6 +391,25 @@ def multibox_loss(predictions, targets, num_classes, overlap_thresh=0.5,
                 loss_c_rows=loss_c_mined, N=N)
 
 
+def multibox_loss_grads(loc_data, conf_data, loc_t, conf_t, pos, neg, N):
+    """Gradients autograd derives from refinedet_multibox_loss.py:105-138 for
+    ``loss_l + loss_c`` (both divided by N): SmoothL1'(d) = clamp(d, -1, 1) on the positives,
+    softmax(x) - onehot(t) on ``pos | neg``, zero elsewhere.  float64 inside, returned as float32."""
+    loc_data, conf_data, loc_t = _f(loc_data), _f(conf_data), _f(loc_t)
+    g_loc = np.zeros(loc_data.shape, np.float64)
+    g_conf = np.zeros(conf_data.shape, np.float64)
+    if N >= 1:
+        d = (loc_data[pos] - loc_t[pos]).astype(np.float64)
+        g_loc[pos] = np.clip(d, -1.0, 1.0) / N
+        sel = pos | neg
+        x = conf_data[sel].astype(np.float64)
+        e = np.exp(x - x.max(1, keepdims=True))
+        sm = e / e.sum(1, keepdims=True)
+        sm[np.arange(sm.shape[0]), conf_t[sel]] -= 1.0
+        g_conf[sel] = sm / N
+    return g_loc.astype(F32), g_conf.astype(F32)
+
+
 # ----------------------------------------------------------------------------
 # layers/functions/prior_box.py + data/config.py (input contract a0)
 # ----------------------------------------------------------------------------

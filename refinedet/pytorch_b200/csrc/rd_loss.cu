@@ -1,0 +1,327 @@
+// rd_loss.cu — tail of RefineDetMultiBoxLoss on B200 (sm_100a), forward and backward.
+//
+// Replaces (reference paths): layers/modules/refinedet_multibox_loss.py:96-139 — the ARM-theta gate
+// of the positives (:96-101), SmoothL1 over the positives (:105-110), the per-anchor confidence loss
+// log_sum_exp(conf) - conf.gather(conf_t) (:113-114, layers/box_utils.py:208-216), the cross-entropy
+// over pos | neg (:126-130), the division by N (:134-138) — and their autograd backward.
+//
+// Kernels
+//   conf_loss_kernel      one pass over conf[B*P,C]: per row  lse = log(sum exp(x - max)) + max,
+//                         ce = lse - x[conf_t]  (the mining loss of :114 AND the cross-entropy term of
+//                         :130 — F.cross_entropy(x, t) is the same quantity), pos = conf_t > 0 gated by
+//                         softmax(arm_conf)[1] > theta.  Warp per row, lane = class (C = 2: thread per row).
+//                         The reference subtracts the GLOBAL max of the tensor (box_utils.py:215); the row
+//                         max used here is the same value mathematically and at least as accurate in fp32.
+//   loss_reduce_kernel    per image: sum of ce over pos | neg, SmoothL1 over pos (fp64 accumulation,
+//                         fixed reduction tree -> deterministic)
+//   loss_final_kernel     sums the per-image partials in order, N = sum(num_pos), divides
+//   loss_backward_kernel  d loss_c / d conf = (softmax(x) - onehot(t)) * g_c / N on pos | neg rows,
+//                         d loss_l / d loc = clamp(loc - loc_t, -1, 1) * g_l / N on pos rows, zeros
+//                         elsewhere; every element of both gradients is written exactly once
+#include "rd_common.cuh"
+
+namespace rd {
+
+constexpr int kLossThreads = 256;
+constexpr int kLossRowBatch = 4;          // conf rows in flight per warp
+constexpr int kLossMaxClasses = 128;
+
+// softmax(arm_conf)[1] <= theta (refinedet_multibox_loss.py:98-101), fp32, max-subtracted like F.softmax
+__device__ __forceinline__ bool arm_filtered(float2 a, float theta) {
+    const float m = fmaxf(a.x, a.y);
+    const float e0 = expf(a.x - m), e1 = expf(a.y - m);
+    return e1 / (e0 + e1) <= theta;
+}
+
+// generic C (3..128): warp per row, lane = class
+__global__ void __launch_bounds__(kLossThreads)
+conf_loss_kernel(const float* __restrict__ conf, const long long* __restrict__ conf_t,
+                 const float2* __restrict__ arm_conf, float theta, long long rows, int C,
+                 float* __restrict__ ce_out, float* __restrict__ lse_out, unsigned char* __restrict__ pos_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * kLossThreads + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * kLossThreads) >> 5;
+    const int nseg = (C + 31) >> 5;
+    for (long long r0 = warp_global * kLossRowBatch; r0 < rows; r0 += nwarps * kLossRowBatch) {
+        float v[kLossRowBatch][4];
+#pragma unroll
+        for (int k = 0; k < kLossRowBatch; ++k) {
+            const long long r = r0 + k;
+            const float* row = conf + (r < rows ? r : 0) * C;
+#pragma unroll
+            for (int sgm = 0; sgm < 4; ++sgm) {
+                const int c = sgm * 32 + lane;
+                v[k][sgm] = (r < rows && sgm < nseg && c < C) ? ldg_stream1(row + c) : -INFINITY;
+            }
+        }
+        // lane k of the warp owns the scalar outputs of row r0 + k
+        long long t_own = 0;
+        float2 arm_own = make_float2(0.f, 0.f);
+        if (lane < kLossRowBatch && r0 + lane < rows) {
+            t_own = conf_t[r0 + lane];
+            if (arm_conf && t_own > 0) arm_own = __ldg(arm_conf + r0 + lane);
+        }
+        float ce_own = 0.f, lse_own = 0.f;
+#pragma unroll
+        for (int k = 0; k < kLossRowBatch; ++k) {
+            if (r0 + k >= rows) break;
+            float m = fmaxf(fmaxf(v[k][0], v[k][1]), fmaxf(v[k][2], v[k][3]));
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, d));
+            float s = 0.f;
+#pragma unroll
+            for (int sgm = 0; sgm < 4; ++sgm) s += (sgm < nseg && sgm * 32 + lane < C) ? expf(v[k][sgm] - m) : 0.f;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
+            const float lse = logf(s) + m;
+            const int t = (int)__shfl_sync(kFullMask, (int)t_own, k);
+            // x[t]: held by lane t & 31 in segment t >> 5
+            float xt = v[k][0];
+            if ((t >> 5) == 1) xt = v[k][1];
+            if ((t >> 5) == 2) xt = v[k][2];
+            if ((t >> 5) == 3) xt = v[k][3];
+            xt = __shfl_sync(kFullMask, xt, t & 31);
+            if (lane == k) { ce_own = lse - xt; lse_own = lse; }
+        }
+        if (lane < kLossRowBatch && r0 + lane < rows) {
+            const long long r = r0 + lane;
+            ce_out[r] = ce_own;
+            lse_out[r] = lse_own;
+            bool pos = t_own > 0;
+            if (pos && arm_conf && arm_filtered(arm_own, theta)) pos = false;
+            pos_out[r] = pos ? 1 : 0;
+        }
+    }
+}
+
+// C == 2 (the ARM criterion): thread per row
+__global__ void __launch_bounds__(kLossThreads)
+conf_loss2_kernel(const float2* __restrict__ conf, const long long* __restrict__ conf_t,
+                  const float2* __restrict__ arm_conf, float theta, long long rows,
+                  float* __restrict__ ce_out, float* __restrict__ lse_out, unsigned char* __restrict__ pos_out) {
+    const long long r = (long long)blockIdx.x * kLossThreads + threadIdx.x;
+    if (r >= rows) return;
+    const float2 x = ldg_stream2(conf + r);
+    const long long t = conf_t[r];
+    const float m = fmaxf(x.x, x.y);
+    const float s = expf(x.x - m) + expf(x.y - m);
+    const float lse = logf(s) + m;
+    ce_out[r] = lse - (t == 1 ? x.y : x.x);
+    lse_out[r] = lse;
+    bool pos = t > 0;
+    if (pos && arm_conf && arm_filtered(__ldg(arm_conf + r), theta)) pos = false;
+    pos_out[r] = pos ? 1 : 0;
+}
+
+// SmoothL1 (beta = 1, reduction = sum), F.smooth_l1_loss: 0.5 d^2 if |d| < 1 else |d| - 0.5
+__device__ __forceinline__ double smooth_l1(float p, float t) {
+    const float d = p - t;
+    const float a = fabsf(d);
+    return a < 1.0f ? 0.5 * (double)d * (double)d : (double)a - 0.5;
+}
+
+// grid = B: partial[b] = { sum_{pos} SmoothL1(loc - loc_t), sum_{pos|neg} ce }
+__global__ void __launch_bounds__(kLossThreads)
+loss_reduce_kernel(const float4* __restrict__ loc, const float4* __restrict__ loc_t, const float* __restrict__ ce,
+                   const unsigned char* __restrict__ pos, const unsigned char* __restrict__ neg, int P,
+                   double* __restrict__ partial) {
+    __shared__ double s_l[kLossThreads / 32], s_c[kLossThreads / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t img = (size_t)b * P;
+    double al = 0.0, ac = 0.0;
+    for (int i = tid; i < P; i += kLossThreads) {
+        const bool p = pos[img + i] != 0;
+        const bool n = neg[img + i] != 0;
+        if (p | n) ac += (double)ce[img + i];
+        if (p) {
+            const float4 x = loc[img + i], t = loc_t[img + i];
+            al += smooth_l1(x.x, t.x) + smooth_l1(x.y, t.y) + smooth_l1(x.z, t.z) + smooth_l1(x.w, t.w);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        al += __shfl_xor_sync(kFullMask, al, d);
+        ac += __shfl_xor_sync(kFullMask, ac, d);
+    }
+    if (lane == 0) { s_l[warp] = al; s_c[warp] = ac; }
+    __syncthreads();
+    if (tid == 0) {
+        double tl = 0.0, tc = 0.0;
+        for (int w = 0; w < kLossThreads / 32; ++w) { tl += s_l[w]; tc += s_c[w]; }
+        partial[2 * b] = tl;
+        partial[2 * b + 1] = tc;
+    }
+}
+
+// one thread: fixed summation order.  N = sum(num_pos) (:134); N < 1 -> zeros (:135-136)
+__global__ void loss_final_kernel(const double* __restrict__ partial, const int* __restrict__ num_pos, int B,
+                                  float* loss_l, float* loss_c, float* n_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double tl = 0.0, tc = 0.0;
+    long long n = 0;
+    for (int b = 0; b < B; ++b) { tl += partial[2 * b]; tc += partial[2 * b + 1]; n += num_pos[b]; }
+    const float N = (float)n;
+    *n_out = N;
+    *loss_l = n > 0 ? (float)tl / N : 0.f;
+    *loss_c = n > 0 ? (float)tc / N : 0.f;
+}
+
+// gradients.  One warp per kLossRowBatch rows; conf rows of unselected anchors are never read.
+__global__ void __launch_bounds__(kLossThreads)
+loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ loc_t,
+                     const float* __restrict__ conf, const long long* __restrict__ conf_t,
+                     const float* __restrict__ lse, const unsigned char* __restrict__ pos,
+                     const unsigned char* __restrict__ neg, const float* __restrict__ g_l,
+                     const float* __restrict__ g_c, const float* __restrict__ n_dev, long long rows, int C,
+                     float4* __restrict__ grad_loc, float* __restrict__ grad_conf) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * kLossThreads + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * kLossThreads) >> 5;
+    const float N = *n_dev;
+    const float sl = (g_l && N > 0.f) ? *g_l / N : 0.f;
+    const float sc = (g_c && N > 0.f) ? *g_c / N : 0.f;
+    const int nseg = (C + 31) >> 5;
+    for (long long r0 = warp_global * 32; r0 < rows; r0 += nwarps * 32) {
+        // 32 rows per step: lane l owns the flags (and the loc gradient) of row r0 + l
+        const long long r = r0 + lane;
+        bool p = false, sel = false;
+        if (r < rows) {
+            p = pos[r] != 0;
+            sel = p || neg[r] != 0;
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grad_loc) {
+                if (p) {
+                    const float4 x = loc[r], t = loc_t[r];
+                    g.x = fminf(fmaxf(x.x - t.x, -1.f), 1.f) * sl;      // d SmoothL1 / d x = clamp(x - t, -1, 1)
+                    g.y = fminf(fmaxf(x.y - t.y, -1.f), 1.f) * sl;
+                    g.z = fminf(fmaxf(x.z - t.z, -1.f), 1.f) * sl;
+                    g.w = fminf(fmaxf(x.w - t.w, -1.f), 1.f) * sl;
+                }
+                grad_loc[r] = g;
+            }
+        }
+        if (!grad_conf) continue;
+        const unsigned selmask = __ballot_sync(kFullMask, sel);
+        const int nvalid = (int)min((long long)32, rows - r0);
+        // zeros for the unselected rows: lanes stride over the 32*C contiguous elements
+        float* base = grad_conf + r0 * C;
+        const int nelem = nvalid * C;
+        const int nvec = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) ? (nelem >> 2) : 0;
+        {
+            // float4 stores; (row, class) of element 4*q tracked incrementally (no division in the loop)
+            int e0 = lane * 4;
+            int rr = e0 / C, c = e0 - rr * C;
+            const int drr = 128 / C, dc = 128 - drr * C;
+            for (int q = lane; q < nvec; q += 32) {
+                int r1 = rr, c1 = c;
+                unsigned sm = 0;                   // bit k: element k belongs to a selected row
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    sm |= ((selmask >> r1) & 1u) << k;
+                    if (++c1 == C) { c1 = 0; ++r1; }
+                }
+                if (sm == 0) {
+                    *reinterpret_cast<float4*>(base + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (!((sm >> k) & 1u)) base[4 * q + k] = 0.f;
+                }
+                rr += drr; c += dc;
+                if (c >= C) { c -= C; ++rr; }
+            }
+        }
+        for (int e = nvec * 4 + lane; e < nelem; e += 32) {      // tail / unaligned base
+            const int rr = e / C;
+            if (!((selmask >> rr) & 1u)) base[e] = 0.f;
+        }
+        // selected rows: softmax(x) - onehot(t), lane = class
+        unsigned m = selmask;
+        while (m) {
+            const int rr = __ffs(m) - 1;
+            m &= m - 1;
+            const long long row = r0 + rr;
+            const float l = lse[row];
+            const int t = (int)conf_t[row];
+            const float* x = conf + row * C;
+            float* g = grad_conf + row * C;
+#pragma unroll
+            for (int sgm = 0; sgm < 4; ++sgm) {
+                const int c = sgm * 32 + lane;
+                if (sgm < nseg && c < C) g[c] = (expf(x[c] - l) - (c == t ? 1.f : 0.f)) * sc;
+            }
+        }
+    }
+}
+
+}  // namespace rd
+
+using namespace rd;
+
+extern "C" {
+
+size_t rd_multibox_loss_workspace_bytes(int B) { return B > 0 ? (size_t)B * 2 * sizeof(double) : 0; }
+
+int rd_conf_loss(const float* conf, const long long* conf_t, const float* arm_conf, float theta, long long rows,
+                 int C, float* ce_out, float* lse_out, unsigned char* pos_out, void* stream) {
+    if (!conf || !conf_t || !ce_out || !lse_out || !pos_out || rows <= 0 || C < 2) return RD_ERR_BAD_ARG;
+    if (C > kLossMaxClasses) return RD_ERR_UNSUPPORTED;
+    if (arm_conf && ((uintptr_t)arm_conf & 7)) return RD_ERR_ALIGNMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C == 2) {
+        if ((uintptr_t)conf & 7) return RD_ERR_ALIGNMENT;
+        const long long blocks = (rows + kLossThreads - 1) / kLossThreads;
+        conf_loss2_kernel<<<(unsigned)blocks, kLossThreads, 0, st>>>((const float2*)conf, conf_t, (const float2*)arm_conf,
+                                                                     theta, rows, ce_out, lse_out, pos_out);
+    } else {
+        const long long warps = (rows + kLossRowBatch - 1) / kLossRowBatch;
+        long long blocks = (warps * 32 + kLossThreads - 1) / kLossThreads;
+        if (blocks > 148 * 64) blocks = 148 * 64;
+        conf_loss_kernel<<<(unsigned)blocks, kLossThreads, 0, st>>>(conf, conf_t, (const float2*)arm_conf, theta, rows, C,
+                                                                    ce_out, lse_out, pos_out);
+    }
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+int rd_multibox_loss_reduce(const float* loc, const float* loc_t, const float* ce, const unsigned char* pos,
+                            const unsigned char* neg, const int* num_pos, int B, int P, void* workspace,
+                            size_t workspace_bytes, float* loss_l, float* loss_c, float* n_out, void* stream) {
+    if (!loc || !loc_t || !ce || !pos || !neg || !num_pos || !workspace || !loss_l || !loss_c || !n_out || B <= 0 ||
+        P <= 0)
+        return RD_ERR_BAD_ARG;
+    if (((uintptr_t)loc | (uintptr_t)loc_t) & 15) return RD_ERR_ALIGNMENT;
+    if ((uintptr_t)workspace & 7) return RD_ERR_ALIGNMENT;
+    if (workspace_bytes < rd_multibox_loss_workspace_bytes(B)) return RD_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    loss_reduce_kernel<<<B, kLossThreads, 0, st>>>((const float4*)loc, (const float4*)loc_t, ce, pos, neg, P,
+                                                   (double*)workspace);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    loss_final_kernel<<<1, 32, 0, st>>>((const double*)workspace, num_pos, B, loss_l, loss_c, n_out);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+int rd_multibox_loss_backward(const float* loc, const float* loc_t, const float* conf, const long long* conf_t,
+                              const float* lse, const unsigned char* pos, const unsigned char* neg,
+                              const float* grad_loss_l, const float* grad_loss_c, const float* n_dev,
+                              long long rows, int C, float* grad_loc, float* grad_conf, void* stream) {
+    if (!loc || !loc_t || !conf || !conf_t || !lse || !pos || !neg || !n_dev || rows <= 0 || C < 2)
+        return RD_ERR_BAD_ARG;
+    if (!grad_loc && !grad_conf) return 0;
+    if (C > kLossMaxClasses) return RD_ERR_UNSUPPORTED;
+    if (((uintptr_t)loc | (uintptr_t)loc_t | (uintptr_t)grad_loc) & 15) return RD_ERR_ALIGNMENT;
+    long long blocks = ((rows + 31) / 32 * 32 + kLossThreads - 1) / kLossThreads;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    loss_backward_kernel<<<(unsigned)blocks, kLossThreads, 0, (cudaStream_t)stream>>>(
+        (const float4*)loc, (const float4*)loc_t, conf, conf_t, lse, pos, neg, grad_loss_l, grad_loss_c, n_dev, rows, C,
+        (float4*)grad_loc, grad_conf);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

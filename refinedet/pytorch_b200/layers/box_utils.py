@@ -74,10 +74,38 @@ def decode(loc, priors, variances):
     return out
 
 
+def conf_loss(conf, conf_t, arm_conf=None, theta=0.01):
+    """One pass over ``conf[..., C]`` (refinedet_multibox_loss.py:96-101,113-114): returns
+    ``(ce, lse, pos)`` shaped like ``conf_t`` — ``lse = log_sum_exp(conf)``, ``ce = lse - conf.gather(conf_t)``
+    (the mining loss AND the cross-entropy term), ``pos = conf_t > 0`` gated by
+    ``softmax(arm_conf)[..., 1] > theta`` when ``arm_conf`` (logits) is given.  No autograd."""
+    conf = require_cuda_f32(conf, 'conf', align=8)
+    C = conf.shape[-1]
+    if conf_t.dtype != torch.int64 or not conf_t.is_cuda:
+        raise TypeError('conf_t must be a CUDA int64 tensor')
+    conf_t = conf_t.contiguous()
+    rows = conf_t.numel()
+    if conf.numel() != rows * C:
+        raise ValueError('conf must hold conf_t.numel() rows of C values')
+    if arm_conf is not None:
+        arm_conf = require_cuda_f32(arm_conf, 'arm_conf', align=8)
+        if arm_conf.numel() != rows * 2:
+            raise ValueError('arm_conf must hold conf_t.numel() rows of 2 logits')
+    ce = torch.empty(conf_t.shape, dtype=torch.float32, device=conf.device)
+    lse = torch.empty_like(ce)
+    pos = torch.empty(conf_t.shape, dtype=torch.bool, device=conf.device)
+    with torch.cuda.device(conf.device):
+        check(lib().rd_conf_loss(ptr(conf), ptr(conf_t), ptr(arm_conf), float(theta), rows, C, ptr(ce), ptr(lse),
+                                 ptr(pos), stream_ptr()), 'rd_conf_loss')
+    return ce, lse, pos
+
+
 def log_sum_exp(x):
-    """layers/box_utils.py:208-216 — stays on stock PyTorch (needs autograd)."""
-    x_max = x.data.max()
-    return torch.log(torch.sum(torch.exp(x - x_max), 1, keepdim=True)) + x_max
+    """layers/box_utils.py:208-216: ``log(sum(exp(x), 1, keepdim=True))`` of ``x[N,C]`` → ``[N,1]``, computed
+    by ``rd_conf_loss`` (row max instead of the reference's global max: same value, no underflow).
+    Values only — the loss module gets its gradients from ``rd_multibox_loss_backward``."""
+    t = torch.zeros(x.shape[0], dtype=torch.int64, device=x.device)
+    return conf_loss(x, t)[1].unsqueeze(1)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -202,6 +230,39 @@ def hnm_select(loss_c, pos, negpos_ratio):
         check(lib().rd_hnm_select(ptr(loss_c), ptr(pos), B, P, int(negpos_ratio), ptr(neg), ptr(num_pos),
                                   stream_ptr()), 'rd_hnm_select')
     return neg, num_pos
+
+
+def multibox_loss_reduce(loc_data, loc_t, ce, pos, neg, num_pos):
+    """``(loss_l, loss_c, N)`` 0-dim device tensors: SmoothL1 over ``pos`` and ``ce`` over ``pos | neg``,
+    both divided by ``N = sum(num_pos)`` (refinedet_multibox_loss.py:105-110,126-138); zeros when ``N < 1``."""
+    loc_data = require_cuda_f32(loc_data, 'loc_data')
+    loc_t = require_cuda_f32(loc_t, 'loc_t')
+    B, P = ce.shape
+    dev = ce.device
+    L = lib()
+    ws = torch.empty(int(L.rd_multibox_loss_workspace_bytes(B)), dtype=torch.uint8, device=dev)
+    out = [torch.empty((), dtype=torch.float32, device=dev) for _ in range(3)]
+    with torch.cuda.device(dev):
+        check(L.rd_multibox_loss_reduce(ptr(loc_data), ptr(loc_t), ptr(ce), ptr(pos), ptr(neg), ptr(num_pos), B, P,
+                                        ptr(ws), ws.numel(), ptr(out[0]), ptr(out[1]), ptr(out[2]), stream_ptr()),
+              'rd_multibox_loss_reduce')
+    return out[0], out[1], out[2]
+
+
+def multibox_loss_backward(loc_data, loc_t, conf_data, conf_t, lse, pos, neg, g_l, g_c, n_dev,
+                           need_loc=True, need_conf=True):
+    """Gradients of ``(loss_l, loss_c)`` w.r.t. ``(loc_data, conf_data)``; ``g_l`` / ``g_c`` are 0-dim device
+    tensors (or None)."""
+    C = conf_data.shape[-1]
+    rows = conf_t.numel()
+    grad_loc = torch.empty_like(loc_data) if need_loc else None
+    grad_conf = torch.empty_like(conf_data) if need_conf else None
+    with torch.cuda.device(conf_data.device):
+        check(lib().rd_multibox_loss_backward(ptr(loc_data), ptr(loc_t), ptr(conf_data), ptr(conf_t), ptr(lse),
+                                              ptr(pos), ptr(neg), ptr(g_l), ptr(g_c), ptr(n_dev), rows, C,
+                                              ptr(grad_loc), ptr(grad_conf), stream_ptr()),
+              'rd_multibox_loss_backward')
+    return grad_loc, grad_conf
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,15 +1,17 @@
 """Drop-in for ``layers/modules/refinedet_multibox_loss.py`` (reference :10-139).
 
-The per-image ``refine_match`` Python loop (:75-86) becomes one batched kernel pair and the
-double sort of the hard-negative mining (:119-123) becomes one radix-select kernel; SmoothL1,
-``log_sum_exp`` and cross-entropy stay on stock PyTorch because they need autograd
-(SURVEY.md §2, §8a a11).
+The per-image ``refine_match`` Python loop (:75-86) becomes one batched kernel pair, the double
+sort of the hard-negative mining (:119-123) one radix-select kernel, and the loss tail
+(:96-138: ARM-theta gate, ``log_sum_exp - gather``, SmoothL1, cross-entropy, ``/ N``) three
+kernels forward and one backward behind a ``torch.autograd.Function`` — ``conf_data`` is read once
+forward and only on the ``pos | neg`` rows backward.
 """
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
-from ..box_utils import LABEL_ARM_BINARY, LABEL_ODM, hnm_select, log_sum_exp, match_batch, pad_targets
+from ..._ffi import require_cuda_f32
+from ..box_utils import (LABEL_ARM_BINARY, LABEL_ODM, conf_loss, hnm_select, match_batch,
+                         multibox_loss_backward, multibox_loss_reduce, pad_targets)
 
 # data/config.py:57 (``coco['variance']``, read at reference :46)
 _VARIANCE = [0.1, 0.2]
@@ -64,36 +66,40 @@ class RefineDetMultiBoxLoss(nn.Module):
             loc_data, conf_data = odm_loc_data, odm_conf_data
         else:
             loc_data, conf_data = arm_loc_data, arm_conf_data
-        num = loc_data.size(0)
         loc_t, conf_t = self.match_targets(predictions, targets)
-
-        pos = conf_t > 0
-        if self.use_ARM:                                            # :96-101
-            P = F.softmax(arm_conf_data, 2)
-            pos = pos & ~(P[:, :, 1] <= self.theta).detach()
-
-        # Localization Loss (Smooth L1), :105-110
-        pos_idx = pos.unsqueeze(pos.dim()).expand_as(loc_data)
-        loc_p = loc_data[pos_idx].view(-1, 4)
-        loc_tp = loc_t[pos_idx].view(-1, 4)
-        loss_l = F.smooth_l1_loss(loc_p, loc_tp, reduction='sum')
-
-        # per-anchor confidence loss for mining, :113-114
-        batch_conf = conf_data.view(-1, self.num_classes)
-        loss_c = log_sum_exp(batch_conf) - batch_conf.gather(1, conf_t.view(-1, 1))
-
-        # Hard Negative Mining, :117-123 (positives are zeroed inside the kernel)
-        neg, num_pos = hnm_select(loss_c.detach().view(num, -1), pos, self.negpos_ratio)
-
-        # Confidence Loss Including Positive and Negative Examples, :126-130
-        sel = pos | neg
-        conf_p = conf_data[sel.unsqueeze(2).expand_as(conf_data)].view(-1, self.num_classes)
-        targets_weighted = conf_t[sel]
-        loss_c = F.cross_entropy(conf_p, targets_weighted, reduction='sum')
-
-        N = num_pos.sum().float()                                   # :134
-        if N < 1:                                                   # :135-136
+        arm_gate = arm_conf_data.detach() if self.use_ARM else None           # :96-101 (softmax inside the kernel)
+        loss_l, loss_c, N = _MultiBoxLossTail.apply(loc_data, conf_data, arm_gate, loc_t, conf_t,
+                                                    float(self.theta), int(self.negpos_ratio))
+        self.last_masks = _MultiBoxLossTail.last_masks
+        if float(N) < 1:                                            # :135-136 (the reference syncs here too)
             return torch.zeros(1), torch.zeros(1)
-        loss_l = loss_l / N
-        loss_c = loss_c / N
         return loss_l, loss_c
+
+
+class _MultiBoxLossTail(torch.autograd.Function):
+    """refinedet_multibox_loss.py:96-138 on the device: forward = rd_conf_loss + rd_hnm_select +
+    rd_multibox_loss_reduce, backward = rd_multibox_loss_backward."""
+    last_masks = None          # (pos, neg) of the latest forward, for inspection / tests
+
+    @staticmethod
+    def forward(ctx, loc_data, conf_data, arm_conf, loc_t, conf_t, theta, negpos_ratio):
+        loc_c = require_cuda_f32(loc_data, 'loc_data')
+        conf_c = require_cuda_f32(conf_data, 'conf_data', align=8)
+        B, P = conf_t.shape
+        ce, lse, pos = conf_loss(conf_c, conf_t, arm_conf, theta)              # :96-101, :113-114
+        neg, num_pos = hnm_select(ce, pos, negpos_ratio)                       # :117-123
+        loss_l, loss_c, N = multibox_loss_reduce(loc_c, loc_t, ce, pos, neg, num_pos)   # :105-110, :126-138
+        ctx.save_for_backward(loc_c, conf_c, loc_t, conf_t, lse, pos, neg, N)
+        ctx.mark_non_differentiable(N)
+        _MultiBoxLossTail.last_masks = (pos, neg)
+        return loss_l, loss_c, N
+
+    @staticmethod
+    def backward(ctx, g_l, g_c, _g_n):
+        loc_c, conf_c, loc_t, conf_t, lse, pos, neg, N = ctx.saved_tensors
+        need_loc, need_conf = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_l = g_l.contiguous().float() if g_l is not None else None
+        g_c = g_c.contiguous().float() if g_c is not None else None
+        grad_loc, grad_conf = multibox_loss_backward(loc_c, loc_t, conf_c, conf_t, lse, pos, neg, g_l, g_c, N,
+                                                     need_loc, need_conf)
+        return grad_loc, grad_conf, None, None, None, None, None

@@ -156,6 +156,83 @@ def test_full_size_loss_step(rd):
     assert torch.equal(c2, conf_t) and torch.equal(l2, loc_t)
 
 
+def _torch_tail(loc_data, conf_data, loc_t, conf_t, pos, neg):
+    """Stock-PyTorch fp32 restatement of refinedet_multibox_loss.py:105-110,126-138 for GIVEN masks."""
+    import torch.nn.functional as F
+    C = conf_data.shape[-1]
+    pos_idx = pos.unsqueeze(pos.dim()).expand_as(loc_data)
+    loss_l = F.smooth_l1_loss(loc_data[pos_idx].view(-1, 4), loc_t[pos_idx].view(-1, 4), reduction='sum')
+    sel = pos | neg
+    conf_p = conf_data[sel.unsqueeze(2).expand_as(conf_data)].view(-1, C)
+    loss_c = F.cross_entropy(conf_p, conf_t[sel], reduction='sum')
+    N = pos.sum().float()
+    return loss_l / N, loss_c / N
+
+
+@pytest.mark.parametrize('B,size,C,G,use_arm', [(4, '320', 21, 9, True), (3, '320', 2, 12, False),
+                                                (2, '512', 81, 50, True), (32, '512', 81, 50, True)])
+def test_loss_tail_kernels(rd, B, size, C, G, use_arm):
+    """f-4 / a11 / a12: rd_conf_loss, rd_multibox_loss_reduce and rd_multibox_loss_backward against stock
+    PyTorch (fp32, tolerance 1e-5 relative — exp/log differ in the last bits and the sums are reduced in
+    a different order) and, at the small sizes, against the oracle's analytic gradients."""
+    bu = rd.box_utils
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward().cuda()
+    P = priors.shape[0]
+    arm_loc, arm_conf, odm_loc, odm_conf = [t.cuda() for t in gen.train_predictions(77 + G, B, P, max(C, 2))]
+    tg = [t.cuda() for t in gen.targets(9100 + G, B, G, C)]
+    crit = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=use_arm)
+    if use_arm:
+        arm_conf[..., 1] -= 4.0        # theta gate: some matched anchors pass, some are filtered
+        loc_data, conf_data = odm_loc, odm_conf
+    else:
+        loc_data, conf_data = arm_loc, arm_conf[..., :2].contiguous()
+    preds = (arm_loc, arm_conf, odm_loc, odm_conf, priors) if use_arm else (arm_loc, conf_data, odm_loc, odm_conf, priors)
+    loc_t, conf_t = crit.match_targets(preds, tg)
+    # --- rd_conf_loss ---------------------------------------------------------------------------
+    ce, lse, pos = bu.conf_loss(conf_data, conf_t, arm_conf if use_arm else None, 0.01)
+    flat = conf_data.view(-1, conf_data.shape[-1])
+    t_lse = torch.logsumexp(flat, 1)
+    t_ce = (t_lse - flat.gather(1, conf_t.view(-1, 1)).squeeze(1)).view(B, P)
+    torch.testing.assert_close(lse.view(-1), t_lse, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(ce, t_ce, rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(bu.log_sum_exp(flat), t_lse.unsqueeze(1), rtol=1e-5, atol=1e-6)
+    t_pos = conf_t > 0
+    if use_arm:
+        t_pos = t_pos & ~(torch.softmax(arm_conf, 2)[:, :, 1] <= 0.01)
+        assert int((conf_t > 0).sum()) > int(t_pos.sum()) > 0          # the gate really removes some
+    assert torch.equal(pos, t_pos)
+    # --- forward / backward through the module --------------------------------------------------
+    p_loc = loc_data.clone().requires_grad_(True)
+    p_conf = conf_data.clone().requires_grad_(True)
+    preds2 = (arm_loc, arm_conf, p_loc, p_conf, priors) if use_arm else (p_loc, p_conf, odm_loc, odm_conf, priors)
+    l, c = crit(preds2, tg)
+    (2.0 * l + 0.5 * c).backward()
+    pos_k, neg_k = crit.last_masks
+    assert torch.equal(pos_k, t_pos)
+    assert torch.equal(neg_k.sum(1), torch.clamp(3 * pos_k.sum(1), max=P - 1))
+    r_loc = loc_data.clone().requires_grad_(True)
+    r_conf = conf_data.clone().requires_grad_(True)
+    rl, rc = _torch_tail(r_loc, r_conf, loc_t, conf_t, pos_k, neg_k)
+    (2.0 * rl + 0.5 * rc).backward()
+    torch.testing.assert_close(l, rl, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(c, rc, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(p_loc.grad, r_loc.grad, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(p_conf.grad, r_conf.grad, rtol=2e-5, atol=1e-9)
+    if B <= 4:
+        N = float(pos_k.sum())
+        g_loc, g_conf = bo.multibox_loss_grads(loc_data.cpu().numpy(), conf_data.cpu().numpy(), loc_t.cpu().numpy(),
+                                               conf_t.cpu().numpy(), pos_k.cpu().numpy(), neg_k.cpu().numpy(), N)
+        np.testing.assert_allclose(p_loc.grad.cpu().numpy(), 2.0 * g_loc, rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(p_conf.grad.cpu().numpy(), 0.5 * g_conf, rtol=2e-5, atol=1e-9)
+    # only one of the two losses used: the other gradient is zero, nothing is left unwritten
+    p_loc.grad = None
+    p_conf.grad = None
+    l2, c2 = crit(preds2, tg)
+    c2.backward()
+    assert float(p_loc.grad.abs().sum()) == 0.0 and float(p_conf.grad.abs().sum()) > 0
+    assert bool(torch.isfinite(p_conf.grad).all())
+
+
 def test_check_targets(rd):
     """SURVEY f-3: the per-coordinate validation loop of train_refinedet.py:240-245 as one reduction."""
     tg = [t.cuda() for t in gen.targets(3, 4, 6, 21)]

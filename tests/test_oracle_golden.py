@@ -176,3 +176,29 @@ def test_model_cfg1_fixture(golden):
             assert np.array_equal(out[j], g['a4_dets'][j, :n])
             checked += 1
     assert checked >= 1
+
+
+def test_oracle_loss_grads_match_autograd():
+    """oracle.multibox_loss_grads (analytic) == torch autograd of the reference's loss tail
+    (refinedet_multibox_loss.py:105-138) on the CPU, for given masks."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    B, P, C = 2, 300, 7
+    loc = torch.randn(B, P, 4, generator=g) * 1.5
+    loc_t = torch.randn(B, P, 4, generator=g)
+    conf = torch.randn(B, P, C, generator=g) * 2
+    conf_t = torch.randint(0, C, (B, P), generator=g)
+    pos = (conf_t > 0) & (torch.rand(B, P, generator=g) < 0.2)
+    neg = ~pos & (torch.rand(B, P, generator=g) < 0.3)
+    N = float(pos.sum())
+    lr, cr = loc.clone().requires_grad_(True), conf.clone().requires_grad_(True)
+    pos_idx = pos.unsqueeze(2).expand_as(lr)
+    loss_l = F.smooth_l1_loss(lr[pos_idx].view(-1, 4), loc_t[pos_idx].view(-1, 4), reduction='sum') / N
+    sel = pos | neg
+    loss_c = F.cross_entropy(cr[sel.unsqueeze(2).expand_as(cr)].view(-1, C), conf_t[sel], reduction='sum') / N
+    (loss_l + loss_c).backward()
+    g_loc, g_conf = bo.multibox_loss_grads(loc.numpy(), conf.numpy(), loc_t.numpy(), conf_t.numpy(), pos.numpy(),
+                                           neg.numpy(), N)
+    np.testing.assert_allclose(g_loc, lr.grad.numpy(), rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(g_conf, cr.grad.numpy(), rtol=1e-5, atol=1e-8)
