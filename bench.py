@@ -421,6 +421,38 @@ def main():
                              'top_k = 1000 and goes through the large-problem kernel (radix select + own bins)'}
         del o_dev
 
+    # f-1: logits in (softmax folded into the stage) against torch.softmax + the stage, one stream, L2 flushed
+    logits_in = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        lg = [t.to(dev) for t in synthetic.detect_logits(seed_for(rank, 0), BATCH, P, C, args.workload)]
+        plan_l = det.plan(lg[0], lg[1], lg[2], lg[3], priors, scale=scale, workspace=lanes[0][0], out=lanes[0][1],
+                          logits=True)
+
+        def fused():
+            plan_l.launch(main)
+
+        def unfused():
+            det.detect(lg[0], torch.softmax(lg[1], -1), lg[2], torch.softmax(lg[3], -1), priors, scale=scale)
+
+        def timed(fn, n=20):
+            for _ in range(3):
+                fn()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+            for a, b in evs:
+                flush_buf.zero_()
+                a.record(main)
+                fn()
+                b.record(main)
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in evs) / n
+        ms_f, ms_u = timed(fused), timed(unfused)
+        same = bool(torch.equal(plan_l.launch(main).counts, plans[0][0].launch(main).counts))
+        logits_in = {'ms_per_step': ms_f, 'value': BATCH / (ms_f * 1e-3), 'unit': UNIT,
+                     'torch_softmax_then_stage_ms': ms_u, 'counts_equal_to_probability_input': same,
+                     'note': 'RD_INPUT_LOGITS: the softmax of models/refinedet.py:143-147 inside collect_kernel (rows of '
+                             'ARM-passing anchors only) instead of a separate read+write pass over odm_conf'}
+        del plan_l
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, done, elapsed = cpu_reference_run(args.workload, 1000, 1, cores, budget_s=12.0)
@@ -438,6 +470,7 @@ def main():
                                arm_pass_fraction=arm_pass, kept_rows_per_step=kept_rows),
                 'latency_ms_per_batch': latency_ms,
                 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'secondary': secondary,
+                'logits_in': logits_in,
                 'gpu_launches': int(launches),
                 'clocks': clocks.summary()}
         print(json.dumps(line))

@@ -9,7 +9,7 @@
 //   conf_loss_kernel      one pass over conf[B*P,C]: per row  lse = log(sum exp(x - max)) + max,
 //                         ce = lse - x[conf_t]  (the mining loss of :114 AND the cross-entropy term of
 //                         :130 — F.cross_entropy(x, t) is the same quantity), pos = conf_t > 0 gated by
-//                         softmax(arm_conf)[1] > theta.  Warp per row, lane = class (C = 2: thread per row).
+//                         softmax(arm_conf)[1] > theta.  Rows staged in shared memory, thread per row.
 //                         The reference subtracts the GLOBAL max of the tensor (box_utils.py:215); the row
 //                         max used here is the same value mathematically and at least as accurate in fp32.
 //   loss_reduce_kernel    per image: sum of ce over pos | neg, SmoothL1 over pos (fp64 accumulation,
@@ -23,7 +23,6 @@
 namespace rd {
 
 constexpr int kLossThreads = 256;
-constexpr int kLossRowBatch = 4;          // conf rows in flight per warp
 constexpr int kLossMaxClasses = 128;
 
 // softmax(arm_conf)[1] <= theta (refinedet_multibox_loss.py:98-101), fp32, max-subtracted like F.softmax
@@ -33,64 +32,78 @@ __device__ __forceinline__ bool arm_filtered(float2 a, float theta) {
     return e1 / (e0 + e1) <= theta;
 }
 
-// generic C (3..128): warp per row, lane = class
-__global__ void __launch_bounds__(kLossThreads)
+// generic C (3..128): a CTA stages kLossRows consecutive rows (one contiguous, coalesced float4 stream)
+// in shared memory with an odd row stride (conflict-free), then one thread per row makes two passes
+// over its row: max, sum of exp.  ~16 thread-instructions per element, against ~60 for a
+// lane-per-class layout with shuffle reductions (the kernel is issue-bound, not bandwidth-bound).
+constexpr int kLossRows = 128;            // rows (= threads) per CTA
+constexpr int kLossLoads = 5;             // float4 loads in flight per thread while staging a tile
+
+__global__ void __launch_bounds__(kLossRows)
 conf_loss_kernel(const float* __restrict__ conf, const long long* __restrict__ conf_t,
                  const float2* __restrict__ arm_conf, float theta, long long rows, int C,
                  float* __restrict__ ce_out, float* __restrict__ lse_out, unsigned char* __restrict__ pos_out) {
-    const int lane = threadIdx.x & 31;
-    const long long warp_global = ((long long)blockIdx.x * kLossThreads + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * kLossThreads) >> 5;
-    const int nseg = (C + 31) >> 5;
-    for (long long r0 = warp_global * kLossRowBatch; r0 < rows; r0 += nwarps * kLossRowBatch) {
-        float v[kLossRowBatch][4];
+    extern __shared__ float s_x[];                   // [kLossRows][Cp]
+    const int Cp = C | 1;
+    const int tid = threadIdx.x;
+    for (long long r0 = (long long)blockIdx.x * kLossRows; r0 < rows; r0 += (long long)gridDim.x * kLossRows) {
+        const int nrows = (int)min((long long)kLossRows, rows - r0);
+        const int nelem = nrows * C;
+        const float* src = conf + r0 * C;
+        // the scalar inputs of this thread's row: issued before the tile load
+        const long long r = r0 + tid;
+        long long t = 0;
+        float2 arm = make_float2(0.f, 0.f);
+        if (tid < nrows) {
+            t = conf_t[r];
+            if (arm_conf && t > 0) arm = __ldg(arm_conf + r);
+        }
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const int nvec = nelem >> 2;
+            int e = tid * 4;
+            int rr = e / C, c = e - rr * C;
+            const int drr = (4 * kLossRows) / C, dc = 4 * kLossRows - drr * C;
+            for (int q0 = tid; q0 < nvec; q0 += kLossLoads * kLossRows) {
+                float4 v[kLossLoads];                              // kLossLoads independent 16-byte loads in flight
 #pragma unroll
-        for (int k = 0; k < kLossRowBatch; ++k) {
-            const long long r = r0 + k;
-            const float* row = conf + (r < rows ? r : 0) * C;
+                for (int u = 0; u < kLossLoads; ++u) {
+                    const int q = q0 + u * kLossRows;
+                    v[u] = q < nvec ? ldg_stream4(reinterpret_cast<const float4*>(src) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
-            for (int sgm = 0; sgm < 4; ++sgm) {
-                const int c = sgm * 32 + lane;
-                v[k][sgm] = (r < rows && sgm < nseg && c < C) ? ldg_stream1(row + c) : -INFINITY;
+                for (int u = 0; u < kLossLoads; ++u) {
+                    if (q0 + u * kLossRows < nvec) {
+                        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                        int r1 = rr, c1 = c;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            s_x[r1 * Cp + c1] = vv[k];
+                            if (++c1 == C) { c1 = 0; ++r1; }
+                        }
+                    }
+                    rr += drr; c += dc;
+                    if (c >= C) { c -= C; ++rr; }
+                }
             }
+            for (int e2 = nvec * 4 + tid; e2 < nelem; e2 += kLossRows) s_x[(e2 / C) * Cp + e2 % C] = src[e2];
+        } else {
+            for (int e2 = tid; e2 < nelem; e2 += kLossRows) s_x[(e2 / C) * Cp + e2 % C] = src[e2];
         }
-        // lane k of the warp owns the scalar outputs of row r0 + k
-        long long t_own = 0;
-        float2 arm_own = make_float2(0.f, 0.f);
-        if (lane < kLossRowBatch && r0 + lane < rows) {
-            t_own = conf_t[r0 + lane];
-            if (arm_conf && t_own > 0) arm_own = __ldg(arm_conf + r0 + lane);
-        }
-        float ce_own = 0.f, lse_own = 0.f;
-#pragma unroll
-        for (int k = 0; k < kLossRowBatch; ++k) {
-            if (r0 + k >= rows) break;
-            float m = fmaxf(fmaxf(v[k][0], v[k][1]), fmaxf(v[k][2], v[k][3]));
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, d));
-            float s = 0.f;
-#pragma unroll
-            for (int sgm = 0; sgm < 4; ++sgm) s += (sgm < nseg && sgm * 32 + lane < C) ? expf(v[k][sgm] - m) : 0.f;
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(kFullMask, s, d);
-            const float lse = logf(s) + m;
-            const int t = (int)__shfl_sync(kFullMask, (int)t_own, k);
-            // x[t]: held by lane t & 31 in segment t >> 5
-            float xt = v[k][0];
-            if ((t >> 5) == 1) xt = v[k][1];
-            if ((t >> 5) == 2) xt = v[k][2];
-            if ((t >> 5) == 3) xt = v[k][3];
-            xt = __shfl_sync(kFullMask, xt, t & 31);
-            if (lane == k) { ce_own = lse - xt; lse_own = lse; }
-        }
-        if (lane < kLossRowBatch && r0 + lane < rows) {
-            const long long r = r0 + lane;
-            ce_out[r] = ce_own;
-            lse_out[r] = lse_own;
-            bool pos = t_own > 0;
-            if (pos && arm_conf && arm_filtered(arm_own, theta)) pos = false;
+        __syncthreads();
+        if (tid < nrows) {
+            const float* x = s_x + tid * Cp;
+            float m = x[0];
+            for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
+            float sum = 0.f;
+            for (int c = 0; c < C; ++c) sum += expf(x[c] - m);
+            const float lse = logf(sum) + m;
+            ce_out[r] = lse - x[(int)t];
+            lse_out[r] = lse;
+            bool pos = t > 0;
+            if (pos && arm_conf && arm_filtered(arm, theta)) pos = false;
             pos_out[r] = pos ? 1 : 0;
         }
+        __syncthreads();
     }
 }
 
@@ -120,16 +133,19 @@ __device__ __forceinline__ double smooth_l1(float p, float t) {
     return a < 1.0f ? 0.5 * (double)d * (double)d : (double)a - 0.5;
 }
 
-// grid = B: partial[b] = { sum_{pos} SmoothL1(loc - loc_t), sum_{pos|neg} ce }
+// grid = (kReduceSplit, B): partial[b][g] = { sum_{pos} SmoothL1(loc - loc_t), sum_{pos|neg} ce } over the
+// anchors i = g*256 + tid (mod kReduceSplit*256) of image b
+constexpr int kReduceSplit = 8;
+
 __global__ void __launch_bounds__(kLossThreads)
 loss_reduce_kernel(const float4* __restrict__ loc, const float4* __restrict__ loc_t, const float* __restrict__ ce,
                    const unsigned char* __restrict__ pos, const unsigned char* __restrict__ neg, int P,
                    double* __restrict__ partial) {
     __shared__ double s_l[kLossThreads / 32], s_c[kLossThreads / 32];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t img = (size_t)b * P;
     double al = 0.0, ac = 0.0;
-    for (int i = tid; i < P; i += kLossThreads) {
+    for (int i = g * kLossThreads + tid; i < P; i += kReduceSplit * kLossThreads) {
         const bool p = pos[img + i] != 0;
         const bool n = neg[img + i] != 0;
         if (p | n) ac += (double)ce[img + i];
@@ -148,8 +164,8 @@ loss_reduce_kernel(const float4* __restrict__ loc, const float4* __restrict__ lo
     if (tid == 0) {
         double tl = 0.0, tc = 0.0;
         for (int w = 0; w < kLossThreads / 32; ++w) { tl += s_l[w]; tc += s_c[w]; }
-        partial[2 * b] = tl;
-        partial[2 * b + 1] = tc;
+        partial[2 * (b * kReduceSplit + g)] = tl;
+        partial[2 * (b * kReduceSplit + g) + 1] = tc;
     }
 }
 
@@ -159,14 +175,15 @@ __global__ void loss_final_kernel(const double* __restrict__ partial, const int*
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double tl = 0.0, tc = 0.0;
     long long n = 0;
-    for (int b = 0; b < B; ++b) { tl += partial[2 * b]; tc += partial[2 * b + 1]; n += num_pos[b]; }
+    for (int q = 0; q < B * kReduceSplit; ++q) { tl += partial[2 * q]; tc += partial[2 * q + 1]; }
+    for (int b = 0; b < B; ++b) n += num_pos[b];
     const float N = (float)n;
     *n_out = N;
     *loss_l = n > 0 ? (float)tl / N : 0.f;
     *loss_c = n > 0 ? (float)tc / N : 0.f;
 }
 
-// gradients.  One warp per kLossRowBatch rows; conf rows of unselected anchors are never read.
+// gradients.  One warp per 32 rows; conf rows of unselected anchors are never read.
 __global__ void __launch_bounds__(kLossThreads)
 loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ loc_t,
                      const float* __restrict__ conf, const long long* __restrict__ conf_t,
@@ -260,7 +277,7 @@ using namespace rd;
 
 extern "C" {
 
-size_t rd_multibox_loss_workspace_bytes(int B) { return B > 0 ? (size_t)B * 2 * sizeof(double) : 0; }
+size_t rd_multibox_loss_workspace_bytes(int B) { return B > 0 ? (size_t)B * kReduceSplit * 2 * sizeof(double) : 0; }
 
 int rd_conf_loss(const float* conf, const long long* conf_t, const float* arm_conf, float theta, long long rows,
                  int C, float* ce_out, float* lse_out, unsigned char* pos_out, void* stream) {
@@ -274,10 +291,16 @@ int rd_conf_loss(const float* conf, const long long* conf_t, const float* arm_co
         conf_loss2_kernel<<<(unsigned)blocks, kLossThreads, 0, st>>>((const float2*)conf, conf_t, (const float2*)arm_conf,
                                                                      theta, rows, ce_out, lse_out, pos_out);
     } else {
-        const long long warps = (rows + kLossRowBatch - 1) / kLossRowBatch;
-        long long blocks = (warps * 32 + kLossThreads - 1) / kLossThreads;
+        const size_t smem = (size_t)kLossRows * (C | 1) * sizeof(float);
+        static size_t s_attr = 48 * 1024;
+        if (smem > s_attr) {
+            cudaError_t e = cudaFuncSetAttribute(conf_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            s_attr = smem;
+        }
+        long long blocks = (rows + kLossRows - 1) / kLossRows;
         if (blocks > 148 * 64) blocks = 148 * 64;
-        conf_loss_kernel<<<(unsigned)blocks, kLossThreads, 0, st>>>(conf, conf_t, (const float2*)arm_conf, theta, rows, C,
+        conf_loss_kernel<<<(unsigned)blocks, kLossRows, smem, st>>>(conf, conf_t, (const float2*)arm_conf, theta, rows, C,
                                                                     ce_out, lse_out, pos_out);
     }
     note_launch();
@@ -295,7 +318,7 @@ int rd_multibox_loss_reduce(const float* loc, const float* loc_t, const float* c
     if ((uintptr_t)workspace & 7) return RD_ERR_ALIGNMENT;
     if (workspace_bytes < rd_multibox_loss_workspace_bytes(B)) return RD_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    loss_reduce_kernel<<<B, kLossThreads, 0, st>>>((const float4*)loc, (const float4*)loc_t, ce, pos, neg, P,
+    loss_reduce_kernel<<<dim3(kReduceSplit, B), kLossThreads, 0, st>>>((const float4*)loc, (const float4*)loc_t, ce, pos, neg, P,
                                                    (double*)workspace);
     note_launch();
     RD_CHECK_LAUNCH();

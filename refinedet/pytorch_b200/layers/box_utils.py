@@ -122,10 +122,14 @@ def pad_targets(targets, device):
     gmax = max(max(counts), 1)
     if gmax > _ffi.RD_MAX_GT:
         raise RuntimeError('more than %d ground-truth boxes in one image (%d)' % (_ffi.RD_MAX_GT, gmax))
-    padded = torch.zeros(len(targets), gmax, 5, dtype=torch.float32, device=device)
-    for i, t in enumerate(targets):
-        if counts[i]:
-            padded[i, :counts[i]] = t.detach().to(device=device, dtype=torch.float32)
+    B = len(targets)
+    padded = torch.zeros(B * gmax, 5, dtype=torch.float32, device=device)
+    if sum(counts):
+        # one concatenation + one indexed store instead of B slice assignments
+        flat = torch.cat([t.detach().to(device=device, dtype=torch.float32).reshape(-1, 5) for t in targets if t.shape[0]])
+        rows = [i * gmax + k for i, n in enumerate(counts) for k in range(n)]
+        padded[torch.tensor(rows, dtype=torch.int64).to(device, non_blocking=True)] = flat
+    padded = padded.view(B, gmax, 5)
     truths = padded[:, :, :4].contiguous()
     labels = padded[:, :, 4].contiguous()
     gt_count = torch.tensor(counts, dtype=torch.int32).to(device, non_blocking=True)

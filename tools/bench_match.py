@@ -67,6 +67,31 @@ def main():
     tgd = [t.to(dev) for t in tg]
     ms = timed(lambda: crit(preds, tgd))
     out['odm_criterion_forward'] = {'ms': ms, 'images_per_s': B / ms * 1e3}
+    # the loss tail kernel by kernel (f-4): forward conf loss (reads conf once), reduce, backward
+    loc_t, conf_t = crit.match_targets(preds, tgd)
+    ms = timed(lambda: bu.conf_loss(odm_conf, conf_t, arm_conf, 0.01))
+    byts = B * P * (4 * C + 8 + 9)                       # conf row + conf_t in; ce, lse, pos out
+    out['conf_loss'] = {'ms': ms, 'algorithmic_GBs': byts / ms / 1e6, 'frac_of_hbm_peak': byts / ms / 1e6 / peak}
+    ce, lse, pos_k = bu.conf_loss(odm_conf, conf_t, arm_conf, 0.01)
+    neg_k, num_pos = bu.hnm_select(ce, pos_k, 3)
+    ms = timed(lambda: bu.multibox_loss_reduce(odm_loc, loc_t, ce, pos_k, neg_k, num_pos))
+    out['loss_reduce'] = {'ms': ms}
+    one = torch.ones((), device=dev)
+    n_dev = pos_k.sum().float()
+    ms = timed(lambda: bu.multibox_loss_backward(odm_loc, loc_t, odm_conf, conf_t, lse, pos_k, neg_k, one, one, n_dev))
+    byts = B * P * (4 * C + 16 + 2)                      # grad_conf + grad_loc written, masks read
+    out['loss_backward'] = {'ms': ms, 'algorithmic_GBs': byts / ms / 1e6, 'frac_of_hbm_peak': byts / ms / 1e6 / peak}
+    p_loc = odm_loc.clone().requires_grad_(True)
+    p_conf = odm_conf.clone().requires_grad_(True)
+    preds_g = (arm_loc, arm_conf, p_loc, p_conf, priors)
+
+    def fwd_bwd():
+        l, c = crit(preds_g, tgd)
+        (l + c).backward()
+        p_loc.grad = None
+        p_conf.grad = None
+    ms = timed(fwd_bwd)
+    out['odm_criterion_forward_backward'] = {'ms': ms, 'images_per_s': B / ms * 1e3}
     # CPU oracle, one image, one core
     t0 = time.perf_counter()
     n_img = 2
