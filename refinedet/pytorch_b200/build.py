@@ -61,7 +61,8 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + \
+        extra = os.environ.get('RD_NVCC_EXTRA', '').split()          # tuning experiments (-DRD_SMALL_THREADS=160 ...)
+        cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + \
               ['-c', os.path.join(CSRC, src), '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -493,32 +493,31 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
     const uint32_t* Ex = G.tab + 1 * kCols * kGraphWS;
     const uint32_t* Sy = G.tab + 2 * kCols * kGraphWS;
     const uint32_t* Ey = G.tab + 3 * kCols * kGraphWS;
-    const int nitems = nown * Wn;
+    // Own node jl (j = g + 16 jl) only needs the words 0 .. j >> 5 = jl >> 1, so the items form a
+    // triangle: the pair of own nodes (2m, 2m + 1) has m + 1 words each and m (m + 1) items precede it.
+    static_assert(kGraphSplit == 16, "item enumeration assumes 2 own nodes per 32-node word");
+    const int mfull = nown >> 1;
+    const int nitems = mfull * (mfull + 1) + ((nown & 1) ? mfull + 1 : 0);
     for (int q0 = 0; q0 < nitems; q0 += kGraphThreads) {
         const int q = q0 + tid;
         uint32_t h = 0;
         int jl = 0, w = 0;
         if (q < nitems) {
-            jl = q / Wn; w = q - jl * Wn;
+            int m = (int)((sqrtf((float)(4 * q + 1)) - 1.0f) * 0.5f);
+            while (m * (m + 1) > q) --m;
+            while ((m + 1) * (m + 2) <= q) ++m;
+            const int rem = q - m * (m + 1);
+            const int second = rem > m ? 1 : 0;
+            jl = 2 * m + second;
+            w = rem - second * (m + 1);
             const int j = g + jl * kGraphSplit;
-            const int jw = j >> 5;
-            if (w <= jw) {
-                const uint32_t cr = G.cr[j];
-                h = Sx[((cr >> 8) & 255u) * kGraphWS + w] & ~Ex[(cr & 255u) * kGraphWS + w] &
-                    Sy[((cr >> 24) & 255u) * kGraphWS + w] & ~Ey[((cr >> 16) & 255u) * kGraphWS + w];
-                if (w == jw) h &= (1u << (j & 31)) - 1u;      // predecessors only
-            }
+            const uint32_t cr = G.cr[j];
+            h = Sx[((cr >> 8) & 255u) * kGraphWS + w] & ~Ex[(cr & 255u) * kGraphWS + w] &
+                Sy[((cr >> 24) & 255u) * kGraphWS + w] & ~Ey[((cr >> 16) & 255u) * kGraphWS + w];
+            if (w == (j >> 5)) h &= (1u << (j & 31)) - 1u;        // predecessors only
         }
-        // reserve list slots: warp-aggregated shared-memory atomic (list order is irrelevant)
-        const int c = __popc(h);
-        int x = c;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, x, d); if (lane >= d) x += o; }
-        const int wtot = __shfl_sync(kFullMask, x, 31);
-        int wbase = 0;
-        if (lane == 31 && wtot) wbase = atomicAdd(&G.npairs, wtot);
-        wbase = __shfl_sync(kFullMask, wbase, 31);
-        int off = wbase + x - c;
+        // reserve list slots: one shared-memory atomic per item that has pairs (list order is irrelevant)
+        int off = h ? atomicAdd(&G.npairs, __popc(h)) : 0;
         const uint32_t tag = (uint32_t)jl << 16;
         while (h) {
             const int i = (w << 5) + __ffs(h) - 1;
@@ -579,7 +578,7 @@ struct FusedNmsArgs {
 __global__ void __launch_bounds__(kSmallThreads, 1536 / kSmallThreads)
 nms_small_kernel(FusedNmsArgs A) {
     __shared__ SmallSmem S;
-    constexpr int kPerT = kGraphNodes / kSmallThreads;
+    constexpr int kPerT = (kGraphNodes + kSmallThreads - 1) / kSmallThreads;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x, b = blockIdx.y;
     const int bc = b * A.C + c;
