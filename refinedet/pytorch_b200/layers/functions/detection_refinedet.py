@@ -106,16 +106,19 @@ class DetectHostPipeline(object):
     """End-to-end detect stage for HOST inputs with several batches in flight.
 
     Each lane owns a stream, a workspace, device output slots and pinned host result buffers.
-    ``submit(host_inputs)`` (pinned ``arm_loc, arm_conf, odm_loc, odm_conf``) copies ``arm_conf`` by DMA and
-    replays the lane's plan — the kernels read the other pinned tensors over PCIe (only rows of ARM-passing
-    anchors cross the bus), the
-    pack kernels store the rows straight into pinned host memory — and returns a ticket at once;
+    ``submit(host_inputs)`` (pinned ``arm_loc, arm_conf, odm_loc, odm_conf``) copies ``arm_conf`` by DMA,
+    replays the lane's plan — the kernels read the other pinned tensors over PCIe, so only the rows of
+    ARM-passing anchors cross the bus — packs the rows and returns a ticket at once.
     ``result(ticket)`` waits for that batch only and returns CPU tensors ``(counts[B,C], rows[total,5])``
-    (views of the lane's buffers, valid until the lane is reused ``lanes`` submits later).  With two
-    lanes the PCIe reads of batch i+1 overlap the kernels and the result write-back of batch i."""
+    (views of the lane's buffers, valid until the lane is reused ``lanes`` submits later).
+    ``dma_rows=True`` (default): rows are packed on the device and ``result`` issues one DMA of exactly
+    ``total`` rows; ``False``: the pack kernel stores them straight into pinned host memory (one wait less,
+    measured ~12 % slower at four lanes).  With several lanes the PCIe reads of batch i+1 overlap the
+    kernels and the write-back of batch i."""
 
-    def __init__(self, det, prior_data, scale, B, lanes=2):
+    def __init__(self, det, prior_data, scale, B, lanes=2, dma_rows=True):
         self.det, self.priors, self.B = det, require_cuda_f32(prior_data, 'prior_data'), B
+        self.dma_rows = dma_rows      # False: pack kernel stores rows into pinned host memory; True: pack on device + DMA
         dev = self.priors.device
         self.device = dev
         C = det.num_classes
@@ -134,6 +137,7 @@ class DetectHostPipeline(object):
                 'host_offsets': torch.empty(B * C + 1, dtype=torch.int32).pin_memory(),
                 'host_counts': torch.empty(B, C, dtype=torch.int32).pin_memory(),
                 'host_rows': torch.empty(B * C * max_out, 5, dtype=torch.float32).pin_memory(),
+                'dev_rows': torch.empty(B * C * max_out, 5, dtype=torch.float32, device=dev) if dma_rows else None,
                 'done': torch.cuda.Event(),
                 'arm_conf': torch.empty(B, self.priors.shape[0], 2, dtype=torch.float32, device=dev),
                 'plans': {},
@@ -162,8 +166,9 @@ class DetectHostPipeline(object):
         res = plan.launch(st)
         B, C, max_out, _ = res.dets.shape
         with torch.cuda.device(self.device), torch.cuda.stream(st):
+            rows_dst = lane['dev_rows'] if self.dma_rows else lane['host_rows']
             check(lib().rd_pack_detections(ptr(res.counts), ptr(res.dets), B, C, max_out, ptr(lane['dev_offsets']),
-                                           ptr(lane['host_rows']), lane['host_rows'].shape[0], st.cuda_stream),
+                                           ptr(rows_dst), rows_dst.shape[0], st.cuda_stream),
                   'rd_pack_detections')
             lane['host_counts'].copy_(res.counts, non_blocking=True)
             lane['host_offsets'].copy_(lane['dev_offsets'], non_blocking=True)
@@ -173,6 +178,11 @@ class DetectHostPipeline(object):
     def result(self, ticket):
         ticket['done'].synchronize()
         total = int(ticket['host_offsets'][-1])
+        if self.dma_rows:       # rows packed on the device: one DMA of exactly `total` rows, then a second wait
+            st = ticket['stream']
+            with torch.cuda.stream(st):
+                ticket['host_rows'][:total].copy_(ticket['dev_rows'][:total], non_blocking=True)
+            st.synchronize()
         return ticket['host_counts'], ticket['host_rows'][:total]
 
 
