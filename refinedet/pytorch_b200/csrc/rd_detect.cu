@@ -575,7 +575,10 @@ struct FusedNmsArgs {
 // K2: one CTA per (image, class).  Launched with programmatic stream serialisation behind graph_kernel
 // (which triggers at its start): the scan of the class's score row and the sort need collect_kernel's
 // results only and run beside graph_kernel; the CTA then waits for the graph and resolves.
-__global__ void __launch_bounds__(kSmallThreads, 1536 / kSmallThreads)
+#ifndef RD_SMALL_MINBLOCKS
+#define RD_SMALL_MINBLOCKS (1536 / RD_SMALL_THREADS)
+#endif
+__global__ void __launch_bounds__(kSmallThreads, RD_SMALL_MINBLOCKS)
 nms_small_kernel(FusedNmsArgs A) {
     __shared__ SmallSmem S;
     constexpr int kPerT = (kGraphNodes + kSmallThreads - 1) / kSmallThreads;

@@ -4,7 +4,7 @@
 ``models/refinedet.py:141`` and the eval scripts call (``forward``,
 ``forward_python_nms``) and adds the fused detect stage the metric is quoted on
 (``detect``: Detect_RefineDet.forward + the per-class loop of
-``eval_refinedet_coco.py:205-232`` in three kernel launches, inputs read once).
+``eval_refinedet_coco.py:205-232`` in four kernel launches, inputs read once).
 """
 import torch
 

@@ -7,6 +7,7 @@
 import csv
 import io
 import json
+import re
 import subprocess
 import sys
 
@@ -23,6 +24,7 @@ def main():
            'kernels': {}}
     for r in data:
         name = r[col['Kernel Name']].split('(')[0]
+        name = re.sub(r'<.*?>', '', re.sub(r'^void\s+', '', name)).split('::')[-1].strip()
         rd = float(r[col['dram__bytes_read.sum']]) * UNIT[units[col['dram__bytes_read.sum']]]
         wr = float(r[col['dram__bytes_write.sum']]) * UNIT[units[col['dram__bytes_write.sum']]]
         dur = float(r[col['gpu__time_duration.sum']])
