@@ -251,6 +251,82 @@ def test_fused_detect_logits_in(rd, arm_shift, B, size, C):
     assert (g_counts[:, 0] == 0).all()
 
 
+def _same_detections(a, b):
+    assert torch.equal(a.counts, b.counts)
+    m = torch.arange(a.dets.shape[2], device=a.dets.device).view(1, 1, -1) < a.counts.unsqueeze(-1)
+    assert torch.equal(a.dets[m], b.dets[m])
+    assert torch.equal(a.anchors[m], b.anchors[m])
+
+
+def test_plan_replay_and_lanes(rd):
+    """rd_detect_plan_*: the captured launch chain gives the results of the direct call, replay after replay,
+    on another stream, with refilled input buffers, and with two plans in flight over separate lanes."""
+    size, C, B = '320', 21, 4
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward().cuda()
+    P = priors.shape[0]
+    det = rd.Detect_RefineDet(C, 320, 0, 1000, 0.01, 0.45, 0.01, 500)
+    scale = torch.tensor([320.0] * 4).cuda()
+    sets = [[t.cuda() for t in gen.detect_inputs(500 + i, B, P, C, 'sparse', arm_shift=-4.0)] for i in range(3)]
+    direct = [det.detect(*a, priors, scale=scale) for a in sets]
+    buf = [t.clone() for t in sets[0]]                               # static input buffers of the plan
+    plan = det.plan(*buf, priors, scale=scale)
+    _same_detections(plan.launch(), direct[0])
+    side = torch.cuda.Stream()
+    for i in (1, 2, 0):
+        for d, s_ in zip(buf, sets[i]):
+            d.copy_(s_)
+        side.wait_stream(torch.cuda.current_stream())
+        res = plan.launch(side)
+        side.synchronize()
+        _same_detections(res, direct[i])
+    # two lanes, two plans, both in flight
+    lanes = [(torch.cuda.Stream(), det.new_workspace(B, P, priors.device), det.new_outputs(B, priors.device))
+             for _ in range(2)]
+    plans = [det.plan(*sets[i], priors, scale=scale, workspace=lanes[i][1], out=lanes[i][2]) for i in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        out = [plans[i].launch(lanes[i][0]) for i in range(2)]
+    torch.cuda.synchronize()
+    for i in range(2):
+        _same_detections(out[i], direct[i])
+    with pytest.raises(ValueError):
+        det.plan(sets[0][0][:, ::2], sets[0][1], sets[0][2], sets[0][3], priors)      # non-contiguous: referenced, not copied
+    plan.close()
+    with pytest.raises(RuntimeError):
+        plan.launch()
+
+
+@pytest.mark.parametrize('dma_rows', [True, False])
+def test_host_pipeline(rd, dma_rows):
+    """DetectHostPipeline (pinned host inputs, several lanes) == detect() + packed() on device copies."""
+    size, C, B = '320', 21, 3
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward().cuda()
+    P = priors.shape[0]
+    det = rd.Detect_RefineDet(C, 320, 0, 1000, 0.01, 0.45, 0.01, 500)
+    scale = torch.tensor([320.0] * 4).cuda()
+    hs = [[t.pin_memory() for t in gen.detect_inputs(700 + i, B, P, C, 'sparse', arm_shift=-4.0)] for i in range(3)]
+    pipe = rd.DetectHostPipeline(det, priors, scale, B, lanes=2, dma_rows=dma_rows)
+    tickets = []
+    got = []
+    for k in range(6):
+        tickets.append((k % 3, pipe.submit(hs[k % 3])))
+        if len(tickets) == 2:
+            i, t = tickets.pop(0)
+            c, r = pipe.result(t)
+            got.append((i, c.clone(), r.clone()))
+    while tickets:
+        i, t = tickets.pop(0)
+        c, r = pipe.result(t)
+        got.append((i, c.clone(), r.clone()))
+    for i, c, r in got:
+        ref = det.detect(*[t.cuda() for t in hs[i]], priors, scale=scale)
+        offs, rows = ref.packed()
+        assert torch.equal(c, ref.counts.cpu())
+        assert torch.equal(r, rows.cpu())
+    c2, r2 = det.detect_host(hs[0], priors, scale)                   # serial form
+    assert torch.equal(c2, got[0][1]) and torch.equal(r2, got[0][2])
+
+
 def test_forward_python_nms_vs_oracle(rd):
     size, C, B, top_k = '320', 5, 2, 200
     priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward()
