@@ -453,6 +453,25 @@ def main():
                              'ARM-passing anchors only) instead of a separate read+write pass over odm_conf'}
         del plan_l
 
+    # a3: Detect_RefineDet.forward as models/refinedet.py:141 calls it (dense boxes + scores out, in-place zeroing)
+    a3 = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        a = dev_sets[0]
+        n3 = 10
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n3 + 2)]
+        for s_ev3, e_ev3 in evs:
+            conf = a[3].clone()
+            flush_buf.zero_()
+            s_ev3.record(main)
+            det.forward(a[0], a[1], a[2], conf, priors)
+            e_ev3.record(main)
+        torch.cuda.synchronize()
+        ms3 = sum(x.elapsed_time(y) for x, y in evs[2:]) / n3
+        bytes3 = BATCH * (BYTES_PER_IMAGE + 4 * P * (4 + C))             # SURVEY 8d "a3 contract only"
+        a3 = {'ms_per_step': ms3, 'value': BATCH / (ms3 * 1e-3), 'unit': UNIT,
+              'achieved_GBs': bytes3 / (ms3 * 1e-3) / 1e9, 'frac_of_hbm_peak': bytes3 / (ms3 * 1e-3) / 1e9 / peak,
+              'algorithmic_bytes_per_launch': bytes3}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, done, elapsed = cpu_reference_run(args.workload, 1000, 1, cores, budget_s=12.0)
@@ -470,7 +489,7 @@ def main():
                                arm_pass_fraction=arm_pass, kept_rows_per_step=kept_rows),
                 'latency_ms_per_batch': latency_ms,
                 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'secondary': secondary,
-                'logits_in': logits_in,
+                'logits_in': logits_in, 'a3_forward': a3,
                 'gpu_launches': int(launches),
                 'clocks': clocks.summary()}
         print(json.dumps(line))

@@ -225,7 +225,7 @@ __device__ __forceinline__ bool arm_pass(float2 ac, const ArmGate& g) {
     return !(e1 / (e0 + e1) <= g.thre);
 }
 
-template <bool kLogits>
+template <bool kLogits, bool kLines>
 __global__ void __launch_bounds__(kCollectThreads)
 collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ arm_conf,
                const float4* __restrict__ odm_loc, const float* __restrict__ odm_conf,
@@ -311,15 +311,46 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
             const int rl0 = wib * kRowsPerWarp + k0;               // row of the tile
             if (rl0 >= rows_here) break;
             float v[kRowBatch][4];
+            if (kLines) {
+                // host-mapped odm_conf (zero-copy over PCIe): one 16-byte load per lane fetches the (up to) four
+                // whole 128-byte lines that cover the row — PCIe read throughput is set by the request size
+                // (measured: 42 GB/s useful this way against 31 GB/s for 4-byte lane = class loads, which
+                // arrive as sector-sized requests) — and shuffles bring the values to lane = class
+                float4 w[kRowBatch];
+                int off[kRowBatch];
 #pragma unroll
-            for (int k = 0; k < kRowBatch; ++k) {
-                const bool rv = rl0 + k < rows_here;
-                const int a = s * kSliceAnchors + (rv ? s_flat[t0 + rl0 + k] : 0);
-                const float* row = odm_conf + (img + a) * C;
+                for (int k = 0; k < kRowBatch; ++k) {
+                    const bool rv = rl0 + k < rows_here;
+                    const int a = s * kSliceAnchors + (rv ? s_flat[t0 + rl0 + k] : 0);
+                    const float* row = odm_conf + (img + a) * C;
+                    const float* line0 = reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(row) & ~(uintptr_t)127);
+                    off[k] = (int)(row - line0);                               // 0..31
+                    const bool need = rv && lane * 4 < off[k] + C;             // lanes past the row's last line stay idle
+                    w[k] = need ? ldg_stream4(reinterpret_cast<const float4*>(line0) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
-                for (int sgm = 0; sgm < 4; ++sgm) {
-                    const int c = sgm * 32 + lane;
-                    v[k][sgm] = (rv && sgm < nseg && c < C) ? ldg_stream1(row + c) : 0.f;
+                for (int k = 0; k < kRowBatch; ++k) {
+#pragma unroll
+                    for (int sgm = 0; sgm < 4; ++sgm) {
+                        const int i = off[k] + sgm * 32 + lane;                // float index inside the 512-byte span
+                        const int src = (i >> 2) & 31;
+                        const float x = __shfl_sync(kFullMask, w[k].x, src), y = __shfl_sync(kFullMask, w[k].y, src);
+                        const float z = __shfl_sync(kFullMask, w[k].z, src), q = __shfl_sync(kFullMask, w[k].w, src);
+                        const int comp = i & 3;
+                        v[k][sgm] = comp == 0 ? x : comp == 1 ? y : comp == 2 ? z : q;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kRowBatch; ++k) {
+                    const bool rv = rl0 + k < rows_here;
+                    const int a = s * kSliceAnchors + (rv ? s_flat[t0 + rl0 + k] : 0);
+                    const float* row = odm_conf + (img + a) * C;
+#pragma unroll
+                    for (int sgm = 0; sgm < 4; ++sgm) {
+                        const int c = sgm * 32 + lane;
+                        v[k][sgm] = (rv && sgm < nseg && c < C) ? ldg_stream1(row + c) : 0.f;
+                    }
                 }
             }
             if (kLogits) {
@@ -922,14 +953,21 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
         gate.gap_lo = (float)(lg - margin);
         gate.gap_hi = (float)(lg + margin);
     }
-    if (nms_flags & RD_INPUT_LOGITS)
-        collect_kernel<true><<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
+    // host-mapped (pinned) odm_conf: fetch whole 128-byte lines (see collect_kernel); needs rows that fit four
+    // lines from any offset, a line-aligned base and a tensor end that no 16-byte load can straddle
+    bool lines = false;
+    if (C <= 97 && ((uintptr_t)odm_conf & 127) == 0 && ((size_t)B * P * C) % 32 == 0) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, odm_conf) == cudaSuccess) lines = pa.type == cudaMemoryTypeHost;
+        else (void)cudaGetLastError();
+    }
+    {
+        auto kern = (nms_flags & RD_INPUT_LOGITS) ? (lines ? collect_kernel<true, true> : collect_kernel<true, false>)
+                                                  : (lines ? collect_kernel<false, true> : collect_kernel<false, false>);
+        kern<<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
             (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
             P, C, ws.S, ws.Pn, gate, v0, v1, ws.nsc, ws.header, GO);
-    else
-        collect_kernel<false><<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
-            (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
-            P, C, ws.S, ws.Pn, gate, v0, v1, ws.nsc, ws.header, GO);
+    }
     note_launch();
     RD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[1], st);

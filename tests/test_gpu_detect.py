@@ -296,10 +296,12 @@ def test_plan_replay_and_lanes(rd):
         plan.launch()
 
 
-@pytest.mark.parametrize('dma_rows', [True, False])
-def test_host_pipeline(rd, dma_rows):
-    """DetectHostPipeline (pinned host inputs, several lanes) == detect() + packed() on device copies."""
-    size, C, B = '320', 21, 3
+@pytest.mark.parametrize('dma_rows,B,C', [(True, 3, 21), (False, 3, 21), (True, 4, 24), (True, 32, 81)])
+def test_host_pipeline(rd, dma_rows, B, C):
+    """DetectHostPipeline (pinned host inputs, several lanes) == detect() + packed() on device copies.
+    (4, 24) and (32, 81) meet the conditions of the line-granular PCIe row fetch of collect_kernel
+    (B*P*C a multiple of 32), with row offsets of every residue inside the 128-byte lines."""
+    size = '320'
     priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward().cuda()
     P = priors.shape[0]
     det = rd.Detect_RefineDet(C, 320, 0, 1000, 0.01, 0.45, 0.01, 500)
