@@ -30,17 +30,6 @@ namespace rd {
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
-#ifdef RD_PROFILE_PHASES
-__device__ long long g_dbg[64];
-#define RD_MARK(slot) do { if (blockIdx.x == 3 && blockIdx.y == 5 && threadIdx.x == 0) g_dbg[slot] = clock64(); } while (0)
-__device__ __forceinline__ unsigned long long rd_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define RD_TMAX(slot) do { if (threadIdx.x == 0) atomicMax((unsigned long long*)&g_dbg[slot], rd_gtime()); } while (0)
-#define RD_TMIN(slot) do { if (threadIdx.x == 0) atomicMin((unsigned long long*)&g_dbg[slot], rd_gtime()); } while (0)
-#else
-#define RD_MARK(slot) do {} while (0)
-#define RD_TMAX(slot) do {} while (0)
-#define RD_TMIN(slot) do {} while (0)
-#endif
 constexpr int kCollectThreads = 256;
 constexpr int kSliceAnchors = 1024;   // anchors per collect CTA
 #ifndef RD_LARGE_THREADS
@@ -238,7 +227,6 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int s = blockIdx.x, b = blockIdx.y;
-    RD_TMIN(25);
     if (s == 0 && b == 0 && threadIdx.x == 0) header[0] = 0;          // queue of the large-NMS kernel
     if (s == 0 && threadIdx.x == 0) GO.img_flag[b] = 0;
     const int a0 = s * kSliceAnchors + wib * (32 * kChunks);          // first anchor of this warp
@@ -475,11 +463,9 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
              uint4* __restrict__ adj_all, int* __restrict__ adjn_all, int* __restrict__ img_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphSmem& G = *reinterpret_cast<GraphSmem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int g = blockIdx.x, b = blockIdx.y;
     grid_dependency_wait();          // collect_kernel has completed (this kernel is launched early)
-    RD_MARK(0);
-    RD_TMIN(24);
     grid_launch_dependents();        // nms_small_kernel's scan + sort (graph independent) may run beside this kernel
     const int N = nnodes[b];
     if (N > kGraphNodes) {
@@ -500,7 +486,6 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
         G.x1[i] = bx.x; G.y1[i] = bx.y; G.x2[i] = bx.z; G.y2[i] = bx.w;
         G.cr[i] = ncr[(size_t)b * kGraphNodes + i];
     }
-    RD_MARK(1);
     // 2. inclusive prefix-OR over the bins, straight from the global marks: S[c] = starts at <= c,
     //    E[c] = ends before c.  One (table, word) column per thread, 32 independent loads each.
     {
@@ -516,8 +501,6 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
         }
     }
     __syncthreads();
-    RD_MARK(2);
-    RD_MARK(3);
     // 3. pairs (i < j) of own nodes that survive the bin cull.  Work item = (own node, mask word):
     //    every thread handles a few items, so nothing serialises on a box that overlaps hundreds of others.
     const uint32_t* Sx = G.tab;
@@ -562,8 +545,6 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
         if (tid == 0) img_flag[b] = 1;
         return;
     }
-    RD_MARK(4);
-    RD_MARK(5);
     {
         const int cnt = min(G.npairs, kGraphPairCap);
         for (int p = tid; p < cnt; p += kGraphThreads) {
@@ -573,9 +554,7 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
         }
     }
     __syncthreads();
-    RD_MARK(6);
     if (tid == 0 && G.overflow) img_flag[b] = 1;
-    RD_TMAX(20);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -616,7 +595,6 @@ nms_small_kernel(FusedNmsArgs A) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x, b = blockIdx.y;
     const int bc = b * A.C + c;
-    RD_TMIN(21);
     if (c == 0) {
         // this CTA has no problem (background is never evaluated, eval_refinedet_coco.py:213): it leaves the
         // graph control block of its image zero for the next call, once graph_kernel is done with it
@@ -684,7 +662,6 @@ nms_small_kernel(FusedNmsArgs A) {
         return;
     }
     cta_sort_small<kSmallThreads>(S, n);
-    RD_TMAX(22);
     grid_dependency_wait();                                       // graph_kernel has completed
     if (A.img_flag[b] != 0) {                                     // degree / pair overflow: no graph after all
         if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
@@ -702,15 +679,13 @@ nms_small_kernel(FusedNmsArgs A) {
     G.nanc = A.nanc + (size_t)b * A.P;
     const int kept = cta_nms_graph<kSmallThreads>(S, n, A.max_out, sink, G);
     if (tid == 0) A.out_counts[bc] = kept;
-    RD_TMAX(23);
 }
 
 __global__ void __launch_bounds__(kLargeThreads)
 nms_large_kernel(FusedNmsArgs A, int mcap) {
     extern __shared__ __align__(16) unsigned char smem[];
     const NmsSmemLayout L = nms_layout(mcap);
-    int* s_cnt = reinterpret_cast<int*>(smem + L.off_cnt);
-    int* s_offs = reinterpret_cast<int*>(smem + L.off_offs);
+    int* s_cnt = reinterpret_cast<int*>(smem + L.off_misc) + 15;     // misc[15]: unused by nms_process
     const int tid = threadIdx.x, lane = tid & 31;
     grid_dependency_wait();          // nms_small_kernel (and everything before it) has completed
     const uint32_t nq = A.header[0];
@@ -746,10 +721,9 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
         }
         __syncthreads();
         const int n = s_cnt[0];
-        if (tid == 0) { s_offs[0] = 0; s_offs[1] = n; }
         __syncthreads();
         NmsProblem pb;
-        pb.cl.base = keys; pb.cl.S = 1; pb.cl.stride = 0; pb.cl.cnt = s_cnt; pb.cl.offs = s_offs; pb.cl.n = n;
+        pb.cl.base = keys; pb.cl.n = n;
         pb.boxes = A.nbox + (size_t)b * A.P;
         pb.has_scale = 0;                                         // node boxes are already scaled
         pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
@@ -787,12 +761,8 @@ nms_single_kernel(const unsigned long long* cand, int n, const float4* boxes, fl
                   int flags, int mcap, long long* keep_out, int* keep_out32, int* count_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     const NmsSmemLayout L = nms_layout(mcap);
-    int* s_cnt = reinterpret_cast<int*>(smem + L.off_cnt);
-    int* s_offs = reinterpret_cast<int*>(smem + L.off_offs);
-    if (threadIdx.x == 0) { s_cnt[0] = n; s_offs[0] = 0; s_offs[1] = n; }
-    __syncthreads();
     NmsProblem pb;
-    pb.cl.base = cand; pb.cl.S = 1; pb.cl.stride = n; pb.cl.cnt = s_cnt; pb.cl.offs = s_offs; pb.cl.n = n;
+    pb.cl.base = cand; pb.cl.n = n;
     pb.boxes = boxes; pb.has_scale = 0;
     pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
     pb.thr = thr; pb.top_k = top_k; pb.max_out = max_out; pb.flags = flags;
@@ -862,14 +832,6 @@ extern "C" {
 
 unsigned long long rd_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-#ifdef RD_PROFILE_PHASES
-__attribute__((visibility("default"))) int rd_debug_read(long long* out64) {
-    return (int)cudaMemcpyFromSymbol(out64, g_dbg, sizeof(long long) * 64);
-}
-__attribute__((visibility("default"))) int rd_debug_write(const long long* in64) {
-    return (int)cudaMemcpyToSymbol(g_dbg, in64, sizeof(long long) * 64);
-}
-#endif
 
 int rd_detect_forward(const float* arm_loc, const float* arm_conf, const float* odm_loc, float* odm_conf,
                       const float* priors, int B, int P, int C, float objectness_thre, float v0, float v1,

@@ -18,8 +18,9 @@
 //   step; the surviving (candidate, kept earlier box) pairs are flattened into a list and tested
 //   by all threads, in-block dependencies are resolved with ballots.
 //
-//   small problems (n <= 256, no select) of images whose suppression graph exists: cta_nms_graph —
-//     sorted runs of 32 in registers (bitonic over shuffles) merged by rank, then graph look-ups
+//   small problems (n <= 256, no select) of images whose suppression graph exists: cta_sort_small
+//     (sorted runs of 32 in registers, bitonic over shuffles, merged by rank) + cta_nms_graph (direct
+//     node -> rank table, graph look-ups, dependency rounds)
 //   everything else: nms_process — radix select over the L2-resident key list when n > top_k,
 //     shared-memory bitonic sort, per-problem bin tables, walk with the tests done in place
 #pragma once
@@ -28,16 +29,10 @@
 namespace rd {
 
 constexpr int kCols = 32;  // spatial bins per axis
-constexpr int kMaxSlices = 64;
 
-// A candidate list stored as S sub-lists (one per producer CTA): sub-list s holds cnt[s] keys at
-// base + s * stride.  cnt / offs live in shared memory; offs[s] = exclusive prefix sum, offs[S] = n.
+// Candidate keys of one problem: n keys at `base`, any order.
 struct CandList {
     const unsigned long long* base;
-    int S;
-    int stride;
-    const int* cnt;
-    const int* offs;
     int n;
 };
 
@@ -363,8 +358,8 @@ struct NmsSmemLayout {
     int W;      // mcap / 32
     int WS;     // padded row stride of the bin tables (odd -> conflict-free)
     int Kp;     // power of two >= mcap (bitonic sort buffer)
-    size_t off_keys, off_x1, off_y1, off_x2, off_y2, off_cr, off_tab, off_keptbits, off_hist, off_cnt,
-        off_offs, off_misc, off_pairs, off_tin, total;
+    size_t off_keys, off_x1, off_y1, off_x2, off_y2, off_cr, off_tab, off_keptbits, off_hist, off_misc,
+        off_pairs, off_tin, total;
 };
 
 __host__ __device__ inline int next_pow2(int v) {
@@ -390,8 +385,6 @@ __host__ __device__ inline NmsSmemLayout nms_layout(int mcap_req) {
     L.off_tab = o;       o += (size_t)4 * kCols * L.WS * 4;
     L.off_keptbits = o;  o += (size_t)L.W * 4;
     L.off_hist = o;      o += 256 * 4;
-    L.off_cnt = o;       o += kMaxSlices * 4;
-    L.off_offs = o;      o += (kMaxSlices + 1) * 4 + 12;
     L.off_misc = o;      o += 16 * 4;
     L.off_tin = o;       o += 32 * 4;
     L.off_pairs = o;     o += (size_t)kLargePairCap * 4;
@@ -399,8 +392,7 @@ __host__ __device__ inline NmsSmemLayout nms_layout(int mcap_req) {
     return L;
 }
 
-// Runs one problem on the calling CTA.  The slice counts / offsets of pb.cl must already be in
-// shared memory (pb.cl.cnt / pb.cl.offs).  Rows are emitted through `sink`.  Returns the kept
+// Runs one problem on the calling CTA.  Rows are emitted through `sink`.  Returns the kept
 // count (uniform over the CTA).
 __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, const NmsProblem& pb,
                                   const RowSink& sink) {
@@ -428,11 +420,7 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
 
     // ---- 1. load or select the m highest keys --------------------------------------------------
     if (n <= top_k) {
-        for (int s = 0; s < cl.S; ++s) {
-            const unsigned long long* p = cl.base + (size_t)s * cl.stride;
-            const int c = cl.cnt[s], o = cl.offs[s];
-            for (int i = tid; i < c; i += nthr) keys[o + i] = p[i];
-        }
+        for (int i = tid; i < n; i += nthr) keys[i] = cl.base[i];
     } else {
         unsigned long long prefix = 0;   // known high bits of the threshold key
         int need = top_k;                // how many keys of the current bucket are wanted
@@ -440,14 +428,10 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
         for (int shift = 56; shift >= 0; shift -= 8) {
             for (int i = tid; i < 256; i += nthr) hist[i] = 0;
             __syncthreads();
-            for (int s = 0; s < cl.S; ++s) {
-                const unsigned long long* p = cl.base + (size_t)s * cl.stride;
-                const int c = cl.cnt[s];
-                for (int i = tid; i < c; i += nthr) {
-                    const unsigned long long k = p[i];
-                    const bool match = (shift == 56) || ((k >> (shift + 8)) == prefix);
-                    if (match) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
-                }
+            for (int i = tid; i < n; i += nthr) {
+                const unsigned long long k = cl.base[i];
+                const bool match = (shift == 56) || ((k >> (shift + 8)) == prefix);
+                if (match) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
             }
             __syncthreads();
             if (warp == 0) {
@@ -488,15 +472,11 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
         }
         if (tid == 0) misc[0] = 0;
         __syncthreads();
-        for (int s = 0; s < cl.S; ++s) {
-            const unsigned long long* p = cl.base + (size_t)s * cl.stride;
-            const int c = cl.cnt[s];
-            for (int i = tid; i < c; i += nthr) {
-                const unsigned long long k = p[i];
-                if (k >= thresh_key) {
-                    const uint32_t pos = atomicAdd(&misc[0], 1u);
-                    if (pos < (uint32_t)top_k) keys[pos] = k;
-                }
+        for (int i = tid; i < n; i += nthr) {
+            const unsigned long long k = cl.base[i];
+            if (k >= thresh_key) {
+                const uint32_t pos = atomicAdd(&misc[0], 1u);
+                if (pos < (uint32_t)top_k) keys[pos] = k;
             }
         }
     }
