@@ -36,6 +36,9 @@ constexpr int kSliceAnchors = 1024;   // anchors per collect CTA
 #define RD_LARGE_THREADS 512
 #endif
 constexpr int kLargeThreads = RD_LARGE_THREADS;
+#ifndef RD_LARGE_PER_SM
+#define RD_LARGE_PER_SM 3          // resident large-problem CTAs per SM (dense stress case: 3 and 4 measure the same with ticketed problems, 2 is slower)
+#endif
 
 // ---------------------------------------------------------------------------------------
 // workspace of the fused stage.  The control block (header, gtab) must be zero when a call
@@ -227,7 +230,7 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int s = blockIdx.x, b = blockIdx.y;
-    if (s == 0 && b == 0 && threadIdx.x == 0) header[0] = 0;          // queue of the large-NMS kernel
+    if (s == 0 && b == 0 && threadIdx.x == 0) { header[0] = 0; header[1] = 0; }   // queue of the large-NMS kernel: length, next ticket
     if (s == 0 && threadIdx.x == 0) GO.img_flag[b] = 0;
     const int a0 = s * kSliceAnchors + wib * (32 * kChunks);          // first anchor of this warp
     const size_t img = (size_t)b * P;
@@ -689,7 +692,14 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
     const int tid = threadIdx.x, lane = tid & 31;
     grid_dependency_wait();          // nms_small_kernel (and everything before it) has completed
     const uint32_t nq = A.header[0];
-    for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
+    // dynamic tickets: problems differ a lot in cost (select passes, pairs), a static stride leaves CTAs idle
+    for (;;) {
+        __shared__ uint32_t s_ticket;
+        if (tid == 0) s_ticket = nq ? atomicAdd(&A.header[1], 1u) : 0xffffffffu;
+        __syncthreads();
+        const uint32_t q = s_ticket;
+        __syncthreads();
+        if (q >= nq) break;
         const int bc = A.queue[q];
         const int b = bc / A.C;
         const int N = A.nnodes[b];
@@ -977,7 +987,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
         }
         int per_sm = (int)((220 * 1024) / (Ll.total + 1024));
         if (per_sm < 1) per_sm = 1;
-        if (per_sm > 8) per_sm = 8;
+        if (per_sm > RD_LARGE_PER_SM) per_sm = RD_LARGE_PER_SM;
         A.large_grid = s_dev_sms * per_sm;
         A.large_mcap = mcap;
         A.large_smem = (int)Ll.total;
