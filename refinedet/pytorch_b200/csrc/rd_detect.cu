@@ -591,10 +591,14 @@ struct FusedNmsArgs {
 #ifndef RD_SMALL_MINBLOCKS
 #define RD_SMALL_MINBLOCKS (1536 / RD_SMALL_THREADS)
 #endif
-__global__ void __launch_bounds__(kSmallThreads, RD_SMALL_MINBLOCKS)
+// Two instantiations: <256 candidates, 128 threads> for the many-class case (thousands of problems, occupancy
+// matters) and <1024, 256> when the grid cannot fill the GPU anyway (few classes: every problem holds a large
+// share of the image's nodes, e.g. the 2-class SAR-ship configuration).
+template <int kCap, int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 nms_small_kernel(FusedNmsArgs A) {
-    __shared__ SmallSmem S;
-    constexpr int kPerT = (kGraphNodes + kSmallThreads - 1) / kSmallThreads;
+    __shared__ SmallSmem<kCap> S;
+    constexpr int kPerT = (kGraphNodes + kThreads - 1) / kThreads;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x, b = blockIdx.y;
     const int bc = b * A.C + c;
@@ -603,7 +607,7 @@ nms_small_kernel(FusedNmsArgs A) {
         // graph control block of its image zero for the next call, once graph_kernel is done with it
         grid_dependency_wait();
         uint32_t* gt = A.gtab + (size_t)b * kGtabWords;
-        for (int i = tid; i < kGtabWords; i += kSmallThreads) gt[i] = 0;
+        for (int i = tid; i < kGtabWords; i += kThreads) gt[i] = 0;
         if (tid == 0) A.out_counts[bc] = 0;
         return;
     }
@@ -616,12 +620,12 @@ nms_small_kernel(FusedNmsArgs A) {
     // with one barrier in between: no atomics.
     {
         const float* row = A.nsc + (size_t)bc * A.Pn;
-        const int nq = (N + kSmallThreads - 1) / kSmallThreads;   // <= kPerT
+        const int nq = (N + kThreads - 1) / kThreads;   // <= kPerT
         float v[kPerT];
         unsigned bal[kPerT];
 #pragma unroll
         for (int q = 0; q < kPerT; ++q) {
-            const int i = q * kSmallThreads + tid;
+            const int i = q * kThreads + tid;
             v[q] = (q < nq && i < N) ? __ldg(row + i) : -INFINITY;
         }
         int cnt = 0;
@@ -637,18 +641,18 @@ nms_small_kernel(FusedNmsArgs A) {
         __syncthreads();
         int slot = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < kSmallThreads / 32; ++w) {
+        for (int w = 0; w < kThreads / 32; ++w) {
             if (w < warp) slot += S.wsum[w];
             tot += S.wsum[w];
         }
         if (tid == 0) S.n = tot;
-        if (tot <= kSmallCap) {
+        if (tot <= kCap) {
             const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
             for (int q = 0; q < kPerT; ++q) {
                 if (q < nq && bal[q]) {
                     if ((bal[q] >> lane) & 1u)
-                        S.u.runs[slot + __popc(bal[q] & lt)] = make_key(v[q], (uint32_t)(q * kSmallThreads + tid));
+                        S.u.runs[slot + __popc(bal[q] & lt)] = make_key(v[q], (uint32_t)(q * kThreads + tid));
                     slot += __popc(bal[q]);
                 }
             }
@@ -660,11 +664,11 @@ nms_small_kernel(FusedNmsArgs A) {
         if (tid == 0) A.out_counts[bc] = 0;
         return;
     }
-    if (n > A.top_k || n > kSmallCap) {                           // needs the top-k select: large kernel
+    if (n > A.top_k || n > kCap) {                           // needs the top-k select: large kernel
         if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
         return;
     }
-    cta_sort_small<kSmallThreads>(S, n);
+    cta_sort_small<kThreads, kCap>(S, n);
     grid_dependency_wait();                                       // graph_kernel has completed
     if (A.img_flag[b] != 0) {                                     // degree / pair overflow: no graph after all
         if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
@@ -680,7 +684,7 @@ nms_small_kernel(FusedNmsArgs A) {
     G.adjn = A.adjn + (size_t)b * kGraphNodes;
     G.nbox = A.nbox + (size_t)b * A.P;
     G.nanc = A.nanc + (size_t)b * A.P;
-    const int kept = cta_nms_graph<kSmallThreads>(S, n, A.max_out, sink, G);
+    const int kept = cta_nms_graph<kThreads, kCap>(S, n, A.max_out, sink, G);
     if (tid == 0) A.out_counts[bc] = kept;
 }
 
@@ -994,7 +998,10 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     }
     if (ev) cudaEventRecord(ev[2], st);
     {   // programmatic dependent launch: the scan + sort of nms_small_kernel run beside graph_kernel
-        cudaError_t e = launch_pdl(nms_small_kernel, dim3(C, B), dim3(kSmallThreads), 0, st, A);
+        const bool wide = (long long)B * (C - 1) <= 2 * 148;       // the grid cannot fill the GPU: footprint is free
+        cudaError_t e = wide ? launch_pdl(nms_small_kernel<kWideCap, kWideThreads, 2>, dim3(C, B), dim3(kWideThreads), 0, st, A)
+                             : launch_pdl(nms_small_kernel<kSmallCap, kSmallThreads, RD_SMALL_MINBLOCKS>, dim3(C, B),
+                                          dim3(kSmallThreads), 0, st, A);
         if (e != cudaSuccess) return (int)e;
     }
     note_launch();

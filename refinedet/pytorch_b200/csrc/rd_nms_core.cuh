@@ -24,6 +24,8 @@
 //   everything else: nms_process — radix select over the L2-resident key list when n > top_k,
 //     shared-memory bitonic sort, per-problem bin tables, walk with the tests done in place
 #pragma once
+#include <type_traits>
+
 #include "rd_common.cuh"
 
 namespace rd {
@@ -160,24 +162,27 @@ __device__ __forceinline__ unsigned long long warp_sort32_desc(unsigned long lon
 #ifndef RD_SMALL_THREADS
 #define RD_SMALL_THREADS 128
 #endif
-constexpr int kSmallThreads = RD_SMALL_THREADS;
+constexpr int kSmallThreads = RD_SMALL_THREADS;   // common variant: <= 256 candidates, 128 threads, 6.7 KB smem
 constexpr int kSmallCap = 256;
-constexpr int kSmallW = kSmallCap / 32;      // 8 mask words
+constexpr int kWideThreads = 256;                 // wide variant (few problems, e.g. C = 2): <= 1024 candidates
+constexpr int kWideCap = 1024;
 
 constexpr int kGraphNodes = 1024;     // images with more ARM-passing anchors have no suppression graph
 constexpr int kAdjDeg = 8;            // adjacency slots per node; an image whose graph overflows is flagged dense
 
+template <int kCap>
 struct SmallSmem {
-    unsigned long long keys[kSmallCap];           // sorted keys
+    using rank_t = typename std::conditional<(kCap > 256), unsigned short, unsigned char>::type;
+    unsigned long long keys[kCap];                // sorted keys
     union {
-        unsigned long long runs[kSmallCap];       // unsorted candidates, then sorted runs of 32 (during the sort)
+        unsigned long long runs[kCap];            // unsorted candidates, then sorted runs of 32 (during the sort)
         struct {
             unsigned short rank[kGraphNodes];     // node -> rank in this problem, 0xffff = not a candidate
-            unsigned char deps[kSmallCap * kAdjDeg];   // ranks of the dependencies of every candidate
+            rank_t deps[kCap * kAdjDeg];          // ranks of the dependencies of every candidate
         } g;
     } u;
-    unsigned char depn[kSmallCap];
-    unsigned char state[kSmallCap];               // 0 undecided, 1 kept, 2 suppressed
+    unsigned char depn[kCap];
+    unsigned char state[kCap];                    // 0 undecided, 1 kept, 2 suppressed
     int wsum[8];
     int n;
 };
@@ -185,8 +190,8 @@ struct SmallSmem {
 // Sort of a small problem: S.u.runs[0..m) holds the candidate keys in any order.  Sorted runs of 32 in
 // registers (one run per warp at a time, bitonic over shuffles), merged by rank.  On return (after a CTA
 // barrier) S.keys[0..m) holds the keys in descending order.
-template <int kThreads>
-__device__ __forceinline__ void cta_sort_small(SmallSmem& S, int m) {
+template <int kThreads, int kCap>
+__device__ __forceinline__ void cta_sort_small(SmallSmem<kCap>& S, int m) {
     constexpr int kSmallWarps = kThreads / 32;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -241,10 +246,11 @@ struct GraphView {
 
 // S.keys[0..m) = the problem's sorted keys (key index = node).  One round of global loads: adjacency row,
 // box and anchor of every candidate.
-template <int kThreads>
-__device__ inline int cta_nms_graph(SmallSmem& S, int m, int max_out, const RowSink& sink, const GraphView& G) {
+template <int kThreads, int kCap>
+__device__ inline int cta_nms_graph(SmallSmem<kCap>& S, int m, int max_out, const RowSink& sink, const GraphView& G) {
+    using rank_t = typename SmallSmem<kCap>::rank_t;
     constexpr int kSmallWarps = kThreads / 32;
-    constexpr int kPerT = (kSmallCap + kThreads - 1) / kThreads;
+    constexpr int kPerT = (kCap + kThreads - 1) / kThreads;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -290,7 +296,7 @@ __device__ inline int cta_nms_graph(SmallSmem& S, int m, int max_out, const RowS
                 if (k < dn[q]) {
                     const uint32_t v = (nb[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
                     const int rv = S.u.g.rank[v];
-                    if (rv < r) S.u.g.deps[r * kAdjDeg + nd++] = (unsigned char)rv;
+                    if (rv < r) S.u.g.deps[r * kAdjDeg + nd++] = (rank_t)rv;
                 }
             }
             S.depn[r] = (unsigned char)nd;
@@ -299,7 +305,7 @@ __device__ inline int cta_nms_graph(SmallSmem& S, int m, int max_out, const RowS
     }
     __syncthreads();
     // ---- resolve in rounds (dependencies always point to earlier ranks: terminates) ---------------
-    for (int round = 0; round < kSmallCap; ++round) {
+    for (int round = 0; round < kCap; ++round) {
         int undecided = 0;
 #pragma unroll
         for (int q = 0; q < kPerT; ++q) {

@@ -4,6 +4,7 @@ Same names, argument order and results as the reference (file:line cited per fun
 every function takes CUDA tensors and calls ``librefinedet_b200.so`` through ``_ffi``.
 There is no CPU path.
 """
+import numpy as np
 import torch
 
 from .. import _ffi
@@ -127,8 +128,10 @@ def pad_targets(targets, device):
     if sum(counts):
         # one concatenation + one indexed store instead of B slice assignments
         flat = torch.cat([t.detach().to(device=device, dtype=torch.float32).reshape(-1, 5) for t in targets if t.shape[0]])
-        rows = [i * gmax + k for i, n in enumerate(counts) for k in range(n)]
-        padded[torch.tensor(rows, dtype=torch.int64).to(device, non_blocking=True)] = flat
+        cnt = np.asarray(counts, dtype=np.int64)
+        start = np.cumsum(cnt) - cnt                                     # first row of every image in `flat`
+        rows = np.repeat(np.arange(B, dtype=np.int64) * gmax - start, cnt) + np.arange(int(cnt.sum()), dtype=np.int64)
+        padded[torch.from_numpy(rows).to(device, non_blocking=True)] = flat
     padded = padded.view(B, gmax, 5)
     truths = padded[:, :, :4].contiguous()
     labels = padded[:, :, 4].contiguous()
