@@ -17,19 +17,28 @@
 //   loss_final_kernel     sums the per-image partials in order, N = sum(num_pos), divides
 //   loss_backward_kernel  d loss_c / d conf = (softmax(x) - onehot(t)) * g_c / N on pos | neg rows,
 //                         d loss_l / d loc = clamp(loc - loc_t, -1, 1) * g_l / N on pos rows, zeros
-//                         elsewhere; every element of both gradients is written exactly once
+//                         elsewhere; every element of both gradients is written (selected rows twice)
 #include "rd_common.cuh"
 
 namespace rd {
 
 constexpr int kLossThreads = 256;
 constexpr int kLossMaxClasses = 128;
+constexpr float kLog2e = 1.4426950408889634f;
 
 // softmax(arm_conf)[1] <= theta (refinedet_multibox_loss.py:98-101), fp32, max-subtracted like F.softmax
 __device__ __forceinline__ bool arm_filtered(float2 a, float theta) {
     const float m = fmaxf(a.x, a.y);
     const float e0 = expf(a.x - m), e1 = expf(a.y - m);
     return e1 / (e0 + e1) <= theta;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // generic C (3..128): a CTA stages kLossRows consecutive rows (one contiguous, coalesced float4 stream)
@@ -43,7 +52,7 @@ __global__ void __launch_bounds__(kLossRows)
 conf_loss_kernel(const float* __restrict__ conf, const long long* __restrict__ conf_t,
                  const float2* __restrict__ arm_conf, float theta, long long rows, int C,
                  float* __restrict__ ce_out, float* __restrict__ lse_out, unsigned char* __restrict__ pos_out) {
-    extern __shared__ float s_x[];                   // [kLossRows][Cp]
+    extern __shared__ __align__(16) float s_x[];     // [kLossRows][Cp]
     const int Cp = C | 1;
     const int tid = threadIdx.x;
     for (long long r0 = (long long)blockIdx.x * kLossRows; r0 < rows; r0 += (long long)gridDim.x * kLossRows) {
@@ -58,7 +67,17 @@ conf_loss_kernel(const float* __restrict__ conf, const long long* __restrict__ c
             t = conf_t[r];
             if (arm_conf && t > 0) arm = __ldg(arm_conf + r);
         }
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+        if (aligned && Cp == C) {
+            // odd C: the tile is a verbatim copy (row stride C is already conflict-free): asynchronous 16-byte
+            // global -> shared copies, all of a thread's ~20 in flight at once, no register staging
+            const int nvec = nelem >> 2;
+            for (int q = tid; q < nvec; q += kLossRows)
+                cp_async16(reinterpret_cast<float4*>(s_x) + q, reinterpret_cast<const float4*>(src) + q);
+            for (int e2 = nvec * 4 + tid; e2 < nelem; e2 += kLossRows) s_x[e2] = src[e2];
+            cp_async_wait_all();
+        } else if (aligned) {
+            // even C: one padding element per row, (row, class) of every element tracked incrementally
             const int nvec = nelem >> 2;
             int e = tid * 4;
             int rr = e / C, c = e - rr * C;
@@ -92,10 +111,21 @@ conf_loss_kernel(const float* __restrict__ conf, const long long* __restrict__ c
         __syncthreads();
         if (tid < nrows) {
             const float* x = s_x + tid * Cp;
-            float m = x[0];
-            for (int c = 1; c < C; ++c) m = fmaxf(m, x[c]);
-            float sum = 0.f;
-            for (int c = 0; c < C; ++c) sum += expf(x[c] - m);
+            // four independent chains each (a thread owns a whole row: the loop is latency-bound otherwise)
+            float m0 = x[0], m1 = m0, m2 = m0, m3 = m0;
+            int c = 0;
+            for (; c + 4 <= C; c += 4) {
+                m0 = fmaxf(m0, x[c]); m1 = fmaxf(m1, x[c + 1]); m2 = fmaxf(m2, x[c + 2]); m3 = fmaxf(m3, x[c + 3]);
+            }
+            for (; c < C; ++c) m0 = fmaxf(m0, x[c]);
+            const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // exp(x - m) = exp2((x - m) log2 e): one MUFU.EX2, rel. error < 2e-7
+            for (c = 0; c + 4 <= C; c += 4) {
+                s0 += exp2f((x[c] - m) * kLog2e); s1 += exp2f((x[c + 1] - m) * kLog2e);
+                s2 += exp2f((x[c + 2] - m) * kLog2e); s3 += exp2f((x[c + 3] - m) * kLog2e);
+            }
+            for (; c < C; ++c) s0 += exp2f((x[c] - m) * kLog2e);
+            const float sum = (s0 + s1) + (s2 + s3);
             const float lse = logf(sum) + m;
             ce_out[r] = lse - x[(int)t];
             lse_out[r] = lse;
@@ -169,18 +199,27 @@ loss_reduce_kernel(const float4* __restrict__ loc, const float4* __restrict__ lo
     }
 }
 
-// one thread: fixed summation order.  N = sum(num_pos) (:134); N < 1 -> zeros (:135-136)
+// one warp: lane l sums the partials q = l, l + 32, ... in order, then a fixed xor tree -> deterministic.
+// N = sum(num_pos) (:134); N < 1 -> zeros (:135-136)
 __global__ void loss_final_kernel(const double* __restrict__ partial, const int* __restrict__ num_pos, int B,
                                   float* loss_l, float* loss_c, float* n_out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int lane = threadIdx.x;
     double tl = 0.0, tc = 0.0;
     long long n = 0;
-    for (int q = 0; q < B * kReduceSplit; ++q) { tl += partial[2 * q]; tc += partial[2 * q + 1]; }
-    for (int b = 0; b < B; ++b) n += num_pos[b];
-    const float N = (float)n;
-    *n_out = N;
-    *loss_l = n > 0 ? (float)tl / N : 0.f;
-    *loss_c = n > 0 ? (float)tc / N : 0.f;
+    for (int q = lane; q < B * kReduceSplit; q += 32) { tl += partial[2 * q]; tc += partial[2 * q + 1]; }
+    for (int b = lane; b < B; b += 32) n += num_pos[b];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        tl += __shfl_xor_sync(kFullMask, tl, d);
+        tc += __shfl_xor_sync(kFullMask, tc, d);
+        n += __shfl_xor_sync(kFullMask, n, d);
+    }
+    if (lane == 0) {
+        const float N = (float)n;
+        *n_out = N;
+        *loss_l = n > 0 ? (float)tl / N : 0.f;
+        *loss_c = n > 0 ? (float)tc / N : 0.f;
+    }
 }
 
 // gradients.  One warp per 32 rows; conf rows of unselected anchors are never read.
@@ -220,38 +259,14 @@ loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ 
         if (!grad_conf) continue;
         const unsigned selmask = __ballot_sync(kFullMask, sel);
         const int nvalid = (int)min((long long)32, rows - r0);
-        // zeros for the unselected rows: lanes stride over the 32*C contiguous elements
+        // zeros over the whole 32*C-element span (contiguous 16-byte stores, no per-element bookkeeping); the
+        // few selected rows (pos | neg, ~6 %) are then overwritten by the same warp, ordered by __syncwarp
         float* base = grad_conf + r0 * C;
         const int nelem = nvalid * C;
         const int nvec = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) ? (nelem >> 2) : 0;
-        {
-            // float4 stores; (row, class) of element 4*q tracked incrementally (no division in the loop)
-            int e0 = lane * 4;
-            int rr = e0 / C, c = e0 - rr * C;
-            const int drr = 128 / C, dc = 128 - drr * C;
-            for (int q = lane; q < nvec; q += 32) {
-                int r1 = rr, c1 = c;
-                unsigned sm = 0;                   // bit k: element k belongs to a selected row
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    sm |= ((selmask >> r1) & 1u) << k;
-                    if (++c1 == C) { c1 = 0; ++r1; }
-                }
-                if (sm == 0) {
-                    *reinterpret_cast<float4*>(base + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (!((sm >> k) & 1u)) base[4 * q + k] = 0.f;
-                }
-                rr += drr; c += dc;
-                if (c >= C) { c -= C; ++rr; }
-            }
-        }
-        for (int e = nvec * 4 + lane; e < nelem; e += 32) {      // tail / unaligned base
-            const int rr = e / C;
-            if (!((selmask >> rr) & 1u)) base[e] = 0.f;
-        }
+        for (int q = lane; q < nvec; q += 32) reinterpret_cast<float4*>(base)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = nvec * 4 + lane; e < nelem; e += 32) base[e] = 0.f;
+        __syncwarp();
         // selected rows: softmax(x) - onehot(t), lane = class
         unsigned m = selmask;
         while (m) {
@@ -265,7 +280,7 @@ loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ 
 #pragma unroll
             for (int sgm = 0; sgm < 4; ++sgm) {
                 const int c = sgm * 32 + lane;
-                if (sgm < nseg && c < C) g[c] = (expf(x[c] - l) - (c == t ? 1.f : 0.f)) * sc;
+                if (sgm < nseg && c < C) g[c] = (exp2f((x[c] - l) * kLog2e) - (c == t ? 1.f : 0.f)) * sc;
             }
         }
     }

@@ -13,7 +13,8 @@
 //   match_pass2_kernel   forced matches (last truth wins, box_utils.py:146-150), labels,
 //                        threshold, encode -> loc_t, conf_t
 //   hnm_select_kernel    one CTA per image row: count positives, MSB-first radix select of the
-//                        num_neg-th largest (loss, ~index) key, write the neg mask
+//                        num_neg-th largest (loss, ~index) key, write the neg mask; the row lives in
+//                        registers (16 values per thread) when P <= 16,384
 //   elementwise kernels  point_form / center_size / decode / encode / intersect / jaccard
 #include "rd_common.cuh"
 
@@ -41,8 +42,7 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
                    float* __restrict__ bt_overlap, int* __restrict__ bt_idx) {       // [B,P] temporaries
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_truth = reinterpret_cast<float4*>(smem_raw);
-    unsigned long long* s_best = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)Gmax * 16);
-    unsigned short* s_list = reinterpret_cast<unsigned short*>(smem_raw + (size_t)Gmax * 24);   // truths to visit
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(smem_raw + (size_t)Gmax * 16);   // truths to visit
     __shared__ uint32_t s_bb[4];          // bounding box of this CTA's anchor boxes (ordered-uint min/max)
     __shared__ int s_wcnt[kMatchThreads / 32];
     __shared__ int s_nlist;
@@ -53,7 +53,6 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
     if (G <= 0) return;
     for (int g = threadIdx.x; g < G; g += kMatchThreads) {
         s_truth[g] = __ldg(truths + (size_t)b * Gmax + g);
-        s_best[g] = 0ull;
     }
     if (threadIdx.x < 4) s_bb[threadIdx.x] = (threadIdx.x < 2) ? 0xffffffffu : 0u;   // min x, min y, max x, max y
     if (threadIdx.x == 0) s_nlist = 0;
@@ -61,12 +60,15 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
     const bool valid = p < P;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) box = anchor_point_box(priors, arm_loc, b, p, P, v0, v1);
+    float wx1, wy1, wx2, wy2;
     {
         uint32_t mnx = valid ? float_to_ordered(box.x) : 0xffffffffu, mny = valid ? float_to_ordered(box.y) : 0xffffffffu;
         uint32_t mxx = valid ? float_to_ordered(box.z) : 0u, mxy = valid ? float_to_ordered(box.w) : 0u;
         mnx = __reduce_min_sync(kFullMask, mnx); mny = __reduce_min_sync(kFullMask, mny);
         mxx = __reduce_max_sync(kFullMask, mxx); mxy = __reduce_max_sync(kFullMask, mxy);
         if (lane == 0) { atomicMin(&s_bb[0], mnx); atomicMin(&s_bb[1], mny); atomicMax(&s_bb[2], mxx); atomicMax(&s_bb[3], mxy); }
+        wx1 = ordered_to_float(mnx); wy1 = ordered_to_float(mny);      // bounding box of this WARP's anchor boxes
+        wx2 = ordered_to_float(mxx); wy2 = ordered_to_float(mxy);
     }
     __syncthreads();
     // Truths that cannot intersect ANY anchor box of this CTA have IoU exactly 0 with all of them
@@ -105,35 +107,54 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
     float best = 0.f;           // IoU with every skipped truth is 0; ties keep the lowest index
     int best_g = 0;
     const bool first_warp_of_row = (blockIdx.x == 0) && (threadIdx.x < 32);
-    for (int li = 0; li < nlist; ++li) {
-        const int g = s_list[li];
-        const float4 t = s_truth[g];
-        // box_utils.py:42-47,62-68 (truth = box_a, anchor = box_b)
-        float w = fmaxf(fminf(t.z, box.z) - fmaxf(t.x, box.x), 0.0f);
-        float h = fmaxf(fminf(t.w, box.w) - fmaxf(t.y, box.y), 0.0f);
-        float inter = w * h;
-        float area_t = (t.z - t.x) * (t.w - t.y);
-        float iou = inter / (area_t + area_b - inter);
-        if (!valid) iou = -1.0f;
-        if (iou > best) { best = iou; best_g = g; }        // first maximal index; (0, g = 0) when nothing overlaps
-        // per-truth best prior: only overlapping anchors (or the row's first warp, which
-        // supplies prior 0 for a truth that overlaps nothing) can win
-        const bool contend = valid && (iou > 0.0f || iou != iou);
-        if (__any_sync(kFullMask, contend) || first_warp_of_row) {
-            uint32_t ord = valid ? float_to_ordered(iou) : 0u;
-            uint32_t mx = __reduce_max_sync(kFullMask, ord);
-            unsigned who = __ballot_sync(kFullMask, valid && ord == mx);
-            if (lane == __ffs(who) - 1) atomicMax(&s_best[g], prior_key(iou, (uint32_t)p));
+    // second, finer cull with the same argument per warp (32 consecutive anchors = a few cells of one row of
+    // the feature map): a truth that cannot intersect any anchor box of the warp is skipped by the warp
+    const bool warp_all = first_warp_of_row || !(wx1 <= wx2) || !(wy1 <= wy2);
+    unsigned long long* bp_row = best_prior + (size_t)b * Gmax;
+    for (int c0 = 0; c0 < nlist; c0 += 32) {
+        // lane = one listed truth: test it against the warp's bounding box, then walk the survivors in
+        // ascending g (list order)
+        const int li = c0 + lane;
+        int g_l = 0;
+        bool hit = false;
+        if (li < nlist) {
+            g_l = s_list[li];
+            hit = warp_all;
+            if (!hit) {
+                const float4 t = s_truth[g_l];
+                const float cw = fminf(t.z, wx2) - fmaxf(t.x, wx1);
+                const float ch = fminf(t.w, wy2) - fmaxf(t.y, wy1);
+                hit = (cw > 0.0f && ch > 0.0f) || !(cw == cw) || !(ch == ch);
+            }
+        }
+        unsigned todo = __ballot_sync(kFullMask, hit);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int g = __shfl_sync(kFullMask, g_l, src);
+            const float4 t = s_truth[g];
+            // box_utils.py:42-47,62-68 (truth = box_a, anchor = box_b)
+            float w = fmaxf(fminf(t.z, box.z) - fmaxf(t.x, box.x), 0.0f);
+            float h = fmaxf(fminf(t.w, box.w) - fmaxf(t.y, box.y), 0.0f);
+            float inter = w * h;
+            float area_t = (t.z - t.x) * (t.w - t.y);
+            float iou = inter / (area_t + area_b - inter);
+            if (!valid) iou = -1.0f;
+            if (iou > best) { best = iou; best_g = g; }        // first maximal index; (0, g = 0) when nothing overlaps
+            // per-truth best prior: only overlapping anchors (or the row's first warp, which supplies prior 0
+            // for a truth that overlaps nothing) can win; one 64-bit global max per (warp, truth)
+            const bool contend = valid && (iou > 0.0f || iou != iou);
+            if (__any_sync(kFullMask, contend) || first_warp_of_row) {
+                uint32_t ord = valid ? float_to_ordered(iou) : 0u;
+                uint32_t mx = __reduce_max_sync(kFullMask, ord);
+                unsigned who = __ballot_sync(kFullMask, valid && ord == mx);
+                if (lane == __ffs(who) - 1) atomicMax(bp_row + g, prior_key(iou, (uint32_t)p));
+            }
         }
     }
     if (valid) {
         bt_overlap[(size_t)b * P + p] = best;
         bt_idx[(size_t)b * P + p] = best_g;
-    }
-    __syncthreads();
-    for (int g = threadIdx.x; g < G; g += kMatchThreads) {
-        unsigned long long k = s_best[g];
-        if (k) atomicMax(best_prior + (size_t)b * Gmax + g, k);
     }
 }
 
@@ -187,7 +208,11 @@ match_pass2_kernel(const float4* __restrict__ truths, const float* __restrict__ 
 // hard-negative mining: neg = the num_neg largest loss_c of the row (positives count as 0)
 // ---------------------------------------------------------------------------------------
 constexpr int kHnmThreads = 1024;
+constexpr int kHnmPerT = 16;            // register-resident rows: P <= 16 * 1024 anchors (RefineDet512: 16,320)
 
+// kRegs: every thread keeps its kHnmPerT (ordered) losses in registers, so the row is read from memory once
+// and the select passes touch shared memory only; otherwise every pass re-reads the row (L2).
+template <bool kRegs>
 __global__ void __launch_bounds__(kHnmThreads)
 hnm_select_kernel(const float* __restrict__ loss_c, const unsigned char* __restrict__ pos, int P, int ratio,
                   unsigned char* __restrict__ neg_out, int* __restrict__ num_pos_out) {
@@ -200,8 +225,19 @@ hnm_select_kernel(const float* __restrict__ loss_c, const unsigned char* __restr
     unsigned char* nrow = neg_out + (size_t)b * P;
     if (tid == 0) s_misc[3] = 0;
     __syncthreads();
+    uint32_t ord[kRegs ? kHnmPerT : 1];
     int local = 0;
-    for (int i = tid; i < P; i += kHnmThreads) local += prow[i] ? 1 : 0;
+    if (kRegs) {
+#pragma unroll
+        for (int j = 0; j < kHnmPerT; ++j) {
+            const int i = j * kHnmThreads + tid;
+            const bool p = i < P && prow[i] != 0;
+            local += p ? 1 : 0;
+            ord[j] = float_to_ordered((i < P && !p) ? row[i] : 0.0f);      // loss_c[pos] = 0, :117
+        }
+    } else {
+        for (int i = tid; i < P; i += kHnmThreads) local += prow[i] ? 1 : 0;
+    }
     local = __reduce_add_sync(kFullMask, local);
     if (lane == 0 && local) atomicAdd(&s_misc[3], (uint32_t)local);
     __syncthreads();
@@ -214,14 +250,24 @@ hnm_select_kernel(const float* __restrict__ loss_c, const unsigned char* __restr
         for (int i = tid; i < P; i += kHnmThreads) nrow[i] = 0;
         return;
     }
+    auto key_of = [&](int j, int i) -> unsigned long long {
+        if (kRegs) return ((unsigned long long)ord[j] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+        return make_key(prow[i] ? 0.0f : row[i], (uint32_t)i);
+    };
+    const int nper = kRegs ? kHnmPerT : (P + kHnmThreads - 1) / kHnmThreads;
     unsigned long long prefix = 0, thresh_key = 0;
     for (int shift = 56; shift >= 0; shift -= 8) {
         for (int i = tid; i < 256; i += kHnmThreads) hist[i] = 0;
         __syncthreads();
-        for (int i = tid; i < P; i += kHnmThreads) {
-            float v = prow[i] ? 0.0f : row[i];             // loss_c[pos] = 0, :117
-            unsigned long long k = make_key(v, (uint32_t)i);
-            if (shift == 56 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+#pragma unroll
+        for (int j = 0; j < (kRegs ? kHnmPerT : 1); ++j) {
+            for (int jj = kRegs ? j : 0; jj < (kRegs ? j + 1 : nper); ++jj) {
+                const int i = jj * kHnmThreads + tid;
+                if (i < P) {
+                    const unsigned long long k = key_of(kRegs ? j : 0, i);
+                    if (shift == 56 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+                }
+            }
         }
         __syncthreads();
         if (warp == 0) {
@@ -258,9 +304,12 @@ hnm_select_kernel(const float* __restrict__ loss_c, const unsigned char* __restr
         __syncthreads();
         if (done || shift == 0) { thresh_key = prefix << shift; break; }
     }
-    for (int i = tid; i < P; i += kHnmThreads) {
-        float v = prow[i] ? 0.0f : row[i];
-        nrow[i] = make_key(v, (uint32_t)i) >= thresh_key ? 1 : 0;
+#pragma unroll
+    for (int j = 0; j < (kRegs ? kHnmPerT : 1); ++j) {
+        for (int jj = kRegs ? j : 0; jj < (kRegs ? j + 1 : nper); ++jj) {
+            const int i = jj * kHnmThreads + tid;
+            if (i < P) nrow[i] = key_of(kRegs ? j : 0, i) >= thresh_key ? 1 : 0;
+        }
     }
 }
 
@@ -380,7 +429,7 @@ int rd_refine_match(const float* truths, const float* labels, const int* gt_coun
     dim3 grid((P + kMatchThreads - 1) / kMatchThreads, B);
     float* tmp_ov = best_truth_overlap;
     int* tmp_idx = best_truth_idx;
-    match_pass1_kernel<<<grid, kMatchThreads, (size_t)Gmax * 26, st>>>(
+    match_pass1_kernel<<<grid, kMatchThreads, (size_t)Gmax * 18, st>>>(
         (const float4*)truths, gt_count, (const float4*)priors, (const float4*)arm_loc, P, Gmax, v0, v1, best_prior,
         tmp_ov, tmp_idx);
     note_launch();
@@ -396,7 +445,10 @@ int rd_refine_match(const float* truths, const float* labels, const int* gt_coun
 int rd_hnm_select(const float* loss_c, const unsigned char* pos, int B, int P, int negpos_ratio,
                   unsigned char* neg_out, int* num_pos_out, void* stream) {
     if (!loss_c || !pos || !neg_out || B <= 0 || P <= 0 || negpos_ratio < 0) return RD_ERR_BAD_ARG;
-    hnm_select_kernel<<<B, kHnmThreads, 0, (cudaStream_t)stream>>>(loss_c, pos, P, negpos_ratio, neg_out, num_pos_out);
+    if (P <= kHnmPerT * kHnmThreads)
+        hnm_select_kernel<true><<<B, kHnmThreads, 0, (cudaStream_t)stream>>>(loss_c, pos, P, negpos_ratio, neg_out, num_pos_out);
+    else
+        hnm_select_kernel<false><<<B, kHnmThreads, 0, (cudaStream_t)stream>>>(loss_c, pos, P, negpos_ratio, neg_out, num_pos_out);
     note_launch();
     RD_CHECK_LAUNCH();
     return 0;
