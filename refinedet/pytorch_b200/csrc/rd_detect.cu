@@ -45,7 +45,8 @@ constexpr int kLargeThreads = RD_LARGE_THREADS;
 // starts: rd_detect_workspace_reset zeroes it once, every call leaves it zero again (collect clears
 // the queue header, nms_small_kernel's class-0 CTAs clear gtab of their image).
 //   header u32 [64]               : [0] = number of queued large problems
-//   gtab   u32 [B][4][32][33]     : start/end bin marks of the first 1024 nodes (OR-ed in by collect)
+//   gtab   u32 [B][4][4][32][33]  : start/end bin marks of the first 4096 nodes, one table per block of 1024
+//                                   nodes (OR-ed in by collect)
 //   nnodes int [B]                : nodes (= ARM-passing anchors) of every image (written by collect)
 //   flag   int [B]                : 1 = the image has no suppression graph (too many nodes / degree overflow)
 //   queue  int [B*C]              : (image,class) problems routed to nms_large_kernel
@@ -56,9 +57,11 @@ constexpr int kLargeThreads = RD_LARGE_THREADS;
 //   adj    u16 [B][1024][8]       : adjacency lists (node indices)
 //   cand   u64 [B*C][P]           : candidate keys of the problems nms_large_kernel handles
 // ---------------------------------------------------------------------------------------
-constexpr int kGraphW = kGraphNodes / 32;
-constexpr int kGraphWS = kGraphW + 1;
-constexpr int kGtabWords = 4 * kCols * kGraphWS;
+constexpr int kBlockNodes = 1024;       // suppressor nodes graph_kernel holds in shared memory at a time
+constexpr int kBlockW = kBlockNodes / 32;
+constexpr int kBlockWS = kBlockW + 1;   // padded row stride of the prefix-OR tables
+constexpr int kBlockTab = 4 * kCols * kBlockWS;                       // words of one block's mark table
+constexpr int kGtabWords = (kGraphNodes / kBlockNodes) * kBlockTab;   // block-major: the first block stays compact
 
 struct DetectWs {
     uint32_t* header;
@@ -409,32 +412,34 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
             GO.adjn[(size_t)b * kGraphNodes + i] = 0;            // degree counter of the suppression graph
             const int ax = cr & 255u, bxx = (cr >> 8) & 255u, ay = (cr >> 16) & 255u, by = cr >> 24;
             const uint32_t bit = 1u << (i & 31);
-            const int w = i >> 5;
-            uint32_t* tab = GO.gtab + (size_t)b * kGtabWords;
-            atomicOr(&tab[(0 * kCols + ax) * kGraphWS + w], bit);
-            if (bxx + 1 < kCols) atomicOr(&tab[(1 * kCols + bxx + 1) * kGraphWS + w], bit);
-            atomicOr(&tab[(2 * kCols + ay) * kGraphWS + w], bit);
-            if (by + 1 < kCols) atomicOr(&tab[(3 * kCols + by + 1) * kGraphWS + w], bit);
+            const int w = (i >> 5) & (kBlockW - 1);
+            uint32_t* tab = GO.gtab + (size_t)b * kGtabWords + (i / kBlockNodes) * kBlockTab;
+            atomicOr(&tab[(0 * kCols + ax) * kBlockWS + w], bit);
+            if (bxx + 1 < kCols) atomicOr(&tab[(1 * kCols + bxx + 1) * kBlockWS + w], bit);
+            atomicOr(&tab[(2 * kCols + ay) * kBlockWS + w], bit);
+            if (by + 1 < kCols) atomicOr(&tab[(3 * kCols + by + 1) * kBlockWS + w], bit);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// KG: suppression graph of one image.  grid = (kGraphSplit, B).  Every CTA loads the image's node
-// array and mark table (one round of coalesced L2 loads), finishes the prefix-OR, owns every
-// kGraphSplit-th node, lists the pairs (i < j) that survive the bin cull and tests them exactly.
+// KG: suppression graph of one image.  grid = (kGraphSplit, B).  The nodes are processed in blocks of
+// kBlockNodes potential suppressors: every CTA loads the block's boxes and the block's columns of the
+// mark table (one round of coalesced L2 loads), finishes the prefix-OR (S[c] = starts <= c, E[c] =
+// ends < c), and — for the nodes it owns (every kGraphSplit-th) that come AFTER a node of the block —
+// lists the pairs (i < j) that survive the bin cull and tests them exactly.
 //   adj[node j] = { node u : suppresses(kept = u, candidate = j) }    (exact fp32 test, boxes scaled)
-// Images with more than kGraphNodes nodes, or a node of degree > kAdjDeg, are flagged and
-// handled by the per-problem bin path instead.
+// One block (<= 1024 nodes) is the common case; images with more than kGraphNodes nodes, a node of
+// degree > kAdjDeg are flagged and handled by the per-problem bin path instead.
 // ---------------------------------------------------------------------------------------
 constexpr int kGraphThreads = 256;
 constexpr int kGraphSplit = 16;         // CTAs per image
 constexpr int kGraphPairCap = 2048;
 
 struct GraphSmem {
-    float x1[kGraphNodes], y1[kGraphNodes], x2[kGraphNodes], y2[kGraphNodes];
-    uint32_t cr[kGraphNodes];
-    uint32_t tab[kGtabWords];
+    float x1[kBlockNodes], y1[kBlockNodes], x2[kBlockNodes], y2[kBlockNodes];
+    uint32_t cr[kBlockNodes];
+    uint32_t tab[4 * kCols * kBlockWS];
     uint32_t pairs[kGraphPairCap];
     int overflow;
     int npairs;
@@ -447,17 +452,125 @@ __device__ __forceinline__ void graph_add_edge(int* __restrict__ adjn, unsigned 
     else *overflow = 1;
 }
 
-// exact tests of one unordered pair (i < j), both directions
-__device__ __forceinline__ void graph_test_pair(const GraphSmem& G, int i, int j, float thr, int flags,
-                                                int* __restrict__ adjn, unsigned short* __restrict__ adj,
-                                                int* overflow) {
-    const bool i_sup_j = suppresses(G.x1[i], G.y1[i], G.x2[i], G.y2[i], G.x1[j], G.y1[j], G.x2[j], G.y2[j], thr, flags);
+// exact test of the unordered pair (block node i, own node n0 + jl), both directions
+__device__ __forceinline__ void graph_test_pair_inline(GraphSmem& G, int i, int jl, int nb, const float4* __restrict__ boxes_n0,
+                                                       float thr, int flags, int* __restrict__ adjn,
+                                                       unsigned short* __restrict__ adj, int n0) {
+    float4 bj;
+    if (jl < nb) bj = make_float4(G.x1[jl], G.y1[jl], G.x2[jl], G.y2[jl]);
+    else bj = __ldg(boxes_n0 + jl);
+    const bool i_sup_j = suppresses(G.x1[i], G.y1[i], G.x2[i], G.y2[i], bj.x, bj.y, bj.z, bj.w, thr, flags);
     // the pixel(+1) IoU is symmetric in fp32 (ai + aj commutes); the normalised one is not ((aj - inter) + ai)
     const bool j_sup_i = (flags & RD_NMS_PIXEL_PLUS1)
                              ? i_sup_j
-                             : suppresses(G.x1[j], G.y1[j], G.x2[j], G.y2[j], G.x1[i], G.y1[i], G.x2[i], G.y2[i], thr, flags);
-    if (i_sup_j) graph_add_edge(adjn, adj, j, i, overflow);
-    if (j_sup_i) graph_add_edge(adjn, adj, i, j, overflow);
+                             : suppresses(bj.x, bj.y, bj.z, bj.w, G.x1[i], G.y1[i], G.x2[i], G.y2[i], thr, flags);
+    if (i_sup_j) graph_add_edge(adjn, adj, n0 + jl, n0 + i, &G.overflow);
+    if (j_sup_i) graph_add_edge(adjn, adj, n0 + i, n0 + jl, &G.overflow);
+}
+// out-of-line twin for the (rare) pairs found after the list has filled up: keeps the listing loop lean
+__device__ __noinline__ void graph_test_pair(GraphSmem& G, int i, int jl, int nb, const float4* __restrict__ boxes_n0,
+                                             float thr, int flags, int* __restrict__ adjn,
+                                             unsigned short* __restrict__ adj, int n0) {
+    graph_test_pair_inline(G, i, jl, nb, boxes_n0, thr, flags, adjn, adj, n0);
+}
+
+// the block loop of graph_kernel.  kSingle: the image has at most kBlockNodes nodes (the common case) — one
+// block, every own node inside it, nothing read from global memory after the staging.
+template <bool kSingle>
+__device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, int tid, const uint32_t* __restrict__ gtab,
+                                            const float4* __restrict__ nbox, const uint32_t* __restrict__ ncr, int P,
+                                            float thr, int flags, uint4* __restrict__ adj_all,
+                                            int* __restrict__ adjn_all) {
+    int* adjn = adjn_all + (size_t)b * kGraphNodes;
+    unsigned short* adj = reinterpret_cast<unsigned short*>(adj_all + (size_t)b * kGraphNodes);
+    const float4* boxes = nbox + (size_t)b * P;
+    const uint32_t* crs = ncr + (size_t)b * kGraphNodes;
+    const uint32_t* gt = gtab + (size_t)b * kGtabWords;
+    const uint32_t* Sx = G.tab;
+    const uint32_t* Ex = G.tab + 1 * kCols * kBlockWS;
+    const uint32_t* Sy = G.tab + 2 * kCols * kBlockWS;
+    const uint32_t* Ey = G.tab + 3 * kCols * kBlockWS;
+    static_assert(kGraphSplit == 16, "item enumeration assumes 2 own nodes per 32-node word");
+    if (tid == 0) G.overflow = 0;
+    for (int n0 = 0; n0 < (kSingle ? 1 : N); n0 += kBlockNodes) {
+        const int nb = kSingle ? N : min(kBlockNodes, N - n0);             // suppressor candidates i = n0 .. n0 + nb - 1
+        const int Wb = (nb + 31) >> 5;
+        if (n0 > 0) __syncthreads();                         // the previous block's tables are no longer read
+        // 1. the block's boxes + mark-table columns -> shared memory (independent loads, one round trip)
+        if (tid == 0) G.npairs = 0;
+        for (int i = tid; i < nb; i += kGraphThreads) {
+            const float4 bx = boxes[n0 + i];
+            G.x1[i] = bx.x; G.y1[i] = bx.y; G.x2[i] = bx.z; G.y2[i] = bx.w;
+            G.cr[i] = crs[n0 + i];
+        }
+        // 2. inclusive prefix-OR over the bins, straight from the global marks.  One (table, word) column per
+        //    thread, 32 independent loads each.
+        for (int task = tid; task < 4 * Wb; task += kGraphThreads) {
+            const int t = task / Wb, w = task - t * Wb;
+            uint32_t v[kCols];
+#pragma unroll
+            for (int c = 0; c < kCols; ++c) v[c] = __ldg(gt + (n0 / kBlockNodes) * kBlockTab + (t * kCols + c) * kBlockWS + w);
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < kCols; ++c) { acc |= v[c]; G.tab[(t * kCols + c) * kBlockWS + w] = acc; }
+        }
+        __syncthreads();
+        // 3. pairs (i in the block) < (own node j) that survive the bin cull.  Work item = (own node, mask word).
+        //    Own nodes inside the block, jo = 0 .. nin-1 (j = n0 + g + 16 jo), only need the words 0 .. jo >> 1:
+        //    the pair of own nodes (2m, 2m + 1) has m + 1 words each and m (m + 1) items precede it.  Own nodes
+        //    of later blocks, jo = nin .., need all Wb words.
+        const int nin = nb > g ? (nb - g + kGraphSplit - 1) / kGraphSplit : 0;
+        const int nall = (N - n0 - g + kGraphSplit - 1) / kGraphSplit;          // own nodes with j >= n0 (N - n0 > g here)
+        const int mfull = nin >> 1;
+        const int ntri = mfull * (mfull + 1) + ((nin & 1) ? mfull + 1 : 0);
+        const int nitems = ntri + ((!kSingle && N - n0 > g) ? (nall - nin) * Wb : 0);
+        for (int q0 = 0; q0 < nitems; q0 += kGraphThreads) {
+            const int q = q0 + tid;
+            uint32_t h = 0;
+            int jo = 0, w = 0;
+            if (q < nitems) {
+                uint32_t cr;
+                if (kSingle || q < ntri) {
+                    int m = (int)((sqrtf((float)(4 * q + 1)) - 1.0f) * 0.5f);
+                    while (m * (m + 1) > q) --m;
+                    while ((m + 1) * (m + 2) <= q) ++m;
+                    const int rem = q - m * (m + 1);
+                    const int second = rem > m ? 1 : 0;
+                    jo = 2 * m + second;
+                    w = rem - second * (m + 1);
+                    cr = G.cr[g + jo * kGraphSplit];
+                } else {
+                    const int r = q - ntri;
+                    jo = nin + r / Wb;
+                    w = r - (jo - nin) * Wb;
+                    cr = __ldg(crs + n0 + g + jo * kGraphSplit);
+                }
+                h = Sx[((cr >> 8) & 255u) * kBlockWS + w] & ~Ex[(cr & 255u) * kBlockWS + w] &
+                    Sy[((cr >> 24) & 255u) * kBlockWS + w] & ~Ey[((cr >> 16) & 255u) * kBlockWS + w];
+                const int jl = g + jo * kGraphSplit;                             // j - n0
+                if (w == (jl >> 5)) h &= (1u << (jl & 31)) - 1u;                 // predecessors only
+            }
+            // reserve list slots: one shared-memory atomic per item that has pairs (list order is irrelevant);
+            // pairs that do not fit the list any more are tested on the spot
+            int off = h ? atomicAdd(&G.npairs, __popc(h)) : 0;
+            const uint32_t tag = (uint32_t)jo << 16;
+            while (h) {
+                const int i = (w << 5) + __ffs(h) - 1;
+                h &= h - 1;
+                if (off < kGraphPairCap) G.pairs[off] = tag | (uint32_t)i;
+                else graph_test_pair(G, i, g + jo * kGraphSplit, kSingle ? kBlockNodes : nb, boxes + n0, thr, flags, adjn, adj, n0);
+                ++off;
+            }
+        }
+        __syncthreads();
+        // 4. exact tests of the listed pairs, both directions
+        const int cnt = min(G.npairs, kGraphPairCap);
+        for (int p = tid; p < cnt; p += kGraphThreads) {
+            const uint32_t e = G.pairs[p];
+            graph_test_pair_inline(G, (int)(e & 0xffffu), g + (int)(e >> 16) * kGraphSplit, kSingle ? kBlockNodes : nb,
+                                   boxes + n0, thr, flags, adjn, adj, n0);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kGraphThreads)
@@ -477,85 +590,9 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
     }
     // own nodes: j = g, g + kGraphSplit, ... (interleaved, so the few large boxes that overlap hundreds
     // of others, and the later nodes that have more predecessors, are spread over the CTAs of the image)
-    const int nown = N > g ? (N - g + kGraphSplit - 1) / kGraphSplit : 0;
-    if (nown == 0) return;
-    int* adjn = adjn_all + (size_t)b * kGraphNodes;
-    unsigned short* adj = reinterpret_cast<unsigned short*>(adj_all + (size_t)b * kGraphNodes);
-    const int Wn = (N + 31) >> 5;
-    // 1. node array + mark table -> shared memory (independent loads, one round trip)
-    if (tid == 0) { G.overflow = 0; G.npairs = 0; }
-    for (int i = tid; i < N; i += kGraphThreads) {
-        const float4 bx = nbox[(size_t)b * P + i];
-        G.x1[i] = bx.x; G.y1[i] = bx.y; G.x2[i] = bx.z; G.y2[i] = bx.w;
-        G.cr[i] = ncr[(size_t)b * kGraphNodes + i];
-    }
-    // 2. inclusive prefix-OR over the bins, straight from the global marks: S[c] = starts at <= c,
-    //    E[c] = ends before c.  One (table, word) column per thread, 32 independent loads each.
-    {
-        const uint32_t* gt = gtab + (size_t)b * kGtabWords;
-        for (int task = tid; task < 4 * Wn; task += kGraphThreads) {
-            const int t = task / Wn, w = task - t * Wn;
-            uint32_t v[kCols];
-#pragma unroll
-            for (int c = 0; c < kCols; ++c) v[c] = __ldg(gt + (t * kCols + c) * kGraphWS + w);
-            uint32_t acc = 0;
-#pragma unroll
-            for (int c = 0; c < kCols; ++c) { acc |= v[c]; G.tab[(t * kCols + c) * kGraphWS + w] = acc; }
-        }
-    }
-    __syncthreads();
-    // 3. pairs (i < j) of own nodes that survive the bin cull.  Work item = (own node, mask word):
-    //    every thread handles a few items, so nothing serialises on a box that overlaps hundreds of others.
-    const uint32_t* Sx = G.tab;
-    const uint32_t* Ex = G.tab + 1 * kCols * kGraphWS;
-    const uint32_t* Sy = G.tab + 2 * kCols * kGraphWS;
-    const uint32_t* Ey = G.tab + 3 * kCols * kGraphWS;
-    // Own node jl (j = g + 16 jl) only needs the words 0 .. j >> 5 = jl >> 1, so the items form a
-    // triangle: the pair of own nodes (2m, 2m + 1) has m + 1 words each and m (m + 1) items precede it.
-    static_assert(kGraphSplit == 16, "item enumeration assumes 2 own nodes per 32-node word");
-    const int mfull = nown >> 1;
-    const int nitems = mfull * (mfull + 1) + ((nown & 1) ? mfull + 1 : 0);
-    for (int q0 = 0; q0 < nitems; q0 += kGraphThreads) {
-        const int q = q0 + tid;
-        uint32_t h = 0;
-        int jl = 0, w = 0;
-        if (q < nitems) {
-            int m = (int)((sqrtf((float)(4 * q + 1)) - 1.0f) * 0.5f);
-            while (m * (m + 1) > q) --m;
-            while ((m + 1) * (m + 2) <= q) ++m;
-            const int rem = q - m * (m + 1);
-            const int second = rem > m ? 1 : 0;
-            jl = 2 * m + second;
-            w = rem - second * (m + 1);
-            const int j = g + jl * kGraphSplit;
-            const uint32_t cr = G.cr[j];
-            h = Sx[((cr >> 8) & 255u) * kGraphWS + w] & ~Ex[(cr & 255u) * kGraphWS + w] &
-                Sy[((cr >> 24) & 255u) * kGraphWS + w] & ~Ey[((cr >> 16) & 255u) * kGraphWS + w];
-            if (w == (j >> 5)) h &= (1u << (j & 31)) - 1u;        // predecessors only
-        }
-        // reserve list slots: one shared-memory atomic per item that has pairs (list order is irrelevant)
-        int off = h ? atomicAdd(&G.npairs, __popc(h)) : 0;
-        const uint32_t tag = (uint32_t)jl << 16;
-        while (h) {
-            const int i = (w << 5) + __ffs(h) - 1;
-            h &= h - 1;
-            if (off < kGraphPairCap) G.pairs[off] = tag | (uint32_t)i;
-            ++off;
-        }
-    }
-    __syncthreads();
-    if (G.npairs > kGraphPairCap) {          // rare: more pairs than the list holds -> leave the graph to the fallback
-        if (tid == 0) img_flag[b] = 1;
-        return;
-    }
-    {
-        const int cnt = min(G.npairs, kGraphPairCap);
-        for (int p = tid; p < cnt; p += kGraphThreads) {
-            const uint32_t e = G.pairs[p];
-            graph_test_pair(G, (int)(e & 0xffffu), g + (int)(e >> 16) * kGraphSplit, thr, flags, adjn, adj,
-                            &G.overflow);
-        }
-    }
+    if (N <= g) return;
+    if (N <= kBlockNodes) graph_image<true>(G, N, g, b, tid, gtab, nbox, ncr, P, thr, flags, adj_all, adjn_all);
+    else graph_image<false>(G, N, g, b, tid, gtab, nbox, ncr, P, thr, flags, adj_all, adjn_all);
     __syncthreads();
     if (tid == 0 && G.overflow) img_flag[b] = 1;
 }
@@ -598,7 +635,7 @@ template <int kCap, int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 nms_small_kernel(FusedNmsArgs A) {
     __shared__ SmallSmem<kCap> S;
-    constexpr int kPerT = (kGraphNodes + kThreads - 1) / kThreads;
+    constexpr int kPerT = (kBlockNodes + kThreads - 1) / kThreads;     // register-resident scan: N <= 1024
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x, b = blockIdx.y;
     const int bc = b * A.C + c;
@@ -607,20 +644,22 @@ nms_small_kernel(FusedNmsArgs A) {
         // graph control block of its image zero for the next call, once graph_kernel is done with it
         grid_dependency_wait();
         uint32_t* gt = A.gtab + (size_t)b * kGtabWords;
-        for (int i = tid; i < kGtabWords; i += kThreads) gt[i] = 0;
+        const int nblk = (min(A.nnodes[b], kGraphNodes) + kBlockNodes - 1) / kBlockNodes;   // tables collect_kernel marked
+        for (int i = tid; i < nblk * kBlockTab; i += kThreads) gt[i] = 0;
         if (tid == 0) A.out_counts[bc] = 0;
         return;
     }
     const int N = A.nnodes[b];
-    if (N > kGraphNodes) {                                        // the image has no graph: own bins, large kernel
-        if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
+    if (N > SmallSmem<kCap>::kMaxNodes) {    // more nodes than this variant's rank table covers (or no graph at all):
+        if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;      // nms_large_kernel resolves or bins it
         return;
     }
-    // candidates: nodes whose score exceeds the threshold.  Two passes over registers (count, then place)
-    // with one barrier in between: no atomics.
-    {
-        const float* row = A.nsc + (size_t)bc * A.Pn;
-        const int nq = (N + kThreads - 1) / kThreads;   // <= kPerT
+    // candidates: nodes whose score exceeds the threshold.  Two passes (count, then place) with one barrier
+    // in between: no atomics.  Up to 1024 nodes the scores stay in registers between the passes.
+    const float* row = A.nsc + (size_t)bc * A.Pn;
+    const int nq = (N + kThreads - 1) / kThreads;
+    const unsigned lt = (1u << lane) - 1u;
+    if (SmallSmem<kCap>::kMaxNodes <= kPerT * kThreads || nq <= kPerT) {      // always, for the common variant
         float v[kPerT];
         unsigned bal[kPerT];
 #pragma unroll
@@ -647,7 +686,6 @@ nms_small_kernel(FusedNmsArgs A) {
         }
         if (tid == 0) S.n = tot;
         if (tot <= kCap) {
-            const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
             for (int q = 0; q < kPerT; ++q) {
                 if (q < nq && bal[q]) {
@@ -655,6 +693,31 @@ nms_small_kernel(FusedNmsArgs A) {
                         S.u.runs[slot + __popc(bal[q] & lt)] = make_key(v[q], (uint32_t)(q * kThreads + tid));
                     slot += __popc(bal[q]);
                 }
+            }
+        }
+    } else {                                                  // 1024 < N <= kGraphNodes: the row is read twice (L2)
+        int cnt = 0;
+        for (int q = 0; q < nq; ++q) {
+            const int i = q * kThreads + tid;
+            const float v = i < N ? __ldg(row + i) : -INFINITY;
+            cnt += __popc(__ballot_sync(kFullMask, v > A.conf_thresh));
+        }
+        if (lane == 0) S.wsum[warp] = cnt;
+        __syncthreads();
+        int slot = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+            if (w < warp) slot += S.wsum[w];
+            tot += S.wsum[w];
+        }
+        if (tid == 0) S.n = tot;
+        if (tot <= kCap) {
+            for (int q = 0; q < nq; ++q) {
+                const int i = q * kThreads + tid;
+                const float v = i < N ? __ldg(row + i) : -INFINITY;
+                const unsigned bal = __ballot_sync(kFullMask, v > A.conf_thresh);
+                if ((bal >> lane) & 1u) S.u.runs[slot + __popc(bal & lt)] = make_key(v, (uint32_t)i);
+                slot += __popc(bal);
             }
         }
     }
@@ -684,22 +747,42 @@ nms_small_kernel(FusedNmsArgs A) {
     G.adjn = A.adjn + (size_t)b * kGraphNodes;
     G.nbox = A.nbox + (size_t)b * A.P;
     G.nanc = A.nanc + (size_t)b * A.P;
-    const int kept = cta_nms_graph<kThreads, kCap>(S, n, A.max_out, sink, G);
+    const int kept = cta_nms_graph<kThreads, kCap>(S, n, N, A.max_out, sink, G);
     if (tid == 0) A.out_counts[bc] = kept;
 }
 
-__global__ void __launch_bounds__(kLargeThreads)
+// A queued problem of an image that has a suppression graph and only outgrew nms_small_kernel's 256 candidates
+// (or its 1024-node rank table): the same sort + graph resolve, 1024 candidates wide, on the large kernel's
+// shared memory.  Out of line, so that the register allocation of the bin path (nms_process) is unaffected.
+__device__ __noinline__ int large_graph_resolve(unsigned char* smem, const unsigned long long* __restrict__ keys, int n,
+                                                int N, int max_out, const uint4* adj, const int* adjn,
+                                                const float4* nbox, const int* nanc, float* rows, int* anchors,
+                                                int row_layout) {
+    SmallSmem<kWideCap>& S = *reinterpret_cast<SmallSmem<kWideCap>*>(smem);
+    for (int i = threadIdx.x; i < n; i += kLargeThreads) S.u.runs[i] = keys[i];
+    __syncthreads();
+    cta_sort_small<kLargeThreads, kWideCap>(S, n);
+    GraphView G;
+    G.adj = adj; G.adjn = adjn; G.nbox = nbox; G.nanc = nanc;
+    RowSink sink;
+    sink.rows = rows; sink.anchors = anchors; sink.keep64 = nullptr; sink.keep32 = nullptr; sink.idx_map = nullptr;
+    sink.row_layout = row_layout;
+    return cta_nms_graph<kLargeThreads, kWideCap>(S, n, N, max_out, sink, G);
+}
+
+__global__ void __launch_bounds__(kLargeThreads, RD_LARGE_PER_SM)      // 3 x 512 threads: 40 registers
 nms_large_kernel(FusedNmsArgs A, int mcap) {
     extern __shared__ __align__(16) unsigned char smem[];
+    grid_dependency_wait();          // nms_small_kernel (and everything before it) has completed
+    const uint32_t nq = A.header[0];
+    if (nq == 0) return;             // the common case: nothing queued — leave before any set-up work
     const NmsSmemLayout L = nms_layout(mcap);
     int* s_cnt = reinterpret_cast<int*>(smem + L.off_misc) + 15;     // misc[15]: unused by nms_process
     const int tid = threadIdx.x, lane = tid & 31;
-    grid_dependency_wait();          // nms_small_kernel (and everything before it) has completed
-    const uint32_t nq = A.header[0];
     // dynamic tickets: problems differ a lot in cost (select passes, pairs), a static stride leaves CTAs idle
     for (;;) {
         __shared__ uint32_t s_ticket;
-        if (tid == 0) s_ticket = nq ? atomicAdd(&A.header[1], 1u) : 0xffffffffu;
+        if (tid == 0) s_ticket = atomicAdd(&A.header[1], 1u);
         __syncthreads();
         const uint32_t q = s_ticket;
         __syncthreads();
@@ -736,19 +819,30 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
         __syncthreads();
         const int n = s_cnt[0];
         __syncthreads();
-        NmsProblem pb;
-        pb.cl.base = keys; pb.cl.n = n;
-        pb.boxes = A.nbox + (size_t)b * A.P;
-        pb.has_scale = 0;                                         // node boxes are already scaled
-        pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
-        pb.thr = A.thr; pb.top_k = A.top_k; pb.max_out = A.max_out; pb.flags = A.flags;
         RowSink sink;
         sink.rows = A.out_dets + (size_t)bc * A.max_out * 5;
         sink.anchors = A.out_anchor ? A.out_anchor + (size_t)bc * A.max_out : nullptr;
         sink.keep64 = nullptr; sink.keep32 = nullptr;
         sink.idx_map = A.nanc + (size_t)b * A.P;
         sink.row_layout = A.row_layout;
-        const int kept = nms_process(smem, L, pb, sink);
+        int kept;
+#ifndef RD_NO_LARGE_GRAPH
+        if (N <= kGraphNodes && A.img_flag[b] == 0 && n <= kWideCap && n <= A.top_k &&
+            sizeof(SmallSmem<kWideCap>) <= L.total) {
+            kept = large_graph_resolve(smem, keys, n, N, A.max_out, A.adj + (size_t)b * kGraphNodes,
+                                       A.adjn + (size_t)b * kGraphNodes, A.nbox + (size_t)b * A.P, A.nanc + (size_t)b * A.P,
+                                       sink.rows, sink.anchors, sink.row_layout);
+        } else
+#endif
+        {
+            NmsProblem pb;
+            pb.cl.base = keys; pb.cl.n = n;
+            pb.boxes = A.nbox + (size_t)b * A.P;
+            pb.has_scale = 0;                                     // node boxes are already scaled
+            pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
+            pb.thr = A.thr; pb.top_k = A.top_k; pb.max_out = A.max_out; pb.flags = A.flags;
+            kept = nms_process(smem, L, pb, sink);
+        }
         if (tid == 0) A.out_counts[bc] = kept;
         __syncthreads();
     }

@@ -167,24 +167,29 @@ constexpr int kSmallCap = 256;
 constexpr int kWideThreads = 256;                 // wide variant (few problems, e.g. C = 2): <= 1024 candidates
 constexpr int kWideCap = 1024;
 
-constexpr int kGraphNodes = 1024;     // images with more ARM-passing anchors have no suppression graph
+#ifndef RD_GRAPH_NODES
+#define RD_GRAPH_NODES 4096
+#endif
+constexpr int kGraphNodes = RD_GRAPH_NODES;   // images with more ARM-passing anchors have no suppression graph
 constexpr int kAdjDeg = 8;            // adjacency slots per node; an image whose graph overflows is flagged dense
 
-template <int kCap>
+// kNodes = largest node index + 1 the rank table covers (images with more nodes are not handled by this instance)
+template <int kCap, int kNodes = (kCap > 256 ? RD_GRAPH_NODES : 1024)>
 struct SmallSmem {
     using rank_t = typename std::conditional<(kCap > 256), unsigned short, unsigned char>::type;
     unsigned long long keys[kCap];                // sorted keys
     union {
         unsigned long long runs[kCap];            // unsorted candidates, then sorted runs of 32 (during the sort)
         struct {
-            unsigned short rank[kGraphNodes];     // node -> rank in this problem, 0xffff = not a candidate
+            unsigned short rank[kNodes];          // node -> rank in this problem, 0xffff = not a candidate
             rank_t deps[kCap * kAdjDeg];          // ranks of the dependencies of every candidate
         } g;
     } u;
     unsigned char depn[kCap];
     unsigned char state[kCap];                    // 0 undecided, 1 kept, 2 suppressed
-    int wsum[8];
+    int wsum[32];
     int n;
+    static constexpr int kMaxNodes = kNodes;
 };
 
 // Sort of a small problem: S.u.runs[0..m) holds the candidate keys in any order.  Sorted runs of 32 in
@@ -244,10 +249,11 @@ struct GraphView {
     const int* nanc;                  // [N] anchor index of every node
 };
 
-// S.keys[0..m) = the problem's sorted keys (key index = node).  One round of global loads: adjacency row,
+// S.keys[0..m) = the problem's sorted keys (key index = node < N).  One round of global loads: adjacency row,
 // box and anchor of every candidate.
 template <int kThreads, int kCap>
-__device__ inline int cta_nms_graph(SmallSmem<kCap>& S, int m, int max_out, const RowSink& sink, const GraphView& G) {
+__device__ inline int cta_nms_graph(SmallSmem<kCap>& S, int m, int N, int max_out, const RowSink& sink,
+                                    const GraphView& G) {
     using rank_t = typename SmallSmem<kCap>::rank_t;
     constexpr int kSmallWarps = kThreads / 32;
     constexpr int kPerT = (kCap + kThreads - 1) / kThreads;
@@ -275,7 +281,9 @@ __device__ inline int cta_nms_graph(SmallSmem<kCap>& S, int m, int max_out, cons
     // rank table (aliases the sort buffer: every thread is past the merge, see the barrier in cta_sort_small)
     {
         uint4* t = reinterpret_cast<uint4*>(S.u.g.rank);
-        for (int i = tid; i < kGraphNodes * 2 / 16; i += kThreads) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        constexpr int kMaxNodes = SmallSmem<kCap>::kMaxNodes;
+        const int nn = kMaxNodes <= 1024 ? kMaxNodes : N;         // small table: constant bound (one store per thread)
+        for (int i = tid; i < (nn * 2 + 15) / 16; i += kThreads) t[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
     }
     __syncthreads();
 #pragma unroll

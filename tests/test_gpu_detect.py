@@ -155,11 +155,14 @@ def _oracle_a4(boxes, scores, scale, conf_thr, top_k, nms_thr, keep_top_k):
     ('sparse-8', 2, '512', 2, 1000, 500),    # few classes: the wide (<= 1024 candidates, 256 threads) graph variant, n > 256
     ('sparse-8', 3, '512', 3, 1000, 120),    # ... with the keep_top_k cap biting
     ('sparse-8', 2, '512', 81, 1000, 500),   # the benchmark regime: ~700 nodes per image, common variant
+    ('sparse-7', 2, '512', 81, 1000, 500),   # ~1900 nodes: two-block graph, > 256 candidates -> graph resolve in nms_large
+    ('sparse-7', 2, '512', 3, 1000, 500),    # ... wide variant overflows 1024 candidates -> per-problem bins
+    ('sparse-5', 2, '320', 21, 1000, 500),   # ~2700 nodes of 6375: three-block graph
 ])
 def test_fused_detect_vs_oracle(rd, kind, B, size, C, top_k, keep):
     priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward()
     P = priors.shape[0]
-    arm_shift = {'sparse': -3.0, 'sparse-8': -8.0, 'dense': 0.0}[kind]
+    arm_shift = {'sparse': -3.0, 'sparse-8': -8.0, 'sparse-7': -7.0, 'sparse-5': -5.0, 'dense': 0.0}[kind]
     kind = kind.split('-')[0]
     conf_thr, nms_thr, obj_thr = 0.01, 0.45, 0.01
     # fp32 softmax scores collide often at these candidate counts, so tie-free inputs are not
