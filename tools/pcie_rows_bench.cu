@@ -1,0 +1,68 @@
+// tools/pcie_rows_bench.cu — microbenchmark behind the line-granular PCIe fetch of collect_kernel: SM reads of scattered
+// 324-byte rows from pinned host memory with (A) 4-byte lane = class loads, (B) 4-byte loads over whole 128-byte lines,
+// (C) one 16-byte load per lane over whole lines, against a DMA of the same bytes.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -include algorithm -o pcie_rows_bench tools/pcie_rows_bench.cu
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("err %s line %d\n",cudaGetErrorString(e),__LINE__);exit(1);} }while(0)
+constexpr int C=81;
+__device__ __forceinline__ float ldnc(const float* p){float r; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];":"=f"(r):"l"(p)); return r;}
+// A: lane = class, 3 loads per row, 4 rows in flight per warp
+__global__ void kA(const float* host, const int* rows, int nrows, float* out){
+  int warp=(blockIdx.x*blockDim.x+threadIdx.x)>>5, lane=threadIdx.x&31, nw=(gridDim.x*blockDim.x)>>5; float acc=0;
+  for(int r0=warp*4;r0<nrows;r0+=nw*4){ float v[4][3];
+    #pragma unroll
+    for(int k=0;k<4;++k){ int r=r0+k<nrows?rows[r0+k]:rows[0]; const float* p=host+(size_t)r*C;
+      #pragma unroll
+      for(int s=0;s<3;++s){int c=s*32+lane; v[k][s]= c<C? ldnc(p+c):0.f;} }
+    #pragma unroll
+    for(int k=0;k<4;++k) acc+=v[k][0]+v[k][1]+v[k][2]; }
+  if(acc==123.456f) out[0]=acc;
+}
+// B: whole aligned 128-byte lines covering the row (4 lines), 4 rows in flight
+__global__ void kB(const float* host, const int* rows, int nrows, float* out){
+  int warp=(blockIdx.x*blockDim.x+threadIdx.x)>>5, lane=threadIdx.x&31, nw=(gridDim.x*blockDim.x)>>5; float acc=0;
+  for(int r0=warp*4;r0<nrows;r0+=nw*4){ float v[4][4];
+    #pragma unroll
+    for(int k=0;k<4;++k){ int r=r0+k<nrows?rows[r0+k]:rows[0]; size_t f=(size_t)r*C; size_t l0=f&~(size_t)31; int nl=(int)((f+C-1-l0)/32)+1;
+      #pragma unroll
+      for(int s=0;s<4;++s) v[k][s]= s<nl? ldnc(host+l0+s*32+lane):0.f; }
+    #pragma unroll
+    for(int k=0;k<4;++k) acc+=v[k][0]+v[k][1]+v[k][2]+v[k][3]; }
+  if(acc==123.456f) out[0]=acc;
+}
+// C: like B but 16-byte loads per lane: 8 lanes cover a 128-byte line, one instruction covers 4 lines = 512 B
+__global__ void kC(const float* host, const int* rows, int nrows, float* out){
+  int warp=(blockIdx.x*blockDim.x+threadIdx.x)>>5, lane=threadIdx.x&31, nw=(gridDim.x*blockDim.x)>>5; float acc=0;
+  for(int r0=warp*8;r0<nrows;r0+=nw*8){ float4 v[8];
+    #pragma unroll
+    for(int k=0;k<8;++k){ int r=r0+k<nrows?rows[r0+k]:rows[0]; size_t f=(size_t)r*C; size_t l0=f&~(size_t)31; int nl=(int)((f+C-1-l0)/32)+1;
+      v[k]= (lane>>3)<nl ? __ldg(reinterpret_cast<const float4*>(host+l0)+lane): make_float4(0,0,0,0); }
+    #pragma unroll
+    for(int k=0;k<8;++k) acc+=v[k].x+v[k].y+v[k].z+v[k].w; }
+  if(acc==123.456f) out[0]=acc;
+}
+int main(){
+  const size_t total=(size_t)32*16320; float* h; CK(cudaHostAlloc(&h,total*C*4,cudaHostAllocDefault));
+  for(size_t i=0;i<total*C;i+=1024) h[i]=1.f;
+  int nrows=22560*4; std::vector<int> rows(nrows); srand(1); for(int i=0;i<nrows;++i) rows[i]=(int)(((size_t)rand()*7919+i*23)%total);
+  // sorted-ish like real passing anchors: ascending order
+  std::sort(rows.begin(),rows.end());
+  int* drows; CK(cudaMalloc(&drows,nrows*4)); CK(cudaMemcpy(drows,rows.data(),nrows*4,cudaMemcpyHostToDevice));
+  float* out; CK(cudaMalloc(&out,4)); float* dev; CK(cudaMalloc(&dev, 64<<20));
+  cudaEvent_t a,b; cudaEventCreate(&a); cudaEventCreate(&b);
+  for(int grid: {148,296,592,1184}) for(int rep=0;rep<2;++rep){
+    float ms;
+    cudaEventRecord(a); kA<<<grid,256>>>(h,drows,nrows,out); cudaEventRecord(b); CK(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms,a,b);
+    printf("grid %4d A lane=class   : %.3f ms  %.1f GB/s useful\n",grid,ms,nrows*324.0/ms/1e6);
+    cudaEventRecord(a); kB<<<grid,256>>>(h,drows,nrows,out); cudaEventRecord(b); CK(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms,a,b);
+    printf("grid %4d B full lines   : %.3f ms  %.1f GB/s useful\n",grid,ms,nrows*324.0/ms/1e6);
+    cudaEventRecord(a); kC<<<grid,256>>>(h,drows,nrows,out); cudaEventRecord(b); CK(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms,a,b);
+    printf("grid %4d C float4 lines : %.3f ms  %.1f GB/s useful\n",grid,ms,nrows*324.0/ms/1e6);
+  }
+  // DMA reference
+  for(int rep=0;rep<2;++rep){ float ms; cudaEventRecord(a); cudaMemcpyAsync(dev,h,(size_t)nrows*324,cudaMemcpyHostToDevice); cudaEventRecord(b); CK(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms,a,b); printf("DMA same bytes contiguous: %.3f ms %.1f GB/s\n",ms,nrows*324.0/ms/1e6);}
+  return 0;
+}
