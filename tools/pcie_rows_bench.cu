@@ -44,6 +44,18 @@ __global__ void kC(const float* host, const int* rows, int nrows, float* out){
     for(int k=0;k<8;++k) acc+=v[k].x+v[k].y+v[k].z+v[k].w; }
   if(acc==123.456f) out[0]=acc;
 }
+// D: one 16-byte item (a loc vector) per thread, scattered
+__global__ void kD(const float4* host, const int* rows, int nrows, float* out){
+  int t=blockIdx.x*blockDim.x+threadIdx.x, nt=gridDim.x*blockDim.x; float acc=0;
+  for(int r=t;r<nrows;r+=nt){ float4 v=__ldg(host+rows[r]); acc+=v.x+v.y+v.z+v.w; }
+  if(acc==123.456f) out[0]=acc;
+}
+// E: the whole 128-byte line around the item, 8 lanes x 16 bytes per item (4 items per warp instruction)
+__global__ void kE(const float4* host, const int* rows, int nrows, float* out){
+  int t=blockIdx.x*blockDim.x+threadIdx.x, nt=gridDim.x*blockDim.x; float acc=0; int sub=threadIdx.x&7;
+  for(int r=t>>3;r<nrows;r+=nt>>3){ size_t i=(size_t)rows[r]; float4 v=__ldg(host+(i&~(size_t)7)+sub); acc+=v.x+v.y+v.z+v.w; }
+  if(acc==123.456f) out[0]=acc;
+}
 int main(){
   const size_t total=(size_t)32*16320; float* h; CK(cudaHostAlloc(&h,total*C*4,cudaHostAllocDefault));
   for(size_t i=0;i<total*C;i+=1024) h[i]=1.f;
@@ -61,6 +73,13 @@ int main(){
     printf("grid %4d B full lines   : %.3f ms  %.1f GB/s useful\n",grid,ms,nrows*324.0/ms/1e6);
     cudaEventRecord(a); kC<<<grid,256>>>(h,drows,nrows,out); cudaEventRecord(b); CK(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms,a,b);
     printf("grid %4d C float4 lines : %.3f ms  %.1f GB/s useful\n",grid,ms,nrows*324.0/ms/1e6);
+  }
+  { // loc vectors: items of 16 bytes among total anchors
+    for(int rep=0;rep<3;++rep){ float ms;
+      cudaEventRecord(a); kD<<<592,256>>>((const float4*)h,drows,nrows,out); cudaEventRecord(b); CK(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms,a,b);
+      printf("D 16-byte items        : %.3f ms  %.1f M items/s\n",ms,nrows/ms/1e3);
+      cudaEventRecord(a); kE<<<592,256>>>((const float4*)h,drows,nrows,out); cudaEventRecord(b); CK(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms,a,b);
+      printf("E 128-byte lines/item  : %.3f ms  %.1f M items/s\n",ms,nrows/ms/1e3); }
   }
   // DMA reference
   for(int rep=0;rep<2;++rep){ float ms; cudaEventRecord(a); cudaMemcpyAsync(dev,h,(size_t)nrows*324,cudaMemcpyHostToDevice); cudaEventRecord(b); CK(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms,a,b); printf("DMA same bytes contiguous: %.3f ms %.1f GB/s\n",ms,nrows*324.0/ms/1e6);}
