@@ -5,19 +5,22 @@
 //
 // Kernels
 //   detect_forward_kernel   a3: ARM filter + two-stage decode, dense boxes/scores, in-place zeroing
-//   collect_kernel          K1: one CTA per (image, slice of 1024 anchors).  ARM filter; the ARM-passing
-//                           anchors of an image become its NODES, numbered in anchor order.  Per node:
-//                           decoded + scaled box, anchor, bin range and bin marks (graph input), and its
-//                           odm_conf row transposed through shared memory into the class-major score
-//                           matrix nsc[image][class][node].  odm_conf / loc rows of ARM-filtered anchors
-//                           are never fetched: traffic scales with the pass rate.  No atomics.
+//   collect_kernel          K1: one CTA per (image, slice of 1024 anchors).  ARM filter (probabilities, or
+//                           logits with the model's softmax folded in); the ARM-passing anchors of an
+//                           image become its NODES, numbered in anchor order.  Per node: decoded + scaled
+//                           box, anchor, bin range and bin marks (graph input), and its odm_conf row
+//                           transposed through shared memory into the class-major score matrix
+//                           nsc[image][class][node].  odm_conf / loc rows of ARM-filtered anchors are never
+//                           fetched: traffic scales with the pass rate.  No atomics on the data path.
+//                           Host-mapped odm_conf (zero-copy over PCIe) is fetched as whole 128-byte lines.
 //   graph_kernel            KG: 16 CTAs per image: exact suppression graph between the nodes of an image
-//                           (class independent), adjacency lists per node
+//                           (class independent, up to 4096 nodes in blocks of 1024), adjacency lists per node
 //   nms_small_kernel        K2: one CTA per (image, class): scan the class's score row, sort the candidates
 //                           (beside graph_kernel: programmatic dependent launch), then resolve the
-//                           suppression through the graph and emit rows
-//   nms_large_kernel        persistent CTAs draining the queue of problems without a graph or with more
-//                           than 256 candidates (radix select when n > top_k, own bin tables)
+//                           suppression through the graph and emit rows.  <256 candidates, 128 threads> or,
+//                           when there are few problems, <1024, 256>
+//   nms_large_kernel        persistent CTAs drawing queued problems: graph resolve up to 1024 candidates for
+//                           what K2 could not hold, else radix select when n > top_k + own bin tables
 //   nms_single_kernel       stand-alone problem (rd_nms / rd_nms_host)
 //   pack kernels            slot layout -> packed rows
 #include "rd_nms_core.cuh"
@@ -37,14 +40,14 @@ constexpr int kSliceAnchors = 1024;   // anchors per collect CTA
 #endif
 constexpr int kLargeThreads = RD_LARGE_THREADS;
 #ifndef RD_LARGE_PER_SM
-#define RD_LARGE_PER_SM 3          // resident large-problem CTAs per SM (dense stress case: 3 and 4 measure the same with ticketed problems, 2 is slower)
+#define RD_LARGE_PER_SM 3          // resident large-problem CTAs per SM (also the kernel's register cap: 40)
 #endif
 
 // ---------------------------------------------------------------------------------------
 // workspace of the fused stage.  The control block (header, gtab) must be zero when a call
 // starts: rd_detect_workspace_reset zeroes it once, every call leaves it zero again (collect clears
 // the queue header, nms_small_kernel's class-0 CTAs clear gtab of their image).
-//   header u32 [64]               : [0] = number of queued large problems
+//   header u32 [64]               : [0] = number of queued large problems, [1] = next ticket
 //   gtab   u32 [B][4][4][32][33]  : start/end bin marks of the first 4096 nodes, one table per block of 1024
 //                                   nodes (OR-ed in by collect)
 //   nnodes int [B]                : nodes (= ARM-passing anchors) of every image (written by collect)
@@ -52,9 +55,9 @@ constexpr int kLargeThreads = RD_LARGE_THREADS;
 //   queue  int [B*C]              : (image,class) problems routed to nms_large_kernel
 //   nsc    f32 [B][C][Pn]         : class-major scores of the nodes, Pn = P rounded up to 32
 //   nbox   f4  [B][P], nanc int [B][P] : node box (scaled) / anchor
-//   ncr    u32 [B][1024]          : bin range of the first 1024 nodes
-//   adjn   int [B][1024]          : graph degree of every node (collect zeroes, graph counts)
-//   adj    u16 [B][1024][8]       : adjacency lists (node indices)
+//   ncr    u32 [B][4096]          : bin range of the first 4096 nodes
+//   adjn   int [B][4096]          : graph degree of every node (collect zeroes, graph counts)
+//   adj    u16 [B][4096][8]       : adjacency lists (node indices)
 //   cand   u64 [B*C][P]           : candidate keys of the problems nms_large_kernel handles
 // ---------------------------------------------------------------------------------------
 constexpr int kBlockNodes = 1024;       // suppressor nodes graph_kernel holds in shared memory at a time

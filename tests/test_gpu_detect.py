@@ -543,10 +543,11 @@ def test_no_candidates_and_all_candidates(rd):
 
 
 def test_graph_fallback_paths_agree(rd):
-    """An image with more ARM-passing anchors than the graph holds (1024) falls back to per-problem
-    bins; both paths must give the oracle's result (here: same generator, pass rate high vs low)."""
-    _run_vs_oracle(rd, 2, 3000, 3, 150, 100, kind='dense')                      # ~2600 passing: flagged
-    _run_vs_oracle(rd, 2, 3000, 3, 150, 100, kind='sparse', arm_shift=-2.0)     # few hundred passing: graph
+    """An image with more nodes than the graph holds (4096), or whose graph overflows a node's 8 adjacency
+    slots, falls back to per-problem bins; every path must give the oracle's result."""
+    _run_vs_oracle(rd, 2, 6000, 3, 150, 100, kind='dense')                      # ~5200 nodes: no graph
+    _run_vs_oracle(rd, 2, 3000, 3, 150, 100, kind='dense')                      # ~2600 nodes, 3 graph blocks, dense overlaps
+    _run_vs_oracle(rd, 2, 3000, 3, 150, 100, kind='sparse', arm_shift=-2.0)     # few hundred nodes: graph
 
 
 def test_limits_raise(rd):
