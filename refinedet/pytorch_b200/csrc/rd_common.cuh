@@ -15,6 +15,22 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // ---- launch accounting (rd_launch_count) ------------------------------------
 void note_launch(int n = 1);
 
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute belongs to the (kernel, device) pair, so
+// the high-water mark is kept per device: a process that drives several GPUs sets it on each of them.
+constexpr int kMaxDevices = 64;
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&high_water)[kMaxDevices]) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    size_t& hw = high_water[(unsigned)dev % kMaxDevices];
+    if (hw == 0) hw = 48 * 1024;                       // the default limit needs no opt-in
+    if (bytes <= hw) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) hw = bytes;
+    return e;
+}
+
 #define RD_CHECK_LAUNCH()                                   \
     do {                                                    \
         cudaError_t e__ = cudaGetLastError();               \

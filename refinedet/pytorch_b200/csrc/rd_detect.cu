@@ -1045,14 +1045,10 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     RD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[1], st);
     {
-        static bool s_graph_attr = false;
-        if (!s_graph_attr) {
-            cudaError_t e = cudaFuncSetAttribute(graph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)sizeof(GraphSmem));
-            if (e != cudaSuccess) return (int)e;
-            s_graph_attr = true;
-        }
-        cudaError_t e = launch_pdl(graph_kernel, dim3(kGraphSplit, B), dim3(kGraphThreads), sizeof(GraphSmem), st,
+        static size_t s_graph_smem[kMaxDevices];
+        cudaError_t e = ensure_dynamic_smem(graph_kernel, sizeof(GraphSmem), s_graph_smem);
+        if (e != cudaSuccess) return (int)e;
+        e = launch_pdl(graph_kernel, dim3(kGraphSplit, B), dim3(kGraphThreads), sizeof(GraphSmem), st,
                                    (const int*)ws.nnodes, (const uint32_t*)ws.gtab, (const float4*)ws.nbox,
                                    (const uint32_t*)ws.ncr, P, nms_thresh, nms_flags, ws.adj, ws.adjn, ws.flag);
         if (e != cudaSuccess) return (int)e;
@@ -1072,17 +1068,14 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     {
         const int mcap = top_k < P ? top_k : P;
         const NmsSmemLayout Ll = nms_layout(mcap);
-        static size_t s_attr = 48 * 1024;
-        if (Ll.total > s_attr) {
-            cudaError_t e = cudaFuncSetAttribute(nms_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)Ll.total);
-            if (e != cudaSuccess) return (int)e;
-            s_attr = Ll.total;
-        }
-        static int s_dev_sms = 0;
+        static size_t s_large_smem[kMaxDevices];
+        cudaError_t e = ensure_dynamic_smem(nms_large_kernel, Ll.total, s_large_smem);
+        if (e != cudaSuccess) return (int)e;
+        static int s_sms[kMaxDevices];
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int& s_dev_sms = s_sms[(unsigned)dev % kMaxDevices];
         if (s_dev_sms == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&s_dev_sms, cudaDevAttrMultiProcessorCount, dev);
             if (s_dev_sms <= 0) s_dev_sms = 148;
         }
@@ -1237,13 +1230,9 @@ static int launch_single(const unsigned long long* keys, int n, const float4* bo
     int m = top_k < n ? top_k : n;
     if (m > RD_MAX_NMS_BOXES) return RD_ERR_UNSUPPORTED;
     const NmsSmemLayout L = nms_layout(m);
-    static size_t s_attr = 48 * 1024;
-    if (L.total > s_attr) {
-        cudaError_t e = cudaFuncSetAttribute(nms_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)L.total);
-        if (e != cudaSuccess) return (int)e;
-        s_attr = L.total;
-    }
+    static size_t s_single_smem[kMaxDevices];
+    cudaError_t e = ensure_dynamic_smem(nms_single_kernel, L.total, s_single_smem);
+    if (e != cudaSuccess) return (int)e;
     nms_single_kernel<<<1, kLargeThreads, L.total, st>>>(keys, n, boxes, thresh, top_k, m, nms_flags, m, keep64,
                                                           keep32, count_out);
     note_launch();

@@ -307,12 +307,9 @@ int rd_conf_loss(const float* conf, const long long* conf_t, const float* arm_co
                                                                      theta, rows, ce_out, lse_out, pos_out);
     } else {
         const size_t smem = (size_t)kLossRows * (C | 1) * sizeof(float);
-        static size_t s_attr = 48 * 1024;
-        if (smem > s_attr) {
-            cudaError_t e = cudaFuncSetAttribute(conf_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-            s_attr = smem;
-        }
+        static size_t s_conf_smem[kMaxDevices];
+        cudaError_t e = ensure_dynamic_smem(conf_loss_kernel, smem, s_conf_smem);
+        if (e != cudaSuccess) return (int)e;
         long long blocks = (rows + kLossRows - 1) / kLossRows;
         if (blocks > 148 * 64) blocks = 148 * 64;
         conf_loss_kernel<<<(unsigned)blocks, kLossRows, smem, st>>>(conf, conf_t, (const float2*)arm_conf, theta, rows, C,
