@@ -176,8 +176,8 @@ RD_API int rd_nms(const float* boxes, const float* scores, int n, float thresh, 
            long long* keep_out, int* count_out, void* stream);
 /* Drop-in for `_nms` (utils/nms/gpu_nms.hpp:1-2, nms_kernel.cu:91-144): HOST pointers,
  * boxes_host[boxes_num, boxes_dim>=5] rows x1,y1,x2,y2,score ALREADY sorted by score
- * descending (gpu_nms.pyx:26-29); pixel +1 IoU, suppress IoU > thresh; synchronous;
- * allocates and frees its own device scratch like the reference. */
+ * descending (gpu_nms.pyx:26-29); pixel +1 IoU, suppress IoU > thresh; synchronous.  The reference
+ * cudaMalloc'd and freed its scratch on every call; this keeps one grow-only scratch per device. */
 RD_API int rd_nms_host(int* keep_out_host, int* num_out_host, const float* boxes_host,
                 int boxes_num, int boxes_dim, float nms_overlap_thresh, int device_id);
 /* same with explicit flavour flags (RD_NMS_PIXEL_PLUS1 | RD_NMS_SUPPRESS_EQ reproduces the

@@ -27,6 +27,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <mutex>
 
 namespace rd {
 
@@ -856,15 +857,14 @@ __global__ void make_keys_kernel(const float* __restrict__ scores, int n, unsign
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = make_key(scores[i], (uint32_t)i);
 }
-// rows already sorted by score descending (rd_nms_host): the key order must follow the row order
-__global__ void make_keys_sorted_kernel(int n, unsigned long long* keys) {
+// rd_nms_host: rows [n, dim] already sorted by score descending -> boxes + keys whose order follows the row order
+__global__ void strip_boxes_kernel(const float* __restrict__ dets, int n, int dim, float4* boxes,
+                                   unsigned long long* keys) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = ((unsigned long long)(0xffffffffu - (uint32_t)i) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
-}
-__global__ void strip_boxes_kernel(const float* __restrict__ dets, int n, int dim, float4* boxes) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) boxes[i] = make_float4(dets[(size_t)i * dim], dets[(size_t)i * dim + 1], dets[(size_t)i * dim + 2],
-                                      dets[(size_t)i * dim + 3]);
+    if (i >= n) return;
+    boxes[i] = make_float4(dets[(size_t)i * dim], dets[(size_t)i * dim + 1], dets[(size_t)i * dim + 2],
+                           dets[(size_t)i * dim + 3]);
+    keys[i] = ((unsigned long long)(0xffffffffu - (uint32_t)i) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
 }
 
 __global__ void __launch_bounds__(kLargeThreads)
@@ -1268,29 +1268,40 @@ int rd_nms_host_ex(int* keep_out_host, int* num_out_host, const float* boxes_hos
     const size_t b_box = align_up((size_t)n * 16, 256);
     const size_t b_keys = align_up((size_t)n * 8, 256);
     const size_t b_keep = align_up((size_t)n * 4, 256);
-    unsigned char* d = nullptr;
-    e = cudaMalloc(&d, b_dets + b_box + b_keys + b_keep + 256);
-    if (e != cudaSuccess) return (int)e;
+    const size_t need = b_dets + b_box + b_keys + b_keep + 256;
+    // grow-only device scratch per device (the reference malloc'd and freed per call, nms_kernel.cu:100-108,
+    // 142-143: two driver round trips that cost more than the NMS itself); the call is synchronous, so the
+    // lock is simply held for its duration
+    static struct { unsigned char* ptr; size_t bytes; } s_scratch[kMaxDevices];
+    static std::mutex s_mu;
+    std::lock_guard<std::mutex> lock(s_mu);
+    auto& sc = s_scratch[(unsigned)device_id % kMaxDevices];
+    if (sc.bytes < need) {
+        if (sc.ptr) cudaFree(sc.ptr);
+        sc.ptr = nullptr; sc.bytes = 0;
+        const size_t grow = need < (1u << 20) ? (1u << 20) : need;
+        e = cudaMalloc(&sc.ptr, grow);
+        if (e != cudaSuccess) return (int)e;
+        sc.bytes = grow;
+    }
+    unsigned char* d = sc.ptr;
     float* d_dets = (float*)d;
     float4* d_box = (float4*)(d + b_dets);
     unsigned long long* d_keys = (unsigned long long*)(d + b_dets + b_box);
     int* d_keep = (int*)(d + b_dets + b_box + b_keys);
     int* d_cnt = (int*)(d + b_dets + b_box + b_keys + b_keep);
-    int rc = 0;
     cudaStream_t st = 0;
     e = cudaMemcpyAsync(d_dets, boxes_host, (size_t)n * boxes_dim * 4, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { cudaFree(d); return (int)e; }
-    strip_boxes_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_dets, n, boxes_dim, d_box);
-    make_keys_sorted_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d_keys);
-    note_launch(2);
-    rc = launch_single(d_keys, n, d_box, nms_overlap_thresh, n, nms_flags, nullptr, d_keep, d_cnt, st);
+    if (e != cudaSuccess) return (int)e;
+    strip_boxes_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_dets, n, boxes_dim, d_box, d_keys);
+    note_launch();
+    int rc = launch_single(d_keys, n, d_box, nms_overlap_thresh, n, nms_flags, nullptr, d_keep, d_cnt, st);
     if (rc == 0) {
         e = cudaMemcpyAsync(num_out_host, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(keep_out_host, d_keep, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         rc = (int)e;
     }
-    cudaFree(d);
     return rc;
 }
 

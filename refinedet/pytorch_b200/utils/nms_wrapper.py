@@ -39,7 +39,7 @@ def gpu_nms(dets, thresh, device_id=None, suppress_on_equal=False):
     check(lib().rd_nms_host_ex(keep.ctypes.data_as(ctypes.c_void_p), ctypes.cast(ctypes.byref(num_out), ctypes.c_void_p),
                                sorted_dets.ctypes.data_as(ctypes.c_void_p), n, dim, float(thresh), int(device_id),
                                flags), 'rd_nms_host')
-    return [int(i) for i in order[keep[:num_out.value]]]
+    return order[keep[:num_out.value]].tolist()
 
 
 def nms(dets, thresh, force_cpu=False):
