@@ -780,8 +780,13 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
     grid_dependency_wait();          // nms_small_kernel (and everything before it) has completed
     const uint32_t nq = A.header[0];
     if (nq == 0) return;             // the common case: nothing queued — leave before any set-up work
-    const NmsSmemLayout L = nms_layout(mcap);
-    int* s_cnt = reinterpret_cast<int*>(smem + L.off_misc) + 15;     // misc[15]: unused by nms_process
+    int* s_cnt;
+    bool wide_fits;                  // the 1024-candidate graph resolve fits this launch's shared memory
+    {
+        const NmsSmemLayout L0 = nms_layout(mcap);
+        s_cnt = reinterpret_cast<int*>(smem + L0.off_misc) + 15;     // misc[15]: unused by nms_process
+        wide_fits = sizeof(SmallSmem<kWideCap>) <= L0.total;
+    }
     const int tid = threadIdx.x, lane = tid & 31;
     // dynamic tickets: problems differ a lot in cost (select passes, pairs), a static stride leaves CTAs idle
     for (;;) {
@@ -831,8 +836,7 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
         sink.row_layout = A.row_layout;
         int kept;
 #ifndef RD_NO_LARGE_GRAPH
-        if (N <= kGraphNodes && A.img_flag[b] == 0 && n <= kWideCap && n <= A.top_k &&
-            sizeof(SmallSmem<kWideCap>) <= L.total) {
+        if (wide_fits && N <= kGraphNodes && A.img_flag[b] == 0 && n <= kWideCap && n <= A.top_k) {
             kept = large_graph_resolve(smem, keys, n, N, A.max_out, A.adj + (size_t)b * kGraphNodes,
                                        A.adjn + (size_t)b * kGraphNodes, A.nbox + (size_t)b * A.P, A.nanc + (size_t)b * A.P,
                                        sink.rows, sink.anchors, sink.row_layout);
@@ -845,6 +849,7 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
             pb.has_scale = 0;                                     // node boxes are already scaled
             pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
             pb.thr = A.thr; pb.top_k = A.top_k; pb.max_out = A.max_out; pb.flags = A.flags;
+            const NmsSmemLayout L = nms_layout(mcap);               // recomputed here: not kept live across the loop
             kept = nms_process(smem, L, pb, sink);
         }
         if (tid == 0) A.out_counts[bc] = kept;
