@@ -475,6 +475,38 @@ def main():
               'achieved_GBs': bytes3 / (ms3 * 1e-3) / 1e9, 'frac_of_hbm_peak': bytes3 / (ms3 * 1e-3) / 1e9 / peak,
               'algorithmic_bytes_per_launch': bytes3}
 
+    # BASELINE.json config 4 (reported, not the headline): RefineDetMultiBoxLoss training step — ARM + ODM criteria,
+    # forward + backward, 50 ground-truth boxes per image, batch 32 (match, conf loss, HNM, reduce, backward kernels)
+    train_step = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        tp = [t.to(dev) for t in synthetic.train_predictions(seed_for(rank, 40), BATCH, P, C)]
+        tg = [t.to(dev) for t in synthetic.targets(seed_for(rank, 41), BATCH, 50, C)]
+        arm_crit = rd.RefineDetMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)
+        odm_crit = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True)
+        leaves = [t.clone().requires_grad_(True) for t in tp]
+
+        def one_step():
+            rd.box_utils._PAD_CACHE = None                      # a real step brings new targets: pad them once, not zero times
+            preds = (leaves[0], leaves[1], leaves[2], leaves[3], priors)
+            al, ac = arm_crit(preds, tg)
+            ol, oc = odm_crit(preds, tg)
+            (al + ac + ol + oc).backward()                      # train_refinedet.py:252-256
+            for t in leaves:
+                t.grad = None
+        for _ in range(3):
+            one_step()
+        torch.cuda.synchronize()
+        n_t = 10
+        t0 = time.perf_counter()
+        for _ in range(n_t):
+            one_step()
+        torch.cuda.synchronize()
+        ms_t = 1e3 * (time.perf_counter() - t0) / n_t
+        train_step = {'ms_per_step': ms_t, 'value': BATCH / (ms_t * 1e-3), 'unit': UNIT,
+                      'what': 'ARM + ODM RefineDetMultiBoxLoss forward + backward (B=32, P=16320, C=81, 50 GT/image), '
+                              'wall clock including the host glue and the two N < 1 host checks'}
+        del leaves, tp, tg
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, done, elapsed = cpu_reference_run(args.workload, 1000, 1, cores, budget_s=12.0)
@@ -492,7 +524,7 @@ def main():
                                arm_pass_fraction=arm_pass, kept_rows_per_step=kept_rows),
                 'latency_ms_per_batch': latency_ms,
                 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'secondary': secondary,
-                'logits_in': logits_in, 'a3_forward': a3,
+                'logits_in': logits_in, 'a3_forward': a3, 'train_step': train_step,
                 'gpu_launches': int(launches),
                 'clocks': clocks.summary()}
         print(json.dumps(line))

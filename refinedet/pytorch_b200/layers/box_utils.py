@@ -113,12 +113,19 @@ def log_sum_exp(x):
 # matching
 # ---------------------------------------------------------------------------------------------
 LABEL_ODM, LABEL_ARM_BINARY, LABEL_SSD_PLUS1 = 0, 1, 2
+_PAD_CACHE = None
 
 
 def pad_targets(targets, device):
     """``targets``: list of B tensors ``[G_i, 5]`` (x1,y1,x2,y2,label) -> padded
     ``truths[B,Gmax,4]``, ``labels[B,Gmax]``, ``gt_count[B]`` on ``device`` (the batched
     form of the per-image slicing at refinedet_multibox_loss.py:76-77)."""
+    # the ARM and the ODM criterion of a training step pad the same list (train_refinedet.py:252-253): keep the
+    # latest result, keyed by the identity, version and storage of every target tensor
+    global _PAD_CACHE
+    key = (str(device),) + tuple((id(t), t._version, t.data_ptr(), t.shape[0]) for t in targets)
+    if _PAD_CACHE is not None and _PAD_CACHE[0] == key:
+        return _PAD_CACHE[1]
     counts = [int(t.shape[0]) for t in targets]
     gmax = max(max(counts), 1)
     if gmax > _ffi.RD_MAX_GT:
@@ -136,6 +143,7 @@ def pad_targets(targets, device):
     truths = padded[:, :, :4].contiguous()
     labels = padded[:, :, 4].contiguous()
     gt_count = torch.tensor(counts, dtype=torch.int32).to(device, non_blocking=True)
+    _PAD_CACHE = (key, (truths, labels, gt_count))
     return truths, labels, gt_count
 
 
