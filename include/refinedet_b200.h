@@ -206,6 +206,13 @@ RD_API int rd_refine_match(const float* truths, const float* labels, const int* 
                     float* loc_t, long long* conf_t, int* best_truth_idx,
                     float* best_truth_overlap, void* stream);
 
+/* target ingestion (data/__init__.py:9-27 detection_collate + the per-image slicing of
+ * refinedet_multibox_loss.py:76-77): flat[total,5] = the step's ragged target tensors concatenated
+ * (x1,y1,x2,y2,label), offsets[B+1] int32 (exclusive prefix sum of the per-image counts) ->
+ * truths[B,Gmax,4], labels[B,Gmax] (zero padded), gt_count[B]. */
+RD_API int rd_pad_targets(const float* flat, const int* offsets, int B, int Gmax,
+                   float* truths, float* labels, int* gt_count, void* stream);
+
 /* hard-negative mining (refinedet_multibox_loss.py:117-123):
  *   loss_c [B,P] float (values at positives are ignored = treated as 0, :117),
  *   pos [B,P] uint8;  neg_out [B,P] uint8 = 1 for the num_neg = min(ratio*num_pos, P-1)

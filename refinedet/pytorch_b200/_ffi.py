@@ -65,6 +65,7 @@ _SIGNATURES = {
     'rd_refine_match': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float,
                                 c_int, _P, c_size_t, _P, _P, _P, _P, _P]),
     'rd_hnm_select': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    'rd_pad_targets': (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P]),
     'rd_conf_loss': (c_int, [_P, _P, _P, c_float, ctypes.c_longlong, c_int, _P, _P, _P, _P]),
     'rd_multibox_loss_workspace_bytes': (c_size_t, [c_int]),
     'rd_multibox_loss_reduce': (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_size_t, _P, _P, _P, _P]),

@@ -314,6 +314,28 @@ hnm_select_kernel(const float* __restrict__ loss_c, const unsigned char* __restr
 }
 
 // ---------------------------------------------------------------------------------------
+// target ingestion: the B ragged [G_i, 5] target tensors of a step (data/__init__.py:9-27 detection_collate),
+// concatenated, -> padded truths[B,Gmax,4], labels[B,Gmax], gt_count[B] in one pass
+// ---------------------------------------------------------------------------------------
+__global__ void pad_targets_kernel(const float* __restrict__ flat, const int* __restrict__ offs, int B, int Gmax,
+                                   float4* __restrict__ truths, float* __restrict__ labels, int* __restrict__ gt_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Gmax) return;
+    const int b = i / Gmax, g = i - b * Gmax;
+    const int o = offs[b], n = offs[b + 1] - o;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    float lab = 0.f;
+    if (g < n) {
+        const float* r = flat + (size_t)(o + g) * 5;
+        t = make_float4(r[0], r[1], r[2], r[3]);
+        lab = r[4];
+    }
+    truths[i] = t;
+    labels[i] = lab;
+    if (g == 0) gt_count[b] = n;
+}
+
+// ---------------------------------------------------------------------------------------
 // element-wise box_utils functions
 // ---------------------------------------------------------------------------------------
 enum { OP_POINT_FORM = 0, OP_CENTER_SIZE = 1 };
@@ -437,6 +459,18 @@ int rd_refine_match(const float* truths, const float* labels, const int* gt_coun
     match_pass2_kernel<<<grid, kMatchThreads, (size_t)Gmax * 4, st>>>(
         (const float4*)truths, labels, gt_count, (const float4*)priors, (const float4*)arm_loc, P, Gmax, threshold,
         v0, v1, label_mode, best_prior, tmp_ov, tmp_idx, (float4*)loc_t, conf_t, best_truth_idx, best_truth_overlap);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+int rd_pad_targets(const float* flat, const int* offsets, int B, int Gmax, float* truths, float* labels,
+                   int* gt_count, void* stream) {
+    if (!flat || !offsets || !truths || !labels || !gt_count || B <= 0 || Gmax <= 0) return RD_ERR_BAD_ARG;
+    if ((uintptr_t)truths & 15) return RD_ERR_ALIGNMENT;
+    const int n = B * Gmax;
+    pad_targets_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(flat, offsets, B, Gmax, (float4*)truths, labels,
+                                                                        gt_count);
     note_launch();
     RD_CHECK_LAUNCH();
     return 0;

@@ -131,18 +131,24 @@ def pad_targets(targets, device):
     if gmax > _ffi.RD_MAX_GT:
         raise RuntimeError('more than %d ground-truth boxes in one image (%d)' % (_ffi.RD_MAX_GT, gmax))
     B = len(targets)
-    padded = torch.zeros(B * gmax, 5, dtype=torch.float32, device=device)
-    if sum(counts):
-        # one concatenation + one indexed store instead of B slice assignments
-        flat = torch.cat([t.detach().to(device=device, dtype=torch.float32).reshape(-1, 5) for t in targets if t.shape[0]])
-        cnt = np.asarray(counts, dtype=np.int64)
-        start = np.cumsum(cnt) - cnt                                     # first row of every image in `flat`
-        rows = np.repeat(np.arange(B, dtype=np.int64) * gmax - start, cnt) + np.arange(int(cnt.sum()), dtype=np.int64)
-        padded[torch.from_numpy(rows).to(device, non_blocking=True)] = flat
-    padded = padded.view(B, gmax, 5)
-    truths = padded[:, :, :4].contiguous()
-    labels = padded[:, :, 4].contiguous()
-    gt_count = torch.tensor(counts, dtype=torch.int32).to(device, non_blocking=True)
+    truths = torch.empty(B, gmax, 4, dtype=torch.float32, device=device)
+    labels = torch.empty(B, gmax, dtype=torch.float32, device=device)
+    gt_count = torch.empty(B, dtype=torch.int32, device=device)
+    if sum(counts) == 0:
+        truths.zero_(); labels.zero_(); gt_count.zero_()
+    else:
+        # one concatenation + one kernel instead of B slice assignments
+        if all(t.is_cuda and t.dtype == torch.float32 and t.device == truths.device for t in targets):
+            flat = torch.cat([t.detach() for t in targets if t.shape[0]])
+        else:
+            flat = torch.cat([t.detach().reshape(-1, 5) for t in targets if t.shape[0]]).to(device=device, dtype=torch.float32)
+        flat = flat.reshape(-1, 5).contiguous()
+        offs = np.zeros(B + 1, dtype=np.int32)
+        np.cumsum(counts, out=offs[1:])
+        offsets = torch.from_numpy(offs).to(device, non_blocking=True)
+        with torch.cuda.device(truths.device):
+            check(lib().rd_pad_targets(ptr(flat), ptr(offsets), B, gmax, ptr(truths), ptr(labels), ptr(gt_count),
+                                       stream_ptr()), 'rd_pad_targets')
     _PAD_CACHE = (key, (truths, labels, gt_count))
     return truths, labels, gt_count
 

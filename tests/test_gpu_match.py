@@ -233,6 +233,28 @@ def test_loss_tail_kernels(rd, B, size, C, G, use_arm):
     assert bool(torch.isfinite(p_conf.grad).all())
 
 
+def test_pad_targets_kernel(rd):
+    """rd_pad_targets (detection_collate's ragged list -> padded batch): ragged counts incl. an empty image,
+    host and device inputs, the ARM/ODM cache hit and its invalidation by an in-place edit."""
+    bu = rd.box_utils
+    tg = gen.targets(17, 5, 7, 21)
+    tg = [tg[0], tg[1][:3], tg[2][:0], tg[3][:1], tg[4]]
+    for src in ([t.cuda() for t in tg], tg):
+        bu._PAD_CACHE = None
+        truths, labels, cnt = bu.pad_targets(src, 'cuda')
+        assert truths.shape == (5, 7, 4) and cnt.tolist() == [7, 3, 0, 1, 7]
+        for i, t in enumerate(tg):
+            n = t.shape[0]
+            assert torch.equal(truths[i, :n].cpu(), t[:, :4]) and torch.equal(labels[i, :n].cpu(), t[:, 4])
+            assert float(truths[i, n:].abs().sum()) == 0.0 and float(labels[i, n:].abs().sum()) == 0.0
+    dev = [t.cuda() for t in tg]
+    a = bu.pad_targets(dev, 'cuda')
+    assert bu.pad_targets(dev, 'cuda')[0] is a[0]                 # second criterion of the step: cached
+    dev[1][0, 0] += 0.25                                           # in-place edit bumps the version
+    b = bu.pad_targets(dev, 'cuda')
+    assert b[0] is not a[0] and float(b[0][1, 0, 0]) == float(dev[1][0, 0])
+
+
 def test_check_targets(rd):
     """SURVEY f-3: the per-coordinate validation loop of train_refinedet.py:240-245 as one reduction."""
     tg = [t.cuda() for t in gen.targets(3, 4, 6, 21)]
