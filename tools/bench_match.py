@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Secondary measurement (BASELINE.json config 4/5): training-side matching and
 hard-negative selection on one B200 — device time with CUDA events, L2 flushed between iterations,
-against the algorithmic bytes (refine_match 40*P + 20*G per image, HNM 6*P per image), next to the
-numpy oracle on the host.
+against the algorithmic bytes (refine_match 40*P + 20*G per image, HNM 6*P per image).  (The CPU side of
+this path is timed by bench.py's cpu_baseline leg only: oracle/ is test infrastructure.)
 
     python tools/bench_match.py [--G 50] [--classes 81] [--steps 30]
 """
@@ -27,7 +27,6 @@ def main():
     args = ap.parse_args()
     import refinedet.pytorch_b200 as rd
     from refinedet.pytorch_b200 import synthetic
-    from oracle import box_oracle as bo
     B, C, G, P = args.batch, args.classes, args.G, 16320
     dev = torch.device('cuda', 0)
     priors = rd.PriorBox(rd.REFINEDET_ANCHORS['512']).forward().to(dev)
@@ -92,13 +91,6 @@ def main():
         p_conf.grad = None
     ms = timed(fwd_bwd)
     out['odm_criterion_forward_backward'] = {'ms': ms, 'images_per_s': B / ms * 1e3}
-    # CPU oracle, one image, one core
-    t0 = time.perf_counter()
-    n_img = 2
-    for i in range(n_img):
-        bo.refine_match(0.5, tg[i][:, :4].numpy(), priors.cpu().numpy(), [0.1, 0.2], tg[i][:, 4].numpy(),
-                        arm_loc[i].cpu().numpy())
-    out['cpu_oracle_refine_match'] = {'images_per_s_per_core': n_img / (time.perf_counter() - t0)}
     print(json.dumps(out))
 
 
