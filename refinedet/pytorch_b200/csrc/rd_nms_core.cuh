@@ -567,14 +567,16 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
     }
     __syncthreads();
 
-    // ---- 5. greedy walk: warp 0 drives 32 candidates per step; the (candidate, kept earlier box) pairs
-    //         that survive the bin cull are flattened into a list and tested by ALL threads, so a box that
-    //         overlaps many others does not serialise the walk -------------------------------------------
+    // ---- 5. greedy walk, 32 candidates per step.  (a) ALL warps enumerate the (candidate, kept earlier box)
+    //         pairs that survive the bin cull -- warp q takes the mask words q, q + nwarps, ... <= ib, lane =
+    //         candidate of the step, a contiguous span of the pair list is reserved per warp with one shared
+    //         atomic (the order of the list is irrelevant: results are ORed); (b) all threads test the listed
+    //         pairs exactly; (c) warp 0 settles the 32 candidates in score order and emits the kept rows ------
     uint32_t* pairs = reinterpret_cast<uint32_t*>(smem + L.off_pairs);
     uint32_t* s_tin = reinterpret_cast<uint32_t*>(smem + L.off_tin);
-    // misc: 9 sup word, 10 pair total, 11 stop
+    // misc: 9 sup word, 10 pairs reserved, 11 stop, 12 end of the valid part of the list
     if (tid < 32) s_tin[tid] = 0;
-    if (tid == 0) { misc[9] = 0; misc[11] = 0; }
+    if (tid == 0) { misc[9] = 0; misc[10] = 0; misc[11] = 0; misc[12] = (uint32_t)kLargePairCap; }
     __syncthreads();
     const float thr = pb.thr;
     const int flags = pb.flags;
@@ -584,47 +586,58 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
     const uint32_t* Sy = tab + 2 * kCols * L.WS;
     const uint32_t* Ey = tab + 3 * kCols * L.WS;
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const int nwarps = nthr >> 5;
     int kept_total = 0;                                   // meaningful in warp 0
     for (int ib = 0; ib < Wm; ++ib) {
         const int j = ib * 32 + lane;
         const bool valid = j < m;
-        bool alive = valid;
         float x1 = 0, y1 = 0, x2 = 0, y2 = 0;
-        const uint32_t *rSx = Sx, *rEx = Ex, *rSy = Sy, *rEy = Ey;
-        int total = 0;
-        if (warp == 0) {
+        if (warp <= ib) {                                 // warp-uniform; lanes past m carry empty masks
             uint32_t cr = 0;
-            if (valid) { x1 = sx1[j]; y1 = sy1[j]; x2 = sx2[j]; y2 = sy2[j]; cr = scr[j]; }
-            rSx = Sx + ((cr >> 8) & 255u) * L.WS;    // S_x[b_j]
-            rEx = Ex + (cr & 255u) * L.WS;           // E_x[a_j]
-            rSy = Sy + ((cr >> 24) & 255u) * L.WS;   // S_y[b_j]
-            rEy = Ey + ((cr >> 16) & 255u) * L.WS;   // E_y[a_j]
-            int nh = 0;
-            if (valid) {
-                for (int w = 0; w <= ib; ++w)
-                    nh += __popc(rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & (w < ib ? keptbits[w] : lt_mask));
-            }
-            int off = nh;
+            if (valid) { cr = scr[j]; x1 = sx1[j]; y1 = sy1[j]; x2 = sx2[j]; y2 = sy2[j]; }
+            const uint32_t* rSx = Sx + ((cr >> 8) & 255u) * L.WS;    // S_x[b_j]
+            const uint32_t* rEx = Ex + (cr & 255u) * L.WS;           // E_x[a_j]
+            const uint32_t* rSy = Sy + ((cr >> 24) & 255u) * L.WS;   // S_y[b_j]
+            const uint32_t* rEy = Ey + ((cr >> 16) & 255u) * L.WS;   // E_y[a_j]
+            for (int w = warp; w <= ib; w += nwarps) {
+                uint32_t h = rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & (w < ib ? keptbits[w] : lt_mask);
+                if (!valid) h = 0u;
+                if (!__ballot_sync(kFullMask, h != 0u)) continue;
+                const int nh = __popc(h);
+                int off = nh;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, off, d); if (lane >= d) off += o; }
-            total = __shfl_sync(kFullMask, off, 31);
-            off -= nh;
-            if (total > 0 && total <= kLargePairCap && valid) {
-                for (int w = 0; w <= ib; ++w) {
-                    uint32_t h = rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & (w < ib ? keptbits[w] : lt_mask);
+                for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, off, d); if (lane >= d) off += o; }
+                const int wtot = __shfl_sync(kFullMask, off, 31);
+                off -= nh;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&misc[10], (uint32_t)wtot);
+                base = __shfl_sync(kFullMask, base, 0);
+                if (base + (uint32_t)wtot <= (uint32_t)kLargePairCap) {
+                    off += (int)base;
                     while (h) {
                         const int i = (w << 5) + __ffs(h) - 1;
                         h &= h - 1;
                         pairs[off++] = ((uint32_t)lane << 16) | (uint32_t)i;
                     }
+                } else {                                  // the list is full: test in place
+                    if (lane == 0) atomicMin(&misc[12], base);
+                    uint32_t tin = 0;
+                    bool sup = false;
+                    while (h) {
+                        const int i = (w << 5) + __ffs(h) - 1;
+                        h &= h - 1;
+                        if (suppresses(sx1[i], sy1[i], sx2[i], sy2[i], x1, y1, x2, y2, thr, flags)) {
+                            if (w < ib) sup = true; else tin |= 1u << (i - ib * 32);
+                        }
+                    }
+                    if (sup) atomicOr(&misc[9], 1u << lane);
+                    if (tin) atomicOr(&s_tin[lane], tin);
                 }
             }
-            if (lane == 0) misc[10] = (uint32_t)total;
         }
         __syncthreads();
-        total = (int)misc[10];
-        const bool listed = total > 0 && total <= kLargePairCap;
-        if (listed) {
+        {
+            const int total = (int)min(misc[10], misc[12]);
             for (int p = tid; p < total; p += nthr) {
                 const uint32_t e = pairs[p];
                 const int jl = (int)(e >> 16), i = (int)(e & 0xffffu);
@@ -637,25 +650,11 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
         }
         __syncthreads();
         if (warp == 0) {
-            uint32_t tin = 0;
-            if (listed) {
-                if ((misc[9] >> lane) & 1u) alive = false;
-                tin = s_tin[lane];
-                __syncwarp();
-                s_tin[lane] = 0;
-                if (lane == 0) misc[9] = 0;
-            } else if (total > 0 && valid) {         // pair list would overflow: test in place
-                for (int w = 0; w <= ib; ++w) {
-                    uint32_t h = rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & (w < ib ? keptbits[w] : lt_mask);
-                    while (h && (alive || w == ib)) {
-                        const int i = (w << 5) + __ffs(h) - 1;
-                        h &= h - 1;
-                        if (suppresses(sx1[i], sy1[i], sx2[i], sy2[i], x1, y1, x2, y2, thr, flags)) {
-                            if (w < ib) alive = false; else tin |= 1u << (i - ib * 32);
-                        }
-                    }
-                }
-            }
+            bool alive = valid && !((misc[9] >> lane) & 1u);
+            const uint32_t tin = s_tin[lane];
+            __syncwarp();
+            s_tin[lane] = 0;
+            if (lane == 0) { misc[9] = 0; misc[10] = 0; misc[12] = (uint32_t)kLargePairCap; }
             uint32_t u = __reduce_or_sync(kFullMask, alive ? tin : 0u);   // in-block resolution in score order
             while (u) {
                 const int k = __ffs(u) - 1;
