@@ -424,6 +424,37 @@ def main():
                              'top_k = 1000 and goes through the large-problem kernel (radix select + own bins)'}
         del o_dev
 
+    # BASELINE.json configs 2 and 5 (reported, not the headline): RefineDet320 VOC and the 2-class SAR-ship
+    # RefineDet512 detect stage, batch 32, both generators, one batch at a time with the L2 flushed before it
+    other_configs = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        other_configs = {}
+        for name, size, dim, C2, nms_thr in (('cfg2_refinedet320_voc', '320', 320.0, 21, 0.45),
+                                             ('cfg5_sarship_2class', '512', 512.0, 2, 0.49)):
+            pri2 = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward().to(dev)
+            P2 = pri2.shape[0]
+            det2 = rd.Detect_RefineDet(C2, int(dim), 0, TOP_K, CONF_THR, nms_thr, OBJ_THR, KEEP_TOP_K)
+            scale2 = torch.tensor([dim] * 4, device=dev).reshape(1, 4).expand(BATCH, 4).contiguous()
+            for gen in ('sparse', 'dense'):
+                x = [t.to(dev) for t in synthetic.detect_inputs(seed_for(rank, 20), BATCH, P2, C2, gen)]
+                for _ in range(3):
+                    r2 = det2.detect(x[0], x[1], x[2], x[3], pri2, scale=scale2)
+                torch.cuda.synchronize()
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+                for a, b in evs:
+                    flush_buf.zero_()
+                    a.record()
+                    det2.detect(x[0], x[1], x[2], x[3], pri2, scale=scale2)
+                    b.record()
+                torch.cuda.synchronize()
+                ms_o = sorted(a.elapsed_time(b) for a, b in evs)[len(evs) // 2]
+                bytes_o = BATCH * 4 * P2 * (10 + C2) + 20 * int(r2.counts.sum())
+                other_configs['%s_%s' % (name, gen)] = {
+                    'ms_per_step': ms_o, 'value': BATCH / (ms_o * 1e-3), 'unit': UNIT, 'anchors': P2, 'classes': C2,
+                    'kept_rows_per_step': int(r2.counts.sum()), 'algorithmic_bytes_per_launch': bytes_o,
+                    'frac_of_hbm_peak': bytes_o / (ms_o * 1e-3) / 1e9 / peak}
+                del x
+
     # f-1: logits in (softmax folded into the stage) against torch.softmax + the stage, one stream, L2 flushed
     logits_in = None
     if rank == 0 and world == 1 and not args.no_secondary:
@@ -524,7 +555,7 @@ def main():
                                arm_pass_fraction=arm_pass, kept_rows_per_step=kept_rows),
                 'latency_ms_per_batch': latency_ms,
                 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'secondary': secondary,
-                'logits_in': logits_in, 'a3_forward': a3, 'train_step': train_step,
+                'other_configs': other_configs, 'logits_in': logits_in, 'a3_forward': a3, 'train_step': train_step,
                 'gpu_launches': int(launches),
                 'clocks': clocks.summary()}
         print(json.dumps(line))

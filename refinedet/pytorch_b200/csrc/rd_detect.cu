@@ -849,6 +849,7 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
             pb.has_scale = 0;                                     // node boxes are already scaled
             pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
             pb.thr = A.thr; pb.top_k = A.top_k; pb.max_out = A.max_out; pb.flags = A.flags;
+            pb.dets = nullptr; pb.dets_dim = 0;
             const NmsSmemLayout L = nms_layout(mcap);               // recomputed here: not kept live across the loop
             kept = nms_process(smem, L, pb, sink);
         }
@@ -862,16 +863,6 @@ __global__ void make_keys_kernel(const float* __restrict__ scores, int n, unsign
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) keys[i] = make_key(scores[i], (uint32_t)i);
 }
-// rd_nms_host: rows [n, dim] already sorted by score descending -> boxes + keys whose order follows the row order
-__global__ void strip_boxes_kernel(const float* __restrict__ dets, int n, int dim, float4* boxes,
-                                   unsigned long long* keys) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    boxes[i] = make_float4(dets[(size_t)i * dim], dets[(size_t)i * dim + 1], dets[(size_t)i * dim + 2],
-                           dets[(size_t)i * dim + 3]);
-    keys[i] = ((unsigned long long)(0xffffffffu - (uint32_t)i) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
-}
-
 __global__ void __launch_bounds__(kLargeThreads)
 nms_single_kernel(const unsigned long long* cand, int n, const float4* boxes, float thr, int top_k, int max_out,
                   int flags, int mcap, long long* keep_out, int* keep_out32, int* count_out) {
@@ -882,8 +873,30 @@ nms_single_kernel(const unsigned long long* cand, int n, const float4* boxes, fl
     pb.boxes = boxes; pb.has_scale = 0;
     pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
     pb.thr = thr; pb.top_k = top_k; pb.max_out = max_out; pb.flags = flags;
+    pb.dets = nullptr; pb.dets_dim = 0;
     RowSink sink;
     sink.rows = nullptr; sink.anchors = nullptr; sink.keep64 = keep_out; sink.keep32 = keep_out32; sink.row_layout = 0;
+    sink.idx_map = nullptr;
+    const int kept = nms_process(smem, L, pb, sink);
+    if (threadIdx.x == 0) *count_out = kept;
+}
+
+// rd_nms_host: `io` is the call's pinned, mapped host buffer  [n*dim floats, padded to 16 B | count | keep[n]] --
+// the rows (already score-descending, the contract of _nms) are read and the kept positions written straight
+// over PCIe, so the whole call is one launch + one stream synchronisation
+constexpr int kHostThreads = 1024;      // one CTA owns the SM: the walk is issue-bound, more warps hide its latencies
+__global__ void __launch_bounds__(kHostThreads)
+nms_host_kernel(const float* dets, int n, int dim, float thr, int flags, int* count_out, int* keep_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const NmsSmemLayout L = nms_layout(n);
+    NmsProblem pb;
+    pb.cl.base = nullptr; pb.cl.n = n;
+    pb.boxes = nullptr; pb.has_scale = 0;
+    pb.scale = make_float4(1.f, 1.f, 1.f, 1.f);
+    pb.thr = thr; pb.top_k = n; pb.max_out = n; pb.flags = flags;
+    pb.dets = dets; pb.dets_dim = dim;
+    RowSink sink;
+    sink.rows = nullptr; sink.anchors = nullptr; sink.keep64 = nullptr; sink.keep32 = keep_out; sink.row_layout = 0;
     sink.idx_map = nullptr;
     const int kept = nms_process(smem, L, pb, sink);
     if (threadIdx.x == 0) *count_out = kept;
@@ -1270,44 +1283,49 @@ int rd_nms_host_ex(int* keep_out_host, int* num_out_host, const float* boxes_hos
     if (e != cudaSuccess) return (int)e;
     const int n = boxes_num;
     const size_t b_dets = align_up((size_t)n * boxes_dim * 4, 256);
-    const size_t b_box = align_up((size_t)n * 16, 256);
-    const size_t b_keys = align_up((size_t)n * 8, 256);
-    const size_t b_keep = align_up((size_t)n * 4, 256);
-    const size_t need = b_dets + b_box + b_keys + b_keep + 256;
-    // grow-only device scratch per device (the reference malloc'd and freed per call, nms_kernel.cu:100-108,
-    // 142-143: two driver round trips that cost more than the NMS itself); the call is synchronous, so the
-    // lock is simply held for its duration
-    static struct { unsigned char* ptr; size_t bytes; } s_scratch[kMaxDevices];
+    const size_t need = b_dets + 256 + align_up((size_t)n * 4, 256);
+    // grow-only pinned + mapped staging buffer per device (the reference malloc'd and freed device scratch per
+    // call, nms_kernel.cu:100-108,142-143: driver round trips that cost more than the NMS itself).  The kernel
+    // reads the rows and writes the result through the mapping, so there is no copy call at all; the call is
+    // synchronous, so the lock is simply held for its duration
+    static struct { unsigned char* ptr; size_t bytes; cudaStream_t st; } s_stage[kMaxDevices];
     static std::mutex s_mu;
     std::lock_guard<std::mutex> lock(s_mu);
-    auto& sc = s_scratch[(unsigned)device_id % kMaxDevices];
+    auto& sc = s_stage[(unsigned)device_id % kMaxDevices];
     if (sc.bytes < need) {
-        if (sc.ptr) cudaFree(sc.ptr);
+        if (sc.ptr) cudaFreeHost(sc.ptr);
         sc.ptr = nullptr; sc.bytes = 0;
-        const size_t grow = need < (1u << 20) ? (1u << 20) : need;
-        e = cudaMalloc(&sc.ptr, grow);
+        const size_t grow = need < (256u << 10) ? (256u << 10) : need;
+        e = cudaHostAlloc((void**)&sc.ptr, grow, cudaHostAllocMapped | cudaHostAllocPortable);
         if (e != cudaSuccess) return (int)e;
         sc.bytes = grow;
     }
-    unsigned char* d = sc.ptr;
-    float* d_dets = (float*)d;
-    float4* d_box = (float4*)(d + b_dets);
-    unsigned long long* d_keys = (unsigned long long*)(d + b_dets + b_box);
-    int* d_keep = (int*)(d + b_dets + b_box + b_keys);
-    int* d_cnt = (int*)(d + b_dets + b_box + b_keys + b_keep);
-    cudaStream_t st = 0;
-    e = cudaMemcpyAsync(d_dets, boxes_host, (size_t)n * boxes_dim * 4, cudaMemcpyHostToDevice, st);
+    float* h_dets = (float*)sc.ptr;
+    int* h_cnt = (int*)(sc.ptr + b_dets);
+    int* h_keep = (int*)(sc.ptr + b_dets + 256);
+    unsigned char* dptr = nullptr;
+    e = cudaHostGetDevicePointer((void**)&dptr, sc.ptr, 0);
     if (e != cudaSuccess) return (int)e;
-    strip_boxes_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_dets, n, boxes_dim, d_box, d_keys);
-    note_launch();
-    int rc = launch_single(d_keys, n, d_box, nms_overlap_thresh, n, nms_flags, nullptr, d_keep, d_cnt, st);
-    if (rc == 0) {
-        e = cudaMemcpyAsync(num_out_host, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(keep_out_host, d_keep, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        rc = (int)e;
+    memcpy(h_dets, boxes_host, (size_t)n * boxes_dim * 4);
+    const NmsSmemLayout L = nms_layout(n);
+    static size_t s_host_smem[kMaxDevices];
+    e = ensure_dynamic_smem(nms_host_kernel, L.total, s_host_smem);
+    if (e != cudaSuccess) return (int)e;
+    if (!sc.st) {     // private stream: no implicit ordering against the caller's other streams (the data is host data)
+        e = cudaStreamCreateWithFlags(&sc.st, cudaStreamNonBlocking);
+        if (e != cudaSuccess) return (int)e;
     }
-    return rc;
+    cudaStream_t st = sc.st;
+    nms_host_kernel<<<1, kHostThreads, L.total, st>>>((const float*)dptr, n, boxes_dim, nms_overlap_thresh, nms_flags,
+                                                       (int*)(dptr + b_dets), (int*)(dptr + b_dets + 256));
+    note_launch();
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return (int)e;
+    const int kept = *h_cnt;
+    *num_out_host = kept;
+    memcpy(keep_out_host, h_keep, (size_t)kept * 4);
+    return 0;
 }
 
 int rd_nms_host(int* keep_out_host, int* num_out_host, const float* boxes_host, int boxes_num, int boxes_dim,

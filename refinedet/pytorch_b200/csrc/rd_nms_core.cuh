@@ -47,6 +47,11 @@ struct NmsProblem {
     int top_k;
     int max_out;
     int flags;
+    // alternative source (rd_nms_host): n rows [x1,y1,x2,y2,score,...] of dets_dim floats, ALREADY in
+    // score-descending order (the contract of _nms, utils/nms/gpu_nms.pyx:26-29), 16-byte aligned; when
+    // set, cl/boxes are unused, nothing is selected or sorted and the key index of a row is its position
+    const float* dets;
+    int dets_dim;
 };
 
 struct RowSink {           // where rows are written
@@ -365,7 +370,9 @@ __device__ inline int cta_nms_graph(SmallSmem<kCap>& S, int m, int N, int max_ou
 // =========================================================================================
 // large problems: one CTA (any multiple of 32 threads), n arbitrary, m = min(n, top_k) <= mcap
 // =========================================================================================
-constexpr int kLargePairCap = 2048;        // flattened (candidate, kept box) pairs per 32-candidate step
+constexpr int kLargePairCap = 2048;        // pair-list words of a CTA, split evenly between its warps
+constexpr int kChunkBlocks = 8;            // the greedy walk settles up to 8 x 32 candidates per CTA-wide step
+constexpr int kTinStride = kChunkBlocks + 1;   // odd row stride of the in-chunk suppressor masks
 
 struct NmsSmemLayout {
     int mcap;   // max boxes held (multiple of 32)
@@ -400,7 +407,7 @@ __host__ __device__ inline NmsSmemLayout nms_layout(int mcap_req) {
     L.off_keptbits = o;  o += (size_t)L.W * 4;
     L.off_hist = o;      o += 256 * 4;
     L.off_misc = o;      o += 16 * 4;
-    L.off_tin = o;       o += 32 * 4;
+    L.off_tin = o;       o += (size_t)(kChunkBlocks * 32 * kTinStride + kChunkBlocks) * 4;
     L.off_pairs = o;     o += (size_t)kLargePairCap * 4;
     L.total = (o + 15) & ~(size_t)15;
     return L;
@@ -431,9 +438,13 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
     const int top_k = pb.top_k < L.mcap ? pb.top_k : L.mcap;
     const int m = n < top_k ? n : top_k;
     if (m <= 0) return 0;
+    const bool presorted = pb.dets != nullptr;
 
     // ---- 1. load or select the m highest keys --------------------------------------------------
-    if (n <= top_k) {
+    if (presorted) {
+        for (int i = tid; i < m; i += nthr)
+            keys[i] = ((unsigned long long)(0xffffffffu - (uint32_t)i) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+    } else if (n <= top_k) {
         for (int i = tid; i < n; i += nthr) keys[i] = cl.base[i];
     } else {
         unsigned long long prefix = 0;   // known high bits of the threshold key
@@ -494,7 +505,7 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
             }
         }
     }
-    const int Kp = next_pow2(m);
+    const int Kp = presorted ? 0 : next_pow2(m);
     for (int i = m + tid; i < Kp; i += nthr) keys[i] = 0ull;
     __syncthreads();
 
@@ -517,12 +528,32 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
     if (tid == 0) misc[8] = 0;
     __syncthreads();
     const bool pixel = (pb.flags & RD_NMS_PIXEL_PLUS1) != 0;
+    if (presorted) {
+        // the rows as one flat array, 16 bytes per load (the buffer may be host memory read over PCIe)
+        const int dim = pb.dets_dim, total = m * dim;
+        const float4* src = reinterpret_cast<const float4*>(pb.dets);
+        for (int e4 = tid; e4 * 4 < total; e4 += nthr) {
+            const float4 v = src[e4];
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int e = e4 * 4 + q, row = e / dim, col = e - row * dim;
+                if (e < total && col < 4) (col == 0 ? sx1 : col == 1 ? sy1 : col == 2 ? sx2 : sy2)[row] = vv[q];
+            }
+        }
+        __syncthreads();
+    }
     {
         uint32_t mnx = 0xffffffffu, mxx = 0, mny = 0xffffffffu, mxy = 0;
         for (int i = tid; i < m; i += nthr) {
-            float4 b = pb.boxes[key_index(keys[i])];
-            if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
-            sx1[i] = b.x; sy1[i] = b.y; sx2[i] = b.z; sy2[i] = b.w;
+            float4 b;
+            if (presorted) {
+                b = make_float4(sx1[i], sy1[i], sx2[i], sy2[i]);
+            } else {
+                b = pb.boxes[key_index(keys[i])];
+                if (pb.has_scale) { b.x *= pb.scale.x; b.y *= pb.scale.y; b.z *= pb.scale.z; b.w *= pb.scale.w; }
+                sx1[i] = b.x; sy1[i] = b.y; sx2[i] = b.z; sy2[i] = b.w;
+            }
             const float cx = 0.5f * b.x + 0.5f * b.z, cy = 0.5f * b.y + 0.5f * b.w;
             if (isfinite(cx)) { mnx = min(mnx, float_to_ordered(cx)); mxx = max(mxx, float_to_ordered(cx)); }
             if (isfinite(cy)) { mny = min(mny, float_to_ordered(cy)); mxy = max(mxy, float_to_ordered(cy)); }
@@ -567,17 +598,19 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
     }
     __syncthreads();
 
-    // ---- 5. greedy walk, 32 candidates per step.  (a) ALL warps enumerate the (candidate, kept earlier box)
-    //         pairs that survive the bin cull -- warp q takes the mask words q, q + nwarps, ... <= ib, lane =
-    //         candidate of the step, a contiguous span of the pair list is reserved per warp with one shared
-    //         atomic (the order of the list is irrelevant: results are ORed); (b) all threads test the listed
-    //         pairs exactly; (c) warp 0 settles the 32 candidates in score order and emits the kept rows ------
+    // ---- 5. greedy walk in chunks of up to kChunkBlocks x 32 candidates.
+    //   (a) every warp takes items (mask word w, block bl of the chunk): lane = candidate of the block, the
+    //       candidates' bin-surviving partners in word w -- KEPT boxes for words before the chunk, every
+    //       earlier candidate inside it -- are flattened into the warp's own pair list and tested exactly by
+    //       all 32 lanes (no CTA barrier inside a chunk; a box that overlaps many others does not serialise
+    //       its lane).  A hit of a kept box kills the candidate; a hit inside the chunk sets a bit of its
+    //       in-chunk suppressor mask tin[candidate][word];
+    //   (b) warp 0 settles the blocks of the chunk in score order from those masks and emits the kept rows.
     uint32_t* pairs = reinterpret_cast<uint32_t*>(smem + L.off_pairs);
     uint32_t* s_tin = reinterpret_cast<uint32_t*>(smem + L.off_tin);
-    // misc: 9 sup word, 10 pairs reserved, 11 stop, 12 end of the valid part of the list
-    if (tid < 32) s_tin[tid] = 0;
-    if (tid == 0) { misc[9] = 0; misc[10] = 0; misc[11] = 0; misc[12] = (uint32_t)kLargePairCap; }
-    __syncthreads();
+    uint32_t* s_dead = s_tin + kChunkBlocks * 32 * kTinStride;
+    // misc: 8 kept count, 11 stop
+    if (tid == 0) misc[11] = 0;
     const float thr = pb.thr;
     const int flags = pb.flags;
     const int max_out = pb.max_out;
@@ -587,100 +620,117 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
     const uint32_t* Ey = tab + 3 * kCols * L.WS;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int nwarps = nthr >> 5;
-    int kept_total = 0;                                   // meaningful in warp 0
-    for (int ib = 0; ib < Wm; ++ib) {
-        const int j = ib * 32 + lane;
-        const bool valid = j < m;
-        float x1 = 0, y1 = 0, x2 = 0, y2 = 0;
-        if (warp <= ib) {                                 // warp-uniform; lanes past m carry empty masks
-            uint32_t cr = 0;
-            if (valid) { cr = scr[j]; x1 = sx1[j]; y1 = sy1[j]; x2 = sx2[j]; y2 = sy2[j]; }
-            const uint32_t* rSx = Sx + ((cr >> 8) & 255u) * L.WS;    // S_x[b_j]
-            const uint32_t* rEx = Ex + (cr & 255u) * L.WS;           // E_x[a_j]
-            const uint32_t* rSy = Sy + ((cr >> 24) & 255u) * L.WS;   // S_y[b_j]
-            const uint32_t* rEy = Ey + ((cr >> 16) & 255u) * L.WS;   // E_y[a_j]
-            for (int w = warp; w <= ib; w += nwarps) {
-                uint32_t h = rSx[w] & ~rEx[w] & rSy[w] & ~rEy[w] & (w < ib ? keptbits[w] : lt_mask);
-                if (!valid) h = 0u;
-                if (!__ballot_sync(kFullMask, h != 0u)) continue;
-                const int nh = __popc(h);
-                int off = nh;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, off, d); if (lane >= d) off += o; }
-                const int wtot = __shfl_sync(kFullMask, off, 31);
-                off -= nh;
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&misc[10], (uint32_t)wtot);
-                base = __shfl_sync(kFullMask, base, 0);
-                if (base + (uint32_t)wtot <= (uint32_t)kLargePairCap) {
-                    off += (int)base;
-                    while (h) {
-                        const int i = (w << 5) + __ffs(h) - 1;
-                        h &= h - 1;
-                        pairs[off++] = ((uint32_t)lane << 16) | (uint32_t)i;
-                    }
-                } else {                                  // the list is full: test in place
-                    if (lane == 0) atomicMin(&misc[12], base);
-                    uint32_t tin = 0;
-                    bool sup = false;
-                    while (h) {
-                        const int i = (w << 5) + __ffs(h) - 1;
-                        h &= h - 1;
-                        if (suppresses(sx1[i], sy1[i], sx2[i], sy2[i], x1, y1, x2, y2, thr, flags)) {
-                            if (w < ib) sup = true; else tin |= 1u << (i - ib * 32);
-                        }
-                    }
-                    if (sup) atomicOr(&misc[9], 1u << lane);
-                    if (tin) atomicOr(&s_tin[lane], tin);
-                }
-            }
+    const int pw_cap = kLargePairCap / nwarps;
+    uint32_t* pw = pairs + warp * pw_cap;
+    int kept_total = 0;                                   // uniform over the CTA (read back from misc[8])
+    for (int cb = 0; cb < Wm;) {
+        int nb = Wm - cb;
+        if (nb > kChunkBlocks) nb = kChunkBlocks;
+        {   // rarely more than room + a few candidates are needed
+            const int want = ((max_out - kept_total + 31) >> 5) + 1;
+            if (nb > want) nb = want;
         }
+        for (int i = tid; i < nb * 32 * kTinStride; i += nthr) s_tin[i] = 0;
+        if (tid < kChunkBlocks) s_dead[tid] = 0;
         __syncthreads();
-        {
-            const int total = (int)min(misc[10], misc[12]);
-            for (int p = tid; p < total; p += nthr) {
-                const uint32_t e = pairs[p];
-                const int jl = (int)(e >> 16), i = (int)(e & 0xffffu);
-                const int jj = ib * 32 + jl;
-                if (suppresses(sx1[i], sy1[i], sx2[i], sy2[i], sx1[jj], sy1[jj], sx2[jj], sy2[jj], thr, flags)) {
-                    if (i < ib * 32) atomicOr(&misc[9], 1u << jl);
-                    else atomicOr(&s_tin[jl], 1u << (i - ib * 32));
+        for (int it = warp; it < (cb + nb) * kChunkBlocks; it += nwarps) {
+            const int w = it / kChunkBlocks, bl = it - w * kChunkBlocks;
+            if (bl >= nb || w > cb + bl) continue;
+            const int jb = (cb + bl) * 32;
+            const int j = jb + lane;
+            uint32_t h = 0;
+            if (j < m) {
+                const uint32_t cr = scr[j];
+                h = Sx[((cr >> 8) & 255u) * L.WS + w] & ~Ex[(cr & 255u) * L.WS + w] &
+                    Sy[((cr >> 24) & 255u) * L.WS + w] & ~Ey[((cr >> 16) & 255u) * L.WS + w] &
+                    (w < cb ? keptbits[w] : (w < cb + bl ? 0xffffffffu : lt_mask));
+            }
+            if (!__ballot_sync(kFullMask, h != 0u)) continue;
+            const bool early = w < cb;
+            uint32_t* trow = s_tin + (bl * 32) * kTinStride + (w - cb);
+            const int nh = __popc(h);
+            int off = nh;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(kFullMask, off, d); if (lane >= d) off += o; }
+            const int wtot = __shfl_sync(kFullMask, off, 31);
+            off -= nh;
+            if (wtot <= pw_cap) {
+                while (h) {
+                    const int i = (w << 5) + __ffs(h) - 1;
+                    h &= h - 1;
+                    pw[off++] = ((uint32_t)lane << 16) | (uint32_t)i;
+                }
+                __syncwarp();
+                for (int p = lane; p < wtot; p += 32) {
+                    const uint32_t e = pw[p];
+                    const int jl = (int)(e >> 16), i = (int)(e & 0xffffu);
+                    const int jj = jb + jl;
+                    if (suppresses(sx1[i], sy1[i], sx2[i], sy2[i], sx1[jj], sy1[jj], sx2[jj], sy2[jj], thr, flags)) {
+                        if (early) atomicOr(&s_dead[bl], 1u << jl);
+                        else atomicOr(&trow[jl * kTinStride], 1u << (i & 31));
+                    }
+                }
+                __syncwarp();
+            } else {                                      // more pairs than the warp's list holds: test in place
+                const float x1 = sx1[j < m ? j : 0], y1 = sy1[j < m ? j : 0], x2 = sx2[j < m ? j : 0], y2 = sy2[j < m ? j : 0];
+                uint32_t hit = 0;
+                while (h) {
+                    const int i = (w << 5) + __ffs(h) - 1;
+                    h &= h - 1;
+                    if (suppresses(sx1[i], sy1[i], sx2[i], sy2[i], x1, y1, x2, y2, thr, flags)) hit |= 1u << (i & 31);
+                }
+                if (hit) {
+                    if (early) atomicOr(&s_dead[bl], 1u << lane);
+                    else atomicOr(&trow[lane * kTinStride], hit);
                 }
             }
         }
         __syncthreads();
         if (warp == 0) {
-            bool alive = valid && !((misc[9] >> lane) & 1u);
-            const uint32_t tin = s_tin[lane];
-            __syncwarp();
-            s_tin[lane] = 0;
-            if (lane == 0) { misc[9] = 0; misc[10] = 0; misc[12] = (uint32_t)kLargePairCap; }
-            uint32_t u = __reduce_or_sync(kFullMask, alive ? tin : 0u);   // in-block resolution in score order
-            while (u) {
-                const int k = __ffs(u) - 1;
-                u &= u - 1;
-                const uint32_t al = __ballot_sync(kFullMask, alive);
-                if (((al >> k) & 1u) && ((tin >> k) & 1u)) alive = false;
+            uint32_t kw[kChunkBlocks];                    // kept words of this chunk (uniform)
+#pragma unroll
+            for (int bl = 0; bl < kChunkBlocks; ++bl) {
+                kw[bl] = 0;
+                if (bl < nb && kept_total < max_out) {
+                    const int j = (cb + bl) * 32 + lane;
+                    const uint32_t* trow = s_tin + (bl * 32 + lane) * kTinStride;
+                    bool alive = j < m && !((s_dead[bl] >> lane) & 1u);
+#pragma unroll
+                    for (int q = 0; q < kChunkBlocks; ++q)
+                        if (q < bl && (trow[q] & kw[q])) alive = false;
+                    const uint32_t tin = trow[bl];
+                    uint32_t u = __reduce_or_sync(kFullMask, alive ? tin : 0u);   // in-block resolution in score order
+                    while (u) {
+                        const int k = __ffs(u) - 1;
+                        u &= u - 1;
+                        const uint32_t al = __ballot_sync(kFullMask, alive);
+                        if (((al >> k) & 1u) && ((tin >> k) & 1u)) alive = false;
+                    }
+                    uint32_t keptw = __ballot_sync(kFullMask, alive);
+                    const int room = max_out - kept_total;
+                    int cnt = __popc(keptw);
+                    if (cnt > room) {   // keep only the first `room` set bits
+                        uint32_t t = keptw, keep = 0;
+                        for (int r = 0; r < room; ++r) { const uint32_t low = t & (0u - t); keep |= low; t ^= low; }
+                        keptw = keep;
+                        cnt = room;
+                    }
+                    if ((keptw >> lane) & 1u)
+                        sink_emit(sink, kept_total + __popc(keptw & lt_mask), keys[j], sx1[j], sy1[j], sx2[j], sy2[j]);
+                    kept_total += cnt;
+                    kw[bl] = keptw;
+                    if (lane == 0) keptbits[cb + bl] = keptw;
+                }
             }
-            uint32_t keptw = __ballot_sync(kFullMask, alive);
-            const int room = max_out - kept_total;
-            int cnt = __popc(keptw);
-            if (cnt > room) {   // keep only the first `room` set bits
-                uint32_t t = keptw, keep = 0;
-                for (int r = 0; r < room; ++r) { const uint32_t low = t & (0u - t); keep |= low; t ^= low; }
-                keptw = keep;
-                cnt = room;
-            }
-            if ((keptw >> lane) & 1u) sink_emit(sink, kept_total + __popc(keptw & lt_mask), keys[j], x1, y1, x2, y2);
-            kept_total += cnt;
             if (lane == 0) {
-                keptbits[ib] = keptw;
                 misc[8] = (uint32_t)kept_total;
                 if (kept_total >= max_out) misc[11] = 1;
             }
         }
         __syncthreads();
+        kept_total = (int)misc[8];
         if (misc[11]) break;
+        cb += nb;
     }
     return (int)misc[8];
 }

@@ -73,3 +73,15 @@ def test_priorbox_matches_reference_layout(golden):
     for size in ('320', '512'):
         p = PriorBox(REFINEDET_ANCHORS[size]).forward().numpy()
         assert hashlib.sha256(p.tobytes()).hexdigest() == str(g['sha' + size])
+
+
+def test_reference_gpu_nms_checker_loads():
+    """oracle/_ref (the reference's own nms_kernel.cu, built unmodified by oracle/build_ref.py) loads
+    and exports ``_nms`` under its C++ name; no compute without a GPU."""
+    import ctypes
+    from oracle import build_ref, ref_nms
+    path = build_ref.build_ref()
+    if path is None:
+        pytest.skip('no reference checkout / nvcc and no prebuilt oracle/_ref')
+    assert path == ref_nms.LIB
+    assert hasattr(ctypes.CDLL(path), ref_nms._SYMBOL)
