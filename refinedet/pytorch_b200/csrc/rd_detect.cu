@@ -58,7 +58,8 @@ constexpr int kLargeThreads = RD_LARGE_THREADS;
 //   nbox   f4  [B][P], nanc int [B][P] : node box (scaled) / anchor
 //   ncr    u32 [B][4096]          : bin range of the first 4096 nodes
 //   adjn   int [B][4096]          : graph degree of every node (collect zeroes, graph counts)
-//   adj    u16 [B][4096][8]       : adjacency lists (node indices)
+//   adj    u16 [B][4096][8]       : adjacency lists (node indices), suppressors 0 .. 7
+//   adj2   u16 [B][4096][24]      : suppressors 8 .. 31 of the nodes that have them
 //   cand   u64 [B*C][P]           : candidate keys of the problems nms_large_kernel handles
 // ---------------------------------------------------------------------------------------
 constexpr int kBlockNodes = 1024;       // suppressor nodes graph_kernel holds in shared memory at a time
@@ -79,6 +80,7 @@ struct DetectWs {
     uint32_t* ncr;
     int* adjn;
     uint4* adj;
+    unsigned short* adj2;
     unsigned long long* cand;
     int S, Pn;
     size_t ctrl_bytes;
@@ -103,6 +105,7 @@ static DetectWs carve_ws(void* base, int B, int P, int C) {
     w.ncr = reinterpret_cast<uint32_t*>(p + o);                o += align_up((size_t)B * kGraphNodes * 4, 256);
     w.adjn = reinterpret_cast<int*>(p + o);                    o += align_up((size_t)B * kGraphNodes * 4, 256);
     w.adj = reinterpret_cast<uint4*>(p + o);                   o += align_up((size_t)B * kGraphNodes * 16, 256);
+    w.adj2 = reinterpret_cast<unsigned short*>(p + o);         o += align_up((size_t)B * kGraphNodes * kAdjDeg2 * 2, 256);
     w.cand = reinterpret_cast<unsigned long long*>(p + o);     o += align_up((size_t)B * C * P * 8, 256);
     w.total = o;
     return w;
@@ -450,16 +453,19 @@ struct GraphSmem {
 };
 
 __device__ __forceinline__ void graph_add_edge(int* __restrict__ adjn, unsigned short* __restrict__ adj,
-                                               int to, int from, int* overflow) {
+                                               unsigned short* __restrict__ adj2, int to, int from, int* overflow) {
     const int slot = atomicAdd(&adjn[to], 1);
     if (slot < kAdjDeg) adj[to * kAdjDeg + slot] = (unsigned short)from;
-    else *overflow = 1;
+    else if (slot < kAdjMax) {
+        adj2[to * kAdjDeg2 + slot - kAdjDeg] = (unsigned short)from;
+        if (slot == kAdjDeg) atomicOr(overflow, kFlagWideDeg);
+    } else if (slot == kAdjMax) atomicOr(overflow, kFlagNoGraph);
 }
 
 // exact test of the unordered pair (block node i, own node n0 + jl), both directions
 __device__ __forceinline__ void graph_test_pair_inline(GraphSmem& G, int i, int jl, int nb, const float4* __restrict__ boxes_n0,
                                                        float thr, int flags, int* __restrict__ adjn,
-                                                       unsigned short* __restrict__ adj, int n0) {
+                                                       unsigned short* __restrict__ adj, unsigned short* __restrict__ adj2, int n0) {
     float4 bj;
     if (jl < nb) bj = make_float4(G.x1[jl], G.y1[jl], G.x2[jl], G.y2[jl]);
     else bj = __ldg(boxes_n0 + jl);
@@ -468,14 +474,14 @@ __device__ __forceinline__ void graph_test_pair_inline(GraphSmem& G, int i, int 
     const bool j_sup_i = (flags & RD_NMS_PIXEL_PLUS1)
                              ? i_sup_j
                              : suppresses(bj.x, bj.y, bj.z, bj.w, G.x1[i], G.y1[i], G.x2[i], G.y2[i], thr, flags);
-    if (i_sup_j) graph_add_edge(adjn, adj, n0 + jl, n0 + i, &G.overflow);
-    if (j_sup_i) graph_add_edge(adjn, adj, n0 + i, n0 + jl, &G.overflow);
+    if (i_sup_j) graph_add_edge(adjn, adj, adj2, n0 + jl, n0 + i, &G.overflow);
+    if (j_sup_i) graph_add_edge(adjn, adj, adj2, n0 + i, n0 + jl, &G.overflow);
 }
 // out-of-line twin for the (rare) pairs found after the list has filled up: keeps the listing loop lean
 __device__ __noinline__ void graph_test_pair(GraphSmem& G, int i, int jl, int nb, const float4* __restrict__ boxes_n0,
                                              float thr, int flags, int* __restrict__ adjn,
-                                             unsigned short* __restrict__ adj, int n0) {
-    graph_test_pair_inline(G, i, jl, nb, boxes_n0, thr, flags, adjn, adj, n0);
+                                             unsigned short* __restrict__ adj, unsigned short* __restrict__ adj2, int n0) {
+    graph_test_pair_inline(G, i, jl, nb, boxes_n0, thr, flags, adjn, adj, adj2, n0);
 }
 
 // the block loop of graph_kernel.  kSingle: the image has at most kBlockNodes nodes (the common case) — one
@@ -484,9 +490,10 @@ template <bool kSingle>
 __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, int tid, const uint32_t* __restrict__ gtab,
                                             const float4* __restrict__ nbox, const uint32_t* __restrict__ ncr, int P,
                                             float thr, int flags, uint4* __restrict__ adj_all,
-                                            int* __restrict__ adjn_all) {
+                                            unsigned short* __restrict__ adj2_all, int* __restrict__ adjn_all) {
     int* adjn = adjn_all + (size_t)b * kGraphNodes;
     unsigned short* adj = reinterpret_cast<unsigned short*>(adj_all + (size_t)b * kGraphNodes);
+    unsigned short* adj2 = adj2_all + (size_t)b * kGraphNodes * kAdjDeg2;
     const float4* boxes = nbox + (size_t)b * P;
     const uint32_t* crs = ncr + (size_t)b * kGraphNodes;
     const uint32_t* gt = gtab + (size_t)b * kGtabWords;
@@ -562,7 +569,7 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
                 const int i = (w << 5) + __ffs(h) - 1;
                 h &= h - 1;
                 if (off < kGraphPairCap) G.pairs[off] = tag | (uint32_t)i;
-                else graph_test_pair(G, i, g + jo * kGraphSplit, kSingle ? kBlockNodes : nb, boxes + n0, thr, flags, adjn, adj, n0);
+                else graph_test_pair(G, i, g + jo * kGraphSplit, kSingle ? kBlockNodes : nb, boxes + n0, thr, flags, adjn, adj, adj2, n0);
                 ++off;
             }
         }
@@ -572,7 +579,7 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
         for (int p = tid; p < cnt; p += kGraphThreads) {
             const uint32_t e = G.pairs[p];
             graph_test_pair_inline(G, (int)(e & 0xffffu), g + (int)(e >> 16) * kGraphSplit, kSingle ? kBlockNodes : nb,
-                                   boxes + n0, thr, flags, adjn, adj, n0);
+                                   boxes + n0, thr, flags, adjn, adj, adj2, n0);
         }
     }
 }
@@ -580,7 +587,8 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
 __global__ void __launch_bounds__(kGraphThreads)
 graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, const float4* __restrict__ nbox,
              const uint32_t* __restrict__ ncr, int P, float thr, int flags,
-             uint4* __restrict__ adj_all, int* __restrict__ adjn_all, int* __restrict__ img_flag) {
+             uint4* __restrict__ adj_all, unsigned short* __restrict__ adj2_all, int* __restrict__ adjn_all,
+             int* __restrict__ img_flag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GraphSmem& G = *reinterpret_cast<GraphSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -589,16 +597,16 @@ graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, 
     grid_launch_dependents();        // nms_small_kernel's scan + sort (graph independent) may run beside this kernel
     const int N = nnodes[b];
     if (N > kGraphNodes) {
-        if (g == 0 && tid == 0) img_flag[b] = 1;
+        if (g == 0 && tid == 0) img_flag[b] = kFlagNoGraph;
         return;
     }
     // own nodes: j = g, g + kGraphSplit, ... (interleaved, so the few large boxes that overlap hundreds
     // of others, and the later nodes that have more predecessors, are spread over the CTAs of the image)
     if (N <= g) return;
-    if (N <= kBlockNodes) graph_image<true>(G, N, g, b, tid, gtab, nbox, ncr, P, thr, flags, adj_all, adjn_all);
-    else graph_image<false>(G, N, g, b, tid, gtab, nbox, ncr, P, thr, flags, adj_all, adjn_all);
+    if (N <= kBlockNodes) graph_image<true>(G, N, g, b, tid, gtab, nbox, ncr, P, thr, flags, adj_all, adj2_all, adjn_all);
+    else graph_image<false>(G, N, g, b, tid, gtab, nbox, ncr, P, thr, flags, adj_all, adj2_all, adjn_all);
     __syncthreads();
-    if (tid == 0 && G.overflow) img_flag[b] = 1;
+    if (tid == 0 && G.overflow) atomicOr(&img_flag[b], G.overflow);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -610,8 +618,9 @@ struct FusedNmsArgs {
     const int* nanc;                 // [B][P] node anchors
     const int* nnodes;               // [B]
     uint32_t* gtab;                  // [B][kGtabWords]   control block, cleared by the class-0 CTA of every image
-    const int* img_flag;             // [B] 1 = no graph for this image
+    const int* img_flag;             // [B] kFlagNoGraph | kFlagWideDeg
     const uint4* adj;                // [B][kGraphNodes]
+    const unsigned short* adj2;      // [B][kGraphNodes][kAdjDeg2]
     const int* adjn;                 // [B][kGraphNodes]
     int* queue;
     uint32_t* header;
@@ -737,7 +746,8 @@ nms_small_kernel(FusedNmsArgs A) {
     }
     cta_sort_small<kThreads, kCap>(S, n);
     grid_dependency_wait();                                       // graph_kernel has completed
-    if (A.img_flag[b] != 0) {                                     // degree / pair overflow: no graph after all
+    const int fl = A.img_flag[b];                                 // degree overflow: no graph (for this variant) after all
+    if ((fl & kFlagNoGraph) || ((fl & kFlagWideDeg) && !SmallSmem<kCap>::kBitRows)) {
         if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
         return;
     }
@@ -748,10 +758,11 @@ nms_small_kernel(FusedNmsArgs A) {
     sink.row_layout = A.row_layout;
     GraphView G;
     G.adj = A.adj + (size_t)b * kGraphNodes;
+    G.adj2 = A.adj2 + (size_t)b * kGraphNodes * kAdjDeg2;
     G.adjn = A.adjn + (size_t)b * kGraphNodes;
     G.nbox = A.nbox + (size_t)b * A.P;
     G.nanc = A.nanc + (size_t)b * A.P;
-    const int kept = cta_nms_graph<kThreads, kCap>(S, n, N, A.max_out, sink, G);
+    const int kept = cta_nms_graph<kThreads, kCap>(S, n, N, A.max_out, sink, G, (fl & kFlagWideDeg) != 0);
     if (tid == 0) A.out_counts[bc] = kept;
 }
 
@@ -767,7 +778,7 @@ __device__ __noinline__ int large_graph_resolve(unsigned char* smem, const unsig
     __syncthreads();
     cta_sort_small<kLargeThreads, kWideCap>(S, n);
     GraphView G;
-    G.adj = adj; G.adjn = adjn; G.nbox = nbox; G.nanc = nanc;
+    G.adj = adj; G.adj2 = nullptr; G.adjn = adjn; G.nbox = nbox; G.nanc = nanc;    // kWideCap: kDeps == kAdjDeg
     RowSink sink;
     sink.rows = rows; sink.anchors = anchors; sink.keep64 = nullptr; sink.keep32 = nullptr; sink.idx_map = nullptr;
     sink.row_layout = row_layout;
@@ -1068,7 +1079,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
         if (e != cudaSuccess) return (int)e;
         e = launch_pdl(graph_kernel, dim3(kGraphSplit, B), dim3(kGraphThreads), sizeof(GraphSmem), st,
                                    (const int*)ws.nnodes, (const uint32_t*)ws.gtab, (const float4*)ws.nbox,
-                                   (const uint32_t*)ws.ncr, P, nms_thresh, nms_flags, ws.adj, ws.adjn, ws.flag);
+                                   (const uint32_t*)ws.ncr, P, nms_thresh, nms_flags, ws.adj, ws.adj2, ws.adjn, ws.flag);
         if (e != cudaSuccess) return (int)e;
         note_launch();
         RD_CHECK_LAUNCH();
@@ -1076,7 +1087,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
 
     FusedNmsArgs A;
     A.nsc = ws.nsc; A.nbox = ws.nbox; A.nanc = ws.nanc; A.nnodes = ws.nnodes; A.gtab = ws.gtab;
-    A.img_flag = ws.flag; A.adj = ws.adj; A.adjn = ws.adjn; A.queue = ws.queue; A.header = ws.header;
+    A.img_flag = ws.flag; A.adj = ws.adj; A.adj2 = ws.adj2; A.adjn = ws.adjn; A.queue = ws.queue; A.header = ws.header;
     A.cand = ws.cand;
     A.nbc = B * C; A.C = C; A.P = P; A.Pn = ws.Pn;
     A.conf_thresh = conf_thresh;

@@ -176,22 +176,47 @@ constexpr int kWideCap = 1024;
 #define RD_GRAPH_NODES 4096
 #endif
 constexpr int kGraphNodes = RD_GRAPH_NODES;   // images with more ARM-passing anchors have no suppression graph
-constexpr int kAdjDeg = 8;            // adjacency slots per node; an image whose graph overflows is flagged dense
+constexpr int kAdjDeg = 8;            // adjacency slots in a node's primary row (one 16-byte load)
+constexpr int kAdjDeg2 = 56;          // further slots in the overflow row: real detector output puts dozens of
+                                      // mutually overlapping boxes on every object
+constexpr int kAdjMax = kAdjDeg + kAdjDeg2;   // an image with a node of higher degree has no graph (flag bit 0)
+constexpr int kFlagNoGraph = 1;       // img_flag bits: no usable graph / some node has more than kAdjDeg suppressors
+constexpr int kFlagWideDeg = 2;
 
 // kNodes = largest node index + 1 the rank table covers (images with more nodes are not handled by this instance)
+// Dependencies of a problem's candidates: lists of at most kAdjDeg ranks per candidate (every node of the image
+// has at most kAdjDeg suppressors: the common case, one 16-byte adjacency row per candidate).  For images flagged
+// kFlagWideDeg the kCap <= 256 instance (kBitRows) switches to one bit row per candidate over the EARLIER ranks
+// -- candidate r of 32-block k = r >> 5 owns k + 1 words at tri_row(r), 4.6 KB in all -- so the degree of a node
+// does not matter; wider instances leave those images to the bin path.
+__device__ __forceinline__ int tri_row(int r) {
+    const int k = r >> 5;
+    return 16 * k * (k + 1) + (r & 31) * (k + 1);
+}
 template <int kCap, int kNodes = (kCap > 256 ? RD_GRAPH_NODES : 1024)>
 struct SmallSmem {
+#ifdef RD_K2_LIST
+    static constexpr bool kBitRows = false;
+#else
+    static constexpr bool kBitRows = kCap <= 256; // false: images flagged kFlagWideDeg are not handled by this instance
+#endif
+    static constexpr int kDeps = kAdjDeg;         // list mode: ranks kept per candidate
+    static constexpr int kTriWords = 16 * (kCap / 32) * (kCap / 32 + 1);
     using rank_t = typename std::conditional<(kCap > 256), unsigned short, unsigned char>::type;
     unsigned long long keys[kCap];                // sorted keys
     union {
         unsigned long long runs[kCap];            // unsorted candidates, then sorted runs of 32 (during the sort)
         struct {
             unsigned short rank[kNodes];          // node -> rank in this problem, 0xffff = not a candidate
-            rank_t deps[kCap * kAdjDeg];          // ranks of the dependencies of every candidate
+            union {
+                rank_t deps[kCap * kDeps];                     // list mode: ranks of the dependencies of every candidate
+                unsigned int bits[kBitRows ? kTriWords : 1];   // bit-row mode (images flagged kFlagWideDeg)
+            };
         } g;
     } u;
     unsigned char depn[kCap];
     unsigned char state[kCap];                    // 0 undecided, 1 kept, 2 suppressed
+    unsigned int keptw[kCap / 32], deadw[kCap / 32];
     int wsum[32];
     int n;
     static constexpr int kMaxNodes = kNodes;
@@ -249,7 +274,8 @@ __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddep
 
 struct GraphView {
     const uint4* adj;                 // [kGraphNodes] node indices of the suppressors, 8 x u16 per node
-    const int* adjn;                  // [kGraphNodes] degree (<= kAdjDeg when the image is not flagged)
+    const unsigned short* adj2;       // [kGraphNodes][kAdjDeg2] suppressors 8 .. 31 of the nodes that have them
+    const int* adjn;                  // [kGraphNodes] degree (<= kAdjMax when the image is not flagged kFlagNoGraph)
     const float4* nbox;               // [N] node boxes, already multiplied by the image scale
     const int* nanc;                  // [N] anchor index of every node
 };
@@ -258,8 +284,9 @@ struct GraphView {
 // box and anchor of every candidate.
 template <int kThreads, int kCap>
 __device__ inline int cta_nms_graph(SmallSmem<kCap>& S, int m, int N, int max_out, const RowSink& sink,
-                                    const GraphView& G) {
+                                    const GraphView& G, bool wide_deg = false) {
     using rank_t = typename SmallSmem<kCap>::rank_t;
+    constexpr int kDeps = SmallSmem<kCap>::kDeps;
     constexpr int kSmallWarps = kThreads / 32;
     constexpr int kPerT = (kCap + kThreads - 1) / kThreads;
     const int tid = threadIdx.x;
@@ -297,6 +324,83 @@ __device__ inline int cta_nms_graph(SmallSmem<kCap>& S, int m, int N, int max_ou
         if (r < m) S.u.g.rank[key_index(key[q])] = (unsigned short)r;
     }
     __syncthreads();
+    const bool bit_rows = SmallSmem<kCap>::kBitRows && wide_deg;       // CTA-uniform
+    if (bit_rows) {
+        // ---- bit rows: bit v of row r = candidate of rank v < r suppresses candidate r when kept ----------
+        constexpr int kW = kCap / 32;
+        uint32_t* bm = S.u.g.bits;
+        unsigned openm = 0;                                          // bit q: candidate q of this thread is undecided
+#pragma unroll
+        for (int q = 0; q < kPerT; ++q) {
+            const int r = q * kThreads + tid;
+            if (r < m) {
+                uint32_t* drow = bm + tri_row(r);                    // only this thread touches row r here; a row
+                // (a row exists once it has a bit)
+                const unsigned long long lo = ((unsigned long long)row[q].y << 32) | row[q].x;
+                const unsigned long long hi = ((unsigned long long)row[q].w << 32) | row[q].z;
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < kAdjDeg; ++k) {
+                    if (k < dn[q]) {
+                        const int rv = S.u.g.rank[(uint32_t)((k < 4 ? lo : hi) >> ((k & 3) * 16)) & 0xffffu];
+                        if (rv < r) {
+                            if (!any) {
+#pragma unroll
+                                for (int w = 0; w < kW; ++w) if (w <= (r >> 5)) drow[w] = 0;
+                                any = true;
+                            }
+                            drow[rv >> 5] |= 1u << (rv & 31);
+                        }
+                    }
+                }
+                if (dn[q] > kAdjDeg) {                               // overflow row (L2): suppressors 8 .. dn - 1
+                    const unsigned short* r2 = G.adj2 + (size_t)key_index(key[q]) * kAdjDeg2;
+                    for (int k = 0; k < dn[q] - kAdjDeg; ++k) {
+                        const int rv = S.u.g.rank[__ldg(r2 + k)];
+                        if (rv < r) {
+                            if (!any) {
+#pragma unroll
+                                for (int w = 0; w < kW; ++w) if (w <= (r >> 5)) drow[w] = 0;
+                                any = true;
+                            }
+                            drow[rv >> 5] |= 1u << (rv & 31);
+                        }
+                    }
+                }
+                if (any) openm |= 1u << q;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kPerT; ++q) {
+            const int r = q * kThreads + tid;
+            const unsigned free_ = __ballot_sync(kFullMask, r < m && !((openm >> q) & 1u));    // no earlier suppressor: kept
+            if (lane == 0 && (r >> 5) < kW) { S.keptw[r >> 5] = free_; S.deadw[r >> 5] = 0; }   // the warp's own word
+        }
+        __syncthreads();
+        // ---- resolve in rounds: a candidate is dead once a dependency is kept, kept once all are dead ------
+        for (int round = 0; round < kCap; ++round) {
+            int undecided = 0;
+#pragma unroll
+            for (int q = 0; q < kPerT; ++q) {
+                const int r = q * kThreads + tid;
+                if (!((openm >> q) & 1u)) continue;
+                uint32_t hit = 0, live = 0;
+                const uint32_t* drow = bm + tri_row(r);
+#pragma unroll
+                for (int w = 0; w < kW; ++w) {
+                    if (w <= (r >> 5)) {
+                        const uint32_t d = drow[w];
+                        hit |= d & S.keptw[w];
+                        live |= d & ~S.deadw[w];
+                    }
+                }
+                if (hit) { atomicOr(&S.deadw[r >> 5], 1u << (r & 31)); openm &= ~(1u << q); }
+                else if (!live) { atomicOr(&S.keptw[r >> 5], 1u << (r & 31)); openm &= ~(1u << q); }
+                else undecided = 1;
+            }
+            if (!__syncthreads_or(undecided)) break;
+        }
+    } else {
     // ---- dependencies: graph neighbours that are candidates of this class and rank earlier --------
 #pragma unroll
     for (int q = 0; q < kPerT; ++q) {
@@ -309,7 +413,7 @@ __device__ inline int cta_nms_graph(SmallSmem<kCap>& S, int m, int N, int max_ou
                 if (k < dn[q]) {
                     const uint32_t v = (nb[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
                     const int rv = S.u.g.rank[v];
-                    if (rv < r) S.u.g.deps[r * kAdjDeg + nd++] = (rank_t)rv;
+                    if (rv < r) S.u.g.deps[r * kDeps + nd++] = (rank_t)rv;
                 }
             }
             S.depn[r] = (unsigned char)nd;
@@ -327,7 +431,7 @@ __device__ inline int cta_nms_graph(SmallSmem<kCap>& S, int m, int N, int max_ou
             const int nd = S.depn[r];
             bool any_kept = false, all_sup = true;
             for (int k = 0; k < nd; ++k) {
-                const unsigned char st = S.state[S.u.g.deps[r * kAdjDeg + k]];
+                const unsigned char st = S.state[S.u.g.deps[r * kDeps + k]];
                 any_kept |= (st == 1);
                 all_sup &= (st == 2);
             }
@@ -337,12 +441,13 @@ __device__ inline int cta_nms_graph(SmallSmem<kCap>& S, int m, int N, int max_ou
         }
         if (!__syncthreads_or(undecided)) break;
     }
+    }
     // ---- emit kept rows in rank order, first max_out: scan of the kept flags chunk by chunk -----------
     int carry = 0;
 #pragma unroll
     for (int q = 0; q < kPerT; ++q) {
         const int r = q * kThreads + tid;
-        const bool kept = r < m && S.state[r] == 1;
+        const bool kept = r < m && (bit_rows ? ((S.keptw[(r >> 5) % (kCap / 32)] >> (r & 31)) & 1u) != 0 : S.state[r] == 1);
         const unsigned bal = __ballot_sync(kFullMask, kept);
         if (lane == 0) S.wsum[warp] = __popc(bal);
         __syncthreads();

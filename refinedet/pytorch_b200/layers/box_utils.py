@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 from .. import _ffi
-from .._ffi import check, lib, ptr, require_cuda_f32, stream_ptr
+from .._ffi import check, lib, on_device, ptr, require_cuda_f32, stream_ptr
 
 
 def _out_like(t, shape=None, dtype=None):
@@ -19,7 +19,7 @@ def point_form(boxes):
     """layers/box_utils.py:5-14  (cx,cy,w,h) -> (x1,y1,x2,y2)."""
     b = require_cuda_f32(boxes, 'boxes')
     out = _out_like(b)
-    with torch.cuda.device(b.device):
+    with on_device(b.device):
         check(lib().rd_point_form(ptr(b), ptr(out), b.shape[0], stream_ptr()), 'rd_point_form')
     return out
 
@@ -28,7 +28,7 @@ def center_size(boxes):
     """layers/box_utils.py:17-26  (x1,y1,x2,y2) -> (cx,cy,w,h)."""
     b = require_cuda_f32(boxes, 'boxes')
     out = _out_like(b)
-    with torch.cuda.device(b.device):
+    with on_device(b.device):
         check(lib().rd_center_size(ptr(b), ptr(out), b.shape[0], stream_ptr()), 'rd_center_size')
     return out
 
@@ -37,7 +37,7 @@ def intersect(box_a, box_b):
     """layers/box_utils.py:29-47  [A,4] x [B,4] -> [A,B] intersection areas."""
     a, b = require_cuda_f32(box_a, 'box_a'), require_cuda_f32(box_b, 'box_b')
     out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
+    with on_device(a.device):
         check(lib().rd_intersect(ptr(a), ptr(b), ptr(out), a.shape[0], b.shape[0], stream_ptr()), 'rd_intersect')
     return out
 
@@ -46,7 +46,7 @@ def jaccard(box_a, box_b):
     """layers/box_utils.py:50-68  [A,4] x [B,4] -> [A,B] IoU."""
     a, b = require_cuda_f32(box_a, 'box_a'), require_cuda_f32(box_b, 'box_b')
     out = torch.empty(a.shape[0], b.shape[0], dtype=torch.float32, device=a.device)
-    with torch.cuda.device(a.device):
+    with on_device(a.device):
         check(lib().rd_jaccard(ptr(a), ptr(b), ptr(out), a.shape[0], b.shape[0], stream_ptr()), 'rd_jaccard')
     return out
 
@@ -57,7 +57,7 @@ def encode(matched, priors, variances):
     if m.shape != p.shape:
         raise ValueError('matched %s and priors %s must have the same shape' % (tuple(m.shape), tuple(p.shape)))
     out = _out_like(m)
-    with torch.cuda.device(m.device):
+    with on_device(m.device):
         check(lib().rd_encode(ptr(m), ptr(p), float(variances[0]), float(variances[1]), ptr(out), m.shape[0],
                               stream_ptr()), 'rd_encode')
     return out
@@ -69,7 +69,7 @@ def decode(loc, priors, variances):
     if l.shape != p.shape:
         raise ValueError('loc %s and priors %s must have the same shape' % (tuple(l.shape), tuple(p.shape)))
     out = _out_like(l)
-    with torch.cuda.device(l.device):
+    with on_device(l.device):
         check(lib().rd_decode(ptr(l), ptr(p), float(variances[0]), float(variances[1]), ptr(out), l.shape[0],
                               stream_ptr()), 'rd_decode')
     return out
@@ -95,7 +95,7 @@ def conf_loss(conf, conf_t, arm_conf=None, theta=0.01):
     ce = torch.empty(conf_t.shape, dtype=torch.float32, device=conf.device)
     lse = torch.empty_like(ce)
     pos = torch.empty(conf_t.shape, dtype=torch.bool, device=conf.device)
-    with torch.cuda.device(conf.device):
+    with on_device(conf.device):
         check(lib().rd_conf_loss(ptr(conf), ptr(conf_t), ptr(arm_conf), float(theta), rows, C, ptr(ce), ptr(lse),
                                  ptr(pos), stream_ptr()), 'rd_conf_loss')
     return ce, lse, pos
@@ -146,7 +146,7 @@ def pad_targets(targets, device):
         offs = np.zeros(B + 1, dtype=np.int32)
         np.cumsum(counts, out=offs[1:])
         offsets = torch.from_numpy(offs).to(device, non_blocking=True)
-        with torch.cuda.device(truths.device):
+        with on_device(truths.device):
             check(lib().rd_pad_targets(ptr(flat), ptr(offsets), B, gmax, ptr(truths), ptr(labels), ptr(gt_count),
                                        stream_ptr()), 'rd_pad_targets')
     _PAD_CACHE = (key, (truths, labels, gt_count))
@@ -195,7 +195,7 @@ def match_batch(threshold, truths, labels, gt_count, priors, variances, arm_loc=
     L = lib()
     ws_bytes = int(L.rd_match_workspace_bytes(B, gmax))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(L.rd_refine_match(ptr(truths), ptr(labels), ptr(gt_count), ptr(priors), ptr(arm_loc), B, P, gmax,
                                 float(threshold), float(variances[0]), float(variances[1]), int(label_mode),
                                 ptr(ws), ws_bytes, ptr(loc_t), ptr(conf_t), ptr(bt_idx), ptr(bt_ov),
@@ -247,7 +247,7 @@ def hnm_select(loss_c, pos, negpos_ratio):
     B, P = loss_c.shape
     neg = torch.empty(B, P, dtype=torch.bool, device=loss_c.device)
     num_pos = torch.empty(B, dtype=torch.int32, device=loss_c.device)
-    with torch.cuda.device(loss_c.device):
+    with on_device(loss_c.device):
         check(lib().rd_hnm_select(ptr(loss_c), ptr(pos), B, P, int(negpos_ratio), ptr(neg), ptr(num_pos),
                                   stream_ptr()), 'rd_hnm_select')
     return neg, num_pos
@@ -263,7 +263,7 @@ def multibox_loss_reduce(loc_data, loc_t, ce, pos, neg, num_pos):
     L = lib()
     ws = torch.empty(int(L.rd_multibox_loss_workspace_bytes(B)), dtype=torch.uint8, device=dev)
     out = [torch.empty((), dtype=torch.float32, device=dev) for _ in range(3)]
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(L.rd_multibox_loss_reduce(ptr(loc_data), ptr(loc_t), ptr(ce), ptr(pos), ptr(neg), ptr(num_pos), B, P,
                                         ptr(ws), ws.numel(), ptr(out[0]), ptr(out[1]), ptr(out[2]), stream_ptr()),
               'rd_multibox_loss_reduce')
@@ -278,7 +278,7 @@ def multibox_loss_backward(loc_data, loc_t, conf_data, conf_t, lse, pos, neg, g_
     rows = conf_t.numel()
     grad_loc = torch.empty_like(loc_data) if need_loc else None
     grad_conf = torch.empty_like(conf_data) if need_conf else None
-    with torch.cuda.device(conf_data.device):
+    with on_device(conf_data.device):
         check(lib().rd_multibox_loss_backward(ptr(loc_data), ptr(loc_t), ptr(conf_data), ptr(conf_t), ptr(lse),
                                               ptr(pos), ptr(neg), ptr(g_l), ptr(g_c), ptr(n_dev), rows, C,
                                               ptr(grad_loc), ptr(grad_conf), stream_ptr()),
@@ -306,7 +306,7 @@ def nms_device(boxes, scores, overlap, top_k, flags=_ffi.RD_NMS_NORMALISED):
     L = lib()
     ws_bytes = int(L.rd_nms_workspace_bytes(n))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(L.rd_nms(ptr(boxes), ptr(scores), n, float(overlap), int(top_k), int(flags), ptr(ws), ws_bytes,
                        ptr(keep), ptr(count), stream_ptr()), 'rd_nms')
     return keep, count

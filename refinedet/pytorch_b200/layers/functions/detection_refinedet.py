@@ -10,7 +10,7 @@ import torch
 
 from .. import box_utils  # noqa: F401  (kept importable like the reference module)
 from ... import _ffi
-from ..._ffi import check, lib, ptr, require_cuda_f32, stream_ptr
+from ..._ffi import check, lib, on_device, ptr, require_cuda_f32, stream_ptr
 
 # data/config.py:103,115 — the only field of the config this layer reads (:25)
 _VARIANCE = {'320': [0.1, 0.2], '512': [0.1, 0.2]}
@@ -31,7 +31,7 @@ class Detections(object):
         dev = self.dets.device
         offsets = torch.empty(B * C + 1, dtype=torch.int32, device=dev)
         rows = torch.empty(B * C * max_out, 5, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib().rd_pack_detections(ptr(self.counts), ptr(self.dets), B, C, max_out, ptr(offsets),
                                            ptr(rows), rows.shape[0], stream_ptr()), 'rd_pack_detections')
         total = int(offsets[-1].item())
@@ -81,7 +81,7 @@ class DetectPlan(object):
         import ctypes
         self.result, self.device, self._keep = result, device, keep_alive
         handle = ctypes.c_void_p(0)
-        with torch.cuda.device(device):
+        with on_device(device):
             check(lib().rd_detect_plan_create(*args, ctypes.byref(handle)), 'rd_detect_plan_create')
         self._handle = handle
 
@@ -229,7 +229,7 @@ class Detect_RefineDet(object):
             L = lib()
             nbytes = int(L.rd_detect_workspace_bytes(B, P, C))
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-            with torch.cuda.device(device):
+            with on_device(device):
                 check(L.rd_detect_workspace_reset(ptr(ws), nbytes, stream_ptr()), 'rd_detect_workspace_reset')
             self._ws, self._ws_key = ws, key
         return self._ws
@@ -244,7 +244,7 @@ class Detect_RefineDet(object):
         dev = odm_loc.device
         boxes = torch.empty(B, P, 4, dtype=torch.float32, device=dev)
         scores = torch.empty(B, P, C, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib().rd_detect_forward(ptr(arm_loc), ptr(arm_conf), ptr(odm_loc), ptr(odm_conf), ptr(priors),
                                           B, P, C, float(self.objectness_thre), float(self.variance[0]),
                                           float(self.variance[1]), ptr(boxes), ptr(scores), stream_ptr()),
@@ -311,7 +311,7 @@ class Detect_RefineDet(object):
             self._host_counts = torch.empty(B, C, dtype=torch.int32).pin_memory()
             self._dev_offsets = torch.empty(B * C + 1, dtype=torch.int32, device=dev)
             self._host_key = key
-        with torch.cuda.device(dev):
+        with on_device(dev):
             check(lib().rd_pack_detections(ptr(res.counts), ptr(res.dets), B, C, max_out, ptr(self._dev_offsets),
                                            ptr(self._host_rows), self._host_rows.shape[0], stream_ptr()),
                   'rd_pack_detections')
@@ -380,7 +380,7 @@ class Detect_RefineDet(object):
                row_layout, max_out, dets=None, timed=None, host_mapped=False):
         args, res, dev, _ = self._prepare(arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data,
                                           scale, flags, row_layout, max_out, dets=dets, host_mapped=host_mapped)
-        with torch.cuda.device(dev):
+        with on_device(dev):
             if timed is None:
                 check(lib().rd_detect_fused(*args, stream_ptr()), 'rd_detect_fused')
             else:
@@ -395,7 +395,7 @@ class Detect_RefineDet(object):
         L = lib()
         nbytes = int(L.rd_detect_workspace_bytes(B, P, self.num_classes))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        with torch.cuda.device(device):
+        with on_device(device):
             check(L.rd_detect_workspace_reset(ptr(ws), nbytes, stream_ptr()), 'rd_detect_workspace_reset')
         return ws
 

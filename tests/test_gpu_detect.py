@@ -158,18 +158,25 @@ def _oracle_a4(boxes, scores, scale, conf_thr, top_k, nms_thr, keep_top_k):
     ('sparse-7', 2, '512', 81, 1000, 500),   # ~1900 nodes: two-block graph, > 256 candidates -> graph resolve in nms_large
     ('sparse-7', 2, '512', 3, 1000, 500),    # ... wide variant overflows 1024 candidates -> per-problem bins
     ('sparse-5', 2, '320', 21, 1000, 500),   # ~2700 nodes of 6375: three-block graph
+    ('clustered', 2, '512', 81, 1000, 500),  # trained-detector-like: dozens of overlapping boxes per object
+    ('clustered', 2, '320', 21, 1000, 500),
+    ('clustered', 3, '512', 2, 1000, 500),
 ])
 def test_fused_detect_vs_oracle(rd, kind, B, size, C, top_k, keep):
     priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward()
     P = priors.shape[0]
-    arm_shift = {'sparse': -3.0, 'sparse-8': -8.0, 'sparse-7': -7.0, 'sparse-5': -5.0, 'dense': 0.0}[kind]
+    arm_shift = {'sparse': -3.0, 'sparse-8': -8.0, 'sparse-7': -7.0, 'sparse-5': -5.0, 'dense': 0.0,
+                 'clustered': 0.0}[kind]
     kind = kind.split('-')[0]
     conf_thr, nms_thr, obj_thr = 0.01, 0.45, 0.01
     # fp32 softmax scores collide often at these candidate counts, so tie-free inputs are not
     # attainable by reseeding; the kernel and the oracle share one documented tie rule (score
     # descending, lower anchor first) and must agree bit-exactly WITH ties present.  The golden
     # fixtures (reference outputs) were generated tie-free, where the rule is unobservable.
-    arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs(4242 + B + C, B, P, C, kind, arm_shift=arm_shift)
+    if kind == 'clustered':
+        arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs_clustered(4242 + B + C, B, priors, C)
+    else:
+        arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs(4242 + B + C, B, P, C, kind, arm_shift=arm_shift)
     det = rd.Detect_RefineDet(C, int(size), 0, top_k, conf_thr, nms_thr, obj_thr, keep)
     scale = np.array([float(size)] * 4, np.float32)
     d_in = [t.cuda() for t in (arm_loc, arm_conf, odm_loc, odm_conf)]
