@@ -452,9 +452,9 @@ struct GraphSmem {
     int npairs;
 };
 
-__device__ __forceinline__ void graph_add_edge(int* __restrict__ adjn, unsigned short* __restrict__ adj,
-                                               unsigned short* __restrict__ adj2, int to, int from, int* overflow) {
-    const int slot = atomicAdd(&adjn[to], 1);
+// an edge is added in two steps so that the atomics of several edges can be in flight before their stores
+__device__ __forceinline__ void graph_store_edge(unsigned short* __restrict__ adj, unsigned short* __restrict__ adj2,
+                                                 int to, int from, int slot, int* overflow) {
     if (slot < kAdjDeg) adj[to * kAdjDeg + slot] = (unsigned short)from;
     else if (slot < kAdjMax) {
         adj2[to * kAdjDeg2 + slot - kAdjDeg] = (unsigned short)from;
@@ -474,8 +474,11 @@ __device__ __forceinline__ void graph_test_pair_inline(GraphSmem& G, int i, int 
     const bool j_sup_i = (flags & RD_NMS_PIXEL_PLUS1)
                              ? i_sup_j
                              : suppresses(bj.x, bj.y, bj.z, bj.w, G.x1[i], G.y1[i], G.x2[i], G.y2[i], thr, flags);
-    if (i_sup_j) graph_add_edge(adjn, adj, adj2, n0 + jl, n0 + i, &G.overflow);
-    if (j_sup_i) graph_add_edge(adjn, adj, adj2, n0 + i, n0 + jl, &G.overflow);
+    int s_j = 0, s_i = 0;
+    if (i_sup_j) s_j = atomicAdd(&adjn[n0 + jl], 1);
+    if (j_sup_i) s_i = atomicAdd(&adjn[n0 + i], 1);
+    if (i_sup_j) graph_store_edge(adj, adj2, n0 + jl, n0 + i, s_j, &G.overflow);
+    if (j_sup_i) graph_store_edge(adj, adj2, n0 + i, n0 + jl, s_i, &G.overflow);
 }
 // out-of-line twin for the (rare) pairs found after the list has filled up: keeps the listing loop lean
 __device__ __noinline__ void graph_test_pair(GraphSmem& G, int i, int jl, int nb, const float4* __restrict__ boxes_n0,
@@ -571,6 +574,22 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
                 if (off < kGraphPairCap) G.pairs[off] = tag | (uint32_t)i;
                 else graph_test_pair(G, i, g + jo * kGraphSplit, kSingle ? kBlockNodes : nb, boxes + n0, thr, flags, adjn, adj, adj2, n0);
                 ++off;
+            }
+            // dense neighbourhoods (dozens of overlapping boxes per object): drain the list between rounds of
+            // items instead of letting it fill up and testing the excess pairs one thread at a time
+            if (q0 + kGraphThreads < nitems) {
+                __syncthreads();
+                if (G.npairs >= kGraphPairCap / 2) {
+                    const int cnt = min(G.npairs, kGraphPairCap);
+                    for (int p = tid; p < cnt; p += kGraphThreads) {
+                        const uint32_t e = G.pairs[p];
+                        graph_test_pair_inline(G, (int)(e & 0xffffu), g + (int)(e >> 16) * kGraphSplit, kSingle ? kBlockNodes : nb,
+                                               boxes + n0, thr, flags, adjn, adj, adj2, n0);
+                    }
+                    __syncthreads();
+                    if (tid == 0) G.npairs = 0;
+                    __syncthreads();
+                }
             }
         }
         __syncthreads();
