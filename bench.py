@@ -538,6 +538,46 @@ def main():
                               'wall clock including the host glue and the two N < 1 host checks'}
         del leaves, tp, tg
 
+    # the one exchange step of the multi-GPU path, timed separately from the stage (N > 1 only):
+    # the gather of every rank's compact detections, through NCCL and through the fused pack + P2P scatter
+    gather = None
+    if dist is not None:
+        from refinedet.pytorch_b200 import dist as rdist
+        res_g = plans[0][0].launch(main)
+        torch.cuda.synchronize()
+
+        def timed_gather(fn, n=20):
+            for _ in range(3):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            torch.cuda.synchronize()
+            dt = torch.tensor([(time.perf_counter() - t0) / n], device=dev)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt) * 1e3
+        counts_n, rows_n = rdist.gather_detections(res_g)
+        gather = {'rows_per_rank': int(rows_n[rank].shape[0]), 'bytes_per_rank': int(rows_n[rank].numel() * 4),
+                  'nccl_ms': timed_gather(lambda: rdist.gather_detections(res_g)),
+                  'nccl_what': 'pack kernel, header all_gather, host read, padded all_gather_into_tensor '
+                               '(dist.gather_packed), wall clock, max over ranks'}
+        try:
+            ex = rdist.PeerExchange(BATCH, C, res_g.dets.shape[2], dev)
+            ex.exchange(res_g)
+            counts_p, rows_p = ex.result()
+            same = all(torch.equal(counts_p[r], counts_n[r]) and torch.equal(rows_p[r], rows_n[r])
+                       for r in range(world))
+            gather.update({'peer_equals_nccl': bool(same),
+                           'peer_ms': timed_gather(lambda: (ex.exchange(res_g), ex.result())),
+                           'peer_device_ms': timed_gather(lambda: ex.exchange(res_g)),
+                           'peer_what': 'rd_pack_scatter: the pack kernel stores counts + rows into every peer\'s '
+                                        'buffer over NVLink (symmetric memory), two device barriers; peer_ms adds '
+                                        'the host read of the headers'})
+            del ex
+        except Exception as e:                                  # symmetric memory unavailable: NCCL number only
+            gather['peer_error'] = repr(e)[:200]
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, done, elapsed = cpu_reference_run(args.workload, 1000, 1, cores, budget_s=12.0)
@@ -555,7 +595,7 @@ def main():
                                arm_pass_fraction=arm_pass, kept_rows_per_step=kept_rows),
                 'latency_ms_per_batch': latency_ms,
                 'roofline': roofline, 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'secondary': secondary,
-                'other_configs': other_configs, 'logits_in': logits_in, 'a3_forward': a3, 'train_step': train_step,
+                'other_configs': other_configs, 'gather': gather, 'logits_in': logits_in, 'a3_forward': a3, 'train_step': train_step,
                 'gpu_launches': int(launches),
                 'clocks': clocks.summary()}
         print(json.dumps(line))

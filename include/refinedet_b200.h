@@ -165,6 +165,21 @@ RD_API int rd_detect_plan_destroy(rd_detect_plan* plan);
 RD_API int rd_pack_detections(const int* counts, const float* dets, int B, int C, int max_out,
                        int* out_offsets, float* packed, int packed_capacity, void* stream);
 
+/* Multi-GPU exchange of the compact detections (the reference has no counterpart: its
+ * nn.DataParallel gathers the dense head outputs on GPU 0, train_refinedet.py:138-139).  Packing fused
+ * with the gather: this rank's counts and packed rows are stored straight into its slot of EVERY peer's
+ * exchange buffer (peer-mapped device memory: P2P stores over NVLink / NVSwitch), no staging copy, no
+ * collective call; the caller places a barrier between the ranks afterwards.
+ *   slot = [64 x i32 header: rows stored, B, C, rows total | counts B*C x i32, padded to 256 B |
+ *           rows capacity_rows x 5 x f32], rd_exchange_slot_bytes(B, C, capacity_rows) bytes, 256-B aligned.
+ *   peer_slots_host: HOST array of `world` device pointers, entry w = base of this rank's slot in the
+ *   buffer of rank w (entry `rank` is the local one).  scratch_offsets[B*C+1] is local scratch.  slot_B >= B
+ *   is the batch the slots were sized for (ranks may hold one image less than the largest shard). */
+RD_API size_t rd_exchange_slot_bytes(int B, int C, int capacity_rows);
+RD_API int rd_pack_scatter(const int* counts, const float* dets, int B, int C, int max_out,
+                           int* scratch_offsets, void* const* peer_slots_host, int world, int rank,
+                           int slot_B, int capacity_rows, void* stream);
+
 /* ---- stand-alone NMS ------------------------------------------------------- */
 RD_API size_t rd_nms_workspace_bytes(int n);
 /* box_utils.nms (box_utils.py:222-286) / utils.nms_wrapper.nms on device tensors:

@@ -980,6 +980,42 @@ __global__ void pack_rows_kernel(const int* __restrict__ counts, const int* __re
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU exchange: packing fused with the gather.  Every rank owns one slot in every
+// peer's exchange buffer ([header 64 x i32 | counts nbc x i32, padded to 256 B | rows capacity x 5 x f32]);
+// the pack kernel stores this rank's counts and packed rows straight into its slot on EVERY peer (P2P
+// stores over NVLink / NVSwitch, peer order rotated by rank so the links are used evenly) -- no staging copy
+// and no collective call; a barrier between the ranks afterwards is all that is needed.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerSlots { unsigned char* p[kMaxPeers]; };
+
+__global__ void pack_scatter_kernel(const int* __restrict__ counts, const int* __restrict__ offsets,
+                                    const float* __restrict__ dets, int max_out, int nbc, int B, int C, PeerSlots peers,
+                                    int world, int rank, int capacity, size_t rows_off) {
+    const int bc = blockIdx.x;
+    if (bc == nbc) {                       // last CTA: header + counts
+        for (int k = 0; k < world; ++k) {
+            unsigned char* slot = peers.p[(rank + 1 + k) % world];
+            int* hdr = reinterpret_cast<int*>(slot);
+            int* cdst = reinterpret_cast<int*>(slot + 256);
+            for (int t = threadIdx.x; t < nbc; t += blockDim.x) cdst[t] = counts[t];
+            if (threadIdx.x == 0) { hdr[0] = min(offsets[nbc], capacity); hdr[1] = B; hdr[2] = C; hdr[3] = offsets[nbc]; }
+        }
+        return;
+    }
+    const int n = counts[bc];
+    const int off = offsets[bc];
+    const float* src = dets + (size_t)bc * max_out * 5;
+    int len = n * 5;
+    if (off + n > capacity) len = max(0, capacity - off) * 5;
+    for (int k = 0; k < world; ++k) {
+        float* dst = reinterpret_cast<float*>(peers.p[(rank + 1 + k) % world] + rows_off) + (size_t)off * 5;
+        for (int t = threadIdx.x; t < len; t += blockDim.x) dst[t] = src[t];
+    }
+}
+
 }  // namespace rd
 
 using namespace rd;
@@ -1262,6 +1298,30 @@ int rd_pack_detections(const int* counts, const float* dets, int B, int C, int m
     note_launch();
     RD_CHECK_LAUNCH();
     pack_rows_kernel<<<B * C, 128, 0, st>>>(counts, out_offsets, dets, max_out, packed, packed_capacity);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+size_t rd_exchange_slot_bytes(int B, int C, int capacity_rows) {
+    if (B <= 0 || C <= 0 || capacity_rows < 0) return 0;
+    return 256 + align_up((size_t)B * C * 4, 256) + align_up((size_t)capacity_rows * 20, 256);
+}
+
+int rd_pack_scatter(const int* counts, const float* dets, int B, int C, int max_out, int* scratch_offsets,
+                    void* const* peer_slots_host, int world, int rank, int slot_B, int capacity_rows, void* stream) {
+    if (slot_B < B) return RD_ERR_BAD_ARG;
+    if (!counts || !dets || !scratch_offsets || !peer_slots_host || B <= 0 || C <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
+    if (world <= 0 || world > kMaxPeers || rank < 0 || rank >= world || capacity_rows < 0) return RD_ERR_BAD_ARG;
+    PeerSlots ps;
+    for (int k = 0; k < kMaxPeers; ++k) ps.p[k] = k < world ? static_cast<unsigned char*>(peer_slots_host[k]) : nullptr;
+    for (int k = 0; k < world; ++k) if (!ps.p[k] || ((uintptr_t)ps.p[k] & 255)) return RD_ERR_ALIGNMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    pack_offsets_kernel<<<1, 1024, 0, st>>>(counts, B * C, scratch_offsets);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    pack_scatter_kernel<<<B * C + 1, 128, 0, st>>>(counts, scratch_offsets, dets, max_out, B * C, B, C, ps, world, rank,
+                                                   capacity_rows, 256 + align_up((size_t)slot_B * C * 4, 256));
     note_launch();
     RD_CHECK_LAUNCH();
     return 0;

@@ -62,3 +62,67 @@ def gather_detections(detections, group=None):
     """``Detections`` of this rank (CUDA) -> ``(counts_all, rows_all)`` of every rank."""
     _, rows = detections.packed()
     return gather_packed(detections.counts, rows, group)
+
+
+# ---------------------------------------------------------------------------------------------
+# packing fused with the gather: P2P stores into every peer's exchange buffer (rd_pack_scatter)
+# ---------------------------------------------------------------------------------------------
+def decode_slots(buf, world, slot_bytes, nbc_capacity):
+    """Views into an exchange buffer (``world`` slots of ``slot_bytes`` bytes, the layout of
+    ``rd_pack_scatter``): ``(counts_all, rows_all)``, one tensor per source rank.  One host sync (the
+    headers)."""
+    slots = buf.view(world, slot_bytes)
+    headers = slots[:, :16].contiguous().view(torch.int32).cpu()          # rows stored, B, C, rows total
+    rows_off = 256 + (nbc_capacity * 4 + 255) // 256 * 256
+    counts_all, rows_all = [], []
+    for r in range(world):
+        stored, b_r, c_r, total = (int(v) for v in headers[r])
+        if stored != total:
+            raise RuntimeError('exchange slot of rank %d holds %d of %d rows: capacity too small' % (r, stored, total))
+        counts_all.append(slots[r, 256:256 + b_r * c_r * 4].view(torch.int32).view(b_r, c_r))
+        rows_all.append(slots[r, rows_off:rows_off + stored * 20].view(torch.float32).view(stored, 5))
+    return counts_all, rows_all
+
+
+class PeerExchange(object):
+    """All-gather of the compact detections WITHOUT a collective call: every rank's pack kernel stores its
+    counts and packed rows straight into its slot of every peer's buffer (symmetric memory: each buffer is
+    mapped into every process of the node, the stores travel over NVLink / NVSwitch), bracketed by two
+    device-side barriers.  ``B`` = the largest per-rank batch; all ranks construct it collectively.
+
+    Needs ``torch.distributed._symmetric_memory`` (one node, NVLink/PCIe P2P); raises otherwise — callers
+    that want a portable path use :func:`gather_packed` (NCCL / gloo)."""
+
+    def __init__(self, B, C, max_out, device, group=None, capacity_rows=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        from ._ffi import lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.B, self.C, self.max_out = int(B), int(C), int(max_out)
+        self.capacity = int(capacity_rows) if capacity_rows is not None else self.B * self.C * self.max_out
+        self.slot_bytes = int(lib().rd_exchange_slot_bytes(self.B, self.C, self.capacity))
+        self.buf = symm_mem.empty(self.world * self.slot_bytes, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._peer_slots = (ctypes.c_void_p * self.world)(*[p + self.rank * self.slot_bytes for p in ptrs])
+        self._offsets = torch.empty(self.B * self.C + 1, dtype=torch.int32, device=device)
+
+    def exchange(self, detections):
+        """Asynchronous on the current stream: barrier (peers are done reading the previous round), pack +
+        scatter, barrier (every peer's stores have landed)."""
+        from ._ffi import check, lib, on_device, ptr, stream_ptr
+        B, C, max_out, _ = detections.dets.shape
+        if B > self.B or C != self.C or max_out != self.max_out:
+            raise ValueError('detections [%d,%d,%d] do not fit the exchange [%d,%d,%d]'
+                             % (B, C, max_out, self.B, self.C, self.max_out))
+        with on_device(self.buf.device):
+            self.hdl.barrier(channel=0)
+            check(lib().rd_pack_scatter(ptr(detections.counts), ptr(detections.dets), B, C, max_out,
+                                        ptr(self._offsets), self._peer_slots, self.world, self.rank, self.B,
+                                        self.capacity, stream_ptr()), 'rd_pack_scatter')
+            self.hdl.barrier(channel=1)
+
+    def result(self):
+        """``(counts_all, rows_all)`` of the latest exchange (views into the local buffer; one host sync)."""
+        return decode_slots(self.buf, self.world, self.slot_bytes, self.B * self.C)
