@@ -40,11 +40,13 @@ def detect_inputs(seed, B, P, C, kind='sparse', arm_shift=-8.0):
             torch.softmax(odm_logits, -1).contiguous())
 
 
-def detect_logits_clustered(seed, B, priors, C, n_obj=12, background_shift=-9.0):
+def detect_logits_clustered(seed, B, priors, C, n_obj=12, background_shift=-9.0, jitter=1.0, near_iou=0.35):
     """Head outputs shaped like a TRAINED detector's: ``n_obj`` objects per image, every anchor whose prior
     overlaps an object (IoU > 0.35) passes the ARM gate, regresses to that object with jitter and scores its
     class -- dozens of mutually overlapping boxes per object, the case greedy NMS exists for -- over the
-    ``sparse`` background (ARM logit gap 2 randn + ``background_shift``).  ``priors``: [P,4] (cx,cy,w,h)."""
+    ``sparse`` background (ARM logit gap 2 randn + ``background_shift``).  ``priors``: [P,4] (cx,cy,w,h).
+    ``jitter`` scales the regression noise: small values make the boxes of an object nearly coincide, so that
+    a node has as many suppressors as its object has anchors (beyond the 64 the suppression graph keeps)."""
     g = torch.Generator().manual_seed(int(seed))
     P = priors.shape[0]
     pr = priors.float().cpu()
@@ -58,16 +60,16 @@ def detect_logits_clustered(seed, B, priors, C, n_obj=12, background_shift=-9.0)
     inter = (rb - lt).clamp(min=0).prod(-1)                                     # [B,P,n_obj]
     iou = inter / (pr[:, 2:].prod(-1)[None, :, None] + wh.prod(-1)[:, None, :] - inter)
     best, which = iou.max(-1)                                                   # [B,P]
-    near = best > 0.35
+    near = best > near_iou
     bi = torch.arange(B)[:, None]
     ocx, owh, ocl = cxy[bi, which], wh[bi, which], cls[bi, which]               # the anchor's object
     enc = torch.cat([(ocx - pr[None, :, :2]) / (0.1 * pr[None, :, 2:]),
                      torch.log(owh / pr[None, :, 2:]) / 0.2], -1)               # encode(object, prior)
     d = torch.where(near, 3.0 + torch.randn(B, P, generator=g), 2.0 * torch.randn(B, P, generator=g) + background_shift)
     arm_logits = torch.stack([torch.zeros(B, P), d], -1)
-    arm_loc = torch.where(near[..., None], 0.8 * enc + 0.3 * torch.randn(B, P, 4, generator=g),
+    arm_loc = torch.where(near[..., None], (1.0 - 0.2 * min(jitter, 1.0)) * enc + 0.3 * jitter * torch.randn(B, P, 4, generator=g),
                           torch.randn(B, P, 4, generator=g))
-    odm_loc = torch.where(near[..., None], 0.4 * torch.randn(B, P, 4, generator=g), torch.randn(B, P, 4, generator=g))
+    odm_loc = torch.where(near[..., None], 0.4 * jitter * torch.randn(B, P, 4, generator=g), torch.randn(B, P, 4, generator=g))
     odm_logits = 1.5 * torch.randn(B, P, C, generator=g)
     odm_logits[..., 0] += 4.0
     boost = torch.zeros(B, P, C)
@@ -76,8 +78,9 @@ def detect_logits_clustered(seed, B, priors, C, n_obj=12, background_shift=-9.0)
     return arm_loc.contiguous(), arm_logits.contiguous(), odm_loc.contiguous(), odm_logits.contiguous()
 
 
-def detect_inputs_clustered(seed, B, priors, C, n_obj=12):
-    arm_loc, arm_logits, odm_loc, odm_logits = detect_logits_clustered(seed, B, priors, C, n_obj)
+def detect_inputs_clustered(seed, B, priors, C, n_obj=12, jitter=1.0, near_iou=0.35):
+    arm_loc, arm_logits, odm_loc, odm_logits = detect_logits_clustered(seed, B, priors, C, n_obj, jitter=jitter,
+                                                                       near_iou=near_iou)
     return (arm_loc, torch.softmax(arm_logits, -1).contiguous(), odm_loc,
             torch.softmax(odm_logits, -1).contiguous())
 

@@ -161,12 +161,14 @@ def _oracle_a4(boxes, scores, scale, conf_thr, top_k, nms_thr, keep_top_k):
     ('clustered', 2, '512', 81, 1000, 500),  # trained-detector-like: dozens of overlapping boxes per object
     ('clustered', 2, '320', 21, 1000, 500),
     ('clustered', 3, '512', 2, 1000, 500),
+    ('clustered-tight', 2, '512', 21, 1000, 500),   # near-coincident boxes: degree > 64 -> no graph, bin path
 ])
 def test_fused_detect_vs_oracle(rd, kind, B, size, C, top_k, keep):
     priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward()
     P = priors.shape[0]
     arm_shift = {'sparse': -3.0, 'sparse-8': -8.0, 'sparse-7': -7.0, 'sparse-5': -5.0, 'dense': 0.0,
-                 'clustered': 0.0}[kind]
+                 'clustered': 0.0, 'clustered-tight': 0.0}[kind]
+    jitter, near_iou = (0.15, 0.2) if kind.endswith('tight') else (1.0, 0.35)
     kind = kind.split('-')[0]
     conf_thr, nms_thr, obj_thr = 0.01, 0.45, 0.01
     # fp32 softmax scores collide often at these candidate counts, so tie-free inputs are not
@@ -174,7 +176,7 @@ def test_fused_detect_vs_oracle(rd, kind, B, size, C, top_k, keep):
     # descending, lower anchor first) and must agree bit-exactly WITH ties present.  The golden
     # fixtures (reference outputs) were generated tie-free, where the rule is unobservable.
     if kind == 'clustered':
-        arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs_clustered(4242 + B + C, B, priors, C)
+        arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs_clustered(4242 + B + C, B, priors, C, jitter=jitter, near_iou=near_iou)
     else:
         arm_loc, arm_conf, odm_loc, odm_conf = gen.detect_inputs(4242 + B + C, B, P, C, kind, arm_shift=arm_shift)
     det = rd.Detect_RefineDet(C, int(size), 0, top_k, conf_thr, nms_thr, obj_thr, keep)
