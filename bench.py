@@ -533,7 +533,33 @@ def main():
             one_step()
         torch.cuda.synchronize()
         ms_t = 1e3 * (time.perf_counter() - t0) / n_t
+        # the same step with the criteria's sync_free extension (no host read of N inside the criteria; the
+        # losses are read once after backward, as train_refinedet.py:258-261 does with .item())
+        arm_sf = rd.RefineDetMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True, sync_free=True)
+        odm_sf = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True, sync_free=True)
+
+        def one_step_sf():
+            rd.box_utils._PAD_CACHE = None
+            preds = (leaves[0], leaves[1], leaves[2], leaves[3], priors)
+            al, ac = arm_sf(preds, tg)
+            ol, oc = odm_sf(preds, tg)
+            (al + ac + ol + oc).backward()
+            vals = torch.stack([al.detach(), ac.detach(), ol.detach(), oc.detach()]).tolist()   # one read per step
+            for t in leaves:
+                t.grad = None
+            return vals
+        for _ in range(3):
+            one_step_sf()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_t):
+            one_step_sf()
+        torch.cuda.synchronize()
+        ms_sf = 1e3 * (time.perf_counter() - t0) / n_t
         train_step = {'ms_per_step': ms_t, 'value': BATCH / (ms_t * 1e-3), 'unit': UNIT,
+                      'sync_free': {'ms_per_step': ms_sf, 'value': BATCH / (ms_sf * 1e-3),
+                                    'what': 'criteria built with sync_free=True: no host read of N inside the criteria, '
+                                            'the four losses read once after backward'},
                       'what': 'ARM + ODM RefineDetMultiBoxLoss forward + backward (B=32, P=16320, C=81, 50 GT/image), '
                               'wall clock including the host glue and the two N < 1 host checks'}
         del leaves, tp, tg

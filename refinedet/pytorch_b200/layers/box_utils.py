@@ -116,6 +116,31 @@ LABEL_ODM, LABEL_ARM_BINARY, LABEL_SSD_PLUS1 = 0, 1, 2
 _PAD_CACHE = None
 
 
+# Offsets of the ragged target list travel through a small ring of PINNED staging buffers: a copy from pageable
+# memory makes the driver drain the stream first (CUDA API synchronisation rules), i.e. one hidden device
+# synchronisation per training step.  A slot is reused only after the copy that read it has completed.
+_PIN_SLOTS, _pin_ring, _pin_next = 8, {}, 0
+
+
+def _offsets_to_device(counts, device):
+    global _pin_next
+    n = len(counts) + 1
+    key = (device.index, n)
+    ring = _pin_ring.get(key)
+    if ring is None:
+        ring = _pin_ring[key] = [(torch.zeros(n, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+                                 for _ in range(_PIN_SLOTS)]
+        for _, ev in ring:
+            ev.record()
+    buf, ev = ring[_pin_next % _PIN_SLOTS]
+    _pin_next += 1
+    ev.synchronize()                                        # normally long complete
+    np.cumsum(counts, out=buf.numpy()[1:])
+    out = buf.to(device, non_blocking=True)
+    ev.record()
+    return out
+
+
 def pad_targets(targets, device):
     """``targets``: list of B tensors ``[G_i, 5]`` (x1,y1,x2,y2,label) -> padded
     ``truths[B,Gmax,4]``, ``labels[B,Gmax]``, ``gt_count[B]`` on ``device`` (the batched
@@ -143,9 +168,7 @@ def pad_targets(targets, device):
         else:
             flat = torch.cat([t.detach().reshape(-1, 5) for t in targets if t.shape[0]]).to(device=device, dtype=torch.float32)
         flat = flat.reshape(-1, 5).contiguous()
-        offs = np.zeros(B + 1, dtype=np.int32)
-        np.cumsum(counts, out=offs[1:])
-        offsets = torch.from_numpy(offs).to(device, non_blocking=True)
+        offsets = _offsets_to_device(counts, truths.device)
         with on_device(truths.device):
             check(lib().rd_pad_targets(ptr(flat), ptr(offsets), B, gmax, ptr(truths), ptr(labels), ptr(gt_count),
                                        stream_ptr()), 'rd_pad_targets')

@@ -20,10 +20,17 @@ _VARIANCE = [0.1, 0.2]
 class RefineDetMultiBoxLoss(nn.Module):
     """RefineDet weighted loss: SmoothL1 localisation + cross-entropy confidence with 3:1 hard
     negative mining, for the ARM (``use_ARM=False``, 2-class) or ODM (``use_ARM=True``)
-    branch.  Constructor arguments are the reference's (:33-48)."""
+    branch.  Constructor arguments are the reference's (:33-48).
+
+    ``sync_free`` (extension, default off): the reference reads ``N = sum(num_pos)`` on the host to return
+    ``(zeros(1), zeros(1))`` when no positive survives (:135-136) — a stream drain in the middle of every
+    criterion call.  With ``sync_free=True`` nothing is read back: the losses are always the 0-dim device
+    tensors, and for ``N < 1`` the kernels deliver exactly zero losses and zero gradients — the same parameter
+    update as the reference's no-grad zeros, so ``train_refinedet.py:252-261`` runs unchanged while the host
+    queues the next criterion and the backward pass behind the running kernels."""
 
     def __init__(self, num_classes, overlap_thresh, prior_for_matching, bkg_label, neg_mining,
-                 neg_pos, neg_overlap, encode_target, use_gpu=True, theta=0.01, use_ARM=False):
+                 neg_pos, neg_overlap, encode_target, use_gpu=True, theta=0.01, use_ARM=False, sync_free=False):
         super(RefineDetMultiBoxLoss, self).__init__()
         self.use_gpu = use_gpu
         self.num_classes = num_classes
@@ -37,6 +44,7 @@ class RefineDetMultiBoxLoss(nn.Module):
         self.variance = _VARIANCE
         self.theta = theta
         self.use_ARM = use_ARM
+        self.sync_free = bool(sync_free)
 
     def match_targets(self, predictions, targets):
         """Targets of reference :62-90 for the whole batch: ``(loc_t[B,P,4], conf_t[B,P])``."""
@@ -71,7 +79,7 @@ class RefineDetMultiBoxLoss(nn.Module):
         loss_l, loss_c, N = _MultiBoxLossTail.apply(loc_data, conf_data, arm_gate, loc_t, conf_t,
                                                     float(self.theta), int(self.negpos_ratio))
         self.last_masks = _MultiBoxLossTail.last_masks
-        if float(N) < 1:                                            # :135-136 (the reference syncs here too)
+        if not self.sync_free and float(N) < 1:                     # :135-136 (the reference syncs here too)
             return torch.zeros(1), torch.zeros(1)
         return loss_l, loss_c
 

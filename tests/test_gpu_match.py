@@ -77,6 +77,15 @@ def test_loss_golden(rd, golden):
     arm_conf_off[..., 0] += 50.0
     zl, zc = odm_crit((preds[0], arm_conf_off, preds[2], preds[3], preds[4]), targets)
     assert zl.shape == (1,) and float(zl) == 0.0 and float(zc) == 0.0
+    # sync_free extension: same values without the host read of N; N < 1 -> 0-dim zeros with zero gradients
+    odm_sf = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True, sync_free=True)
+    sl, sc = odm_sf(preds, targets)
+    assert sl.dim() == 0 and sl.is_cuda and float(sl) == float(ol) and float(sc) == float(oc)
+    p0 = tuple(t.clone().requires_grad_(True) if i in (2, 3) else t for i, t in enumerate(preds))
+    zl2, zc2 = odm_sf((p0[0], arm_conf_off, p0[2], p0[3], p0[4]), targets)
+    assert zl2.dim() == 0 and float(zl2) == 0.0 and float(zc2) == 0.0
+    (zl2 + zc2).backward()
+    assert float(p0[2].grad.abs().sum()) == 0.0 and float(p0[3].grad.abs().sum()) == 0.0
     # gradients flow to the predictions through the stock-PyTorch loss tail
     p2 = tuple(t.clone().requires_grad_(True) if i < 4 else t for i, t in enumerate(preds))
     l, c = odm_crit(p2, targets)
