@@ -183,7 +183,6 @@ constexpr int kAdjMax = kAdjDeg + kAdjDeg2;   // an image with a node of higher 
 constexpr int kFlagNoGraph = 1;       // img_flag bits: no usable graph / some node has more than kAdjDeg suppressors
 constexpr int kFlagWideDeg = 2;
 
-// kNodes = largest node index + 1 the rank table covers (images with more nodes are not handled by this instance)
 // Dependencies of a problem's candidates: lists of at most kAdjDeg ranks per candidate (every node of the image
 // has at most kAdjDeg suppressors: the common case, one 16-byte adjacency row per candidate).  For images flagged
 // kFlagWideDeg the kCap <= 256 instance (kBitRows) switches to one bit row per candidate over the EARLIER ranks
@@ -193,13 +192,10 @@ __device__ __forceinline__ int tri_row(int r) {
     const int k = r >> 5;
     return 16 * k * (k + 1) + (r & 31) * (k + 1);
 }
+// kNodes = largest node index + 1 the rank table covers (images with more nodes are not handled by this instance)
 template <int kCap, int kNodes = (kCap > 256 ? RD_GRAPH_NODES : 1024)>
 struct SmallSmem {
-#ifdef RD_K2_LIST
-    static constexpr bool kBitRows = false;
-#else
     static constexpr bool kBitRows = kCap <= 256; // false: images flagged kFlagWideDeg are not handled by this instance
-#endif
     static constexpr int kDeps = kAdjDeg;         // list mode: ranks kept per candidate
     static constexpr int kTriWords = 16 * (kCap / 32) * (kCap / 32 + 1);
     using rank_t = typename std::conditional<(kCap > 256), unsigned short, unsigned char>::type;

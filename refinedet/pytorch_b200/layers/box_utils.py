@@ -4,6 +4,8 @@ Same names, argument order and results as the reference (file:line cited per fun
 every function takes CUDA tensors and calls ``librefinedet_b200.so`` through ``_ffi``.
 There is no CPU path.
 """
+import operator
+
 import numpy as np
 import torch
 
@@ -114,6 +116,7 @@ def log_sum_exp(x):
 # ---------------------------------------------------------------------------------------------
 LABEL_ODM, LABEL_ARM_BINARY, LABEL_SSD_PLUS1 = 0, 1, 2
 _PAD_CACHE = None
+_is = operator.is_
 
 
 # Offsets of the ragged target list travel through a small ring of PINNED staging buffers: a copy from pageable
@@ -145,13 +148,23 @@ def pad_targets(targets, device):
     """``targets``: list of B tensors ``[G_i, 5]`` (x1,y1,x2,y2,label) -> padded
     ``truths[B,Gmax,4]``, ``labels[B,Gmax]``, ``gt_count[B]`` on ``device`` (the batched
     form of the per-image slicing at refinedet_multibox_loss.py:76-77)."""
-    # the ARM and the ODM criterion of a training step pad the same list (train_refinedet.py:252-253): keep the
-    # latest result, keyed by the identity, version and storage of every target tensor
+    return _padded(targets, device)[:3]
+
+
+def _padded(targets, device):
+    """:func:`pad_targets` plus the smallest per-image count (the host already knows it)."""
+    # The ARM and the ODM criterion of a training step pad the same list (train_refinedet.py:252-253): the
+    # latest result is kept.  The cache HOLDS the target tensors, so neither their ids nor their storage can
+    # be recycled for another batch while the entry is alive; in-place edits show in ``_version``.
     global _PAD_CACHE
-    key = (str(device),) + tuple((id(t), t._version, t.data_ptr(), t.shape[0]) for t in targets)
-    if _PAD_CACHE is not None and _PAD_CACHE[0] == key:
-        return _PAD_CACHE[1]
-    counts = [int(t.shape[0]) for t in targets]
+    device = torch.device(device)
+    if device.index is None:
+        device = torch.device(device.type, torch.cuda.current_device())
+    c = _PAD_CACHE
+    if c is not None and c[0] == device and len(c[1]) == len(targets) and all(map(_is, targets, c[1])) \
+            and [t._version for t in targets] == c[2]:
+        return c[3]
+    counts = [t.shape[0] for t in targets]
     gmax = max(max(counts), 1)
     if gmax > _ffi.RD_MAX_GT:
         raise RuntimeError('more than %d ground-truth boxes in one image (%d)' % (_ffi.RD_MAX_GT, gmax))
@@ -163,17 +176,21 @@ def pad_targets(targets, device):
         truths.zero_(); labels.zero_(); gt_count.zero_()
     else:
         # one concatenation + one kernel instead of B slice assignments
-        if all(t.is_cuda and t.dtype == torch.float32 and t.device == truths.device for t in targets):
-            flat = torch.cat([t.detach() for t in targets if t.shape[0]])
-        else:
-            flat = torch.cat([t.detach().reshape(-1, 5) for t in targets if t.shape[0]]).to(device=device, dtype=torch.float32)
-        flat = flat.reshape(-1, 5).contiguous()
-        offsets = _offsets_to_device(counts, truths.device)
-        with on_device(truths.device):
+        try:
+            flat = torch.cat(targets)                     # same device everywhere, [G_i,5] rows: the common case
+        except (RuntimeError, TypeError):
+            flat = torch.cat([t.detach().reshape(-1, 5).to(device) for t in targets if t.shape[0]])
+        flat = flat.detach().reshape(-1, 5)
+        if flat.device != device or flat.dtype != torch.float32:
+            flat = flat.to(device=device, dtype=torch.float32)
+        flat = flat.contiguous()
+        offsets = _offsets_to_device(counts, device)
+        with on_device(device):
             check(lib().rd_pad_targets(ptr(flat), ptr(offsets), B, gmax, ptr(truths), ptr(labels), ptr(gt_count),
                                        stream_ptr()), 'rd_pad_targets')
-    _PAD_CACHE = (key, (truths, labels, gt_count))
-    return truths, labels, gt_count
+    out = (truths, labels, gt_count, min(counts))
+    _PAD_CACHE = (device, list(targets), [t._version for t in targets], out)
+    return out
 
 
 def check_targets(targets, device=None):

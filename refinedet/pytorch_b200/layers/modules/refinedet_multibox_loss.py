@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from ..._ffi import require_cuda_f32
 from ..box_utils import (LABEL_ARM_BINARY, LABEL_ODM, conf_loss, hnm_select, match_batch,
-                         multibox_loss_backward, multibox_loss_reduce, pad_targets)
+                         multibox_loss_backward, multibox_loss_reduce, _padded)
 
 # data/config.py:57 (``coco['variance']``, read at reference :46)
 _VARIANCE = [0.1, 0.2]
@@ -53,12 +53,11 @@ class RefineDetMultiBoxLoss(nn.Module):
         if not loc_data.is_cuda:
             raise RuntimeError('RefineDetMultiBoxLoss: predictions must be CUDA tensors '
                                '(refinedet.pytorch_b200 has no CPU fallback)')
-        for t in targets:
-            if t.shape[0] == 0:
-                raise IndexError('RefineDetMultiBoxLoss: an image has no ground-truth boxes '
-                                 '(the reference raises in refine_match, box_utils.py:139)')
+        truths, labels, gt_count, min_count = _padded(targets, loc_data.device)
+        if min_count == 0:
+            raise IndexError('RefineDetMultiBoxLoss: an image has no ground-truth boxes '
+                             '(the reference raises in refine_match, box_utils.py:139)')
         priors = priors[:loc_data.size(1), :]                       # :68 (DataParallel gather)
-        truths, labels, gt_count = pad_targets(targets, loc_data.device)
         if self.num_classes == 2 and not self.use_ARM:
             mode = LABEL_ARM_BINARY                                 # labels = labels >= 0, :78-79
         else:
