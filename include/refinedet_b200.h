@@ -98,6 +98,25 @@ RD_API int rd_detect_forward(const float* arm_loc, const float* arm_conf, const 
                       float objectness_thre, float v0, float v1,
                       float* boxes_out, float* scores_out, void* stream);
 
+/* SURVEY §8b name of the same entry point ("rd_decode_filter": ARM-objectness filter + two-stage decode) */
+RD_API int rd_decode_filter(const float* arm_loc, const float* arm_conf, const float* odm_loc,
+                      float* odm_conf, const float* priors, int B, int P, int C,
+                      float objectness_thre, float v0, float v1,
+                      float* boxes_out, float* scores_out, void* stream);
+
+/* ---- stand-alone threshold + top-k select ---------------------------------------- */
+/* Per (image b, class c >= first_class): the anchors with scores[b,p,c] > conf_thresh
+ * (eval_refinedet_coco.py:214, detection_refinedet.py:98), the top_k highest of them in
+ * score-descending order (eval :222 `argsort()[::-1][:top_k]`; box_utils.py:242-244), lower anchor
+ * index first on equal scores.  scores[B,P,C] (the a3 `scores` output or any [B,P,C] tensor);
+ *   idx_out   [B,C,top_k] int32   anchor index per rank; only the first count_out[b,c] entries are written
+ *   score_out [B,C,top_k] float   their scores (may be NULL)
+ *   count_out [B,C]       int32   min(#candidates, top_k); 0 for classes < first_class
+ * No workspace.  min(top_k, P) <= 4 * RD_MAX_NMS_BOXES.  The fused stage does not call this (it selects
+ * inside its per-class CTAs); it is the §8b `rd_select_topk` for callers that want the lists. */
+RD_API int rd_select_topk(const float* scores, int B, int P, int C, float conf_thresh, int top_k,
+                    int first_class, int* idx_out, float* score_out, int* count_out, void* stream);
+
 /* ---- fused detect stage ---------------------------------------------------- */
 /* (Detect_RefineDet.forward + the per-class loop of eval_refinedet_coco.py:205-232,
  *  or Detect_RefineDet.forward_python_nms, detection_refinedet.py:67-113, depending
@@ -122,6 +141,16 @@ RD_API int rd_detect_fused(const float* arm_loc, const float* arm_conf, const fl
                     int row_layout, float v0, float v1,
                     void* workspace, size_t workspace_bytes,
                     int* out_counts, float* out_dets, int* out_anchor, void* stream);
+
+/* SURVEY §8b names of rd_detect_fused / rd_detect_workspace_bytes (same arguments, same behaviour) */
+RD_API int rd_detect(const float* arm_loc, const float* arm_conf, const float* odm_loc,
+                    const float* odm_conf, const float* priors, int B, int P, int C,
+                    float objectness_thre, float conf_thresh, float nms_thresh,
+                    int top_k, int max_out, const float* img_scale, int nms_flags,
+                    int row_layout, float v0, float v1,
+                    void* workspace, size_t workspace_bytes,
+                    int* out_counts, float* out_dets, int* out_anchor, void* stream);
+RD_API size_t rd_workspace_bytes(int B, int P, int C);
 
 /* Diagnostics twin of rd_detect_fused: records CUDA events between the stage's kernels on
  * `stream`, WAITS for the stage, and writes the device time in ms of

@@ -221,6 +221,28 @@ def detect_stage_eval(boxes, scores, scale, conf_thresh=0.01, top_k=1000,
     return out, anchors
 
 
+def select_topk(scores, conf_thresh, top_k, first_class=1):
+    """The candidate list the reference hands to NMS, per (image, class): ``where(scores[:, j] > thresh)``
+    (eval_refinedet_coco.py:214; detection_refinedet.py:98) then ``argsort()[::-1][:top_k]`` (eval :222;
+    the last ``top_k`` of the ascending sort in box_utils.py:242-244), lower anchor first on ties.
+
+    ``scores[B,P,C]`` -> ``lists[b][c]`` = int64 anchor indices, score-descending (empty for c < first_class)."""
+    scores = _f(scores)
+    B, P, C = scores.shape
+    out = []
+    for b in range(B):
+        row = []
+        for c in range(C):
+            if c < first_class:
+                row.append(np.empty((0,), dtype=np.int64))
+                continue
+            inds = np.where(scores[b, :, c] > F32(conf_thresh))[0]
+            order = _order_desc(scores[b, inds, c])[:top_k]
+            row.append(inds[order].astype(np.int64))
+        out.append(row)
+    return out
+
+
 def forward_python_nms(arm_loc, arm_conf, odm_loc, odm_conf, priors, num_classes,
                        top_k, conf_thresh, nms_thresh, objectness_thre=0.01,
                        variance=(0.1, 0.2)):

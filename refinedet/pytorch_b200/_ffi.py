@@ -43,6 +43,13 @@ _SIGNATURES = {
     'rd_jaccard': (c_int, [_P, _P, _P, c_int, c_int, _P]),
     'rd_detect_forward': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float,
                                   _P, _P, _P]),
+    'rd_decode_filter': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float,
+                                 _P, _P, _P]),
+    'rd_select_topk': (c_int, [_P, c_int, c_int, c_int, c_float, c_int, c_int, _P, _P, _P, _P]),
+    'rd_detect': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float,
+                          c_int, c_int, _P, c_int, c_int, c_float, c_float, _P, c_size_t,
+                          _P, _P, _P, _P]),
+    'rd_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'rd_detect_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
     'rd_detect_workspace_reset': (c_int, [_P, c_size_t, _P]),
     'rd_detect_fused': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float,

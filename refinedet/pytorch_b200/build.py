@@ -21,7 +21,7 @@ CSRC = os.path.join(HERE, 'csrc')
 INCLUDE = os.path.join(ROOT, 'include')
 LIB_DIR = os.path.join(HERE, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'librefinedet_b200.so')
-SOURCES = ['rd_detect.cu', 'rd_match.cu', 'rd_loss.cu']
+SOURCES = ['rd_detect.cu', 'rd_match.cu', 'rd_loss.cu', 'rd_select.cu']
 HEADERS = ['rd_common.cuh', 'rd_nms_core.cuh']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',

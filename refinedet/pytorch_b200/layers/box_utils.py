@@ -327,6 +327,39 @@ def multibox_loss_backward(loc_data, loc_t, conf_data, conf_t, lse, pos, neg, g_
 
 
 # ---------------------------------------------------------------------------------------------
+# threshold + top-k select
+# ---------------------------------------------------------------------------------------------
+def select_topk(scores, conf_thresh, top_k, first_class=1):
+    """Per (image, class) candidate lists of the detect stage as the reference builds them before NMS:
+    ``scores[b,:,c] > conf_thresh`` (eval_refinedet_coco.py:214, detection_refinedet.py:98), the ``top_k``
+    highest in score-descending order (eval :222, box_utils.py:242-244), lower anchor first on ties.
+
+    ``scores[B,P,C]`` (e.g. the second output of ``Detect_RefineDet.forward``).  Returns device tensors
+    ``(idx[B,C,top_k] int32, sc[B,C,top_k] f32, counts[B,C] int32)``; only the first ``counts[b,c]``
+    entries of a slot are written; classes below ``first_class`` (background) get count 0.  No host sync."""
+    s = require_cuda_f32(scores, 'scores', align=4)
+    if s.dim() != 3:
+        raise ValueError('scores must be [B,P,C], got %s' % (tuple(s.shape),))
+    B, P, C = (int(v) for v in s.shape)
+    top_k = int(top_k)
+    if top_k <= 0:
+        raise ValueError('top_k must be positive')
+    if min(top_k, P) > 4 * _ffi.RD_MAX_NMS_BOXES:
+        raise RuntimeError('select_topk: min(top_k, P) = %d exceeds the supported %d'
+                           % (min(top_k, P), 4 * _ffi.RD_MAX_NMS_BOXES))
+    dev = s.device
+    idx = torch.empty(B, C, top_k, dtype=torch.int32, device=dev)
+    sc = torch.empty(B, C, top_k, dtype=torch.float32, device=dev)
+    counts = torch.empty(B, C, dtype=torch.int32, device=dev)
+    if B == 0 or P == 0 or C == 0:
+        return idx, sc, counts.zero_()
+    with on_device(dev):
+        check(lib().rd_select_topk(ptr(s), B, P, C, float(conf_thresh), top_k, int(first_class), ptr(idx), ptr(sc),
+                                   ptr(counts), stream_ptr()), 'rd_select_topk')
+    return idx, sc, counts
+
+
+# ---------------------------------------------------------------------------------------------
 # NMS
 # ---------------------------------------------------------------------------------------------
 def nms_device(boxes, scores, overlap, top_k, flags=_ffi.RD_NMS_NORMALISED):

@@ -42,6 +42,11 @@ def test_error_strings_and_argument_validation_without_gpu():
     assert L.rd_decode(None, None, 0.1, 0.2, None, 4, None) == _ffi.RD_ERR_BAD_ARG
     assert L.rd_detect_fused(*([None] * 5), 1, 1, 1, 0.0, 0.0, 0.5, 1, 1, None, 0, 0, 0.1, 0.2, None, 0,
                              None, None, None, None) == _ffi.RD_ERR_BAD_ARG
+    assert L.rd_detect(*([None] * 5), 1, 1, 1, 0.0, 0.0, 0.5, 1, 1, None, 0, 0, 0.1, 0.2, None, 0,
+                       None, None, None, None) == _ffi.RD_ERR_BAD_ARG
+    assert L.rd_decode_filter(*([None] * 5), 1, 1, 1, 0.0, 0.1, 0.2, None, None, None) == _ffi.RD_ERR_BAD_ARG
+    assert L.rd_select_topk(None, 1, 1, 1, 0.0, 1, 1, None, None, None, None) == _ffi.RD_ERR_BAD_ARG
+    assert L.rd_workspace_bytes(32, 16320, 81) == L.rd_detect_workspace_bytes(32, 16320, 81)
     assert L.rd_detect_workspace_bytes(32, 16320, 81) > 32 * 81 * 16320 * 8
     assert L.rd_nms_workspace_bytes(1000) >= 1000 * 8
 

@@ -202,3 +202,27 @@ def test_oracle_loss_grads_match_autograd():
                                            neg.numpy(), N)
     np.testing.assert_allclose(g_loc, lr.grad.numpy(), rtol=1e-5, atol=1e-8)
     np.testing.assert_allclose(g_conf, cr.grad.numpy(), rtol=1e-5, atol=1e-8)
+
+
+def test_select_topk_oracle_is_the_front_half_of_the_eval_loop(golden):
+    """``select_topk`` restates eval_refinedet_coco.py:214-222; NMS of its lists on the reference's own
+    boxes / scores must give the fixture's a4 rows (outputs of the unmodified reference)."""
+    g = golden('detect_dense.npz')
+    C, top_k, keep_top_k, conf_thr, nms_thr, obj_thr = g['params']
+    lists = bo.select_topk(g['scores'], conf_thr, int(top_k))
+    for b in range(g['scores'].shape[0]):
+        boxes = g['boxes'][b] * g['scale'][None, :]
+        assert lists[b][0].size == 0
+        for c in range(1, int(C)):
+            idx = lists[b][c]
+            assert idx.size <= int(top_k)
+            sc = g['scores'][b, idx, c]
+            assert (np.diff(sc) <= 0).all() and (sc > conf_thr).all()
+            dets = np.hstack([boxes[idx], sc[:, None]]).astype(np.float32)
+            keep = bo.nms_pixel(dets, float(nms_thr))[:int(keep_top_k)]
+            m = int(g['a4_counts'][b, c])
+            assert len(keep) == m and np.array_equal(dets[keep], g['a4_dets'][b, c, :m])
+    # ties: lower anchor first; NaN is never a candidate
+    s = np.array([[[0.0, 0.5], [0.0, 0.7], [0.0, 0.5], [0.0, np.nan], [0.0, 0.005]]], np.float32)
+    assert bo.select_topk(s, 0.01, 10)[0][1].tolist() == [1, 0, 2]
+    assert bo.select_topk(s, 0.01, 2)[0][1].tolist() == [1, 0]
