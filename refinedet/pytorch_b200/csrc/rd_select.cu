@@ -1,19 +1,27 @@
 // rd_select.cu — stand-alone threshold + top-k select (SURVEY §8b `rd_select_topk`) and the §8b names of the
 // entry points that rd_detect.cu implements under longer names.
 //
-//   select_topk_kernel     one CTA per (image, class): `scores[b, :, c] > conf_thresh`
+//   select_topk_kernel     one CTA per (image, group of G <= 8 adjacent classes): `scores[b, :, c] > conf_thresh`
 //                          (eval_refinedet_coco.py:214, detection_refinedet.py:98), the top_k highest in
 //                          score-descending order (eval :222 `argsort()[::-1][:top_k]`, box_utils.py:242-244).
 //
 // The fused stage never materialises this list (its per-class CTAs select, sort and resolve in one pass);
-// the kernel here serves callers that want the candidate lists themselves.  No workspace: the MSB-first
-// 8-bit radix select re-scans the class column (81 CTAs of an image read the same 5.3 MB, L2-resident)
-// instead of keeping an n-entry key list, the ≤ top_k selected keys are sorted in shared memory.
+// the kernel here serves callers that want the candidate lists themselves.  No workspace.
+//
+// Memory behaviour: `scores` is [B,P,C] row-major, so one class is a column with a stride of C floats — a
+// CTA per class with lane = row pulls a whole 32-byte sector per 4-byte score and spends 32 L1 wavefronts per
+// warp load (measured 0.36 ms per batch at config 3, four to five strided passes of the radix select).  A CTA
+// therefore owns G adjacent classes and maps lane = (row, class): a warp load covers 32/G rows x 4*G
+// contiguous bytes.  ONE scan appends the keys of every class to its own shared-memory list (capacity `cap` >= top_k, normally 2*top_k); lists are then sorted
+// together (one bitonic network over all G lists) and the first min(n, top_k) entries leave.  Only a class
+// with more than `cap` candidates falls back to the MSB-first 8-bit radix select over its column (re-scans,
+// L2-resident) to find the top_k-th key before its list is filled.
 #include "rd_common.cuh"
 
 namespace rd {
 
-constexpr int kSelectThreads = 256;
+constexpr int kSelectThreads = 512;
+constexpr int kSelectMaxGroup = 8;
 
 __host__ __device__ inline int select_pow2(int v) {
     int p = 1;
@@ -21,31 +29,19 @@ __host__ __device__ inline int select_pow2(int v) {
     return p;
 }
 
-__global__ void __launch_bounds__(kSelectThreads)
-select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_thresh, int top_k, int first_class,
-                   int* __restrict__ idx_out, float* __restrict__ score_out, int* __restrict__ count_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t misc[4];      // 0 fill counter, 1 digit, 2 need, 3 done
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
-    const int c = blockIdx.x, b = blockIdx.y;
+// Radix select of the top_k-th largest key of one class column (n > top_k candidates); CTA-wide, returns the
+// key such that exactly top_k candidate keys are >= it (keys are unique: the anchor index is part of the key).
+__device__ unsigned long long select_threshold_key(const float* __restrict__ col, int P, int C, float conf_thresh,
+                                                   int top_k, uint32_t* hist, uint32_t* misc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t slot = ((size_t)b * C + c) * (size_t)top_k;
-    if (c < first_class) {            // background is never evaluated (eval :213, detection_refinedet.py:97)
-        if (tid == 0) count_out[b * C + c] = 0;
-        return;
-    }
-    const float* col = scores + (size_t)b * P * C + c;
-
-    unsigned long long prefix = 0, thresh_key = 0;
-    int need = top_k, n = 0;
-    bool take_all = false;
+    unsigned long long prefix = 0;
+    int need = top_k;
     for (int shift = 56; shift >= 0; shift -= 8) {
         for (int i = tid; i < 256; i += kSelectThreads) hist[i] = 0;
         __syncthreads();
         for (int p = tid; p < P; p += kSelectThreads) {
             const float s = __ldg(col + (size_t)p * C);
-            if (s > conf_thresh) {    // NaN fails the compare, like the reference's mask
+            if (s > conf_thresh) {
                 const unsigned long long k = make_key(s, (uint32_t)p);
                 if (shift == 56 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
             }
@@ -62,7 +58,6 @@ select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_th
                 const uint32_t o = __shfl_down_sync(kFullMask, v, d);
                 if (lane + d < 32) v += o;
             }
-            const uint32_t total = __shfl_sync(kFullMask, v, 0);
             uint32_t cum = v - sum;   // keys in the digits owned by higher lanes
             int found = -1;
             uint32_t new_need = 0;
@@ -74,7 +69,6 @@ select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_th
                 }
                 cum += loc[q];
             }
-            if (shift == 56 && lane == 0) misc[0] = total;
             if (found >= 0) {
                 misc[1] = (uint32_t)found;
                 misc[2] = new_need;
@@ -82,55 +76,120 @@ select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_th
             }
         }
         __syncthreads();
-        if (shift == 56) {
-            n = (int)misc[0];
-            if (n <= top_k) { take_all = true; __syncthreads(); break; }
-        }
         prefix = (prefix << 8) | misc[1];
         need = (int)misc[2];
         const bool done = misc[3] != 0;
         __syncthreads();
-        if (done || shift == 0) { thresh_key = prefix << shift; break; }
+        if (done || shift == 0) return prefix << shift;
     }
-    const int m = n < top_k ? n : top_k;
-    if (m == 0) {
-        if (tid == 0) count_out[b * C + c] = 0;
-        return;
-    }
-    if (take_all) thresh_key = 0;
-    if (tid == 0) misc[0] = 0;
+    return 0ull;
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_thresh, int top_k, int first_class,
+                   int G, int cap, int* __restrict__ idx_out, float* __restrict__ score_out,
+                   int* __restrict__ count_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t misc[4];
+    __shared__ uint32_t cnt[kSelectMaxGroup];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);     // [G][cap]
+    const int cbase = blockIdx.x * G, b = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int nact = (C - cbase) < G ? (C - cbase) : G;
+    if (tid < kSelectMaxGroup) cnt[tid] = 0;
     __syncthreads();
-    for (int p = tid; p < P; p += kSelectThreads) {
-        const float s = __ldg(col + (size_t)p * C);
-        if (s > conf_thresh) {
-            const unsigned long long k = make_key(s, (uint32_t)p);
-            if (k >= thresh_key) {
-                const uint32_t pos = atomicAdd(&misc[0], 1u);
-                if (pos < (uint32_t)m) keys[pos] = k;
+
+    // ---- one scan: append the keys of every class of the group to its list ---------------------------------
+    // lane = (row r, class g): a warp load covers 32/G consecutive rows x the group's G adjacent classes, i.e.
+    // 32/G pieces of 4*G contiguous bytes (1-2 sectors each) instead of 32 sectors for 32 scores
+    const float* rows = scores + (size_t)b * P * C + cbase;
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int gshift = __ffs(G) - 1;                        // G is a power of two
+        const int g = lane & (G - 1), r = lane >> gshift;
+        const int rpw = 32 >> gshift;                           // rows per warp load
+        const int stride = (kSelectThreads >> 5) * rpw;         // rows per CTA step
+        // classes below first_class (background) are never evaluated (eval :213, detection_refinedet.py:97)
+        const bool cls_ok = g < nact && cbase + g >= first_class;
+        unsigned long long* list = keys + (size_t)g * cap;
+        constexpr int kUnroll = 8;                              // independent loads in flight per thread
+        const size_t step = (size_t)stride * C;                 // floats between two rows of this lane
+        int p0 = warp * rpw + r;
+        const float* q = rows + g + (size_t)p0 * C;
+        for (; p0 < P; p0 += kUnroll * stride, q += kUnroll * step) {
+            float s[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)                   // == thresh: not a candidate
+                s[u] = (cls_ok && p0 + u * stride < P) ? __ldg(q + u * step) : conf_thresh;
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (s[u] > conf_thresh) {                       // NaN fails the compare, like the reference's mask
+                    const uint32_t pos = atomicAdd(&cnt[g], 1u);
+                    if (pos < (uint32_t)cap) list[pos] = make_key(s[u], (uint32_t)(p0 + u * stride));
+                }
             }
         }
     }
-    const int Kp = select_pow2(m);
-    for (int i = m + tid; i < Kp; i += kSelectThreads) keys[i] = 0ull;      // below every real key
     __syncthreads();
-    for (int k = 2; k <= Kp; k <<= 1) {           // bitonic sort, descending
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (Kp >> 1); t += kSelectThreads) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int l = i + j;
-                const bool desc = (i & k) == 0;
-                const unsigned long long a = keys[i], bb = keys[l];
-                if ((a < bb) == desc) { keys[i] = bb; keys[l] = a; }
+
+    // ---- rare: a class with more candidates than the list holds -> exact top_k by radix select ------------
+    for (int g = 0; g < nact; ++g) {
+        if ((int)cnt[g] <= cap) continue;                       // uniform over the CTA
+        const float* col = rows + g;
+        const unsigned long long thresh_key = select_threshold_key(col, P, C, conf_thresh, top_k, hist, misc);
+        if (tid == 0) misc[0] = 0;
+        __syncthreads();
+        for (int p = tid; p < P; p += kSelectThreads) {
+            const float s = __ldg(col + (size_t)p * C);
+            if (s > conf_thresh) {
+                const unsigned long long k = make_key(s, (uint32_t)p);
+                if (k >= thresh_key) {
+                    const uint32_t pos = atomicAdd(&misc[0], 1u);
+                    if (pos < (uint32_t)top_k) keys[(size_t)g * cap + pos] = k;
+                }
             }
-            __syncthreads();
+        }
+        __syncthreads();
+        if (tid == 0) cnt[g] = (uint32_t)top_k;                 // exactly top_k keys are >= thresh_key
+        __syncthreads();
+    }
+
+    // ---- sort all lists together, descending ---------------------------------------------------------------
+    int nmax = 0;
+    for (int g = 0; g < nact; ++g) nmax = (int)cnt[g] > nmax ? (int)cnt[g] : nmax;
+    if (nmax > 0) {
+        const int Kp = select_pow2(nmax);                       // <= cap (a power of two)
+        for (int g = 0; g < nact; ++g)
+            for (int i = (int)cnt[g] + tid; i < Kp; i += kSelectThreads) keys[(size_t)g * cap + i] = 0ull;   // below every real key
+        __syncthreads();
+        const int half = Kp >> 1, work = nact * half, hshift = __ffs(half) - 1;     // half is a power of two (or 0)
+        for (int k = 2; k <= Kp; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int w = tid; w < work; w += kSelectThreads) {
+                    const int g = w >> hshift, t = w & (half - 1);
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                    const int l = i + j;
+                    const bool desc = (i & k) == 0;
+                    unsigned long long* kg = keys + (size_t)g * cap;
+                    const unsigned long long a = kg[i], bb = kg[l];
+                    if ((a < bb) == desc) { kg[i] = bb; kg[l] = a; }
+                }
+                __syncthreads();
+            }
         }
     }
-    for (int t = tid; t < m; t += kSelectThreads) {
-        const unsigned long long k = keys[t];
-        idx_out[slot + t] = (int)key_index(k);
-        if (score_out) score_out[slot + t] = key_score(k);
+    for (int g = 0; g < nact; ++g) {
+        const int n = (int)cnt[g];
+        const int m = n < top_k ? n : top_k;
+        const size_t slot = ((size_t)b * C + cbase + g) * (size_t)top_k;
+        for (int t = tid; t < m; t += kSelectThreads) {
+            const unsigned long long k = keys[(size_t)g * cap + t];
+            idx_out[slot + t] = (int)key_index(k);
+            if (score_out) score_out[slot + t] = key_score(k);
+        }
+        if (tid == 0) count_out[b * C + cbase + g] = m;
     }
-    if (tid == 0) count_out[b * C + c] = m;
 }
 
 }  // namespace rd
@@ -144,14 +203,23 @@ int rd_select_topk(const float* scores, int B, int P, int C, float conf_thresh, 
     if (!scores || !idx_out || !count_out || B <= 0 || P <= 0 || C <= 0 || top_k <= 0 || first_class < 0)
         return RD_ERR_BAD_ARG;
     if (B > 65535) return RD_ERR_UNSUPPORTED;
-    const int cap = top_k < P ? top_k : P;
-    if (cap > 4 * RD_MAX_NMS_BOXES) return RD_ERR_UNSUPPORTED;          // 128 KB of keys in shared memory
-    const size_t smem = (size_t)select_pow2(cap) * 8;
+    const int need = top_k < P ? top_k : P;                       // a list must hold the selected keys
+    if (need > 4 * RD_MAX_NMS_BOXES) return RD_ERR_UNSUPPORTED;   // 128 KB of keys in shared memory
+    // list capacity: twice top_k when that still leaves room for several classes per CTA (64 KB budget,
+    // 3 CTAs/SM); never more than the P candidates a class can have
+    int cap = select_pow2(need);
+    const int roomy = select_pow2((long long)2 * top_k < (long long)P ? 2 * top_k : P);
+    if (roomy > cap && (size_t)roomy * 8 * 4 <= (64u << 10)) cap = roomy;
+    int G = kSelectMaxGroup;
+    while (G > 1 && (size_t)G * cap * 8 > (64u << 10)) G >>= 1;
+    if (G > C) G = select_pow2(C);
+    if (G > kSelectMaxGroup) G = kSelectMaxGroup;
+    const size_t smem = (size_t)G * cap * 8;
     static size_t s_smem[kMaxDevices];
     cudaError_t e = ensure_dynamic_smem(select_topk_kernel, smem, s_smem);
     if (e != cudaSuccess) return (int)e;
-    select_topk_kernel<<<dim3((unsigned)C, (unsigned)B), kSelectThreads, smem, (cudaStream_t)stream>>>(
-        scores, P, C, conf_thresh, top_k, first_class, idx_out, score_out, count_out);
+    select_topk_kernel<<<dim3((unsigned)((C + G - 1) / G), (unsigned)B), kSelectThreads, smem, (cudaStream_t)stream>>>(
+        scores, P, C, conf_thresh, top_k, first_class, G, cap, idx_out, score_out, count_out);
     note_launch();
     RD_CHECK_LAUNCH();
     return 0;
