@@ -113,19 +113,32 @@ select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_th
         // classes below first_class (background) are never evaluated (eval :213, detection_refinedet.py:97)
         const bool cls_ok = g < nact && cbase + g >= first_class;
         unsigned long long* list = keys + (size_t)g * cap;
+        unsigned cmask = 0;                                     // lanes of this lane's class
+        for (int l = g; l < 32; l += G) cmask |= 1u << l;
+        const unsigned lt_mask = (1u << lane) - 1u;
         constexpr int kUnroll = 8;                              // independent loads in flight per thread
         const size_t step = (size_t)stride * C;                 // floats between two rows of this lane
-        int p0 = warp * rpw + r;
-        const float* q = rows + g + (size_t)p0 * C;
-        for (; p0 < P; p0 += kUnroll * stride, q += kUnroll * step) {
+        const float* q = rows + g + (size_t)(warp * rpw + r) * C;
+        // the loop bound is warp-uniform (first row of the warp's piece): the ballots below need all 32 lanes
+        for (int pw = warp * rpw; pw < P; pw += kUnroll * stride, q += kUnroll * step) {
+            const int p0 = pw + r;
             float s[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u)                   // == thresh: not a candidate
                 s[u] = (cls_ok && p0 + u * stride < P) ? __ldg(q + u * step) : conf_thresh;
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                if (s[u] > conf_thresh) {                       // NaN fails the compare, like the reference's mask
-                    const uint32_t pos = atomicAdd(&cnt[g], 1u);
+                const bool cand = s[u] > conf_thresh;           // NaN fails the compare, like the reference's mask
+                const unsigned bal = __ballot_sync(kFullMask, cand);
+                if (bal == 0) continue;                         // warp-uniform
+                // the lanes of one class reserve their list slots with ONE shared-memory atomic
+                const unsigned peers = bal & cmask;
+                const int leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (cand && lane == leader) base = atomicAdd(&cnt[g], (uint32_t)__popc(peers));
+                base = __shfl_sync(kFullMask, base, leader < 0 ? 0 : leader);
+                if (cand) {
+                    const uint32_t pos = base + (uint32_t)__popc(peers & lt_mask);
                     if (pos < (uint32_t)cap) list[pos] = make_key(s[u], (uint32_t)(p0 + u * stride));
                 }
             }
