@@ -24,7 +24,9 @@ inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&hig
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     size_t& hw = high_water[(unsigned)dev % kMaxDevices];
-    if (hw == 0) hw = 48 * 1024;                       // the default limit needs no opt-in
+    // The 48 KB that need no opt-in cover STATIC + dynamic shared memory; the kernels here hold at most a few
+    // KB of static arrays, so anything above 40 KB of dynamic memory opts in (once per kernel and device).
+    if (hw == 0) hw = 40 * 1024;
     if (bytes <= hw) return cudaSuccess;
     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e == cudaSuccess) hw = bytes;

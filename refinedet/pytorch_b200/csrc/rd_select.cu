@@ -10,12 +10,14 @@
 //
 // Memory behaviour: `scores` is [B,P,C] row-major, so one class is a column with a stride of C floats — a
 // CTA per class with lane = row pulls a whole 32-byte sector per 4-byte score and spends 32 L1 wavefronts per
-// warp load (measured 0.36 ms per batch at config 3, four to five strided passes of the radix select).  A CTA
-// therefore owns G adjacent classes and maps lane = (row, class): a warp load covers 32/G rows x 4*G
-// contiguous bytes.  ONE scan appends the keys of every class to its own shared-memory list (capacity `cap` >= top_k, normally 2*top_k); lists are then sorted
-// together (one bitonic network over all G lists) and the first min(n, top_k) entries leave.  Only a class
-// with more than `cap` candidates falls back to the MSB-first 8-bit radix select over its column (re-scans,
-// L2-resident) to find the top_k-th key before its list is filled.
+// warp load (first version: 0.36 ms per batch at config 3, four to five strided passes of a radix select).  A
+// CTA therefore owns G adjacent classes and maps lane = (row, class): a warp load covers 32/G rows x 4*G
+// contiguous bytes.  ONE scan appends the candidate ANCHORS of every class to its own shared-memory list
+// (16-bit entries when P <= 65536; capacity `cap` >= top_k, normally 2*top_k), so 8 classes and the sort buffer
+// fit 48 KB and all CTAs of a config-3 batch are resident at once.  Keys (score bits, ~anchor) are then built
+// from a gather of the listed scores (L2-resident), several classes at a time when their lists are short,
+// sorted with one bitonic network and the first min(n, top_k) entries leave.  Only a class with more than `cap`
+// candidates falls back to the MSB-first 8-bit radix select over its column (re-scans) for its exact top_k.
 #include "rd_common.cuh"
 
 namespace rd {
@@ -85,22 +87,45 @@ __device__ unsigned long long select_threshold_key(const float* __restrict__ col
     return 0ull;
 }
 
+// Sorts `nseg` key segments of Kp keys (stride Kp) in `buf`, descending, with one bitonic network.
+__device__ __forceinline__ void sort_segments_desc(unsigned long long* buf, int nseg, int Kp) {
+    const int half = Kp >> 1, work = nseg * half, hshift = __ffs(half) - 1;      // Kp is a power of two
+    for (int k = 2; k <= Kp; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int w = threadIdx.x; w < work; w += kSelectThreads) {
+                const int q = w >> hshift, t = w & (half - 1);
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i + j;
+                const bool desc = (i & k) == 0;
+                unsigned long long* kg = buf + (size_t)q * Kp;
+                const unsigned long long a = kg[i], bb = kg[l];
+                if ((a < bb) == desc) { kg[i] = bb; kg[l] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// IdxT: anchor index type of the candidate lists (uint16_t when P <= 65536: 2 bytes per candidate keep
+// 8 classes x 2*top_k candidates + the sort buffer within 48 KB, so every CTA of a config-3 batch is resident).
+template <typename IdxT>
 __global__ void __launch_bounds__(kSelectThreads)
 select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_thresh, int top_k, int first_class,
-                   int G, int cap, int* __restrict__ idx_out, float* __restrict__ score_out,
+                   int G, int cap, int sb, int* __restrict__ idx_out, float* __restrict__ score_out,
                    int* __restrict__ count_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t misc[4];
     __shared__ uint32_t cnt[kSelectMaxGroup];
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);     // [G][cap]
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(smem_raw);            // [sb] keys, sb >= cap
+    IdxT* lists = reinterpret_cast<IdxT*>(smem_raw + (size_t)sb * 8);                          // [G][cap] anchors
     const int cbase = blockIdx.x * G, b = blockIdx.y;
     const int tid = threadIdx.x;
     const int nact = (C - cbase) < G ? (C - cbase) : G;
     if (tid < kSelectMaxGroup) cnt[tid] = 0;
     __syncthreads();
 
-    // ---- one scan: append the keys of every class of the group to its list ---------------------------------
+    // ---- one scan: append the candidate anchors of every class of the group to its list ---------------------
     // lane = (row r, class g): a warp load covers 32/G consecutive rows x the group's G adjacent classes, i.e.
     // 32/G pieces of 4*G contiguous bytes (1-2 sectors each) instead of 32 sectors for 32 scores
     const float* rows = scores + (size_t)b * P * C + cbase;
@@ -112,7 +137,7 @@ select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_th
         const int stride = (kSelectThreads >> 5) * rpw;         // rows per CTA step
         // classes below first_class (background) are never evaluated (eval :213, detection_refinedet.py:97)
         const bool cls_ok = g < nact && cbase + g >= first_class;
-        unsigned long long* list = keys + (size_t)g * cap;
+        IdxT* list = lists + (size_t)g * cap;
         unsigned cmask = 0;                                     // lanes of this lane's class
         for (int l = g; l < 32; l += G) cmask |= 1u << l;
         const unsigned lt_mask = (1u << lane) - 1u;
@@ -139,69 +164,79 @@ select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_th
                 base = __shfl_sync(kFullMask, base, leader < 0 ? 0 : leader);
                 if (cand) {
                     const uint32_t pos = base + (uint32_t)__popc(peers & lt_mask);
-                    if (pos < (uint32_t)cap) list[pos] = make_key(s[u], (uint32_t)(p0 + u * stride));
+                    if (pos < (uint32_t)cap) list[pos] = (IdxT)(p0 + u * stride);
                 }
             }
         }
     }
     __syncthreads();
 
-    // ---- rare: a class with more candidates than the list holds -> exact top_k by radix select ------------
-    for (int g = 0; g < nact; ++g) {
-        if ((int)cnt[g] <= cap) continue;                       // uniform over the CTA
-        const float* col = rows + g;
-        const unsigned long long thresh_key = select_threshold_key(col, P, C, conf_thresh, top_k, hist, misc);
-        if (tid == 0) misc[0] = 0;
-        __syncthreads();
-        for (int p = tid; p < P; p += kSelectThreads) {
-            const float s = __ldg(col + (size_t)p * C);
-            if (s > conf_thresh) {
-                const unsigned long long k = make_key(s, (uint32_t)p);
-                if (k >= thresh_key) {
-                    const uint32_t pos = atomicAdd(&misc[0], 1u);
-                    if (pos < (uint32_t)top_k) keys[(size_t)g * cap + pos] = k;
-                }
-            }
-        }
-        __syncthreads();
-        if (tid == 0) cnt[g] = (uint32_t)top_k;                 // exactly top_k keys are >= thresh_key
-        __syncthreads();
-    }
-
-    // ---- sort all lists together, descending ---------------------------------------------------------------
-    int nmax = 0;
-    for (int g = 0; g < nact; ++g) nmax = (int)cnt[g] > nmax ? (int)cnt[g] : nmax;
-    if (nmax > 0) {
-        const int Kp = select_pow2(nmax);                       // <= cap (a power of two)
-        for (int g = 0; g < nact; ++g)
-            for (int i = (int)cnt[g] + tid; i < Kp; i += kSelectThreads) keys[(size_t)g * cap + i] = 0ull;   // below every real key
-        __syncthreads();
-        const int half = Kp >> 1, work = nact * half, hshift = __ffs(half) - 1;     // half is a power of two (or 0)
-        for (int k = 2; k <= Kp; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int w = tid; w < work; w += kSelectThreads) {
-                    const int g = w >> hshift, t = w & (half - 1);
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                    const int l = i + j;
-                    const bool desc = (i & k) == 0;
-                    unsigned long long* kg = keys + (size_t)g * cap;
-                    const unsigned long long a = kg[i], bb = kg[l];
-                    if ((a < bb) == desc) { kg[i] = bb; kg[l] = a; }
-                }
-                __syncthreads();
-            }
-        }
-    }
+    // ---- keys, sort, emit: classes whose lists fit are packed into the sort buffer several at a time; a class
+    //      with more candidates than its list holds gets its exact top_k by radix select, alone --------------------
+    int nmax = 1;
     for (int g = 0; g < nact; ++g) {
         const int n = (int)cnt[g];
-        const int m = n < top_k ? n : top_k;
-        const size_t slot = ((size_t)b * C + cbase + g) * (size_t)top_k;
-        for (int t = tid; t < m; t += kSelectThreads) {
-            const unsigned long long k = keys[(size_t)g * cap + t];
-            idx_out[slot + t] = (int)key_index(k);
-            if (score_out) score_out[slot + t] = key_score(k);
+        if (n <= cap && n > nmax) nmax = n;
+    }
+    const int Kp = select_pow2(nmax);                           // segment size of the packed classes (<= cap)
+    const int nper = sb / Kp;                                   // segments the sort buffer holds
+    int g0 = 0;
+    while (g0 < nact) {                                         // every quantity below is uniform over the CTA
+        int nseg, kp;
+        if ((int)cnt[g0] > cap) {
+            const float* col = rows + g0;
+            const unsigned long long thresh_key = select_threshold_key(col, P, C, conf_thresh, top_k, hist, misc);
+            kp = select_pow2(top_k);                            // top_k < n <= P and top_k <= cap here
+            for (int i = top_k + tid; i < kp; i += kSelectThreads) sortbuf[i] = 0ull;
+            if (tid == 0) misc[0] = 0;
+            __syncthreads();
+            for (int p = tid; p < P; p += kSelectThreads) {
+                const float s = __ldg(col + (size_t)p * C);
+                if (s > conf_thresh) {
+                    const unsigned long long k = make_key(s, (uint32_t)p);
+                    if (k >= thresh_key) {                      // exactly top_k keys are
+                        const uint32_t pos = atomicAdd(&misc[0], 1u);
+                        if (pos < (uint32_t)top_k) sortbuf[pos] = k;
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) cnt[g0] = (uint32_t)top_k;
+            nseg = 1;
+        } else {
+            nseg = 1;
+            while (nseg < nper && g0 + nseg < nact && (int)cnt[g0 + nseg] <= cap) ++nseg;
+            kp = Kp;
+            const int kshift = __ffs(kp) - 1;
+            for (int w = tid; w < nseg * kp; w += kSelectThreads) {
+                const int qs = w >> kshift, i = w & (kp - 1);
+                unsigned long long k = 0ull;                    // padding: below every real key
+                if (i < (int)cnt[g0 + qs]) {
+                    const uint32_t p = (uint32_t)lists[(size_t)(g0 + qs) * cap + i];
+                    k = make_key(__ldg(rows + (size_t)p * C + g0 + qs), p);
+                }
+                sortbuf[w] = k;
+            }
         }
-        if (tid == 0) count_out[b * C + cbase + g] = m;
+        __syncthreads();
+        sort_segments_desc(sortbuf, nseg, kp);
+        const int kshift = __ffs(kp) - 1;
+        for (int w = tid; w < nseg * kp; w += kSelectThreads) {
+            const int qs = w >> kshift, t = w & (kp - 1);
+            const int n = (int)cnt[g0 + qs];
+            if (t < (n < top_k ? n : top_k)) {
+                const unsigned long long k = sortbuf[w];
+                const size_t slot = ((size_t)b * C + cbase + g0 + qs) * (size_t)top_k;
+                idx_out[slot + t] = (int)key_index(k);
+                if (score_out) score_out[slot + t] = key_score(k);
+            }
+        }
+        if (tid < nseg) {
+            const int n = (int)cnt[g0 + tid];
+            count_out[b * C + cbase + g0 + tid] = n < top_k ? n : top_k;
+        }
+        __syncthreads();                                        // the sort buffer is reused by the next pack
+        g0 += nseg;
     }
 }
 
@@ -216,23 +251,35 @@ int rd_select_topk(const float* scores, int B, int P, int C, float conf_thresh, 
     if (!scores || !idx_out || !count_out || B <= 0 || P <= 0 || C <= 0 || top_k <= 0 || first_class < 0)
         return RD_ERR_BAD_ARG;
     if (B > 65535) return RD_ERR_UNSUPPORTED;
-    const int need = top_k < P ? top_k : P;                       // a list must hold the selected keys
+    const int need = top_k < P ? top_k : P;                       // the sort buffer must hold the selected keys
     if (need > 4 * RD_MAX_NMS_BOXES) return RD_ERR_UNSUPPORTED;   // 128 KB of keys in shared memory
-    // list capacity: twice top_k when that still leaves room for several classes per CTA (64 KB budget,
-    // 3 CTAs/SM); never more than the P candidates a class can have
+    const bool narrow = P <= 65536;                               // anchor indices fit 16 bits
+    const size_t isz = narrow ? 2 : 4;
+    // shared memory per CTA = sb * 8 [sort buffer, sb >= cap keys] + cap * G * isz [lists].  List capacity:
+    // twice top_k when 8 classes then still fit the 64 KB budget (48 KB at top_k = 1000: 4 CTAs/SM); never more
+    // than the P candidates a class can have.
     int cap = select_pow2(need);
     const int roomy = select_pow2((long long)2 * top_k < (long long)P ? 2 * top_k : P);
-    if (roomy > cap && (size_t)roomy * 8 * 4 <= (64u << 10)) cap = roomy;
+    if (roomy > cap && (size_t)roomy * (8 + kSelectMaxGroup * isz) <= (64u << 10)) cap = roomy;
     int G = kSelectMaxGroup;
-    while (G > 1 && (size_t)G * cap * 8 > (64u << 10)) G >>= 1;
+    while (G > 1 && (size_t)cap * (8 + G * isz) > (64u << 10)) G >>= 1;
     if (G > C) G = select_pow2(C);
     if (G > kSelectMaxGroup) G = kSelectMaxGroup;
-    const size_t smem = (size_t)G * cap * 8;
-    static size_t s_smem[kMaxDevices];
-    cudaError_t e = ensure_dynamic_smem(select_topk_kernel, smem, s_smem);
+    // a sort buffer of 2*cap keys (two full lists sorted at a time) was measured: 64 KB instead of 48 KB per CTA
+    // costs more (cfg 3 sparse 0.092 -> 0.150 ms, dense 0.45 -> 0.54 ms) than the halved number of sort rounds saves
+    const int sb = cap;
+    const size_t smem = (size_t)sb * 8 + (size_t)cap * G * isz;
+    static size_t s_smem16[kMaxDevices], s_smem32[kMaxDevices];
+    cudaError_t e = narrow ? ensure_dynamic_smem(select_topk_kernel<uint16_t>, smem, s_smem16)
+                           : ensure_dynamic_smem(select_topk_kernel<uint32_t>, smem, s_smem32);
     if (e != cudaSuccess) return (int)e;
-    select_topk_kernel<<<dim3((unsigned)((C + G - 1) / G), (unsigned)B), kSelectThreads, smem, (cudaStream_t)stream>>>(
-        scores, P, C, conf_thresh, top_k, first_class, G, cap, idx_out, score_out, count_out);
+    const dim3 grid((unsigned)((C + G - 1) / G), (unsigned)B);
+    if (narrow)
+        select_topk_kernel<uint16_t><<<grid, kSelectThreads, smem, (cudaStream_t)stream>>>(
+            scores, P, C, conf_thresh, top_k, first_class, G, cap, sb, idx_out, score_out, count_out);
+    else
+        select_topk_kernel<uint32_t><<<grid, kSelectThreads, smem, (cudaStream_t)stream>>>(
+            scores, P, C, conf_thresh, top_k, first_class, G, cap, sb, idx_out, score_out, count_out);
     note_launch();
     RD_CHECK_LAUNCH();
     return 0;

@@ -43,6 +43,7 @@ def _check(rd, scores, thr, top_k, first_class=1):
     (1, 16320, 2, 16384, -1.0),     # everything passes: n = P <= top_k, 128 KB of keys
     (2, 300, 4, 50, 2.0),           # nothing passes
     (1, 16320, 2, 1000, 0.01),      # config 5 dense: ~12 k candidates > list capacity -> radix-select fallback
+    (1, 70000, 3, 100, 0.3),        # P > 65536: 32-bit candidate lists
     (2, 3000, 11, 200, 0.001),      # 11 classes = one full group of 8 + a ragged one; every list overflows
 ])
 def test_select_topk_vs_oracle(rd, B, P, C, top_k, thr):
