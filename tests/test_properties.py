@@ -96,3 +96,51 @@ def test_gpu_nms_normalised_equals_oracle(bs, thr, top_k):
     ek, ec = bo.nms(boxes, scores, thr, top_k)
     keep, count = rd.box_utils.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), thr, top_k)
     assert count == ec and np.array_equal(keep.cpu().numpy(), ek)
+
+
+@st.composite
+def score_tensor(draw):
+    B, P, C = draw(st.integers(1, 2)), draw(st.integers(1, 90)), draw(st.integers(1, 11))
+    levels = draw(st.integers(2, 40))                 # few distinct values: runs of exact ties cross the top_k cut
+    vals = draw(st.lists(st.integers(0, levels), min_size=B * P * C, max_size=B * P * C))
+    return (np.array(vals, F32) / F32(levels)).reshape(B, P, C)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(score_tensor(), st.sampled_from([0.0, 0.01, 0.5]), st.sampled_from([1, 3, 16, 200]), st.integers(0, 2))
+def test_oracle_select_topk_invariants(scores, thr, top_k, first_class):
+    lists = bo.select_topk(scores, thr, top_k, first_class)
+    B, P, C = scores.shape
+    for b in range(B):
+        for c in range(C):
+            idx = lists[b][c]
+            col = scores[b, :, c]
+            if c < first_class:
+                assert idx.size == 0
+                continue
+            n = int((col > F32(thr)).sum())
+            assert idx.size == min(n, top_k) and len(set(idx.tolist())) == idx.size
+            s = col[idx]
+            assert (s > F32(thr)).all()
+            # score descending, lower anchor first inside a run of equal scores
+            assert all(s[i] > s[i + 1] or (s[i] == s[i + 1] and idx[i] < idx[i + 1]) for i in range(idx.size - 1))
+            if idx.size:                               # nothing left out beats the last one taken
+                rest = np.setdiff1d(np.where(col > F32(thr))[0], idx)
+                assert all(col[r] < s[-1] or (col[r] == s[-1] and r > idx[-1]) for r in rest)
+
+
+@pytest.mark.gpu
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(score_tensor(), st.sampled_from([0.0, 0.01, 0.5]), st.sampled_from([1, 3, 16, 200]), st.integers(0, 2))
+def test_gpu_select_topk_equals_oracle(scores, thr, top_k, first_class):
+    import torch
+    import refinedet.pytorch_b200 as rd
+    idx, sc, counts = rd.box_utils.select_topk(torch.from_numpy(scores).cuda(), thr, top_k, first_class)
+    idx, sc, counts = idx.cpu().numpy(), sc.cpu().numpy(), counts.cpu().numpy()
+    ref = bo.select_topk(scores, thr, top_k, first_class)
+    for b in range(scores.shape[0]):
+        for c in range(scores.shape[2]):
+            n = ref[b][c].size
+            assert counts[b, c] == n
+            assert np.array_equal(idx[b, c, :n], ref[b][c])
+            assert np.array_equal(sc[b, c, :n], scores[b, ref[b][c], c])
