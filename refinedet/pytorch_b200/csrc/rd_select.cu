@@ -16,8 +16,10 @@
 // (16-bit entries when P <= 65536; capacity `cap` >= top_k, normally 2*top_k), so 8 classes and the sort buffer
 // fit 48 KB and all CTAs of a config-3 batch are resident at once.  Keys (score bits, ~anchor) are then built
 // from a gather of the listed scores (L2-resident), several classes at a time when their lists are short,
-// sorted with one bitonic network and the first min(n, top_k) entries leave.  Only a class with more than `cap`
-// candidates falls back to the MSB-first 8-bit radix select over its column (re-scans) for its exact top_k.
+// sorted with one bitonic network and the first min(n, top_k) entries leave.  A class with more than top_k
+// candidates first finds its top_k-th key with an MSB-first 8-bit radix select — over the listed scores staged
+// in shared memory when the list held them all, over its column (re-scans) when the list overflowed — so that
+// only top_k keys are sorted.
 #include "rd_common.cuh"
 
 namespace rd {
@@ -31,22 +33,22 @@ __host__ __device__ inline int select_pow2(int v) {
     return p;
 }
 
-// Radix select of the top_k-th largest key of one class column (n > top_k candidates); CTA-wide, returns the
-// key such that exactly top_k candidate keys are >= it (keys are unique: the anchor index is part of the key).
-__device__ unsigned long long select_threshold_key(const float* __restrict__ col, int P, int C, float conf_thresh,
-                                                   int top_k, uint32_t* hist, uint32_t* misc) {
+// Radix select of the top_k-th largest of the keys `key_at(0 .. n-1)` (0 = not a candidate, skipped; more than
+// top_k candidates); CTA-wide, returns the key such that exactly top_k candidate keys are >= it (keys are
+// unique: the anchor index is part of the key).
+template <typename KeyAt>
+__device__ __forceinline__ unsigned long long select_threshold_key(int n, KeyAt key_at, int top_k, uint32_t* hist,
+                                                                   uint32_t* misc) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long prefix = 0;
     int need = top_k;
     for (int shift = 56; shift >= 0; shift -= 8) {
         for (int i = tid; i < 256; i += kSelectThreads) hist[i] = 0;
         __syncthreads();
-        for (int p = tid; p < P; p += kSelectThreads) {
-            const float s = __ldg(col + (size_t)p * C);
-            if (s > conf_thresh) {
-                const unsigned long long k = make_key(s, (uint32_t)p);
-                if (shift == 56 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
-            }
+        for (int i = tid; i < n; i += kSelectThreads) {
+            const unsigned long long k = key_at(i);
+            if (k != 0ull && (shift == 56 || (k >> (shift + 8)) == prefix))
+                atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
         }
         __syncthreads();
         if (warp == 0) {
@@ -171,41 +173,71 @@ select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_th
     }
     __syncthreads();
 
-    // ---- keys, sort, emit: classes whose lists fit are packed into the sort buffer several at a time; a class
-    //      with more candidates than its list holds gets its exact top_k by radix select, alone --------------------
+    // ---- keys, sort, emit.  Three kinds of classes (n = candidates, all decisions uniform over the CTA):
+    //   n <= limit        keys built from a gather of the listed scores, several classes packed into the sort
+    //                     buffer at a time, sorted, first min(n, top_k) emitted
+    //   limit < n <= cap  (only when the buffer has room: cap >= 2 * pow2(top_k), limit = top_k) the listed
+    //                     scores are staged in the upper half of the buffer, a shared-memory radix select finds
+    //                     the top_k-th key, the top_k keys are compacted into the lower half: a 1024-key sort
+    //                     instead of a 2048-key one at top_k = 1000
+    //   n > cap           the list overflowed: radix select over the class column (re-scans), alone
+    const int kp_top = select_pow2(top_k);
+    const bool smem_select = top_k < cap && cap >= 2 * kp_top;
+    const int limit = smem_select ? top_k : cap;
     int nmax = 1;
     for (int g = 0; g < nact; ++g) {
         const int n = (int)cnt[g];
-        if (n <= cap && n > nmax) nmax = n;
+        if (n <= limit && n > nmax) nmax = n;
     }
     const int Kp = select_pow2(nmax);                           // segment size of the packed classes (<= cap)
     const int nper = sb / Kp;                                   // segments the sort buffer holds
     int g0 = 0;
-    while (g0 < nact) {                                         // every quantity below is uniform over the CTA
-        int nseg, kp;
-        if ((int)cnt[g0] > cap) {
+    while (g0 < nact) {
+        int nseg = 1, kp = kp_top;
+        const int n0 = (int)cnt[g0];
+        if (n0 > cap) {
             const float* col = rows + g0;
-            const unsigned long long thresh_key = select_threshold_key(col, P, C, conf_thresh, top_k, hist, misc);
-            kp = select_pow2(top_k);                            // top_k < n <= P and top_k <= cap here
-            for (int i = top_k + tid; i < kp; i += kSelectThreads) sortbuf[i] = 0ull;
+            auto key_at = [&](int p) -> unsigned long long {
+                const float s = __ldg(col + (size_t)p * C);
+                return s > conf_thresh ? make_key(s, (uint32_t)p) : 0ull;
+            };
+            const unsigned long long thresh_key = select_threshold_key(P, key_at, top_k, hist, misc);
+            for (int i = top_k + tid; i < kp; i += kSelectThreads) sortbuf[i] = 0ull;     // top_k <= kp <= cap here
             if (tid == 0) misc[0] = 0;
             __syncthreads();
             for (int p = tid; p < P; p += kSelectThreads) {
-                const float s = __ldg(col + (size_t)p * C);
-                if (s > conf_thresh) {
-                    const unsigned long long k = make_key(s, (uint32_t)p);
-                    if (k >= thresh_key) {                      // exactly top_k keys are
-                        const uint32_t pos = atomicAdd(&misc[0], 1u);
-                        if (pos < (uint32_t)top_k) sortbuf[pos] = k;
-                    }
+                const unsigned long long k = key_at(p);
+                if (k >= thresh_key && k != 0ull) {             // exactly top_k keys are
+                    const uint32_t pos = atomicAdd(&misc[0], 1u);
+                    if (pos < (uint32_t)top_k) sortbuf[pos] = k;
                 }
             }
             __syncthreads();
             if (tid == 0) cnt[g0] = (uint32_t)top_k;
-            nseg = 1;
+        } else if (n0 > limit) {
+            uint32_t* sc32 = reinterpret_cast<uint32_t*>(sortbuf + (cap >> 1));           // upper half: [cap] words
+            const IdxT* lst = lists + (size_t)g0 * cap;
+            for (int i = tid; i < n0; i += kSelectThreads)
+                sc32[i] = float_to_ordered(__ldg(rows + (size_t)lst[i] * C + g0));
+            __syncthreads();
+            auto key_at = [&](int i) -> unsigned long long {
+                return ((unsigned long long)sc32[i] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)lst[i]);
+            };
+            const unsigned long long thresh_key = select_threshold_key(n0, key_at, top_k, hist, misc);
+            for (int i = top_k + tid; i < kp; i += kSelectThreads) sortbuf[i] = 0ull;     // kp <= cap / 2: lower half
+            if (tid == 0) misc[0] = 0;
+            __syncthreads();
+            for (int i = tid; i < n0; i += kSelectThreads) {
+                const unsigned long long k = key_at(i);
+                if (k >= thresh_key) {
+                    const uint32_t pos = atomicAdd(&misc[0], 1u);
+                    if (pos < (uint32_t)top_k) sortbuf[pos] = k;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) cnt[g0] = (uint32_t)top_k;
         } else {
-            nseg = 1;
-            while (nseg < nper && g0 + nseg < nact && (int)cnt[g0 + nseg] <= cap) ++nseg;
+            while (nseg < nper && g0 + nseg < nact && (int)cnt[g0 + nseg] <= limit) ++nseg;
             kp = Kp;
             const int kshift = __ffs(kp) - 1;
             for (int w = tid; w < nseg * kp; w += kSelectThreads) {

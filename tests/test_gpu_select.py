@@ -43,6 +43,7 @@ def _check(rd, scores, thr, top_k, first_class=1):
     (1, 16320, 2, 16384, -1.0),     # everything passes: n = P <= top_k, 128 KB of keys
     (2, 300, 4, 50, 2.0),           # nothing passes
     (1, 16320, 2, 1000, 0.01),      # config 5 dense: ~12 k candidates > list capacity -> radix-select fallback
+    (2, 1500, 9, 1000, -1.0),       # top_k < n = 1500 <= list capacity 2048: shared-memory radix select, 1024-key sort
     (1, 70000, 3, 100, 0.3),        # P > 65536: 32-bit candidate lists
     (2, 3000, 11, 200, 0.001),      # 11 classes = one full group of 8 + a ragged one; every list overflows
 ])
@@ -62,7 +63,7 @@ def test_select_topk_ties_nan_and_first_class(rd):
     scores[0, 5, 1] = float('nan')               # NaN > thr is false: never a candidate (eval :214)
     scores[1, 9, 2] = float('inf')
     s = scores.numpy()
-    for top_k in (1, 10, 100, 699, 700, 2000):
+    for top_k in (1, 10, 100, 300, 699, 700, 2000):       # 300: n ~ 560 in (top_k, capacity]: smem select through ties
         _check(rd, s, 0.2, top_k)
     counts = _check(rd, s, 0.2, 50, first_class=0)      # background column too
     assert counts[:, 0].all()
