@@ -113,8 +113,8 @@ __device__ __forceinline__ void sort_segments_desc(unsigned long long* buf, int 
 template <typename IdxT>
 __global__ void __launch_bounds__(kSelectThreads)
 select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_thresh, int top_k, int first_class,
-                   int G, int cap, int sb, int* __restrict__ idx_out, float* __restrict__ score_out,
-                   int* __restrict__ count_out) {
+                   int slot_stride, int G, int cap, int sb, int* __restrict__ idx_out, float* __restrict__ score_out,
+                   int* __restrict__ count_out) {      // top_k here is min(top_k, P); slot_stride the caller's top_k
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t misc[4];
@@ -258,7 +258,7 @@ select_topk_kernel(const float* __restrict__ scores, int P, int C, float conf_th
             const int n = (int)cnt[g0 + qs];
             if (t < (n < top_k ? n : top_k)) {
                 const unsigned long long k = sortbuf[w];
-                const size_t slot = ((size_t)b * C + cbase + g0 + qs) * (size_t)top_k;
+                const size_t slot = ((size_t)b * C + cbase + g0 + qs) * (size_t)slot_stride;
                 idx_out[slot + t] = (int)key_index(k);
                 if (score_out) score_out[slot + t] = key_score(k);
             }
@@ -283,7 +283,7 @@ int rd_select_topk(const float* scores, int B, int P, int C, float conf_thresh, 
     if (!scores || !idx_out || !count_out || B <= 0 || P <= 0 || C <= 0 || top_k <= 0 || first_class < 0)
         return RD_ERR_BAD_ARG;
     if (B > 65535) return RD_ERR_UNSUPPORTED;
-    const int need = top_k < P ? top_k : P;                       // the sort buffer must hold the selected keys
+    const int need = top_k < P ? top_k : P;                       // what a class can yield; the kernel's top_k
     if (need > 4 * RD_MAX_NMS_BOXES) return RD_ERR_UNSUPPORTED;   // 128 KB of keys in shared memory
     const bool narrow = P <= 65536;                               // anchor indices fit 16 bits
     const size_t isz = narrow ? 2 : 4;
@@ -291,7 +291,7 @@ int rd_select_topk(const float* scores, int B, int P, int C, float conf_thresh, 
     // twice top_k when 8 classes then still fit the 64 KB budget (48 KB at top_k = 1000: 4 CTAs/SM); never more
     // than the P candidates a class can have.
     int cap = select_pow2(need);
-    const int roomy = select_pow2((long long)2 * top_k < (long long)P ? 2 * top_k : P);
+    const int roomy = select_pow2(2 * need < P ? 2 * need : P);
     if (roomy > cap && (size_t)roomy * (8 + kSelectMaxGroup * isz) <= (64u << 10)) cap = roomy;
     int G = kSelectMaxGroup;
     while (G > 1 && (size_t)cap * (8 + G * isz) > (64u << 10)) G >>= 1;
@@ -308,10 +308,10 @@ int rd_select_topk(const float* scores, int B, int P, int C, float conf_thresh, 
     const dim3 grid((unsigned)((C + G - 1) / G), (unsigned)B);
     if (narrow)
         select_topk_kernel<uint16_t><<<grid, kSelectThreads, smem, (cudaStream_t)stream>>>(
-            scores, P, C, conf_thresh, top_k, first_class, G, cap, sb, idx_out, score_out, count_out);
+            scores, P, C, conf_thresh, need, first_class, top_k, G, cap, sb, idx_out, score_out, count_out);
     else
         select_topk_kernel<uint32_t><<<grid, kSelectThreads, smem, (cudaStream_t)stream>>>(
-            scores, P, C, conf_thresh, top_k, first_class, G, cap, sb, idx_out, score_out, count_out);
+            scores, P, C, conf_thresh, need, first_class, top_k, G, cap, sb, idx_out, score_out, count_out);
     note_launch();
     RD_CHECK_LAUNCH();
     return 0;
