@@ -217,3 +217,60 @@ def test_multibox_loss_no_positives(ref):
     r = bo.multibox_loss([t.numpy() for t in preds], [t.numpy() for t in targets], 4, 0.5, 3, 1.5, True, VAR)
     assert float(ll) == float(lc) == 0.0 and tuple(ll.shape) == (1,)
     assert r['loss_l'] == r['loss_c'] == 0.0 and r['N'] == 0
+
+
+def test_full_size_config3_and_config4(ref):
+    """BASELINE.json sizes (P = 16,320 anchors of RefineDet512; C = 81; 50 ground-truth boxes per image) through
+    the reference and the oracle: a3 forward, the a4 candidate + NMS loop on the sparse generator, and the ODM
+    match targets — one image each (the reference's Python loops take seconds per image)."""
+    pri = ref.PriorBox(ref.coco['512']).forward()
+    P, C = pri.shape[0], 81
+    assert P == 16320
+    for seed in range(900, 920):                      # SURVEY 8d sparse generator; redraw until tie-free per class
+        g = torch.Generator().manual_seed(seed)
+        d = 2.0 * torch.randn(1, P, generator=g) - 8.0
+        arm_conf = torch.softmax(torch.stack([torch.zeros(1, P), d], -1), -1)
+        logits = 1.5 * torch.randn(1, P, C, generator=g)
+        logits[..., 0] += 4.0
+        odm_conf = torch.softmax(logits, -1)
+        arm_loc, odm_loc = torch.randn(1, P, 4, generator=g), torch.randn(1, P, 4, generator=g)
+        live = odm_conf[0][arm_conf[0, :, 1] > 0.01]
+        if all(len(set(col[col > 0.01].tolist())) == int((col > 0.01).sum()) for col in live.t()[1:]):
+            break
+    else:
+        pytest.fail('no tie-free draw in 20 seeds')
+    det = ref.Detect(C, 512, 0, 1000, 0.01, 0.45, 0.01, 500)
+    conf_r = odm_conf.clone()
+    boxes_r, scores_r = det.forward(arm_loc, arm_conf, odm_loc, conf_r, pri)
+    conf_o = odm_conf.numpy().copy()
+    boxes_o, scores_o = bo.detect_forward(arm_loc.numpy(), arm_conf.numpy(), odm_loc.numpy(), conf_o, pri.numpy(),
+                                          0.01, VAR)
+    np.testing.assert_allclose(boxes_o, boxes_r.numpy(), rtol=1e-5, atol=1e-6)
+    assert np.array_equal(scores_o, scores_r.numpy()) and np.array_equal(conf_o, conf_r.numpy())
+    # a4 (eval_refinedet_coco.py:205-232) with the reference's own py_cpu_nms on the reference's boxes
+    scale = np.array([512.0] * 4, np.float32)
+    dets_o, _ = bo.detect_stage_eval(boxes_r[0].numpy(), scores_r[0].numpy(), scale, 0.01, 1000, 0.45, 500)
+    px = boxes_r[0].numpy() * scale[None, :]
+    sc = scores_r[0].numpy()
+    n_rows = 0
+    for j in range(1, C):
+        inds = np.where(sc[:, j] > 0.01)[0]
+        if len(inds) == 0:
+            assert dets_o[j].shape[0] == 0
+            continue
+        c_scores = sc[inds, j]
+        assert len(set(c_scores.tolist())) == len(c_scores)              # the tie-free draw chosen above
+        order = c_scores.argsort()[::-1][:1000]
+        c_dets = np.hstack((px[inds][order], c_scores[order][:, None])).astype(np.float32)
+        keep = ref.py_cpu_nms(c_dets, 0.45)[:500]
+        assert np.array_equal(dets_o[j], c_dets[keep, :]), j
+        n_rows += len(keep)
+    assert n_rows > 5000
+    # config 4: ODM match targets, 50 ground-truth boxes
+    t = ref.mg.gen_targets(g, 1, 50, C)[0]
+    a = 0.1 * torch.randn(P, 4, generator=g)
+    loc_t, conf_t = torch.zeros(1, P, 4), torch.zeros(1, P, dtype=torch.long)
+    ref.bu.refine_match(0.5, t[:, :4], pri, list(VAR), t[:, 4], loc_t, conf_t, 0, a)
+    lo, co, _, _ = bo.refine_match(0.5, t[:, :4].numpy(), pri.numpy(), VAR, t[:, 4].numpy(), a.numpy())
+    assert np.array_equal(co, conf_t[0].numpy()) and (co > 0).sum() >= 50
+    np.testing.assert_allclose(lo, loc_t[0].numpy(), rtol=2e-5, atol=3e-5)
