@@ -89,10 +89,34 @@ __device__ __forceinline__ unsigned long long select_threshold_key(int n, KeyAt 
     return 0ull;
 }
 
+// Stages k = 2 .. 32 of the bitonic network below for the 32 keys a warp holds (one per lane, i = index of the
+// lane's key in the buffer): 15 compare-exchange steps over shuffles instead of shared memory + CTA barriers.
+__device__ __forceinline__ unsigned long long warp_bitonic32(unsigned long long a, int i) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool desc = (i & k) == 0;
+            const bool lower = (i & j) == 0;
+            const unsigned long long b = __shfl_xor_sync(kFullMask, a, j);
+            a = (lower == desc) ? (a > b ? a : b) : (a < b ? a : b);
+        }
+    }
+    return a;
+}
+
 // Sorts `nseg` key segments of Kp keys (stride Kp) in `buf`, descending, with one bitonic network.
 __device__ __forceinline__ void sort_segments_desc(unsigned long long* buf, int nseg, int Kp) {
     const int half = Kp >> 1, work = nseg * half, hshift = __ffs(half) - 1;      // Kp is a power of two
-    for (int k = 2; k <= Kp; k <<= 1) {
+    int kstart = 2;
+    if (Kp >= 64) {                   // runs of 32 in registers (segment offsets are multiples of 64: i & k unchanged)
+        const int total = nseg * Kp, lane = threadIdx.x & 31;
+        for (int base = (threadIdx.x >> 5) * 32; base < total; base += (kSelectThreads >> 5) * 32)
+            buf[base + lane] = warp_bitonic32(buf[base + lane], base + lane);
+        __syncthreads();
+        kstart = 64;
+    }
+    for (int k = kstart; k <= Kp; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int w = threadIdx.x; w < work; w += kSelectThreads) {
                 const int q = w >> hshift, t = w & (half - 1);
