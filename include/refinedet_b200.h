@@ -65,6 +65,14 @@ extern "C" {
  * into the stage — the separate read+write pass over odm_conf disappears.  Scores agree with
  * torch.softmax to fp32 rounding (the sum is reduced in a different order). */
 #define RD_INPUT_LOGITS     4
+/* TEST-ONLY, OR-able into the nms_flags of the fused detect stage: force one instantiation of the per-class
+ * kernel (nms_small_kernel) regardless of the grid-size heuristic, so that the parity tests can hold every
+ * instantiation to the oracle at small sizes too.  0 = choose automatically (the only value product code uses). */
+#define RD_DEBUG_INSTANCE_SHIFT 8
+#define RD_DEBUG_INSTANCE_MASK  (3 << RD_DEBUG_INSTANCE_SHIFT)
+#define RD_DEBUG_INSTANCE_256   (1 << RD_DEBUG_INSTANCE_SHIFT)   /* <= 256 candidates, 128 threads  */
+#define RD_DEBUG_INSTANCE_1024  (2 << RD_DEBUG_INSTANCE_SHIFT)   /* <= 1024 candidates, 256 threads */
+#define RD_DEBUG_INSTANCE_512   (3 << RD_DEBUG_INSTANCE_SHIFT)   /* <= 512 candidates, 128 threads  */
 /* output row layout of the fused detect stage */
 #define RD_ROW_BOX_SCORE    0  /* x1,y1,x2,y2,score  (eval_refinedet_coco.py:226) */
 #define RD_ROW_SCORE_BOX    1  /* score,x1,y1,x2,y2  (detection_refinedet.py:106-108) */
@@ -97,6 +105,11 @@ RD_API int rd_detect_forward(const float* arm_loc, const float* arm_conf, const 
                       float* odm_conf, const float* priors, int B, int P, int C,
                       float objectness_thre, float v0, float v1,
                       float* boxes_out, float* scores_out, void* stream);
+
+/* The in-place half of the above on its own (detection_refinedet.py:79-81, the first step of
+ * forward_python_nms): rows r of odm_conf[rows,C] with arm_conf[r,1] <= objectness_thre become all-zero. */
+RD_API int rd_arm_zero_rows(const float* arm_conf, float* odm_conf, long long rows, int C,
+                     float objectness_thre, void* stream);
 
 /* SURVEY §8b name of the same entry point ("rd_decode_filter": ARM-objectness filter + two-stage decode) */
 RD_API int rd_decode_filter(const float* arm_loc, const float* arm_conf, const float* odm_loc,
@@ -208,6 +221,15 @@ RD_API size_t rd_exchange_slot_bytes(int B, int C, int capacity_rows);
 RD_API int rd_pack_scatter(const int* counts, const float* dets, int B, int C, int max_out,
                            int* scratch_offsets, void* const* peer_slots_host, int world, int rank,
                            int slot_B, int capacity_rows, void* stream);
+/* Same, with the two knobs of the copy phase.  The rows are first packed into this rank's OWN slot (local HBM), then
+ * the slot's used prefix is streamed to the peers as 16-byte words:
+ *   multicast_slot != NULL: the address of this rank's slot in the MULTICAST mapping of the symmetric buffer
+ *                           (NVSwitch replicates every store to all ranks: `multimem.st`, the rows leave the GPU once);
+ *   multicast_slot == NULL: unicast P2P stores, one group of CTAs per peer.
+ *   copy_ctas: CTAs per destination (<= 0 = default).  scratch_offsets may be NULL. */
+RD_API int rd_pack_scatter_ex(const int* counts, const float* dets, int B, int C, int max_out,
+                           int* scratch_offsets, void* const* peer_slots_host, int world, int rank,
+                           int slot_B, int capacity_rows, void* multicast_slot, int copy_ctas, void* stream);
 
 /* ---- stand-alone NMS ------------------------------------------------------- */
 RD_API size_t rd_nms_workspace_bytes(int n);
@@ -267,7 +289,8 @@ RD_API int rd_hnm_select(const float* loss_c, const unsigned char* pos, int B, i
 /* ---- loss tail of RefineDetMultiBoxLoss (refinedet_multibox_loss.py:96-139) ---------- */
 /* Per row r of conf[rows,C] (rows = B*P, 2 <= C <= 128):
  *   lse_out[r] = log(sum_c exp(conf[r,c]))         (log_sum_exp, box_utils.py:208-216; max-subtracted)
- *   ce_out[r]  = lse_out[r] - conf[r, conf_t[r]]   (the mining loss of :114 = the cross-entropy term of :130)
+ *   ce_out[r]  = lse_out[r] - conf[r, conf_t[r]]   (the mining loss of :114 = the cross-entropy term of :130);
+ *                NaN when conf_t[r] is outside [0, C) (the reference's gather raises there)
  *   pos_out[r] = conf_t[r] > 0, and — when arm_conf[rows,2] (LOGITS) is given — not
  *                softmax(arm_conf[r])[1] <= theta  (:96-101)                                   */
 RD_API int rd_conf_loss(const float* conf, const long long* conf_t, const float* arm_conf, float theta,

@@ -28,6 +28,8 @@ RD_MAX_NMS_BOXES = 4096
 RD_MAX_GT = 1024
 RD_NMS_NORMALISED, RD_NMS_PIXEL_PLUS1, RD_NMS_SUPPRESS_EQ = 0, 1, 2
 RD_INPUT_LOGITS = 4
+RD_DEBUG_INSTANCE_SHIFT = 8
+RD_DEBUG_INSTANCE_256, RD_DEBUG_INSTANCE_1024, RD_DEBUG_INSTANCE_512 = 1 << 8, 2 << 8, 3 << 8
 RD_ROW_BOX_SCORE, RD_ROW_SCORE_BOX = 0, 1
 
 _P = c_void_p
@@ -45,6 +47,7 @@ _SIGNATURES = {
                                   _P, _P, _P]),
     'rd_decode_filter': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float,
                                  _P, _P, _P]),
+    'rd_arm_zero_rows': (c_int, [_P, _P, ctypes.c_longlong, c_int, c_float, _P]),
     'rd_select_topk': (c_int, [_P, c_int, c_int, c_int, c_float, c_int, c_int, _P, _P, _P, _P]),
     'rd_detect': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float,
                           c_int, c_int, _P, c_int, c_int, c_float, c_float, _P, c_size_t,
@@ -66,6 +69,7 @@ _SIGNATURES = {
     'rd_pack_detections': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P]),
     'rd_exchange_slot_bytes': (c_size_t, [c_int, c_int, c_int]),
     'rd_pack_scatter': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    'rd_pack_scatter_ex': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
     'rd_nms_workspace_bytes': (c_size_t, [c_int]),
     'rd_nms': (c_int, [_P, _P, c_int, c_float, c_int, c_int, _P, c_size_t, _P, _P, _P]),
     'rd_nms_host': (c_int, [_P, _P, _P, c_int, c_int, c_float, c_int]),

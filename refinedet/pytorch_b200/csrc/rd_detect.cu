@@ -178,6 +178,23 @@ detect_forward_kernel(const float4* __restrict__ arm_loc, const float2* __restri
     }
 }
 
+// The in-place half of a3 on its own (detection_refinedet.py:79-81 inside forward_python_nms): rows of odm_conf
+// whose anchor fails the ARM gate become all-zero.  Warp per 32 rows, lanes stride over the rows' contiguous span.
+__global__ void __launch_bounds__(kCollectThreads)
+zero_filtered_rows_kernel(const float2* __restrict__ arm_conf, float* odm_conf, long long total, int C, float obj_thre) {
+    const int lane = threadIdx.x & 31;
+    const long long g0 = (((long long)blockIdx.x * kCollectThreads + threadIdx.x) >> 5) * 32;
+    if (g0 >= total) return;
+    const long long g = g0 + lane;
+    const bool pass = g < total && !(ldg_stream2(arm_conf + g).y <= obj_thre);
+    const unsigned mask = __ballot_sync(kFullMask, pass);
+    if (mask == kFullMask) return;
+    const int nelem = (int)min((long long)32, total - g0) * C;
+    float* conf = odm_conf + g0 * C;
+    for (int e = lane; e < nelem; e += 32)
+        if (!((mask >> (e / C)) & 1u)) conf[e] = 0.f;
+}
+
 // ---------------------------------------------------------------------------------------
 // K1: ARM filter + decode + node registration + class-major score matrix
 // grid = (S, B); CTA (s, b) owns anchors [s*1024, s*1024 + 1024) of image b: 8 warps x 128 anchors.
@@ -215,7 +232,13 @@ struct GraphOut {            // what collect contributes to the per-image suppre
 struct ArmGate {
     float thre;
     float gap_lo, gap_hi;     // d < gap_lo: fails for sure; d > gap_hi: passes for sure (logits only)
+    int admit_all;            // conf_thresh < 0: the reference zeroes the scores of ARM-filtered anchors
+                              // (detection_refinedet.py:40-42) and then tests `score > conf_thresh`
+                              // (eval_refinedet_coco.py:214), so filtered anchors ARE candidates, with score 0:
+                              // every anchor becomes a node, filtered ones carry an all-zero score row
 };
+constexpr unsigned short kFlatFiltered = 0x8000;   // s_flat entry: node of an ARM-filtered anchor (admit_all only)
+constexpr unsigned short kFlatMask = 0x7fff;
 template <bool kLogits>
 __device__ __forceinline__ bool arm_pass(float2 ac, const ArmGate& g) {
     if (!kLogits) return !(ac.y <= g.thre);
@@ -260,16 +283,19 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
 #pragma unroll
             for (int k = 0; k < 4; ++k) o4[k] = __ldg(arm_conf + img + a + k * kCollectThreads);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) before += arm_pass<kLogits>(o4[k], gate) ? 1 : 0;
+            for (int k = 0; k < 4; ++k) before += (gate.admit_all || arm_pass<kLogits>(o4[k], gate)) ? 1 : 0;
         }
         before = __reduce_add_sync(kFullMask, before);
     }
     unsigned pmask[kChunks];
+    unsigned filt = 0;                       // bit ch: this lane's anchor of chunk ch is a node only because of admit_all
     int npass = 0;
 #pragma unroll
     for (int ch = 0; ch < kChunks; ++ch) {
         const int a = a0 + ch * 32 + lane;
-        const bool pass = (a < P) && arm_pass<kLogits>(obj[ch], gate);
+        const bool arm_ok = arm_pass<kLogits>(obj[ch], gate);
+        const bool pass = (a < P) && (arm_ok || gate.admit_all);
+        if (pass && !arm_ok) filt |= 1u << ch;
         pmask[ch] = __ballot_sync(kFullMask, pass);
         npass += __popc(pmask[ch]);
     }
@@ -287,7 +313,8 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
 #pragma unroll
         for (int ch = 0; ch < kChunks; ++ch) {
             if ((pmask[ch] >> lane) & 1u)
-                s_flat[pos + __popc(pmask[ch] & ((1u << lane) - 1u))] = (unsigned short)(wib * (32 * kChunks) + ch * 32 + lane);
+                s_flat[pos + __popc(pmask[ch] & ((1u << lane) - 1u))] =
+                    (unsigned short)((wib * (32 * kChunks) + ch * 32 + lane) | (((filt >> ch) & 1u) ? kFlatFiltered : 0));
             pos += __popc(pmask[ch]);
         }
     }
@@ -296,7 +323,7 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
     // decode inputs of the first kCollectThreads nodes: issue the loads now, use them after the row phase
     float4 pre_al = make_float4(0.f, 0.f, 0.f, 0.f), pre_ol = pre_al, pre_pr = pre_al;
     if ((int)threadIdx.x < tot) {
-        const int a = s * kSliceAnchors + s_flat[threadIdx.x];
+        const int a = s * kSliceAnchors + (s_flat[threadIdx.x] & kFlatMask);
         pre_al = ldg_stream4(arm_loc + img + a);
         pre_ol = ldg_stream4(odm_loc + img + a);
         pre_pr = __ldg(priors + a);
@@ -321,8 +348,9 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
                 int off[kRowBatch];
 #pragma unroll
                 for (int k = 0; k < kRowBatch; ++k) {
-                    const bool rv = rl0 + k < rows_here;
-                    const int a = s * kSliceAnchors + (rv ? s_flat[t0 + rl0 + k] : 0);
+                    const unsigned short fe = rl0 + k < rows_here ? s_flat[t0 + rl0 + k] : kFlatFiltered;
+                    const bool rv = !(fe & kFlatFiltered);               // filtered nodes: all-zero row, nothing fetched
+                    const int a = s * kSliceAnchors + (fe & kFlatMask);
                     const float* row = odm_conf + (img + a) * C;
                     const float* line0 = reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(row) & ~(uintptr_t)127);
                     off[k] = (int)(row - line0);                               // 0..31
@@ -344,8 +372,9 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
             } else {
 #pragma unroll
                 for (int k = 0; k < kRowBatch; ++k) {
-                    const bool rv = rl0 + k < rows_here;
-                    const int a = s * kSliceAnchors + (rv ? s_flat[t0 + rl0 + k] : 0);
+                    const unsigned short fe = rl0 + k < rows_here ? s_flat[t0 + rl0 + k] : kFlatFiltered;
+                    const bool rv = !(fe & kFlatFiltered);
+                    const int a = s * kSliceAnchors + (fe & kFlatMask);
                     const float* row = odm_conf + (img + a) * C;
 #pragma unroll
                     for (int sgm = 0; sgm < 4; ++sgm) {
@@ -374,8 +403,9 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
                     }
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(kFullMask, sum, d);
+                    const bool zero_row = gate.admit_all && rl0 + k < rows_here && (s_flat[t0 + rl0 + k] & kFlatFiltered);
 #pragma unroll
-                    for (int sgm = 0; sgm < 4; ++sgm) v[k][sgm] = v[k][sgm] / sum;
+                    for (int sgm = 0; sgm < 4; ++sgm) v[k][sgm] = zero_row ? 0.f : v[k][sgm] / sum;
                 }
             }
 #pragma unroll
@@ -405,7 +435,7 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
     const float invx = scale.x > 0.f ? (float)kCols / scale.x : 0.f;
     const float invy = scale.y > 0.f ? (float)kCols / scale.y : 0.f;
     for (int t = threadIdx.x; t < tot; t += kCollectThreads) {
-        const int a = s * kSliceAnchors + s_flat[t];
+        const int a = s * kSliceAnchors + (s_flat[t] & kFlatMask);
         float4 bx = t < kCollectThreads ? refine_decode(pre_al, pre_ol, pre_pr, v0, v1)
                                         : refine_decode(ldg_stream4(arm_loc + img + a), ldg_stream4(odm_loc + img + a),
                                                         __ldg(priors + a), v0, v1);
@@ -577,9 +607,11 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
             }
             // dense neighbourhoods (dozens of overlapping boxes per object): drain the list between rounds of
             // items instead of letting it fill up and testing the excess pairs one thread at a time
+            //  The decision is taken CTA-wide by the barrier itself (__syncthreads_or): a thread that read npairs
+            //  on its own could skip the branch and append pairs of the next round before a slower warp has
+            //  looked at the counter, and the barriers inside the branch would pair up at different places.
             if (q0 + kGraphThreads < nitems) {
-                __syncthreads();
-                if (G.npairs >= kGraphPairCap / 2) {
+                if (__syncthreads_or(G.npairs >= kGraphPairCap / 2)) {
                     const int cnt = min(G.npairs, kGraphPairCap);
                     for (int p = tid; p < cnt; p += kGraphThreads) {
                         const uint32_t e = G.pairs[p];
@@ -990,29 +1022,92 @@ __global__ void pack_rows_kernel(const int* __restrict__ counts, const int* __re
 // ---------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
 struct PeerSlots { unsigned char* p[kMaxPeers]; };
+constexpr int kPackThreads = 128;
 
-__global__ void pack_scatter_kernel(const int* __restrict__ counts, const int* __restrict__ offsets,
-                                    const float* __restrict__ dets, int max_out, int nbc, int B, int C, PeerSlots peers,
-                                    int world, int rank, int capacity, size_t rows_off) {
+// exclusive prefix of counts at bc (sum over [0, bc)) computed by the calling CTA: the list is a few thousand
+// ints from L2, cheaper than a separate single-CTA scan kernel in front of the copy
+__device__ __forceinline__ int cta_count_prefix(const int* __restrict__ counts, int bc, int* s_red) {
+    int acc = 0;
+    for (int i = threadIdx.x; i < bc; i += blockDim.x) acc += __ldg(counts + i);
+    acc = __reduce_add_sync(kFullMask, acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    int tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
+    __syncthreads();
+    return tot;
+}
+
+// phase 1: pack this rank's rows into ITS OWN slot of its own exchange buffer (local HBM), write counts + header
+__global__ void __launch_bounds__(kPackThreads)
+pack_local_kernel(const int* __restrict__ counts, const float* __restrict__ dets, int max_out, int nbc, int B, int C,
+                  unsigned char* slot, int capacity, size_t rows_off, int* __restrict__ offsets_out) {
+    __shared__ int s_red[kPackThreads / 32];
     const int bc = blockIdx.x;
-    if (bc == nbc) {                       // last CTA: header + counts
-        for (int k = 0; k < world; ++k) {
-            unsigned char* slot = peers.p[(rank + 1 + k) % world];
-            int* hdr = reinterpret_cast<int*>(slot);
-            int* cdst = reinterpret_cast<int*>(slot + 256);
-            for (int t = threadIdx.x; t < nbc; t += blockDim.x) cdst[t] = counts[t];
-            if (threadIdx.x == 0) { hdr[0] = min(offsets[nbc], capacity); hdr[1] = B; hdr[2] = C; hdr[3] = offsets[nbc]; }
+    const int off = cta_count_prefix(counts, bc, s_red);
+    if (bc == nbc) {                       // last CTA: header + counts (off = total rows)
+        int* hdr = reinterpret_cast<int*>(slot);
+        int* cdst = reinterpret_cast<int*>(slot + 256);
+        for (int t = threadIdx.x; t < nbc; t += blockDim.x) cdst[t] = counts[t];
+        if (threadIdx.x == 0) {
+            hdr[0] = min(off, capacity); hdr[1] = B; hdr[2] = C; hdr[3] = off;
+            if (offsets_out) offsets_out[nbc] = off;
         }
         return;
     }
+    if (offsets_out && threadIdx.x == 0) offsets_out[bc] = off;
     const int n = counts[bc];
-    const int off = offsets[bc];
     const float* src = dets + (size_t)bc * max_out * 5;
     int len = n * 5;
     if (off + n > capacity) len = max(0, capacity - off) * 5;
-    for (int k = 0; k < world; ++k) {
-        float* dst = reinterpret_cast<float*>(peers.p[(rank + 1 + k) % world] + rows_off) + (size_t)off * 5;
-        for (int t = threadIdx.x; t < len; t += blockDim.x) dst[t] = src[t];
+    float* dst = reinterpret_cast<float*>(slot + rows_off) + (size_t)off * 5;
+    for (int t = threadIdx.x; t < len; t += blockDim.x) dst[t] = src[t];
+}
+
+__device__ __forceinline__ void st_multimem_v4(void* mc_addr, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+
+// phase 2: the local slot [header | counts | rows stored] -> the same slot of every peer's buffer, as a flat stream
+// of 16-byte words (the slot is 256-byte aligned, its regions 256-byte padded: whole words, no tails).
+//   grid = (chunks, targets).  targets = world - 1 unicast destinations (peer order rotated by rank so that the
+//   ranks do not all write to the same peer at once), or ONE multicast destination (kMulticast: the address of the
+//   slot in the multicast mapping of the symmetric buffer -- a single store is replicated to every rank by the
+//   NVSwitch, so the rows leave this GPU once instead of world - 1 times).
+// kUnroll independent 16-byte loads in flight per thread before the stores: NVLink stores are fire-and-forget, the
+// kernel is bound by how fast the SMs can issue them.
+constexpr int kCopyThreads = 256;
+constexpr int kCopyUnroll = 8;
+template <bool kMulticast>
+__global__ void __launch_bounds__(kCopyThreads)
+slot_copy_kernel(const unsigned char* __restrict__ local_slot, PeerSlots peers, unsigned char* mc_slot, int world, int rank,
+                 size_t rows_off) {
+    const int* hdr = reinterpret_cast<const int*>(local_slot);
+    const int stored = hdr[0];
+    const size_t head_words = rows_off / 16;                                  // header + counts region
+    const size_t words = head_words + ((size_t)stored * 20 + 15) / 16;
+    const uint4* src = reinterpret_cast<const uint4*>(local_slot);
+    uint4* dst;
+    if (kMulticast) dst = reinterpret_cast<uint4*>(mc_slot);
+    else dst = reinterpret_cast<uint4*>(peers.p[(rank + 1 + blockIdx.y) % world]);
+    const size_t stride = (size_t)gridDim.x * kCopyThreads;
+    for (size_t w0 = (size_t)blockIdx.x * kCopyThreads + threadIdx.x; w0 < words; w0 += stride * kCopyUnroll) {
+        uint4 v[kCopyUnroll];
+#pragma unroll
+        for (int u = 0; u < kCopyUnroll; ++u) {
+            const size_t w = w0 + u * stride;
+            if (w < words) v[u] = __ldg(src + w);
+        }
+#pragma unroll
+        for (int u = 0; u < kCopyUnroll; ++u) {
+            const size_t w = w0 + u * stride;
+            if (w < words) {
+                if (kMulticast) st_multimem_v4(dst + w, v[u]);
+                else dst[w] = v[u];
+            }
+        }
     }
 }
 
@@ -1043,6 +1138,17 @@ int rd_detect_forward(const float* arm_loc, const float* arm_conf, const float* 
     detect_forward_kernel<<<blocks, kCollectThreads, 0, (cudaStream_t)stream>>>(
         (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
         total, P, C, objectness_thre, v0, v1, (float4*)boxes_out, scores_out);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+int rd_arm_zero_rows(const float* arm_conf, float* odm_conf, long long rows, int C, float objectness_thre, void* stream) {
+    if (!arm_conf || !odm_conf || rows <= 0 || C <= 0) return RD_ERR_BAD_ARG;
+    if ((uintptr_t)arm_conf & 7) return RD_ERR_ALIGNMENT;
+    const long long blocks = (rows + kCollectThreads - 1) / kCollectThreads;
+    zero_filtered_rows_kernel<<<(unsigned)blocks, kCollectThreads, 0, (cudaStream_t)stream>>>(
+        (const float2*)arm_conf, odm_conf, rows, C, objectness_thre);
     note_launch();
     RD_CHECK_LAUNCH();
     return 0;
@@ -1103,6 +1209,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     if (ev) cudaEventRecord(ev[0], st);
     ArmGate gate;
     gate.thre = objectness_thre;
+    gate.admit_all = conf_thresh < 0.f ? 1 : 0;
     gate.gap_lo = INFINITY; gate.gap_hi = -INFINITY;                  // always evaluate the formula ...
     if (objectness_thre > 0.f && objectness_thre < 1.f) {             // ... unless logit(thre) exists
         const double lg = std::log((double)objectness_thre / (1.0 - (double)objectness_thre));
@@ -1172,7 +1279,10 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     }
     if (ev) cudaEventRecord(ev[2], st);
     {   // programmatic dependent launch: the scan + sort of nms_small_kernel run beside graph_kernel
-        const bool wide = (long long)B * (C - 1) <= 2 * 148;       // the grid cannot fill the GPU: footprint is free
+        bool wide = (long long)B * (C - 1) <= 2 * 148;             // the grid cannot fill the GPU: footprint is free
+        const int forced = nms_flags & RD_DEBUG_INSTANCE_MASK;     // test-only override (parity tests of every instance)
+        if (forced == RD_DEBUG_INSTANCE_256) wide = false;
+        else if (forced == RD_DEBUG_INSTANCE_1024) wide = true;
         cudaError_t e = wide ? launch_pdl(nms_small_kernel<kWideCap, kWideThreads, 2>, dim3(C, B), dim3(kWideThreads), 0, st, A)
                              : launch_pdl(nms_small_kernel<kSmallCap, kSmallThreads, RD_SMALL_MINBLOCKS>, dim3(C, B),
                                           dim3(kSmallThreads), 0, st, A);
@@ -1308,23 +1418,40 @@ size_t rd_exchange_slot_bytes(int B, int C, int capacity_rows) {
     return 256 + align_up((size_t)B * C * 4, 256) + align_up((size_t)capacity_rows * 20, 256);
 }
 
-int rd_pack_scatter(const int* counts, const float* dets, int B, int C, int max_out, int* scratch_offsets,
-                    void* const* peer_slots_host, int world, int rank, int slot_B, int capacity_rows, void* stream) {
+int rd_pack_scatter_ex(const int* counts, const float* dets, int B, int C, int max_out, int* scratch_offsets,
+                       void* const* peer_slots_host, int world, int rank, int slot_B, int capacity_rows,
+                       void* multicast_slot, int copy_ctas, void* stream) {
     if (slot_B < B) return RD_ERR_BAD_ARG;
-    if (!counts || !dets || !scratch_offsets || !peer_slots_host || B <= 0 || C <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
+    if (!counts || !dets || !peer_slots_host || B <= 0 || C <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
     if (world <= 0 || world > kMaxPeers || rank < 0 || rank >= world || capacity_rows < 0) return RD_ERR_BAD_ARG;
     PeerSlots ps;
     for (int k = 0; k < kMaxPeers; ++k) ps.p[k] = k < world ? static_cast<unsigned char*>(peer_slots_host[k]) : nullptr;
     for (int k = 0; k < world; ++k) if (!ps.p[k] || ((uintptr_t)ps.p[k] & 255)) return RD_ERR_ALIGNMENT;
+    if (multicast_slot && ((uintptr_t)multicast_slot & 255)) return RD_ERR_ALIGNMENT;
     cudaStream_t st = (cudaStream_t)stream;
-    pack_offsets_kernel<<<1, 1024, 0, st>>>(counts, B * C, scratch_offsets);
+    const size_t rows_off = 256 + align_up((size_t)slot_B * C * 4, 256);
+    unsigned char* local = ps.p[rank];
+    pack_local_kernel<<<B * C + 1, kPackThreads, 0, st>>>(counts, dets, max_out, B * C, B, C, local, capacity_rows,
+                                                          rows_off, scratch_offsets);
     note_launch();
     RD_CHECK_LAUNCH();
-    pack_scatter_kernel<<<B * C + 1, 128, 0, st>>>(counts, scratch_offsets, dets, max_out, B * C, B, C, ps, world, rank,
-                                                   capacity_rows, 256 + align_up((size_t)slot_B * C * 4, 256));
+    if (world == 1) return 0;
+    if (copy_ctas <= 0) copy_ctas = multicast_slot ? 96 : 24;        // CTAs per destination
+    if (multicast_slot)
+        slot_copy_kernel<true><<<dim3(copy_ctas, 1), kCopyThreads, 0, st>>>(local, ps, (unsigned char*)multicast_slot,
+                                                                             world, rank, rows_off);
+    else
+        slot_copy_kernel<false><<<dim3(copy_ctas, world - 1), kCopyThreads, 0, st>>>(local, ps, nullptr, world, rank,
+                                                                                      rows_off);
     note_launch();
     RD_CHECK_LAUNCH();
     return 0;
+}
+
+int rd_pack_scatter(const int* counts, const float* dets, int B, int C, int max_out, int* scratch_offsets,
+                    void* const* peer_slots_host, int world, int rank, int slot_B, int capacity_rows, void* stream) {
+    return rd_pack_scatter_ex(counts, dets, B, C, max_out, scratch_offsets, peer_slots_host, world, rank, slot_B,
+                              capacity_rows, nullptr, 0, stream);
 }
 
 // ---- stand-alone NMS --------------------------------------------------------------------

@@ -127,7 +127,9 @@ conf_loss_kernel(const float* __restrict__ conf, const long long* __restrict__ c
             for (; c < C; ++c) s0 += exp2f((x[c] - m) * kLog2e);
             const float sum = (s0 + s1) + (s2 + s3);
             const float lse = logf(sum) + m;
-            ce_out[r] = lse - x[(int)t];
+            // a label outside [0, C) (dataset / num_classes mismatch) makes the reference's gather raise; here the
+            // row's loss becomes NaN, which poisons loss_c visibly instead of reading past the staged row
+            ce_out[r] = (t >= 0 && t < C) ? lse - x[(int)t] : __int_as_float(0x7fc00000);
             lse_out[r] = lse;
             bool pos = t > 0;
             if (pos && arm_conf && arm_filtered(arm, theta)) pos = false;
@@ -149,7 +151,7 @@ conf_loss2_kernel(const float2* __restrict__ conf, const long long* __restrict__
     const float m = fmaxf(x.x, x.y);
     const float s = expf(x.x - m) + expf(x.y - m);
     const float lse = logf(s) + m;
-    ce_out[r] = lse - (t == 1 ? x.y : x.x);
+    ce_out[r] = t == 1 ? lse - x.y : t == 0 ? lse - x.x : __int_as_float(0x7fc00000);   // label outside {0, 1}: NaN
     lse_out[r] = lse;
     bool pos = t > 0;
     if (pos && arm_conf && arm_filtered(__ldg(arm_conf + r), theta)) pos = false;

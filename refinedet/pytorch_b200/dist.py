@@ -85,16 +85,20 @@ def decode_slots(buf, world, slot_bytes, nbc_capacity):
 
 
 class PeerExchange(object):
-    """All-gather of the compact detections WITHOUT a collective call: every rank's pack kernel stores its
-    counts and packed rows straight into its slot of every peer's buffer (symmetric memory: each buffer is
-    mapped into every process of the node, the stores travel over NVLink / NVSwitch), bracketed by two
-    device-side barriers.  ``B`` = the largest per-rank batch; all ranks construct it collectively.
+    """All-gather of the compact detections WITHOUT a collective call (``rd_pack_scatter_ex``): every rank packs
+    its counts and rows into its own slot of its own buffer, then streams the slot's used prefix into the same
+    slot of every peer's buffer — symmetric memory: each buffer is mapped into every process of the node, the
+    stores travel over NVLink / NVSwitch — bracketed by two device-side barriers.  With NVSwitch multicast
+    (``mode == 'multicast'``) one ``multimem.st`` is replicated to all ranks by the switch, so the rows leave the GPU
+    once instead of ``world - 1`` times; otherwise (``mode == 'p2p'``) one group of CTAs stores to each peer.
+    ``B`` = the largest per-rank batch; all ranks construct it collectively.
 
     Needs ``torch.distributed._symmetric_memory`` (one node, NVLink/PCIe P2P); raises otherwise — callers
     that want a portable path use :func:`gather_packed` (NCCL / gloo)."""
 
-    def __init__(self, B, C, max_out, device, group=None, capacity_rows=None):
+    def __init__(self, B, C, max_out, device, group=None, capacity_rows=None, mode=None, copy_ctas=0):
         import ctypes
+        import os
         import torch.distributed._symmetric_memory as symm_mem
         from ._ffi import lib
         self.group = group if group is not None else dist.group.WORLD
@@ -104,23 +108,38 @@ class PeerExchange(object):
         self.slot_bytes = int(lib().rd_exchange_slot_bytes(self.B, self.C, self.capacity))
         self.buf = symm_mem.empty(self.world * self.slot_bytes, dtype=torch.uint8, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
-        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        off = int(getattr(self.hdl, 'offset', 0) or 0)
+        ptrs = [int(p) + off for p in self.hdl.buffer_ptrs]
         self._peer_slots = (ctypes.c_void_p * self.world)(*[p + self.rank * self.slot_bytes for p in ptrs])
-        self._offsets = torch.empty(self.B * self.C + 1, dtype=torch.int32, device=device)
+        mode = mode or os.environ.get('RD_EXCHANGE_MODE') or 'auto'
+        mc = 0
+        if mode in ('auto', 'multicast') and self.world > 1:
+            try:
+                mc = int(self.hdl.multicast_ptr or 0)
+            except Exception:
+                mc = 0
+            if mode == 'multicast' and not mc:
+                raise RuntimeError('PeerExchange(mode="multicast"): the symmetric buffer has no multicast mapping')
+        self._mc_slot = ctypes.c_void_p(mc + off + self.rank * self.slot_bytes) if mc else ctypes.c_void_p(0)
+        self.mode = 'multicast' if mc else 'p2p'
+        self.copy_ctas = int(copy_ctas or os.environ.get('RD_EXCHANGE_CTAS') or 0)
 
-    def exchange(self, detections):
-        """Asynchronous on the current stream: barrier (peers are done reading the previous round), pack +
-        scatter, barrier (every peer's stores have landed)."""
-        from ._ffi import check, lib, on_device, ptr, stream_ptr
+    def exchange(self, detections, stream=None):
+        """Asynchronous on ``stream`` (default: the current stream): barrier (peers are done reading the previous
+        round), pack + copy, barrier (every peer's stores have landed)."""
+        from ._ffi import check, lib, ptr
         B, C, max_out, _ = detections.dets.shape
         if B > self.B or C != self.C or max_out != self.max_out:
             raise ValueError('detections [%d,%d,%d] do not fit the exchange [%d,%d,%d]'
                              % (B, C, max_out, self.B, self.C, self.max_out))
-        with on_device(self.buf.device):
+        dev = self.buf.device
+        ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.device(dev)
+        with ctx:
+            st = torch.cuda.current_stream(dev).cuda_stream
             self.hdl.barrier(channel=0)
-            check(lib().rd_pack_scatter(ptr(detections.counts), ptr(detections.dets), B, C, max_out,
-                                        ptr(self._offsets), self._peer_slots, self.world, self.rank, self.B,
-                                        self.capacity, stream_ptr()), 'rd_pack_scatter')
+            check(lib().rd_pack_scatter_ex(ptr(detections.counts), ptr(detections.dets), B, C, max_out, None,
+                                           self._peer_slots, self.world, self.rank, self.B, self.capacity,
+                                           self._mc_slot, self.copy_ctas, st), 'rd_pack_scatter_ex')
             self.hdl.barrier(channel=1)
 
     def result(self):

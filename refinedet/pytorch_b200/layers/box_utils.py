@@ -5,6 +5,7 @@ every function takes CUDA tensors and calls ``librefinedet_b200.so`` through ``_
 There is no CPU path.
 """
 import operator
+import threading
 
 import numpy as np
 import torch
@@ -115,32 +116,44 @@ def log_sum_exp(x):
 # matching
 # ---------------------------------------------------------------------------------------------
 LABEL_ODM, LABEL_ARM_BINARY, LABEL_SSD_PLUS1 = 0, 1, 2
-_PAD_CACHE = None
 _is = operator.is_
+_tls = threading.local()            # per-thread: the padded targets of the latest step (see _padded)
+
+
+def clear_pad_cache():
+    """Drop this thread's cached padded targets (they pin the step's target tensors until the next step)."""
+    _tls.pad_cache = None
+
 
 
 # Offsets of the ragged target list travel through a small ring of PINNED staging buffers: a copy from pageable
 # memory makes the driver drain the stream first (CUDA API synchronisation rules), i.e. one hidden device
 # synchronisation per training step.  A slot is reused only after the copy that read it has completed.
-_PIN_SLOTS, _pin_ring, _pin_next = 8, {}, 0
+_PIN_SLOTS = 8
 
 
 def _offsets_to_device(counts, device):
-    global _pin_next
+    """The ring (and its cursor) is per thread and per (device, length); the copy and the event that guards the
+    slot are issued with ``device`` current, so the event is recorded on the stream the copy went to."""
     n = len(counts) + 1
+    rings = getattr(_tls, 'pin_rings', None)
+    if rings is None:
+        rings = _tls.pin_rings = {}
     key = (device.index, n)
-    ring = _pin_ring.get(key)
-    if ring is None:
-        ring = _pin_ring[key] = [(torch.zeros(n, dtype=torch.int32).pin_memory(), torch.cuda.Event())
-                                 for _ in range(_PIN_SLOTS)]
-        for _, ev in ring:
-            ev.record()
-    buf, ev = ring[_pin_next % _PIN_SLOTS]
-    _pin_next += 1
-    ev.synchronize()                                        # normally long complete
-    np.cumsum(counts, out=buf.numpy()[1:])
-    out = buf.to(device, non_blocking=True)
-    ev.record()
+    with on_device(device):
+        st = torch.cuda.current_stream(device)
+        ring = rings.get(key)
+        if ring is None:
+            ring = rings[key] = {'next': 0, 'slots': [(torch.zeros(n, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+                                                      for _ in range(_PIN_SLOTS)]}
+            for _, ev in ring['slots']:
+                ev.record(st)
+        buf, ev = ring['slots'][ring['next'] % _PIN_SLOTS]
+        ring['next'] += 1
+        ev.synchronize()                                    # normally long complete
+        np.cumsum(counts, out=buf.numpy()[1:])
+        out = buf.to(device, non_blocking=True)
+        ev.record(st)
     return out
 
 
@@ -156,11 +169,10 @@ def _padded(targets, device):
     # The ARM and the ODM criterion of a training step pad the same list (train_refinedet.py:252-253): the
     # latest result is kept.  The cache HOLDS the target tensors, so neither their ids nor their storage can
     # be recycled for another batch while the entry is alive; in-place edits show in ``_version``.
-    global _PAD_CACHE
     device = torch.device(device)
     if device.index is None:
         device = torch.device(device.type, torch.cuda.current_device())
-    c = _PAD_CACHE
+    c = getattr(_tls, 'pad_cache', None)
     if c is not None and c[0] == device and len(c[1]) == len(targets) and all(map(_is, targets, c[1])) \
             and [t._version for t in targets] == c[2]:
         return c[3]
@@ -189,7 +201,7 @@ def _padded(targets, device):
             check(lib().rd_pad_targets(ptr(flat), ptr(offsets), B, gmax, ptr(truths), ptr(labels), ptr(gt_count),
                                        stream_ptr()), 'rd_pad_targets')
     out = (truths, labels, gt_count, min(counts))
-    _PAD_CACHE = (device, list(targets), [t._version for t in targets], out)
+    _tls.pad_cache = (device, list(targets), [t._version for t in targets], out)
     return out
 
 

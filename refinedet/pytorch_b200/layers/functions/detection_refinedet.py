@@ -224,7 +224,10 @@ class Detect_RefineDet(object):
         return arm_loc, arm_conf, odm_loc, odm_conf, priors, B, P, C
 
     def _workspace(self, B, P, C, device):
-        key = (B, P, C, device)
+        # keyed by the stream too: the control block must be zero at call start and is re-zeroed by the call's
+        # own kernels, which orders calls on ONE stream only.  A call on another stream gets a fresh workspace
+        # (allocated and reset on that stream) instead of racing on this one.
+        key = (B, P, C, device, stream_ptr(device).value)
         if self._ws_key != key:
             L = lib()
             nbytes = int(L.rd_detect_workspace_bytes(B, P, C))
@@ -254,8 +257,11 @@ class Detect_RefineDet(object):
         self.boxes, self.scores = boxes, scores                  # the reference keeps them on the instance
         return self.boxes, self.scores
 
+    _INSTANCES = {None: 0, 'auto': 0, 256: _ffi.RD_DEBUG_INSTANCE_256, 1024: _ffi.RD_DEBUG_INSTANCE_1024,
+                  512: _ffi.RD_DEBUG_INSTANCE_512}
+
     def detect(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale=None,
-               force_cpu_semantics=False, logits=False):
+               force_cpu_semantics=False, logits=False, instance=None):
         """Fused detect stage as evaluated (eval_refinedet_coco.py:205-232), whole batch:
         ARM filter, two-stage decode, ``boxes *= scale``, per class ``score > conf_thresh``,
         top ``top_k``, pixel(+1) NMS at ``nms_thresh``, first ``keep_top_k`` rows per class.
@@ -380,13 +386,19 @@ class Detect_RefineDet(object):
                row_layout, max_out, dets=None, timed=None, host_mapped=False):
         args, res, dev, _ = self._prepare(arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data,
                                           scale, flags, row_layout, max_out, dets=dets, host_mapped=host_mapped)
-        with on_device(dev):
-            if timed is None:
-                check(lib().rd_detect_fused(*args, stream_ptr()), 'rd_detect_fused')
-            else:
-                import ctypes
-                check(lib().rd_detect_fused_timed(*args, stream_ptr(), ctypes.cast(timed, ctypes.c_void_p)),
-                      'rd_detect_fused_timed')
+        try:
+            with on_device(dev):
+                if timed is None:
+                    check(lib().rd_detect_fused(*args, stream_ptr()), 'rd_detect_fused')
+                else:
+                    import ctypes
+                    check(lib().rd_detect_fused_timed(*args, stream_ptr(), ctypes.cast(timed, ctypes.c_void_p)),
+                          'rd_detect_fused_timed')
+        except RuntimeError:
+            # a launch of the chain failed after collect_kernel may have marked the control block: the cached
+            # workspace is no longer known to be clean, so it is dropped (the next call allocates + resets one)
+            self._ws, self._ws_key = None, None
+            raise
         return res
 
     # -- plans: the stage for fixed buffers as one CUDA-graph replay ---------------------------
@@ -408,14 +420,14 @@ class Detect_RefineDet(object):
                           torch.empty(B, C, max_out, dtype=torch.int32, device=device), row_layout)
 
     def plan(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale=None,
-             workspace=None, out=None, force_cpu_semantics=False, logits=False):
+             workspace=None, out=None, force_cpu_semantics=False, logits=False, instance=None):
         """:meth:`detect` for FIXED input buffers, captured once (``rd_detect_plan_create``): the returned
         :class:`DetectPlan` replays the whole launch chain with one driver call per batch.  The tensors are
         referenced, not copied — refill them in place between replays.  Plans that share ``workspace`` /
         ``out`` must be replayed on the same stream; give every batch in flight its own pair
         (:meth:`new_workspace`, :meth:`new_outputs`)."""
         flags = _ffi.RD_NMS_PIXEL_PLUS1 | (_ffi.RD_NMS_SUPPRESS_EQ if force_cpu_semantics else 0) | \
-            (_ffi.RD_INPUT_LOGITS if logits else 0)
+            (_ffi.RD_INPUT_LOGITS if logits else 0) | self._INSTANCES[instance]
         for name, t in (('arm_loc_data', arm_loc_data), ('arm_conf_data', arm_conf_data),
                         ('odm_loc_data', odm_loc_data), ('odm_conf_data', odm_conf_data)):
             if not t.is_contiguous() or t.data_ptr() % 16:
@@ -439,9 +451,14 @@ class Detect_RefineDet(object):
                           _ffi.RD_NMS_NORMALISED, _ffi.RD_ROW_SCORE_BOX, self.top_k, dets=output)
         self.last_detections = res
         # in-place ARM zeroing of the caller's tensor (:79-81)
-        arm_obj = arm_conf_data.detach().reshape(B, -1, 2)[:, :, 1:]
-        conf_view = odm_conf_data.detach().view(B, -1, self.num_classes)
-        conf_view.masked_fill_(arm_obj <= self.objectness_thre, 0)
+        arm_c = require_cuda_f32(arm_conf_data, 'arm_conf_data', align=8)
+        conf = odm_conf_data.detach()
+        conf_c = conf if conf.is_contiguous() else conf.contiguous()
+        with on_device(conf_c.device):
+            check(lib().rd_arm_zero_rows(ptr(arm_c), ptr(conf_c), arm_c.numel() // 2, self.num_classes,
+                                         float(self.objectness_thre), stream_ptr()), 'rd_arm_zero_rows')
+        if conf_c.data_ptr() != conf.data_ptr():                 # a copy was made: mirror the in-place write
+            conf.copy_(conf_c.view(conf.shape))
         return output
 
     __call__ = forward

@@ -75,9 +75,9 @@ class RefineDetMultiBoxLoss(nn.Module):
             loc_data, conf_data = arm_loc_data, arm_conf_data
         loc_t, conf_t = self.match_targets(predictions, targets)
         arm_gate = arm_conf_data.detach() if self.use_ARM else None           # :96-101 (softmax inside the kernel)
-        loss_l, loss_c, N = _MultiBoxLossTail.apply(loc_data, conf_data, arm_gate, loc_t, conf_t,
-                                                    float(self.theta), int(self.negpos_ratio))
-        self.last_masks = _MultiBoxLossTail.last_masks
+        loss_l, loss_c, N, pos, neg = _MultiBoxLossTail.apply(loc_data, conf_data, arm_gate, loc_t, conf_t,
+                                                              float(self.theta), int(self.negpos_ratio))
+        self.last_masks = (pos, neg)        # of this criterion's latest forward, for inspection / tests
         if not self.sync_free and float(N) < 1:                     # :135-136 (the reference syncs here too)
             return torch.zeros(1), torch.zeros(1)
         return loss_l, loss_c
@@ -86,7 +86,6 @@ class RefineDetMultiBoxLoss(nn.Module):
 class _MultiBoxLossTail(torch.autograd.Function):
     """refinedet_multibox_loss.py:96-138 on the device: forward = rd_conf_loss + rd_hnm_select +
     rd_multibox_loss_reduce, backward = rd_multibox_loss_backward."""
-    last_masks = None          # (pos, neg) of the latest forward, for inspection / tests
 
     @staticmethod
     def forward(ctx, loc_data, conf_data, arm_conf, loc_t, conf_t, theta, negpos_ratio):
@@ -97,12 +96,11 @@ class _MultiBoxLossTail(torch.autograd.Function):
         neg, num_pos = hnm_select(ce, pos, negpos_ratio)                       # :117-123
         loss_l, loss_c, N = multibox_loss_reduce(loc_c, loc_t, ce, pos, neg, num_pos)   # :105-110, :126-138
         ctx.save_for_backward(loc_c, conf_c, loc_t, conf_t, lse, pos, neg, N)
-        ctx.mark_non_differentiable(N)
-        _MultiBoxLossTail.last_masks = (pos, neg)
-        return loss_l, loss_c, N
+        ctx.mark_non_differentiable(N, pos, neg)
+        return loss_l, loss_c, N, pos, neg
 
     @staticmethod
-    def backward(ctx, g_l, g_c, _g_n):
+    def backward(ctx, g_l, g_c, _g_n, _g_pos, _g_neg):
         loc_c, conf_c, loc_t, conf_t, lse, pos, neg, N = ctx.saved_tensors
         need_loc, need_conf = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g_l = g_l.contiguous().float() if g_l is not None else None

@@ -249,7 +249,7 @@ def test_pad_targets_kernel(rd):
     tg = gen.targets(17, 5, 7, 21)
     tg = [tg[0], tg[1][:3], tg[2][:0], tg[3][:1], tg[4]]
     for src in ([t.cuda() for t in tg], tg):
-        bu._PAD_CACHE = None
+        bu.clear_pad_cache()
         truths, labels, cnt = bu.pad_targets(src, 'cuda')
         assert truths.shape == (5, 7, 4) and cnt.tolist() == [7, 3, 0, 1, 7]
         for i, t in enumerate(tg):
