@@ -283,19 +283,21 @@ def main():
     lanes = [(det.new_workspace(B_loc, P, dev), det.new_outputs(B_loc, dev)) for _ in range(S)]
     plans = [[det.plan(a[0], a[1], a[2], a[3], priors, scale=scale, workspace=lanes[l][0], out=lanes[l][1])
               for a in dev_sets] for l in range(S)]
-    exchanges, exchange_err = None, None
+    exchanges, exchange_err, xplans = None, None, None
     if dist is not None and not args.no_exchange:
         try:
             exchanges = [rdist.PeerExchange(B_max, C, lanes[l][1].dets.shape[2], dev) for l in range(S)]
+            # stage + exchange of its result as ONE plan per (lane, input set): a step stays one driver call
+            xplans = [[det.plan(a[0], a[1], a[2], a[3], priors, scale=scale, workspace=lanes[l][0], out=lanes[l][1],
+                                then=exchanges[l].exchange) for a in dev_sets] for l in range(S)]
         except Exception as e:                                              # symmetric memory unavailable
-            exchange_err = repr(e)[:200]
+            exchanges, xplans, exchange_err = None, None, repr(e)[:200]
 
     def step(i, with_exchange=True):
         l = i % S
-        res = plans[l][i % NBUF].launch(streams[l])
-        if exchanges is not None and with_exchange:
-            exchanges[l].exchange(res, stream=streams[l])
-        return res
+        if xplans is not None and with_exchange:
+            return xplans[l][i % NBUF].launch(streams[l])
+        return plans[l][i % NBUF].launch(streams[l])
 
     def barrier():
         if dist is not None:
@@ -601,8 +603,37 @@ def main():
             return 1e3 * (time.perf_counter() - t0) / n
         ms_t = wall_ms(make_step(False))
         ms_sf = wall_ms(make_step(True))
+        # the kernels of the ODM criterion one by one (device time, L2 flushed) against their algorithmic bytes:
+        # refine_match 40 P + 20 G per image, conf loss 4 P C + 17 P, mining 6 P, backward 4 P C + 18 P
+        bu = rd.box_utils
+        truths_k, labels_k, cnt_k = bu.pad_targets(tg, dev)
+        lt_k, ct_k = bu.match_batch(0.5, truths_k, labels_k, cnt_k, priors, [0.1, 0.2], tp[0], bu.LABEL_ODM)
+        ce_k, lse_k, pos_k = bu.conf_loss(tp[3], ct_k, tp[1], 0.01)
+        neg_k, npos_k = bu.hnm_select(ce_k, pos_k, 3)
+        one_k, n_k = torch.ones((), device=dev), pos_k.sum().float()
+        kernels = {}
+        for name, byts, fn in (
+                ('refine_match', BATCH * (40 * P + 20 * 50),
+                 lambda: bu.match_batch(0.5, truths_k, labels_k, cnt_k, priors, [0.1, 0.2], tp[0], bu.LABEL_ODM)),
+                ('conf_loss', BATCH * P * (4 * C + 17), lambda: bu.conf_loss(tp[3], ct_k, tp[1], 0.01)),
+                ('hnm_select', BATCH * 6 * P, lambda: bu.hnm_select(ce_k, pos_k, 3)),
+                ('loss_reduce', BATCH * P * 6, lambda: bu.multibox_loss_reduce(tp[2], lt_k, ce_k, pos_k, neg_k, npos_k)),
+                ('loss_backward', BATCH * P * (4 * C + 18),
+                 lambda: bu.multibox_loss_backward(tp[2], lt_k, tp[3], ct_k, lse_k, pos_k, neg_k, one_k, one_k, n_k))):
+            ms_k = flushed_ms(fn, n=10)
+            kernels[name] = {'ms': round(ms_k, 5), 'frac': round(byts / (ms_k * 1e-3) / 1e9 / peak, 4)}
+        # device time of the whole step (events around it, the host runs ahead)
+        step_sf = make_step(True)
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev_a.record(main_st)
+        for _ in range(10):
+            step_sf()
+        ev_b.record(main_st)
+        torch.cuda.synchronize()
         train_step = {'ms_per_step': ms_t, 'value': BATCH / (ms_t * 1e-3), 'sync_free_ms_per_step': ms_sf,
-                      'cpu_baseline': None}
+                      'event_ms_per_step': ev_a.elapsed_time(ev_b) / 10, 'kernels': kernels, 'cpu_baseline': None}
+        del truths_k, labels_k, cnt_k, lt_k, ct_k, ce_k, lse_k, pos_k, neg_k
         detail['train_step'] = 'ARM + ODM RefineDetMultiBoxLoss forward + backward (B=32, P=16320, C=81, 50 GT/image), wall ' \
                                'clock incl. host glue; sync_free: no host read of N inside the criteria, losses read once'
         if not args.no_cpu_baseline:

@@ -72,7 +72,6 @@ extern "C" {
 #define RD_DEBUG_INSTANCE_MASK  (3 << RD_DEBUG_INSTANCE_SHIFT)
 #define RD_DEBUG_INSTANCE_256   (1 << RD_DEBUG_INSTANCE_SHIFT)   /* <= 256 candidates, 128 threads  */
 #define RD_DEBUG_INSTANCE_1024  (2 << RD_DEBUG_INSTANCE_SHIFT)   /* <= 1024 candidates, 256 threads */
-#define RD_DEBUG_INSTANCE_512   (3 << RD_DEBUG_INSTANCE_SHIFT)   /* <= 512 candidates, 128 threads  */
 /* output row layout of the fused detect stage */
 #define RD_ROW_BOX_SCORE    0  /* x1,y1,x2,y2,score  (eval_refinedet_coco.py:226) */
 #define RD_ROW_SCORE_BOX    1  /* score,x1,y1,x2,y2  (detection_refinedet.py:106-108) */
@@ -198,6 +197,10 @@ RD_API int rd_detect_plan_create(const float* arm_loc, const float* arm_conf, co
                     int row_layout, float v0, float v1,
                     void* workspace, size_t workspace_bytes,
                     int* out_counts, float* out_dets, int* out_anchor, rd_detect_plan** plan_out);
+/* Generic capture: everything the caller enqueues on `stream` (a non-default stream) between begin and end --
+ * rd_detect_fused followed by the exchange of its result, for example -- becomes one plan.  Thread-local capture. */
+RD_API int rd_plan_capture_begin(void* stream);
+RD_API int rd_plan_capture_end(void* stream, rd_detect_plan** plan_out);
 RD_API int rd_detect_plan_launch(rd_detect_plan* plan, void* stream);
 RD_API int rd_detect_plan_destroy(rd_detect_plan* plan);
 
@@ -206,6 +209,18 @@ RD_API int rd_detect_plan_destroy(rd_detect_plan* plan);
  * of counts; packed[total,5]; packed_capacity = rows available in `packed`. */
 RD_API int rd_pack_detections(const int* counts, const float* dets, int B, int C, int max_out,
                        int* out_offsets, float* packed, int packed_capacity, void* stream);
+
+/* Result wire format of the reference's eval (data/sarship_coco.py:293-336, built there by a Python double loop):
+ * COCO result records straight from the device-side detections, in the reference's order -- classes ascending
+ * (class 0 and classes with class_to_cat[c] < 0 skipped; class_to_cat may be NULL), images ascending inside a
+ * class, rows score-descending -- with bbox = [x, y, x2 - x + 1, y2 - y + 1] in float64 (:296-303).
+ *   dets: the slot layout [B,C,max_out,5] (max_out > 0), or packed rows [total,5] with src_offsets[B*C+1] = their
+ *         image-major exclusive prefix (max_out = 0: the output of rd_pack_detections or of the multi-GPU gather)
+ *   out_ids  [capacity,2] int32 (image index b, class c);  out_vals [capacity,5] float64 (x, y, w, h, score);
+ *   out_total[1] = number of records (may exceed capacity: then only the first `capacity` were written).       */
+RD_API int rd_coco_records(const int* counts, const float* dets, int B, int C, int max_out,
+                    const int* src_offsets, const int* class_to_cat, int* out_ids, double* out_vals,
+                    int capacity, int* out_total, void* stream);
 
 /* Multi-GPU exchange of the compact detections (the reference has no counterpart: its
  * nn.DataParallel gathers the dense head outputs on GPU 0, train_refinedet.py:138-139).  Packing fused
@@ -303,6 +318,21 @@ RD_API size_t rd_multibox_loss_workspace_bytes(int B);
 RD_API int rd_multibox_loss_reduce(const float* loc, const float* loc_t, const float* ce,
                  const unsigned char* pos, const unsigned char* neg, const int* num_pos, int B, int P,
                  void* workspace, size_t workspace_bytes, float* loss_l, float* loss_c, float* n_out,
+                 void* stream);
+/* The whole criterion forward (refinedet_multibox_loss.py:62-138) as ONE call: refine_match / match over the
+ * padded batch, the per-anchor confidence loss with the ARM-theta gate, hard-negative mining, both reductions
+ * and the division by N -- six kernels chained with programmatic dependent launch, no host involvement.
+ *   inputs : truths / labels / gt_count / priors / arm_loc / threshold / label_mode as rd_refine_match,
+ *            loc_data [B,P,4], conf_data [B,P,C] (the branch's predictions), arm_conf_gate [B,P,2] LOGITS or NULL
+ *            (ODM criterion: :96-101), theta, negpos_ratio
+ *   outputs: loc_t [B,P,4], conf_t [B,P] int64, ce / lse [B,P] float, pos / neg [B,P] uint8, num_pos [B] int32,
+ *            losses [3] float = { loss_l, loss_c, N }  (zeros when N < 1).  Everything the backward needs.   */
+RD_API size_t rd_multibox_criterion_workspace_bytes(int B, int P, int Gmax);
+RD_API int rd_multibox_criterion(const float* truths, const float* labels, const int* gt_count, const float* priors,
+                 const float* arm_loc, const float* loc_data, const float* conf_data, const float* arm_conf_gate,
+                 int B, int P, int C, int Gmax, float threshold, float v0, float v1, int label_mode, float theta,
+                 int negpos_ratio, void* workspace, size_t workspace_bytes, float* loc_t, long long* conf_t,
+                 float* ce, float* lse, unsigned char* pos, unsigned char* neg, int* num_pos, float* losses,
                  void* stream);
 /* backward of the two losses (what autograd derives from :105-138): with g_l = *grad_loss_l,
  * g_c = *grad_loss_c (device scalars, either may be NULL = 0) and N = *n_dev,

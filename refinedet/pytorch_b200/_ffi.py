@@ -29,7 +29,7 @@ RD_MAX_GT = 1024
 RD_NMS_NORMALISED, RD_NMS_PIXEL_PLUS1, RD_NMS_SUPPRESS_EQ = 0, 1, 2
 RD_INPUT_LOGITS = 4
 RD_DEBUG_INSTANCE_SHIFT = 8
-RD_DEBUG_INSTANCE_256, RD_DEBUG_INSTANCE_1024, RD_DEBUG_INSTANCE_512 = 1 << 8, 2 << 8, 3 << 8
+RD_DEBUG_INSTANCE_256, RD_DEBUG_INSTANCE_1024 = 1 << 8, 2 << 8
 RD_ROW_BOX_SCORE, RD_ROW_SCORE_BOX = 0, 1
 
 _P = c_void_p
@@ -64,9 +64,12 @@ _SIGNATURES = {
     'rd_detect_plan_create': (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, c_float, c_float,
                                       c_int, c_int, _P, c_int, c_int, c_float, c_float, _P, c_size_t,
                                       _P, _P, _P, _P]),
+    'rd_plan_capture_begin': (c_int, [_P]),
+    'rd_plan_capture_end': (c_int, [_P, _P]),
     'rd_detect_plan_launch': (c_int, [_P, _P]),
     'rd_detect_plan_destroy': (c_int, [_P]),
     'rd_pack_detections': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, _P]),
+    'rd_coco_records': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P]),
     'rd_exchange_slot_bytes': (c_size_t, [c_int, c_int, c_int]),
     'rd_pack_scatter': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'rd_pack_scatter_ex': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
@@ -82,6 +85,8 @@ _SIGNATURES = {
     'rd_conf_loss': (c_int, [_P, _P, _P, c_float, ctypes.c_longlong, c_int, _P, _P, _P, _P]),
     'rd_multibox_loss_workspace_bytes': (c_size_t, [c_int]),
     'rd_multibox_loss_reduce': (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, c_size_t, _P, _P, _P, _P]),
+    'rd_multibox_criterion_workspace_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'rd_multibox_criterion': (c_int, [_P] * 8 + [c_int] * 4 + [c_float] * 3 + [c_int, c_float, c_int, _P, c_size_t] + [_P] * 9),
     'rd_multibox_loss_backward': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_longlong, c_int,
                                           _P, _P, _P]),
 }

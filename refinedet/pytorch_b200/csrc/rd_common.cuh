@@ -33,11 +33,43 @@ inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&hig
     return e;
 }
 
+// ---- launchers shared between translation units (the fused criterion in rd_loss.cu chains kernels of rd_match.cu)
+// `pdl`: launch with programmatic stream serialisation (every kernel of the chain waits with grid_dependency_wait)
+int match_launch(const float4* truths, const float* labels, const int* gt_count, const float4* priors,
+                 const float4* arm_loc, int B, int P, int Gmax, float threshold, float v0, float v1, int label_mode,
+                 unsigned long long* best_prior, float* bt_overlap, int* bt_idx, float4* loc_t, long long* conf_t,
+                 cudaStream_t st, bool pdl);
+int hnm_launch(const float* loss_c, const unsigned char* pos, int B, int P, int negpos_ratio, unsigned char* neg_out,
+               int* num_pos_out, cudaStream_t st, bool pdl);
+
 #define RD_CHECK_LAUNCH()                                   \
     do {                                                    \
         cudaError_t e__ = cudaGetLastError();               \
         if (e__ != cudaSuccess) return (int)e__;            \
     } while (0)
+
+// ---- programmatic dependent launch (sm_90+) ----------------------------------
+// wait until the preceding kernel of the stream has completed and its memory is visible / allow the next kernel
+// of the stream to start launching.  A kernel launched WITHOUT the attribute passes the wait at once.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// launch with programmatic stream serialisation: the kernel may begin launching while its predecessor in
+// the stream drains; kernels launched this way call grid_dependency_wait() before touching its results
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 // ---- streaming loads ---------------------------------------------------------
 // read-once data: bypass L1 allocation (guide: Guideline 13/14)

@@ -278,12 +278,16 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
     int before = 0;
     {
         const int nprev = s * kSliceAnchors;                           // multiple of kCollectThreads * 4
-        for (int a = threadIdx.x; a < nprev; a += kCollectThreads * 4) {
-            float2 o4[4];
+        if (gate.admit_all) {
+            before = threadIdx.x == 0 ? nprev : 0;                     // every anchor is a node
+        } else {
+            for (int a = threadIdx.x; a < nprev; a += kCollectThreads * 4) {
+                float2 o4[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o4[k] = __ldg(arm_conf + img + a + k * kCollectThreads);
+                for (int k = 0; k < 4; ++k) o4[k] = __ldg(arm_conf + img + a + k * kCollectThreads);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) before += (gate.admit_all || arm_pass<kLogits>(o4[k], gate)) ? 1 : 0;
+                for (int k = 0; k < 4; ++k) before += arm_pass<kLogits>(o4[k], gate) ? 1 : 0;
+            }
         }
         before = __reduce_add_sync(kFullMask, before);
     }
@@ -469,7 +473,10 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
 // One block (<= 1024 nodes) is the common case; images with more than kGraphNodes nodes, a node of
 // degree > kAdjDeg are flagged and handled by the per-problem bin path instead.
 // ---------------------------------------------------------------------------------------
-constexpr int kGraphThreads = 256;
+#ifndef RD_GRAPH_THREADS
+#define RD_GRAPH_THREADS 256
+#endif
+constexpr int kGraphThreads = RD_GRAPH_THREADS;
 constexpr int kGraphSplit = 16;         // CTAs per image
 constexpr int kGraphPairCap = 2048;
 
@@ -795,7 +802,7 @@ nms_small_kernel(FusedNmsArgs A) {
         if (tid == 0) A.queue[atomicAdd(&A.header[0], 1u)] = bc;
         return;
     }
-    cta_sort_small<kThreads, kCap>(S, n);
+    cta_sort_small<kThreads, kCap>(S, n, A.conf_thresh);
     grid_dependency_wait();                                       // graph_kernel has completed
     const int fl = A.img_flag[b];                                 // degree overflow: no graph (for this variant) after all
     if ((fl & kFlagNoGraph) || ((fl & kFlagWideDeg) && !SmallSmem<kCap>::kBitRows)) {
@@ -821,19 +828,64 @@ nms_small_kernel(FusedNmsArgs A) {
 // (or its 1024-node rank table): the same sort + graph resolve, 1024 candidates wide, on the large kernel's
 // shared memory.  Out of line, so that the register allocation of the bin path (nms_process) is unaffected.
 __device__ __noinline__ int large_graph_resolve(unsigned char* smem, const unsigned long long* __restrict__ keys, int n,
-                                                int N, int max_out, const uint4* adj, const int* adjn,
+                                                float conf_thresh, int N, int max_out, const uint4* adj, const int* adjn,
                                                 const float4* nbox, const int* nanc, float* rows, int* anchors,
                                                 int row_layout) {
     SmallSmem<kWideCap>& S = *reinterpret_cast<SmallSmem<kWideCap>*>(smem);
     for (int i = threadIdx.x; i < n; i += kLargeThreads) S.u.runs[i] = keys[i];
     __syncthreads();
-    cta_sort_small<kLargeThreads, kWideCap>(S, n);
+    cta_sort_small<kLargeThreads, kWideCap>(S, n, conf_thresh);
     GraphView G;
     G.adj = adj; G.adj2 = nullptr; G.adjn = adjn; G.nbox = nbox; G.nanc = nanc;    // kWideCap: kDeps == kAdjDeg
     RowSink sink;
     sink.rows = rows; sink.anchors = anchors; sink.keep64 = nullptr; sink.keep32 = nullptr; sink.idx_map = nullptr;
     sink.row_layout = row_layout;
     return cta_nms_graph<kLargeThreads, kWideCap>(S, n, N, max_out, sink, G);
+}
+
+// The common kind of queued problem -- an image with a graph whose 1025 .. 4096 nodes outgrew nms_small_kernel's rank
+// table, at most kMidCap candidates: candidates are compacted from the score row straight into shared memory (no
+// round trip through the global key list), bucket-sorted and resolved through the graph, one candidate per thread.
+// Returns -1 (nothing written) when the problem has more than kMidCap / top_k candidates.
+__device__ __noinline__ int large_mid_resolve(unsigned char* smem, const float* __restrict__ row, int N, float conf_thresh,
+                                              int top_k, int max_out, const uint4* adj, const int* adjn, const float4* nbox,
+                                              const int* nanc, float* rows, int* anchors, int row_layout) {
+    SmallSmem<kMidCap>& S = *reinterpret_cast<SmallSmem<kMidCap>*>(smem);
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) S.n = 0;
+    __syncthreads();
+    constexpr int kU = 4;
+    for (int i0 = 0; i0 < N; i0 += kLargeThreads * kU) {
+        float v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int i = i0 + u * kLargeThreads + tid;
+            v[u] = i < N ? __ldg(row + i) : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const bool pass = v[u] > conf_thresh;
+            const unsigned bal = __ballot_sync(kFullMask, pass);
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&S.n, __popc(bal));
+                base = __shfl_sync(kFullMask, base, 0) + __popc(bal & ((1u << lane) - 1u));
+                if (pass && base < kMidCap) S.u.runs[base] = make_key(v[u], (uint32_t)(i0 + u * kLargeThreads + tid));
+            }
+        }
+    }
+    __syncthreads();
+    const int n = S.n;
+    __syncthreads();                                      // S.n is rewritten by the next problem of this CTA
+    if (n > kMidCap || n > top_k) return -1;
+    if (n == 0) return 0;
+    cta_sort_small<kLargeThreads, kMidCap>(S, n, conf_thresh);
+    GraphView G;
+    G.adj = adj; G.adj2 = nullptr; G.adjn = adjn; G.nbox = nbox; G.nanc = nanc;
+    RowSink sink;
+    sink.rows = rows; sink.anchors = anchors; sink.keep64 = nullptr; sink.keep32 = nullptr; sink.idx_map = nullptr;
+    sink.row_layout = row_layout;
+    return cta_nms_graph<kLargeThreads, kMidCap>(S, n, N, max_out, sink, G);
 }
 
 __global__ void __launch_bounds__(kLargeThreads, RD_LARGE_PER_SM)      // 3 x 512 threads: 40 registers
@@ -861,6 +913,20 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
         const int bc = A.queue[q];
         const int b = bc / A.C;
         const int N = A.nnodes[b];
+#ifndef RD_NO_LARGE_GRAPH
+        if (wide_fits && N <= kGraphNodes && A.img_flag[b] == 0) {
+            const int kept = large_mid_resolve(smem, A.nsc + (size_t)bc * A.Pn, N, A.conf_thresh, A.top_k, A.max_out,
+                                               A.adj + (size_t)b * kGraphNodes, A.adjn + (size_t)b * kGraphNodes,
+                                               A.nbox + (size_t)b * A.P, A.nanc + (size_t)b * A.P,
+                                               A.out_dets + (size_t)bc * A.max_out * 5,
+                                               A.out_anchor ? A.out_anchor + (size_t)bc * A.max_out : nullptr, A.row_layout);
+            if (kept >= 0) {
+                if (tid == 0) A.out_counts[bc] = kept;
+                __syncthreads();
+                continue;
+            }
+        }
+#endif
         // candidate keys of the problem -> its slot of the global scratch list
         unsigned long long* keys = A.cand + (size_t)bc * A.P;
         const float* row = A.nsc + (size_t)bc * A.Pn;
@@ -899,7 +965,7 @@ nms_large_kernel(FusedNmsArgs A, int mcap) {
         int kept;
 #ifndef RD_NO_LARGE_GRAPH
         if (wide_fits && N <= kGraphNodes && A.img_flag[b] == 0 && n <= kWideCap && n <= A.top_k) {
-            kept = large_graph_resolve(smem, keys, n, N, A.max_out, A.adj + (size_t)b * kGraphNodes,
+            kept = large_graph_resolve(smem, keys, n, A.conf_thresh, N, A.max_out, A.adj + (size_t)b * kGraphNodes,
                                        A.adjn + (size_t)b * kGraphNodes, A.nbox + (size_t)b * A.P, A.nanc + (size_t)b * A.P,
                                        sink.rows, sink.anchors, sink.row_layout);
         } else
@@ -1022,46 +1088,98 @@ __global__ void pack_rows_kernel(const int* __restrict__ counts, const int* __re
 // ---------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;
 struct PeerSlots { unsigned char* p[kMaxPeers]; };
-constexpr int kPackThreads = 128;
+constexpr int kPackThreads = 256;
+constexpr int kPackPer = kPackThreads / 32;       // (image, class) slots per CTA: one warp each
 
-// exclusive prefix of counts at bc (sum over [0, bc)) computed by the calling CTA: the list is a few thousand
-// ints from L2, cheaper than a separate single-CTA scan kernel in front of the copy
-__device__ __forceinline__ int cta_count_prefix(const int* __restrict__ counts, int bc, int* s_red) {
-    int acc = 0;
-    for (int i = threadIdx.x; i < bc; i += blockDim.x) acc += __ldg(counts + i);
-    acc = __reduce_add_sync(kFullMask, acc);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    int tot = 0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
-    __syncthreads();
-    return tot;
-}
-
-// phase 1: pack this rank's rows into ITS OWN slot of its own exchange buffer (local HBM), write counts + header
+// phase 1: pack this rank's rows into ITS OWN slot of its own exchange buffer (local HBM), write counts + header.
+// The exclusive prefix of the counts is computed by the CTA itself (a few thousand ints from L2, once per 8 slots):
+// no separate scan kernel in front of the copy.
 __global__ void __launch_bounds__(kPackThreads)
 pack_local_kernel(const int* __restrict__ counts, const float* __restrict__ dets, int max_out, int nbc, int B, int C,
                   unsigned char* slot, int capacity, size_t rows_off, int* __restrict__ offsets_out) {
-    __shared__ int s_red[kPackThreads / 32];
-    const int bc = blockIdx.x;
-    const int off = cta_count_prefix(counts, bc, s_red);
-    if (bc == nbc) {                       // last CTA: header + counts (off = total rows)
-        int* hdr = reinterpret_cast<int*>(slot);
-        int* cdst = reinterpret_cast<int*>(slot + 256);
-        for (int t = threadIdx.x; t < nbc; t += blockDim.x) cdst[t] = counts[t];
-        if (threadIdx.x == 0) {
-            hdr[0] = min(off, capacity); hdr[1] = B; hdr[2] = C; hdr[3] = off;
-            if (offsets_out) offsets_out[nbc] = off;
-        }
-        return;
+    __shared__ int s_red[kPackPer];
+    __shared__ int s_cnt[kPackPer];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bc0 = blockIdx.x * kPackPer;
+    int acc = 0;
+    for (int i = threadIdx.x; i < bc0; i += kPackThreads) acc += __ldg(counts + i);
+    acc = __reduce_add_sync(kFullMask, acc);
+    const int bc = bc0 + warp;
+    const int n = bc < nbc ? __ldg(counts + bc) : 0;
+    if (lane == 0) { s_red[warp] = acc; s_cnt[warp] = n; }
+    __syncthreads();
+    int off = 0;
+#pragma unroll
+    for (int w = 0; w < kPackPer; ++w) off += s_red[w] + (w < warp ? s_cnt[w] : 0);
+    if (bc < nbc) {
+        if (offsets_out && lane == 0) offsets_out[bc] = off;
+        const float* src = dets + (size_t)bc * max_out * 5;
+        int len = n * 5;
+        if (off + n > capacity) len = max(0, capacity - off) * 5;
+        float* dst = reinterpret_cast<float*>(slot + rows_off) + (size_t)off * 5;
+        for (int t = lane; t < len; t += 32) dst[t] = src[t];
     }
-    if (offsets_out && threadIdx.x == 0) offsets_out[bc] = off;
-    const int n = counts[bc];
-    const float* src = dets + (size_t)bc * max_out * 5;
-    int len = n * 5;
-    if (off + n > capacity) len = max(0, capacity - off) * 5;
-    float* dst = reinterpret_cast<float*>(slot + rows_off) + (size_t)off * 5;
-    for (int t = threadIdx.x; t < len; t += blockDim.x) dst[t] = src[t];
+    // counts of this CTA's slots; the CTA that owns the last slot also writes the header (total = its running sum)
+    int* cdst = reinterpret_cast<int*>(slot + 256);
+    if (bc < nbc && lane == 0) cdst[bc] = n;
+    if (bc == nbc - 1 && lane == 0) {
+        const int total = off + n;
+        int* hdr = reinterpret_cast<int*>(slot);
+        hdr[0] = min(total, capacity); hdr[1] = B; hdr[2] = C; hdr[3] = total;
+        if (offsets_out) offsets_out[nbc] = total;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// result wire format (data/sarship_coco.py:293-336): the rows of the slot layout (or of packed / gathered rows)
+// as COCO result records, in the reference's order -- classes ascending (background and unmapped classes skipped),
+// images ascending inside a class, rows score-descending -- with bbox = [x, y, x2 - x + 1, y2 - y + 1] computed in
+// float64 exactly as `dets.astype(np.float)` does (:296-303).  One warp per (class, image); the exclusive prefix of
+// the counts in that (class-major) order is computed by the CTA itself.
+//   out_ids  [capacity, 2] int32   (image index b, class c)      -- the host maps them to image_id / category_id
+//   out_vals [capacity, 5] float64 (x, y, w, h, score)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPackThreads)
+coco_records_kernel(const int* __restrict__ counts, const float* __restrict__ dets, int B, int C, int max_out,
+                    const int* __restrict__ src_offsets, const int* __restrict__ class_to_cat, int* __restrict__ out_ids,
+                    double* __restrict__ out_vals, int capacity, int* __restrict__ out_total) {
+    __shared__ int s_red[kPackPer];
+    __shared__ int s_cnt[kPackPer];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nbc = B * C;
+    const int t0 = blockIdx.x * kPackPer;                 // slots in class-major order: t = c * B + b
+    auto count_of = [&](int t) -> int {
+        const int c = t / B, b = t - c * B;
+        return (c == 0 || (class_to_cat && __ldg(class_to_cat + c) < 0)) ? 0 : __ldg(counts + b * C + c);
+    };
+    int acc = 0;
+    for (int t = threadIdx.x; t < t0; t += kPackThreads) acc += count_of(t);
+    acc = __reduce_add_sync(kFullMask, acc);
+    const int t = t0 + warp;
+    const int n = t < nbc ? count_of(t) : 0;
+    if (lane == 0) { s_red[warp] = acc; s_cnt[warp] = n; }
+    __syncthreads();
+    int off = 0;
+#pragma unroll
+    for (int w = 0; w < kPackPer; ++w) off += s_red[w] + (w < warp ? s_cnt[w] : 0);
+    if (t == nbc - 1 && lane == 0) *out_total = off + n;
+    if (t >= nbc || n == 0) return;
+    const int c = t / B, b = t - c * B;
+    const int bc = b * C + c;
+    const float* src = max_out > 0 ? dets + (size_t)bc * max_out * 5 : dets + (size_t)__ldg(src_offsets + bc) * 5;
+    for (int k = lane; k < n; k += 32) {
+        const int o = off + k;
+        if (o >= capacity) break;
+        const float* r = src + (size_t)k * 5;
+        const double x = (double)r[0], y = (double)r[1];
+        double* v = out_vals + (size_t)o * 5;
+        v[0] = x; v[1] = y;
+        v[2] = (double)r[2] - x + 1.0;                    // :302
+        v[3] = (double)r[3] - y + 1.0;
+        v[4] = (double)r[4];
+        out_ids[2 * o] = b;
+        out_ids[2 * o + 1] = c;
+    }
 }
 
 __device__ __forceinline__ void st_multimem_v4(void* mc_addr, uint4 v) {
@@ -1168,23 +1286,6 @@ int rd_detect_workspace_reset(void* workspace, size_t workspace_bytes, void* str
 
 }  // extern "C"
 
-// launch with programmatic stream serialisation: the kernel may begin launching while its predecessor in
-// the stream drains; kernels launched this way call grid_dependency_wait() before touching its results
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, args...);
-}
-
 static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
                              const float* priors, int B, int P, int C, float objectness_thre, float conf_thresh,
                              float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
@@ -1279,7 +1380,11 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     }
     if (ev) cudaEventRecord(ev[2], st);
     {   // programmatic dependent launch: the scan + sort of nms_small_kernel run beside graph_kernel
-        bool wide = (long long)B * (C - 1) <= 2 * 148;             // the grid cannot fill the GPU: footprint is free
+        // few problems (the grid cannot fill the GPU: footprint is free): the <1024, 256> instance, else <256, 128>.
+        // (A separate <512, 256> kernel for the images with 1025 .. 4096 nodes was measured: 0.086 against 0.104 ms at
+        // 1185 nodes per image, but its empty launch costs the sparse workload 1.7 us per batch with four batches in
+        // flight and 3 us alone; those images are resolved by nms_large_kernel's mid path instead.)
+        bool wide = (long long)B * (C - 1) <= 2 * 148;
         const int forced = nms_flags & RD_DEBUG_INSTANCE_MASK;     // test-only override (parity tests of every instance)
         if (forced == RD_DEBUG_INSTANCE_256) wide = false;
         else if (forced == RD_DEBUG_INSTANCE_1024) wide = true;
@@ -1287,8 +1392,8 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
                              : launch_pdl(nms_small_kernel<kSmallCap, kSmallThreads, RD_SMALL_MINBLOCKS>, dim3(C, B),
                                           dim3(kSmallThreads), 0, st, A);
         if (e != cudaSuccess) return (int)e;
+        note_launch();
     }
-    note_launch();
     RD_CHECK_LAUNCH();
     {
         cudaError_t e = launch_pdl(nms_large_kernel, dim3(A.large_grid < B * C ? A.large_grid : B * C),
@@ -1384,6 +1489,35 @@ int rd_detect_plan_create(const float* arm_loc, const float* arm_conf, const flo
     return 0;
 }
 
+// Generic form: capture whatever the caller enqueues on `stream` between begin and end -- the stage's launch chain
+// followed by the exchange (device barriers of the symmetric-memory handle, rd_pack_scatter_ex), say -- into one
+// plan.  Thread-local capture mode: other threads' CUDA calls are unaffected.
+static thread_local unsigned long long t_capture_l0 = 0;
+int rd_plan_capture_begin(void* stream) {
+    if (!stream) return RD_ERR_BAD_ARG;                       // the legacy default stream cannot be captured
+    t_capture_l0 = g_launches.load(std::memory_order_relaxed);
+    return (int)cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal);
+}
+
+int rd_plan_capture_end(void* stream, rd_detect_plan** plan_out) {
+    if (!stream || !plan_out) return RD_ERR_BAD_ARG;
+    *plan_out = nullptr;
+    const unsigned long long l1 = g_launches.load(std::memory_order_relaxed);
+    g_launches.fetch_sub(l1 - t_capture_l0, std::memory_order_relaxed);      // captured, not executed
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &graph);
+    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return (int)e; }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) { cudaGraphDestroy(graph); return (int)e; }
+    rd_detect_plan* p = new rd_detect_plan;
+    p->graph = graph;
+    p->exec = exec;
+    p->launches = (int)(l1 - t_capture_l0);
+    *plan_out = p;
+    return 0;
+}
+
 int rd_detect_plan_launch(rd_detect_plan* plan, void* stream) {
     if (!plan || !plan->exec) return RD_ERR_BAD_ARG;
     cudaError_t e = cudaGraphLaunch(plan->exec, (cudaStream_t)stream);
@@ -1413,6 +1547,18 @@ int rd_pack_detections(const int* counts, const float* dets, int B, int C, int m
     return 0;
 }
 
+int rd_coco_records(const int* counts, const float* dets, int B, int C, int max_out, const int* src_offsets,
+                    const int* class_to_cat, int* out_ids, double* out_vals, int capacity, int* out_total, void* stream) {
+    if (!counts || !dets || !out_ids || !out_vals || !out_total || B <= 0 || C <= 0 || capacity < 0) return RD_ERR_BAD_ARG;
+    if (max_out <= 0 && !src_offsets) return RD_ERR_BAD_ARG;
+    if ((uintptr_t)out_vals & 7) return RD_ERR_ALIGNMENT;
+    coco_records_kernel<<<(B * C + kPackPer - 1) / kPackPer, kPackThreads, 0, (cudaStream_t)stream>>>(
+        counts, dets, B, C, max_out, src_offsets, class_to_cat, out_ids, out_vals, capacity, out_total);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
 size_t rd_exchange_slot_bytes(int B, int C, int capacity_rows) {
     if (B <= 0 || C <= 0 || capacity_rows < 0) return 0;
     return 256 + align_up((size_t)B * C * 4, 256) + align_up((size_t)capacity_rows * 20, 256);
@@ -1431,8 +1577,8 @@ int rd_pack_scatter_ex(const int* counts, const float* dets, int B, int C, int m
     cudaStream_t st = (cudaStream_t)stream;
     const size_t rows_off = 256 + align_up((size_t)slot_B * C * 4, 256);
     unsigned char* local = ps.p[rank];
-    pack_local_kernel<<<B * C + 1, kPackThreads, 0, st>>>(counts, dets, max_out, B * C, B, C, local, capacity_rows,
-                                                          rows_off, scratch_offsets);
+    pack_local_kernel<<<(B * C + kPackPer - 1) / kPackPer, kPackThreads, 0, st>>>(counts, dets, max_out, B * C, B, C, local,
+                                                                                  capacity_rows, rows_off, scratch_offsets);
     note_launch();
     RD_CHECK_LAUNCH();
     if (world == 1) return 0;

@@ -18,6 +18,8 @@
 //   loss_backward_kernel  d loss_c / d conf = (softmax(x) - onehot(t)) * g_c / N on pos | neg rows,
 //                         d loss_l / d loc = clamp(loc - loc_t, -1, 1) * g_l / N on pos rows, zeros
 //                         elsewhere; every element of both gradients is written (selected rows twice)
+#include <cstdlib>
+
 #include "rd_common.cuh"
 
 namespace rd {
@@ -41,6 +43,34 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// one row staged in shared memory: lse = log(sum exp(x - max)) + max, ce = lse - x[t], pos (gated by the ARM theta)
+__device__ __forceinline__ void conf_row(const float* __restrict__ x, int C, long long t, float2 arm, bool has_arm,
+                                         float theta, float* ce_out, float* lse_out, unsigned char* pos_out) {
+    // four independent chains each (a thread owns a whole row: the loop is latency-bound otherwise)
+    float m0 = x[0], m1 = m0, m2 = m0, m3 = m0;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+        m0 = fmaxf(m0, x[c]); m1 = fmaxf(m1, x[c + 1]); m2 = fmaxf(m2, x[c + 2]); m3 = fmaxf(m3, x[c + 3]);
+    }
+    for (; c < C; ++c) m0 = fmaxf(m0, x[c]);
+    const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // exp(x - m) = exp2((x - m) log2 e): one MUFU.EX2, rel. error < 2e-7
+    for (c = 0; c + 4 <= C; c += 4) {
+        s0 += exp2f((x[c] - m) * kLog2e); s1 += exp2f((x[c + 1] - m) * kLog2e);
+        s2 += exp2f((x[c + 2] - m) * kLog2e); s3 += exp2f((x[c + 3] - m) * kLog2e);
+    }
+    for (; c < C; ++c) s0 += exp2f((x[c] - m) * kLog2e);
+    const float sum = (s0 + s1) + (s2 + s3);
+    const float lse = logf(sum) + m;
+    // a label outside [0, C) (dataset / num_classes mismatch) makes the reference's gather raise; here the
+    // row's loss becomes NaN, which poisons loss_c visibly instead of reading past the staged row
+    *ce_out = (t >= 0 && t < C) ? lse - x[(int)t] : __int_as_float(0x7fc00000);
+    *lse_out = lse;
+    bool pos = t > 0;
+    if (pos && has_arm && arm_filtered(arm, theta)) pos = false;
+    *pos_out = pos ? 1 : 0;
+}
+
 // generic C (3..128): a CTA stages kLossRows consecutive rows (one contiguous, coalesced float4 stream)
 // in shared memory with an odd row stride (conflict-free), then one thread per row makes two passes
 // over its row: max, sum of exp.  ~16 thread-instructions per element, against ~60 for a
@@ -55,26 +85,32 @@ conf_loss_kernel(const float* __restrict__ conf, const long long* __restrict__ c
     extern __shared__ __align__(16) float s_x[];     // [kLossRows][Cp]
     const int Cp = C | 1;
     const int tid = threadIdx.x;
+    bool waited = false;                             // conf_t comes from the kernel before this one (match_pass2_kernel)
     for (long long r0 = (long long)blockIdx.x * kLossRows; r0 < rows; r0 += (long long)gridDim.x * kLossRows) {
         const int nrows = (int)min((long long)kLossRows, rows - r0);
         const int nelem = nrows * C;
         const float* src = conf + r0 * C;
-        // the scalar inputs of this thread's row: issued before the tile load
         const long long r = r0 + tid;
         long long t = 0;
         float2 arm = make_float2(0.f, 0.f);
-        if (tid < nrows) {
-            t = conf_t[r];
-            if (arm_conf && t > 0) arm = __ldg(arm_conf + r);
-        }
         const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-        if (aligned && Cp == C) {
+        const bool async_tile = aligned && Cp == C;
+        if (async_tile) {
             // odd C: the tile is a verbatim copy (row stride C is already conflict-free): asynchronous 16-byte
-            // global -> shared copies, all of a thread's ~20 in flight at once, no register staging
+            // global -> shared copies, all of a thread's ~20 in flight at once, no register staging.  conf is an
+            // input of the whole chain, so the first tile is requested BEFORE waiting for the preceding kernel
             const int nvec = nelem >> 2;
             for (int q = tid; q < nvec; q += kLossRows)
                 cp_async16(reinterpret_cast<float4*>(s_x) + q, reinterpret_cast<const float4*>(src) + q);
             for (int e2 = nvec * 4 + tid; e2 < nelem; e2 += kLossRows) s_x[e2] = src[e2];
+        }
+        if (!waited) { grid_dependency_wait(); waited = true; }
+        // the scalar inputs of this thread's row
+        if (tid < nrows) {
+            t = conf_t[r];
+            if (arm_conf && t > 0) arm = __ldg(arm_conf + r);
+        }
+        if (async_tile) {
             cp_async_wait_all();
         } else if (aligned) {
             // even C: one padding element per row, (row, class) of every element tracked incrementally
@@ -109,33 +145,103 @@ conf_loss_kernel(const float* __restrict__ conf, const long long* __restrict__ c
             for (int e2 = tid; e2 < nelem; e2 += kLossRows) s_x[(e2 / C) * Cp + e2 % C] = src[e2];
         }
         __syncthreads();
-        if (tid < nrows) {
-            const float* x = s_x + tid * Cp;
-            // four independent chains each (a thread owns a whole row: the loop is latency-bound otherwise)
-            float m0 = x[0], m1 = m0, m2 = m0, m3 = m0;
-            int c = 0;
-            for (; c + 4 <= C; c += 4) {
-                m0 = fmaxf(m0, x[c]); m1 = fmaxf(m1, x[c + 1]); m2 = fmaxf(m2, x[c + 2]); m3 = fmaxf(m3, x[c + 3]);
-            }
-            for (; c < C; ++c) m0 = fmaxf(m0, x[c]);
-            const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // exp(x - m) = exp2((x - m) log2 e): one MUFU.EX2, rel. error < 2e-7
-            for (c = 0; c + 4 <= C; c += 4) {
-                s0 += exp2f((x[c] - m) * kLog2e); s1 += exp2f((x[c + 1] - m) * kLog2e);
-                s2 += exp2f((x[c + 2] - m) * kLog2e); s3 += exp2f((x[c + 3] - m) * kLog2e);
-            }
-            for (; c < C; ++c) s0 += exp2f((x[c] - m) * kLog2e);
-            const float sum = (s0 + s1) + (s2 + s3);
-            const float lse = logf(sum) + m;
-            // a label outside [0, C) (dataset / num_classes mismatch) makes the reference's gather raise; here the
-            // row's loss becomes NaN, which poisons loss_c visibly instead of reading past the staged row
-            ce_out[r] = (t >= 0 && t < C) ? lse - x[(int)t] : __int_as_float(0x7fc00000);
-            lse_out[r] = lse;
-            bool pos = t > 0;
-            if (pos && arm_conf && arm_filtered(arm, theta)) pos = false;
-            pos_out[r] = pos ? 1 : 0;
-        }
+        if (tid < nrows)
+            conf_row(s_x + tid * Cp, C, t, arm, arm_conf != nullptr, theta, ce_out + r, lse_out + r, pos_out + r);
         __syncthreads();
+    }
+}
+
+// ---- TMA variant (odd C, 16-byte aligned conf): persistent CTAs, a ring of kTmaStages tiles of kLossRows rows in
+// shared memory.  A tile is one contiguous span of global memory (rows are consecutive, the odd row stride is already
+// conflict-free), so ONE bulk asynchronous copy (cp.async.bulk, the 1-D TMA: SASS UBLKCP) per tile fetches it and
+// signals the stage's mbarrier with the byte count; thread 0 issues the copy of tile i + kTmaStages - 1 before the CTA
+// computes tile i.  No per-thread copy instructions, no register staging, loads of the next tile always in flight.
+constexpr int kTmaStages = 2;
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kLossRows)
+conf_loss_tma_kernel(const float* __restrict__ conf, const long long* __restrict__ conf_t,
+                     const float2* __restrict__ arm_conf, float theta, long long rows, int C,
+                     float* __restrict__ ce_out, float* __restrict__ lse_out, unsigned char* __restrict__ pos_out) {
+    extern __shared__ __align__(128) float s_x[];            // [kTmaStages][kLossRows * C], each stage 16-byte aligned
+    __shared__ __align__(8) unsigned long long s_bar[kTmaStages];
+    const int tid = threadIdx.x;
+    const int tile_floats = kLossRows * C;                   // multiple of 4 (kLossRows = 128)
+    const long long ntiles = (rows + kLossRows - 1) / kLossRows;
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < kTmaStages; ++st) mbar_init(&s_bar[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long tile, int st) {               // thread 0 only
+        const long long r0 = tile * kLossRows;
+        const int nrows = (int)min((long long)kLossRows, rows - r0);
+        const unsigned bytes = (unsigned)(((size_t)nrows * C * 4) & ~(size_t)15);      // whole 16-byte words; tail below
+        mbar_expect_tx(&s_bar[st], bytes);                   // (zero bytes: the arrival alone completes the phase)
+        if (bytes) tma_load_1d(s_x + (size_t)st * tile_floats, conf + r0 * C, bytes, &s_bar[st]);
+    };
+    // conf is an input of the whole chain: the first tiles are requested before waiting for the preceding kernel
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < kTmaStages - 1; ++k) {
+            const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
+            if (tile < ntiles) issue(tile, k);
+        }
+    }
+    grid_dependency_wait();                                   // conf_t comes from the kernel before this one
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int st = it % kTmaStages;
+        const unsigned parity = (unsigned)((it / kTmaStages) & 1);
+        const long long r0 = tile * kLossRows;
+        const int nrows = (int)min((long long)kLossRows, rows - r0);
+        // keep the ring full: the stage refilled here was released by the barrier at the end of the previous tile
+        if (tid == 0) {
+            const long long nxt = tile + (long long)(kTmaStages - 1) * gridDim.x;
+            if (nxt < ntiles) issue(nxt, (it + kTmaStages - 1) % kTmaStages);
+        }
+        const long long r = r0 + tid;
+        long long t = 0;
+        float2 arm = make_float2(0.f, 0.f);
+        if (tid < nrows) {
+            t = conf_t[r];
+            if (arm_conf && t > 0) arm = __ldg(arm_conf + r);
+        }
+        float* x_tile = s_x + (size_t)st * tile_floats;
+        const int nelem = nrows * C;
+        for (int e2 = (nelem & ~3) + tid; e2 < nelem; e2 += kLossRows) x_tile[e2] = conf[r0 * C + e2];   // < 4 floats, last tile only
+        mbar_wait(&s_bar[st], parity);
+        if ((nelem & 3) != 0) __syncthreads();
+        if (tid < nrows)
+            conf_row(x_tile + tid * C, C, t, arm, arm_conf != nullptr, theta, ce_out + r, lse_out + r, pos_out + r);
+        __syncthreads();                                      // every thread is done with the stage: it may be refilled
     }
 }
 
@@ -147,6 +253,7 @@ conf_loss2_kernel(const float2* __restrict__ conf, const long long* __restrict__
     const long long r = (long long)blockIdx.x * kLossThreads + threadIdx.x;
     if (r >= rows) return;
     const float2 x = ldg_stream2(conf + r);
+    grid_dependency_wait();                          // conf_t comes from the kernel before this one
     const long long t = conf_t[r];
     const float m = fmaxf(x.x, x.y);
     const float s = expf(x.x - m) + expf(x.y - m);
@@ -169,13 +276,42 @@ __device__ __forceinline__ double smooth_l1(float p, float t) {
 // anchors i = g*256 + tid (mod kReduceSplit*256) of image b
 constexpr int kReduceSplit = 8;
 
+// the final step, one warp: lane l sums the partials q = l, l + 32, ... in order, then a fixed xor tree ->
+// deterministic.  N = sum(num_pos) (:134); N < 1 -> zeros (:135-136)
+__device__ __forceinline__ void loss_final_warp(const double* __restrict__ partial, const int* __restrict__ num_pos, int B,
+                                                float* loss_l, float* loss_c, float* n_out) {
+    const int lane = threadIdx.x & 31;
+    double tl = 0.0, tc = 0.0;
+    long long n = 0;
+    for (int q = lane; q < B * kReduceSplit; q += 32) { tl += partial[2 * q]; tc += partial[2 * q + 1]; }
+    for (int b = lane; b < B; b += 32) n += num_pos[b];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        tl += __shfl_xor_sync(kFullMask, tl, d);
+        tc += __shfl_xor_sync(kFullMask, tc, d);
+        n += __shfl_xor_sync(kFullMask, n, d);
+    }
+    if (lane == 0) {
+        const float N = (float)n;
+        *n_out = N;
+        *loss_l = n > 0 ? (float)tl / N : 0.f;
+        *loss_c = n > 0 ? (float)tc / N : 0.f;
+    }
+}
+
+// kFinal: the CTA that finishes last (a ticket counter, zero before the launch and left zero) also runs the final
+// step, in the same fixed order as the separate kernel -- one launch and ~6 us of pure latency less per criterion.
+template <bool kFinal>
 __global__ void __launch_bounds__(kLossThreads)
 loss_reduce_kernel(const float4* __restrict__ loc, const float4* __restrict__ loc_t, const float* __restrict__ ce,
                    const unsigned char* __restrict__ pos, const unsigned char* __restrict__ neg, int P,
-                   double* __restrict__ partial) {
+                   double* __restrict__ partial, unsigned int* ticket, const int* __restrict__ num_pos, int B,
+                   float* loss_l, float* loss_c, float* n_out) {
     __shared__ double s_l[kLossThreads / 32], s_c[kLossThreads / 32];
+    __shared__ int s_last;
     const int g = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t img = (size_t)b * P;
+    grid_dependency_wait();                          // neg / num_pos of the mining kernel (and everything before it)
     double al = 0.0, ac = 0.0;
     for (int i = g * kLossThreads + tid; i < P; i += kReduceSplit * kLossThreads) {
         const bool p = pos[img + i] != 0;
@@ -198,30 +334,24 @@ loss_reduce_kernel(const float4* __restrict__ loc, const float4* __restrict__ lo
         for (int w = 0; w < kLossThreads / 32; ++w) { tl += s_l[w]; tc += s_c[w]; }
         partial[2 * (b * kReduceSplit + g)] = tl;
         partial[2 * (b * kReduceSplit + g) + 1] = tc;
+        if (kFinal) {
+            __threadfence();                         // the partials are visible before the ticket is
+            s_last = atomicAdd(ticket, 1u) == (unsigned int)(gridDim.x * gridDim.y) - 1u;
+        }
+    }
+    if (!kFinal) return;
+    __syncthreads();
+    if (!s_last) return;
+    if (warp == 0) {
+        __threadfence();
+        loss_final_warp(partial, num_pos, B, loss_l, loss_c, n_out);
+        if (lane == 0) *ticket = 0u;
     }
 }
 
-// one warp: lane l sums the partials q = l, l + 32, ... in order, then a fixed xor tree -> deterministic.
-// N = sum(num_pos) (:134); N < 1 -> zeros (:135-136)
 __global__ void loss_final_kernel(const double* __restrict__ partial, const int* __restrict__ num_pos, int B,
                                   float* loss_l, float* loss_c, float* n_out) {
-    const int lane = threadIdx.x;
-    double tl = 0.0, tc = 0.0;
-    long long n = 0;
-    for (int q = lane; q < B * kReduceSplit; q += 32) { tl += partial[2 * q]; tc += partial[2 * q + 1]; }
-    for (int b = lane; b < B; b += 32) n += num_pos[b];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        tl += __shfl_xor_sync(kFullMask, tl, d);
-        tc += __shfl_xor_sync(kFullMask, tc, d);
-        n += __shfl_xor_sync(kFullMask, n, d);
-    }
-    if (lane == 0) {
-        const float N = (float)n;
-        *n_out = N;
-        *loss_l = n > 0 ? (float)tl / N : 0.f;
-        *loss_c = n > 0 ? (float)tc / N : 0.f;
-    }
+    loss_final_warp(partial, num_pos, B, loss_l, loss_c, n_out);
 }
 
 // gradients.  One warp per 32 rows; conf rows of unselected anchors are never read.
@@ -292,6 +422,49 @@ loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ 
 
 using namespace rd;
 
+// launches the confidence-loss kernel that fits (C == 2: thread per row; odd C and aligned rows: the TMA ring;
+// otherwise the cp.async / register-staged tiles)
+static int conf_loss_launch(const float* conf, const long long* conf_t, const float* arm_conf, float theta, long long rows,
+                            int C, float* ce_out, float* lse_out, unsigned char* pos_out, cudaStream_t st, bool pdl) {
+    cudaError_t e = cudaSuccess;
+    if (C == 2) {
+        const long long blocks = (rows + kLossThreads - 1) / kLossThreads;
+        if (pdl) e = launch_pdl(conf_loss2_kernel, dim3((unsigned)blocks), dim3(kLossThreads), 0, st, (const float2*)conf, conf_t,
+                                (const float2*)arm_conf, theta, rows, ce_out, lse_out, pos_out);
+        else conf_loss2_kernel<<<(unsigned)blocks, kLossThreads, 0, st>>>((const float2*)conf, conf_t, (const float2*)arm_conf,
+                                                                          theta, rows, ce_out, lse_out, pos_out);
+    } else if ((C & 1) && ((uintptr_t)conf & 15) == 0 && !getenv("RD_NO_TMA")) {
+        const size_t smem = (size_t)kTmaStages * kLossRows * C * sizeof(float);
+        static size_t s_tma_smem[kMaxDevices];
+        e = ensure_dynamic_smem(conf_loss_tma_kernel, smem, s_tma_smem);
+        if (e != cudaSuccess) return (int)e;
+        const long long ntiles = (rows + kLossRows - 1) / kLossRows;
+        long long per_sm = (long long)(220 * 1024) / (long long)(smem + 1024);
+        if (per_sm < 1) per_sm = 1;
+        long long blocks = 148 * per_sm;                      // persistent: one wave
+        if (blocks > ntiles) blocks = ntiles;
+        if (pdl) e = launch_pdl(conf_loss_tma_kernel, dim3((unsigned)blocks), dim3(kLossRows), smem, st, conf, conf_t,
+                                (const float2*)arm_conf, theta, rows, C, ce_out, lse_out, pos_out);
+        else conf_loss_tma_kernel<<<(unsigned)blocks, kLossRows, smem, st>>>(conf, conf_t, (const float2*)arm_conf, theta, rows,
+                                                                             C, ce_out, lse_out, pos_out);
+    } else {
+        const size_t smem = (size_t)kLossRows * (C | 1) * sizeof(float);
+        static size_t s_conf_smem[kMaxDevices];
+        e = ensure_dynamic_smem(conf_loss_kernel, smem, s_conf_smem);
+        if (e != cudaSuccess) return (int)e;
+        long long blocks = (rows + kLossRows - 1) / kLossRows;
+        if (blocks > 148 * 64) blocks = 148 * 64;
+        if (pdl) e = launch_pdl(conf_loss_kernel, dim3((unsigned)blocks), dim3(kLossRows), smem, st, conf, conf_t,
+                                (const float2*)arm_conf, theta, rows, C, ce_out, lse_out, pos_out);
+        else conf_loss_kernel<<<(unsigned)blocks, kLossRows, smem, st>>>(conf, conf_t, (const float2*)arm_conf, theta, rows, C,
+                                                                         ce_out, lse_out, pos_out);
+    }
+    if (e != cudaSuccess) return (int)e;
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" {
 
 size_t rd_multibox_loss_workspace_bytes(int B) { return B > 0 ? (size_t)B * kReduceSplit * 2 * sizeof(double) : 0; }
@@ -301,25 +474,8 @@ int rd_conf_loss(const float* conf, const long long* conf_t, const float* arm_co
     if (!conf || !conf_t || !ce_out || !lse_out || !pos_out || rows <= 0 || C < 2) return RD_ERR_BAD_ARG;
     if (C > kLossMaxClasses) return RD_ERR_UNSUPPORTED;
     if (arm_conf && ((uintptr_t)arm_conf & 7)) return RD_ERR_ALIGNMENT;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (C == 2) {
-        if ((uintptr_t)conf & 7) return RD_ERR_ALIGNMENT;
-        const long long blocks = (rows + kLossThreads - 1) / kLossThreads;
-        conf_loss2_kernel<<<(unsigned)blocks, kLossThreads, 0, st>>>((const float2*)conf, conf_t, (const float2*)arm_conf,
-                                                                     theta, rows, ce_out, lse_out, pos_out);
-    } else {
-        const size_t smem = (size_t)kLossRows * (C | 1) * sizeof(float);
-        static size_t s_conf_smem[kMaxDevices];
-        cudaError_t e = ensure_dynamic_smem(conf_loss_kernel, smem, s_conf_smem);
-        if (e != cudaSuccess) return (int)e;
-        long long blocks = (rows + kLossRows - 1) / kLossRows;
-        if (blocks > 148 * 64) blocks = 148 * 64;
-        conf_loss_kernel<<<(unsigned)blocks, kLossRows, smem, st>>>(conf, conf_t, (const float2*)arm_conf, theta, rows, C,
-                                                                    ce_out, lse_out, pos_out);
-    }
-    note_launch();
-    RD_CHECK_LAUNCH();
-    return 0;
+    if (C == 2 && ((uintptr_t)conf & 7)) return RD_ERR_ALIGNMENT;
+    return conf_loss_launch(conf, conf_t, arm_conf, theta, rows, C, ce_out, lse_out, pos_out, (cudaStream_t)stream, false);
 }
 
 int rd_multibox_loss_reduce(const float* loc, const float* loc_t, const float* ce, const unsigned char* pos,
@@ -332,11 +488,83 @@ int rd_multibox_loss_reduce(const float* loc, const float* loc_t, const float* c
     if ((uintptr_t)workspace & 7) return RD_ERR_ALIGNMENT;
     if (workspace_bytes < rd_multibox_loss_workspace_bytes(B)) return RD_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    loss_reduce_kernel<<<dim3(kReduceSplit, B), kLossThreads, 0, st>>>((const float4*)loc, (const float4*)loc_t, ce, pos, neg, P,
-                                                   (double*)workspace);
+    loss_reduce_kernel<false><<<dim3(kReduceSplit, B), kLossThreads, 0, st>>>((const float4*)loc, (const float4*)loc_t, ce, pos, neg,
+                                                                              P, (double*)workspace, nullptr, num_pos, B, loss_l,
+                                                                              loss_c, n_out);
     note_launch();
     RD_CHECK_LAUNCH();
     loss_final_kernel<<<1, 32, 0, st>>>((const double*)workspace, num_pos, B, loss_l, loss_c, n_out);
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---- the whole criterion forward as one call ---------------------------------------------------------------------
+// workspace: [ticket u32, padded to 256 B | best_prior u64 [B][Gmax] | bt_idx i32 [B][P] | bt_overlap f32 [B][P] |
+//             partial f64 [B][kReduceSplit][2]]; ticket + best_prior are cleared by one memset
+struct CriterionWs {
+    unsigned int* ticket;
+    unsigned long long* best_prior;
+    int* bt_idx;
+    float* bt_ov;
+    double* partial;
+    size_t clear_bytes, total;
+};
+static CriterionWs carve_criterion(void* base, int B, int P, int Gmax) {
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    CriterionWs w;
+    unsigned char* p = static_cast<unsigned char*>(base);
+    size_t o = 0;
+    w.ticket = reinterpret_cast<unsigned int*>(p + o);             o += 256;
+    w.best_prior = reinterpret_cast<unsigned long long*>(p + o);   o += up((size_t)B * Gmax * 8);
+    w.clear_bytes = o;
+    w.bt_idx = reinterpret_cast<int*>(p + o);                      o += up((size_t)B * P * 4);
+    w.bt_ov = reinterpret_cast<float*>(p + o);                     o += up((size_t)B * P * 4);
+    w.partial = reinterpret_cast<double*>(p + o);                  o += up((size_t)B * kReduceSplit * 2 * sizeof(double));
+    w.total = o;
+    return w;
+}
+
+size_t rd_multibox_criterion_workspace_bytes(int B, int P, int Gmax) {
+    if (B <= 0 || P <= 0 || Gmax <= 0) return 0;
+    return carve_criterion(nullptr, B, P, Gmax).total;
+}
+
+int rd_multibox_criterion(const float* truths, const float* labels, const int* gt_count, const float* priors,
+                          const float* arm_loc, const float* loc_data, const float* conf_data, const float* arm_conf_gate,
+                          int B, int P, int C, int Gmax, float threshold, float v0, float v1, int label_mode, float theta,
+                          int negpos_ratio, void* workspace, size_t workspace_bytes, float* loc_t, long long* conf_t,
+                          float* ce, float* lse, unsigned char* pos, unsigned char* neg, int* num_pos, float* losses,
+                          void* stream) {
+    if (!truths || !labels || !gt_count || !priors || !loc_data || !conf_data || !workspace || !loc_t || !conf_t || !ce ||
+        !lse || !pos || !neg || !num_pos || !losses)
+        return RD_ERR_BAD_ARG;
+    if (B <= 0 || P <= 0 || Gmax <= 0 || C < 2 || label_mode < 0 || label_mode > 2 || negpos_ratio < 0) return RD_ERR_BAD_ARG;
+    if (Gmax > RD_MAX_GT || B > 65535 || C > kLossMaxClasses) return RD_ERR_UNSUPPORTED;
+    if ((((uintptr_t)truths | (uintptr_t)priors | (uintptr_t)loc_t | (uintptr_t)loc_data | (uintptr_t)workspace) & 15) ||
+        (arm_loc && ((uintptr_t)arm_loc & 15)) || ((uintptr_t)conf_t & 7) || (arm_conf_gate && ((uintptr_t)arm_conf_gate & 7)) ||
+        (C == 2 && ((uintptr_t)conf_data & 7)))
+        return RD_ERR_ALIGNMENT;
+    const CriterionWs w = carve_criterion(workspace, B, P, Gmax);
+    if (workspace_bytes < w.total) return RD_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(workspace, 0, w.clear_bytes, st);
+    if (e != cudaSuccess) return (int)e;
+    // refine_match / match (box_utils.py:70-160), batched: pass 1 + pass 2
+    int rc = match_launch((const float4*)truths, labels, gt_count, (const float4*)priors, (const float4*)arm_loc, B, P, Gmax,
+                          threshold, v0, v1, label_mode, w.best_prior, w.bt_ov, w.bt_idx, (float4*)loc_t, conf_t, st, true);
+    if (rc != 0) return rc;
+    // per-anchor confidence loss, ARM-theta gate of the positives (:96-101, :113-114)
+    rc = conf_loss_launch(conf_data, conf_t, arm_conf_gate, theta, (long long)B * P, C, ce, lse, pos, st, true);
+    if (rc != 0) return rc;
+    // hard-negative mining (:117-123)
+    rc = hnm_launch(ce, pos, B, P, negpos_ratio, neg, num_pos, st, true);
+    if (rc != 0) return rc;
+    // SmoothL1 over pos, cross-entropy over pos | neg, / N (:105-110, :126-138); the last CTA finishes
+    e = launch_pdl(loss_reduce_kernel<true>, dim3(kReduceSplit, B), dim3(kLossThreads), 0, st, (const float4*)loc_data,
+                   (const float4*)loc_t, (const float*)ce, (const unsigned char*)pos, (const unsigned char*)neg, P, w.partial,
+                   w.ticket, (const int*)num_pos, B, losses, losses + 1, losses + 2);
+    if (e != cudaSuccess) return (int)e;
     note_launch();
     RD_CHECK_LAUNCH();
     return 0;

@@ -16,11 +16,14 @@
 //                        num_neg-th largest (loss, ~index) key, write the neg mask; the row lives in
 //                        registers (16 values per thread) when P <= 16,384
 //   elementwise kernels  point_form / center_size / decode / encode / intersect / jaccard
+#include <cooperative_groups.h>
+
 #include "rd_common.cuh"
 
 namespace rd {
 
 constexpr int kMatchThreads = 256;
+constexpr int kMatchDirect = 96;       // up to this many truths per image: no CTA-level truth list (see match_pass1_kernel)
 
 // key of (overlap, prior): larger overlap wins, then the LOWER prior index (torch.max returns
 // the first maximal index)
@@ -47,6 +50,7 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
     __shared__ int s_wcnt[kMatchThreads / 32];
     __shared__ int s_nlist;
     const int b = blockIdx.y;
+    grid_dependency_wait();                 // padded targets / cleared best_prior of the launches before this one
     const int G = gt_count[b];
     const int p = blockIdx.x * kMatchThreads + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -54,8 +58,14 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
     for (int g = threadIdx.x; g < G; g += kMatchThreads) {
         s_truth[g] = __ldg(truths + (size_t)b * Gmax + g);
     }
+    // Few truths (G <= kMatchDirect): the warp-level cull below tests every truth with one lane each in a round or
+    // three; building the CTA-level list first (bounding box of the CTA, ordered compaction: five barriers) costs
+    // more than it saves.  The list is then the identity.
+    const bool direct = G <= kMatchDirect;                               // CTA-uniform
     if (threadIdx.x < 4) s_bb[threadIdx.x] = (threadIdx.x < 2) ? 0xffffffffu : 0u;   // min x, min y, max x, max y
-    if (threadIdx.x == 0) s_nlist = 0;
+    if (threadIdx.x == 0) s_nlist = direct ? G : 0;
+    if (direct)
+        for (int g = threadIdx.x; g < G; g += kMatchThreads) s_list[g] = (unsigned short)g;
     __syncthreads();
     const bool valid = p < P;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -66,17 +76,17 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
         uint32_t mxx = valid ? float_to_ordered(box.z) : 0u, mxy = valid ? float_to_ordered(box.w) : 0u;
         mnx = __reduce_min_sync(kFullMask, mnx); mny = __reduce_min_sync(kFullMask, mny);
         mxx = __reduce_max_sync(kFullMask, mxx); mxy = __reduce_max_sync(kFullMask, mxy);
-        if (lane == 0) { atomicMin(&s_bb[0], mnx); atomicMin(&s_bb[1], mny); atomicMax(&s_bb[2], mxx); atomicMax(&s_bb[3], mxy); }
+        if (!direct && lane == 0) { atomicMin(&s_bb[0], mnx); atomicMin(&s_bb[1], mny); atomicMax(&s_bb[2], mxx); atomicMax(&s_bb[3], mxy); }
         wx1 = ordered_to_float(mnx); wy1 = ordered_to_float(mny);      // bounding box of this WARP's anchor boxes
         wx2 = ordered_to_float(mxx); wy2 = ordered_to_float(mxy);
     }
-    __syncthreads();
     // Truths that cannot intersect ANY anchor box of this CTA have IoU exactly 0 with all of them
     // (min(t.x2, a.x2) - max(t.x1, a.x1) <= min(t.x2, bb.x2) - max(t.x1, bb.x1) <= 0, clamped): they can
     // neither become an anchor's best truth (strict >, ascending g, start at (0, g = 0)) nor win a best
     // prior, so they are skipped.  The first CTA of an image visits every truth: it supplies prior 0
     // for truths that overlap nothing (torch.max returns the first index).
-    {
+    if (!direct) {
+        __syncthreads();
         const float bx1 = ordered_to_float(s_bb[0]), by1 = ordered_to_float(s_bb[1]);
         const float bx2 = ordered_to_float(s_bb[2]), by2 = ordered_to_float(s_bb[3]);
         const bool all = blockIdx.x == 0 || !(bx1 <= bx2) || !(by1 <= by2);
@@ -127,7 +137,13 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
                 hit = (cw > 0.0f && ch > 0.0f) || !(cw == cw) || !(ch == ch);
             }
         }
+        // Walk the survivors in ascending g (list order); the loop is warp-uniform.  Per truth: the anchors' IoUs,
+        // each anchor's running best truth, and the warp's best prior for the truth by two warp reductions (max of
+        // the ordered IoU, then the lowest prior among the lanes that reach it -- torch.max returns the first
+        // index); the lane that OWNS the truth in this round keeps the pair and issues ONE 64-bit global max for it
+        // after the walk.  No ballots, branches or atomics inside the walk.
         unsigned todo = __ballot_sync(kFullMask, hit);
+        uint32_t my_mx = 0u, my_who = 0xffffffffu;
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -141,16 +157,15 @@ match_pass1_kernel(const float4* __restrict__ truths, const int* __restrict__ gt
             float iou = inter / (area_t + area_b - inter);
             if (!valid) iou = -1.0f;
             if (iou > best) { best = iou; best_g = g; }        // first maximal index; (0, g = 0) when nothing overlaps
-            // per-truth best prior: only overlapping anchors (or the row's first warp, which supplies prior 0
-            // for a truth that overlaps nothing) can win; one 64-bit global max per (warp, truth)
-            const bool contend = valid && (iou > 0.0f || iou != iou);
-            if (__any_sync(kFullMask, contend) || first_warp_of_row) {
-                uint32_t ord = valid ? float_to_ordered(iou) : 0u;
-                uint32_t mx = __reduce_max_sync(kFullMask, ord);
-                unsigned who = __ballot_sync(kFullMask, valid && ord == mx);
-                if (lane == __ffs(who) - 1) atomicMax(bp_row + g, prior_key(iou, (uint32_t)p));
-            }
+            const uint32_t ord = valid ? float_to_ordered(iou) : 0u;
+            const uint32_t mx = __reduce_max_sync(kFullMask, ord);
+            const uint32_t who = __reduce_min_sync(kFullMask, (valid && ord == mx) ? (uint32_t)p : 0xffffffffu);
+            if (lane == src) { my_mx = mx; my_who = who; }
         }
+        // per-truth best prior: only overlapping anchors (IoU > 0 or NaN) can win -- or the row's first warp, which
+        // supplies prior 0 for a truth that overlaps nothing
+        if (hit && my_who != 0xffffffffu && (my_mx > float_to_ordered(0.0f) || first_warp_of_row))
+            atomicMax(bp_row + g_l, ((unsigned long long)my_mx << 32) | (unsigned long long)(0xffffffffu - my_who));
     }
     if (valid) {
         bt_overlap[(size_t)b * P + p] = best;
@@ -166,13 +181,20 @@ match_pass2_kernel(const float4* __restrict__ truths, const float* __restrict__ 
                    const float* bt_overlap_tmp, const int* bt_idx_tmp,
                    float4* __restrict__ loc_t, long long* __restrict__ conf_t,
                    int* out_bt_idx, float* out_bt_overlap) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int* s_bp = reinterpret_cast<int*>(smem_raw);   // best prior index of each truth
+    // forced[t] = the LAST truth (ascending j, box_utils.py:146-150) whose best prior is anchor p0 + t, or -1: the
+    // truths scatter themselves (one shared-memory max each) instead of every anchor scanning every truth
+    __shared__ int s_forced[kMatchThreads];
     const int b = blockIdx.y;
+    const int p0 = blockIdx.x * kMatchThreads;
+    const int p = p0 + threadIdx.x;
+    s_forced[threadIdx.x] = -1;
+    grid_dependency_wait();                 // match_pass1_kernel
     const int G = gt_count[b];
-    const int p = blockIdx.x * kMatchThreads + threadIdx.x;
-    for (int g = threadIdx.x; g < G; g += kMatchThreads)
-        s_bp[g] = (int)key_index(best_prior[(size_t)b * Gmax + g]);
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += kMatchThreads) {
+        const int bp = (int)key_index(best_prior[(size_t)b * Gmax + g]) - p0;
+        if (bp >= 0 && bp < kMatchThreads) atomicMax(&s_forced[bp], g);
+    }
     __syncthreads();
     if (p >= P) return;
     const size_t o = (size_t)b * P + p;
@@ -186,8 +208,7 @@ match_pass2_kernel(const float4* __restrict__ truths, const float* __restrict__ 
     float ov = bt_overlap_tmp[o];
     int idx = bt_idx_tmp[o];
     // box_utils.py:146-150: best_truth_overlap[best_prior_idx] = 2; ascending j, last j wins
-    for (int g = 0; g < G; ++g)
-        if (s_bp[g] == p) { idx = g; ov = 2.0f; }
+    if (s_forced[threadIdx.x] >= 0) { idx = s_forced[threadIdx.x]; ov = 2.0f; }
     const float4 m = __ldg(truths + (size_t)b * Gmax + idx);
     const float lab = __ldg(labels + (size_t)b * Gmax + idx);
     long long conf;
@@ -314,6 +335,214 @@ hnm_select_kernel(const float* __restrict__ loss_c, const unsigned char* __restr
 }
 
 // ---------------------------------------------------------------------------------------
+// Hard-negative mining, P <= 16,384: one thread-block CLUSTER of kHnmSplit CTAs per image row (4 x 256 threads, every
+// thread keeps 16 (loss, ~index) keys in registers; 128 CTAs for a batch of 32 instead of 32).  The num_neg-th
+// largest key is found by narrowing a key interval [lo, hi]: one histogram round over kHnmBins buckets LINEAR in
+// the key ((key - lo) >> shift; lo / hi start at the row's min / max key, so the buckets adapt to the range the
+// losses really occupy -- a fixed 8-bit digit of the float pattern would put a whole row of cross-entropy values,
+// which share their exponent, into two or three contended bins), per-CTA histograms in shared memory, combined
+// by every CTA of the cluster over distributed shared memory.  The bucket where the count from the top crosses
+// num_neg becomes the new interval (2048 x narrower per round); once it holds few keys they are listed and
+// ranked exactly.  Typically ONE round + the list.  Exact for any input: ties in the loss are ordered by index
+// (the low word of the key), degenerate rows (all losses equal) narrow on the index bits.
+// ---------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int kHnmSplit = 4;
+constexpr int kHnmCT = 256;
+constexpr int kHnmBins = 2048;
+constexpr int kHnmBinsPerT = kHnmBins / kHnmCT;     // 8
+constexpr int kHnmList = 512;                       // keys of the final interval, whole cluster
+
+struct HnmClusterSmem {
+    uint32_t hist[kHnmBins];
+    unsigned long long list[kHnmList];              // this CTA's keys of the final interval
+    unsigned long long all[kHnmList];               // the cluster's
+    unsigned long long kmin, kmax, kmin_neg;        // this CTA's min / max key, min key of a non-positive anchor
+    unsigned long long thresh;
+    uint32_t npos, nlist;
+    uint32_t wsum[kHnmCT / 32];
+    uint32_t found_bin, found_need, found_cnt, total;
+};
+
+__global__ void __cluster_dims__(kHnmSplit, 1, 1) __launch_bounds__(kHnmCT)
+hnm_cluster_kernel(const float* __restrict__ loss_c, const unsigned char* __restrict__ pos, int P, int ratio,
+                   unsigned char* __restrict__ neg_out, int* __restrict__ num_pos_out) {
+    __shared__ HnmClusterSmem S;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    const int b = blockIdx.x / kHnmSplit;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* row = loss_c + (size_t)b * P;
+    const unsigned char* prow = pos + (size_t)b * P;
+    unsigned char* nrow = neg_out + (size_t)b * P;
+    const int i0 = r * (kHnmCT * kHnmPerT);
+    grid_dependency_wait();                                   // the producer of loss_c / pos (conf_loss kernel)
+    if (tid == 0) { S.npos = 0; S.nlist = 0; S.kmin = ~0ull; S.kmax = 0ull; S.kmin_neg = ~0ull; }
+    __syncthreads();
+    // ---- ordered losses into registers (the key of element i is (ord << 32) | ~i, rebuilt where needed);
+    //      positives count as loss 0 (refinedet_multibox_loss.py:117) ------------------------------------------
+    uint32_t ord[kHnmPerT];
+    auto key_of = [&](int j) -> unsigned long long {          // 0 = not an element of the row
+        const int i = i0 + j * kHnmCT + tid;
+        return i < P ? (((unsigned long long)ord[j] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i)) : 0ull;
+    };
+    int local = 0;
+    unsigned long long mn = ~0ull, mx = 0ull, mn_neg = ~0ull;   // mn_neg: over the non-positive anchors only
+#pragma unroll
+    for (int j = 0; j < kHnmPerT; ++j) {
+        const int i = i0 + j * kHnmCT + tid;
+        ord[j] = 0u;
+        if (i < P) {
+            const bool p = prow[i] != 0;
+            local += p ? 1 : 0;
+            ord[j] = float_to_ordered(p ? 0.0f : row[i]);
+            const unsigned long long k = key_of(j);
+            mn = k < mn ? k : mn;
+            mx = k > mx ? k : mx;
+            if (!p) mn_neg = k < mn_neg ? k : mn_neg;
+        }
+    }
+    local = __reduce_add_sync(kFullMask, local);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(kFullMask, mn, d), c = __shfl_xor_sync(kFullMask, mx, d);
+        const unsigned long long e = __shfl_xor_sync(kFullMask, mn_neg, d);
+        mn = a < mn ? a : mn;
+        mx = c > mx ? c : mx;
+        mn_neg = e < mn_neg ? e : mn_neg;
+    }
+    if (lane == 0) {
+        if (local) atomicAdd(&S.npos, (uint32_t)local);
+        atomicMin(&S.kmin, mn);
+        atomicMax(&S.kmax, mx);
+        atomicMin(&S.kmin_neg, mn_neg);
+    }
+    cluster.sync();
+    int num_pos = 0;
+    unsigned long long lo_all = ~0ull, lo = ~0ull, hi = 0ull;
+#pragma unroll
+    for (int q = 0; q < kHnmSplit; ++q) {
+        const HnmClusterSmem* R = cluster.map_shared_rank(&S, q);
+        num_pos += (int)R->npos;
+        lo_all = R->kmin < lo_all ? R->kmin : lo_all;
+        lo = R->kmin_neg < lo ? R->kmin_neg : lo;
+        hi = R->kmax > hi ? R->kmax : hi;
+    }
+    // The first interval starts at the smallest NEGATIVE's key: the positives sit at loss 0, far below the losses
+    // of the negatives, and would stretch the first round's buckets over a range that holds nothing (all negatives
+    // of a row of cross-entropy values in a dozen contended bins).  Should num_neg reach below that key (rows with
+    // more positives than a third of the anchors), the search moves on to [min key, lo - 1] -- see `below`.
+    if (lo > hi) lo = lo_all;                                  // no negative at all
+    if (r == 0 && tid == 0 && num_pos_out) num_pos_out[b] = num_pos;
+    long long want = (long long)ratio * num_pos;
+    if (want > P - 1) want = P - 1;                           // torch.clamp(max=P-1), :122
+    int need = (int)(want < 0 ? 0 : want);
+    unsigned long long thresh_key = ~0ull;                    // need == 0: nothing selected
+    bool listed = false;
+    while (need > 0) {
+        // ---- one narrowing round over [lo, hi] ---------------------------------------------------------------
+        const unsigned long long range = hi - lo;
+        int shift = (64 - __clzll((long long)(range | 1ull))) - 11;      // (range >> shift) < kHnmBins
+        if (shift < 0) shift = 0;
+        for (int i = tid; i < kHnmBins; i += kHnmCT) S.hist[i] = 0;
+        if (tid == 0) S.found_bin = 0xffffffffu;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kHnmPerT; ++j) {
+            const unsigned long long k = key_of(j);
+            if (k >= lo && k <= hi && k != 0ull) atomicAdd(&S.hist[(uint32_t)((k - lo) >> shift)], 1u);
+        }
+        cluster.sync();
+        // combined histogram: thread t owns bins [8 t, 8 t + 8); suffix sums from the top
+        uint32_t c[kHnmBinsPerT];
+        uint32_t s = 0;
+#pragma unroll
+        for (int q = 0; q < kHnmBinsPerT; ++q) c[q] = 0;
+#pragma unroll
+        for (int rr = 0; rr < kHnmSplit; ++rr) {
+            const uint4* h4 = reinterpret_cast<const uint4*>(cluster.map_shared_rank(S.hist, rr)) + tid * (kHnmBinsPerT / 4);
+#pragma unroll
+            for (int q4 = 0; q4 < kHnmBinsPerT / 4; ++q4) {
+                const uint4 v = h4[q4];
+                c[q4 * 4 + 0] += v.x; c[q4 * 4 + 1] += v.y; c[q4 * 4 + 2] += v.z; c[q4 * 4 + 3] += v.w;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kHnmBinsPerT; ++q) s += c[q];
+        uint32_t incl = s;                                    // inclusive suffix sum over the lanes (higher lane = higher keys)
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_down_sync(kFullMask, incl, d);
+            if (lane + d < 32) incl += o;
+        }
+        if (lane == 0) S.wsum[warp] = incl;
+        __syncthreads();
+        uint32_t above = incl - s;                            // keys in bins owned by higher threads
+#pragma unroll
+        for (int w = 0; w < kHnmCT / 32; ++w) if (w > warp) above += S.wsum[w];
+#pragma unroll
+        for (int q = kHnmBinsPerT - 1; q >= 0; --q) {
+            if (above < (uint32_t)need && above + c[q] >= (uint32_t)need) {
+                S.found_bin = (uint32_t)(tid * kHnmBinsPerT + q);
+                S.found_need = (uint32_t)need - above;
+                S.found_cnt = c[q];
+            }
+            above += c[q];
+        }
+        if (tid == 0) S.total = above;                        // keys inside [lo, hi]
+        __syncthreads();
+        const uint32_t fb = S.found_bin, fcnt = S.found_cnt;
+        if (fb == 0xffffffffu) {                              // below: num_neg reaches under the interval (see above)
+            need -= (int)S.total;
+            hi = lo - 1ull;
+            lo = lo_all;
+            cluster.sync();                                   // every CTA has read every histogram
+            continue;
+        }
+        need = (int)S.found_need;
+        const unsigned long long nlo = lo + ((unsigned long long)fb << shift);
+        unsigned long long nhi = nlo + ((1ull << shift) - 1ull);
+        if (nhi > hi || nhi < nlo) nhi = hi;
+        lo = nlo; hi = nhi;
+        cluster.sync();                                       // every CTA has read every histogram: they may be reused
+        if (fcnt == (uint32_t)need) { thresh_key = lo; break; }       // the whole bucket is selected
+        if (fcnt <= (uint32_t)kHnmList) { listed = true; break; }
+    }
+    if (listed) {
+        // ---- the final interval holds few keys: list them, rank exactly ---------------------------------------
+#pragma unroll
+        for (int j = 0; j < kHnmPerT; ++j) {
+            const unsigned long long k = key_of(j);
+            if (k >= lo && k <= hi && k != 0ull) S.list[atomicAdd(&S.nlist, 1u)] = k;
+        }
+        cluster.sync();
+        int tot = 0;
+#pragma unroll
+        for (int rr = 0; rr < kHnmSplit; ++rr) {
+            const HnmClusterSmem* R = cluster.map_shared_rank(&S, rr);
+            const int n_r = (int)R->nlist;
+            for (int i = tid; i < n_r; i += kHnmCT) S.all[tot + i] = R->list[i];
+            tot += n_r;
+        }
+        __syncthreads();
+        for (int i = tid; i < tot; i += kHnmCT) {
+            const unsigned long long k = S.all[i];
+            int rank = 0;
+            for (int q = 0; q < tot; ++q) rank += S.all[q] > k ? 1 : 0;
+            if (rank == need - 1) S.thresh = k;
+        }
+        __syncthreads();
+        thresh_key = S.thresh;
+    }
+#pragma unroll
+    for (int j = 0; j < kHnmPerT; ++j) {
+        const int i = i0 + j * kHnmCT + tid;
+        if (i < P) nrow[i] = (need > 0 && key_of(j) >= thresh_key) ? 1 : 0;
+    }
+    cluster.sync();                                           // nobody leaves while a peer may still read its shared memory
+}
+
+// ---------------------------------------------------------------------------------------
 // target ingestion: the B ragged [G_i, 5] target tensors of a step (data/__init__.py:9-27 detection_collate),
 // concatenated, -> padded truths[B,Gmax,4], labels[B,Gmax], gt_count[B] in one pass
 // ---------------------------------------------------------------------------------------
@@ -363,6 +592,49 @@ __global__ void pairwise_kernel(const float4* __restrict__ box_a, const float4* 
     out[(size_t)i * Bn + j] = IOU ? jaccard_pair(a, b) : intersect_pair(a, b);
 }
 
+
+int hnm_launch(const float* loss_c, const unsigned char* pos, int B, int P, int negpos_ratio, unsigned char* neg_out,
+               int* num_pos_out, cudaStream_t st, bool pdl) {
+    cudaError_t e = cudaSuccess;
+    if (P <= kHnmSplit * kHnmCT * kHnmPerT) {
+        // one cluster of kHnmSplit CTAs per image (the cluster shape is a compile-time attribute of the kernel)
+        if (pdl) e = launch_pdl(hnm_cluster_kernel, dim3(B * kHnmSplit), dim3(kHnmCT), 0, st, loss_c, pos, P, negpos_ratio,
+                                neg_out, num_pos_out);
+        else hnm_cluster_kernel<<<B * kHnmSplit, kHnmCT, 0, st>>>(loss_c, pos, P, negpos_ratio, neg_out, num_pos_out);
+    } else {
+        hnm_select_kernel<false><<<B, kHnmThreads, 0, st>>>(loss_c, pos, P, negpos_ratio, neg_out, num_pos_out);
+    }
+    if (e != cudaSuccess) return (int)e;
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
+
+int match_launch(const float4* truths, const float* labels, const int* gt_count, const float4* priors,
+                 const float4* arm_loc, int B, int P, int Gmax, float threshold, float v0, float v1, int label_mode,
+                 unsigned long long* best_prior, float* bt_overlap, int* bt_idx, float4* loc_t, long long* conf_t,
+                 cudaStream_t st, bool pdl) {
+    const dim3 grid((P + kMatchThreads - 1) / kMatchThreads, B);
+    cudaError_t e;
+    // pass 1 follows the memset of best_prior (not a kernel): plain stream order
+    match_pass1_kernel<<<grid, kMatchThreads, (size_t)Gmax * 18, st>>>(truths, gt_count, priors, arm_loc, P, Gmax, v0, v1,
+                                                                         best_prior, bt_overlap, bt_idx);
+    e = cudaSuccess;
+    note_launch();
+    RD_CHECK_LAUNCH();
+    if (pdl) e = launch_pdl(match_pass2_kernel, grid, dim3(kMatchThreads), (size_t)Gmax * 4, st, truths, labels, gt_count, priors,
+                            arm_loc, P, Gmax, threshold, v0, v1, label_mode, (const unsigned long long*)best_prior,
+                            (const float*)bt_overlap, (const int*)bt_idx, loc_t, conf_t, bt_idx, bt_overlap);
+    else
+        match_pass2_kernel<<<grid, kMatchThreads, (size_t)Gmax * 4, st>>>(truths, labels, gt_count, priors, arm_loc, P, Gmax,
+                                                                            threshold, v0, v1, label_mode, best_prior, bt_overlap,
+                                                                            bt_idx, loc_t, conf_t, bt_idx, bt_overlap);
+    if (e != cudaSuccess) return (int)e;
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
 }  // namespace rd
 
 using namespace rd;
@@ -448,20 +720,9 @@ int rd_refine_match(const float* truths, const float* labels, const int* gt_coun
     if (e != cudaSuccess) return (int)e;
     // best_truth_idx / best_truth_overlap are outputs AND the scratch between the two passes
     if (!best_truth_idx || !best_truth_overlap) return RD_ERR_BAD_ARG;
-    dim3 grid((P + kMatchThreads - 1) / kMatchThreads, B);
-    float* tmp_ov = best_truth_overlap;
-    int* tmp_idx = best_truth_idx;
-    match_pass1_kernel<<<grid, kMatchThreads, (size_t)Gmax * 18, st>>>(
-        (const float4*)truths, gt_count, (const float4*)priors, (const float4*)arm_loc, P, Gmax, v0, v1, best_prior,
-        tmp_ov, tmp_idx);
-    note_launch();
-    RD_CHECK_LAUNCH();
-    match_pass2_kernel<<<grid, kMatchThreads, (size_t)Gmax * 4, st>>>(
-        (const float4*)truths, labels, gt_count, (const float4*)priors, (const float4*)arm_loc, P, Gmax, threshold,
-        v0, v1, label_mode, best_prior, tmp_ov, tmp_idx, (float4*)loc_t, conf_t, best_truth_idx, best_truth_overlap);
-    note_launch();
-    RD_CHECK_LAUNCH();
-    return 0;
+    return match_launch((const float4*)truths, labels, gt_count, (const float4*)priors, (const float4*)arm_loc, B, P, Gmax,
+                        threshold, v0, v1, label_mode, best_prior, best_truth_overlap, best_truth_idx, (float4*)loc_t, conf_t,
+                        st, false);
 }
 
 int rd_pad_targets(const float* flat, const int* offsets, int B, int Gmax, float* truths, float* labels,
@@ -479,13 +740,7 @@ int rd_pad_targets(const float* flat, const int* offsets, int B, int Gmax, float
 int rd_hnm_select(const float* loss_c, const unsigned char* pos, int B, int P, int negpos_ratio,
                   unsigned char* neg_out, int* num_pos_out, void* stream) {
     if (!loss_c || !pos || !neg_out || B <= 0 || P <= 0 || negpos_ratio < 0) return RD_ERR_BAD_ARG;
-    if (P <= kHnmPerT * kHnmThreads)
-        hnm_select_kernel<true><<<B, kHnmThreads, 0, (cudaStream_t)stream>>>(loss_c, pos, P, negpos_ratio, neg_out, num_pos_out);
-    else
-        hnm_select_kernel<false><<<B, kHnmThreads, 0, (cudaStream_t)stream>>>(loss_c, pos, P, negpos_ratio, neg_out, num_pos_out);
-    note_launch();
-    RD_CHECK_LAUNCH();
-    return 0;
+    return hnm_launch(loss_c, pos, B, P, negpos_ratio, neg_out, num_pos_out, (cudaStream_t)stream, false);
 }
 
 int rd_abi_version(void) { return RD_ABI_VERSION; }

@@ -64,6 +64,34 @@ def gather_detections(detections, group=None):
     return gather_packed(detections.counts, rows, group)
 
 
+def gathered_to_coco_arrays(counts_all, rows_all, class_to_cat_id=None):
+    """COCO result records (``rd_coco_records``, see ``Detections.to_coco_arrays``) of the GATHERED detections of
+    every rank — ``(counts_all, rows_all)`` as returned by :func:`gather_packed` / ``PeerExchange.result`` — built on
+    the device from the packed rows: ``ids[n,2]`` int32 = (global image index, class), ``vals[n,5]`` float64."""
+    from ._ffi import check, lib, on_device, ptr, stream_ptr
+    counts = torch.cat([c.reshape(-1, c.shape[-1]) for c in counts_all]).contiguous()
+    rows = torch.cat([r.reshape(-1, 5) for r in rows_all]).contiguous()
+    if not counts.is_cuda:
+        raise RuntimeError('gathered_to_coco_arrays needs CUDA tensors (refinedet.pytorch_b200 has no CPU fallback)')
+    B, C = counts.shape
+    dev = counts.device
+    offsets = torch.zeros(B * C + 1, dtype=torch.int32, device=dev)
+    offsets[1:] = counts.reshape(-1).cumsum(0)
+    cats = None
+    if class_to_cat_id is not None:
+        cats = torch.tensor([-1 if (c == 0 or class_to_cat_id[c] is None) else 1 for c in range(C)],
+                            dtype=torch.int32).to(dev)
+    cap = rows.shape[0]
+    total = torch.empty(1, dtype=torch.int32, device=dev)
+    ids = torch.empty(max(cap, 1), 2, dtype=torch.int32, device=dev)
+    vals = torch.empty(max(cap, 1), 5, dtype=torch.float64, device=dev)
+    with on_device(dev):
+        check(lib().rd_coco_records(ptr(counts), ptr(rows), B, C, 0, ptr(offsets), ptr(cats), ptr(ids), ptr(vals), cap,
+                                    ptr(total), stream_ptr()), 'rd_coco_records')
+    n = int(total.item())
+    return ids[:n].cpu().numpy(), vals[:n].cpu().numpy()
+
+
 # ---------------------------------------------------------------------------------------------
 # packing fused with the gather: P2P stores into every peer's exchange buffer (rd_pack_scatter)
 # ---------------------------------------------------------------------------------------------

@@ -37,31 +37,55 @@ class Detections(object):
         total = int(offsets[-1].item())
         return offsets, rows[:total]
 
+    def to_coco_arrays(self, class_to_cat_id=None):
+        """The records of :meth:`to_coco_results` as two numpy arrays, built on the device (``rd_coco_records``) and
+        copied back once: ``ids[n,2]`` int32 = (image index b, class c), ``vals[n,5]`` float64 = (x, y, w, h, score),
+        in the reference's order (classes ascending, images ascending inside a class, rows score-descending)."""
+        import numpy as np
+        B, C, max_out, _ = self.dets.shape
+        dev = self.dets.device
+        cats = None
+        if class_to_cat_id is not None:
+            cats = torch.tensor([-1 if (c == 0 or class_to_cat_id[c] is None) else 1 for c in range(C)],
+                                dtype=torch.int32).to(dev)
+        cap = B * C * max_out
+        total = torch.empty(1, dtype=torch.int32, device=dev)
+        ids = torch.empty(cap, 2, dtype=torch.int32, device=dev)
+        vals = torch.empty(cap, 5, dtype=torch.float64, device=dev)
+        with on_device(dev):
+            check(lib().rd_coco_records(ptr(self.counts), ptr(self.dets), B, C, max_out, None, ptr(cats), ptr(ids),
+                                        ptr(vals), cap, ptr(total), stream_ptr()), 'rd_coco_records')
+        n = int(total.item())
+        return ids[:n].cpu().numpy(), vals[:n].cpu().numpy()
+
+    def to_coco_numpy(self, image_ids, class_to_cat_id):
+        """The results as ONE ``[n,7]`` float64 array ``(image_id, x, y, w, h, score, category_id)`` — the layout
+        ``pycocotools``' ``COCO.loadRes`` accepts directly (``loadNumpyAnnotations``), so the evaluation needs neither
+        the list of dicts nor the json file of data/sarship_coco.py:293-336.  No Python loop over rows.
+        (``image_ids`` / category ids must be numeric here.)"""
+        import numpy as np
+        ids, vals = self.to_coco_arrays(class_to_cat_id)
+        out = np.empty((ids.shape[0], 7), np.float64)
+        out[:, 0] = np.asarray(image_ids, np.float64)[ids[:, 0]]
+        out[:, 1:6] = vals
+        cats = np.asarray([-1 if c is None else c for c in class_to_cat_id], np.float64)
+        out[:, 6] = cats[ids[:, 1]]
+        return out
+
     def to_coco_results(self, image_ids, class_to_cat_id):
         """The result wire format of the reference's eval (``data/sarship_coco.py:293-336``): a list of
         ``{'image_id', 'category_id', 'bbox': [x, y, w, h], 'score'}`` with ``w = x2 - x1 + 1``,
         ``h = y2 - y1 + 1`` computed in float64 (the reference's ``astype(np.float)``), classes ascending
         (background skipped), images ascending inside a class, rows score-descending.
         ``image_ids[b]`` is the dataset index of image b, ``class_to_cat_id[c]`` the COCO category of
-        class c (``None`` skips the class)."""
-        import numpy as np
-        counts = self.counts.cpu().numpy()
-        dets = self.dets.cpu().numpy()
-        B, C = counts.shape
-        results = []
-        for c in range(1, C):
-            cat = class_to_cat_id[c]
-            if cat is None:
-                continue
-            for b in range(B):
-                d = dets[b, c, :counts[b, c]].astype(np.float64)
-                if d.shape[0] == 0:
-                    continue
-                xs, ys = d[:, 0], d[:, 1]
-                ws, hs = d[:, 2] - xs + 1, d[:, 3] - ys + 1
-                results.extend({'image_id': image_ids[b], 'category_id': cat,
-                                'bbox': [xs[k], ys[k], ws[k], hs[k]], 'score': d[k, 4]} for k in range(d.shape[0]))
-        return results
+        class c (``None`` skips the class).  The records come from the device (:meth:`to_coco_arrays`); the host
+        maps the two indices and wraps the rows — the dicts themselves are what takes the time at 4 x 10^5 rows;
+        :meth:`to_coco_numpy` avoids them."""
+        ids, vals = self.to_coco_arrays(class_to_cat_id)
+        img = [image_ids[b] for b in ids[:, 0].tolist()]
+        cat = [class_to_cat_id[c] for c in ids[:, 1].tolist()]
+        return [{'image_id': i, 'category_id': c, 'bbox': bb, 'score': sc}
+                for i, c, bb, sc in zip(img, cat, vals[:, :4].tolist(), vals[:, 4].tolist())]
 
     def to_all_boxes(self):
         """``all_boxes[c][b]`` numpy arrays ``[n,5]`` as built by eval_refinedet_coco.py:214-232."""
@@ -84,6 +108,26 @@ class DetectPlan(object):
         with on_device(device):
             check(lib().rd_detect_plan_create(*args, ctypes.byref(handle)), 'rd_detect_plan_create')
         self._handle = handle
+
+    @classmethod
+    def capture(cls, device, body, result=None, keep_alive=None):
+        """A plan from whatever ``body()`` enqueues on the current stream (``rd_plan_capture_begin/end``): the
+        stage's launch chain followed by the exchange of its result, for example."""
+        import ctypes
+        self = cls.__new__(cls)
+        self.result, self.device, self._keep = result, device, keep_alive
+        handle = ctypes.c_void_p(0)
+        st = torch.cuda.Stream(device)
+        torch.cuda.synchronize(device)
+        with torch.cuda.stream(st):
+            check(lib().rd_plan_capture_begin(st.cuda_stream), 'rd_plan_capture_begin')
+            try:
+                body()
+            finally:
+                rc = lib().rd_plan_capture_end(st.cuda_stream, ctypes.byref(handle))
+            check(rc, 'rd_plan_capture_end')
+        self._handle = handle
+        return self
 
     def launch(self, stream=None):
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
@@ -257,8 +301,7 @@ class Detect_RefineDet(object):
         self.boxes, self.scores = boxes, scores                  # the reference keeps them on the instance
         return self.boxes, self.scores
 
-    _INSTANCES = {None: 0, 'auto': 0, 256: _ffi.RD_DEBUG_INSTANCE_256, 1024: _ffi.RD_DEBUG_INSTANCE_1024,
-                  512: _ffi.RD_DEBUG_INSTANCE_512}
+    _INSTANCES = {None: 0, 'auto': 0, 256: _ffi.RD_DEBUG_INSTANCE_256, 1024: _ffi.RD_DEBUG_INSTANCE_1024}
 
     def detect(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale=None,
                force_cpu_semantics=False, logits=False, instance=None):
@@ -420,12 +463,14 @@ class Detect_RefineDet(object):
                           torch.empty(B, C, max_out, dtype=torch.int32, device=device), row_layout)
 
     def plan(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale=None,
-             workspace=None, out=None, force_cpu_semantics=False, logits=False, instance=None):
+             workspace=None, out=None, force_cpu_semantics=False, logits=False, instance=None, then=None):
         """:meth:`detect` for FIXED input buffers, captured once (``rd_detect_plan_create``): the returned
         :class:`DetectPlan` replays the whole launch chain with one driver call per batch.  The tensors are
         referenced, not copied — refill them in place between replays.  Plans that share ``workspace`` /
         ``out`` must be replayed on the same stream; give every batch in flight its own pair
-        (:meth:`new_workspace`, :meth:`new_outputs`)."""
+        (:meth:`new_workspace`, :meth:`new_outputs`).  ``then(result)``: a callable that enqueues the consumer of
+        the result on the current stream (e.g. ``PeerExchange.exchange``) — captured into the same plan, so that a
+        step of stage + exchange is still one driver call."""
         flags = _ffi.RD_NMS_PIXEL_PLUS1 | (_ffi.RD_NMS_SUPPRESS_EQ if force_cpu_semantics else 0) | \
             (_ffi.RD_INPUT_LOGITS if logits else 0) | self._INSTANCES[instance]
         for name, t in (('arm_loc_data', arm_loc_data), ('arm_conf_data', arm_conf_data),
@@ -436,7 +481,13 @@ class Detect_RefineDet(object):
                                              scale, flags, _ffi.RD_ROW_BOX_SCORE, self.keep_top_k,
                                              workspace=workspace, out=out)
         torch.cuda.synchronize(dev)      # the workspace reset / pending writers are done before the capture
-        return DetectPlan(args, res, dev, keep)
+        if then is None:
+            return DetectPlan(args, res, dev, keep)
+
+        def body():                      # the launch chain, then whatever consumes the result on the same stream
+            check(lib().rd_detect_fused(*args, stream_ptr()), 'rd_detect_fused')
+            then(res)
+        return DetectPlan.capture(dev, body, res, (keep, then))
 
     def forward_python_nms(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data):
         """detection_refinedet.py:67-113.  Returns ``output[B,C,top_k,5]`` rows

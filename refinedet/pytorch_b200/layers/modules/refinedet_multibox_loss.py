@@ -9,9 +9,10 @@ forward and only on the ``pos | neg`` rows backward
 import torch
 import torch.nn as nn
 
-from ..._ffi import require_cuda_f32
-from ..box_utils import (LABEL_ARM_BINARY, LABEL_ODM, conf_loss, hnm_select, match_batch,
-                         multibox_loss_backward, multibox_loss_reduce, _padded)
+from ctypes import c_void_p
+
+from ..._ffi import check, lib, on_device, ptr, require_cuda_f32, stream_ptr
+from ..box_utils import LABEL_ARM_BINARY, LABEL_ODM, match_batch, _padded
 
 # data/config.py:57 (``coco['variance']``, read at reference :46)
 _VARIANCE = [0.1, 0.2]
@@ -67,44 +68,128 @@ class RefineDetMultiBoxLoss(nn.Module):
 
     def forward(self, predictions, targets):
         """reference :50-139.  ``predictions`` = (arm_loc, arm_conf, odm_loc, odm_conf, priors),
-        ``targets`` = list of ``[G_i,5]`` tensors.  Returns ``(loss_l, loss_c)``."""
+        ``targets`` = list of ``[G_i,5]`` tensors.  Returns ``(loss_l, loss_c)``.
+
+        One native call (``rd_multibox_criterion``: match, confidence loss, mining, reductions — six kernels chained
+        on the device) behind a ``torch.autograd.Function``; backward is one more (``rd_multibox_loss_backward``)."""
         arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, priors = predictions
         if self.use_ARM:
             loc_data, conf_data = odm_loc_data, odm_conf_data
         else:
             loc_data, conf_data = arm_loc_data, arm_conf_data
-        loc_t, conf_t = self.match_targets(predictions, targets)
+        if not loc_data.is_cuda:
+            raise RuntimeError('RefineDetMultiBoxLoss: predictions must be CUDA tensors '
+                               '(refinedet.pytorch_b200 has no CPU fallback)')
+        truths, labels, gt_count, min_count = _padded(targets, loc_data.device)
+        if min_count == 0:
+            raise IndexError('RefineDetMultiBoxLoss: an image has no ground-truth boxes '
+                             '(the reference raises in refine_match, box_utils.py:139)')
+        priors = priors[:loc_data.size(1), :]                                 # :68 (DataParallel gather)
+        mode = LABEL_ARM_BINARY if (self.num_classes == 2 and not self.use_ARM) else LABEL_ODM     # :78-79
+        arm_loc = arm_loc_data.detach() if self.use_ARM else None             # :80-85
         arm_gate = arm_conf_data.detach() if self.use_ARM else None           # :96-101 (softmax inside the kernel)
-        loss_l, loss_c, N, pos, neg = _MultiBoxLossTail.apply(loc_data, conf_data, arm_gate, loc_t, conf_t,
-                                                              float(self.theta), int(self.negpos_ratio))
-        self.last_masks = (pos, neg)        # of this criterion's latest forward, for inspection / tests
+        state = _CriterionState()
+        loss_l, loss_c, N = _Criterion.apply(loc_data, conf_data, state, truths, labels, gt_count, priors.detach(),
+                                             arm_loc, arm_gate, float(self.threshold), self.variance, mode,
+                                             float(self.theta), int(self.negpos_ratio))
+        self._last = state
         if not self.sync_free and float(N) < 1:                     # :135-136 (the reference syncs here too)
             return torch.zeros(1), torch.zeros(1)
         return loss_l, loss_c
 
+    @property
+    def last_masks(self):
+        """``(pos, neg)`` bool ``[B,P]`` of this criterion's latest forward (inspection / tests)."""
+        st = self._last
+        return st.view('pos', torch.bool), st.view('neg', torch.bool)
 
-class _MultiBoxLossTail(torch.autograd.Function):
-    """refinedet_multibox_loss.py:96-138 on the device: forward = rd_conf_loss + rd_hnm_select +
-    rd_multibox_loss_reduce, backward = rd_multibox_loss_backward."""
+    @property
+    def last_targets(self):
+        """``(loc_t, conf_t)`` of this criterion's latest forward."""
+        st = self._last
+        return st.view('loc_t', torch.float32, 4), st.view('conf_t', torch.int64)
+
+
+def _up(n):
+    return (n + 255) // 256 * 256
+
+
+class _CriterionState(object):
+    """Everything one criterion forward leaves on the device for its backward, in ONE allocation:
+    ``loc_t | conf_t | ce | lse | pos | neg | num_pos | workspace`` (256-byte aligned regions)."""
+    __slots__ = ('buf', 'off', 'B', 'P', 'losses')
+    _FIELDS = (('loc_t', 16), ('conf_t', 8), ('ce', 4), ('lse', 4), ('pos', 1), ('neg', 1))
+
+    def allocate(self, B, P, G, device):
+        self.B, self.P = B, P
+        off, o = {}, 0
+        for name, width in self._FIELDS:
+            off[name] = o
+            o += _up(B * P * width)
+        off['num_pos'] = o
+        o += _up(B * 4)
+        off['ws'] = o
+        ws_bytes = int(lib().rd_multibox_criterion_workspace_bytes(B, P, G))
+        self.off = off
+        self.buf = torch.empty(o + ws_bytes, dtype=torch.uint8, device=device)
+        self.losses = torch.empty(3, dtype=torch.float32, device=device)
+        return ws_bytes
+
+    def ptr(self, name):
+        return c_void_p(self.buf.data_ptr() + self.off[name])
+
+    def view(self, name, dtype, inner=None):
+        width = dict(self._FIELDS)[name]
+        t = self.buf[self.off[name]:self.off[name] + self.B * self.P * width].view(dtype)
+        return t.view(self.B, self.P, inner) if inner else t.view(self.B, self.P)
+
+
+class _Criterion(torch.autograd.Function):
+    """refinedet_multibox_loss.py:62-138 on the device: forward = rd_multibox_criterion, backward =
+    rd_multibox_loss_backward.  Differentiable in ``loc_data`` and ``conf_data`` only."""
 
     @staticmethod
-    def forward(ctx, loc_data, conf_data, arm_conf, loc_t, conf_t, theta, negpos_ratio):
+    def forward(ctx, loc_data, conf_data, state, truths, labels, gt_count, priors, arm_loc, arm_gate, threshold,
+                variance, mode, theta, negpos_ratio):
         loc_c = require_cuda_f32(loc_data, 'loc_data')
         conf_c = require_cuda_f32(conf_data, 'conf_data', align=8)
-        B, P = conf_t.shape
-        ce, lse, pos = conf_loss(conf_c, conf_t, arm_conf, theta)              # :96-101, :113-114
-        neg, num_pos = hnm_select(ce, pos, negpos_ratio)                       # :117-123
-        loss_l, loss_c, N = multibox_loss_reduce(loc_c, loc_t, ce, pos, neg, num_pos)   # :105-110, :126-138
-        ctx.save_for_backward(loc_c, conf_c, loc_t, conf_t, lse, pos, neg, N)
-        ctx.mark_non_differentiable(N, pos, neg)
-        return loss_l, loss_c, N, pos, neg
+        priors = require_cuda_f32(priors, 'priors')
+        if arm_loc is not None:
+            arm_loc = require_cuda_f32(arm_loc, 'arm_loc_data')
+        if arm_gate is not None:
+            arm_gate = require_cuda_f32(arm_gate, 'arm_conf_data', align=8)
+        B, P = loc_c.shape[0], loc_c.shape[1]
+        C = conf_c.shape[-1]
+        G = truths.shape[1]
+        if conf_c.numel() != B * P * C or priors.shape[0] != P:
+            raise ValueError('conf_data must be [B,P,C] and priors [P,4] for loc_data [B,P,4]')
+        ws_bytes = state.allocate(B, P, G, loc_c.device)
+        with on_device(loc_c.device):
+            check(lib().rd_multibox_criterion(
+                ptr(truths), ptr(labels), ptr(gt_count), ptr(priors), ptr(arm_loc), ptr(loc_c), ptr(conf_c), ptr(arm_gate),
+                B, P, C, G, threshold, float(variance[0]), float(variance[1]), mode, theta, negpos_ratio,
+                state.ptr('ws'), ws_bytes, state.ptr('loc_t'), state.ptr('conf_t'), state.ptr('ce'), state.ptr('lse'),
+                state.ptr('pos'), state.ptr('neg'), state.ptr('num_pos'), ptr(state.losses), stream_ptr()),
+                'rd_multibox_criterion')
+        loss_l, loss_c, N = state.losses.unbind(0)
+        ctx.save_for_backward(loc_c, conf_c)
+        ctx.state, ctx.keep = state, (truths, labels, gt_count, priors, arm_loc, arm_gate)
+        ctx.mark_non_differentiable(N)
+        return loss_l, loss_c, N
 
     @staticmethod
-    def backward(ctx, g_l, g_c, _g_n, _g_pos, _g_neg):
-        loc_c, conf_c, loc_t, conf_t, lse, pos, neg, N = ctx.saved_tensors
+    def backward(ctx, g_l, g_c, _g_n):
+        loc_c, conf_c = ctx.saved_tensors
+        st = ctx.state
         need_loc, need_conf = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g_l = g_l.contiguous().float() if g_l is not None else None
         g_c = g_c.contiguous().float() if g_c is not None else None
-        grad_loc, grad_conf = multibox_loss_backward(loc_c, loc_t, conf_c, conf_t, lse, pos, neg, g_l, g_c, N,
-                                                     need_loc, need_conf)
-        return grad_loc, grad_conf, None, None, None, None, None
+        grad_loc = torch.empty_like(loc_c) if need_loc else None
+        grad_conf = torch.empty_like(conf_c) if need_conf else None
+        n_dev = c_void_p(st.losses.data_ptr() + 8)
+        with on_device(conf_c.device):
+            check(lib().rd_multibox_loss_backward(ptr(loc_c), st.ptr('loc_t'), ptr(conf_c), st.ptr('conf_t'), st.ptr('lse'),
+                                                  st.ptr('pos'), st.ptr('neg'), ptr(g_l), ptr(g_c), n_dev,
+                                                  st.B * st.P, conf_c.shape[-1], ptr(grad_loc), ptr(grad_conf), stream_ptr()),
+                  'rd_multibox_loss_backward')
+        return (grad_loc, grad_conf) + (None,) * 12

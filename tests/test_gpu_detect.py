@@ -648,3 +648,47 @@ def test_coco_wire_format(rd):
         assert a['bbox'] == b['bbox'] and a['score'] == b['score']
     import json
     json.dumps(got)                                              # serialisable like the reference's file
+
+
+def test_coco_records_device_full_scale(rd):
+    """f-2 at config-3 scale (B = 32, C = 81: ~390 k rows): the device-built records (rd_coco_records) equal the
+    reference's host loop (oracle ``coco_results`` = data/sarship_coco.py:293-336), from the slot layout and from
+    the packed (gathered) rows; classes mapped to None are skipped."""
+    import time
+    from refinedet.pytorch_b200 import dist as rdist
+    B, C = 32, 81
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS['512']).forward().cuda()
+    ins = [t.cuda() for t in gen.detect_inputs(4234, B, priors.shape[0], C, 'sparse')]
+    det = rd.Detect_RefineDet(C, 512, 0, 1000, 0.01, 0.45, 0.01, 500)
+    res = det.detect(*ins, priors, scale=[512.] * 4)
+    ids = [1000 + 3 * b for b in range(B)]
+    cats = [None] + [c + 10 for c in range(1, C)]
+    cats[7] = None                                                # an unmapped class
+    t0 = time.perf_counter()
+    got = res.to_coco_results(ids, cats)
+    t_dev = time.perf_counter() - t0
+    ab = res.to_all_boxes()
+    ab[7] = [np.empty((0, 5), np.float32) for _ in range(B)]
+    t0 = time.perf_counter()
+    exp = bo.coco_results(ab, ids, cats)
+    t_host = time.perf_counter() - t0
+    assert len(got) == len(exp) > 300000
+    assert got == exp                                             # ids, categories, float64 boxes, scores: all equal
+    print('coco records: device path %.3f s, host double loop %.3f s, %d rows' % (t_dev, t_host, len(got)))
+    # arrays only (no dicts): the form a json / pycocotools writer consumes
+    a_ids, a_vals = res.to_coco_arrays(cats)
+    assert a_ids.shape == (len(exp), 2) and a_vals.dtype == np.float64
+    t0 = time.perf_counter()
+    arr7 = res.to_coco_numpy(ids, cats)                           # pycocotools loadRes(ndarray) layout
+    t_np = time.perf_counter() - t0
+    assert arr7.shape == (len(exp), 7)
+    assert np.array_equal(arr7[:, 0], [e['image_id'] for e in exp]) and np.array_equal(arr7[:, 6], [e['category_id'] for e in exp])
+    assert np.array_equal(arr7[:, 1:5], np.array([e['bbox'] for e in exp])) and np.array_equal(arr7[:, 5], [e['score'] for e in exp])
+    print('coco records as one [n,7] array: %.3f s' % t_np)
+    # the same from packed rows (what the multi-GPU gather delivers), split as two "ranks"
+    offs, rows = res.packed()
+    offs = offs.long()
+    half = B // 2
+    cut = int(offs[half * C])
+    g_ids, g_vals = rdist.gathered_to_coco_arrays([res.counts[:half], res.counts[half:]], [rows[:cut], rows[cut:]], cats)
+    assert np.array_equal(g_ids, a_ids) and np.array_equal(g_vals, a_vals)

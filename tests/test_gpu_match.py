@@ -163,6 +163,44 @@ def test_full_size_loss_step(rd):
     assert int((conf_t > 0).sum(1).min()) >= 1
     l2, c2 = odm_crit.match_targets(preds, tg)
     assert torch.equal(c2, conf_t) and torch.equal(l2, loc_t)
+    # the fused criterion call (rd_multibox_criterion) leaves the same targets / masks as the step-by-step entry points
+    for crit, use_arm in ((arm_crit, False), (odm_crit, True)):
+        lt, ct = crit.match_targets(preds, tg)
+        f_lt, f_ct = crit.last_targets
+        assert torch.equal(f_ct, ct) and torch.equal(f_lt, lt)
+        conf = preds[3] if use_arm else preds[1]
+        ce, lse, pos = rd.box_utils.conf_loss(conf, ct, preds[1] if use_arm else None, 0.01)
+        neg, num_pos = rd.box_utils.hnm_select(ce, pos, 3)
+        f_pos, f_neg = crit.last_masks
+        assert torch.equal(f_pos, pos) and torch.equal(f_neg, neg)
+        ll, lc, n = rd.box_utils.multibox_loss_reduce(preds[2] if use_arm else preds[0], lt, ce, pos, neg, num_pos)
+        fl, fc = crit(preds, tg)
+        assert float(fl) == float(ll) and float(fc) == float(lc) and float(n) == float(pos.sum())
+
+
+@pytest.mark.parametrize('P', [16320, 16384, 6375, 300, 20000])
+def test_hnm_degenerate_rows(rd, P):
+    """The interval-narrowing select of hnm_cluster_kernel (P <= 16,384; the radix kernel beyond) on rows built to
+    defeat a value-based bucketing: all losses equal (ties broken by index only), two distinct values, a few huge
+    outliers, losses that differ in their last bit, inf / tiny values, every anchor positive but one."""
+    g = torch.Generator().manual_seed(P)
+    rows = [torch.full((P,), 2.5), torch.zeros(P),
+            torch.where(torch.rand(P, generator=g) < 0.5, torch.tensor(1.0), torch.tensor(3.0)),
+            torch.cat([torch.rand(P - 3, generator=g), torch.tensor([1e30, 3e38, float('inf')])]),
+            (torch.full((P,), 4.0).view(torch.int32) + torch.randint(0, 4, (P,), generator=g, dtype=torch.int32)).view(torch.float32),
+            torch.rand(P, generator=g) * 1e-38, torch.rand(P, generator=g) * 8, torch.rand(P, generator=g)]
+    loss = torch.stack(rows)
+    B = loss.shape[0]
+    pos = torch.rand(B, P, generator=g) < 0.02
+    pos[-1] = True
+    pos[-1, P // 2] = False                          # one negative, 3 * num_pos clamps to P - 1 ... of which one exists
+    pos[-2] = torch.rand(P, generator=g) < 0.3       # clamp bites
+    neg, num_pos = rd.box_utils.hnm_select(loss.cuda(), pos.cuda(), 3)
+    e_neg, _ = bo.hnm_select(loss.numpy(), pos.numpy(), 3)
+    assert np.array_equal(num_pos.cpu().numpy(), pos.sum(1).numpy())
+    got = neg.cpu().numpy()
+    for b in range(B):
+        assert np.array_equal(got[b], e_neg[b]), (b, int(got[b].sum()), int(e_neg[b].sum()))
 
 
 def _torch_tail(loc_data, conf_data, loc_t, conf_t, pos, neg):

@@ -48,18 +48,55 @@ def main():
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         return float(dt) * 1e3
 
+    def timed_dev(fn, n=30):
+        """device time per call (CUDA events on the current stream), max over ranks"""
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        dt = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt)
+
     counts_n, rows_n = rdist.gather_detections(res)
     ms_nccl = timed(lambda: rdist.gather_detections(res))
-    out = {'world': world, 'rows_per_rank': int(rows_n[rank].shape[0]), 'nccl_gather_ms': ms_nccl}
+    out = {'world': world, 'rows_per_rank': int(rows_n[rank].shape[0]), 'nccl_gather_ms': ms_nccl, 'sweep': []}
+    ok_all = True
     try:
-        ex = rdist.PeerExchange(B, C, res.dets.shape[2], dev)
-        ex.exchange(res)
-        counts_p, rows_p = ex.result()
-        ok = all(torch.equal(counts_p[r], counts_n[r]) and torch.equal(rows_p[r], rows_n[r]) for r in range(world))
-        out['peer_equals_nccl'] = bool(ok)
-        out['peer_exchange_ms'] = timed(lambda: (ex.exchange(res), ex.result()))
-        # device-only time of the fused pack + scatter (+ the two barriers), no host read of the headers
-        out['peer_exchange_device_ms'] = timed(lambda: ex.exchange(res))
+        for mode in ('p2p', 'multicast'):
+            for ctas in ((8, 16, 24, 48) if mode == 'p2p' else (24, 48, 96, 148)):
+                try:
+                    ex = rdist.PeerExchange(B, C, res.dets.shape[2], dev, mode=mode, copy_ctas=ctas)
+                except RuntimeError as e:
+                    out['sweep'].append({'mode': mode, 'error': repr(e)[:120]})
+                    break
+                ex.buf.zero_()
+                torch.cuda.synchronize()
+                dist.barrier()
+                ex.exchange(res)
+                counts_p, rows_p = ex.result()
+                ok = all(torch.equal(counts_p[r], counts_n[r]) and torch.equal(rows_p[r], rows_n[r]) for r in range(world))
+                ok_all = ok_all and ok
+                rec = {'mode': ex.mode, 'copy_ctas': ctas, 'equals_nccl': bool(ok),
+                       'device_ms': timed_dev(lambda: ex.exchange(res)),
+                       'with_host_read_ms': timed(lambda: (ex.exchange(res), ex.result()))}
+                if not out['sweep'] or 'barriers_only_device_ms' not in out:
+                    out['barriers_only_device_ms'] = timed_dev(lambda: (ex.hdl.barrier(channel=0), ex.hdl.barrier(channel=1)))
+                out['sweep'].append(rec)
+                del ex
+        out['peer_equals_nccl'] = bool(ok_all)
+        good = [r for r in out['sweep'] if 'device_ms' in r]
+        if good:
+            best = min(good, key=lambda r: r['device_ms'])
+            out['best'] = best
+            bytes_out = out['rows_per_rank'] * 20 * (world - 1)
+            out['egress_GBs_unicast_equiv'] = bytes_out / (best['device_ms'] * 1e-3) / 1e9
     except Exception as e:  # symmetric memory not available on this box
         out['peer_exchange_error'] = repr(e)[:300]
     if rank == 0:

@@ -23,8 +23,10 @@ def main():
     out = {'source': rep.split('/')[-1], 'how': 'ncu --set full --clock-control none, one launch per kernel',
            'kernels': {}}
     for r in data:
-        name = r[col['Kernel Name']].split('(')[0]
-        name = re.sub(r'<.*?>', '', re.sub(r'^void\s+', '', name)).split('::')[-1].strip()
+        name = r[col['Kernel Name']].split('(FusedNmsArgs')[0].split('(const')[0]
+        name = re.sub(r'\(int\)|\(bool\)|rd::', '', re.sub(r'^void\s+', '', name)).strip()     # keeps the template arguments
+        while name in out['kernels']:
+            name += "'"
         rd = float(r[col['dram__bytes_read.sum']]) * UNIT[units[col['dram__bytes_read.sum']]]
         wr = float(r[col['dram__bytes_write.sum']]) * UNIT[units[col['dram__bytes_write.sum']]]
         dur = float(r[col['gpu__time_duration.sum']])
