@@ -7,9 +7,10 @@
 A *step* is one pass of the detect stage (ARM filter, two-stage decode, per-class threshold,
 top-k 1000, pixel NMS 0.45, keep 500/class) over a batch of synthetic images of BASELINE.json
 config 3 (P = 16,320 anchors, C = 81 classes): 32 images per rank (``--scaling weak``, default) or
-32 images in all, sharded by rank (``--scaling strong``).  With more than one rank a step also
-contains the path's one exchange: the all-gather of the compact detections (pack + P2P scatter over
-NVLink, ``dist.PeerExchange``), overlapped with the stage of the next batches on the other lanes.
+32 images in all, sharded by rank (``--scaling strong``).  With more than one rank the line also
+carries ``with_exchange``: the same steps with the path's one exchange inside every step -- the
+all-gather of the compact detections (pack + P2P copy over NVLink + rendezvous, ``dist.PeerExchange``),
+captured into the step's plan and overlapped with the stage of the next batches on the other lanes.
 
 ONE compact JSON line on stdout (rank 0); the long-form record (notes, per-kernel times, every
 secondary measurement) goes to stderr as a second JSON line prefixed ``BENCH_DETAIL``.
@@ -64,8 +65,8 @@ def make_config(workload, scaling):
         batch, per_gpu = 'B=%d in all, sharded over the ranks' % BATCH, None
     else:
         batch, per_gpu = 'B=%d/GPU' % BATCH, BATCH
-    sharding = 'images sharded by rank; the one exchange (all-gather of the compact detections over NVLink) ' \
-               'is inside every step when n_gpus > 1'
+    sharding = 'images sharded by rank; value = the detect stage of every rank (no data-path collective inside it); ' \
+               'with_exchange = the same steps with the all-gather of the compact detections over NVLink inside every step'
     return {'workload': 'RefineDet512 COCO detect stage: %s, P=%d, C=%d, top_k=%d, keep_top_k=%d, %s generator'
                         % (batch, P, C, TOP_K, KEEP_TOP_K, workload),
             'batch_per_gpu': per_gpu, 'anchors': P, 'classes': C, 'generator': workload, 'sharding': sharding}
@@ -199,6 +200,26 @@ def cpu_reference_run(kind, steps, warmup, cores, budget_s=None):
         'eval_refinedet_coco.py:205-232 with py_cpu_nms semantics (baseline/_ref absent)'
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process (and, by first touch, the pinned host buffers it allocates afterwards) to the CPU cores NVML
+    reports as local to GPU ``index``: with one process per GPU the zero-copy reads of the e2e path then cross the
+    GPU's own PCIe root instead of the socket interconnect.  Returns the number of cores, or None when unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def median(xs):
     s = sorted(xs)
     return s[len(s) // 2]
@@ -245,6 +266,7 @@ def main():
     # ---- native arm -------------------------------------------------------------------------
     if not torch.cuda.is_available():
         raise RuntimeError('bench.py (native arm) needs a CUDA device: there is no CPU fallback')
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     dist = None
@@ -343,20 +365,29 @@ def main():
     # ---- timed regions: exactly K steps each --------------------------------------------------------
     K = max(1, args.steps)
     R = max(1, args.regions)
+    # value = the detect stage (decode + NMS: BASELINE.json's metric), every rank on its own images
     launches0 = _ffi.launch_count()
     with clocks:
-        reg_ms, reg_local = timed_regions(K, R, step)
+        reg_ms, reg_local = timed_regions(K, R, lambda i: step(i, False))
     launches = (_ffi.launch_count() - launches0) // R
     total_ms = median(reg_ms)
     ms_per_step = total_ms / K
     value = B_total * K / (total_ms * 1e-3)
     regions = {'n': R, 'ms_per_step_min': min(reg_ms) / K, 'ms_per_step_median': ms_per_step,
                'ms_per_step_max': max(reg_ms) / K}
-    stage_only = None
-    if exchanges is not None:                    # the same regions without the exchange (what round 1 reported)
+    # with_exchange = the same K-step regions with the path's one exchange inside EVERY step: stage + all-gather of the
+    # compact detections as one captured plan per lane, the exchange of a batch overlapping the stage of the next
+    # batches on the other lanes (N > 1 only)
+    with_exchange = None
+    if exchanges is not None:
         with clocks:
-            so_ms, _ = timed_regions(K, max(3, R // 3), lambda i: step(i, False))
-        stage_only = {'value': B_total * K / (median(so_ms) * 1e-3), 'ms_per_step': median(so_ms) / K}
+            x_ms, _ = timed_regions(K, R, lambda i: step(i, True))
+        with_exchange = {'value': B_total * K / (median(x_ms) * 1e-3), 'unit': UNIT, 'ms_per_step': median(x_ms) / K,
+                         'ms_per_step_min': min(x_ms) / K, 'ms_per_step_max': max(x_ms) / K, 'regions': R,
+                         'mode': exchanges[0].mode,
+                         'bytes_received_per_gpu_per_step': 20 * kept_rows * (world - 1)}
+    elif dist is not None:
+        with_exchange = {'error': exchange_err}
 
     # ---- latency of ONE batch: single stream, L2 flushed (untimed) before every step -------------------
     KL = min(max(K, 20), 50)
@@ -477,13 +508,17 @@ def main():
                                    'h2d_bytes_per_step': full_bytes}}
         del pipe
 
-    def flushed_ms(fn, n=10, warm=3):
+    def flushed_ms(fn, n=10, warm=3, flush=True):
+        """Median device time of fn() with a 512 MiB memset (L2 flush, untimed) before every call.  The memset also keeps
+        the GPU busy while the host prepares the launch, so the event pair brackets device time only (measured: with
+        rotated inputs and NO memset the same kernels read 12 - 14 us longer -- the host's launch latency)."""
         for _ in range(warm):
             fn()
         torch.cuda.synchronize()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         for a, b in evs:
-            flush_buf.zero_()
+            if flush:
+                flush_buf.zero_()
             a.record(main_st)
             fn()
             b.record(main_st)
@@ -612,16 +647,32 @@ def main():
         neg_k, npos_k = bu.hnm_select(ce_k, pos_k, 3)
         one_k, n_k = torch.ones((), device=dev), pos_k.sum().float()
         kernels = {}
-        for name, byts, fn in (
+        conf_rot = [tp[3], tp[3].clone()]                       # 2 x 169 MB, alternated
+        gconf_rot = [torch.empty_like(tp[3]) for _ in range(2)]
+        gloc_k = torch.empty_like(tp[2])
+        rot = {'i': 0}
+
+        def conf_loss_rot():
+            rot['i'] += 1
+            bu.conf_loss(conf_rot[rot['i'] & 1], ct_k, tp[1], 0.01)
+
+        def backward_rot():
+            rot['i'] += 1
+            with torch.cuda.device(dev):
+                _ffi.check(_ffi.lib().rd_multibox_loss_backward(
+                    _ffi.ptr(tp[2]), _ffi.ptr(lt_k), _ffi.ptr(conf_rot[rot['i'] & 1]), _ffi.ptr(ct_k), _ffi.ptr(lse_k),
+                    _ffi.ptr(pos_k), _ffi.ptr(neg_k), _ffi.ptr(one_k), _ffi.ptr(one_k), _ffi.ptr(n_k), BATCH * P, C,
+                    _ffi.ptr(gloc_k), _ffi.ptr(gconf_rot[rot['i'] & 1]), _ffi.stream_ptr()), 'rd_multibox_loss_backward')
+        for name, byts, fn, flush in (
                 ('refine_match', BATCH * (40 * P + 20 * 50),
-                 lambda: bu.match_batch(0.5, truths_k, labels_k, cnt_k, priors, [0.1, 0.2], tp[0], bu.LABEL_ODM)),
-                ('conf_loss', BATCH * P * (4 * C + 17), lambda: bu.conf_loss(tp[3], ct_k, tp[1], 0.01)),
-                ('hnm_select', BATCH * 6 * P, lambda: bu.hnm_select(ce_k, pos_k, 3)),
-                ('loss_reduce', BATCH * P * 6, lambda: bu.multibox_loss_reduce(tp[2], lt_k, ce_k, pos_k, neg_k, npos_k)),
-                ('loss_backward', BATCH * P * (4 * C + 18),
-                 lambda: bu.multibox_loss_backward(tp[2], lt_k, tp[3], ct_k, lse_k, pos_k, neg_k, one_k, one_k, n_k))):
-            ms_k = flushed_ms(fn, n=10)
+                 lambda: bu.match_batch(0.5, truths_k, labels_k, cnt_k, priors, [0.1, 0.2], tp[0], bu.LABEL_ODM), True),
+                ('conf_loss', BATCH * P * (4 * C + 17), conf_loss_rot, True),
+                ('hnm_select', BATCH * 6 * P, lambda: bu.hnm_select(ce_k, pos_k, 3), True),
+                ('loss_reduce', BATCH * P * 6, lambda: bu.multibox_loss_reduce(tp[2], lt_k, ce_k, pos_k, neg_k, npos_k), True),
+                ('loss_backward', BATCH * P * (4 * C + 18), backward_rot, True)):
+            ms_k = flushed_ms(fn, n=10, flush=flush)
             kernels[name] = {'ms': round(ms_k, 5), 'frac': round(byts / (ms_k * 1e-3) / 1e9 / peak, 4)}
+        del conf_rot, gconf_rot, gloc_k
         # device time of the whole step (events around it, the host runs ahead)
         step_sf = make_step(True)
         ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -699,14 +750,14 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K,
                 'warmup': W, 'ms_per_step': ms_per_step, 'higher_is_better': True,
                 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': config, 'roofline': roofline, 'regions': regions, 'stage_only': stage_only,
+                'with_exchange': with_exchange, 'config': config, 'roofline': roofline, 'regions': regions,
                 'gpu_launches': int(launches), 'clocks': clocks.summary(),
                 'cpu_baseline': cpu_baseline, 'e2e': e2e, 'gather': gather, 'secondary': secondary,
                 'train_step': train_step, 'a3_forward': a3, 'logits_in': logits_in, 'other_configs': other_configs,
                 'run_info': {'l2': 'inputs larger than L2: %d input sets (1.5 GB) rotated, no flush in the timed region' % NBUF,
                              'batches_in_flight': S, 'launch': 'one CUDA-graph replay per step',
-                             'exchange_in_step': exchanges is not None, 'arm_pass_fraction': arm_pass,
-                             'kept_rows_per_step': kept_rows, 'batch_this_rank': B_loc}}
+                             'arm_pass_fraction': arm_pass,
+                             'kept_rows_per_step': kept_rows, 'batch_this_rank': B_loc, 'numa_bound_cores': numa}}
         print(json.dumps(line))
         sys.stderr.write('BENCH_DETAIL ' + json.dumps(detail) + '\n')
     if dist is not None:

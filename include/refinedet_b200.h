@@ -246,6 +246,22 @@ RD_API int rd_pack_scatter_ex(const int* counts, const float* dets, int B, int C
                            int* scratch_offsets, void* const* peer_slots_host, int world, int rank,
                            int slot_B, int capacity_rows, void* multicast_slot, int copy_ctas, void* stream);
 
+/* The exchange with its synchronisation folded in: two launches and ONE cross-GPU rendezvous per round, no
+ * barrier kernels, replayable from a CUDA graph (the round counter lives on the device).
+ *   Every rank owns one symmetric buffer  [control block, rd_exchange_ctrl_bytes() | world slots, parity 0 |
+ *   world slots, parity 1], zero before the first round; peer_bases_host[w] = base of rank w's buffer as mapped
+ *   into THIS process (entry `rank` = the local one); multicast_base = base of the multicast mapping, or NULL.
+ *   Round e writes this rank's slot of parity e & 1 on every rank (layout of a slot: rd_pack_scatter), publishes e in
+ *   flags[rank] of every rank's control block and returns -- on the stream -- once every rank's flag has arrived
+ *   here: the rows of all ranks of round e are then readable in the local buffer (header word 4 of a slot = e).
+ *   Consumers read on `stream` (or after it) BEFORE the next round is enqueued; the second parity is what makes a
+ *   separate "buffer free" rendezvous unnecessary.  timeout_ms (<= 0: 10 s): a wait that long sets word `error`
+ *   of the control block (offset 264) instead of hanging the GPU.  All ranks must call in lockstep. */
+RD_API size_t rd_exchange_ctrl_bytes(void);
+RD_API int rd_exchange_round(const int* counts, const float* dets, int B, int C, int max_out,
+                      void* const* peer_bases_host, void* multicast_base, int world, int rank, int slot_B,
+                      int capacity_rows, int copy_ctas, int timeout_ms, void* stream);
+
 /* ---- stand-alone NMS ------------------------------------------------------- */
 RD_API size_t rd_nms_workspace_bytes(int n);
 /* box_utils.nms (box_utils.py:222-286) / utils.nms_wrapper.nms on device tensors:
@@ -289,7 +305,8 @@ RD_API int rd_refine_match(const float* truths, const float* labels, const int* 
 
 /* target ingestion (data/__init__.py:9-27 detection_collate + the per-image slicing of
  * refinedet_multibox_loss.py:76-77): flat[total,5] = the step's ragged target tensors concatenated
- * (x1,y1,x2,y2,label), offsets[B+1] int32 (exclusive prefix sum of the per-image counts) ->
+ * (x1,y1,x2,y2,label), offsets[B+1] int32 (exclusive prefix sum of the per-image counts; device memory, or pinned
+ * host memory read over PCIe -- 33 ints, no copy call) ->
  * truths[B,Gmax,4], labels[B,Gmax] (zero padded), gt_count[B]. */
 RD_API int rd_pad_targets(const float* flat, const int* offsets, int B, int Gmax,
                    float* truths, float* labels, int* gt_count, void* stream);

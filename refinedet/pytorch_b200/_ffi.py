@@ -73,6 +73,8 @@ _SIGNATURES = {
     'rd_exchange_slot_bytes': (c_size_t, [c_int, c_int, c_int]),
     'rd_pack_scatter': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     'rd_pack_scatter_ex': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, _P]),
+    'rd_exchange_ctrl_bytes': (c_size_t, []),
+    'rd_exchange_round': (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
     'rd_nms_workspace_bytes': (c_size_t, [c_int]),
     'rd_nms': (c_int, [_P, _P, c_int, c_float, c_int, c_int, _P, c_size_t, _P, _P, _P]),
     'rd_nms_host': (c_int, [_P, _P, _P, c_int, c_int, c_float, c_int]),

@@ -4,6 +4,7 @@
 // with -fmad=false so no mul/add pair is contracted.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include "../../../include/refinedet_b200.h"
@@ -32,6 +33,15 @@ inline cudaError_t ensure_dynamic_smem(Kernel kernel, size_t bytes, size_t (&hig
     if (e == cudaSuccess) hw = bytes;
     return e;
 }
+
+// ---- NVTX range around the launches of one C-ABI entry (header-only NVTX 3: a no-op unless a tool is attached;
+// Nsight Systems / Compute then show "rd_detect_fused", "rd_multibox_criterion", ... around their kernels)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // ---- launchers shared between translation units (the fused criterion in rd_loss.cu chains kernels of rd_match.cu)
 // `pdl`: launch with programmatic stream serialisation (every kernel of the chain waits with grid_dependency_wait)

@@ -1229,6 +1229,242 @@ slot_copy_kernel(const unsigned char* __restrict__ local_slot, PeerSlots peers, 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// The exchange with its synchronisation folded in (rd_exchange_*): no barrier kernels, ONE cross-GPU rendezvous per
+// round.  Every rank's symmetric buffer is [ExchangeCtrl | slots of parity 0 | slots of parity 1]; round e (the
+// epoch, kept on the device so that the launch pair can be replayed from a CUDA graph) uses the slots of parity
+// e & 1.  pack: rows -> this rank's own slot (local HBM).  copy: the slot's used prefix -> the same slot of every
+// peer (P2P or multicast stores); the CTA that finishes last publishes the epoch in flags[rank] of every rank and
+// waits until every flag of its OWN control block has reached the epoch: when the kernel completes, the rows of
+// every rank have landed here.  The second parity makes a "buffer free" rendezvous unnecessary: a rank can only
+// start writing round e + 2 after round e + 1 has completed everywhere, i.e. after every peer has, in ITS stream,
+// passed the reads of round e that it enqueued before its round e + 1.
+// ---------------------------------------------------------------------------------------
+struct ExchangeCtrl {
+    unsigned int flags[kMaxPeers];     // flags[q] = latest epoch published by rank q (written by rank q)
+    unsigned int pad0[64 - kMaxPeers];
+    unsigned int epoch;                // rounds completed by this rank (local)
+    unsigned int done;                 // CTAs of the running copy kernel that have finished their stores (local)
+    unsigned int error;                // 1 = a wait timed out
+    unsigned int pad1[256 - 64 - 3];
+};
+static_assert(sizeof(ExchangeCtrl) == 1024, "control block is 1 KB");
+struct PeerBases { unsigned char* p[kMaxPeers]; };
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(kPackThreads)
+exchange_pack_kernel(const int* __restrict__ counts, const float* __restrict__ dets, int max_out, int nbc, int B, int C,
+                     unsigned char* local_base, int world, int rank, size_t slot_bytes, int capacity, size_t rows_off) {
+    __shared__ int s_red[kPackPer];
+    __shared__ int s_cnt[kPackPer];
+    const ExchangeCtrl* ctrl = reinterpret_cast<const ExchangeCtrl*>(local_base);
+    grid_dependency_wait();                                  // the producer of counts / dets
+    const unsigned int e = *reinterpret_cast<const volatile unsigned int*>(&ctrl->epoch) + 1u;
+    unsigned char* slot = local_base + sizeof(ExchangeCtrl) + ((size_t)(e & 1u) * world + rank) * slot_bytes;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bc0 = blockIdx.x * kPackPer;
+    int acc = 0;
+    for (int i = threadIdx.x; i < bc0; i += kPackThreads) acc += __ldg(counts + i);
+    acc = __reduce_add_sync(kFullMask, acc);
+    const int bc = bc0 + warp;
+    const int n = bc < nbc ? __ldg(counts + bc) : 0;
+    if (lane == 0) { s_red[warp] = acc; s_cnt[warp] = n; }
+    __syncthreads();
+    int off = 0;
+#pragma unroll
+    for (int w = 0; w < kPackPer; ++w) off += s_red[w] + (w < warp ? s_cnt[w] : 0);
+    if (bc < nbc) {
+        const float* src = dets + (size_t)bc * max_out * 5;
+        int len = n * 5;
+        if (off + n > capacity) len = max(0, capacity - off) * 5;
+        float* dst = reinterpret_cast<float*>(slot + rows_off) + (size_t)off * 5;
+        for (int t = lane; t < len; t += 32) dst[t] = src[t];
+        if (lane == 0) reinterpret_cast<int*>(slot + 256)[bc] = n;
+    }
+    if (bc == nbc - 1 && lane == 0) {
+        const int total = off + n;
+        int* hdr = reinterpret_cast<int*>(slot);
+        hdr[0] = min(total, capacity); hdr[1] = B; hdr[2] = C; hdr[3] = total; hdr[4] = (int)e;
+    }
+}
+
+template <bool kMulticast>
+__global__ void __launch_bounds__(kCopyThreads)
+exchange_copy_kernel(PeerBases bases, unsigned char* mc_base, int world, int rank, size_t slot_bytes, size_t rows_off,
+                     unsigned long long timeout_ns) {
+    __shared__ int s_last;
+    ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(bases.p[rank]);
+    grid_dependency_wait();                                  // exchange_pack_kernel
+    const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&ctrl->epoch) + 1u;
+    const size_t slot_off = sizeof(ExchangeCtrl) + ((size_t)(e & 1u) * world + rank) * slot_bytes;
+    const unsigned char* local_slot = bases.p[rank] + slot_off;
+    const int stored = reinterpret_cast<const int*>(local_slot)[0];
+    const size_t words = rows_off / 16 + ((size_t)stored * 20 + 15) / 16;      // header + counts + rows, 16-byte words
+    const uint4* src = reinterpret_cast<const uint4*>(local_slot);
+    if (world > 1) {
+        uint4* dst = kMulticast ? reinterpret_cast<uint4*>(mc_base + slot_off)
+                                : reinterpret_cast<uint4*>(bases.p[(rank + 1 + blockIdx.y) % world] + slot_off);
+        const size_t stride = (size_t)gridDim.x * kCopyThreads;
+        for (size_t w0 = (size_t)blockIdx.x * kCopyThreads + threadIdx.x; w0 < words; w0 += stride * kCopyUnroll) {
+            uint4 v[kCopyUnroll];
+#pragma unroll
+            for (int u = 0; u < kCopyUnroll; ++u) {
+                const size_t w = w0 + u * stride;
+                if (w < words) v[u] = __ldg(src + w);
+            }
+#pragma unroll
+            for (int u = 0; u < kCopyUnroll; ++u) {
+                const size_t w = w0 + u * stride;
+                if (w < words) {
+                    if (kMulticast) st_multimem_v4(dst + w, v[u]);
+                    else dst[w] = v[u];
+                }
+            }
+        }
+    }
+    // ---- completion: the last CTA publishes the epoch everywhere, then waits for everybody's ------------------
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                              // this CTA's stores, system-wide, before its ticket
+        const unsigned int total = gridDim.x * gridDim.y;
+        s_last = atomicAdd(&ctrl->done, 1u) == total - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) {
+        ctrl->done = 0u;
+        ctrl->epoch = e;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < world) {                          // thread q: publish on rank q, then wait for rank q here
+        ExchangeCtrl* peer = reinterpret_cast<ExchangeCtrl*>(bases.p[threadIdx.x]);
+        *reinterpret_cast<volatile unsigned int*>(&peer->flags[rank]) = e;
+        const volatile unsigned int* mine = &ctrl->flags[threadIdx.x];
+        const unsigned long long t0 = global_timer_ns();
+        while ((int)(*mine - e) < 0) {
+            if (global_timer_ns() - t0 > timeout_ns) { ctrl->error = 1u; break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();                              // the peers' rows are visible to whatever follows in the stream
+    }
+}
+
+
+// ---- the copy phase on the TMA engines (unicast).  Stores to a peer's memory issued by the SMs' load/store units
+// hold up the whole SM's memory pipeline while NVLink drains them (measured at 2 GPUs: with the LSU copy on 24 - 48 SMs
+// the exchange ADDED its 12 - 16 us to the 26 us stage of the other lanes instead of hiding behind them), so the rows
+// never pass through registers here: one thread per CTA moves 16 KB chunks local slot -> shared memory
+// (cp.async.bulk, mbarrier) -> the peer's slot (cp.async.bulk.global.shared::cta), a ring of kXStages chunks in
+// flight.  grid = (CTAs per peer, world - 1), 32 threads; the completion protocol is that of exchange_copy_kernel.
+constexpr int kXChunk = 16 * 1024;
+constexpr int kXStages = 4;
+
+__device__ __forceinline__ void x_mbar_init(unsigned long long* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void x_load(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void x_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "XWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra XDONE_%=;\n"
+        "bra XWAIT_%=;\n"
+        "XDONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void x_store(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(32)
+exchange_copy_tma_kernel(PeerBases bases, int world, int rank, size_t slot_bytes, size_t rows_off, unsigned long long timeout_ns) {
+    extern __shared__ __align__(128) unsigned char x_smem[];          // kXStages chunks
+    __shared__ __align__(8) unsigned long long s_bar[kXStages];
+    __shared__ int s_last;
+    ExchangeCtrl* ctrl = reinterpret_cast<ExchangeCtrl*>(bases.p[rank]);
+    grid_dependency_wait();                                  // exchange_pack_kernel
+    const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&ctrl->epoch) + 1u;
+    const size_t slot_off = sizeof(ExchangeCtrl) + ((size_t)(e & 1u) * world + rank) * slot_bytes;
+    const unsigned char* src = bases.p[rank] + slot_off;
+    if (threadIdx.x == 0 && world > 1) {
+        const int stored = reinterpret_cast<const int*>(src)[0];
+        const size_t bytes = rows_off + (((size_t)stored * 20 + 15) & ~(size_t)15);    // header + counts + rows
+        unsigned char* dst = bases.p[(rank + 1 + blockIdx.y) % world] + slot_off;
+        const size_t nchunks = (bytes + kXChunk - 1) / kXChunk;
+#pragma unroll
+        for (int st = 0; st < kXStages; ++st) x_mbar_init(&s_bar[st]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        auto chunk_bytes = [&](size_t c) { return (unsigned)min((size_t)kXChunk, bytes - c * kXChunk); };
+        // prologue: the first kXStages - 1 chunks of this CTA are requested
+        size_t c_load = blockIdx.x;
+        int n_load = 0;
+        for (; n_load < kXStages - 1 && c_load < nchunks; ++n_load, c_load += gridDim.x)
+            x_load(x_smem + (size_t)(n_load % kXStages) * kXChunk, src + c_load * kXChunk, chunk_bytes(c_load), &s_bar[n_load % kXStages]);
+        int it = 0;
+        for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+            const int st = it % kXStages;
+            x_wait(&s_bar[st], (unsigned)((it / kXStages) & 1));
+            x_store(dst + c * kXChunk, x_smem + (size_t)st * kXChunk, chunk_bytes(c));
+            // refill: load number n_load goes to the stage chunk it - 1 was stored from; that store (every bulk group
+            // but the one just committed) must have finished reading shared memory
+            if (c_load < nchunks) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                x_load(x_smem + (size_t)(n_load % kXStages) * kXChunk, src + c_load * kXChunk, chunk_bytes(c_load),
+                       &s_bar[n_load % kXStages]);
+                ++n_load;
+                c_load += gridDim.x;
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every store of this CTA has been performed
+    }
+    // ---- completion: the last CTA publishes the epoch everywhere, then waits for everybody's ------------------
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int total = gridDim.x * gridDim.y;
+        s_last = atomicAdd(&ctrl->done, 1u) == total - 1u;
+    }
+    __syncwarp();
+    if (!s_last) return;
+    if (threadIdx.x == 0) {
+        ctrl->done = 0u;
+        ctrl->epoch = e;
+        __threadfence_system();
+    }
+    __syncwarp();
+    if ((int)threadIdx.x < world) {
+        ExchangeCtrl* peer = reinterpret_cast<ExchangeCtrl*>(bases.p[threadIdx.x]);
+        *reinterpret_cast<volatile unsigned int*>(&peer->flags[rank]) = e;
+        const volatile unsigned int* mine = &ctrl->flags[threadIdx.x];
+        const unsigned long long t0 = global_timer_ns();
+        while ((int)(*mine - e) < 0) {
+            if (global_timer_ns() - t0 > timeout_ns) { ctrl->error = 1u; break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+}
+
 }  // namespace rd
 
 using namespace rd;
@@ -1244,6 +1480,7 @@ unsigned long long rd_launch_count(void) { return g_launches.load(std::memory_or
 int rd_detect_forward(const float* arm_loc, const float* arm_conf, const float* odm_loc, float* odm_conf,
                       const float* priors, int B, int P, int C, float objectness_thre, float v0, float v1,
                       float* boxes_out, float* scores_out, void* stream) {
+    NvtxRange nvtx_range("rd_detect_forward");
     if (!arm_loc || !arm_conf || !odm_loc || !odm_conf || !priors || !boxes_out || !scores_out) return RD_ERR_BAD_ARG;
     if (B <= 0 || P <= 0 || C <= 0) return RD_ERR_BAD_ARG;
     if (C > kMaxClasses) return RD_ERR_UNSUPPORTED;
@@ -1291,6 +1528,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
                              float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
                              int row_layout, float v0, float v1, void* workspace, size_t workspace_bytes,
                              int* out_counts, float* out_dets, int* out_anchor, void* stream, cudaEvent_t* ev) {
+    NvtxRange nvtx_range("rd_detect_fused");
     if (!arm_loc || !arm_conf || !odm_loc || !odm_conf || !priors || !workspace || !out_counts || !out_dets)
         return RD_ERR_BAD_ARG;
     if (B <= 0 || P <= 0 || C <= 0 || top_k <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
@@ -1519,6 +1757,7 @@ int rd_plan_capture_end(void* stream, rd_detect_plan** plan_out) {
 }
 
 int rd_detect_plan_launch(rd_detect_plan* plan, void* stream) {
+    NvtxRange nvtx_range("rd_detect_plan_launch");
     if (!plan || !plan->exec) return RD_ERR_BAD_ARG;
     cudaError_t e = cudaGraphLaunch(plan->exec, (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
@@ -1536,6 +1775,7 @@ int rd_detect_plan_destroy(rd_detect_plan* plan) {
 
 int rd_pack_detections(const int* counts, const float* dets, int B, int C, int max_out, int* out_offsets,
                        float* packed, int packed_capacity, void* stream) {
+    NvtxRange nvtx_range("rd_pack_detections");
     if (!counts || !dets || !out_offsets || !packed || B <= 0 || C <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     pack_offsets_kernel<<<1, 1024, 0, st>>>(counts, B * C, out_offsets);
@@ -1549,6 +1789,7 @@ int rd_pack_detections(const int* counts, const float* dets, int B, int C, int m
 
 int rd_coco_records(const int* counts, const float* dets, int B, int C, int max_out, const int* src_offsets,
                     const int* class_to_cat, int* out_ids, double* out_vals, int capacity, int* out_total, void* stream) {
+    NvtxRange nvtx_range("rd_coco_records");
     if (!counts || !dets || !out_ids || !out_vals || !out_total || B <= 0 || C <= 0 || capacity < 0) return RD_ERR_BAD_ARG;
     if (max_out <= 0 && !src_offsets) return RD_ERR_BAD_ARG;
     if ((uintptr_t)out_vals & 7) return RD_ERR_ALIGNMENT;
@@ -1567,6 +1808,7 @@ size_t rd_exchange_slot_bytes(int B, int C, int capacity_rows) {
 int rd_pack_scatter_ex(const int* counts, const float* dets, int B, int C, int max_out, int* scratch_offsets,
                        void* const* peer_slots_host, int world, int rank, int slot_B, int capacity_rows,
                        void* multicast_slot, int copy_ctas, void* stream) {
+    NvtxRange nvtx_range("rd_pack_scatter");
     if (slot_B < B) return RD_ERR_BAD_ARG;
     if (!counts || !dets || !peer_slots_host || B <= 0 || C <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
     if (world <= 0 || world > kMaxPeers || rank < 0 || rank >= world || capacity_rows < 0) return RD_ERR_BAD_ARG;
@@ -1600,6 +1842,53 @@ int rd_pack_scatter(const int* counts, const float* dets, int B, int C, int max_
                               capacity_rows, nullptr, 0, stream);
 }
 
+size_t rd_exchange_ctrl_bytes(void) { return sizeof(ExchangeCtrl); }
+
+int rd_exchange_round(const int* counts, const float* dets, int B, int C, int max_out, void* const* peer_bases_host,
+                      void* multicast_base, int world, int rank, int slot_B, int capacity_rows, int copy_ctas,
+                      int timeout_ms, void* stream) {
+    NvtxRange nvtx_range("rd_exchange_round");
+    if (slot_B < B) return RD_ERR_BAD_ARG;
+    if (!counts || !dets || !peer_bases_host || B <= 0 || C <= 0 || max_out <= 0) return RD_ERR_BAD_ARG;
+    if (world <= 0 || world > kMaxPeers || rank < 0 || rank >= world || capacity_rows < 0) return RD_ERR_BAD_ARG;
+    PeerBases pb;
+    for (int k = 0; k < kMaxPeers; ++k) pb.p[k] = k < world ? static_cast<unsigned char*>(peer_bases_host[k]) : nullptr;
+    for (int k = 0; k < world; ++k) if (!pb.p[k] || ((uintptr_t)pb.p[k] & 255)) return RD_ERR_ALIGNMENT;
+    if (multicast_base && ((uintptr_t)multicast_base & 255)) return RD_ERR_ALIGNMENT;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t rows_off = 256 + align_up((size_t)slot_B * C * 4, 256);
+    const size_t slot_bytes = rd_exchange_slot_bytes(slot_B, C, capacity_rows);
+    cudaError_t e = launch_pdl(exchange_pack_kernel, dim3((B * C + kPackPer - 1) / kPackPer), dim3(kPackThreads), 0, st, counts, dets,
+                               max_out, B * C, B, C, pb.p[rank], world, rank, slot_bytes, capacity_rows, rows_off);
+    if (e != cudaSuccess) return (int)e;
+    note_launch();
+    RD_CHECK_LAUNCH();
+    const unsigned long long timeout_ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 10000) * 1000000ull;
+    const bool mc = multicast_base != nullptr && world > 1;
+    // unicast: the TMA engines move the rows (copy_ctas > 0: that many single-warp CTAs per peer, default 16);
+    // copy_ctas < 0 selects the load/store-unit kernel with -copy_ctas CTAs per peer (kept for comparison);
+    // multicast: multimem.st is an LSU instruction, |copy_ctas| CTAs (default 96)
+    if (mc) {
+        const int n = copy_ctas == 0 ? 96 : (copy_ctas < 0 ? -copy_ctas : copy_ctas);
+        e = launch_pdl(exchange_copy_kernel<true>, dim3(n, 1), dim3(kCopyThreads), 0, st, pb, (unsigned char*)multicast_base, world,
+                       rank, slot_bytes, rows_off, timeout_ns);
+    } else if (copy_ctas < 0) {
+        e = launch_pdl(exchange_copy_kernel<false>, dim3(-copy_ctas, world == 1 ? 1 : world - 1), dim3(kCopyThreads), 0, st, pb,
+                       (unsigned char*)nullptr, world, rank, slot_bytes, rows_off, timeout_ns);
+    } else {
+        const int n = copy_ctas == 0 ? 16 : copy_ctas;
+        static size_t s_x_smem[kMaxDevices];
+        e = ensure_dynamic_smem(exchange_copy_tma_kernel, (size_t)kXStages * kXChunk, s_x_smem);
+        if (e != cudaSuccess) return (int)e;
+        e = launch_pdl(exchange_copy_tma_kernel, dim3(n, world == 1 ? 1 : world - 1), dim3(32), (size_t)kXStages * kXChunk, st, pb,
+                       world, rank, slot_bytes, rows_off, timeout_ns);
+    }
+    if (e != cudaSuccess) return (int)e;
+    note_launch();
+    RD_CHECK_LAUNCH();
+    return 0;
+}
+
 // ---- stand-alone NMS --------------------------------------------------------------------
 size_t rd_nms_workspace_bytes(int n) {
     if (n <= 0) return 256;
@@ -1623,6 +1912,7 @@ static int launch_single(const unsigned long long* keys, int n, const float4* bo
 
 int rd_nms(const float* boxes, const float* scores, int n, float thresh, int top_k, int nms_flags,
            void* workspace, size_t workspace_bytes, long long* keep_out, int* count_out, void* stream) {
+    NvtxRange nvtx_range("rd_nms");
     if (!count_out || n < 0 || top_k <= 0) return RD_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return (int)cudaMemsetAsync(count_out, 0, sizeof(int), st);
@@ -1638,6 +1928,7 @@ int rd_nms(const float* boxes, const float* scores, int n, float thresh, int top
 
 int rd_nms_host_ex(int* keep_out_host, int* num_out_host, const float* boxes_host, int boxes_num, int boxes_dim,
                    float nms_overlap_thresh, int device_id, int nms_flags) {
+    NvtxRange nvtx_range("rd_nms_host");
     if (!keep_out_host || !num_out_host || boxes_num < 0 || boxes_dim < 5) return RD_ERR_BAD_ARG;
     if (boxes_num == 0) { *num_out_host = 0; return 0; }
     if (!boxes_host) return RD_ERR_BAD_ARG;

@@ -151,12 +151,26 @@ conf_loss_kernel(const float* __restrict__ conf, const long long* __restrict__ c
     }
 }
 
-// ---- TMA variant (odd C, 16-byte aligned conf): persistent CTAs, a ring of kTmaStages tiles of kLossRows rows in
+// ---- TMA variant (odd C, 16-byte aligned conf): persistent CTAs, a ring of kTmaStages tiles of kTmaRows rows in
 // shared memory.  A tile is one contiguous span of global memory (rows are consecutive, the odd row stride is already
 // conflict-free), so ONE bulk asynchronous copy (cp.async.bulk, the 1-D TMA: SASS UBLKCP) per tile fetches it and
 // signals the stage's mbarrier with the byte count; thread 0 issues the copy of tile i + kTmaStages - 1 before the CTA
 // computes tile i.  No per-thread copy instructions, no register staging, loads of the next tile always in flight.
-constexpr int kTmaStages = 2;
+// Tile and ring are sized by two needs that compete for the 227 KB of shared memory: bytes in flight per SM (the
+// tiles being fetched: Little's law against the ~3 us a tile takes to arrive under load) and warps per SM (the exp
+// work).  Measured at C = 81, 174 MB: 128 rows x 2 stages (two CTAs per SM, 16 warps, 83 KB in flight) 42.0 us;
+// 64 rows x 4 stages (8 warps, 124 KB) 47.1 us; 112 and 96 rows x 3 stages (14 / 12 warps, 145 / 124 KB) 44.0 us: neither more
+// bytes in flight nor more warps move it -- the kernel sits at ~4.2 TB/s of pure reads like its cp.async predecessor.
+#ifndef RD_TMA_ROWS
+#define RD_TMA_ROWS 128
+#endif
+#ifndef RD_TMA_STAGES
+#define RD_TMA_STAGES 2
+#endif
+constexpr int kTmaRows = RD_TMA_ROWS;                      // even, a multiple of 4 (tile bytes = 4 rows C: whole 16-byte words)
+constexpr int kTmaStages = RD_TMA_STAGES;
+constexpr int kTmaSplit = 2;                               // threads per row: lane pair (2 i, 2 i + 1) shares row i
+constexpr int kTmaThreads = kTmaRows * kTmaSplit;
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
@@ -185,15 +199,94 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
-__global__ void __launch_bounds__(kLossRows)
+// one row shared by kTmaSplit = 2 adjacent lanes: lane half h takes the classes h, h + 2, ... (with the odd row stride
+// the 32 lanes of a warp -- 16 rows x 2 halves -- hit 32 different banks), max and sum are combined with one shuffle
+// each.  Twice the warps for the same tile: the exp work of a tile takes half as long, and 16 warps per SM instead
+// of 8 keep the issue slots busy while the next tile streams in.
+__device__ __forceinline__ void conf_row_pair(const float* __restrict__ x, int C, int h, long long t, float2 arm, bool has_arm,
+                                              float theta, float* ce_out, float* lse_out, unsigned char* pos_out) {
+    const int n = (C - h + 1) >> 1;                        // classes of this half
+    const float* xh = x + h;
+    float m0 = xh[0], m1 = m0, m2 = m0, m3 = m0;
+    int k = 0;
+    for (; k + 4 <= n; k += 4) {
+        m0 = fmaxf(m0, xh[2 * k]); m1 = fmaxf(m1, xh[2 * k + 2]); m2 = fmaxf(m2, xh[2 * k + 4]); m3 = fmaxf(m3, xh[2 * k + 6]);
+    }
+    for (; k < n; ++k) m0 = fmaxf(m0, xh[2 * k]);
+    float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 1));
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (k = 0; k + 4 <= n; k += 4) {
+        s0 += exp2f((xh[2 * k] - m) * kLog2e); s1 += exp2f((xh[2 * k + 2] - m) * kLog2e);
+        s2 += exp2f((xh[2 * k + 4] - m) * kLog2e); s3 += exp2f((xh[2 * k + 6] - m) * kLog2e);
+    }
+    for (; k < n; ++k) s0 += exp2f((xh[2 * k] - m) * kLog2e);
+    float sum = (s0 + s1) + (s2 + s3);
+    sum += __shfl_xor_sync(kFullMask, sum, 1);
+    if (h != 0) return;
+    const float lse = logf(sum) + m;
+    *ce_out = (t >= 0 && t < C) ? lse - x[(int)t] : __int_as_float(0x7fc00000);     // label outside [0, C): NaN (see conf_row)
+    *lse_out = lse;
+    bool pos = t > 0;
+    if (pos && has_arm && arm_filtered(arm, theta)) pos = false;
+    *pos_out = pos ? 1 : 0;
+}
+
+// The same with the class count known at compile time: the half row (<= 41 values at C = 81) is read from shared
+// memory ONCE into registers, both passes run on registers, and (x - m) log2 e is one fused multiply-add against the
+// pre-scaled maximum -- 5 instructions per element instead of 8 (the kernel is bound by instruction issue, not by
+// the tile stream: 17.3 M warp-instructions for 174 MB at C = 81 before this).
+template <int kC>
+__device__ __forceinline__ void conf_row_pair_regs(const float* __restrict__ x, int h, long long t, float2 arm, bool has_arm,
+                                                   float theta, float* ce_out, float* lse_out, unsigned char* pos_out) {
+    constexpr int kN = (kC + 1) / 2;                       // classes of half 0; half 1 has kC / 2
+    const int n = (kC - h + 1) >> 1;
+    const float* xh = x + h;
+    float v[kN];
+#pragma unroll
+    for (int k = 0; k < kN; ++k) v[k] = (k < kC / 2 || k < n) ? xh[2 * k] : -INFINITY;
+    float m0 = v[0], m1 = v[0], m2 = v[0], m3 = v[0];
+#pragma unroll
+    for (int k = 0; k < kN; ++k) {
+        if ((k & 3) == 0) m0 = fmaxf(m0, v[k]);
+        else if ((k & 3) == 1) m1 = fmaxf(m1, v[k]);
+        else if ((k & 3) == 2) m2 = fmaxf(m2, v[k]);
+        else m3 = fmaxf(m3, v[k]);
+    }
+    float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 1));
+    const float nm2 = -m * kLog2e;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kN; ++k) {
+        const float e = exp2f(__fmaf_rn(v[k], kLog2e, nm2));             // a padded -inf contributes exp2(-inf) = 0
+        if ((k & 3) == 0) s0 += e;
+        else if ((k & 3) == 1) s1 += e;
+        else if ((k & 3) == 2) s2 += e;
+        else s3 += e;
+    }
+    float sum = (s0 + s1) + (s2 + s3);
+    sum += __shfl_xor_sync(kFullMask, sum, 1);
+    if (h != 0) return;
+    const float lse = logf(sum) + m;
+    *ce_out = (t >= 0 && t < kC) ? lse - x[(int)t] : __int_as_float(0x7fc00000);    // label outside [0, C): NaN (see conf_row)
+    *lse_out = lse;
+    bool pos = t > 0;
+    if (pos && has_arm && arm_filtered(arm, theta)) pos = false;
+    *pos_out = pos ? 1 : 0;
+}
+
+template <int kC>
+__global__ void __launch_bounds__(kTmaThreads)
 conf_loss_tma_kernel(const float* __restrict__ conf, const long long* __restrict__ conf_t,
                      const float2* __restrict__ arm_conf, float theta, long long rows, int C,
                      float* __restrict__ ce_out, float* __restrict__ lse_out, unsigned char* __restrict__ pos_out) {
-    extern __shared__ __align__(128) float s_x[];            // [kTmaStages][kLossRows * C], each stage 16-byte aligned
+    extern __shared__ __align__(128) float s_x[];            // [kTmaStages][kTmaRows * C], each stage 16-byte aligned
     __shared__ __align__(8) unsigned long long s_bar[kTmaStages];
     const int tid = threadIdx.x;
-    const int tile_floats = kLossRows * C;                   // multiple of 4 (kLossRows = 128)
-    const long long ntiles = (rows + kLossRows - 1) / kLossRows;
+    const int rit = tid >> 1, h = tid & 1;                   // row in the tile, half of the row
+    const int tile_floats = kTmaRows * C;                    // multiple of 4
+    const long long ntiles = (rows + kTmaRows - 1) / kTmaRows;
     if (tid == 0) {
 #pragma unroll
         for (int st = 0; st < kTmaStages; ++st) mbar_init(&s_bar[st], 1);
@@ -201,8 +294,8 @@ conf_loss_tma_kernel(const float* __restrict__ conf, const long long* __restrict
     }
     __syncthreads();
     auto issue = [&](long long tile, int st) {               // thread 0 only
-        const long long r0 = tile * kLossRows;
-        const int nrows = (int)min((long long)kLossRows, rows - r0);
+        const long long r0 = tile * kTmaRows;
+        const int nrows = (int)min((long long)kTmaRows, rows - r0);
         const unsigned bytes = (unsigned)(((size_t)nrows * C * 4) & ~(size_t)15);      // whole 16-byte words; tail below
         mbar_expect_tx(&s_bar[st], bytes);                   // (zero bytes: the arrival alone completes the phase)
         if (bytes) tma_load_1d(s_x + (size_t)st * tile_floats, conf + r0 * C, bytes, &s_bar[st]);
@@ -216,32 +309,46 @@ conf_loss_tma_kernel(const float* __restrict__ conf, const long long* __restrict
         }
     }
     grid_dependency_wait();                                   // conf_t comes from the kernel before this one
+    // the row's scalar inputs are fetched one tile AHEAD, like the tile itself
+    auto row_inputs = [&](long long tile, long long& t, float2& arm) {
+        t = 0; arm = make_float2(0.f, 0.f);
+        const long long r = tile * kTmaRows + rit;
+        if (tile < ntiles && r < rows && h == 0) {
+            t = conf_t[r];
+            if (arm_conf) arm = __ldg(arm_conf + r);
+        }
+    };
+    long long t_cur, t_nxt;
+    float2 arm_cur, arm_nxt;
+    row_inputs(blockIdx.x, t_cur, arm_cur);
     int it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int st = it % kTmaStages;
         const unsigned parity = (unsigned)((it / kTmaStages) & 1);
-        const long long r0 = tile * kLossRows;
-        const int nrows = (int)min((long long)kLossRows, rows - r0);
+        const long long r0 = tile * kTmaRows;
+        const int nrows = (int)min((long long)kTmaRows, rows - r0);
         // keep the ring full: the stage refilled here was released by the barrier at the end of the previous tile
         if (tid == 0) {
             const long long nxt = tile + (long long)(kTmaStages - 1) * gridDim.x;
             if (nxt < ntiles) issue(nxt, (it + kTmaStages - 1) % kTmaStages);
         }
-        const long long r = r0 + tid;
-        long long t = 0;
-        float2 arm = make_float2(0.f, 0.f);
-        if (tid < nrows) {
-            t = conf_t[r];
-            if (arm_conf && t > 0) arm = __ldg(arm_conf + r);
-        }
+        row_inputs(tile + gridDim.x, t_nxt, arm_nxt);
         float* x_tile = s_x + (size_t)st * tile_floats;
         const int nelem = nrows * C;
-        for (int e2 = (nelem & ~3) + tid; e2 < nelem; e2 += kLossRows) x_tile[e2] = conf[r0 * C + e2];   // < 4 floats, last tile only
+        for (int e2 = (nelem & ~3) + tid; e2 < nelem; e2 += kTmaThreads) x_tile[e2] = conf[r0 * C + e2];   // < 4 floats, last tile only
         mbar_wait(&s_bar[st], parity);
         if ((nelem & 3) != 0) __syncthreads();
-        if (tid < nrows)
-            conf_row(x_tile + tid * C, C, t, arm, arm_conf != nullptr, theta, ce_out + r, lse_out + r, pos_out + r);
+        const long long r = r0 + rit;
+        // both lanes of a pair take part (shuffles); a pair past the last row works on row 0 of the tile and writes nothing
+        const bool live = rit < nrows;
+        if (kC > 0)
+            conf_row_pair_regs<(kC > 0 ? kC : 3)>(x_tile + (live ? rit : 0) * C, live ? h : 1, t_cur, arm_cur, arm_conf != nullptr,
+                                                  theta, ce_out + r, lse_out + r, pos_out + r);
+        else
+            conf_row_pair(x_tile + (live ? rit : 0) * C, C, live ? h : 1, t_cur, arm_cur, arm_conf != nullptr, theta, ce_out + r,
+                          lse_out + r, pos_out + r);
         __syncthreads();                                      // every thread is done with the stage: it may be refilled
+        t_cur = t_nxt; arm_cur = arm_nxt;
     }
 }
 
@@ -313,13 +420,37 @@ loss_reduce_kernel(const float4* __restrict__ loc, const float4* __restrict__ lo
     const size_t img = (size_t)b * P;
     grid_dependency_wait();                          // neg / num_pos of the mining kernel (and everything before it)
     double al = 0.0, ac = 0.0;
-    for (int i = g * kLossThreads + tid; i < P; i += kReduceSplit * kLossThreads) {
-        const bool p = pos[img + i] != 0;
-        const bool n = neg[img + i] != 0;
-        if (p | n) ac += (double)ce[img + i];
-        if (p) {
-            const float4 x = loc[img + i], t = loc_t[img + i];
-            al += smooth_l1(x.x, t.x) + smooth_l1(x.y, t.y) + smooth_l1(x.z, t.z) + smooth_l1(x.w, t.w);
+    // the masks and ce are loaded UNCONDITIONALLY (a ce load that waits for the masks' values is a second trip to
+    // DRAM per anchor), four consecutive anchors per thread when the row allows 16-byte loads; only the loc rows of
+    // the positives (~1.5 %) are fetched on demand
+    const bool vec = (P & 3) == 0 && (reinterpret_cast<uintptr_t>(ce) & 15) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(neg)) & 3) == 0;
+    if (vec) {
+        for (int i = 4 * (g * kLossThreads + tid); i < P; i += 4 * kReduceSplit * kLossThreads) {
+            const float4 c4 = ldg_stream4(reinterpret_cast<const float4*>(ce + img + i));
+            const uchar4 p4 = __ldg(reinterpret_cast<const uchar4*>(pos + img + i));
+            const uchar4 n4 = __ldg(reinterpret_cast<const uchar4*>(neg + img + i));
+            const float cv[4] = {c4.x, c4.y, c4.z, c4.w};
+            const unsigned char pv[4] = {p4.x, p4.y, p4.z, p4.w}, nv[4] = {n4.x, n4.y, n4.z, n4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (pv[k] | nv[k]) ac += (double)cv[k];
+                if (pv[k]) {
+                    const float4 x = loc[img + i + k], t = loc_t[img + i + k];
+                    al += smooth_l1(x.x, t.x) + smooth_l1(x.y, t.y) + smooth_l1(x.z, t.z) + smooth_l1(x.w, t.w);
+                }
+            }
+        }
+    } else {
+        for (int i = g * kLossThreads + tid; i < P; i += kReduceSplit * kLossThreads) {
+            const bool p = pos[img + i] != 0;
+            const bool n = neg[img + i] != 0;
+            const float c1 = ce[img + i];
+            if (p | n) ac += (double)c1;
+            if (p) {
+                const float4 x = loc[img + i], t = loc_t[img + i];
+                al += smooth_l1(x.x, t.x) + smooth_l1(x.y, t.y) + smooth_l1(x.z, t.z) + smooth_l1(x.w, t.w);
+            }
         }
     }
 #pragma unroll
@@ -391,8 +522,32 @@ loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ 
         if (!grad_conf) continue;
         const unsigned selmask = __ballot_sync(kFullMask, sel);
         const int nvalid = (int)min((long long)32, rows - r0);
+        // the first kPre selected rows (pos | neg, ~2 of 32) are fetched BEFORE the zero stores are issued, lane =
+        // class: their trip to DRAM overlaps the stores instead of following them one row after the other
+        constexpr int kPre = 4;
+        float xs[kPre][4];
+        float ls[kPre];
+        int ts[kPre], rrs[kPre];
+        unsigned m = selmask;
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+            rrs[u] = -1;
+            if (m) {
+                rrs[u] = __ffs(m) - 1;
+                m &= m - 1;
+                const long long row = r0 + rrs[u];
+                ls[u] = lse[row];
+                ts[u] = (int)conf_t[row];
+                const float* x = conf + row * C;
+#pragma unroll
+                for (int sgm = 0; sgm < 4; ++sgm) {
+                    const int c = sgm * 32 + lane;
+                    xs[u][sgm] = (sgm < nseg && c < C) ? x[c] : 0.f;
+                }
+            }
+        }
         // zeros over the whole 32*C-element span (contiguous 16-byte stores, no per-element bookkeeping); the
-        // few selected rows (pos | neg, ~6 %) are then overwritten by the same warp, ordered by __syncwarp
+        // few selected rows are then overwritten by the same warp, ordered by __syncwarp
         float* base = grad_conf + r0 * C;
         const int nelem = nvalid * C;
         const int nvec = ((reinterpret_cast<uintptr_t>(base) & 15) == 0) ? (nelem >> 2) : 0;
@@ -400,8 +555,18 @@ loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ 
         for (int e = nvec * 4 + lane; e < nelem; e += 32) base[e] = 0.f;
         __syncwarp();
         // selected rows: softmax(x) - onehot(t), lane = class
-        unsigned m = selmask;
-        while (m) {
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+            if (rrs[u] >= 0) {
+                float* g = grad_conf + (r0 + rrs[u]) * C;
+#pragma unroll
+                for (int sgm = 0; sgm < 4; ++sgm) {
+                    const int c = sgm * 32 + lane;
+                    if (sgm < nseg && c < C) g[c] = (exp2f((xs[u][sgm] - ls[u]) * kLog2e) - (c == ts[u] ? 1.f : 0.f)) * sc;
+                }
+            }
+        }
+        while (m) {                                           // more than kPre selected rows in the group: one by one
             const int rr = __ffs(m) - 1;
             m &= m - 1;
             const long long row = r0 + rr;
@@ -416,6 +581,135 @@ loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ 
             }
         }
     }
+}
+
+
+// ---- TMA variant of the backward (odd C, 16-byte aligned grad_conf): the gradient of a tile of kBwdRows rows is
+// BUILT in shared memory -- zeros, with the few selected rows (pos | neg, ~6 %) computed into place -- and leaves as ONE
+// bulk asynchronous store (cp.async.bulk.global.shared::cta, the 1-D TMA store: SASS UBLKCP), two tiles in flight per
+// CTA.  The 127 MB of zeros no longer pass through the load/store units as 16-byte stores of every lane (the
+// register kernel spends a fifth of its stall samples in lg_throttle); only the rows selected in a buffer's previous
+// use are re-zeroed.  Persistent CTAs of four warps over 64-row tiles (41 KB of shared memory: five CTAs per SM, so
+// that the trips to DRAM of one CTA -- flags, then the selected rows -- hide behind the others'); thread = row for
+// the flags (fetched one tile ahead) and the loc gradient, warp = selected row (lane = class) for the conf gradient.
+constexpr int kBwdRows = 64;
+constexpr int kBwdThreads = 128;
+
+__global__ void __launch_bounds__(kBwdThreads)
+loss_backward_tma_kernel(const float4* __restrict__ loc, const float4* __restrict__ loc_t,
+                         const float* __restrict__ conf, const long long* __restrict__ conf_t,
+                         const float* __restrict__ lse, const unsigned char* __restrict__ pos,
+                         const unsigned char* __restrict__ neg, const float* __restrict__ g_l,
+                         const float* __restrict__ g_c, const float* __restrict__ n_dev, long long rows, int C,
+                         float4* __restrict__ grad_loc, float* __restrict__ grad_conf) {
+    extern __shared__ __align__(128) float s_g[];            // [2][kBwdRows * C]
+    __shared__ unsigned char s_list[2][kBwdRows];            // rows of the tile that hold a non-zero gradient
+    __shared__ int s_nsel[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_floats = kBwdRows * C;
+    const long long ntiles = (rows + kBwdRows - 1) / kBwdRows;
+    const float N = *n_dev;
+    const float sl = (g_l && N > 0.f) ? *g_l / N : 0.f;
+    const float sc = (g_c && N > 0.f) ? *g_c / N : 0.f;
+    const int nseg = (C + 31) >> 5;
+    for (int i = tid; i < 2 * tile_floats / 4; i += kBwdThreads) reinterpret_cast<float4*>(s_g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < 2) s_nsel[tid] = 0;
+    // flags of this thread's row, one tile ahead
+    auto flags_of = [&](long long tile, unsigned char& pf, unsigned char& nf) {
+        pf = 0; nf = 0;
+        const long long r = tile * kBwdRows + tid;
+        if (tile < ntiles && tid < kBwdRows && r < rows) { pf = pos[r]; nf = neg[r]; }
+    };
+    unsigned char pf, nf, pf_n, nf_n;
+    flags_of(blockIdx.x, pf, nf);
+    __syncthreads();
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int b = it & 1;
+        float* g_tile = s_g + (size_t)b * tile_floats;
+        const long long r0 = tile * kBwdRows;
+        const int nrows = (int)min((long long)kBwdRows, rows - r0);
+        flags_of(tile + gridDim.x, pf_n, nf_n);
+        // the store that last read this buffer (two tiles ago) is done with it: all groups but the latest have read
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads();
+        // back to zeros: only the rows written in the buffer's previous use
+        const int nprev = s_nsel[b];
+        for (int k = warp; k < nprev; k += kBwdThreads / 32) {
+            float* g = g_tile + (int)s_list[b][k] * C;
+#pragma unroll
+            for (int sgm = 0; sgm < 4; ++sgm) {
+                const int c = sgm * 32 + lane;
+                if (sgm < nseg && c < C) g[c] = 0.f;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_nsel[b] = 0;
+        __syncthreads();
+        // selected rows of this tile -> list; loc gradient: thread = row
+        const long long r = r0 + tid;
+        const bool in_tile = tid < nrows;                        // nrows <= kBwdRows <= kBwdThreads
+        const bool sel = in_tile && (pf | nf) != 0;
+        if (in_tile && grad_loc) {
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pf) {
+                const float4 x = loc[r], t = loc_t[r];
+                g.x = fminf(fmaxf(x.x - t.x, -1.f), 1.f) * sl;      // d SmoothL1 / d x = clamp(x - t, -1, 1)
+                g.y = fminf(fmaxf(x.y - t.y, -1.f), 1.f) * sl;
+                g.z = fminf(fmaxf(x.z - t.z, -1.f), 1.f) * sl;
+                g.w = fminf(fmaxf(x.w - t.w, -1.f), 1.f) * sl;
+            }
+            grad_loc[r] = g;
+        }
+        const unsigned bal = __ballot_sync(kFullMask, sel);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nsel[b], __popc(bal));
+            base = __shfl_sync(kFullMask, base, 0);
+            if (sel) s_list[b][base + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)tid;
+        }
+        __syncthreads();
+        // selected rows: softmax(x) - onehot(t), warp = row, lane = class; two rows in flight per warp
+        const int nsel = s_nsel[b];
+        for (int k = warp; k < nsel; k += 2 * (kBwdThreads / 32)) {
+            const int k2 = k + kBwdThreads / 32;
+            const int ra = s_list[b][k], rb = k2 < nsel ? s_list[b][k2] : -1;
+            const long long rowa = r0 + ra, rowb = r0 + (rb >= 0 ? rb : ra);
+            const float la = lse[rowa], lb = lse[rowb];
+            const int ta = (int)conf_t[rowa], tb = (int)conf_t[rowb];
+            float xa[4], xb[4];
+#pragma unroll
+            for (int sgm = 0; sgm < 4; ++sgm) {
+                const int c = sgm * 32 + lane;
+                const bool on = sgm < nseg && c < C;
+                xa[sgm] = on ? conf[rowa * C + c] : 0.f;
+                xb[sgm] = (on && rb >= 0) ? conf[rowb * C + c] : 0.f;
+            }
+#pragma unroll
+            for (int sgm = 0; sgm < 4; ++sgm) {
+                const int c = sgm * 32 + lane;
+                if (sgm < nseg && c < C) {
+                    g_tile[ra * C + c] = (exp2f((xa[sgm] - la) * kLog2e) - (c == ta ? 1.f : 0.f)) * sc;
+                    if (rb >= 0) g_tile[rb * C + c] = (exp2f((xb[sgm] - lb) * kLog2e) - (c == tb ? 1.f : 0.f)) * sc;
+                }
+            }
+        }
+        // shared-memory writes of the generic proxy -> visible to the bulk-copy engine, then one store for the tile
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        const int nelem = nrows * C;
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)(((size_t)nelem * 4) & ~(size_t)15);
+            if (bytes)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(grad_conf + r0 * C),
+                             "r"((unsigned)__cvta_generic_to_shared(g_tile)), "r"(bytes)
+                             : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        for (int e2 = (nelem & ~3) + tid; e2 < nelem; e2 += kBwdThreads) grad_conf[r0 * C + e2] = g_tile[e2];   // < 4 floats, last tile only
+        pf = pf_n; nf = nf_n;
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // shared memory stays alive until the stores have read it
 }
 
 }  // namespace rd
@@ -434,19 +728,20 @@ static int conf_loss_launch(const float* conf, const long long* conf_t, const fl
         else conf_loss2_kernel<<<(unsigned)blocks, kLossThreads, 0, st>>>((const float2*)conf, conf_t, (const float2*)arm_conf,
                                                                           theta, rows, ce_out, lse_out, pos_out);
     } else if ((C & 1) && ((uintptr_t)conf & 15) == 0 && !getenv("RD_NO_TMA")) {
-        const size_t smem = (size_t)kTmaStages * kLossRows * C * sizeof(float);
-        static size_t s_tma_smem[kMaxDevices];
-        e = ensure_dynamic_smem(conf_loss_tma_kernel, smem, s_tma_smem);
-        if (e != cudaSuccess) return (int)e;
-        const long long ntiles = (rows + kLossRows - 1) / kLossRows;
+        const size_t smem = (size_t)kTmaStages * kTmaRows * C * sizeof(float);
+        const long long ntiles = (rows + kTmaRows - 1) / kTmaRows;
         long long per_sm = (long long)(220 * 1024) / (long long)(smem + 1024);
         if (per_sm < 1) per_sm = 1;
         long long blocks = 148 * per_sm;                      // persistent: one wave
         if (blocks > ntiles) blocks = ntiles;
-        if (pdl) e = launch_pdl(conf_loss_tma_kernel, dim3((unsigned)blocks), dim3(kLossRows), smem, st, conf, conf_t,
+        auto kern = C == 81 ? conf_loss_tma_kernel<81> : C == 21 ? conf_loss_tma_kernel<21> : conf_loss_tma_kernel<0>;
+        static size_t s_tma_smem[3][kMaxDevices];
+        e = ensure_dynamic_smem(kern, smem, s_tma_smem[C == 81 ? 0 : C == 21 ? 1 : 2]);
+        if (e != cudaSuccess) return (int)e;
+        if (pdl) e = launch_pdl(kern, dim3((unsigned)blocks), dim3(kTmaThreads), smem, st, conf, conf_t,
                                 (const float2*)arm_conf, theta, rows, C, ce_out, lse_out, pos_out);
-        else conf_loss_tma_kernel<<<(unsigned)blocks, kLossRows, smem, st>>>(conf, conf_t, (const float2*)arm_conf, theta, rows,
-                                                                             C, ce_out, lse_out, pos_out);
+        else kern<<<(unsigned)blocks, kTmaThreads, smem, st>>>(conf, conf_t, (const float2*)arm_conf, theta, rows, C, ce_out,
+                                                               lse_out, pos_out);
     } else {
         const size_t smem = (size_t)kLossRows * (C | 1) * sizeof(float);
         static size_t s_conf_smem[kMaxDevices];
@@ -471,6 +766,7 @@ size_t rd_multibox_loss_workspace_bytes(int B) { return B > 0 ? (size_t)B * kRed
 
 int rd_conf_loss(const float* conf, const long long* conf_t, const float* arm_conf, float theta, long long rows,
                  int C, float* ce_out, float* lse_out, unsigned char* pos_out, void* stream) {
+    NvtxRange nvtx_range("rd_conf_loss");
     if (!conf || !conf_t || !ce_out || !lse_out || !pos_out || rows <= 0 || C < 2) return RD_ERR_BAD_ARG;
     if (C > kLossMaxClasses) return RD_ERR_UNSUPPORTED;
     if (arm_conf && ((uintptr_t)arm_conf & 7)) return RD_ERR_ALIGNMENT;
@@ -481,6 +777,7 @@ int rd_conf_loss(const float* conf, const long long* conf_t, const float* arm_co
 int rd_multibox_loss_reduce(const float* loc, const float* loc_t, const float* ce, const unsigned char* pos,
                             const unsigned char* neg, const int* num_pos, int B, int P, void* workspace,
                             size_t workspace_bytes, float* loss_l, float* loss_c, float* n_out, void* stream) {
+    NvtxRange nvtx_range("rd_multibox_loss_reduce");
     if (!loc || !loc_t || !ce || !pos || !neg || !num_pos || !workspace || !loss_l || !loss_c || !n_out || B <= 0 ||
         P <= 0)
         return RD_ERR_BAD_ARG;
@@ -536,6 +833,7 @@ int rd_multibox_criterion(const float* truths, const float* labels, const int* g
                           int negpos_ratio, void* workspace, size_t workspace_bytes, float* loc_t, long long* conf_t,
                           float* ce, float* lse, unsigned char* pos, unsigned char* neg, int* num_pos, float* losses,
                           void* stream) {
+    NvtxRange nvtx_range("rd_multibox_criterion");
     if (!truths || !labels || !gt_count || !priors || !loc_data || !conf_data || !workspace || !loc_t || !conf_t || !ce ||
         !lse || !pos || !neg || !num_pos || !losses)
         return RD_ERR_BAD_ARG;
@@ -574,11 +872,30 @@ int rd_multibox_loss_backward(const float* loc, const float* loc_t, const float*
                               const float* lse, const unsigned char* pos, const unsigned char* neg,
                               const float* grad_loss_l, const float* grad_loss_c, const float* n_dev,
                               long long rows, int C, float* grad_loc, float* grad_conf, void* stream) {
+    NvtxRange nvtx_range("rd_multibox_loss_backward");
     if (!loc || !loc_t || !conf || !conf_t || !lse || !pos || !neg || !n_dev || rows <= 0 || C < 2)
         return RD_ERR_BAD_ARG;
     if (!grad_loc && !grad_conf) return 0;
     if (C > kLossMaxClasses) return RD_ERR_UNSUPPORTED;
     if (((uintptr_t)loc | (uintptr_t)loc_t | (uintptr_t)grad_loc) & 15) return RD_ERR_ALIGNMENT;
+    if (grad_conf && (C & 1) && ((uintptr_t)grad_conf & 15) == 0 && !getenv("RD_NO_TMA")) {
+        const size_t smem = (size_t)2 * kBwdRows * C * sizeof(float);
+        static size_t s_bwd_smem[kMaxDevices];
+        cudaError_t e = ensure_dynamic_smem(loss_backward_tma_kernel, smem, s_bwd_smem);
+        if (e != cudaSuccess) return (int)e;
+        const long long ntiles = (rows + kBwdRows - 1) / kBwdRows;
+        long long per_sm = (long long)(220 * 1024) / (long long)(smem + 1024);
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 8) per_sm = 8;
+        long long nb = 148 * per_sm;
+        if (nb > ntiles) nb = ntiles;
+        loss_backward_tma_kernel<<<(unsigned)nb, kBwdThreads, smem, (cudaStream_t)stream>>>(
+            (const float4*)loc, (const float4*)loc_t, conf, conf_t, lse, pos, neg, grad_loss_l, grad_loss_c, n_dev, rows, C,
+            (float4*)grad_loc, grad_conf);
+        note_launch();
+        RD_CHECK_LAUNCH();
+        return 0;
+    }
     long long blocks = ((rows + 31) / 32 * 32 + kLossThreads - 1) / kLossThreads;
     if (blocks > 148 * 32) blocks = 148 * 32;
     loss_backward_kernel<<<(unsigned)blocks, kLossThreads, 0, (cudaStream_t)stream>>>(

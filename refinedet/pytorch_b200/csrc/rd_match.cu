@@ -380,22 +380,50 @@ hnm_cluster_kernel(const float* __restrict__ loss_c, const unsigned char* __rest
     if (tid == 0) { S.npos = 0; S.nlist = 0; S.kmin = ~0ull; S.kmax = 0ull; S.kmin_neg = ~0ull; }
     __syncthreads();
     // ---- ordered losses into registers (the key of element i is (ord << 32) | ~i, rebuilt where needed);
-    //      positives count as loss 0 (refinedet_multibox_loss.py:117) ------------------------------------------
+    //      positives count as loss 0 (refinedet_multibox_loss.py:117).  Element (j, tid) of this CTA is anchor
+    //      i0 + (j / 4) * 1024 + 4 tid + (j % 4): four consecutive anchors per thread and round, so that the losses
+    //      arrive as one 16-byte load and the flags as one 4-byte load, all sixteen independent of each other (a load
+    //      of the loss that waits for the flag's value costs a second trip to DRAM per element). ---------------------
     uint32_t ord[kHnmPerT];
+    auto index_of = [&](int j) -> int { return i0 + (j >> 2) * (4 * kHnmCT) + 4 * tid + (j & 3); };
     auto key_of = [&](int j) -> unsigned long long {          // 0 = not an element of the row
-        const int i = i0 + j * kHnmCT + tid;
+        const int i = index_of(j);
         return i < P ? (((unsigned long long)ord[j] << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i)) : 0ull;
     };
+    float lossv[kHnmPerT];
+    unsigned char posv[kHnmPerT];
+    const bool vec = (P & 3) == 0 && (reinterpret_cast<uintptr_t>(loss_c) & 15) == 0 && (reinterpret_cast<uintptr_t>(pos) & 3) == 0;
+    if (vec) {
+#pragma unroll
+        for (int j4 = 0; j4 < kHnmPerT / 4; ++j4) {
+            const int i = index_of(4 * j4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            uchar4 f = make_uchar4(0, 0, 0, 0);
+            if (i < P) {                                          // P % 4 == 0: the four are in or out together
+                v = ldg_stream4(reinterpret_cast<const float4*>(row + i));
+                f = __ldg(reinterpret_cast<const uchar4*>(prow + i));
+            }
+            lossv[4 * j4] = v.x; lossv[4 * j4 + 1] = v.y; lossv[4 * j4 + 2] = v.z; lossv[4 * j4 + 3] = v.w;
+            posv[4 * j4] = f.x; posv[4 * j4 + 1] = f.y; posv[4 * j4 + 2] = f.z; posv[4 * j4 + 3] = f.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kHnmPerT; ++j) {
+            const int i = index_of(j);
+            lossv[j] = i < P ? __ldg(row + i) : 0.f;
+            posv[j] = i < P ? __ldg(prow + i) : (unsigned char)0;
+        }
+    }
     int local = 0;
     unsigned long long mn = ~0ull, mx = 0ull, mn_neg = ~0ull;   // mn_neg: over the non-positive anchors only
 #pragma unroll
     for (int j = 0; j < kHnmPerT; ++j) {
-        const int i = i0 + j * kHnmCT + tid;
+        const int i = index_of(j);
         ord[j] = 0u;
         if (i < P) {
-            const bool p = prow[i] != 0;
+            const bool p = posv[j] != 0;
             local += p ? 1 : 0;
-            ord[j] = float_to_ordered(p ? 0.0f : row[i]);
+            ord[j] = float_to_ordered(p ? 0.0f : lossv[j]);
             const unsigned long long k = key_of(j);
             mn = k < mn ? k : mn;
             mx = k > mx ? k : mx;
@@ -534,10 +562,25 @@ hnm_cluster_kernel(const float* __restrict__ loss_c, const unsigned char* __rest
         __syncthreads();
         thresh_key = S.thresh;
     }
+    if (vec && (reinterpret_cast<uintptr_t>(neg_out) & 3) == 0) {
 #pragma unroll
-    for (int j = 0; j < kHnmPerT; ++j) {
-        const int i = i0 + j * kHnmCT + tid;
-        if (i < P) nrow[i] = (need > 0 && key_of(j) >= thresh_key) ? 1 : 0;
+        for (int j4 = 0; j4 < kHnmPerT / 4; ++j4) {
+            const int i = index_of(4 * j4);
+            if (i < P) {
+                uchar4 o;
+                o.x = (need > 0 && key_of(4 * j4) >= thresh_key) ? 1 : 0;
+                o.y = (need > 0 && key_of(4 * j4 + 1) >= thresh_key) ? 1 : 0;
+                o.z = (need > 0 && key_of(4 * j4 + 2) >= thresh_key) ? 1 : 0;
+                o.w = (need > 0 && key_of(4 * j4 + 3) >= thresh_key) ? 1 : 0;
+                *reinterpret_cast<uchar4*>(nrow + i) = o;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kHnmPerT; ++j) {
+            const int i = index_of(j);
+            if (i < P) nrow[i] = (need > 0 && key_of(j) >= thresh_key) ? 1 : 0;
+        }
     }
     cluster.sync();                                           // nobody leaves while a peer may still read its shared memory
 }
@@ -707,6 +750,7 @@ int rd_refine_match(const float* truths, const float* labels, const int* gt_coun
                     const float* arm_loc, int B, int P, int Gmax, float threshold, float v0, float v1,
                     int label_mode, void* workspace, size_t workspace_bytes, float* loc_t, long long* conf_t,
                     int* best_truth_idx, float* best_truth_overlap, void* stream) {
+    NvtxRange nvtx_range("rd_refine_match");
     if (!truths || !labels || !gt_count || !priors || !workspace || !loc_t || !conf_t) return RD_ERR_BAD_ARG;
     if (B <= 0 || P <= 0 || Gmax <= 0 || label_mode < 0 || label_mode > 2) return RD_ERR_BAD_ARG;
     if (Gmax > RD_MAX_GT || B > 65535) return RD_ERR_UNSUPPORTED;
@@ -727,6 +771,7 @@ int rd_refine_match(const float* truths, const float* labels, const int* gt_coun
 
 int rd_pad_targets(const float* flat, const int* offsets, int B, int Gmax, float* truths, float* labels,
                    int* gt_count, void* stream) {
+    NvtxRange nvtx_range("rd_pad_targets");
     if (!flat || !offsets || !truths || !labels || !gt_count || B <= 0 || Gmax <= 0) return RD_ERR_BAD_ARG;
     if ((uintptr_t)truths & 15) return RD_ERR_ALIGNMENT;
     const int n = B * Gmax;
@@ -739,6 +784,7 @@ int rd_pad_targets(const float* flat, const int* offsets, int B, int Gmax, float
 
 int rd_hnm_select(const float* loss_c, const unsigned char* pos, int B, int P, int negpos_ratio,
                   unsigned char* neg_out, int* num_pos_out, void* stream) {
+    NvtxRange nvtx_range("rd_hnm_select");
     if (!loss_c || !pos || !neg_out || B <= 0 || P <= 0 || negpos_ratio < 0) return RD_ERR_BAD_ARG;
     return hnm_launch(loss_c, pos, B, P, negpos_ratio, neg_out, num_pos_out, (cudaStream_t)stream, false);
 }

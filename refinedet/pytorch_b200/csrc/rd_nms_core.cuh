@@ -582,6 +582,83 @@ __host__ __device__ inline NmsSmemLayout nms_layout(int mcap_req) {
     return L;
 }
 
+// Descending sort of keys[0..m) (64-bit, pairwise distinct) by the whole CTA, any thread count: the bucket sort of
+// cta_sort_small for the large path.  Buckets are linear in the key over [min key, max key] of the problem (the
+// keys that survive a top-k select span a few octaves of score), nb of them; `scratch` (8-byte aligned) provides
+// 256 bytes (reductions) + 8 m bytes (keys regrouped by bucket) + 4 (nb + 1) bytes (counts, then starts) + 2 m bytes
+// (slot of every key inside its bucket).  Seven CTA barriers instead of the 55 of a 1024-key bitonic network, ~10 x fewer
+// instructions; an adversarial input (everything in one bucket) degrades to an O(m^2 / threads) exact rank.
+__device__ __forceinline__ void cta_bucket_sort(unsigned long long* keys, int m, unsigned char* scratch, int nb) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+    unsigned long long* red = reinterpret_cast<unsigned long long*>(scratch);          // 2 words + 32 warp totals: 256 bytes
+    scratch += 256;
+    unsigned long long* tmp = reinterpret_cast<unsigned long long*>(scratch);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(scratch + (size_t)m * 8);
+    unsigned short* slots = reinterpret_cast<unsigned short*>(scratch + (size_t)m * 8 + (size_t)(nb + 1) * 4);
+    if (tid == 0) { red[0] = ~0ull; red[1] = 0ull; }
+    for (int i = tid; i <= nb; i += nthr) hist[i] = 0;
+    __syncthreads();
+    unsigned long long mn = ~0ull, mx = 0ull;
+    for (int e = tid; e < m; e += nthr) {
+        const unsigned long long k = keys[e];
+        mn = k < mn ? k : mn;
+        mx = k > mx ? k : mx;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(kFullMask, mn, d), c = __shfl_xor_sync(kFullMask, mx, d);
+        mn = a < mn ? a : mn;
+        mx = c > mx ? c : mx;
+    }
+    if (lane == 0) { atomicMin(&red[0], mn); atomicMax(&red[1], mx); }
+    __syncthreads();
+    const unsigned long long lo = red[0], range = red[1] - lo;
+    int lg = 0;
+    while ((1 << lg) < nb) ++lg;
+    int shift = (64 - __clzll((long long)(range | 1ull))) - lg;        // (range >> shift) < nb
+    if (shift < 0) shift = 0;
+    for (int e = tid; e < m; e += nthr) {
+        const int b = nb - 1 - (int)((keys[e] - lo) >> shift);         // bucket 0 = the highest keys
+        slots[e] = (unsigned short)atomicAdd(&hist[b], 1u);
+    }
+    __syncthreads();
+    // exclusive scan of hist[0..nb) in place (nb <= 1024: one pass of the first nb threads' chunks)
+    {
+        const int per = (nb + nthr - 1) / nthr;
+        unsigned int sum = 0;
+        for (int i = 0; i < per; ++i) { const int b = tid * per + i; sum += b < nb ? hist[b] : 0u; }
+        unsigned int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const unsigned int o = __shfl_up_sync(kFullMask, incl, d); if (lane >= d) incl += o; }
+        unsigned int* wtot = reinterpret_cast<unsigned int*>(red) + 4;  // up to 32 warp totals behind the two words
+        if (lane == 31) wtot[tid >> 5] = incl;
+        __syncthreads();
+        unsigned int run = incl - sum;
+        for (int w = 0; w < (tid >> 5); ++w) run += wtot[w];
+        for (int i = 0; i < per; ++i) {
+            const int b = tid * per + i;
+            if (b < nb) { const unsigned int c = hist[b]; hist[b] = run; run += c; }
+        }
+        if (tid == nthr - 1) hist[nb] = (unsigned int)m;
+    }
+    __syncthreads();
+    for (int e = tid; e < m; e += nthr) {
+        const unsigned long long k = keys[e];
+        const int b = nb - 1 - (int)((k - lo) >> shift);
+        tmp[hist[b] + slots[e]] = k;
+    }
+    __syncthreads();
+    for (int p = tid; p < m; p += nthr) {
+        const unsigned long long k = tmp[p];
+        const int b = nb - 1 - (int)((k - lo) >> shift);
+        const int blo = (int)hist[b], bhi = (int)hist[b + 1];
+        int pos = blo;
+        for (int i = blo; i < bhi; ++i) pos += tmp[i] > k ? 1 : 0;
+        keys[pos] = k;
+    }
+    __syncthreads();
+}
+
 // Runs one problem on the calling CTA.  Rows are emitted through `sink`.  Returns the kept
 // count (uniform over the CTA).
 __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, const NmsProblem& pb,
@@ -674,11 +751,18 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
             }
         }
     }
-    const int Kp = presorted ? 0 : next_pow2(m);
+    const bool bucket_sort = !presorted && m > 64;
+    const int Kp = (presorted || bucket_sort) ? 0 : next_pow2(m);
     for (int i = m + tid; i < Kp; i += nthr) keys[i] = 0ull;
     __syncthreads();
 
-    // ---- 2. bitonic sort, descending -------------------------------------------------------------
+    // ---- 2. sort, descending: bucket sort (the box arrays are not in use yet: they are its scratch), a bitonic
+    //         network for the few-key problems ------------------------------------------------------------------
+    if (bucket_sort) {
+        int nb = 1024;
+        while (nb > L.mcap) nb >>= 1;                          // scratch: 256 + 10 m + 4 nb + 4 <= 20 mcap bytes (m > 64)
+        cta_bucket_sort(keys, m, smem + L.off_x1, nb);
+    }
     for (int k = 2; k <= Kp; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < (Kp >> 1); t += nthr) {

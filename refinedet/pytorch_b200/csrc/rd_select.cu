@@ -304,6 +304,7 @@ extern "C" {
 
 int rd_select_topk(const float* scores, int B, int P, int C, float conf_thresh, int top_k, int first_class,
                    int* idx_out, float* score_out, int* count_out, void* stream) {
+    NvtxRange nvtx_range("rd_select_topk");
     if (!scores || !idx_out || !count_out || B <= 0 || P <= 0 || C <= 0 || top_k <= 0 || first_class < 0)
         return RD_ERR_BAD_ARG;
     if (B > 65535) return RD_ERR_UNSUPPORTED;

@@ -113,18 +113,20 @@ def decode_slots(buf, world, slot_bytes, nbc_capacity):
 
 
 class PeerExchange(object):
-    """All-gather of the compact detections WITHOUT a collective call (``rd_pack_scatter_ex``): every rank packs
-    its counts and rows into its own slot of its own buffer, then streams the slot's used prefix into the same
-    slot of every peer's buffer — symmetric memory: each buffer is mapped into every process of the node, the
-    stores travel over NVLink / NVSwitch — bracketed by two device-side barriers.  With NVSwitch multicast
-    (``mode == 'multicast'``) one ``multimem.st`` is replicated to all ranks by the switch, so the rows leave the GPU
-    once instead of ``world - 1`` times; otherwise (``mode == 'p2p'``) one group of CTAs stores to each peer.
-    ``B`` = the largest per-rank batch; all ranks construct it collectively.
+    """All-gather of the compact detections WITHOUT a collective call and without barrier kernels
+    (``rd_exchange_round``): every rank packs its counts and rows into its own slot of its own buffer, streams the
+    slot's used prefix into the same slot of every peer's buffer — symmetric memory: each buffer is mapped into every
+    process of the node, the stores travel over NVLink / NVSwitch — and the copy kernel itself publishes the round
+    number on every rank and waits for everybody's: ONE cross-GPU rendezvous per round, two launches, replayable
+    from a CUDA graph.  With NVSwitch multicast (``mode == 'multicast'``) one ``multimem.st`` is replicated to all
+    ranks by the switch, so the rows leave the GPU once instead of ``world - 1`` times; otherwise (``mode == 'p2p'``)
+    one group of CTAs stores to each peer.  Slots are double-buffered by the parity of the round.
+    ``B`` = the largest per-rank batch; all ranks construct it collectively and call :meth:`exchange` in lockstep.
 
     Needs ``torch.distributed._symmetric_memory`` (one node, NVLink/PCIe P2P); raises otherwise — callers
     that want a portable path use :func:`gather_packed` (NCCL / gloo)."""
 
-    def __init__(self, B, C, max_out, device, group=None, capacity_rows=None, mode=None, copy_ctas=0):
+    def __init__(self, B, C, max_out, device, group=None, capacity_rows=None, mode=None, copy_ctas=0, timeout_ms=10000):
         import ctypes
         import os
         import torch.distributed._symmetric_memory as symm_mem
@@ -134,27 +136,36 @@ class PeerExchange(object):
         self.B, self.C, self.max_out = int(B), int(C), int(max_out)
         self.capacity = int(capacity_rows) if capacity_rows is not None else self.B * self.C * self.max_out
         self.slot_bytes = int(lib().rd_exchange_slot_bytes(self.B, self.C, self.capacity))
-        self.buf = symm_mem.empty(self.world * self.slot_bytes, dtype=torch.uint8, device=device)
+        self.ctrl_bytes = int(lib().rd_exchange_ctrl_bytes())
+        self.buf = symm_mem.empty(self.ctrl_bytes + 2 * self.world * self.slot_bytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()                                         # control block: epoch 0, flags 0
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         off = int(getattr(self.hdl, 'offset', 0) or 0)
-        ptrs = [int(p) + off for p in self.hdl.buffer_ptrs]
-        self._peer_slots = (ctypes.c_void_p * self.world)(*[p + self.rank * self.slot_bytes for p in ptrs])
-        mode = mode or os.environ.get('RD_EXCHANGE_MODE') or 'auto'
+        self._bases = (ctypes.c_void_p * self.world)(*[int(p) + off for p in self.hdl.buffer_ptrs])
+        # 'p2p' (default): unicast, the rows are moved by the TMA engines; 'multicast': one multimem.st per 16 bytes,
+        # replicated by the NVSwitch.  Measured on 8 B200: both are bound by the 54 MB every GPU RECEIVES per round
+        # (0.098 - 0.104 ms, ~550 GB/s of ingress) -- multicast saves egress, which is not the limit -- and at 2 GPUs
+        # unicast is faster (0.027 against 0.038 ms), so multicast is opt-in.
+        mode = mode or os.environ.get('RD_EXCHANGE_MODE') or 'p2p'
         mc = 0
-        if mode in ('auto', 'multicast') and self.world > 1:
+        if mode == 'multicast' and self.world > 1:
             try:
                 mc = int(self.hdl.multicast_ptr or 0)
             except Exception:
                 mc = 0
-            if mode == 'multicast' and not mc:
+            if not mc:
                 raise RuntimeError('PeerExchange(mode="multicast"): the symmetric buffer has no multicast mapping')
-        self._mc_slot = ctypes.c_void_p(mc + off + self.rank * self.slot_bytes) if mc else ctypes.c_void_p(0)
+        self._mc_base = ctypes.c_void_p(mc + off) if mc else ctypes.c_void_p(0)
         self.mode = 'multicast' if mc else 'p2p'
         self.copy_ctas = int(copy_ctas or os.environ.get('RD_EXCHANGE_CTAS') or 0)
+        self.timeout_ms = int(timeout_ms)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)                                 # every rank's control block is zero before the first round
 
     def exchange(self, detections, stream=None):
-        """Asynchronous on ``stream`` (default: the current stream): barrier (peers are done reading the previous
-        round), pack + copy, barrier (every peer's stores have landed)."""
+        """Asynchronous on ``stream`` (default: the current stream): pack + copy + rendezvous.  When the work
+        completes on the stream, the rows of every rank are in the local buffer (:meth:`result`).  Read them on that
+        stream (or after synchronising with it) before the next :meth:`exchange` is enqueued."""
         from ._ffi import check, lib, ptr
         B, C, max_out, _ = detections.dets.shape
         if B > self.B or C != self.C or max_out != self.max_out:
@@ -164,12 +175,16 @@ class PeerExchange(object):
         ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.device(dev)
         with ctx:
             st = torch.cuda.current_stream(dev).cuda_stream
-            self.hdl.barrier(channel=0)
-            check(lib().rd_pack_scatter_ex(ptr(detections.counts), ptr(detections.dets), B, C, max_out, None,
-                                           self._peer_slots, self.world, self.rank, self.B, self.capacity,
-                                           self._mc_slot, self.copy_ctas, st), 'rd_pack_scatter_ex')
-            self.hdl.barrier(channel=1)
+            check(lib().rd_exchange_round(ptr(detections.counts), ptr(detections.dets), B, C, max_out, self._bases,
+                                          self._mc_base, self.world, self.rank, self.B, self.capacity, self.copy_ctas,
+                                          self.timeout_ms, st), 'rd_exchange_round')
 
     def result(self):
-        """``(counts_all, rows_all)`` of the latest exchange (views into the local buffer; one host sync)."""
-        return decode_slots(self.buf, self.world, self.slot_bytes, self.B * self.C)
+        """``(counts_all, rows_all)`` of the latest completed round (views into the local buffer; one host sync)."""
+        ctrl = self.buf[:self.ctrl_bytes].view(torch.int32).cpu()
+        epoch, error = int(ctrl[64]), int(ctrl[66])
+        if error:
+            raise RuntimeError('PeerExchange: a rank did not arrive within %d ms (control block error flag)' % self.timeout_ms)
+        half = self.buf[self.ctrl_bytes + (epoch & 1) * self.world * self.slot_bytes:
+                        self.ctrl_bytes + ((epoch & 1) + 1) * self.world * self.slot_bytes]
+        return decode_slots(half, self.world, self.slot_bytes, self.B * self.C)

@@ -126,35 +126,31 @@ def clear_pad_cache():
 
 
 
-# Offsets of the ragged target list travel through a small ring of PINNED staging buffers: a copy from pageable
-# memory makes the driver drain the stream first (CUDA API synchronisation rules), i.e. one hidden device
-# synchronisation per training step.  A slot is reused only after the copy that read it has completed.
+# Offsets of the ragged target list live in a small ring of PINNED host slots that the pad kernel reads directly: a
+# copy from pageable memory would make the driver drain the stream first (CUDA API synchronisation rules), i.e. one
+# hidden device synchronisation per training step.  A slot is reused only after the kernel that read it has completed.
 _PIN_SLOTS = 8
 
 
-def _offsets_to_device(counts, device):
-    """The ring (and its cursor) is per thread and per (device, length); the copy and the event that guards the
-    slot are issued with ``device`` current, so the event is recorded on the stream the copy went to."""
+def _offsets_slot(counts, device):
+    """A pinned host slot holding the exclusive prefix sum of ``counts`` + the event that guards its reuse.  The pad
+    kernel reads the offsets straight from the pinned slot (unified addressing: 33 ints over PCIe) — no H2D copy
+    call at all; the caller records the event after launching the kernel.  The ring (and its cursor) is per thread
+    and per (device, length)."""
     n = len(counts) + 1
     rings = getattr(_tls, 'pin_rings', None)
     if rings is None:
         rings = _tls.pin_rings = {}
     key = (device.index, n)
-    with on_device(device):
-        st = torch.cuda.current_stream(device)
-        ring = rings.get(key)
-        if ring is None:
-            ring = rings[key] = {'next': 0, 'slots': [(torch.zeros(n, dtype=torch.int32).pin_memory(), torch.cuda.Event())
-                                                      for _ in range(_PIN_SLOTS)]}
-            for _, ev in ring['slots']:
-                ev.record(st)
-        buf, ev = ring['slots'][ring['next'] % _PIN_SLOTS]
-        ring['next'] += 1
-        ev.synchronize()                                    # normally long complete
-        np.cumsum(counts, out=buf.numpy()[1:])
-        out = buf.to(device, non_blocking=True)
-        ev.record(st)
-    return out
+    ring = rings.get(key)
+    if ring is None:
+        ring = rings[key] = {'next': 0, 'slots': [(torch.zeros(n, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+                                                  for _ in range(_PIN_SLOTS)]}
+    buf, ev = ring['slots'][ring['next'] % _PIN_SLOTS]
+    ring['next'] += 1
+    ev.synchronize()                                        # the kernel that last read the slot is done (normally long ago)
+    np.cumsum(counts, out=buf.numpy()[1:])
+    return buf, ev
 
 
 def pad_targets(targets, device):
@@ -196,10 +192,11 @@ def _padded(targets, device):
         if flat.device != device or flat.dtype != torch.float32:
             flat = flat.to(device=device, dtype=torch.float32)
         flat = flat.contiguous()
-        offsets = _offsets_to_device(counts, device)
+        offsets, ev = _offsets_slot(counts, device)
         with on_device(device):
             check(lib().rd_pad_targets(ptr(flat), ptr(offsets), B, gmax, ptr(truths), ptr(labels), ptr(gt_count),
                                        stream_ptr()), 'rd_pad_targets')
+            ev.record(torch.cuda.current_stream(device))
     out = (truths, labels, gt_count, min(counts))
     _tls.pad_cache = (device, list(targets), [t._version for t in targets], out)
     return out

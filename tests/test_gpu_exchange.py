@@ -77,3 +77,54 @@ def test_pack_scatter_capacity_and_arguments():
     bad = (ctypes.c_void_p * 1)(buf.data_ptr() + 16)
     assert lib().rd_pack_scatter(ptr(counts), ptr(dets), B, C, max_out, ptr(offsets), bad, 1, 0, B, capacity,
                                  stream_ptr()) == _ffi.RD_ERR_ALIGNMENT
+
+
+def test_exchange_round_single_rank_and_replay():
+    """rd_exchange_round (pack + copy + folded rendezvous) with world = 1: rounds alternate between the two slot
+    parities, the epoch lives on the device, so the launch pair can be replayed from a captured plan.  (The
+    multi-rank rendezvous spins on flags other GPUs write: it is exercised by tools/exchange_check.py under torchrun,
+    never by several emulated ranks on one GPU.)"""
+    import refinedet.pytorch_b200 as rd
+    from refinedet.pytorch_b200 import dist as rdist
+    from refinedet.pytorch_b200._ffi import check, lib, ptr, stream_ptr
+    from refinedet.pytorch_b200.layers.functions.detection_refinedet import DetectPlan
+    C, size, keep = 21, '320', 500
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward().cuda()
+    det = rd.Detect_RefineDet(C, int(size), 0, 1000, 0.01, 0.45, 0.01, keep)
+    scale = np.array([float(size)] * 4, np.float32)
+    B = 3
+    results = [det.detect(*[t.cuda() for t in gen.detect_inputs(910 + k, B, priors.shape[0], C, 'sparse', arm_shift=-5.0)],
+                          priors, scale=scale) for k in range(3)]
+    capacity = B * C * keep
+    slot_bytes = int(lib().rd_exchange_slot_bytes(B, C, capacity))
+    ctrl_bytes = int(lib().rd_exchange_ctrl_bytes())
+    assert ctrl_bytes == 1024
+    buf = torch.zeros(ctrl_bytes + 2 * slot_bytes, dtype=torch.uint8, device='cuda')
+    bases = (ctypes.c_void_p * 1)(buf.data_ptr())
+
+    def one_round(res):
+        check(lib().rd_exchange_round(ptr(res.counts), ptr(res.dets), B, C, keep, bases, None, 1, 0, B, capacity, 0, 2000,
+                                      stream_ptr()), 'rd_exchange_round')
+
+    def latest():
+        ctrl = buf[:ctrl_bytes].view(torch.int32).cpu()
+        epoch = int(ctrl[64])
+        assert int(ctrl[66]) == 0 and int(ctrl[0]) == epoch               # no timeout; own flag = epoch
+        half = buf[ctrl_bytes + (epoch & 1) * slot_bytes:ctrl_bytes + ((epoch & 1) + 1) * slot_bytes]
+        counts_all, rows_all = rdist.decode_slots(half, 1, slot_bytes, B * C)
+        assert int(half[:32].view(torch.int32)[4]) == epoch
+        return epoch, counts_all[0], rows_all[0]
+
+    for k, res in enumerate(results):
+        one_round(res)
+        epoch, counts, rows = latest()
+        assert epoch == k + 1
+        _, exp_rows = res.packed()
+        assert torch.equal(counts, res.counts) and torch.equal(rows, exp_rows)
+    # captured once, replayed: the epoch advances on the device
+    plan = DetectPlan.capture(torch.device('cuda', torch.cuda.current_device()), lambda: one_round(results[0]))
+    for k in range(3):
+        plan.launch()
+        epoch, counts, rows = latest()
+        assert epoch == 4 + k
+        assert torch.equal(rows, results[0].packed()[1])

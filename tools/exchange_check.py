@@ -70,15 +70,12 @@ def main():
     ok_all = True
     try:
         for mode in ('p2p', 'multicast'):
-            for ctas in ((8, 16, 24, 48) if mode == 'p2p' else (24, 48, 96, 148)):
+            for ctas in ((1, 2, 4, 8, 16, -24, -48) if mode == 'p2p' else (24, 48, 96, 148)):     # p2p: n > 0 TMA CTAs per peer, n < 0 LSU CTAs
                 try:
                     ex = rdist.PeerExchange(B, C, res.dets.shape[2], dev, mode=mode, copy_ctas=ctas)
                 except RuntimeError as e:
                     out['sweep'].append({'mode': mode, 'error': repr(e)[:120]})
                     break
-                ex.buf.zero_()
-                torch.cuda.synchronize()
-                dist.barrier()
                 ex.exchange(res)
                 counts_p, rows_p = ex.result()
                 ok = all(torch.equal(counts_p[r], counts_n[r]) and torch.equal(rows_p[r], rows_n[r]) for r in range(world))
