@@ -482,6 +482,7 @@ constexpr int kGraphPairCap = 2048;
 
 struct GraphSmem {
     float x1[kBlockNodes], y1[kBlockNodes], x2[kBlockNodes], y2[kBlockNodes];
+    float area[kBlockNodes];         // box area in the flavour of the IoU (the area-ratio pre-test of the item loop)
     uint32_t cr[kBlockNodes];
     uint32_t tab[4 * kCols * kBlockWS];
     uint32_t pairs[kGraphPairCap];
@@ -542,6 +543,15 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
     const uint32_t* Sy = G.tab + 2 * kCols * kBlockWS;
     const uint32_t* Ey = G.tab + 3 * kCols * kBlockWS;
     static_assert(kGraphSplit == 16, "item enumeration assumes 2 own nodes per 32-node word");
+    const bool pixel = (flags & RD_NMS_PIXEL_PLUS1) != 0;
+    // Area-ratio pre-test.  The intersection of two boxes is at most the smaller area and their union at least the
+    // larger one, so IoU <= min(a_i, a_j) / max(a_i, a_j): a bin-surviving pair whose ratio is below the threshold
+    // (with a 2^-12 margin, far above the rounding of the fp32 IoU) cannot be an edge and is neither listed nor
+    // tested.  Anchors come in scales a factor 2 apart (areas a factor 4), so most pairs a large box forms with the
+    // small boxes under it go this way.  Only for positive finite areas; never when the cull is disabled.  Used for
+    // images of more than one block of nodes only: measured, it takes 10 % off graph_kernel at 1.9 - 3.9 k nodes per
+    // image (208 -> 185 us) but ADDS 1 us at the 700 nodes of the headline workload, where few pairs survive the bins.
+    const float ratio_thr = cull_disabled(thr, flags) ? -1.0f : thr * (1.0f - 2.44140625e-4f);
     if (tid == 0) G.overflow = 0;
     for (int n0 = 0; n0 < (kSingle ? 1 : N); n0 += kBlockNodes) {
         const int nb = kSingle ? N : min(kBlockNodes, N - n0);             // suppressor candidates i = n0 .. n0 + nb - 1
@@ -552,6 +562,7 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
         for (int i = tid; i < nb; i += kGraphThreads) {
             const float4 bx = boxes[n0 + i];
             G.x1[i] = bx.x; G.y1[i] = bx.y; G.x2[i] = bx.z; G.y2[i] = bx.w;
+            if (!kSingle) G.area[i] = box_area(bx.x, bx.y, bx.z, bx.w, pixel);
             G.cr[i] = crs[n0 + i];
         }
         // 2. inclusive prefix-OR over the bins, straight from the global marks.  One (table, word) column per
@@ -600,6 +611,19 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
                     Sy[((cr >> 24) & 255u) * kBlockWS + w] & ~Ey[((cr >> 16) & 255u) * kBlockWS + w];
                 const int jl = g + jo * kGraphSplit;                             // j - n0
                 if (w == (jl >> 5)) h &= (1u << (jl & 31)) - 1u;                 // predecessors only
+                if (!kSingle && h && ratio_thr > 0.0f) {
+                    float aj;
+                    if (jl < nb) aj = G.area[jl];
+                    else { const float4 bj = __ldg(boxes + n0 + jl); aj = box_area(bj.x, bj.y, bj.z, bj.w, pixel); }
+                    uint32_t rest = h;
+                    while (rest) {
+                        const int bit = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        const float ai = G.area[(w << 5) + bit];
+                        const float lo = fminf(ai, aj), hi = fmaxf(ai, aj);
+                        if (lo > 0.0f && lo < ratio_thr * hi) h &= ~(1u << bit);
+                    }
+                }
             }
             // reserve list slots: one shared-memory atomic per item that has pairs (list order is irrelevant);
             // pairs that do not fit the list any more are tested on the spot
