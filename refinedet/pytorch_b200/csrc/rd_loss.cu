@@ -28,6 +28,15 @@ constexpr int kLossThreads = 256;
 constexpr int kLossMaxClasses = 128;
 constexpr float kLog2e = 1.4426950408889634f;
 
+// 2^x for x <= 0 (max-subtracted logits, log-probabilities): the bare MUFU.EX2.  exp2f() wraps the same instruction in
+// a range test and two predicated multiplies that only matter for results below 2^-126 -- here those are terms of a
+// sum that is >= 1 (or gradients below 1e-38), and the wrapper was 40 % of conf_loss_tma_kernel's instructions.
+__device__ __forceinline__ float exp2_nonpos(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // softmax(arm_conf)[1] <= theta (refinedet_multibox_loss.py:98-101), fp32, max-subtracted like F.softmax
 __device__ __forceinline__ bool arm_filtered(float2 a, float theta) {
     const float m = fmaxf(a.x, a.y);
@@ -56,10 +65,10 @@ __device__ __forceinline__ void conf_row(const float* __restrict__ x, int C, lon
     const float m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;       // exp(x - m) = exp2((x - m) log2 e): one MUFU.EX2, rel. error < 2e-7
     for (c = 0; c + 4 <= C; c += 4) {
-        s0 += exp2f((x[c] - m) * kLog2e); s1 += exp2f((x[c + 1] - m) * kLog2e);
-        s2 += exp2f((x[c + 2] - m) * kLog2e); s3 += exp2f((x[c + 3] - m) * kLog2e);
+        s0 += exp2_nonpos((x[c] - m) * kLog2e); s1 += exp2_nonpos((x[c + 1] - m) * kLog2e);
+        s2 += exp2_nonpos((x[c + 2] - m) * kLog2e); s3 += exp2_nonpos((x[c + 3] - m) * kLog2e);
     }
-    for (; c < C; ++c) s0 += exp2f((x[c] - m) * kLog2e);
+    for (; c < C; ++c) s0 += exp2_nonpos((x[c] - m) * kLog2e);
     const float sum = (s0 + s1) + (s2 + s3);
     const float lse = logf(sum) + m;
     // a label outside [0, C) (dataset / num_classes mismatch) makes the reference's gather raise; here the
@@ -217,10 +226,10 @@ __device__ __forceinline__ void conf_row_pair(const float* __restrict__ x, int C
     m = fmaxf(m, __shfl_xor_sync(kFullMask, m, 1));
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     for (k = 0; k + 4 <= n; k += 4) {
-        s0 += exp2f((xh[2 * k] - m) * kLog2e); s1 += exp2f((xh[2 * k + 2] - m) * kLog2e);
-        s2 += exp2f((xh[2 * k + 4] - m) * kLog2e); s3 += exp2f((xh[2 * k + 6] - m) * kLog2e);
+        s0 += exp2_nonpos((xh[2 * k] - m) * kLog2e); s1 += exp2_nonpos((xh[2 * k + 2] - m) * kLog2e);
+        s2 += exp2_nonpos((xh[2 * k + 4] - m) * kLog2e); s3 += exp2_nonpos((xh[2 * k + 6] - m) * kLog2e);
     }
-    for (; k < n; ++k) s0 += exp2f((xh[2 * k] - m) * kLog2e);
+    for (; k < n; ++k) s0 += exp2_nonpos((xh[2 * k] - m) * kLog2e);
     float sum = (s0 + s1) + (s2 + s3);
     sum += __shfl_xor_sync(kFullMask, sum, 1);
     if (h != 0) return;
@@ -259,7 +268,7 @@ __device__ __forceinline__ void conf_row_pair_regs(const float* __restrict__ x, 
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
     for (int k = 0; k < kN; ++k) {
-        const float e = exp2f(__fmaf_rn(v[k], kLog2e, nm2));             // a padded -inf contributes exp2(-inf) = 0
+        const float e = exp2_nonpos(__fmaf_rn(v[k], kLog2e, nm2));             // a padded -inf contributes exp2(-inf) = 0
         if ((k & 3) == 0) s0 += e;
         else if ((k & 3) == 1) s1 += e;
         else if ((k & 3) == 2) s2 += e;
@@ -562,7 +571,7 @@ loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ 
 #pragma unroll
                 for (int sgm = 0; sgm < 4; ++sgm) {
                     const int c = sgm * 32 + lane;
-                    if (sgm < nseg && c < C) g[c] = (exp2f((xs[u][sgm] - ls[u]) * kLog2e) - (c == ts[u] ? 1.f : 0.f)) * sc;
+                    if (sgm < nseg && c < C) g[c] = (exp2_nonpos((xs[u][sgm] - ls[u]) * kLog2e) - (c == ts[u] ? 1.f : 0.f)) * sc;
                 }
             }
         }
@@ -577,7 +586,7 @@ loss_backward_kernel(const float4* __restrict__ loc, const float4* __restrict__ 
 #pragma unroll
             for (int sgm = 0; sgm < 4; ++sgm) {
                 const int c = sgm * 32 + lane;
-                if (sgm < nseg && c < C) g[c] = (exp2f((x[c] - l) * kLog2e) - (c == t ? 1.f : 0.f)) * sc;
+                if (sgm < nseg && c < C) g[c] = (exp2_nonpos((x[c] - l) * kLog2e) - (c == t ? 1.f : 0.f)) * sc;
             }
         }
     }
@@ -689,8 +698,8 @@ loss_backward_tma_kernel(const float4* __restrict__ loc, const float4* __restric
             for (int sgm = 0; sgm < 4; ++sgm) {
                 const int c = sgm * 32 + lane;
                 if (sgm < nseg && c < C) {
-                    g_tile[ra * C + c] = (exp2f((xa[sgm] - la) * kLog2e) - (c == ta ? 1.f : 0.f)) * sc;
-                    if (rb >= 0) g_tile[rb * C + c] = (exp2f((xb[sgm] - lb) * kLog2e) - (c == tb ? 1.f : 0.f)) * sc;
+                    g_tile[ra * C + c] = (exp2_nonpos((xa[sgm] - la) * kLog2e) - (c == ta ? 1.f : 0.f)) * sc;
+                    if (rb >= 0) g_tile[rb * C + c] = (exp2_nonpos((xb[sgm] - lb) * kLog2e) - (c == tb ? 1.f : 0.f)) * sc;
                 }
             }
         }
@@ -710,6 +719,207 @@ loss_backward_tma_kernel(const float4* __restrict__ loc, const float4* __restric
         pf = pf_n; nf = nf_n;
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // shared memory stays alive until the stores have read it
+}
+
+// ---- zero-stream variant of the backward (any C, 16-byte aligned grad_conf; the default).  grad_conf is 94 % zeros:
+// they leave as bulk asynchronous stores (cp.async.bulk.global.shared::cta, SASS UBLKCP) from ONE constant 16 KB
+// block of zeros in shared memory -- nothing is built, re-zeroed or waited for on that stream: lane 0 of the last warp
+// keeps kZsDepth + 1 tiles in flight and publishes in `s_done` how many of this CTA's tiles have LANDED (wait_group
+// without .read).  135 MB of zeros alone take 33 us this way (tools/zero_bw.cu: memset 29 us, 16-byte stores 31-33 us).
+// The other eight warps do every READ of the CTA up front, while the write queues are still short (a load issued
+// behind 100 MB of queued zeros takes several us -- the first version, which fetched flags and rows tile by tile,
+// spent 53 us, 60 % of its stall samples waiting for those loads):
+//   1. flags of all rows of the CTA's tiles (thread = row, four independent rows per thread), loc gradient, list of
+//      the selected rows (pos | neg, ~6 %) in shared memory;
+//   2. softmax - onehot of the listed rows (warp = row, lane = class, four rows in flight per warp) into a staging
+//      area in shared memory;
+//   3. staged rows written over the zeros of their tile once it has landed.
+// Rows beyond the staging area (a CTA with more than kZsStageBytes of selected rows) are fetched and written one by
+// one after their tile has landed.  (The tile variant above builds every 64-row tile in shared memory between four
+// barriers: 38 us under ncu, IPC 0.78.)
+constexpr int kZsRowWarps = 8;
+constexpr int kZsRowThreads = 32 * kZsRowWarps;
+constexpr int kZsThreads = kZsRowThreads + 32;
+constexpr int kZsZeroBytes = 16 * 1024;
+constexpr int kZsDepth = 1;                  // + the tile being issued: with three CTAs per SM >= 330 KB of stores in flight per SM
+constexpr int kZsList = 2048;                // rows of one round (a round = as many tiles as fit)
+constexpr int kZsStageBytes = 40 * 1024;
+
+__device__ __forceinline__ void zs_row_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kZsRowThreads) : "memory"); }
+
+__global__ void __launch_bounds__(kZsThreads)
+loss_backward_zs_kernel(const float4* __restrict__ loc, const float4* __restrict__ loc_t,
+                        const float* __restrict__ conf, const long long* __restrict__ conf_t,
+                        const float* __restrict__ lse, const unsigned char* __restrict__ pos,
+                        const unsigned char* __restrict__ neg, const float* __restrict__ g_l,
+                        const float* __restrict__ g_c, const float* __restrict__ n_dev, long long rows, int C,
+                        int groups_per_tile, float4* __restrict__ grad_loc, float* __restrict__ grad_conf) {
+    extern __shared__ __align__(128) unsigned char s_zs[];   // [zeros kZsZeroBytes | staging kZsStageBytes]
+    __shared__ unsigned int s_list[kZsList];                 // (tile of this CTA << 16) | row in the tile
+    __shared__ int s_n, s_done;                              // listed rows; tiles of this CTA whose zeros have landed
+    unsigned char* s_zero = s_zs;
+    float* s_stage = reinterpret_cast<float*>(s_zs + kZsZeroBytes);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile_rows = 32 * groups_per_tile;              // <= kZsList
+    const long long ntiles = (rows + tile_rows - 1) / tile_rows;
+    const int T = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);       // tiles of this CTA (grid <= ntiles)
+    for (int i = tid; i < kZsZeroBytes / 16; i += kZsThreads) reinterpret_cast<float4*>(s_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) s_done = 0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zeros -> visible to the bulk-copy engine
+    __syncthreads();
+    volatile int* done = &s_done;
+    if (warp == kZsRowWarps) {
+        if (lane != 0 || !grad_conf) return;
+        for (int it = 0; it < T; ++it) {
+            const long long r0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * tile_rows;
+            const long long nelem = min((long long)tile_rows, rows - r0) * C;
+            const size_t bytes = ((size_t)nelem * 4) & ~(size_t)15;
+            unsigned char* dst = reinterpret_cast<unsigned char*>(grad_conf + r0 * C);
+            for (size_t off = 0; off < bytes; off += kZsZeroBytes) {
+                const unsigned n = (unsigned)min((size_t)kZsZeroBytes, bytes - off);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off),
+                             "r"((unsigned)__cvta_generic_to_shared(s_zero)), "r"(n)
+                             : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            for (long long e = (long long)(bytes >> 2); e < nelem; ++e) grad_conf[r0 * C + e] = 0.f;   // < 4 floats, last tile only
+            if (it >= kZsDepth) {
+                asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kZsDepth) : "memory");
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                __threadfence_block();
+                *done = it - kZsDepth + 1;
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // (also: shared memory stays alive until it was read)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence_block();
+        *done = T;
+        return;
+    }
+    const float N = *n_dev;
+    const float sl = (g_l && N > 0.f) ? *g_l / N : 0.f;
+    const float sc = (g_c && N > 0.f) ? *g_c / N : 0.f;
+    const int nseg = (C + 31) >> 5;
+    const int cap = min(kZsList, kZsStageBytes / (4 * C));   // rows the staging area holds
+    const int R = kZsList / tile_rows;                       // tiles per round: the list cannot overflow
+    auto row_of = [&](unsigned int e) {
+        return ((long long)blockIdx.x + (long long)(e >> 16) * gridDim.x) * tile_rows + (long long)(e & 0xffffu);
+    };
+    for (int it0 = 0; it0 < T; it0 += R) {
+        const int it1 = min(T, it0 + R);
+        zs_row_barrier();                                    // the previous round is done with the list and the staging area
+        if (tid == 0) s_n = 0;
+        zs_row_barrier();
+        // 1. flags, loc gradient, list
+        const int round_rows = (it1 - it0) * tile_rows;
+        for (int f0 = 0; f0 < round_rows; f0 += 4 * kZsRowThreads) {
+            unsigned char pf[4], nf[4];
+            long long rr[4];
+            unsigned int ee[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int f = f0 + u * kZsRowThreads + tid;
+                const int itl = f / tile_rows, rit = f - itl * tile_rows;
+                ee[u] = ((unsigned int)(it0 + itl) << 16) | (unsigned int)rit;
+                rr[u] = f < round_rows ? row_of(ee[u]) : rows;
+                pf[u] = 0; nf[u] = 0;
+                if (rr[u] < rows) { pf[u] = pos[rr[u]]; nf[u] = neg[rr[u]]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long r = rr[u];
+                if (r < rows && grad_loc) {
+                    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (pf[u]) {
+                        const float4 x = loc[r], t = loc_t[r];
+                        g.x = fminf(fmaxf(x.x - t.x, -1.f), 1.f) * sl;      // d SmoothL1 / d x = clamp(x - t, -1, 1)
+                        g.y = fminf(fmaxf(x.y - t.y, -1.f), 1.f) * sl;
+                        g.z = fminf(fmaxf(x.z - t.z, -1.f), 1.f) * sl;
+                        g.w = fminf(fmaxf(x.w - t.w, -1.f), 1.f) * sl;
+                    }
+                    grad_loc[r] = g;
+                }
+                const bool sel = grad_conf && (pf[u] | nf[u]) != 0;
+                const unsigned bal = __ballot_sync(kFullMask, sel);
+                if (bal) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_n, __popc(bal));
+                    base = __shfl_sync(kFullMask, base, 0);
+                    if (sel) s_list[base + __popc(bal & ((1u << lane) - 1u))] = ee[u];
+                }
+            }
+        }
+        zs_row_barrier();
+        const int n = s_n, staged = min(n, cap);
+        // 2. the listed rows -> staging area; four rows in flight per warp
+        for (int k0 = 4 * warp; k0 < staged; k0 += 4 * kZsRowWarps) {
+            float xs[4][4], ls[4];
+            int ts[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k0 + u < staged) {
+                    const long long row = row_of(s_list[k0 + u]);
+                    ls[u] = lse[row];
+                    ts[u] = (int)conf_t[row];
+                    const float* x = conf + row * C;
+#pragma unroll
+                    for (int sgm = 0; sgm < 4; ++sgm) {
+                        const int c = sgm * 32 + lane;
+                        xs[u][sgm] = (sgm < nseg && c < C) ? x[c] : 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k0 + u < staged) {
+                    float* g = s_stage + (size_t)(k0 + u) * C;
+#pragma unroll
+                    for (int sgm = 0; sgm < 4; ++sgm) {
+                        const int c = sgm * 32 + lane;
+                        if (sgm < nseg && c < C) g[c] = (exp2_nonpos((xs[u][sgm] - ls[u]) * kLog2e) - (c == ts[u] ? 1.f : 0.f)) * sc;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // 3. staged rows (written by this warp) over the zeros of their tile, once it has landed
+        for (int k0 = 4 * warp; k0 < staged; k0 += 4 * kZsRowWarps) {
+            for (int u = 0; u < 4 && k0 + u < staged; ++u) {
+                const unsigned int e = s_list[k0 + u];
+                while (*done <= (int)(e >> 16)) {}
+                __threadfence_block();
+                float* g = grad_conf + row_of(e) * C;
+                const float* sg = s_stage + (size_t)(k0 + u) * C;
+#pragma unroll
+                for (int sgm = 0; sgm < 4; ++sgm) {
+                    const int c = sgm * 32 + lane;
+                    if (sgm < nseg && c < C) g[c] = sg[c];
+                }
+            }
+        }
+        // 4. rows the staging area could not hold
+        for (int k = cap + warp; k < n; k += kZsRowWarps) {
+            const unsigned int e = s_list[k];
+            const long long row = row_of(e);
+            const float l = lse[row];
+            const int t = (int)conf_t[row];
+            const float* x = conf + row * C;
+            float xv[4];
+#pragma unroll
+            for (int sgm = 0; sgm < 4; ++sgm) {
+                const int c = sgm * 32 + lane;
+                xv[sgm] = (sgm < nseg && c < C) ? x[c] : 0.f;
+            }
+            while (*done <= (int)(e >> 16)) {}
+            __threadfence_block();
+            float* g = grad_conf + row * C;
+#pragma unroll
+            for (int sgm = 0; sgm < 4; ++sgm) {
+                const int c = sgm * 32 + lane;
+                if (sgm < nseg && c < C) g[c] = (exp2_nonpos((xv[sgm] - l) * kLog2e) - (c == t ? 1.f : 0.f)) * sc;
+            }
+        }
+    }
 }
 
 }  // namespace rd
@@ -878,7 +1088,32 @@ int rd_multibox_loss_backward(const float* loc, const float* loc_t, const float*
     if (!grad_loc && !grad_conf) return 0;
     if (C > kLossMaxClasses) return RD_ERR_UNSUPPORTED;
     if (((uintptr_t)loc | (uintptr_t)loc_t | (uintptr_t)grad_loc) & 15) return RD_ERR_ALIGNMENT;
-    if (grad_conf && (C & 1) && ((uintptr_t)grad_conf & 15) == 0 && !getenv("RD_NO_TMA")) {
+    // wide rows (C >= 48, the COCO head): the zero-stream kernel, 43 us against 45 us for the tile kernel at C = 81; at
+    // C = 21 / C = 2 its three phases per CTA are a longer chain than the whole job (33 / 29 us against 26 / 20 us)
+    static const char* s_variant = getenv("RD_BWD");          // "tile" / "regs" / "zs": force a variant (A/B runs)
+    const bool want_zs = s_variant ? s_variant[0] == 'z' : C >= 48;
+    if (((uintptr_t)grad_conf & 15) == 0 && want_zs && !getenv("RD_NO_TMA")) {
+        // tiles of about 80 KB: 8 groups of 32 rows at C = 81, 64 at C = 2
+        long long gpt = (81920 + 64ll * C) / (128ll * C);
+        gpt = gpt < 1 ? 1 : gpt > 64 ? 64 : gpt;
+        const long long ntiles = (rows + 32 * gpt - 1) / (32 * gpt);
+        static const char* s_per_sm = getenv("RD_BWD_PER_SM");
+        const long long per_sm = s_per_sm ? atoll(s_per_sm) : 3;          // resident CTAs per SM (64 KB of shared memory each)
+        const long long waves = (ntiles + 148 * per_sm - 1) / (148 * per_sm);
+        const long long nb = (ntiles + waves - 1) / waves;                // the same number of tiles for every CTA
+        const size_t smem = kZsZeroBytes + kZsStageBytes;
+        static size_t s_zs_smem[kMaxDevices];
+        cudaError_t e = ensure_dynamic_smem(loss_backward_zs_kernel, smem, s_zs_smem);
+        if (e != cudaSuccess) return (int)e;
+        loss_backward_zs_kernel<<<(unsigned)nb, kZsThreads, smem, (cudaStream_t)stream>>>(
+            (const float4*)loc, (const float4*)loc_t, conf, conf_t, lse, pos, neg, grad_loss_l, grad_loss_c, n_dev, rows, C,
+            (int)gpt, (float4*)grad_loc, grad_conf);
+        note_launch();
+        RD_CHECK_LAUNCH();
+        return 0;
+    }
+    if (grad_conf && (C & 1) && ((uintptr_t)grad_conf & 15) == 0 && !getenv("RD_NO_TMA") &&
+        !(s_variant && s_variant[0] == 'r')) {
         const size_t smem = (size_t)2 * kBwdRows * C * sizeof(float);
         static size_t s_bwd_smem[kMaxDevices];
         cudaError_t e = ensure_dynamic_smem(loss_backward_tma_kernel, smem, s_bwd_smem);

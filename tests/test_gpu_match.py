@@ -280,6 +280,23 @@ def test_loss_tail_kernels(rd, B, size, C, G, use_arm):
     assert bool(torch.isfinite(p_conf.grad).all())
 
 
+@pytest.mark.parametrize('variant', ['zs', 'tile', 'regs'])
+def test_loss_backward_variants(variant):
+    """The library picks the backward kernel by the class count (zero-stream for C >= 48, tile for odd C, register
+    stores otherwise); ``RD_BWD`` forces one of them for every shape.  The variable is read once per process, so
+    the stock-PyTorch comparison above (C = 2 / 21 / 81, B up to 32) is re-run in a child process per variant."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RD_BWD=variant)
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_match.py'), '-q', '-x',
+                        '-k', 'test_loss_tail_kernels', '-p', 'no:cacheprovider'],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert '4 passed' in r.stdout, r.stdout[-500:]
+
+
 def test_pad_targets_kernel(rd):
     """rd_pad_targets (detection_collate's ragged list -> padded batch): ragged counts incl. an empty image,
     host and device inputs, the ARM/ODM cache hit and its invalidation by an in-place edit."""
