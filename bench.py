@@ -610,18 +610,22 @@ def main():
         tg = [t.to(dev) for t in synthetic.targets(seed_for(rank, 41), BATCH, 50, C)]
         leaves = [t.clone().requires_grad_(True) for t in tp]
 
-        def make_step(sync_free):
+        def make_step(sync_free, paired=True, read=True):
             arm_crit = rd.RefineDetMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True, sync_free=sync_free)
             odm_crit = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True, sync_free=sync_free)
+            pair = rd.RefineDetCriterionPair(arm_crit, odm_crit)
 
             def one_step():
                 rd.box_utils.clear_pad_cache()                  # a real step brings new targets: pad them once, not zero times
                 preds = (leaves[0], leaves[1], leaves[2], leaves[3], priors)
-                al, ac = arm_crit(preds, tg)
-                ol, oc = odm_crit(preds, tg)
-                (al + ac + ol + oc).backward()                  # train_refinedet.py:252-256
+                if paired:                                      # one call for both criteria (the two chains on two streams)
+                    al, ac, ol, oc = pair(preds, tg)
+                else:                                           # the reference's call sequence, train_refinedet.py:252-253
+                    al, ac = arm_crit(preds, tg)
+                    ol, oc = odm_crit(preds, tg)
+                (al + ac + ol + oc).backward()                  # train_refinedet.py:254-256
                 vals = torch.stack([al.detach().reshape(()), ac.detach().reshape(()), ol.detach().reshape(()),
-                                    oc.detach().reshape(())]).tolist() if sync_free else None   # :258-261 .item()
+                                    oc.detach().reshape(())]).tolist() if (sync_free and read) else None   # :258-261 .item()
                 for t in leaves:
                     t.grad = None
                 return vals
@@ -638,6 +642,8 @@ def main():
             return 1e3 * (time.perf_counter() - t0) / n
         ms_t = wall_ms(make_step(False))
         ms_sf = wall_ms(make_step(True))
+        ms_two = wall_ms(make_step(False, paired=False))
+        ms_two_sf = wall_ms(make_step(True, paired=False))
         # the kernels of the ODM criterion one by one (device time, L2 flushed) against their algorithmic bytes:
         # refine_match 40 P + 20 G per image, conf loss 4 P C + 17 P, mining 6 P, backward 4 P C + 18 P
         bu = rd.box_utils
@@ -673,20 +679,32 @@ def main():
             ms_k = flushed_ms(fn, n=10, flush=flush)
             kernels[name] = {'ms': round(ms_k, 5), 'frac': round(byts / (ms_k * 1e-3) / 1e9 / peak, 4)}
         del conf_rot, gconf_rot, gloc_k
-        # device time of the whole step (events around it, the host runs ahead)
-        step_sf = make_step(True)
-        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        ev_a.record(main_st)
-        for _ in range(10):
-            step_sf()
-        ev_b.record(main_st)
-        torch.cuda.synchronize()
+        # device time of the whole step with the host AHEAD of the GPU, as it is inside a training loop (the criterion is
+        # queued while the network's forward pass still runs): a spin kernel holds the stream while the steps are queued,
+        # nothing is read back in between
+        def device_ms(step, k=6):
+            step()
+            torch.cuda.synchronize()
+            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(int(12e-3 * 1.9e9))              # ~12 ms; the host queues k steps in 3-4 ms
+            ev_a.record(main_st)
+            for _ in range(k):
+                step()
+            ev_b.record(main_st)
+            torch.cuda.synchronize()
+            return ev_a.elapsed_time(ev_b) / k
+        dev_pair = device_ms(make_step(True, read=False))
+        dev_two = device_ms(make_step(True, paired=False, read=False))
         train_step = {'ms_per_step': ms_t, 'value': BATCH / (ms_t * 1e-3), 'sync_free_ms_per_step': ms_sf,
-                      'event_ms_per_step': ev_a.elapsed_time(ev_b) / 10, 'kernels': kernels, 'cpu_baseline': None}
+                      'two_call_ms_per_step': ms_two, 'two_call_sync_free_ms_per_step': ms_two_sf,
+                      'device_ms_per_step': dev_pair, 'two_call_device_ms_per_step': dev_two, 'kernels': kernels,
+                      'cpu_baseline': None}
         del truths_k, labels_k, cnt_k, lt_k, ct_k, ce_k, lse_k, pos_k, neg_k
         detail['train_step'] = 'ARM + ODM RefineDetMultiBoxLoss forward + backward (B=32, P=16320, C=81, 50 GT/image), wall ' \
-                               'clock incl. host glue; sync_free: no host read of N inside the criteria, losses read once'
+                               'clock incl. host glue, through RefineDetCriterionPair (one call for both criteria, N read ' \
+                               'once per step); two_call: the two modules one after the other as train_refinedet.py:252-253; ' \
+                               'sync_free: no host read of N inside the criteria, losses read once; device_ms: GPU time per step when ' \
+                               'the host runs ahead (as inside a training loop), no read-back'
         if not args.no_cpu_baseline:
             try:
                 from baseline import reference_arm as ra

@@ -362,6 +362,33 @@ RD_API int rd_multibox_loss_backward(const float* loc, const float* loc_t, const
                  const float* n_dev, long long rows, int C, float* grad_loc, float* grad_conf,
                  void* stream);
 
+/* ---- the ARM and the ODM criterion of a training step as ONE call (train_refinedet.py:252-253 calls
+ * refinedet_multibox_loss.py:50-139 twice on the same predictions and targets) ------------------------------------
+ * A criterion STATE is one device allocation of rd_criterion_state_bytes(B, P, Gmax) bytes (256-byte aligned) that
+ * holds everything a forward leaves for its backward; rd_criterion_state_layout writes the byte offsets of its
+ * regions: { loc_t f32[B,P,4], conf_t i64[B,P], ce f32[B,P], lse f32[B,P], pos u8[B,P], neg u8[B,P],
+ * num_pos i32[B], losses f32[3] = { loss_l, loss_c, N }, workspace } into offsets[9].
+ *
+ * rd_multibox_criterion_pair: the ARM criterion (use_ARM=False: match against the priors, labels by arm_label_mode,
+ * predictions arm_loc / arm_conf[B,P,2]) on `stream`, the ODM criterion (use_ARM=True: refine_match against
+ * decode(arm_loc), predictions odm_loc / odm_conf[B,P,C], positives gated by softmax(arm_conf)[1] <= theta) on
+ * `side_stream` -- forked from and joined back into `stream` with events, so the two chains of six kernels run
+ * CONCURRENTLY and the caller sees one stream-ordered call.  side_stream == NULL or == stream: one after the other.
+ * rd_multibox_loss_backward_pair: both backward kernels the same way.  g_* are device scalars (NULL = 0), grad_*
+ * outputs may be NULL (that gradient is not needed). */
+RD_API size_t rd_criterion_state_bytes(int B, int P, int Gmax);
+RD_API int rd_criterion_state_layout(int B, int P, int Gmax, size_t* offsets /* [9] */);
+RD_API int rd_multibox_criterion_pair(const float* truths, const float* labels, const int* gt_count,
+                 const float* priors, const float* arm_loc, const float* arm_conf, const float* odm_loc,
+                 const float* odm_conf, int B, int P, int C, int Gmax, float arm_threshold, float odm_threshold,
+                 float v0, float v1, int arm_label_mode, float theta, int arm_negpos_ratio, int odm_negpos_ratio,
+                 void* arm_state, void* odm_state, size_t state_bytes, void* stream, void* side_stream);
+RD_API int rd_multibox_loss_backward_pair(const float* arm_loc, const float* arm_conf, const float* odm_loc,
+                 const float* odm_conf, const void* arm_state, const void* odm_state, int B, int P, int C, int Gmax,
+                 const float* g_arm_l, const float* g_arm_c, const float* g_odm_l, const float* g_odm_c,
+                 float* grad_arm_loc, float* grad_arm_conf, float* grad_odm_loc, float* grad_odm_conf,
+                 void* stream, void* side_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,8 +12,8 @@ from .layers import box_utils  # noqa: F401
 from .layers.functions.detection_refinedet import (Detect_RefineDet, Detections, DetectPlan,  # noqa: F401
                                                          DetectHostPipeline)  # noqa: F401
 from .layers.functions.prior_box import PriorBox, REFINEDET_ANCHORS  # noqa: F401
-from .layers.modules.refinedet_multibox_loss import RefineDetMultiBoxLoss  # noqa: F401
+from .layers.modules.refinedet_multibox_loss import RefineDetMultiBoxLoss, RefineDetCriterionPair  # noqa: F401
 from .utils import nms_wrapper  # noqa: F401
 
-__all__ = ['Detect_RefineDet', 'Detections', 'DetectPlan', 'DetectHostPipeline', 'RefineDetMultiBoxLoss', 'PriorBox', 'REFINEDET_ANCHORS',
+__all__ = ['Detect_RefineDet', 'Detections', 'DetectPlan', 'DetectHostPipeline', 'RefineDetMultiBoxLoss', 'RefineDetCriterionPair', 'PriorBox', 'REFINEDET_ANCHORS',
            'box_utils', 'nms_wrapper']

@@ -91,6 +91,11 @@ _SIGNATURES = {
     'rd_multibox_criterion': (c_int, [_P] * 8 + [c_int] * 4 + [c_float] * 3 + [c_int, c_float, c_int, _P, c_size_t] + [_P] * 9),
     'rd_multibox_loss_backward': (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, ctypes.c_longlong, c_int,
                                           _P, _P, _P]),
+    'rd_criterion_state_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'rd_criterion_state_layout': (c_int, [c_int, c_int, c_int, _P]),
+    'rd_multibox_criterion_pair': (c_int, [_P] * 8 + [c_int] * 4 + [c_float] * 4 + [c_int, c_float, c_int, c_int] +
+                                   [_P, _P, c_size_t, _P, _P]),
+    'rd_multibox_loss_backward_pair': (c_int, [_P] * 6 + [c_int] * 4 + [_P] * 10),
 }
 
 _lib = None

@@ -1141,4 +1141,140 @@ int rd_multibox_loss_backward(const float* loc, const float* loc_t, const float*
     return 0;
 }
 
+// ---- both criteria of a training step as one call ----------------------------------------------------------------
+struct CriterionState {
+    float* loc_t; long long* conf_t; float* ce; float* lse; unsigned char* pos; unsigned char* neg; int* num_pos;
+    float* losses; void* ws;
+    size_t ws_bytes, total;
+    size_t off[9];
+};
+static CriterionState carve_state(void* base, int B, int P, int Gmax) {
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t n = (size_t)B * P;
+    const size_t widths[6] = {16, 8, 4, 4, 1, 1};
+    CriterionState s;
+    size_t o = 0;
+    for (int i = 0; i < 6; ++i) { s.off[i] = o; o += up(n * widths[i]); }
+    s.off[6] = o; o += up((size_t)B * 4);
+    s.off[7] = o; o += 256;
+    s.off[8] = o;
+    s.ws_bytes = carve_criterion(nullptr, B, P, Gmax).total;
+    s.total = o + s.ws_bytes;
+    unsigned char* p = static_cast<unsigned char*>(base);
+    s.loc_t = reinterpret_cast<float*>(p + s.off[0]);
+    s.conf_t = reinterpret_cast<long long*>(p + s.off[1]);
+    s.ce = reinterpret_cast<float*>(p + s.off[2]);
+    s.lse = reinterpret_cast<float*>(p + s.off[3]);
+    s.pos = p + s.off[4];
+    s.neg = p + s.off[5];
+    s.num_pos = reinterpret_cast<int*>(p + s.off[6]);
+    s.losses = reinterpret_cast<float*>(p + s.off[7]);
+    s.ws = p + s.off[8];
+    return s;
+}
+
+// fork / join of the side stream: two events per (thread, device), created once.  Re-recording an event does not
+// disturb a wait that was enqueued on its earlier record, so the pair is reused by every call of the thread.
+struct ForkJoin {
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static cudaError_t fork_join_events(ForkJoin** out) {
+    static thread_local ForkJoin tl[kMaxDevices];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    ForkJoin& fj = tl[(unsigned)dev % kMaxDevices];
+    if (!fj.fork) {
+        e = cudaEventCreateWithFlags(&fj.fork, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+        e = cudaEventCreateWithFlags(&fj.join, cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    *out = &fj;
+    return cudaSuccess;
+}
+
+size_t rd_criterion_state_bytes(int B, int P, int Gmax) {
+    if (B <= 0 || P <= 0 || Gmax <= 0) return 0;
+    return carve_state(nullptr, B, P, Gmax).total;
+}
+
+int rd_criterion_state_layout(int B, int P, int Gmax, size_t* offsets) {
+    if (B <= 0 || P <= 0 || Gmax <= 0 || !offsets) return RD_ERR_BAD_ARG;
+    const CriterionState s = carve_state(nullptr, B, P, Gmax);
+    for (int i = 0; i < 9; ++i) offsets[i] = s.off[i];
+    return 0;
+}
+
+int rd_multibox_criterion_pair(const float* truths, const float* labels, const int* gt_count, const float* priors,
+                               const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
+                               int B, int P, int C, int Gmax, float arm_threshold, float odm_threshold, float v0, float v1,
+                               int arm_label_mode, float theta, int arm_negpos_ratio, int odm_negpos_ratio,
+                               void* arm_state, void* odm_state, size_t state_bytes, void* stream, void* side_stream) {
+    NvtxRange nvtx_range("rd_multibox_criterion_pair");
+    if (!arm_loc || !arm_conf || !odm_loc || !odm_conf || !arm_state || !odm_state || B <= 0 || P <= 0 || Gmax <= 0)
+        return RD_ERR_BAD_ARG;
+    if (((uintptr_t)arm_state | (uintptr_t)odm_state) & 255) return RD_ERR_ALIGNMENT;
+    const CriterionState a = carve_state(arm_state, B, P, Gmax), o = carve_state(odm_state, B, P, Gmax);
+    if (state_bytes < a.total) return RD_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream, side = (cudaStream_t)side_stream;
+    const bool two = side && side != st;
+    ForkJoin* fj = nullptr;
+    if (two) {
+        cudaError_t e = fork_join_events(&fj);
+        if (e == cudaSuccess) e = cudaEventRecord(fj->fork, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, fj->fork, 0);
+        if (e != cudaSuccess) return (int)e;
+    }
+    // the ODM chain is the long one (the C-class confidence loss): it is issued first
+    int rc = rd_multibox_criterion(truths, labels, gt_count, priors, arm_loc, odm_loc, odm_conf, arm_conf, B, P, C, Gmax,
+                                   odm_threshold, v0, v1, 0 /* labels as they are */, theta, odm_negpos_ratio, o.ws, o.ws_bytes,
+                                   o.loc_t, o.conf_t, o.ce, o.lse, o.pos, o.neg, o.num_pos, o.losses, two ? side : st);
+    int rc2 = rd_multibox_criterion(truths, labels, gt_count, priors, nullptr, arm_loc, arm_conf, nullptr, B, P, 2, Gmax,
+                                    arm_threshold, v0, v1, arm_label_mode, theta, arm_negpos_ratio, a.ws, a.ws_bytes, a.loc_t,
+                                    a.conf_t, a.ce, a.lse, a.pos, a.neg, a.num_pos, a.losses, st);
+    if (two) {                                               // joined even after an error: `stream` stays ordered behind `side`
+        cudaError_t e = cudaEventRecord(fj->join, side);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, fj->join, 0);
+        if (e != cudaSuccess && rc == 0 && rc2 == 0) return (int)e;
+    }
+    return rc != 0 ? rc : rc2;
+}
+
+int rd_multibox_loss_backward_pair(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
+                                   const void* arm_state, const void* odm_state, int B, int P, int C, int Gmax,
+                                   const float* g_arm_l, const float* g_arm_c, const float* g_odm_l, const float* g_odm_c,
+                                   float* grad_arm_loc, float* grad_arm_conf, float* grad_odm_loc, float* grad_odm_conf,
+                                   void* stream, void* side_stream) {
+    NvtxRange nvtx_range("rd_multibox_loss_backward_pair");
+    if (!arm_loc || !arm_conf || !odm_loc || !odm_conf || !arm_state || !odm_state || B <= 0 || P <= 0 || Gmax <= 0)
+        return RD_ERR_BAD_ARG;
+    const CriterionState a = carve_state(const_cast<void*>(arm_state), B, P, Gmax);
+    const CriterionState o = carve_state(const_cast<void*>(odm_state), B, P, Gmax);
+    cudaStream_t st = (cudaStream_t)stream, side = (cudaStream_t)side_stream;
+    const bool need_arm = grad_arm_loc || grad_arm_conf, need_odm = grad_odm_loc || grad_odm_conf;
+    const bool two = side && side != st && need_arm && need_odm;
+    ForkJoin* fj = nullptr;
+    if (two) {
+        cudaError_t e = fork_join_events(&fj);
+        if (e == cudaSuccess) e = cudaEventRecord(fj->fork, st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, fj->fork, 0);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const long long rows = (long long)B * P;
+    int rc = 0, rc2 = 0;
+    if (need_odm)
+        rc = rd_multibox_loss_backward(odm_loc, o.loc_t, odm_conf, o.conf_t, o.lse, o.pos, o.neg, g_odm_l, g_odm_c, o.losses + 2,
+                                       rows, C, grad_odm_loc, grad_odm_conf, st);
+    if (need_arm)
+        rc2 = rd_multibox_loss_backward(arm_loc, a.loc_t, arm_conf, a.conf_t, a.lse, a.pos, a.neg, g_arm_l, g_arm_c, a.losses + 2,
+                                        rows, 2, grad_arm_loc, grad_arm_conf, two ? side : st);
+    if (two) {
+        cudaError_t e = cudaEventRecord(fj->join, side);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, fj->join, 0);
+        if (e != cudaSuccess && rc == 0 && rc2 == 0) return (int)e;
+    }
+    return rc != 0 ? rc : rc2;
+}
+
 }  // extern "C"

@@ -1,3 +1,3 @@
-from .refinedet_multibox_loss import RefineDetMultiBoxLoss
+from .refinedet_multibox_loss import RefineDetMultiBoxLoss, RefineDetCriterionPair
 
-__all__ = ['RefineDetMultiBoxLoss']
+__all__ = ['RefineDetMultiBoxLoss', 'RefineDetCriterionPair']

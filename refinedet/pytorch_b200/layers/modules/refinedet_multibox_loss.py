@@ -6,6 +6,9 @@ sort of the hard-negative mining (:119-123) one radix-select kernel, and the los
 kernels forward and one backward behind a ``torch.autograd.Function`` — ``conf_data`` is read once
 forward and only on the ``pos | neg`` rows backward.
 """
+import ctypes
+import threading
+
 import torch
 import torch.nn as nn
 
@@ -193,3 +196,172 @@ class _Criterion(torch.autograd.Function):
                                                   st.B * st.P, conf_c.shape[-1], ptr(grad_loc), ptr(grad_conf), stream_ptr()),
                   'rd_multibox_loss_backward')
         return (grad_loc, grad_conf) + (None,) * 12
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# both criteria of a training step in one call
+# ---------------------------------------------------------------------------------------------------------------
+_tls = threading.local()
+_STATE_FIELDS = ('loc_t', 'conf_t', 'ce', 'lse', 'pos', 'neg', 'num_pos', 'losses', 'ws')
+_layouts = {}
+
+
+def _state_layout(B, P, G):
+    """``(state_bytes, {field: offset})`` of one criterion state (``rd_criterion_state_layout``), cached per shape."""
+    key = (B, P, G)
+    lay = _layouts.get(key)
+    if lay is None:
+        offs = (ctypes.c_size_t * 9)()
+        check(lib().rd_criterion_state_layout(B, P, G, offs), 'rd_criterion_state_layout')
+        lay = _layouts[key] = (int(lib().rd_criterion_state_bytes(B, P, G)), dict(zip(_STATE_FIELDS, [int(o) for o in offs])))
+    return lay
+
+
+def _side_stream(device):
+    """This thread's side stream on ``device`` (the ODM chain of a pair runs there, forked from the current stream)."""
+    streams = getattr(_tls, 'side', None)
+    if streams is None:
+        streams = _tls.side = {}
+    st = streams.get(device.index)
+    if st is None:
+        st = streams[device.index] = torch.cuda.Stream(device=device)
+    return st
+
+
+class _PairState(object):
+    """The states of the ARM and the ODM criterion of one step: ONE device allocation ``[arm state | odm state]``."""
+    __slots__ = ('buf', 'off', 'nbytes', 'B', 'P', 'G')
+    _WIDTH = {'loc_t': 16, 'conf_t': 8, 'ce': 4, 'lse': 4, 'pos': 1, 'neg': 1}
+
+    def allocate(self, B, P, G, device):
+        self.B, self.P, self.G = B, P, G
+        self.nbytes, self.off = _state_layout(B, P, G)
+        self.buf = torch.empty(2 * self.nbytes, dtype=torch.uint8, device=device)
+
+    def base(self, which):
+        return self.buf.data_ptr() + which * self.nbytes
+
+    def losses(self, which):
+        o = which * self.nbytes + self.off['losses']
+        return self.buf[o:o + 12].view(torch.float32)
+
+    def view(self, which, name, dtype, inner=None):
+        o = which * self.nbytes + self.off[name]
+        t = self.buf[o:o + self.B * self.P * self._WIDTH[name]].view(dtype)
+        return t.view(self.B, self.P, inner) if inner else t.view(self.B, self.P)
+
+
+class _CriterionPair(torch.autograd.Function):
+    """train_refinedet.py:252-253 on the device: forward = rd_multibox_criterion_pair (twelve kernels, the two chains
+    on two streams), backward = rd_multibox_loss_backward_pair.  Differentiable in the four prediction tensors."""
+
+    @staticmethod
+    def forward(ctx, arm_loc, arm_conf, odm_loc, odm_conf, state, truths, labels, gt_count, priors, arm_threshold,
+                odm_threshold, variance, arm_mode, theta, arm_negpos, odm_negpos, concurrent):
+        arm_loc_c = require_cuda_f32(arm_loc, 'arm_loc_data')
+        arm_conf_c = require_cuda_f32(arm_conf, 'arm_conf_data', align=8)
+        odm_loc_c = require_cuda_f32(odm_loc, 'odm_loc_data')
+        odm_conf_c = require_cuda_f32(odm_conf, 'odm_conf_data', align=8)
+        priors = require_cuda_f32(priors, 'priors')
+        B, P = odm_loc_c.shape[0], odm_loc_c.shape[1]
+        C = odm_conf_c.shape[-1]
+        G = truths.shape[1]
+        if (arm_loc_c.numel() != B * P * 4 or arm_conf_c.numel() != B * P * 2 or odm_conf_c.numel() != B * P * C
+                or priors.shape[0] != P):
+            raise ValueError('predictions must be arm_loc [B,P,4], arm_conf [B,P,2], odm_loc [B,P,4], odm_conf [B,P,C], '
+                             'priors [P,4]')
+        dev = odm_loc_c.device
+        state.allocate(B, P, G, dev)
+        with on_device(dev):
+            side = c_void_p(_side_stream(dev).cuda_stream) if concurrent else c_void_p(0)
+            check(lib().rd_multibox_criterion_pair(
+                ptr(truths), ptr(labels), ptr(gt_count), ptr(priors), ptr(arm_loc_c), ptr(arm_conf_c), ptr(odm_loc_c),
+                ptr(odm_conf_c), B, P, C, G, arm_threshold, odm_threshold, float(variance[0]), float(variance[1]), arm_mode,
+                theta, arm_negpos, odm_negpos, c_void_p(state.base(0)), c_void_p(state.base(1)), state.nbytes, stream_ptr(),
+                side), 'rd_multibox_criterion_pair')
+        al, ac, an = state.losses(0).unbind(0)
+        ol, oc, on = state.losses(1).unbind(0)
+        ctx.save_for_backward(arm_loc_c, arm_conf_c, odm_loc_c, odm_conf_c)
+        ctx.state, ctx.keep, ctx.concurrent = state, (truths, labels, gt_count, priors), concurrent
+        ctx.mark_non_differentiable(an, on)
+        return al, ac, an, ol, oc, on
+
+    @staticmethod
+    def backward(ctx, g_al, g_ac, _g_an, g_ol, g_oc, _g_on):
+        arm_loc_c, arm_conf_c, odm_loc_c, odm_conf_c = ctx.saved_tensors
+        st = ctx.state
+        gs = [g.contiguous().float() if g is not None else None for g in (g_al, g_ac, g_ol, g_oc)]
+        outs = [torch.empty_like(t) if need else None
+                for t, need in zip((arm_loc_c, arm_conf_c, odm_loc_c, odm_conf_c), ctx.needs_input_grad[:4])]
+        dev = odm_conf_c.device
+        with on_device(dev):
+            side = c_void_p(_side_stream(dev).cuda_stream) if ctx.concurrent else c_void_p(0)
+            check(lib().rd_multibox_loss_backward_pair(
+                ptr(arm_loc_c), ptr(arm_conf_c), ptr(odm_loc_c), ptr(odm_conf_c), c_void_p(st.base(0)), c_void_p(st.base(1)),
+                st.B, st.P, odm_conf_c.shape[-1], st.G, ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(gs[3]), ptr(outs[0]),
+                ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), stream_ptr(), side), 'rd_multibox_loss_backward_pair')
+        return tuple(outs) + (None,) * 13
+
+
+class RefineDetCriterionPair(nn.Module):
+    """The ARM and the ODM criterion of a RefineDet training step in ONE call (extension; the reference calls its two
+    ``RefineDetMultiBoxLoss`` modules one after the other on the same ``(predictions, targets)``,
+    ``train_refinedet.py:252-253``):
+
+        pair = RefineDetCriterionPair(arm_criterion, odm_criterion)
+        arm_loss_l, arm_loss_c, odm_loss_l, odm_loss_c = pair(out, targets)
+
+    One native call forward (``rd_multibox_criterion_pair``: targets padded once, the two kernel chains run
+    concurrently on two streams) and one backward, one ``autograd.Function`` instead of two.  Values and gradients are
+    those of the two modules called separately (the same kernels on the same inputs).  When either module has
+    ``sync_free=False`` the two ``N`` are read after both chains were queued (one wait for the step instead of two in
+    the middle of it) and a criterion with ``N < 1`` returns the reference's ``(zeros(1), zeros(1))`` (:135-136)."""
+
+    def __init__(self, arm_criterion, odm_criterion, concurrent=True):
+        super(RefineDetCriterionPair, self).__init__()
+        if arm_criterion.use_ARM or not odm_criterion.use_ARM:
+            raise ValueError('RefineDetCriterionPair(arm_criterion [use_ARM=False], odm_criterion [use_ARM=True])')
+        if arm_criterion.num_classes != 2:
+            raise ValueError('the ARM criterion of a pair is the binary one (num_classes=2, train_refinedet.py:124)')
+        self.arm_criterion, self.odm_criterion = arm_criterion, odm_criterion
+        self.concurrent = bool(concurrent)
+        self.sync_free = arm_criterion.sync_free and odm_criterion.sync_free
+
+    def forward(self, predictions, targets):
+        arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, priors = predictions
+        if not odm_loc_data.is_cuda:
+            raise RuntimeError('RefineDetCriterionPair: predictions must be CUDA tensors '
+                               '(refinedet.pytorch_b200 has no CPU fallback)')
+        a, o = self.arm_criterion, self.odm_criterion
+        if odm_conf_data.shape[-1] != o.num_classes:
+            raise ValueError('odm_conf_data has %d classes, the ODM criterion %d' % (odm_conf_data.shape[-1], o.num_classes))
+        truths, labels, gt_count, min_count = _padded(targets, odm_loc_data.device)
+        if min_count == 0:
+            raise IndexError('RefineDetMultiBoxLoss: an image has no ground-truth boxes '
+                             '(the reference raises in refine_match, box_utils.py:139)')
+        priors = priors[:odm_loc_data.size(1), :]                             # :68 (DataParallel gather)
+        state = _PairState()
+        al, ac, an, ol, oc, on = _CriterionPair.apply(
+            arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, state, truths, labels, gt_count, priors.detach(),
+            float(a.threshold), float(o.threshold), o.variance, LABEL_ARM_BINARY, float(o.theta), int(a.negpos_ratio),
+            int(o.negpos_ratio), self.concurrent)
+        a._last = _StateView(state, 0)
+        o._last = _StateView(state, 1)
+        if not self.sync_free:
+            if float(an) < 1:                                       # :135-136 (the reference syncs here too)
+                al, ac = torch.zeros(1), torch.zeros(1)
+            if float(on) < 1:
+                ol, oc = torch.zeros(1), torch.zeros(1)
+        return al, ac, ol, oc
+
+
+class _StateView(object):
+    """One half of a :class:`_PairState` behind the ``view`` interface of :class:`_CriterionState`
+    (``last_masks`` / ``last_targets`` of the two modules after a paired call)."""
+    __slots__ = ('state', 'which')
+
+    def __init__(self, state, which):
+        self.state, self.which = state, which
+
+    def view(self, name, dtype, inner=None):
+        return self.state.view(self.which, name, dtype, inner)

@@ -280,6 +280,80 @@ def test_loss_tail_kernels(rd, B, size, C, G, use_arm):
     assert bool(torch.isfinite(p_conf.grad).all())
 
 
+@pytest.mark.parametrize('B,size,C,G', [(3, '320', 21, 9), (32, '512', 81, 50)])
+@pytest.mark.parametrize('concurrent', [True, False])
+def test_criterion_pair(rd, B, size, C, G, concurrent):
+    """RefineDetCriterionPair (rd_multibox_criterion_pair / rd_multibox_loss_backward_pair: the two chains on two
+    streams) == the two modules called one after the other as train_refinedet.py:252-256 does: losses, masks,
+    targets and all four gradients BIT-identical (the same kernels on the same inputs)."""
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS[size]).forward().cuda()
+    P = priors.shape[0]
+    tp = [t.cuda() for t in gen.train_predictions(300 + G, B, P, C)]
+    tp[1][..., 1] -= 3.0                                    # the theta gate removes some ODM positives
+    tg = [t.cuda() for t in gen.targets(9300 + G, B, G, C)]
+    mk = lambda: [t.clone().requires_grad_(True) for t in tp]                       # noqa: E731
+    arm_crit = rd.RefineDetMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)
+    odm_crit = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True)
+    ref = mk()
+    preds = tuple(ref) + (priors,)
+    al, ac = arm_crit(preds, tg)
+    ol, oc = odm_crit(preds, tg)
+    (1.5 * al + ac + ol + 0.25 * oc).backward()
+    ref_masks = [m.clone() for m in arm_crit.last_masks + odm_crit.last_masks]
+    ref_targets = [t.clone() for t in arm_crit.last_targets + odm_crit.last_targets]
+    for sync_free in (False, True):
+        a2 = rd.RefineDetMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True, sync_free=sync_free)
+        o2 = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True, sync_free=sync_free)
+        pair = rd.RefineDetCriterionPair(a2, o2, concurrent=concurrent)
+        got = mk()
+        pal, pac, pol, poc = pair(tuple(got) + (priors,), tg)
+        for x, y in ((pal, al), (pac, ac), (pol, ol), (poc, oc)):
+            assert float(x) == float(y) and float(x) > 0
+        (1.5 * pal + pac + pol + 0.25 * poc).backward()
+        for g, r in zip(got, ref):
+            assert torch.equal(g.grad, r.grad)
+        for m, r in zip(a2.last_masks + o2.last_masks, ref_masks):
+            assert torch.equal(m, r)
+        for t, r in zip(a2.last_targets + o2.last_targets, ref_targets):
+            assert torch.equal(t, r)
+    # only the ODM losses used: the ARM gradients are zeros, nothing is left unwritten
+    got = mk()
+    _, _, pol, poc = pair(tuple(got) + (priors,), tg)
+    (pol + poc).backward()
+    assert float(got[0].grad.abs().sum()) == 0.0 and float(got[1].grad.abs().sum()) == 0.0
+    assert float(got[3].grad.abs().sum()) > 0
+
+
+def test_criterion_pair_empty_odm(rd):
+    """Every matched anchor fails the ARM-theta gate: the ODM criterion has N = 0.  The pair returns the reference's
+    (zeros(1), zeros(1)) for it (refinedet_multibox_loss.py:135-136) and the ARM losses unchanged; with sync_free the
+    ODM losses are device zeros with zero gradients."""
+    B, C, G = 2, 21, 5
+    priors = rd.PriorBox(rd.REFINEDET_ANCHORS['320']).forward().cuda()
+    P = priors.shape[0]
+    tp = [t.cuda() for t in gen.train_predictions(812, B, P, C)]
+    tp[1][..., 0] += 40.0                                   # softmax(arm_conf)[1] ~ 0 everywhere
+    tg = [t.cuda() for t in gen.targets(813, B, G, C)]
+    arm_crit = rd.RefineDetMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True)
+    al, ac = arm_crit(tuple(tp) + (priors,), tg)
+    for sync_free in (False, True):
+        a2 = rd.RefineDetMultiBoxLoss(2, 0.5, True, 0, True, 3, 0.5, False, True, sync_free=sync_free)
+        o2 = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True, sync_free=sync_free)
+        got = [t.clone().requires_grad_(True) for t in tp]
+        pal, pac, pol, poc = rd.RefineDetCriterionPair(a2, o2)(tuple(got) + (priors,), tg)
+        assert float(pal) == float(al) and float(pac) == float(ac)
+        assert float(pol) == 0.0 and float(poc) == 0.0
+        if sync_free:
+            assert pol.is_cuda and pol.dim() == 0
+            (pal + pac + pol + poc).backward()
+            assert float(got[2].grad.abs().sum()) == 0.0 and float(got[3].grad.abs().sum()) == 0.0
+            assert float(got[1].grad.abs().sum()) > 0
+        else:
+            assert not pol.is_cuda and tuple(pol.shape) == (1,)
+    with pytest.raises(ValueError):
+        rd.RefineDetCriterionPair(o2, a2)
+
+
 @pytest.mark.parametrize('variant', ['zs', 'tile', 'regs'])
 def test_loss_backward_variants(variant):
     """The library picks the backward kernel by the class count (zero-stream for C >= 48, tile for odd C, register
