@@ -482,6 +482,40 @@ def test_full_size_properties(rd):
         assert np.array_equal(res.anchors[5, c, :n].cpu().numpy(), anc[c])
 
 
+@pytest.mark.parametrize('kind,B,P,C', [('sparse', 32, 16320, 81), ('dense', 32, 16320, 81), ('sparse', 5, 6375, 21),
+                                         ('sparse', 3, 1000, 2), ('dense', 7, 777, 33)])
+def test_forward_full_size(rd, kind, B, P, C):
+    """a3 at BASELINE.json's sizes: scores / in-place zeroing bit-exact against the masked copy the reference's
+    ``odm_conf_data[no_object_index] = 0`` amounts to (detection_refinedet.py:40-42), the scalar path of the kernel
+    (a misaligned view of the same data) against the 16-byte path, row counts that are no multiple of 32, and a
+    second call on the already zeroed tensor (idempotent)."""
+    arm_loc, arm_conf, odm_loc, odm_conf = [t.cuda() for t in gen.detect_inputs(99 + B + C, B, P, C, kind)]
+    priors = torch.rand(P, 4).cuda() * 0.5 + 0.05
+    det = rd.Detect_RefineDet(C, 512, 0, 1000, 0.01, 0.45, 0.01, 500)
+    conf = odm_conf.clone()
+    boxes, scores = det.forward(arm_loc, arm_conf, odm_loc, conf, priors)
+    keep = ~(arm_conf[..., 1] <= 0.01)
+    want = odm_conf * keep.unsqueeze(-1)
+    assert torch.equal(scores, want)
+    assert torch.equal(conf, want)
+    frac = float(keep.float().mean())
+    assert (frac < 0.2) if kind == 'sparse' else (frac > 0.5)
+    # a misaligned copy of the same data (4-byte offset: no 16-byte alignment, the kernel's scalar path)
+    pad = torch.empty(odm_conf.numel() + 1, device='cuda')
+    conf2 = pad[1:].view_as(odm_conf)
+    conf2.copy_(odm_conf)
+    pad_s = torch.empty(odm_conf.numel() + 1, device='cuda')
+    scores2 = pad_s[1:].view_as(odm_conf)
+    boxes2 = torch.empty_like(boxes)
+    ffi = rd._ffi
+    ffi.check(ffi.lib().rd_detect_forward(ffi.ptr(arm_loc), ffi.ptr(arm_conf), ffi.ptr(odm_loc), ffi.ptr(conf2), ffi.ptr(priors),
+                                          B, P, C, 0.01, det.variance[0], det.variance[1], ffi.ptr(boxes2), ffi.ptr(scores2),
+                                          ffi.stream_ptr()), 'rd_detect_forward')
+    assert torch.equal(boxes2, boxes) and torch.equal(scores2, want) and torch.equal(conf2, want)
+    boxes3, scores3 = det.forward(arm_loc, arm_conf, odm_loc, conf, priors)
+    assert torch.equal(scores3, want) and torch.equal(conf, want) and torch.equal(boxes3, boxes)
+
+
 def test_detect_host_zero_copy_matches_staged(rd):
     """e2e API: kernels reading the pinned host tensors directly give the same packed rows as the
     staged H2D copy path."""

@@ -175,7 +175,38 @@ def test_full_size_loss_step(rd):
         assert torch.equal(f_pos, pos) and torch.equal(f_neg, neg)
         ll, lc, n = rd.box_utils.multibox_loss_reduce(preds[2] if use_arm else preds[0], lt, ce, pos, neg, num_pos)
         fl, fc = crit(preds, tg)
-        assert float(fl) == float(ll) and float(fc) == float(lc) and float(n) == float(pos.sum())
+        assert abs(float(fl) - float(ll)) <= 2e-7 * abs(float(ll)) and abs(float(fc) - float(lc)) <= 2e-7 * abs(float(lc))
+        assert float(n) == float(pos.sum())
+
+
+@pytest.mark.parametrize('P', [16384, 20000, 300])
+def test_criterion_tail_paths(rd, P):
+    """The one-call criterion with the cluster mining kernel (rows up to 16,384 anchors) and with the single-CTA one
+    (longer rows), on priors that are not a RefineDet grid: against the step-by-step entry points and stock PyTorch."""
+    B, C, G = 3, 7, 6
+    g = torch.Generator().manual_seed(P)
+    cxcy = torch.rand(P, 2, generator=g)
+    wh = 0.03 + 0.3 * torch.rand(P, 2, generator=g)
+    priors = torch.cat([cxcy, wh], 1).cuda()
+    arm_loc, arm_conf, odm_loc, odm_conf = [t.cuda() for t in gen.train_predictions(P + 1, B, P, C)]
+    tg = [t.cuda() for t in gen.targets(P + 2, B, G, C, 0.05, 0.4)]
+    crit = rd.RefineDetMultiBoxLoss(C, 0.5, True, 0, True, 3, 0.5, False, True, use_ARM=True)
+    p_loc = odm_loc.clone().requires_grad_(True)
+    p_conf = odm_conf.clone().requires_grad_(True)
+    preds = (arm_loc, arm_conf, p_loc, p_conf, priors)
+    fl, fc = crit(preds, tg)
+    lt, ct = crit.match_targets(preds, tg)
+    ce, lse, pos = rd.box_utils.conf_loss(odm_conf, ct, arm_conf, 0.01)
+    neg, num_pos = rd.box_utils.hnm_select(ce, pos, 3)
+    f_pos, f_neg = crit.last_masks
+    assert torch.equal(f_pos, pos) and torch.equal(f_neg, neg) and int(pos.sum()) > 0
+    ll, lc, n = rd.box_utils.multibox_loss_reduce(odm_loc, lt, ce, pos, neg, num_pos)
+    assert abs(float(fl) - float(ll)) <= 2e-7 * abs(float(ll)) and abs(float(fc) - float(lc)) <= 2e-7 * abs(float(lc))
+    rl, rc = _torch_tail(odm_loc, odm_conf, lt, ct, pos, neg)
+    torch.testing.assert_close(fl, rl, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(fc, rc, rtol=1e-5, atol=1e-7)
+    (fl + fc).backward()
+    assert bool(torch.isfinite(p_conf.grad).all()) and float(p_conf.grad.abs().sum()) > 0
 
 
 @pytest.mark.parametrize('P', [16320, 16384, 6375, 300, 20000])
