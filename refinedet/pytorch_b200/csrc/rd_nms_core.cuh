@@ -885,8 +885,15 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
         }
         for (int i = tid; i < nb * 32 * kTinStride; i += nthr) s_tin[i] = 0;
         if (tid < kChunkBlocks) s_dead[tid] = 0;
+        if (tid == 0) misc[12] = 0;                       // next item of the chunk
         __syncthreads();
-        for (int it = warp; it < (cb + nb) * kChunkBlocks; it += nwarps) {
+        // items are drawn from a counter, not dealt round robin: their cost (pairs that survive the bins) varies by
+        // an order of magnitude, and a fifth of the kernel's stall samples sat at the barrier behind this loop
+        for (;;) {
+            int it = 0;
+            if (lane == 0) it = (int)atomicAdd(&misc[12], 1u);
+            it = __shfl_sync(kFullMask, it, 0);
+            if (it >= (cb + nb) * kChunkBlocks) break;
             const int w = it / kChunkBlocks, bl = it - w * kChunkBlocks;
             if (bl >= nb || w > cb + bl) continue;
             const int jb = (cb + bl) * 32;
@@ -939,6 +946,7 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
             }
         }
         __syncthreads();
+        const int kept_before = kept_total;               // rows kept before this chunk (warp 0 advances kept_total below)
         if (warp == 0) {
             uint32_t kw[kChunkBlocks];                    // kept words of this chunk (uniform)
 #pragma unroll
@@ -951,15 +959,20 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
 #pragma unroll
                     for (int q = 0; q < kChunkBlocks; ++q)
                         if (q < bl && (trow[q] & kw[q])) alive = false;
+                    // in-block resolution in score order: lane i survives iff no SURVIVING earlier lane of the block
+                    // suppresses it.  The recursion runs over strictly lower lanes, so it has one solution and the
+                    // iteration M <- { i : alive_i and tin_i & M == 0 } reaches it from any start -- bits 0 .. t-1 are
+                    // final after t rounds -- in as many rounds as the longest suppression chain is deep (2 - 4),
+                    // instead of one round per suppressor bit.
                     const uint32_t tin = trow[bl];
-                    uint32_t u = __reduce_or_sync(kFullMask, alive ? tin : 0u);   // in-block resolution in score order
-                    while (u) {
-                        const int k = __ffs(u) - 1;
-                        u &= u - 1;
-                        const uint32_t al = __ballot_sync(kFullMask, alive);
-                        if (((al >> k) & 1u) && ((tin >> k) & 1u)) alive = false;
-                    }
                     uint32_t keptw = __ballot_sync(kFullMask, alive);
+                    if (__any_sync(kFullMask, alive && (tin & keptw))) {
+                        for (;;) {
+                            const uint32_t nm = __ballot_sync(kFullMask, alive && !(tin & keptw));
+                            if (nm == keptw) break;
+                            keptw = nm;
+                        }
+                    }
                     const int room = max_out - kept_total;
                     int cnt = __popc(keptw);
                     if (cnt > room) {   // keep only the first `room` set bits
@@ -968,11 +981,11 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
                         keptw = keep;
                         cnt = room;
                     }
-                    if ((keptw >> lane) & 1u)
-                        sink_emit(sink, kept_total + __popc(keptw & lt_mask), keys[j], sx1[j], sy1[j], sx2[j], sy2[j]);
-                    kept_total += cnt;
+                    kept_total += cnt;                        // (the rows are emitted by the whole CTA, below)
                     kw[bl] = keptw;
                     if (lane == 0) keptbits[cb + bl] = keptw;
+                } else if (bl < nb && lane == 0) {
+                    keptbits[cb + bl] = 0u;               // the output is full: nothing of this block is kept (or emitted)
                 }
             }
             if (lane == 0) {
@@ -981,6 +994,18 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
             }
         }
         __syncthreads();
+        // the chunk's kept rows, one candidate per thread: rank = rows kept before the chunk + kept bits before it
+        // (warp 0 only decides; 5 - 7 scattered stores per kept row no longer sit in its serial walk)
+        for (int t = tid; t < nb * 32; t += nthr) {
+            const int q = t >> 5;
+            const uint32_t kwq = keptbits[cb + q];
+            if ((kwq >> (t & 31)) & 1u) {
+                int rank = kept_before + __popc(kwq & ((1u << (t & 31)) - 1u));
+                for (int q2 = 0; q2 < q; ++q2) rank += __popc(keptbits[cb + q2]);
+                const int j = cb * 32 + t;
+                sink_emit(sink, rank, keys[j], sx1[j], sy1[j], sx2[j], sy2[j]);
+            }
+        }
         kept_total = (int)misc[8];
         if (misc[11]) break;
         cb += nb;
