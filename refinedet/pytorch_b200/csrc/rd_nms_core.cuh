@@ -893,9 +893,17 @@ __device__ inline int nms_process(unsigned char* smem, const NmsSmemLayout& L, c
             int it = 0;
             if (lane == 0) it = (int)atomicAdd(&misc[12], 1u);
             it = __shfl_sync(kFullMask, it, 0);
-            if (it >= (cb + nb) * kChunkBlocks) break;
-            const int w = it / kChunkBlocks, bl = it - w * kChunkBlocks;
-            if (bl >= nb || w > cb + bl) continue;
+            // only the items that exist: every (earlier word, block) pair, then (word wi of the chunk, block bl >= wi)
+            if (it >= cb * nb + (nb * (nb + 1)) / 2) break;
+            int w, bl;
+            if (it < cb * nb) {
+                w = it / nb; bl = it - w * nb;
+            } else {
+                int t = it - cb * nb;
+                bl = 0;
+                while (t > bl) { t -= bl + 1; ++bl; }          // nb <= kChunkBlocks rounds
+                w = cb + t;
+            }
             const int jb = (cb + bl) * 32;
             const int j = jb + lane;
             uint32_t h = 0;
