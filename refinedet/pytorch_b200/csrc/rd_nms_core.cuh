@@ -194,7 +194,10 @@ __device__ __forceinline__ int tri_row(int r) {
     return 16 * k * (k + 1) + (r & 31) * (k + 1);
 }
 // kNodes = largest node index + 1 the rank table covers (images with more nodes are not handled by this instance)
-template <int kCap, int kNodes = (kCap > 256 ? RD_GRAPH_NODES : 1024)>
+#ifndef RD_SMALL_NODES
+#define RD_SMALL_NODES 1024     // 2048 keeps images of 1025 - 2048 nodes in this kernel (1185 nodes: 0.100 -> 0.092 ms) but costs the headline 3 % (28.3 -> 29.1 us: the two-pass scan becomes live code, 32 bytes of spills)
+#endif
+template <int kCap, int kNodes = (kCap > 256 ? RD_GRAPH_NODES : RD_SMALL_NODES)>
 struct SmallSmem {
     static constexpr bool kBitRows = kCap <= 256; // false: images flagged kFlagWideDeg are not handled by this instance
     static constexpr int kDeps = kAdjDeg;         // list mode: ranks kept per candidate
