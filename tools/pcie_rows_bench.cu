@@ -1,6 +1,7 @@
 // tools/pcie_rows_bench.cu — microbenchmark behind the line-granular PCIe fetch of collect_kernel: SM reads of scattered
 // 324-byte rows from pinned host memory with (A) 4-byte lane = class loads, (B) 4-byte loads over whole 128-byte lines,
-// (C) one 16-byte load per lane over whole lines, against a DMA of the same bytes.
+// (C) one 16-byte load per lane over whole lines, (F) one bulk asynchronous copy (cp.async.bulk, the TMA engine) per row
+// span into shared memory -- whole 128-byte lines or the row's own 16-byte-aligned bytes -- against a DMA of the same bytes.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -include algorithm -o pcie_rows_bench tools/pcie_rows_bench.cu
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -56,6 +57,32 @@ __global__ void kE(const float4* host, const int* rows, int nrows, float* out){
   for(int r=t>>3;r<nrows;r+=nt>>3){ size_t i=(size_t)rows[r]; float4 v=__ldg(host+(i&~(size_t)7)+sub); acc+=v.x+v.y+v.z+v.w; }
   if(acc==123.456f) out[0]=acc;
 }
+// F: one bulk copy per row into shared memory, kInFlight rows per CTA behind one mbarrier; `lines`: the aligned 128-byte
+//    lines that cover the row (512 B), else the 16-byte-aligned span (336 - 352 B)
+constexpr int kInFlight=32;
+__global__ void kF(const float* host, const int* rows, int nrows, float* out, int lines){
+  __shared__ __align__(128) unsigned char buf[kInFlight][512];
+  __shared__ __align__(8) unsigned long long bar;
+  const int tid=threadIdx.x; float acc=0;
+  if(tid==0){ asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;"::"r"((unsigned)__cvta_generic_to_shared(&bar))); asm volatile("fence.mbarrier_init.release.cluster;":::"memory"); }
+  __syncthreads();
+  unsigned parity=0;
+  for(int r0=blockIdx.x*kInFlight;r0<nrows;r0+=gridDim.x*kInFlight){
+    if(tid==0){
+      unsigned tot=0; unsigned nb[kInFlight]; const char* src[kInFlight]; int cnt=min(kInFlight,nrows-r0);
+      for(int k=0;k<cnt;++k){ size_t f=(size_t)rows[r0+k]*C*4; size_t a0= lines? (f&~(size_t)127) : (f&~(size_t)15); size_t a1= lines? ((f+C*4+127)&~(size_t)127) : ((f+C*4+15)&~(size_t)15);
+        src[k]=reinterpret_cast<const char*>(host)+a0; nb[k]=(unsigned)(a1-a0); tot+=nb[k]; }
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"::"r"((unsigned)__cvta_generic_to_shared(&bar)),"r"(tot):"memory");
+      for(int k=0;k<cnt;++k)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"::"r"((unsigned)__cvta_generic_to_shared(buf[k])),"l"(src[k]),"r"(nb[k]),"r"((unsigned)__cvta_generic_to_shared(&bar)):"memory");
+    }
+    unsigned ok=0; while(!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }":"=r"(ok):"r"((unsigned)__cvta_generic_to_shared(&bar)),"r"(parity):"memory");
+    parity^=1;
+    for(int i=tid;i<kInFlight*128;i+=blockDim.x) acc+=reinterpret_cast<const float*>(buf)[i];
+    __syncthreads();
+  }
+  if(acc==123.456f) out[0]=acc;
+}
 int main(){
   const size_t total=(size_t)32*16320; float* h; CK(cudaHostAlloc(&h,total*C*4,cudaHostAllocDefault));
   for(size_t i=0;i<total*C;i+=1024) h[i]=1.f;
@@ -73,6 +100,11 @@ int main(){
     printf("grid %4d B full lines   : %.3f ms  %.1f GB/s useful\n",grid,ms,nrows*324.0/ms/1e6);
     cudaEventRecord(a); kC<<<grid,256>>>(h,drows,nrows,out); cudaEventRecord(b); CK(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms,a,b);
     printf("grid %4d C float4 lines : %.3f ms  %.1f GB/s useful\n",grid,ms,nrows*324.0/ms/1e6);
+  }
+  for(int lines: {1,0}) for(int grid: {148,296,592,1184}) for(int thr: {32,128}){ float ms;
+    kF<<<grid,thr>>>(h,drows,nrows,out,lines);
+    cudaEventRecord(a); kF<<<grid,thr>>>(h,drows,nrows,out,lines); cudaEventRecord(b); CK(cudaEventSynchronize(b)); cudaEventElapsedTime(&ms,a,b);
+    printf("grid %4d x%3d F bulk copy %s : %.3f ms  %.1f GB/s useful\n",grid,thr,lines?"128-B lines":"16-B span  ",ms,nrows*324.0/ms/1e6);
   }
   { // loc vectors: items of 16 bytes among total anchors
     for(int rep=0;rep<3;++rep){ float ms;
