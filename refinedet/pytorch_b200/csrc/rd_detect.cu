@@ -666,6 +666,8 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
     }
 }
 
+// kTune: two instances of the same code with different shared-memory carve-outs (see set_stage_carveouts)
+template <int kTune>
 __global__ void __launch_bounds__(kGraphThreads)
 graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, const float4* __restrict__ nbox,
              const uint32_t* __restrict__ ncr, int P, float thr, int flags,
@@ -1547,6 +1549,40 @@ int rd_detect_workspace_reset(void* workspace, size_t workspace_bytes, void* str
 
 }  // extern "C"
 
+// Shared-memory carve-out of the stage's kernels, set once per device instead of left to the driver's per-kernel
+// choice (measured on B200, cfg 3 sparse, `RD_CARVEOUT="collect,graph,small,large"` in percent overrides it for
+// experiments).  What matters is graph_kernel: at 228 KB the per-class CTAs of nms_small_kernel (10 KB each) find room
+// beside the four running graph CTAs of an SM (4 x 46.6 KB) and their scan + sort overlaps the graph -- one batch alone
+// takes 45 us instead of 49 us; at 196 KB they do not, the SM takes CTAs of the NEXT batch in flight instead, and four
+// batches in flight take 27.1 us per batch instead of 28.3 us.  Hence two instances of graph_kernel, chosen by
+// RD_TUNE_IN_FLIGHT.  collect_kernel and nms_small_kernel<256,128> at 164 KB are the better choice in both regimes.
+static void set_stage_carveouts() {
+    static bool s_done[kMaxDevices];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    bool& done = s_done[(unsigned)dev % kMaxDevices];
+    if (done) return;
+    done = true;
+    int pc = 72, pg0 = 100, pg1 = 85, ps = 72, pl = -1;
+    if (const char* env = getenv("RD_CARVEOUT")) {
+        int a = -1, b = -1, c = -1, d = -1;
+        const int nf = sscanf(env, "%d,%d,%d,%d", &a, &b, &c, &d);
+        if (nf >= 1) { pc = a; pg0 = pg1 = (nf >= 2 ? b : a); ps = (nf >= 3 ? c : a); pl = (nf >= 4 ? d : a); }
+    }
+    const auto attr = cudaFuncAttributePreferredSharedMemoryCarveout;
+    if (pc >= 0) {
+        cudaFuncSetAttribute(collect_kernel<false, false>, attr, pc);
+        cudaFuncSetAttribute(collect_kernel<false, true>, attr, pc);
+        cudaFuncSetAttribute(collect_kernel<true, false>, attr, pc);
+        cudaFuncSetAttribute(collect_kernel<true, true>, attr, pc);
+    }
+    if (pg0 >= 0) cudaFuncSetAttribute(graph_kernel<0>, attr, pg0);
+    if (pg1 >= 0) cudaFuncSetAttribute(graph_kernel<1>, attr, pg1);
+    if (ps >= 0) cudaFuncSetAttribute(nms_small_kernel<kSmallCap, kSmallThreads, RD_SMALL_MINBLOCKS>, attr, ps);
+    if (pl >= 0) cudaFuncSetAttribute(nms_large_kernel, attr, pl);
+    (void)cudaGetLastError();
+}
+
 static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const float* odm_loc, const float* odm_conf,
                              const float* priors, int B, int P, int C, float objectness_thre, float conf_thresh,
                              float nms_thresh, int top_k, int max_out, const float* img_scale, int nms_flags,
@@ -1565,6 +1601,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     DetectWs ws = carve_ws(workspace, B, P, C);
     if (workspace_bytes < ws.total) return RD_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    set_stage_carveouts();
 
     GraphOut GO;
     GO.nnodes = ws.nnodes; GO.gtab = ws.gtab; GO.nbox = ws.nbox; GO.nanc = ws.nanc; GO.ncr = ws.ncr;
@@ -1599,12 +1636,14 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     RD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[1], st);
     {
-        static size_t s_graph_smem[kMaxDevices];
-        cudaError_t e = ensure_dynamic_smem(graph_kernel, sizeof(GraphSmem), s_graph_smem);
+        static size_t s_graph_smem[2][kMaxDevices];
+        const bool in_flight = (nms_flags & RD_TUNE_IN_FLIGHT) != 0;
+        auto gk = in_flight ? graph_kernel<1> : graph_kernel<0>;
+        cudaError_t e = ensure_dynamic_smem(gk, sizeof(GraphSmem), s_graph_smem[in_flight ? 1 : 0]);
         if (e != cudaSuccess) return (int)e;
-        e = launch_pdl(graph_kernel, dim3(kGraphSplit, B), dim3(kGraphThreads), sizeof(GraphSmem), st,
-                                   (const int*)ws.nnodes, (const uint32_t*)ws.gtab, (const float4*)ws.nbox,
-                                   (const uint32_t*)ws.ncr, P, nms_thresh, nms_flags, ws.adj, ws.adj2, ws.adjn, ws.flag);
+        e = launch_pdl(gk, dim3(kGraphSplit, B), dim3(kGraphThreads), sizeof(GraphSmem), st,
+                       (const int*)ws.nnodes, (const uint32_t*)ws.gtab, (const float4*)ws.nbox,
+                       (const uint32_t*)ws.ncr, P, nms_thresh, nms_flags, ws.adj, ws.adj2, ws.adjn, ws.flag);
         if (e != cudaSuccess) return (int)e;
         note_launch();
         RD_CHECK_LAUNCH();
