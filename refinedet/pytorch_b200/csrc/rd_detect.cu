@@ -641,7 +641,12 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
             //  The decision is taken CTA-wide by the barrier itself (__syncthreads_or): a thread that read npairs
             //  on its own could skip the branch and append pairs of the next round before a slower warp has
             //  looked at the counter, and the barriers inside the branch would pair up at different places.
-            if (q0 + kGraphThreads < nitems) {
+#ifndef RD_GRAPH_DRAIN_EVERY
+#define RD_GRAPH_DRAIN_EVERY 4     // 1: 57.4 us at 1871 nodes per image, 4: 51.6 us; 8 and 16 let the list overflow at 3.9 k nodes (185 / 168 / 188 / 203 us)
+#endif
+            // (multi-block images: the check -- a CTA-wide barrier -- every RD_GRAPH_DRAIN_EVERY-th round of items)
+            if (q0 + kGraphThreads < nitems &&
+                (kSingle || RD_GRAPH_DRAIN_EVERY == 1 || ((q0 / kGraphThreads) % RD_GRAPH_DRAIN_EVERY) == RD_GRAPH_DRAIN_EVERY - 1)) {
                 if (__syncthreads_or(G.npairs >= kGraphPairCap / 2)) {
                     const int cnt = min(G.npairs, kGraphPairCap);
                     for (int p = tid; p < cnt; p += kGraphThreads) {
