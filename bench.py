@@ -303,19 +303,15 @@ def main():
     # buffer; one plan (CUDA graph of the launch chain, rd_detect_plan_*) per (lane, input set)
     streams = [torch.cuda.Stream(dev) for _ in range(S)]
     lanes = [(det.new_workspace(B_loc, P, dev), det.new_outputs(B_loc, dev)) for _ in range(S)]
-    plans = [[det.plan(a[0], a[1], a[2], a[3], priors, scale=scale, workspace=lanes[l][0], out=lanes[l][1], in_flight=S)
+    plans = [[det.plan(a[0], a[1], a[2], a[3], priors, scale=scale, workspace=lanes[l][0], out=lanes[l][1])
               for a in dev_sets] for l in range(S)]
-    # the plans of the single-batch latency measurement: the same chain without the several-batches-in-flight tuning
-    # (RD_TUNE_IN_FLIGHT trades 4 us of one batch's latency for 1.2 us per batch of pipelined throughput)
-    lat_plans = [det.plan(a[0], a[1], a[2], a[3], priors, scale=scale, workspace=lanes[0][0], out=lanes[0][1])
-                 for a in dev_sets] if S > 1 else plans[0]
     exchanges, exchange_err, xplans = None, None, None
     if dist is not None and not args.no_exchange:
         try:
             exchanges = [rdist.PeerExchange(B_max, C, lanes[l][1].dets.shape[2], dev) for l in range(S)]
             # stage + exchange of its result as ONE plan per (lane, input set): a step stays one driver call
             xplans = [[det.plan(a[0], a[1], a[2], a[3], priors, scale=scale, workspace=lanes[l][0], out=lanes[l][1],
-                                then=exchanges[l].exchange, in_flight=S) for a in dev_sets] for l in range(S)]
+                                then=exchanges[l].exchange) for a in dev_sets] for l in range(S)]
         except Exception as e:                                              # symmetric memory unavailable
             exchanges, xplans, exchange_err = None, None, repr(e)[:200]
 
@@ -401,7 +397,7 @@ def main():
         for i in range(KL):
             flush_buf.zero_()
             starts[i].record(main_st)
-            lat_plans[i % NBUF].launch(main_st)
+            plans[0][i % NBUF].launch(main_st)
             stops[i].record(main_st)
         torch.cuda.synchronize()
     lat = sorted(s_.elapsed_time(e_) for s_, e_ in zip(starts, stops))
@@ -441,8 +437,7 @@ def main():
         'stage_ms_serialised': stage_ms_serialised, 'kernels_ms': kern,
         'kernel_share': {k: v / stage_ms_serialised for k, v in kern.items()},
         'single_batch': {'median_ms': latency_ms, 'mean_ms': float(sum(lat)) / KL, 'min_ms': lat[0],
-                         'how': 'one stream, 512 MiB memset (L2 flush, untimed) before every step, %d steps; plans created with '
-                                'in_flight=1 (the timed regions use in_flight=%d plans)' % (KL, S)},
+                         'how': 'one stream, 512 MiB memset (L2 flush, untimed) before every step, %d steps' % KL},
         'note': 'achieved = stage bytes (SURVEY 8d: 4*P*(10+C) B/image + 20 B/kept row) / (median event-timed region / K '
                 'steps), %d batches in flight; ARM-filtered anchors (%.1f%% here) are never fetched, so DRAM traffic '
                 '(dram_frac) is far below the algorithmic bytes: the stage is issue/latency-bound' % (S, 100 * (1 - arm_pass))}

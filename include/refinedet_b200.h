@@ -68,13 +68,6 @@ extern "C" {
 /* TEST-ONLY, OR-able into the nms_flags of the fused detect stage: force one instantiation of the per-class
  * kernel (nms_small_kernel) regardless of the grid-size heuristic, so that the parity tests can hold every
  * instantiation to the oracle at small sizes too.  0 = choose automatically (the only value product code uses). */
-/* OR-able tuning hint of rd_detect_fused / rd_detect_plan_create: SEVERAL batches are in flight on separate streams
- * (a serving loop over a few plans).  It selects the instance of graph_kernel whose shared-memory carve-out is
- * 196 KB instead of 228 KB: with four batches in flight the stage takes 27.1 us instead of 28.3 us per batch, one
- * batch alone 49 us instead of 45 us (with the larger carve-out the per-class CTAs of nms_small_kernel find room
- * beside the running graph CTAs of their own batch; with the smaller one the SM takes the next batch's CTAs
- * sooner).  Results are identical. */
-#define RD_TUNE_IN_FLIGHT   8
 #define RD_DEBUG_INSTANCE_SHIFT 8
 #define RD_DEBUG_INSTANCE_MASK  (3 << RD_DEBUG_INSTANCE_SHIFT)
 #define RD_DEBUG_INSTANCE_256   (1 << RD_DEBUG_INSTANCE_SHIFT)   /* <= 256 candidates, 128 threads  */

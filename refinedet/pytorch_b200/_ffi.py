@@ -28,7 +28,6 @@ RD_MAX_NMS_BOXES = 4096
 RD_MAX_GT = 1024
 RD_NMS_NORMALISED, RD_NMS_PIXEL_PLUS1, RD_NMS_SUPPRESS_EQ = 0, 1, 2
 RD_INPUT_LOGITS = 4
-RD_TUNE_IN_FLIGHT = 8
 RD_DEBUG_INSTANCE_SHIFT = 8
 RD_DEBUG_INSTANCE_256, RD_DEBUG_INSTANCE_1024 = 1 << 8, 2 << 8
 RD_ROW_BOX_SCORE, RD_ROW_SCORE_BOX = 0, 1

@@ -482,7 +482,9 @@ constexpr int kGraphPairCap = 2048;
 
 struct GraphSmem {
     float x1[kBlockNodes], y1[kBlockNodes], x2[kBlockNodes], y2[kBlockNodes];
-    float area[kBlockNodes];         // box area in the flavour of the IoU (the area-ratio pre-test of the item loop)
+    // (no array of box areas: the area-ratio pre-test of the multi-block path recomputes them -- 4 KB less per CTA let
+    //  two CTAs of nms_small_kernel sit beside the four graph CTAs of an SM: 27.1 -> 25.9 us per batch with four batches in
+    //  flight, for + 2 - 5 % on images of more than 1024 nodes)
     uint32_t cr[kBlockNodes];
     uint32_t tab[4 * kCols * kBlockWS];
     uint32_t pairs[kGraphPairCap];
@@ -562,7 +564,6 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
         for (int i = tid; i < nb; i += kGraphThreads) {
             const float4 bx = boxes[n0 + i];
             G.x1[i] = bx.x; G.y1[i] = bx.y; G.x2[i] = bx.z; G.y2[i] = bx.w;
-            if (!kSingle) G.area[i] = box_area(bx.x, bx.y, bx.z, bx.w, pixel);
             G.cr[i] = crs[n0 + i];
         }
         // 2. inclusive prefix-OR over the bins, straight from the global marks.  One (table, word) column per
@@ -613,13 +614,14 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
                 if (w == (jl >> 5)) h &= (1u << (jl & 31)) - 1u;                 // predecessors only
                 if (!kSingle && h && ratio_thr > 0.0f) {
                     float aj;
-                    if (jl < nb) aj = G.area[jl];
+                    if (jl < nb) aj = box_area(G.x1[jl], G.y1[jl], G.x2[jl], G.y2[jl], pixel);
                     else { const float4 bj = __ldg(boxes + n0 + jl); aj = box_area(bj.x, bj.y, bj.z, bj.w, pixel); }
                     uint32_t rest = h;
                     while (rest) {
                         const int bit = __ffs(rest) - 1;
                         rest &= rest - 1;
-                        const float ai = G.area[(w << 5) + bit];
+                        const int ii = (w << 5) + bit;
+                        const float ai = box_area(G.x1[ii], G.y1[ii], G.x2[ii], G.y2[ii], pixel);
                         const float lo = fminf(ai, aj), hi = fmaxf(ai, aj);
                         if (lo > 0.0f && lo < ratio_thr * hi) h &= ~(1u << bit);
                     }
@@ -671,8 +673,6 @@ __device__ __forceinline__ void graph_image(GraphSmem& G, int N, int g, int b, i
     }
 }
 
-// kTune: two instances of the same code with different shared-memory carve-outs (see set_stage_carveouts)
-template <int kTune>
 __global__ void __launch_bounds__(kGraphThreads)
 graph_kernel(const int* __restrict__ nnodes, const uint32_t* __restrict__ gtab, const float4* __restrict__ nbox,
              const uint32_t* __restrict__ ncr, int P, float thr, int flags,
@@ -1555,12 +1555,12 @@ int rd_detect_workspace_reset(void* workspace, size_t workspace_bytes, void* str
 }  // extern "C"
 
 // Shared-memory carve-out of the stage's kernels, set once per device instead of left to the driver's per-kernel
-// choice (measured on B200, cfg 3 sparse, `RD_CARVEOUT="collect,graph,small,large"` in percent overrides it for
-// experiments).  What matters is graph_kernel: at 228 KB the per-class CTAs of nms_small_kernel (10 KB each) find room
-// beside the four running graph CTAs of an SM (4 x 46.6 KB) and their scan + sort overlaps the graph -- one batch alone
-// takes 45 us instead of 49 us; at 196 KB they do not, the SM takes CTAs of the NEXT batch in flight instead, and four
-// batches in flight take 27.1 us per batch instead of 28.3 us.  Hence two instances of graph_kernel, chosen by
-// RD_TUNE_IN_FLIGHT.  collect_kernel and nms_small_kernel<256,128> at 164 KB are the better choice in both regimes.
+// choice (measured on B200, cfg 3 sparse; `RD_CARVEOUT="collect,graph,small,large"` in percent overrides it for
+// experiments).  With the driver's choice -- 228 KB for graph_kernel -- four batches in flight took 28.3 us per batch; at
+// 196 KB for graph_kernel and 164 KB for collect_kernel / nms_small_kernel<256,128> the SMs take the CTAs of the next
+// batch sooner: 27.1 us.  One batch alone went the other way (45 -> 49 us: at 196 KB the per-class CTAs of
+// nms_small_kernel, 10 KB each, found no room beside the four running graph CTAs of an SM, 4 x 46.6 KB, and their scan +
+// sort no longer overlapped the graph) until graph_kernel's footprint shrank to 42.5 KB per CTA: 25.9 us / 45.1 us.
 static void set_stage_carveouts() {
     static bool s_done[kMaxDevices];
     int dev = 0;
@@ -1568,11 +1568,11 @@ static void set_stage_carveouts() {
     bool& done = s_done[(unsigned)dev % kMaxDevices];
     if (done) return;
     done = true;
-    int pc = 72, pg0 = 100, pg1 = 85, ps = 72, pl = -1;
+    int pc = 72, pg = 85, ps = 72, pl = -1;
     if (const char* env = getenv("RD_CARVEOUT")) {
         int a = -1, b = -1, c = -1, d = -1;
         const int nf = sscanf(env, "%d,%d,%d,%d", &a, &b, &c, &d);
-        if (nf >= 1) { pc = a; pg0 = pg1 = (nf >= 2 ? b : a); ps = (nf >= 3 ? c : a); pl = (nf >= 4 ? d : a); }
+        if (nf >= 1) { pc = a; pg = (nf >= 2 ? b : a); ps = (nf >= 3 ? c : a); pl = (nf >= 4 ? d : a); }
     }
     const auto attr = cudaFuncAttributePreferredSharedMemoryCarveout;
     if (pc >= 0) {
@@ -1581,8 +1581,7 @@ static void set_stage_carveouts() {
         cudaFuncSetAttribute(collect_kernel<true, false>, attr, pc);
         cudaFuncSetAttribute(collect_kernel<true, true>, attr, pc);
     }
-    if (pg0 >= 0) cudaFuncSetAttribute(graph_kernel<0>, attr, pg0);
-    if (pg1 >= 0) cudaFuncSetAttribute(graph_kernel<1>, attr, pg1);
+    if (pg >= 0) cudaFuncSetAttribute(graph_kernel, attr, pg);
     if (ps >= 0) cudaFuncSetAttribute(nms_small_kernel<kSmallCap, kSmallThreads, RD_SMALL_MINBLOCKS>, attr, ps);
     if (pl >= 0) cudaFuncSetAttribute(nms_large_kernel, attr, pl);
     (void)cudaGetLastError();
@@ -1641,12 +1640,10 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     RD_CHECK_LAUNCH();
     if (ev) cudaEventRecord(ev[1], st);
     {
-        static size_t s_graph_smem[2][kMaxDevices];
-        const bool in_flight = (nms_flags & RD_TUNE_IN_FLIGHT) != 0;
-        auto gk = in_flight ? graph_kernel<1> : graph_kernel<0>;
-        cudaError_t e = ensure_dynamic_smem(gk, sizeof(GraphSmem), s_graph_smem[in_flight ? 1 : 0]);
+        static size_t s_graph_smem[kMaxDevices];
+        cudaError_t e = ensure_dynamic_smem(graph_kernel, sizeof(GraphSmem), s_graph_smem);
         if (e != cudaSuccess) return (int)e;
-        e = launch_pdl(gk, dim3(kGraphSplit, B), dim3(kGraphThreads), sizeof(GraphSmem), st,
+        e = launch_pdl(graph_kernel, dim3(kGraphSplit, B), dim3(kGraphThreads), sizeof(GraphSmem), st,
                        (const int*)ws.nnodes, (const uint32_t*)ws.gtab, (const float4*)ws.nbox,
                        (const uint32_t*)ws.ncr, P, nms_thresh, nms_flags, ws.adj, ws.adj2, ws.adjn, ws.flag);
         if (e != cudaSuccess) return (int)e;

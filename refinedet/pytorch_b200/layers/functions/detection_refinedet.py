@@ -202,8 +202,7 @@ class DetectHostPipeline(object):
                     raise RuntimeError('DetectHostPipeline needs contiguous pinned float32 host tensors')
             args, res, dev, keep = self.det._prepare(
                 host_inputs[0], lane['arm_conf'], host_inputs[2], host_inputs[3], self.priors, self.scale,
-                _ffi.RD_NMS_PIXEL_PLUS1 | (_ffi.RD_TUNE_IN_FLIGHT if len(self.lanes) > 1 else 0), _ffi.RD_ROW_BOX_SCORE,
-                self.det.keep_top_k, host_mapped=True,
+                _ffi.RD_NMS_PIXEL_PLUS1, _ffi.RD_ROW_BOX_SCORE, self.det.keep_top_k, host_mapped=True,
                 workspace=lane['ws'], out=lane['out'])
             torch.cuda.synchronize(self.device)
             plan = lane['plans'][key] = DetectPlan(args, res, dev, keep)
@@ -466,21 +465,16 @@ class Detect_RefineDet(object):
                           torch.empty(B, C, max_out, dtype=torch.int32, device=device), row_layout)
 
     def plan(self, arm_loc_data, arm_conf_data, odm_loc_data, odm_conf_data, prior_data, scale=None,
-             workspace=None, out=None, force_cpu_semantics=False, logits=False, instance=None, then=None,
-             in_flight=1):
+             workspace=None, out=None, force_cpu_semantics=False, logits=False, instance=None, then=None):
         """:meth:`detect` for FIXED input buffers, captured once (``rd_detect_plan_create``): the returned
         :class:`DetectPlan` replays the whole launch chain with one driver call per batch.  The tensors are
         referenced, not copied — refill them in place between replays.  Plans that share ``workspace`` /
         ``out`` must be replayed on the same stream; give every batch in flight its own pair
         (:meth:`new_workspace`, :meth:`new_outputs`).  ``then(result)``: a callable that enqueues the consumer of
         the result on the current stream (e.g. ``PeerExchange.exchange``) — captured into the same plan, so that a
-        step of stage + exchange is still one driver call.  ``in_flight``: how many plans the caller replays
-        concurrently on separate streams (a serving loop); more than one selects the throughput tuning of the chain
-        (``RD_TUNE_IN_FLIGHT``: 27.1 instead of 28.3 us per batch with four in flight, 49 instead of 45 us for one
-        batch alone).  Results do not depend on it."""
+        step of stage + exchange is still one driver call."""
         flags = _ffi.RD_NMS_PIXEL_PLUS1 | (_ffi.RD_NMS_SUPPRESS_EQ if force_cpu_semantics else 0) | \
-            (_ffi.RD_INPUT_LOGITS if logits else 0) | self._INSTANCES[instance] | \
-            (_ffi.RD_TUNE_IN_FLIGHT if in_flight > 1 else 0)
+            (_ffi.RD_INPUT_LOGITS if logits else 0) | self._INSTANCES[instance]
         for name, t in (('arm_loc_data', arm_loc_data), ('arm_conf_data', arm_conf_data),
                         ('odm_loc_data', odm_loc_data), ('odm_conf_data', odm_conf_data)):
             if not t.is_contiguous() or t.data_ptr() % 16:

@@ -29,7 +29,7 @@ def test_header_constants_match_python_mirror():
     defs = dict(re.findall(r'#define\s+(RD_\w+)\s+\(?(-?\d+)\)?', text))
     for name in ('RD_ABI_VERSION', 'RD_ERR_BAD_ARG', 'RD_ERR_ALIGNMENT', 'RD_ERR_UNSUPPORTED', 'RD_ERR_WORKSPACE',
                  'RD_MAX_NMS_BOXES', 'RD_MAX_GT', 'RD_NMS_NORMALISED', 'RD_NMS_PIXEL_PLUS1', 'RD_NMS_SUPPRESS_EQ',
-                 'RD_ROW_BOX_SCORE', 'RD_ROW_SCORE_BOX', 'RD_INPUT_LOGITS', 'RD_TUNE_IN_FLIGHT'):
+                 'RD_ROW_BOX_SCORE', 'RD_ROW_SCORE_BOX', 'RD_INPUT_LOGITS'):
         assert int(defs[name]) == getattr(_ffi, name), name
 
 

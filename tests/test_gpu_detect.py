@@ -298,8 +298,7 @@ def test_plan_replay_and_lanes(rd):
     # two lanes, two plans, both in flight
     lanes = [(torch.cuda.Stream(), det.new_workspace(B, P, priors.device), det.new_outputs(B, priors.device))
              for _ in range(2)]
-    # (in_flight=2: the RD_TUNE_IN_FLIGHT instance of graph_kernel -- another carve-out, the same results)
-    plans = [det.plan(*sets[i], priors, scale=scale, workspace=lanes[i][1], out=lanes[i][2], in_flight=2) for i in range(2)]
+    plans = [det.plan(*sets[i], priors, scale=scale, workspace=lanes[i][1], out=lanes[i][2]) for i in range(2)]
     torch.cuda.synchronize()
     for rep in range(3):
         out = [plans[i].launch(lanes[i][0]) for i in range(2)]
