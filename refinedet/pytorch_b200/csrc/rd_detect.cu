@@ -256,7 +256,10 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
                const float4* __restrict__ odm_loc, const float* __restrict__ odm_conf,
                const float4* __restrict__ priors, int P, int C, int S, int Pn, ArmGate gate,
                float v0, float v1, float* __restrict__ nsc, uint32_t* header, GraphOut GO) {
-    __shared__ float s_tile[kMaxClasses][kTileRows + 1];               // [class][node of the tile], padded
+    // [class][node of the tile], padded; C rows of dynamic shared memory (21 KB at C = 81, not the 33 KB of
+    // kMaxClasses rows: the CTAs of the other kernels of the batches in flight share the SM with this one)
+    extern __shared__ __align__(16) float s_tile[];
+    constexpr int kTileStride = kTileRows + 1;
     __shared__ unsigned short s_flat[kSliceAnchors];                   // passing anchors of the slice, anchor order
     __shared__ int s_wpass[kCollectThreads / 32];
     __shared__ int s_before[kCollectThreads / 32];
@@ -417,7 +420,7 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
 #pragma unroll
                 for (int sgm = 0; sgm < 4; ++sgm) {
                     const int c = sgm * 32 + lane;
-                    if (sgm < nseg && c < C) s_tile[c][rl0 + k] = v[k][sgm];
+                    if (sgm < nseg && c < C) s_tile[c * kTileStride + rl0 + k] = v[k][sgm];
                 }
             }
         }
@@ -425,7 +428,7 @@ collect_kernel(const float4* __restrict__ arm_loc, const float2* __restrict__ ar
         // class 0 = background, never evaluated (eval_refinedet_coco.py:213)
         for (int task = 2 + wib; task < 2 * C; task += kCollectThreads / 32) {
             const int c = task >> 1, r = (task & 1) * 32 + lane;
-            if (r < rows_here) nsc_b[c * Pn + t0 + r] = s_tile[c][r];
+            if (r < rows_here) nsc_b[c * Pn + t0 + r] = s_tile[c * kTileStride + r];
         }
         __syncthreads();
     }
@@ -1632,7 +1635,7 @@ static int detect_fused_impl(const float* arm_loc, const float* arm_conf, const 
     {
         auto kern = (nms_flags & RD_INPUT_LOGITS) ? (lines ? collect_kernel<true, true> : collect_kernel<true, false>)
                                                   : (lines ? collect_kernel<false, true> : collect_kernel<false, false>);
-        kern<<<dim3(ws.S, B), kCollectThreads, 0, st>>>(
+        kern<<<dim3(ws.S, B), kCollectThreads, (size_t)C * (kTileRows + 1) * sizeof(float), st>>>(
             (const float4*)arm_loc, (const float2*)arm_conf, (const float4*)odm_loc, odm_conf, (const float4*)priors,
             P, C, ws.S, ws.Pn, gate, v0, v1, ws.nsc, ws.header, GO);
     }
