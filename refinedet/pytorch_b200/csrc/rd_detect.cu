@@ -485,9 +485,10 @@ constexpr int kGraphPairCap = 2048;
 
 struct GraphSmem {
     float x1[kBlockNodes], y1[kBlockNodes], x2[kBlockNodes], y2[kBlockNodes];
-    // (no array of box areas: the area-ratio pre-test of the multi-block path recomputes them -- 4 KB less per CTA let
-    //  two CTAs of nms_small_kernel sit beside the four graph CTAs of an SM: 27.1 -> 25.9 us per batch with four batches in
-    //  flight, for + 2 - 5 % on images of more than 1024 nodes)
+    // (no array of box areas: the area-ratio pre-test of the multi-block path recomputes them.  With it a CTA took
+    //  49.7 + 1 KB and only THREE of the kernel's four CTAs per SM fit the 196 KB carve-out the chain runs best at;
+    //  at 45.6 + 1 KB four fit: 27.1 -> 25.8 us per batch with four batches in flight, 49 -> 45 us for one batch alone,
+    //  for + 2 - 5 % on images of more than 1024 nodes)
     uint32_t cr[kBlockNodes];
     uint32_t tab[4 * kCols * kBlockWS];
     uint32_t pairs[kGraphPairCap];
@@ -1559,11 +1560,11 @@ int rd_detect_workspace_reset(void* workspace, size_t workspace_bytes, void* str
 
 // Shared-memory carve-out of the stage's kernels, set once per device instead of left to the driver's per-kernel
 // choice (measured on B200, cfg 3 sparse; `RD_CARVEOUT="collect,graph,small,large"` in percent overrides it for
-// experiments).  With the driver's choice -- 228 KB for graph_kernel -- four batches in flight took 28.3 us per batch; at
-// 196 KB for graph_kernel and 164 KB for collect_kernel / nms_small_kernel<256,128> the SMs take the CTAs of the next
-// batch sooner: 27.1 us.  One batch alone went the other way (45 -> 49 us: at 196 KB the per-class CTAs of
-// nms_small_kernel, 10 KB each, found no room beside the four running graph CTAs of an SM, 4 x 46.6 KB, and their scan +
-// sort no longer overlapped the graph) until graph_kernel's footprint shrank to 42.5 KB per CTA: 25.9 us / 45.1 us.
+// experiments).  The carve-out is a state of the whole SM, so the choice of one kernel is also the L1 size of every CTA
+// of the other batches in flight that shares the SM with it.  With the driver's choice -- 228 KB for graph_kernel, 28 KB
+// of L1 left -- four batches in flight took 28.3 us per batch; with 196 KB for graph_kernel and 164 KB for
+// collect_kernel / nms_small_kernel<256,128>: 27.1 us, and 25.8 us once graph_kernel's footprint had shrunk to 46.6 KB
+// per CTA so that its four CTAs per SM fit the 196 KB (with 50.7 KB only three did, which cost one batch alone 4 us).
 static void set_stage_carveouts() {
     static bool s_done[kMaxDevices];
     int dev = 0;
