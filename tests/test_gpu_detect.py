@@ -343,6 +343,14 @@ def test_host_pipeline(rd, dma_rows, B, C):
         assert torch.equal(r, rows.cpu())
     c2, r2 = det.detect_host(hs[0], priors, scale)                   # serial form
     assert torch.equal(c2, got[0][1]) and torch.equal(r2, got[0][2])
+    # one lane, batches of growing and shrinking row counts through the same lane buffers
+    if dma_rows:
+        dense = [t.pin_memory() for t in gen.detect_inputs(990, B, P, C, 'sparse', arm_shift=-2.0)]
+        pipe1 = rd.DetectHostPipeline(det, priors, scale, B, lanes=1)
+        for h in (hs[0], dense, hs[1], dense, dense, hs[2]):
+            c, r = pipe1.result(pipe1.submit(h))
+            ref = det.detect(*[t.cuda() for t in h], priors, scale=scale)
+            assert torch.equal(c, ref.counts.cpu()) and torch.equal(r, ref.packed()[1].cpu())
 
 
 def test_forward_python_nms_vs_oracle(rd):
